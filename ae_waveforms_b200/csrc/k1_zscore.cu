@@ -1,0 +1,199 @@
+// k1_zscore.cu -- whole-record NaN-aware z-score statistics and apply (K1).
+//
+// Replaces, per record of a ragged batch, the reference's
+//     (data - np.nanmean(data)) / np.nanstd(data)
+// (data_load_preprocess/filters.py:5-12, called at data_extract_vitaldb.py:64).
+// mean and std are BIT-IDENTICAL to NumPy's: the sums follow NumPy's pairwise
+// tree (aew_pairwise.cuh), NaN -> 0 in the sums, divisor = count of non-NaN.
+//
+// Data layout: one flat float64 array holding all records back to back,
+// rec_off[n_rec+1] (int64) giving each record's range.  Work decomposition: a
+// 256-thread block owns 32 consecutive leaf slots of one record (8 lanes per
+// slot, 64-byte coalesced reads, up to 16 independent loads in flight per lane)
+// and folds them 5 tree levels into one node; a second tiny kernel folds the
+// nodes of each record to the root.  blk_start[n_rec+1] (int64, from
+// aew_zscore_plan) maps block -> record.
+// HBM traffic: 8 B/sample for the mean pass, 8 B/sample for the variance pass
+// (+ 16 B/sample for a materialised apply; the filter kernel fuses the apply
+// into its load instead).  Roofline: HBM.
+#include "aew_pairwise.cuh"
+
+namespace {
+
+struct LoadSum {   // pass 1: NaN -> 0, count the non-NaN
+  const double* x;
+  int cnt;
+  __device__ __forceinline__ double operator()(long long i, bool primary) {
+    const double v = __ldg(x + i);
+    const bool ok = !isnan(v);
+    if (primary && ok) ++cnt;
+    return ok ? v : 0.0;
+  }
+};
+struct LoadDev2 {  // pass 2: squared deviation from the mean, NaN -> 0
+  const double* x;
+  double mean;
+  int cnt;
+  __device__ __forceinline__ double operator()(long long i, bool) {
+    const double v = __ldg(x + i);
+    if (isnan(v)) return 0.0;
+    const double d = __dsub_rn(v, mean);
+    return __dmul_rn(d, d);
+  }
+};
+
+__device__ __forceinline__ long long find_record(const long long* __restrict__ start, long long n_rec,
+                                                 long long b) {
+  long long lo = 0, hi = n_rec;  // start[lo] <= b < start[hi]
+  while (hi - lo > 1) {
+    const long long mid = (lo + hi) >> 1;
+    if (start[mid] <= b) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// PASS 1: nodes <- sums of x (NaN->0), cnt[r] += non-NaN count.
+// PASS 2: nodes <- sums of (x-mean[r])^2.
+template <int PASS>
+__global__ void __launch_bounds__(256) k1_leaf(const double* __restrict__ x, const long long* __restrict__ rec_off,
+                                               const long long* __restrict__ blk_start, long long n_rec,
+                                               const double* __restrict__ mean, double* __restrict__ nodes,
+                                               unsigned long long* __restrict__ cnt) {
+  __shared__ double s_vals[32];
+  __shared__ unsigned char s_valid[32];
+  __shared__ long long s_rec;
+  __shared__ int s_cnt;
+  const long long b = blockIdx.x;
+  if (threadIdx.x == 0) { s_rec = find_record(blk_start, n_rec, b); s_cnt = 0; }
+  __syncthreads();
+  const long long r = s_rec;
+  const long long base = rec_off[r], n = rec_off[r + 1] - base;
+  const int depth = pw_depth(n);
+  const int sub = depth < 5 ? depth : 5;
+  const unsigned j = (unsigned)(b - blk_start[r]);
+  const int group = threadIdx.x >> 3, g = threadIdx.x & 7;
+  long long off = 0, size = 0;
+  if (group < (1 << sub)) pw_node(n, depth, (j << sub) + (unsigned)group, off, size);
+  double v;
+  int mycnt = 0;
+  if (PASS == 1) {
+    LoadSum f{x + base, 0};
+    v = pw_leaf_sum8(f, off, (int)size, g);
+    mycnt = f.cnt;
+  } else {
+    LoadDev2 f{x + base, mean[r], 0};
+    v = pw_leaf_sum8(f, off, (int)size, g);
+  }
+  if (g == 0) { s_vals[group] = v; s_valid[group] = size > 0; }
+  if (PASS == 1) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mycnt += __shfl_xor_sync(AEW_FULL, mycnt, o);
+    if ((threadIdx.x & 31) == 0 && mycnt) atomicAdd(&s_cnt, mycnt);
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) pw_warp_combine(s_vals, s_valid, sub, threadIdx.x);
+  if (threadIdx.x == 0) {
+    nodes[b] = s_vals[0];
+    if (PASS == 1 && s_cnt) atomicAdd(cnt + r, (unsigned long long)s_cnt);
+  }
+}
+
+// Fold the nodes of each record (2^(depth-5) of them) to the root.
+// PASS 1 writes mean[r] = sum / cnt; PASS 2 writes sd[r] = sqrt(sum / cnt).
+template <int PASS>
+__global__ void __launch_bounds__(256) k1_combine(const long long* __restrict__ rec_off,
+                                                  const long long* __restrict__ blk_start,
+                                                  double* __restrict__ nodes, double* __restrict__ nodes2,
+                                                  const unsigned long long* __restrict__ cnt,
+                                                  double* __restrict__ out) {
+  const long long r = blockIdx.x;
+  const long long n = rec_off[r + 1] - rec_off[r];
+  const int depth = pw_depth(n);
+  const int dn = depth > 5 ? depth - 5 : 0;
+  double* src = nodes + blk_start[r];
+  double* dst = nodes2 + blk_start[r];
+  for (int lvl = dn - 1; lvl >= 0; --lvl) {
+    const int c = 1 << lvl;
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+      long long o, sa, sb;
+      pw_node(n, lvl + 1, 2u * i, o, sa);
+      pw_node(n, lvl + 1, 2u * i + 1u, o, sb);
+      const double a = src[2 * i], bb = src[2 * i + 1];
+      dst[i] = (sa > 0 && sb > 0) ? __dadd_rn(a, bb) : a;
+    }
+    __threadfence_block();
+    __syncthreads();
+    double* t = src; src = dst; dst = t;
+  }
+  if (threadIdx.x == 0) {
+    const double q = __ddiv_rn(src[0], (double)cnt[r]);
+    out[r] = PASS == 1 ? q : __dsqrt_rn(q);
+  }
+}
+
+__global__ void __launch_bounds__(256) k1_apply(const double* __restrict__ x, const long long* __restrict__ rec_off,
+                                                long long n_rec, const double* __restrict__ mean,
+                                                const double* __restrict__ sd, double* __restrict__ out,
+                                                long long total) {
+  const long long per_thread = 4;
+  long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * per_thread;
+  if (i >= total) return;
+  long long r = find_record(rec_off, n_rec, i);
+  for (int k = 0; k < per_thread && i < total; ++k, ++i) {
+    while (i >= rec_off[r + 1]) ++r;
+    out[i] = __ddiv_rn(__dsub_rn(x[i], mean[r]), sd[r]);
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- host side
+extern "C" long long aew_zscore_plan(const long long* h_rec_off, long long n_rec, long long* h_blk_start) {
+  long long acc = 0;
+  for (long long r = 0; r < n_rec; ++r) {
+    if (h_blk_start) h_blk_start[r] = acc;
+    const int d = pw_depth(h_rec_off[r + 1] - h_rec_off[r]);
+    acc += 1ll << (d > 5 ? d - 5 : 0);
+  }
+  if (h_blk_start) h_blk_start[n_rec] = acc;
+  return acc;  // number of leaf blocks == number of tree nodes
+}
+
+extern "C" size_t aew_zscore_workspace_bytes(long long n_rec, long long n_blocks) {
+  return (size_t)(2 * n_blocks) * sizeof(double) + (size_t)n_rec * sizeof(unsigned long long) + 64;
+}
+
+extern "C" int aew_zscore_stats_f64(const double* x, const long long* d_rec_off, const long long* d_blk_start,
+                                    long long n_rec, long long n_blocks, double* mean, double* sd,
+                                    long long* count, void* ws, size_t ws_bytes, void* stream) {
+  if (!x || !d_rec_off || !d_blk_start || !mean || !sd || !ws || n_rec < 0) return AEW_ERR_ARG;
+  if (n_rec == 0) return AEW_OK;
+  if (ws_bytes < aew_zscore_workspace_bytes(n_rec, n_blocks)) return AEW_ERR_WORKSPACE;
+  if (n_blocks > 0x7fffffffll) return AEW_ERR_UNSUPPORTED;
+  double* nodes = (double*)ws;
+  double* nodes2 = nodes + n_blocks;
+  unsigned long long* cnt = count ? (unsigned long long*)count : (unsigned long long*)(nodes2 + n_blocks);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(cnt, 0, (size_t)n_rec * sizeof(unsigned long long), st);
+  AEW_LAUNCH(k1_leaf<1>, (unsigned)n_blocks, 256, 0, st, x, d_rec_off, d_blk_start, n_rec, (const double*)nullptr,
+             nodes, cnt);
+  AEW_LAUNCH(k1_combine<1>, (unsigned)n_rec, 256, 0, st, d_rec_off, d_blk_start, nodes, nodes2,
+             (const unsigned long long*)cnt, mean);
+  AEW_LAUNCH(k1_leaf<2>, (unsigned)n_blocks, 256, 0, st, x, d_rec_off, d_blk_start, n_rec, (const double*)mean,
+             nodes, cnt);
+  AEW_LAUNCH(k1_combine<2>, (unsigned)n_rec, 256, 0, st, d_rec_off, d_blk_start, nodes, nodes2,
+             (const unsigned long long*)cnt, sd);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int aew_zscore_apply_f64(const double* x, const long long* d_rec_off, long long n_rec,
+                                    const double* mean, const double* sd, double* out, long long total,
+                                    void* stream) {
+  if (!x || !d_rec_off || !mean || !sd || !out || n_rec < 0 || total < 0) return AEW_ERR_ARG;
+  if (total == 0) return AEW_OK;
+  const long long threads = (total + 3) / 4;
+  const long long blocks = (threads + 255) / 256;
+  if (blocks > 0x7fffffffll) return AEW_ERR_UNSUPPORTED;
+  AEW_LAUNCH(k1_apply, (unsigned)blocks, 256, 0, (cudaStream_t)stream, x, d_rec_off, n_rec, mean, sd, out, total);
+  return (int)cudaGetLastError();
+}

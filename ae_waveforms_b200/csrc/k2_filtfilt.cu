@@ -1,0 +1,549 @@
+// k2_filtfilt.cu -- zero-phase IIR filtering of NaN-delimited segments (K2).
+//
+// Replaces data_load_preprocess/filters.py:15-55 (`butterworth`): the output is
+// NaN where the input is NaN; every maximal non-NaN segment longer than
+// padlen = 3*max(len(a),len(b)) gets scipy.signal.filtfilt(b, a, seg)
+// (odd extension by padlen, zi-scaled initial state, forward DF2T pass,
+// reversal, second pass, reversal, trim -- SURVEY.md appendix B.1); shorter
+// segments are copied through (filters.py:50-51).  The optional (mean, sd)
+// arguments fuse the whole-record z-score of data_extract_vitaldb.py:64 into the
+// load, so the z-scored record is never materialised.
+//
+// Kernels
+//   k2_seg_find   one block per record; finds the segments with a block-wide
+//                 "latest start" max-scan, appends (start, length, record,
+//                 first tile) to the segment table, fills the tile->segment map
+//                 and writes NaN to the output at NaN inputs.  Records whose
+//                 non-NaN count equals their length (known from K1) skip the scan.
+//   k2_pass<REV>  persistent blocks pull 8448-sample tiles off an atomic counter.
+//                 A tile is staged in shared memory; thread t runs the DF2T
+//                 recursion over its own 33-sample chunk from a ZERO state
+//                 (stride 33 doubles = conflict-free).  The recursion is carried in
+//                 MODAL form (two complex first-order sections, k2_tables.cpp) so
+//                 that the state transition is diagonal: the chunk end states are
+//                 combined by a warp-shuffle Kogge-Stone scan that costs two
+//                 complex multiplications per step, warps are chained, and the
+//                 state entering the tile comes from a bounded look-back over the
+//                 published end states of the previous tiles (|p|^8448 ~ 2e-18 for
+//                 the 1 Hz high-pass, so one predecessor suffices; the depth is
+//                 computed per filter on the host).  Outputs are then corrected in
+//                 place with y[j] += G[j] . s (zero-input response) and stored
+//                 coalesced.
+//                 REV=false is the forward pass (x -> tmp), REV=true the backward
+//                 pass over the reversed forward output (tmp -> out).
+//   k2_exact      one thread per segment, the literal sequential DF2T order
+//                 without FMA: bit-identical to SciPy, used by the parity suite
+//                 (mode 1) to show the rest of the chain is bit-exact end to end.
+//
+// Algorithmic HBM bytes: 16 B/sample per pass, 32 B/sample per filtfilt
+// (SURVEY.md section 8d).  Roofline: HBM; FP64 work is ~17 FMA/sample/pass.
+#include "aew_rt.h"
+#include "k2_layout.h"
+
+namespace {
+
+// ---- workspace header (int64 slots)
+enum { H_SEG_COUNT = 0, H_TILE_TOTAL = 1, H_WORK_FWD = 2, H_WORK_BWD = 3, H_STATUS = 4, H_WORK_EXACT = 5, H_SLOTS = 8 };
+
+struct K2Ws {
+  long long* hdr;       // [H_SLOTS]
+  long long* segs;      // [max_seg][4] : g0, n, rec, tile_base
+  double* vext;         // [max_seg][16] forward outputs over the right extension
+  int* tile_seg;        // [max_tiles]
+  int* flags_fwd;       // [max_tiles]
+  int* flags_bwd;       // [max_tiles]
+  double* tstate;       // [max_tiles][4]
+  long long max_seg, max_tiles;
+};
+
+__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+inline size_t k2_ws_layout(void* base, long long max_seg, long long max_tiles, K2Ws* w) {
+  size_t o = 0;
+  unsigned char* p = (unsigned char*)base;
+  auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 128); return p ? p + at : (unsigned char*)nullptr; };
+  K2Ws t;
+  t.hdr = (long long*)take(H_SLOTS * sizeof(long long));
+  t.segs = (long long*)take((size_t)max_seg * 4 * sizeof(long long));
+  t.vext = (double*)take((size_t)max_seg * 16 * sizeof(double));
+  t.tile_seg = (int*)take((size_t)max_tiles * sizeof(int));
+  t.flags_fwd = (int*)take((size_t)max_tiles * sizeof(int));
+  t.flags_bwd = (int*)take((size_t)max_tiles * sizeof(int));
+  t.tstate = (double*)take((size_t)max_tiles * 4 * sizeof(double));
+  t.max_seg = max_seg;
+  t.max_tiles = max_tiles;
+  if (w) *w = t;
+  return o;
+}
+
+// ------------------------------------------------------------ segment discovery
+#define SEG_THREADS 256
+#define SEG_ITEMS 8
+
+__global__ void __launch_bounds__(SEG_THREADS) k2_seg_find(const double* __restrict__ x,
+                                                           const long long* __restrict__ rec_off,
+                                                           const long long* __restrict__ nonnan_count,
+                                                           double* __restrict__ nan_fill, K2Ws ws) {
+  __shared__ long long s_warp[SEG_THREADS / 32];
+  __shared__ long long s_carry;
+  const long long r = blockIdx.x;
+  const long long base = rec_off[r], n = rec_off[r + 1] - base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+
+  auto append = [&](long long start, long long len) {
+    const long long idx = (long long)atomicAdd((unsigned long long*)(ws.hdr + H_SEG_COUNT), 1ull);
+    if (idx >= ws.max_seg) { atomicOr((int*)(ws.hdr + H_STATUS), AEW_DEV_SEG_OVERFLOW); return; }
+    const long long nt = (len + K2_T - 1) / K2_T;
+    const long long tb = (long long)atomicAdd((unsigned long long*)(ws.hdr + H_TILE_TOTAL), (unsigned long long)nt);
+    long long* s = ws.segs + 4 * idx;
+    s[0] = base + start; s[1] = len; s[2] = r;
+    if (tb + nt > ws.max_tiles) {
+      atomicOr((int*)(ws.hdr + H_STATUS), AEW_DEV_TILE_OVERFLOW);
+      s[3] = -1;
+      return;
+    }
+    s[3] = tb;
+    for (long long t = 0; t < nt; ++t) ws.tile_seg[tb + t] = (int)idx;
+  };
+
+  if (n <= 0) return;
+  if (nonnan_count && nonnan_count[r] == n) {      // no NaN in this record: one segment, no scan
+    if (tid == 0) append(0, n);
+    return;
+  }
+  if (tid == 0) s_carry = -1;
+  __syncthreads();
+  const double* xr = x + base;
+  for (long long blk0 = 0; blk0 < n; blk0 += (long long)SEG_THREADS * SEG_ITEMS) {
+    const long long p0 = blk0 + (long long)tid * SEG_ITEMS;
+    // local walk: last segment start inside my items (or -1)
+    bool prev = (p0 > 0 && p0 - 1 < n) ? !isnan(xr[p0 - 1]) : false;
+    bool ok[SEG_ITEMS];
+    long long my_last = -1;
+#pragma unroll
+    for (int k = 0; k < SEG_ITEMS; ++k) {
+      const long long p = p0 + k;
+      ok[k] = (p < n) ? !isnan(xr[p]) : false;
+      if (p < n && !ok[k] && nan_fill) nan_fill[base + p] = qnan;
+      const bool pv = k == 0 ? prev : ok[k - 1];
+      if (ok[k] && !pv) my_last = p;
+    }
+    // exclusive max-scan of my_last over the block
+    long long incl = my_last;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const long long o = __shfl_up_sync(AEW_FULL, incl, d);
+      if (lane >= d && o > incl) incl = o;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    long long before = s_carry;                     // latest start in earlier iterations / warps
+    for (int w = 0; w < warp; ++w) if (s_warp[w] > before) before = s_warp[w];
+    long long excl = __shfl_up_sync(AEW_FULL, incl, 1);
+    if (lane == 0) excl = -1;
+    if (before > excl) excl = before;
+    // emit the segments that END inside my items
+    long long cur = excl;
+#pragma unroll
+    for (int k = 0; k < SEG_ITEMS; ++k) {
+      const long long p = p0 + k;
+      if (p >= n) break;
+      const bool pv = k == 0 ? prev : ok[k - 1];
+      if (ok[k] && !pv) cur = p;
+      const bool nx = (p + 1 < n) ? (k + 1 < SEG_ITEMS ? ok[k + 1] : !isnan(xr[p + 1])) : false;
+      if (ok[k] && !nx) append(cur, p + 1 - cur);
+    }
+    __syncthreads();
+    if (tid == SEG_THREADS - 1) {
+      long long c = s_carry;
+      for (int w = 0; w < SEG_THREADS / 32; ++w) if (s_warp[w] > c) c = s_warp[w];
+      s_carry = c;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------ modal-form helpers
+// s = (u1.re, u1.im, u2.re, u2.im);  u' = p u + x;  y = d x + GC . s   (k2_layout.h)
+struct Modal { double d, p1r, p1i, p2r, p2i, g0, g1, g2, g3; };
+
+__device__ __forceinline__ Modal load_modal(const double* tab) {
+  Modal c;
+  c.d = tab[K2_TAB_D];
+  c.p1r = tab[K2_TAB_P + 0]; c.p1i = tab[K2_TAB_P + 1]; c.p2r = tab[K2_TAB_P + 2]; c.p2i = tab[K2_TAB_P + 3];
+  c.g0 = tab[K2_TAB_GC + 0]; c.g1 = tab[K2_TAB_GC + 1]; c.g2 = tab[K2_TAB_GC + 2]; c.g3 = tab[K2_TAB_GC + 3];
+  return c;
+}
+
+// one sample (fast path: FMA allowed, results within 1e-6 relative of SciPy's)
+__device__ __forceinline__ double modal_step(const Modal& c, double x, double s[4]) {
+  const double y = fma(c.g3, s[3], fma(c.g2, s[2], fma(c.g1, s[1], fma(c.g0, s[0], c.d * x))));
+  const double n0 = fma(c.p1r, s[0], fma(-c.p1i, s[1], x));
+  const double n1 = fma(c.p1r, s[1], c.p1i * s[0]);
+  const double n2 = fma(c.p2r, s[2], fma(-c.p2i, s[3], x));
+  const double n3 = fma(c.p2r, s[3], c.p2i * s[2]);
+  s[0] = n0; s[1] = n1; s[2] = n2; s[3] = n3;
+  return y;
+}
+
+// acc += P (.) v   (two complex multiplications; P = (p1.re, p1.im, p2.re, p2.im))
+__device__ __forceinline__ void cmul_acc(const double* __restrict__ P, const double v[4], double acc[4]) {
+  acc[0] = fma(P[0], v[0], fma(-P[1], v[1], acc[0]));
+  acc[1] = fma(P[0], v[1], fma(P[1], v[0], acc[1]));
+  acc[2] = fma(P[2], v[2], fma(-P[3], v[3], acc[2]));
+  acc[3] = fma(P[2], v[3], fma(P[3], v[2], acc[3]));
+}
+
+// SciPy's initial DF2T state zi*scale, mapped to modal coordinates
+__device__ __forceinline__ void modal_initial(const double* tab, double scale, double s[4]) {
+  double z[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) z[i] = tab[K2_TAB_ZI + i] * scale;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double* row = tab + K2_TAB_PZ + 4 * i;
+    s[i] = fma(row[3], z[3], fma(row[2], z[2], fma(row[1], z[1], row[0] * z[0])));
+  }
+}
+
+__device__ __forceinline__ double zs(double v, bool on, double mean, double sd) {
+  return on ? __ddiv_rn(__dsub_rn(v, mean), sd) : v;
+}
+
+// ------------------------------------------------------------ tiled pass
+struct PassArgs {
+  const double* src;      // forward: x (raw or previous stage); backward: tmp (forward output)
+  const double* mean;     // optional per-record z-score (forward only)
+  const double* sd;
+  double* dst;            // forward: tmp; backward: out
+  double* passthrough;    // forward: out (short segments are copied here)
+  const double* tab;      // device coefficient table (k2_layout.h)
+  K2Ws ws;
+};
+
+template <bool REV>
+__global__ void __launch_bounds__(K2_NT, 3) k2_pass(PassArgs a) {
+  AEW_DYN_SMEM(smem_raw);
+  double* sm = (double*)smem_raw;                     // [K2_T] tile, then tables
+  double* s_tab = sm + K2_T;                          // [K2_TAB_LEN]
+  double* s_W = s_tab + K2_TAB_LEN;                   // [K2_NW][4] warp totals
+  double* s_S = s_W + 4 * K2_NW;                      // [K2_NW][4] state entering each warp
+  double* s_in = s_S + 4 * K2_NW;                     // [4] state entering the tile (tile 0 pre-step)
+  __shared__ long long s_tile;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < K2_TAB_LEN; i += K2_NT) s_tab[i] = a.tab[i];
+  __syncthreads();
+  const Modal cf = load_modal(s_tab);
+  const int pad = (int)s_tab[K2_TAB_PAD];
+  const int lookback = (int)s_tab[K2_TAB_LOOKBACK];
+  long long* work = a.ws.hdr + (REV ? H_WORK_BWD : H_WORK_FWD);
+  int* flags = REV ? a.ws.flags_bwd : a.ws.flags_fwd;
+  long long n_tiles = a.ws.hdr[H_TILE_TOTAL];
+  if (n_tiles > a.ws.max_tiles) n_tiles = a.ws.max_tiles;
+
+  for (;;) {
+    if (tid == 0) s_tile = (long long)atomicAdd((unsigned long long*)work, 1ull);
+    __syncthreads();
+    const long long tile = s_tile;
+    if (tile >= n_tiles) break;
+    const int seg = a.ws.tile_seg[tile];
+    const long long* sg = a.ws.segs + 4ll * seg;
+    const long long g0 = sg[0], n = sg[1], rec = sg[2], tb = sg[3];
+    const long long k = tile - tb;
+    const bool zon = (!REV) && a.mean != nullptr;
+    const double mean = zon ? a.mean[rec] : 0.0, sd = zon ? a.sd[rec] : 1.0;
+
+    if (n <= pad) {                                    // filters.py:50-51: too short, copy through
+      if (!REV)
+        for (long long i = tid; i < n; i += K2_NT) a.passthrough[g0 + i] = zs(a.src[g0 + i], zon, mean, sd);
+      __syncthreads();
+      continue;
+    }
+    const long long t0 = k * K2_T;                     // first logical position of the tile
+    const long long remain = n - t0;
+    const int cnt = remain < K2_T ? (int)remain : K2_T;
+
+    // ---- stage the tile (zero padded); logical position p <-> sample g0+p (fwd) or g0+n-1-p (bwd)
+    for (int j = tid; j < K2_T; j += K2_NT) {
+      double v = 0.0;
+      if (j < cnt) {
+        const long long p = t0 + j;
+        v = REV ? a.src[g0 + n - 1 - p] : zs(a.src[g0 + p], zon, mean, sd);
+      }
+      sm[j] = v;
+    }
+    __syncthreads();
+
+    // ---- tile 0: run the odd extension (padlen samples) from SciPy's zi-scaled state
+    if (k == 0 && tid == 0) {
+      double z[4];
+      if (!REV) {
+        const double x0 = sm[0];
+        modal_initial(s_tab, 2.0 * x0 - sm[pad], z);
+        for (int e = 0; e < pad; ++e) modal_step(cf, 2.0 * x0 - sm[pad - e], z);
+      } else {
+        const double* ve = a.ws.vext + 16ll * seg;     // forward outputs over the right extension
+        modal_initial(s_tab, ve[pad - 1], z);
+        for (int e = 0; e < pad; ++e) modal_step(cf, ve[pad - 1 - e], z);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s_in[i] = z[i];
+    }
+
+    // ---- phase 1: zero-state recursion over my chunk, outputs stored in place
+    double* mine = sm + tid * K2_C;
+    double E[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 3
+    for (int j = 0; j < K2_C; ++j) mine[j] = modal_step(cf, mine[j], E);
+
+    // ---- phase 2a: warp scan of chunk end states (Kogge-Stone with p^(C*2^k))
+#pragma unroll
+    for (int kk = 0; kk < 5; ++kk) {
+      const int d = 1 << kk;
+      double o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = __shfl_up_sync(AEW_FULL, E[i], d);
+      if (lane >= d) cmul_acc(s_tab + K2_TAB_PK + 4 * kk, o, E);
+    }
+    if (lane == 31) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s_W[4 * warp + i] = E[i];
+    }
+    __syncthreads();
+
+    // ---- phase 2b (thread 0): publish the tile's end state, look back, chain the warps
+    if (tid == 0) {
+      const double* PW = s_tab + K2_TAB_PWARP;
+      double S[4] = {0.0, 0.0, 0.0, 0.0};
+      if (k == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) S[i] = s_in[i];
+      }
+      // end state of the tile given S (tile 0: inclusive; others: zero-state aggregate)
+      double Z[4] = {S[0], S[1], S[2], S[3]};
+      for (int w = 0; w < K2_NW; ++w) {
+        double t[4] = {s_W[4 * w], s_W[4 * w + 1], s_W[4 * w + 2], s_W[4 * w + 3]};
+        cmul_acc(PW, Z, t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) Z[i] = t[i];
+      }
+      double* pub = a.ws.tstate + 4 * tile;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pub[i] = Z[i];
+      __threadfence();
+      atomicExch(flags + tile, 1);
+      if (k > 0) {
+        // S = sum_j (p^T)^j Q[tile-1-j], j < min(lookback, k)
+        const double* PT = s_tab + K2_TAB_PTILE;
+        double Wm[4] = {1.0, 0.0, 1.0, 0.0};
+        const long long depth = k < lookback ? k : lookback;
+        for (long long j = 0; j < depth; ++j) {
+          const long long pred = tile - 1 - j;
+          volatile int* f = flags + pred;
+          unsigned spins = 0;
+          while (*f == 0) {
+            __nanosleep(64);
+            if (++spins > (1u << 24)) { atomicOr((int*)(a.ws.hdr + H_STATUS), AEW_DEV_LOOKBACK_TIMEOUT); break; }
+          }
+          __threadfence();
+          const volatile double* qv = a.ws.tstate + 4 * pred;
+          const double Q[4] = {qv[0], qv[1], qv[2], qv[3]};
+          cmul_acc(Wm, Q, S);
+          if (j + 1 < depth) {                        // Wm <- Wm * p^T
+            const double w0 = Wm[0] * PT[0] - Wm[1] * PT[1], w1 = Wm[0] * PT[1] + Wm[1] * PT[0];
+            const double w2 = Wm[2] * PT[2] - Wm[3] * PT[3], w3 = Wm[2] * PT[3] + Wm[3] * PT[2];
+            Wm[0] = w0; Wm[1] = w1; Wm[2] = w2; Wm[3] = w3;
+          }
+        }
+      }
+      // state entering each warp
+      for (int w = 0; w < K2_NW; ++w) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s_S[4 * w + i] = S[i];
+        double t[4] = {s_W[4 * w], s_W[4 * w + 1], s_W[4 * w + 2], s_W[4 * w + 3]};
+        cmul_acc(PW, S, t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) S[i] = t[i];
+      }
+    }
+    __syncthreads();
+
+    // ---- phase 2c: state entering my chunk = p^(C*lane) S_warp + end state of the lane before me
+    double s[4];
+    {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s[i] = __shfl_up_sync(AEW_FULL, E[i], 1);
+      if (lane == 0) { s[0] = s[1] = s[2] = s[3] = 0.0; }
+      const double Sw[4] = {s_S[4 * warp], s_S[4 * warp + 1], s_S[4 * warp + 2], s_S[4 * warp + 3]};
+      cmul_acc(s_tab + K2_TAB_PLANE + 4 * lane, Sw, s);
+    }
+
+    // ---- forward pass, last tile: state at the end of the segment -> right extension outputs
+    if (!REV && remain <= K2_T) {
+      const int tl = (cnt - 1) / K2_C;                 // thread holding the last valid sample
+      if (tid == tl) {
+        const int c = cnt - tl * K2_C;                 // valid samples in its chunk, 1..C
+        double z[4] = {s[0], s[1], s[2], s[3]};
+        const double* xs = a.src + g0 + t0 + (long long)tl * K2_C;
+        for (int j = 0; j < c; ++j) modal_step(cf, zs(xs[j], zon, mean, sd), z);
+        const double* xe = a.src + g0 + n - 1;         // last sample of the segment
+        const double xl = zs(xe[0], zon, mean, sd);
+        double* ve = a.ws.vext + 16ll * seg;
+        for (int m = 0; m < pad; ++m) ve[m] = modal_step(cf, 2.0 * xl - zs(xe[-1 - m], zon, mean, sd), z);
+      }
+    }
+
+    // ---- phase 3: add the zero-input response of the entering state
+    {
+      const double* G = s_tab + K2_TAB_G;
+#pragma unroll 3
+      for (int j = 0; j < K2_C; ++j)
+        mine[j] += fma(G[4 * j + 3], s[3], fma(G[4 * j + 2], s[2], fma(G[4 * j + 1], s[1], G[4 * j] * s[0])));
+    }
+    __syncthreads();
+
+    // ---- store
+    for (int j = tid; j < cnt; j += K2_NT) {
+      const long long p = t0 + j;
+      a.dst[REV ? (g0 + n - 1 - p) : (g0 + p)] = sm[j];
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------ exact sequential mode
+// scipy's evaluation order, separate multiply and add, runtime order.
+__device__ __forceinline__ double df2t_step_exact(const double* b, const double* a, int ord, double x, double* z) {
+  const double y = __dadd_rn(z[0], __dmul_rn(b[0], x));
+  for (int k = 0; k < ord - 1; ++k)
+    z[k] = __dsub_rn(__dadd_rn(z[k + 1], __dmul_rn(x, b[k + 1])), __dmul_rn(y, a[k + 1]));
+  z[ord - 1] = __dsub_rn(__dmul_rn(x, b[ord]), __dmul_rn(y, a[ord]));
+  return y;
+}
+
+__global__ void __launch_bounds__(32) k2_exact(PassArgs a) {
+  const long long n_seg = a.ws.hdr[H_SEG_COUNT] < a.ws.max_seg ? a.ws.hdr[H_SEG_COUNT] : a.ws.max_seg;
+  const long long seg = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (seg >= n_seg) return;
+  const long long* sg = a.ws.segs + 4 * seg;
+  const long long g0 = sg[0], n = sg[1], rec = sg[2];
+  const bool zon = a.mean != nullptr;
+  const double mean = zon ? a.mean[rec] : 0.0, sd = zon ? a.sd[rec] : 1.0;
+  const int ord = (int)a.tab[K2_TAB_ORDER], pad = (int)a.tab[K2_TAB_PAD];
+  double b[5], ac[5], zi[4], z[4];
+  for (int i = 0; i < 5; ++i) { b[i] = a.tab[K2_TAB_B + i]; ac[i] = a.tab[K2_TAB_A + i]; }
+  for (int i = 0; i < 4; ++i) zi[i] = a.tab[K2_TAB_ZI + i];
+  const double* xs = a.src + g0;
+  double* out = a.passthrough + g0;
+  double* tmp = a.dst + g0;
+  if (n <= pad) {
+    for (long long i = 0; i < n; ++i) out[i] = zs(xs[i], zon, mean, sd);
+    return;
+  }
+  double ve[K2_MAXPAD];
+  const double x0 = zs(xs[0], zon, mean, sd), xl = zs(xs[n - 1], zon, mean, sd);
+  const double e0 = __dsub_rn(__dmul_rn(2.0, x0), zs(xs[pad], zon, mean, sd));
+  for (int i = 0; i < ord; ++i) z[i] = __dmul_rn(zi[i], e0);
+  for (int e = 0; e < pad; ++e)
+    df2t_step_exact(b, ac, ord, __dsub_rn(__dmul_rn(2.0, x0), zs(xs[pad - e], zon, mean, sd)), z);
+  for (long long i = 0; i < n; ++i) tmp[i] = df2t_step_exact(b, ac, ord, zs(xs[i], zon, mean, sd), z);
+  for (int m = 0; m < pad; ++m)
+    ve[m] = df2t_step_exact(b, ac, ord, __dsub_rn(__dmul_rn(2.0, xl), zs(xs[n - 2 - m], zon, mean, sd)), z);
+  for (int i = 0; i < ord; ++i) z[i] = __dmul_rn(zi[i], ve[pad - 1]);
+  for (int e = 0; e < pad; ++e) df2t_step_exact(b, ac, ord, ve[pad - 1 - e], z);
+  for (long long i = n - 1; i >= 0; --i) out[i] = df2t_step_exact(b, ac, ord, tmp[i], z);
+}
+
+int g_sm_count = 0;
+inline int sm_count() {
+#ifdef AEW_EMUL
+  return 2;
+#else
+  if (!g_sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+  }
+  return g_sm_count;
+#endif
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ C ABI
+extern "C" long long aew_filt_max_tiles(long long n_rec, long long total_samples, long long max_seg) {
+  return total_samples / K2_T + n_rec + max_seg + 1;
+}
+
+extern "C" size_t aew_filt_workspace_bytes(long long n_rec, long long total_samples, long long max_seg) {
+  return k2_ws_layout(nullptr, max_seg, aew_filt_max_tiles(n_rec, total_samples, max_seg), nullptr) + 128;
+}
+
+// Finds the non-NaN segments of every record and (if nan_fill != NULL) writes NaN
+// to nan_fill at every NaN input position.  nonnan_count (device, optional, from
+// aew_zscore_stats_f64) lets NaN-free records skip the scan.
+extern "C" int aew_segments_find_f64(const double* x, const long long* d_rec_off, long long n_rec,
+                                     long long total_samples, const long long* d_nonnan_count, double* nan_fill,
+                                     void* ws, size_t ws_bytes, long long max_seg, void* stream) {
+  if (!x || !d_rec_off || !ws || n_rec < 0 || max_seg < 1) return AEW_ERR_ARG;
+  if (ws_bytes < aew_filt_workspace_bytes(n_rec, total_samples, max_seg)) return AEW_ERR_WORKSPACE;
+  if (n_rec > 0x7fffffffll || max_seg > 0x7fffffffll) return AEW_ERR_UNSUPPORTED;
+  K2Ws w;
+  k2_ws_layout((void*)align_up((size_t)ws, 128), max_seg, aew_filt_max_tiles(n_rec, total_samples, max_seg), &w);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(w.hdr, 0, H_SLOTS * sizeof(long long), st);
+  if (n_rec == 0) return AEW_OK;
+  AEW_LAUNCH(k2_seg_find, (unsigned)n_rec, SEG_THREADS, 0, st, x, d_rec_off, d_nonnan_count, nan_fill, w);
+  return (int)cudaGetLastError();
+}
+
+// filtfilt of every segment found by aew_segments_find_f64 (same ws).
+//   src  input samples (flat), optionally z-scored on load with mean/sd per record
+//   out  filtered output (may alias src); tmp: scratch of the same length
+//   mode 0 = tiled scan (fast), 1 = exact sequential SciPy order (parity suite)
+extern "C" int aew_filtfilt_f64(const double* src, const double* mean, const double* sd, double* out, double* tmp,
+                                const double* d_tab, long long n_rec, long long total_samples, void* ws,
+                                size_t ws_bytes, long long max_seg, int mode, void* stream) {
+  if (!src || !out || !tmp || !d_tab || !ws || (mean && !sd)) return AEW_ERR_ARG;
+  if (ws_bytes < aew_filt_workspace_bytes(n_rec, total_samples, max_seg)) return AEW_ERR_WORKSPACE;
+  K2Ws w;
+  k2_ws_layout((void*)align_up((size_t)ws, 128), max_seg, aew_filt_max_tiles(n_rec, total_samples, max_seg), &w);
+  cudaStream_t st = (cudaStream_t)stream;
+  PassArgs a;
+  a.src = src; a.mean = mean; a.sd = sd; a.dst = tmp; a.passthrough = out; a.tab = d_tab; a.ws = w;
+  if (mode == 1) {
+    const long long blocks = (max_seg + 31) / 32;
+    AEW_LAUNCH(k2_exact, (unsigned)blocks, 32, 0, st, a);
+    return (int)cudaGetLastError();
+  }
+  if (mode != 0) return AEW_ERR_ARG;
+  const size_t smem = (size_t)(K2_T + K2_TAB_LEN + 8 * K2_NW + 4) * sizeof(double);
+  static bool attr_done = false;
+  if (!attr_done) {
+    AEW_SET_MAX_SMEM(k2_pass<false>, smem);
+    AEW_SET_MAX_SMEM(k2_pass<true>, smem);
+    attr_done = true;
+  }
+  cudaMemsetAsync(w.hdr + H_WORK_FWD, 0, 2 * sizeof(long long), st);
+  cudaMemsetAsync(w.flags_fwd, 0, (size_t)w.max_tiles * sizeof(int), st);
+  cudaMemsetAsync(w.flags_bwd, 0, (size_t)w.max_tiles * sizeof(int), st);
+  const long long cap = (long long)sm_count() * 3;
+  const long long grid = w.max_tiles < cap ? w.max_tiles : cap;
+  AEW_LAUNCH(k2_pass<false>, (unsigned)grid, K2_NT, smem, st, a);
+  PassArgs r = a;
+  r.src = tmp; r.mean = nullptr; r.sd = nullptr; r.dst = out;
+  AEW_LAUNCH(k2_pass<true>, (unsigned)grid, K2_NT, smem, st, r);
+  return (int)cudaGetLastError();
+}
+
+// Reads back nothing: copies the 8-slot header (segment count, tile count, ...,
+// status bits) into a caller-provided DEVICE buffer so the host can fetch it with
+// its own (stream-ordered) copy.
+extern "C" int aew_filt_header(void* ws, long long** d_header_out) {
+  if (!ws || !d_header_out) return AEW_ERR_ARG;
+  *d_header_out = (long long*)align_up((size_t)ws, 128);
+  return AEW_OK;
+}
