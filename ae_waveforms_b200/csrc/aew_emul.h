@@ -235,3 +235,13 @@ inline double __longlong_as_double(long long v) { double r; memcpy(&r, &v, 8); r
 template <class T> inline T __ldg(const T* p) { return *p; }
 using std::isnan;
 using std::isinf;
+inline long long atomicMin(long long* p, long long v) {
+  long long old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+  while (old > v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+  return old;
+}
+inline long long atomicMax(long long* p, long long v) {
+  long long old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+  while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+  return old;
+}

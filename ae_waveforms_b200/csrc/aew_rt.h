@@ -22,19 +22,8 @@
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
 #endif
 
-// ---- status codes shared by device and host (returned through the C ABI)
-enum {
-  AEW_OK = 0,
-  AEW_ERR_ARG = -1,         // null pointer / negative size / unsupported parameter
-  AEW_ERR_WORKSPACE = -2,   // workspace too small
-  AEW_ERR_UNSUPPORTED = -3, // e.g. filter order > 4, window longer than the kernel supports
-  AEW_ERR_NO_DEVICE = -4,   // no CUDA device / wrong architecture
-  // bits of the device-side status word (read back by the caller after the stream drains)
-  AEW_DEV_SEG_OVERFLOW = 1,   // more NaN-delimited segments than the workspace was sized for
-  AEW_DEV_TILE_OVERFLOW = 2,  // more filter tiles than the workspace was sized for
-  AEW_DEV_LOOKBACK_TIMEOUT = 4, // a tile waited too long for its predecessor (should never happen)
-  AEW_DEV_RUN_OVERFLOW = 8,   // more QRS runs in a window than the kernel's table holds
-};
+// ---- status codes shared by device and host: include/aewave.h
+#include "../../include/aewave.h"
 
 #define AEW_WARP 32
 #define AEW_FULL 0xffffffffu

@@ -55,7 +55,7 @@ __device__ __forceinline__ long long find_record(const long long* __restrict__ s
 // PASS 1: nodes <- sums of x (NaN->0), cnt[r] += non-NaN count.
 // PASS 2: nodes <- sums of (x-mean[r])^2.
 template <int PASS>
-__global__ void __launch_bounds__(256) k1_leaf(const double* __restrict__ x, const long long* __restrict__ rec_off,
+__global__ void __launch_bounds__(256) k1_leaf(const double* __restrict__ x, const long long* __restrict__ rec_beg, const long long* __restrict__ rec_end,
                                                const long long* __restrict__ blk_start, long long n_rec,
                                                const double* __restrict__ mean, double* __restrict__ nodes,
                                                unsigned long long* __restrict__ cnt) {
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) k1_leaf(const double* __restrict__ x, con
   if (threadIdx.x == 0) { s_rec = find_record(blk_start, n_rec, b); s_cnt = 0; }
   __syncthreads();
   const long long r = s_rec;
-  const long long base = rec_off[r], n = rec_off[r + 1] - base;
+  const long long base = rec_beg[r], n = rec_end[r] - base;
   const int depth = pw_depth(n);
   const int sub = depth < 5 ? depth : 5;
   const unsigned j = (unsigned)(b - blk_start[r]);
@@ -101,13 +101,13 @@ __global__ void __launch_bounds__(256) k1_leaf(const double* __restrict__ x, con
 // Fold the nodes of each record (2^(depth-5) of them) to the root.
 // PASS 1 writes mean[r] = sum / cnt; PASS 2 writes sd[r] = sqrt(sum / cnt).
 template <int PASS>
-__global__ void __launch_bounds__(256) k1_combine(const long long* __restrict__ rec_off,
+__global__ void __launch_bounds__(256) k1_combine(const long long* __restrict__ rec_beg, const long long* __restrict__ rec_end,
                                                   const long long* __restrict__ blk_start,
                                                   double* __restrict__ nodes, double* __restrict__ nodes2,
                                                   const unsigned long long* __restrict__ cnt,
                                                   double* __restrict__ out) {
   const long long r = blockIdx.x;
-  const long long n = rec_off[r + 1] - rec_off[r];
+  const long long n = rec_end[r] - rec_beg[r];
   const int depth = pw_depth(n);
   const int dn = depth > 5 ? depth - 5 : 0;
   double* src = nodes + blk_start[r];
@@ -131,28 +131,61 @@ __global__ void __launch_bounds__(256) k1_combine(const long long* __restrict__ 
   }
 }
 
-__global__ void __launch_bounds__(256) k1_apply(const double* __restrict__ x, const long long* __restrict__ rec_off,
-                                                long long n_rec, const double* __restrict__ mean,
-                                                const double* __restrict__ sd, double* __restrict__ out,
-                                                long long total) {
+// out[i] = (x[i] - mean[r]) / sd[r] for i inside record r; NaN between records
+__global__ void __launch_bounds__(256) k1_apply(const double* __restrict__ x, const long long* __restrict__ rec_beg,
+                                                const long long* __restrict__ rec_end, long long n_rec,
+                                                const double* __restrict__ mean, const double* __restrict__ sd,
+                                                double* __restrict__ out, long long lo, long long hi) {
   const long long per_thread = 4;
-  long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * per_thread;
-  if (i >= total) return;
-  long long r = find_record(rec_off, n_rec, i);
-  for (int k = 0; k < per_thread && i < total; ++k, ++i) {
-    while (i >= rec_off[r + 1]) ++r;
-    out[i] = __ddiv_rn(__dsub_rn(x[i], mean[r]), sd[r]);
+  long long i = lo + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * per_thread;
+  if (i >= hi) return;
+  long long r = find_record(rec_beg, n_rec, i);
+  for (int k = 0; k < per_thread && i < hi; ++k, ++i) {
+    while (r + 1 < n_rec && i >= rec_beg[r + 1]) ++r;
+    out[i] = (i >= rec_beg[r] && i < rec_end[r]) ? __ddiv_rn(__dsub_rn(x[i], mean[r]), sd[r])
+                                                 : __longlong_as_double(0x7ff8000000000000ll);
+  }
+}
+
+// first / one-past-last non-NaN sample of every record (data_extract_vitaldb.py:53-57):
+// trimmed[2r] = begin, trimmed[2r+1] = end (begin == end when the record is all NaN)
+__global__ void __launch_bounds__(256) k1_trim(const double* __restrict__ x, const long long* __restrict__ rec_beg,
+                                               const long long* __restrict__ rec_end,
+                                               long long* __restrict__ trimmed) {
+  const long long r = blockIdx.x;
+  const long long b = rec_beg[r], e = rec_end[r];
+  __shared__ long long s_first, s_last;
+  if (threadIdx.x == 0) { s_first = e; s_last = b - 1; }
+  __syncthreads();
+  for (long long base = b; base < e; base += blockDim.x) {       // from the front
+    const long long i = base + threadIdx.x;
+    const int ok = (i < e) && !isnan(x[i]);
+    if (ok) atomicMin(&s_first, i);
+    if (__syncthreads_or(ok)) break;
+  }
+  for (long long top = e; top > b; top -= blockDim.x) {          // from the back
+    const long long i = top - 1 - threadIdx.x;
+    const int ok = (i >= b) && !isnan(x[i]);
+    if (ok) atomicMax(&s_last, i);
+    if (__syncthreads_or(ok)) break;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const bool any = s_first < e;
+    trimmed[2 * r] = any ? s_first : b;
+    trimmed[2 * r + 1] = any ? s_last + 1 : b;
   }
 }
 
 }  // namespace
 
 // ---------------------------------------------------------------- host side
-extern "C" long long aew_zscore_plan(const long long* h_rec_off, long long n_rec, long long* h_blk_start) {
+extern "C" long long aew_zscore_plan(const long long* h_rec_beg, const long long* h_rec_end, long long n_rec,
+                                     long long* h_blk_start) {
   long long acc = 0;
   for (long long r = 0; r < n_rec; ++r) {
     if (h_blk_start) h_blk_start[r] = acc;
-    const int d = pw_depth(h_rec_off[r + 1] - h_rec_off[r]);
+    const int d = pw_depth(h_rec_end[r] - h_rec_beg[r]);
     acc += 1ll << (d > 5 ? d - 5 : 0);
   }
   if (h_blk_start) h_blk_start[n_rec] = acc;
@@ -163,37 +196,48 @@ extern "C" size_t aew_zscore_workspace_bytes(long long n_rec, long long n_blocks
   return (size_t)(2 * n_blocks) * sizeof(double) + (size_t)n_rec * sizeof(unsigned long long) + 64;
 }
 
-extern "C" int aew_zscore_stats_f64(const double* x, const long long* d_rec_off, const long long* d_blk_start,
-                                    long long n_rec, long long n_blocks, double* mean, double* sd,
-                                    long long* count, void* ws, size_t ws_bytes, void* stream) {
-  if (!x || !d_rec_off || !d_blk_start || !mean || !sd || !ws || n_rec < 0) return AEW_ERR_ARG;
+extern "C" int aew_trim_nan_edges_f64(const double* x, const long long* d_rec_beg, const long long* d_rec_end,
+                                      long long n_rec, long long* d_trimmed, void* stream) {
+  if (!x || !d_rec_beg || !d_rec_end || !d_trimmed || n_rec < 0) return AEW_ERR_ARG;
+  if (n_rec == 0) return AEW_OK;
+  if (n_rec > 0x7fffffffll) return AEW_ERR_UNSUPPORTED;
+  AEW_LAUNCH(k1_trim, (unsigned)n_rec, 256, 0, (cudaStream_t)stream, x, d_rec_beg, d_rec_end, d_trimmed);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int aew_zscore_stats_f64(const double* x, const long long* d_rec_beg, const long long* d_rec_end,
+                                    const long long* d_blk_start, long long n_rec, long long n_blocks, double* mean,
+                                    double* sd, long long* count, void* ws, size_t ws_bytes, void* stream) {
+  if (!x || !d_rec_beg || !d_rec_end || !d_blk_start || !mean || !sd || !ws || n_rec < 0) return AEW_ERR_ARG;
   if (n_rec == 0) return AEW_OK;
   if (ws_bytes < aew_zscore_workspace_bytes(n_rec, n_blocks)) return AEW_ERR_WORKSPACE;
-  if (n_blocks > 0x7fffffffll) return AEW_ERR_UNSUPPORTED;
+  if (n_blocks > 0x7fffffffll || n_rec > 0x7fffffffll) return AEW_ERR_UNSUPPORTED;
   double* nodes = (double*)ws;
   double* nodes2 = nodes + n_blocks;
   unsigned long long* cnt = count ? (unsigned long long*)count : (unsigned long long*)(nodes2 + n_blocks);
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(cnt, 0, (size_t)n_rec * sizeof(unsigned long long), st);
-  AEW_LAUNCH(k1_leaf<1>, (unsigned)n_blocks, 256, 0, st, x, d_rec_off, d_blk_start, n_rec, (const double*)nullptr,
-             nodes, cnt);
-  AEW_LAUNCH(k1_combine<1>, (unsigned)n_rec, 256, 0, st, d_rec_off, d_blk_start, nodes, nodes2,
+  AEW_LAUNCH(k1_leaf<1>, (unsigned)n_blocks, 256, 0, st, x, d_rec_beg, d_rec_end, d_blk_start, n_rec,
+             (const double*)nullptr, nodes, cnt);
+  AEW_LAUNCH(k1_combine<1>, (unsigned)n_rec, 256, 0, st, d_rec_beg, d_rec_end, d_blk_start, nodes, nodes2,
              (const unsigned long long*)cnt, mean);
-  AEW_LAUNCH(k1_leaf<2>, (unsigned)n_blocks, 256, 0, st, x, d_rec_off, d_blk_start, n_rec, (const double*)mean,
-             nodes, cnt);
-  AEW_LAUNCH(k1_combine<2>, (unsigned)n_rec, 256, 0, st, d_rec_off, d_blk_start, nodes, nodes2,
+  AEW_LAUNCH(k1_leaf<2>, (unsigned)n_blocks, 256, 0, st, x, d_rec_beg, d_rec_end, d_blk_start, n_rec,
+             (const double*)mean, nodes, cnt);
+  AEW_LAUNCH(k1_combine<2>, (unsigned)n_rec, 256, 0, st, d_rec_beg, d_rec_end, d_blk_start, nodes, nodes2,
              (const unsigned long long*)cnt, sd);
   return (int)cudaGetLastError();
 }
 
-extern "C" int aew_zscore_apply_f64(const double* x, const long long* d_rec_off, long long n_rec,
-                                    const double* mean, const double* sd, double* out, long long total,
-                                    void* stream) {
-  if (!x || !d_rec_off || !mean || !sd || !out || n_rec < 0 || total < 0) return AEW_ERR_ARG;
-  if (total == 0) return AEW_OK;
-  const long long threads = (total + 3) / 4;
+// applies over flat positions [lo, hi); positions outside every record get NaN
+extern "C" int aew_zscore_apply_f64(const double* x, const long long* d_rec_beg, const long long* d_rec_end,
+                                    long long n_rec, const double* mean, const double* sd, double* out,
+                                    long long lo, long long hi, void* stream) {
+  if (!x || !d_rec_beg || !d_rec_end || !mean || !sd || !out || n_rec < 1 || hi < lo) return AEW_ERR_ARG;
+  if (hi == lo) return AEW_OK;
+  const long long threads = (hi - lo + 3) / 4;
   const long long blocks = (threads + 255) / 256;
   if (blocks > 0x7fffffffll) return AEW_ERR_UNSUPPORTED;
-  AEW_LAUNCH(k1_apply, (unsigned)blocks, 256, 0, (cudaStream_t)stream, x, d_rec_off, n_rec, mean, sd, out, total);
+  AEW_LAUNCH(k1_apply, (unsigned)blocks, 256, 0, (cudaStream_t)stream, x, d_rec_beg, d_rec_end, n_rec, mean, sd, out,
+             lo, hi);
   return (int)cudaGetLastError();
 }

@@ -81,13 +81,13 @@ inline size_t k2_ws_layout(void* base, long long max_seg, long long max_tiles, K
 #define SEG_ITEMS 8
 
 __global__ void __launch_bounds__(SEG_THREADS) k2_seg_find(const double* __restrict__ x,
-                                                           const long long* __restrict__ rec_off,
+                                                           const long long* __restrict__ rec_beg, const long long* __restrict__ rec_end,
                                                            const long long* __restrict__ nonnan_count,
                                                            double* __restrict__ nan_fill, K2Ws ws) {
   __shared__ long long s_warp[SEG_THREADS / 32];
   __shared__ long long s_carry;
   const long long r = blockIdx.x;
-  const long long base = rec_off[r], n = rec_off[r + 1] - base;
+  const long long base = rec_beg[r], n = rec_end[r] - base;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double qnan = __longlong_as_double(0x7ff8000000000000ll);
 
@@ -485,10 +485,11 @@ extern "C" size_t aew_filt_workspace_bytes(long long n_rec, long long total_samp
 // Finds the non-NaN segments of every record and (if nan_fill != NULL) writes NaN
 // to nan_fill at every NaN input position.  nonnan_count (device, optional, from
 // aew_zscore_stats_f64) lets NaN-free records skip the scan.
-extern "C" int aew_segments_find_f64(const double* x, const long long* d_rec_off, long long n_rec,
+extern "C" int aew_segments_find_f64(const double* x, const long long* d_rec_beg, const long long* d_rec_end,
+                                     long long n_rec,
                                      long long total_samples, const long long* d_nonnan_count, double* nan_fill,
                                      void* ws, size_t ws_bytes, long long max_seg, void* stream) {
-  if (!x || !d_rec_off || !ws || n_rec < 0 || max_seg < 1) return AEW_ERR_ARG;
+  if (!x || !d_rec_beg || !d_rec_end || !ws || n_rec < 0 || max_seg < 1) return AEW_ERR_ARG;
   if (ws_bytes < aew_filt_workspace_bytes(n_rec, total_samples, max_seg)) return AEW_ERR_WORKSPACE;
   if (n_rec > 0x7fffffffll || max_seg > 0x7fffffffll) return AEW_ERR_UNSUPPORTED;
   K2Ws w;
@@ -496,7 +497,7 @@ extern "C" int aew_segments_find_f64(const double* x, const long long* d_rec_off
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(w.hdr, 0, H_SLOTS * sizeof(long long), st);
   if (n_rec == 0) return AEW_OK;
-  AEW_LAUNCH(k2_seg_find, (unsigned)n_rec, SEG_THREADS, 0, st, x, d_rec_off, d_nonnan_count, nan_fill, w);
+  AEW_LAUNCH(k2_seg_find, (unsigned)n_rec, SEG_THREADS, 0, st, x, d_rec_beg, d_rec_end, d_nonnan_count, nan_fill, w);
   return (int)cudaGetLastError();
 }
 

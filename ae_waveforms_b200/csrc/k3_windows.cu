@@ -1,0 +1,605 @@
+// k3_windows.cu -- per-window z-score, R-peak detection, physiological screen
+// and median beat (K3 + K4, fused: the window is read from HBM once).
+//
+// One 512-thread block per 20 s window (L = 10,000 samples, 80 KB, staged once in
+// shared memory).  Replaces, per window,
+//   data_extract_vitaldb.py:93          per-window zscore            (bit-exact)
+//   remove_samples.py:31-33,43          drop windows containing NaN
+//   remove_samples.py:50-51             nk.ecg_findpeaks (default "neurokit" method,
+//                                       SURVEY.md appendix B.2 / oracle/nk_peaks.py)
+//   remove_samples.py:53-64,85-121      bounds filter, estimate_hr, rmssd, np.std, sd/n
+//   remove_samples.py:70-74             keep/remove mask                (bit-exact)
+//   median_sample.py:6-54               320-sample R-aligned sections, column-wise
+//                                       nanmedian -> np_waves row       (bit-exact)
+//
+// Exactness.  Everything downstream of the QRS indicator works on integers or on
+// NumPy-ordered reductions (aew_pairwise.cuh) and is bit-identical to the
+// reference.  The indicator smoothgrad > 1.5*avggrad comes from two
+// scipy.ndimage.uniform_filter1d calls whose C code is ONE running sum over the
+// window (appendix B.3): 2 x 10,000 dependent additions.  The kernel evaluates both
+// box filters with block-wide prefix sums instead (different rounding, ~1e-13),
+// flags a window as a HAZARD when any sample's comparison is closer to a tie than a
+// bound that dominates both evaluations' rounding error, and only for those
+// (about 1 window in 10^3) thread 0 re-runs SciPy's literal running sums.  Integer
+// outputs are therefore identical to the sequential evaluation for every window.
+// mode 1 forces the sequential evaluation everywhere (parity suite); mode 2
+// disables the fallback (measurement only).
+//
+// Algorithmic HBM bytes: 8 B per input sample read + (320*12 + 72*4 + 48) B per
+// window written.  Bound: B200's FP64 pipe, not HBM -- ~3 IEEE divisions and
+// ~40 other FP64 operations per sample.
+#include "aew_pairwise.cuh"
+#include "../../include/aewave.h"
+
+#define K3_NT 512
+#define K3_ITEMS 21                       // odd -> conflict-free per-thread strips
+#define K3_MAXL (K3_NT * K3_ITEMS)        // 10752 samples per window at most
+#define K3_MAXP 72                        // peaks are > 150 samples apart -> at most 71 in 10752
+#define K3_BEAT 320
+#define K3_NONE 0xffffu
+
+namespace {
+
+struct K3Smem {
+  double* A;            // [L]  z-scored window
+  double* B;            // [L]  prefix sums / sequential smoothgrad
+  double* pw_vals;      // [128]
+  double* wtot;         // [16]
+  double* scal;         // [16] scalars
+  int* ipeaks;          // [K3_MAXP]
+  int* iscal;           // [16]
+  unsigned short* beg;  // [L/2 + 2]
+  unsigned short* end;
+  unsigned short* cand;
+  unsigned char* Q;     // [L]
+  unsigned char* pw_valid;  // [128]
+};
+
+__host__ __device__ inline size_t k3_smem_layout(unsigned char* base, int L, K3Smem* s) {
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o = (o + bytes + 15) & ~(size_t)15; return base ? base + at : (unsigned char*)0; };
+  K3Smem t;
+  t.A = (double*)take(sizeof(double) * L);
+  t.B = (double*)take(sizeof(double) * L);
+  t.pw_vals = (double*)take(sizeof(double) * 128);
+  t.wtot = (double*)take(sizeof(double) * 16);
+  t.scal = (double*)take(sizeof(double) * 16);
+  t.ipeaks = (int*)take(sizeof(int) * K3_MAXP);
+  t.iscal = (int*)take(sizeof(int) * 16);
+  const int rmax = L / 2 + 2;
+  t.beg = (unsigned short*)take(sizeof(unsigned short) * rmax);
+  t.end = (unsigned short*)take(sizeof(unsigned short) * rmax);
+  t.cand = (unsigned short*)take(sizeof(unsigned short) * rmax);
+  t.Q = (unsigned char*)take(L);
+  t.pw_valid = (unsigned char*)take(128);
+  if (s) *s = t;
+  return o;
+}
+
+// np.gradient(z) magnitude: interior (z[i+1]-z[i-1])/2, one-sided at the edges
+__device__ __forceinline__ double absgrad(const double* __restrict__ z, int i, int L) {
+  double g;
+  if (i == 0) g = __dsub_rn(z[1], z[0]);
+  else if (i == L - 1) g = __dsub_rn(z[L - 1], z[L - 2]);
+  else g = __dmul_rn(__dsub_rn(z[i + 1], z[i - 1]), 0.5);
+  return fabs(g);
+}
+
+struct SumPlain { const double* a; __device__ __forceinline__ double operator()(long long i, bool) { return a[i]; } };
+struct SumDev2 {
+  const double* a; double m;
+  __device__ __forceinline__ double operator()(long long i, bool) { const double d = __dsub_rn(a[i], m); return __dmul_rn(d, d); }
+};
+
+// exclusive block scan of one double per thread (fast path; not order-sensitive)
+__device__ __forceinline__ double block_excl_scan(double v, double* wtot) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const double o = __shfl_up_sync(AEW_FULL, incl, d);
+    if (lane >= d) incl += o;
+  }
+  if (lane == 31) wtot[warp] = incl;
+  __syncthreads();
+  double base = 0.0;
+  for (int w = 0; w < warp; ++w) base += wtot[w];
+  __syncthreads();
+  return base + (incl - v);
+}
+__device__ __forceinline__ int block_excl_scan_int(int v, int* wtot) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(AEW_FULL, incl, d);
+    if (lane >= d) incl += o;
+  }
+  if (lane == 31) wtot[warp] = incl;
+  __syncthreads();
+  int base = 0;
+  for (int w = 0; w < warp; ++w) base += wtot[w];
+  __syncthreads();
+  return base + (incl - v);
+}
+
+// sum over a clamped ("nearest") window [lo, hi] from an inclusive prefix array
+__device__ __forceinline__ double clamped_window(const double* __restrict__ P, int lo, int hi, int L, double first,
+                                                 double last) {
+  const int nl = lo < 0 ? -lo : 0, nr = hi > L - 1 ? hi - (L - 1) : 0;
+  const int lo2 = lo < 0 ? 0 : lo, hi2 = hi > L - 1 ? L - 1 : hi;
+  double s = P[hi2] - (lo2 > 0 ? P[lo2 - 1] : 0.0);
+  s += (double)nl * first + (double)nr * last;
+  return s;
+}
+
+// ---- warp bitonic sort of 32*K doubles, element e = k*32 + lane, ascending
+template <int K>
+__device__ __forceinline__ void warp_sort(double (&v)[K], int lane) {
+#pragma unroll
+  for (int size = 2; size <= 32 * K; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride >= 32) {
+        const int ks = stride >> 5;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          if ((k & ks) == 0) {
+            const int e = k * 32;                       // direction depends on bits >= 5 only here
+            const bool asc = ((e & size) == 0);
+            const double a = v[k], b = v[k | ks];
+            const bool swap = asc ? (a > b) : (a < b);
+            v[k] = swap ? b : a;
+            v[k | ks] = swap ? a : b;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const int e = k * 32 + lane;
+          const bool asc = ((e & size) == 0);
+          const double o = __shfl_xor_sync(AEW_FULL, v[k], stride);
+          const bool lower = (lane & stride) == 0;
+          const bool take_min = (lower == asc);
+          v[k] = take_min ? (o < v[k] ? o : v[k]) : (o > v[k] ? o : v[k]);
+        }
+      }
+    }
+  }
+}
+
+template <int K>
+__device__ __forceinline__ double warp_pick(const double (&v)[K], int rank, int lane) {
+  double r = 0.0;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const double c = __shfl_sync(AEW_FULL, v[k], rank & 31);
+    if ((rank >> 5) == k) r = c;
+  }
+  return r;
+}
+
+// column-wise nanmedian over the beats of one window (median_sample.py:30-47).
+// z: window samples (shared or global), peaks: n beat positions.  One warp per
+// column; lane b holds beats b, b+32, ...  (lo+hi)/2 with lo == hi for odd counts,
+// exactly as np.ma.median evaluates it.
+template <int K>
+__device__ __forceinline__ double column_median(const double* __restrict__ z, const int* __restrict__ peaks, int n,
+                                                int c, int L, int pre, int post, int lane) {
+  double v[K];
+  int valid = 0;
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int b = k * 32 + lane;
+    v[k] = inf;
+    if (b < n) {
+      const int p = peaks[b];
+      const int s = p - pre < 0 ? 0 : p - pre;
+      const int e = p + post > L ? L : p + post;
+      const int idx = s + c;                           // short slices are left-aligned (appendix A.4)
+      if (idx < e) { v[k] = z[idx]; ++valid; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) valid += __shfl_xor_sync(AEW_FULL, valid, o);
+  warp_sort<K>(v, lane);
+  const int h = valid >> 1;
+  const double hi = warp_pick<K>(v, h < 32 * K - 1 ? h : 32 * K - 1, lane);
+  const double lo = warp_pick<K>(v, (valid & 1) ? h : (h > 0 ? h - 1 : 0), lane);
+  if (valid == 0) return __longlong_as_double(0x7ff8000000000000ll);
+  return __dmul_rn(__dadd_rn(lo, hi), 0.5);
+}
+
+__device__ __forceinline__ void window_median(const double* __restrict__ z, const int* __restrict__ peaks, int n,
+                                              int L, int pre, int post, double* __restrict__ med,
+                                              float* __restrict__ waves) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int c = warp; c < pre + post; c += nwarp) {
+    double m;
+    if (n <= 32) m = column_median<1>(z, peaks, n, c, L, pre, post, lane);
+    else if (n <= 64) m = column_median<2>(z, peaks, n, c, L, pre, post, lane);
+    else m = column_median<4>(z, peaks, n, c, L, pre, post, lane);
+    if (lane == 0) {
+      if (med) med[c] = m;
+      if (waves) waves[c] = (float)m;
+    }
+  }
+}
+
+// NumPy order sum of a short vector (n <= 128) by one thread
+__device__ inline double leaf_sum_seq(const double* v, int n) {
+  if (n < 8) {
+    double r = 0.0;
+    for (int i = 0; i < n; ++i) r = __dadd_rn(r, v[i]);
+    return r;
+  }
+  double r[8];
+  for (int k = 0; k < 8; ++k) r[k] = v[k];
+  int i = 8;
+  for (; i + 8 <= n; i += 8)
+    for (int k = 0; k < 8; ++k) r[k] = __dadd_rn(r[k], v[i + k]);
+  double s = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                       __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+  for (; i < n; ++i) s = __dadd_rn(s, v[i]);
+  return s;
+}
+
+__global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p) {
+  AEW_DYN_SMEM(smem_raw);
+  K3Smem sm;
+  k3_smem_layout(smem_raw, p.L, &sm);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int L = p.L;
+  const long long w = blockIdx.x;
+  const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+  if (p.win_start[w] < 0) {                             // padding slot of an over-allocated window table
+    if (tid == 0) {
+      p.keep[w] = 0; p.has_nan[w] = 2; p.n_peaks[w] = 0;
+      for (int k = 0; k < 4; ++k) p.stats[4 * w + k] = qnan;
+    }
+    return;
+  }
+  const double* src = p.y + p.win_start[w];
+  double* A = sm.A;
+  double* B = sm.B;
+
+  // ---- load, NaN screen (remove_samples.py:31-33)
+  int bad = 0;
+  for (int i = tid; i < L; i += K3_NT) {
+    const double v = src[i];
+    A[i] = v;
+    bad |= isnan(v) ? 1 : 0;
+  }
+  bad = __syncthreads_or(bad);
+  const int depth = pw_depth(L);
+  double mean = 0.0, sd0 = 0.0;
+  if (!bad && p.zscore_windows) {
+    // ---- per-window z-score (data_extract_vitaldb.py:93), NumPy summation order
+    SumPlain f1{A};
+    mean = __ddiv_rn(pw_block_sum(f1, L, depth, sm.pw_vals, sm.pw_valid), (double)L);
+    SumDev2 f2{A, mean};
+    sd0 = __dsqrt_rn(__ddiv_rn(pw_block_sum(f2, L, depth, sm.pw_vals, sm.pw_valid), (double)L));
+    int nonfinite = 0;
+    for (int i = tid; i < L; i += K3_NT) {
+      const double z = __ddiv_rn(__dsub_rn(A[i], mean), sd0);
+      A[i] = z;
+      nonfinite |= (isnan(z) || isinf(z)) ? 1 : 0;     // constant window: 0/0
+    }
+    bad = __syncthreads_or(nonfinite);
+  }
+  if (p.zwin) {
+    double* zw = p.zwin + w * (long long)L;
+    for (int i = tid; i < L; i += K3_NT) zw[i] = A[i];  // NaN windows: as z-scored by the reference or raw
+  }
+  if (bad) {
+    if (tid == 0) {
+      p.keep[w] = 0; p.has_nan[w] = 1; p.n_peaks[w] = 0;
+      for (int k = 0; k < 4; ++k) p.stats[4 * w + k] = qnan;
+    }
+    return;
+  }
+
+  // ---- ecg_sd = np.std(window) (remove_samples.py:62)
+  SumPlain f3{A};
+  const double m2 = __ddiv_rn(pw_block_sum(f3, L, depth, sm.pw_vals, sm.pw_valid), (double)L);
+  SumDev2 f4{A, m2};
+  const double sd = __dsqrt_rn(__ddiv_rn(pw_block_sum(f4, L, depth, sm.pw_vals, sm.pw_valid), (double)L));
+
+  // ---- QRS indicator: smoothgrad > 1.5 * avggrad
+  const int ks = p.smooth_k, ka = p.avg_k;
+  const int ls = ks / 2, la = ka / 2;                  // uniform_filter1d: window [i - k/2, i - k/2 + k)
+  int hazard = 0;
+  if (p.mode != 1) {
+    const int i0 = tid * K3_ITEMS;
+    double loc[K3_ITEMS], smv[K3_ITEMS];
+    double run = 0.0;
+#pragma unroll
+    for (int k = 0; k < K3_ITEMS; ++k) {
+      const int i = i0 + k;
+      run += (i < L) ? absgrad(A, i, L) : 0.0;
+      loc[k] = run;
+    }
+    double base = block_excl_scan(run, sm.wtot);
+#pragma unroll
+    for (int k = 0; k < K3_ITEMS; ++k) if (i0 + k < L) B[i0 + k] = base + loc[k];
+    if (tid == 0) { sm.scal[0] = absgrad(A, 0, L); sm.scal[1] = absgrad(A, L - 1, L); }
+    __syncthreads();
+    const double ag0 = sm.scal[0], agL = sm.scal[1], ptot = B[L - 1];
+    const double inv_s = 1.0 / (double)ks, inv_a = 1.0 / (double)ka;
+    run = 0.0;
+#pragma unroll
+    for (int k = 0; k < K3_ITEMS; ++k) {
+      const int i = i0 + k;
+      double s = 0.0;
+      if (i < L) s = clamped_window(B, i - ls, i - ls + ks - 1, L, ag0, agL) * inv_s;
+      smv[k] = s;
+      run += s;
+      loc[k] = run;
+      if (i == 0) sm.scal[2] = s;
+      if (i == L - 1) sm.scal[3] = s;
+    }
+    base = block_excl_scan(run, sm.wtot);               // (its barriers also end all reads of B)
+#pragma unroll
+    for (int k = 0; k < K3_ITEMS; ++k) if (i0 + k < L) B[i0 + k] = base + loc[k];
+    __syncthreads();
+    const double s0 = sm.scal[2], sL = sm.scal[3];
+    const double tol_abs = 2e-12 * ptot * inv_s;
+#pragma unroll
+    for (int k = 0; k < K3_ITEMS; ++k) {
+      const int i = i0 + k;
+      if (i < L) {
+        const double a = clamped_window(B, i - la, i - la + ka - 1, L, s0, sL) * inv_a;
+        const double thr = 1.5 * a;
+        sm.Q[i] = smv[k] > thr;
+        const double tol = 1e-9 * (smv[k] + thr) + tol_abs;
+        hazard |= (fabs(smv[k] - thr) <= tol) ? 1 : 0;
+      }
+    }
+    hazard = __syncthreads_or(hazard);
+    if (p.mode == 2) hazard = 0;
+    if (hazard && tid == 0 && p.hazard_count) atomicAdd(p.hazard_count, 1ull);
+  }
+  if (p.mode == 1 || hazard) {
+    // SciPy's literal evaluation: one undivided running sum per box filter (appendix B.3)
+    if (tid == 0) {
+      const double dks = (double)ks, dka = (double)ka;
+      double t = 0.0;
+      for (int e = 0; e < ks; ++e) {
+        int j = e - ls; j = j < 0 ? 0 : (j > L - 1 ? L - 1 : j);
+        t = __dadd_rn(t, absgrad(A, j, L));
+      }
+      B[0] = __ddiv_rn(t, dks);
+      for (int i = 1; i < L; ++i) {
+        int jin = i + ks - 1 - ls, jout = i - 1 - ls;
+        jin = jin > L - 1 ? L - 1 : jin;
+        jout = jout < 0 ? 0 : jout;
+        t = __dadd_rn(t, __dsub_rn(absgrad(A, jin, L), absgrad(A, jout, L)));
+        B[i] = __ddiv_rn(t, dks);
+      }
+      double t2 = 0.0;
+      for (int e = 0; e < ka; ++e) {
+        int j = e - la; j = j < 0 ? 0 : (j > L - 1 ? L - 1 : j);
+        t2 = __dadd_rn(t2, B[j]);
+      }
+      sm.Q[0] = B[0] > __dmul_rn(1.5, __ddiv_rn(t2, dka));
+      for (int i = 1; i < L; ++i) {
+        int jin = i + ka - 1 - la, jout = i - 1 - la;
+        jin = jin > L - 1 ? L - 1 : jin;
+        jout = jout < 0 ? 0 : jout;
+        t2 = __dadd_rn(t2, __dsub_rn(B[jin], B[jout]));
+        sm.Q[i] = B[i] > __dmul_rn(1.5, __ddiv_rn(t2, dka));
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- QRS runs: beg where ~q[i] & q[i+1], end where q[i] & ~q[i+1]  (ordered compaction)
+  {
+    const int i0 = tid * K3_ITEMS;
+    int nb = 0, ne = 0;
+#pragma unroll
+    for (int k = 0; k < K3_ITEMS; ++k) {
+      const int i = i0 + k;
+      if (i < L - 1) {
+        const int a = sm.Q[i], b = sm.Q[i + 1];
+        nb += (!a && b);
+        ne += (a && !b);
+      }
+    }
+    const int packed = block_excl_scan_int(nb | (ne << 16), (int*)sm.wtot);
+    int ob = packed & 0xffff, oe = packed >> 16;
+#pragma unroll
+    for (int k = 0; k < K3_ITEMS; ++k) {
+      const int i = i0 + k;
+      if (i < L - 1) {
+        const int a = sm.Q[i], b = sm.Q[i + 1];
+        if (!a && b) sm.beg[ob++] = (unsigned short)i;
+        if (a && !b) sm.end[oe++] = (unsigned short)i;
+      }
+    }
+    if (tid == K3_NT - 1) { sm.iscal[0] = ob; sm.iscal[1] = oe; }
+    __syncthreads();
+  }
+  const int nbeg = sm.iscal[0], nend = sm.iscal[1];
+  // ends that precede the first beg are dropped (at most one, runs alternate)
+  const int skip = (nbeg > 0 && nend > 0 && sm.end[0] <= sm.beg[0]) ? 1 : 0;
+  int num = nend - skip < nbeg ? nend - skip : nbeg;
+  if (nbeg == 0) num = 0;
+  const unsigned short* endp = sm.end + skip;
+
+  // ---- min_len = mean(end - beg) * 0.4 (integer sum is exact in any order)
+  {
+    long long part = 0;
+    for (int i = tid; i < num; i += K3_NT) part += (long long)endp[i] - (long long)sm.beg[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(AEW_FULL, part, o);
+    if (lane == 0) ((long long*)sm.wtot)[warp] = part;
+    __syncthreads();
+    if (tid == 0) {
+      long long tot = 0;
+      for (int k = 0; k < K3_NT / 32; ++k) tot += ((long long*)sm.wtot)[k];
+      sm.scal[4] = num > 0 ? __dmul_rn(__ddiv_rn((double)tot, (double)num), 0.4) : 0.0;
+    }
+    __syncthreads();
+  }
+  const double min_len = sm.scal[4];
+
+  // ---- per run: most prominent strict local maximum (scipy.signal.find_peaks semantics)
+  for (int r = warp; r < num; r += K3_NT / 32) {
+    const int b = sm.beg[r], e = endp[r];
+    const int n = e - b;
+    const double* d = A + b;
+    double best = -1.0;
+    int best_i = 0x7fffffff;
+    if (!((double)n < min_len)) {
+      for (int i = 1 + lane; i < n - 1; i += 32) {
+        if (d[i - 1] < d[i]) {
+          int ahead = i + 1;
+          while (ahead < n - 1 && d[ahead] == d[i]) ++ahead;
+          if (d[ahead] < d[i]) {
+            const int pk = (i + ahead - 1) / 2;        // plateau midpoint
+            const double h = d[pk];
+            double lmin = h, rmin = h;
+            for (int j = pk; j >= 0 && d[j] <= h; --j) lmin = d[j] < lmin ? d[j] : lmin;
+            for (int j = pk; j <= n - 1 && d[j] <= h; ++j) rmin = d[j] < rmin ? d[j] : rmin;
+            const double prom = __dsub_rn(h, lmin > rmin ? lmin : rmin);
+            if (prom > best || (prom == best && pk < best_i)) { best = prom; best_i = pk; }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(AEW_FULL, best, o);
+      const int oi = __shfl_xor_sync(AEW_FULL, best_i, o);
+      if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+    }
+    if (lane == 0) sm.cand[r] = best_i == 0x7fffffff ? (unsigned short)K3_NONE : (unsigned short)(b + best_i);
+  }
+  __syncthreads();
+
+  // ---- refractory chain, statistics, mask (thread 0)
+  if (tid == 0) {
+    int np = 0, last = 0;
+    for (int r = 0; r < num; ++r) {
+      const int c = sm.cand[r];
+      if (c == (int)K3_NONE) continue;
+      if (c - last > p.refractory) {
+        if (np < K3_MAXP) sm.ipeaks[np] = c;
+        ++np;
+        last = c;
+      }
+    }
+    if (np > K3_MAXP) { atomicOr(p.status, AEW_DEV_RUN_OVERFLOW); np = K3_MAXP; }
+    // remove_samples.py:53-54 keeps 0 < p < L (always true here: p > refractory)
+    double hr = qnan, rms = qnan;
+    if (np >= 2) {
+      int diffs[K3_MAXP];
+      for (int i = 0; i + 1 < np; ++i) diffs[i] = sm.ipeaks[i + 1] - sm.ipeaks[i];
+      const int nd = np - 1;
+      for (int i = 1; i < nd; ++i) {                   // insertion sort, <= 71 values
+        const int v = diffs[i];
+        int j = i - 1;
+        while (j >= 0 && diffs[j] > v) { diffs[j + 1] = diffs[j]; --j; }
+        diffs[j + 1] = v;
+      }
+      const double med = (nd & 1) ? (double)diffs[nd / 2]
+                                  : __dmul_rn(__dadd_rn((double)diffs[nd / 2 - 1], (double)diffs[nd / 2]), 0.5);
+      hr = __ddiv_rn(p.hr_num, med);
+    }
+    if (np >= 3) {
+      double sq[K3_MAXP];
+      double prev = __ddiv_rn((double)(sm.ipeaks[1] - sm.ipeaks[0]), p.rr_div);
+      for (int i = 1; i + 1 < np; ++i) {
+        const double cur = __ddiv_rn((double)(sm.ipeaks[i + 1] - sm.ipeaks[i]), p.rr_div);
+        const double dd = __dsub_rn(cur, prev);
+        sq[i - 1] = __dmul_rn(dd, dd);
+        prev = cur;
+      }
+      rms = __dsqrt_rn(__ddiv_rn(leaf_sum_seq(sq, np - 2), (double)(np - 2)));
+    }
+    const double sdn = __ddiv_rn(sd, (double)np);
+    const bool remove = (hr < p.hr_lo) || (hr > p.hr_hi) || isnan(hr) || (rms > p.pvc_threshold) ||
+                        (sdn > p.sd_threshold);
+    sm.iscal[2] = np;
+    sm.iscal[3] = remove ? 0 : 1;
+    p.keep[w] = remove ? 0 : 1;
+    p.has_nan[w] = 0;
+    p.n_peaks[w] = np;
+    p.stats[4 * w + 0] = hr; p.stats[4 * w + 1] = rms; p.stats[4 * w + 2] = sd; p.stats[4 * w + 3] = sdn;
+  }
+  __syncthreads();
+  const int np = sm.iscal[2];
+  for (int i = tid; i < K3_MAXP; i += K3_NT) p.peaks[w * K3_MAXP + i] = i < np ? sm.ipeaks[i] : -1;
+
+  // ---- median beat of kept windows (median_sample.py:6-54) -> np_waves row
+  if (sm.iscal[3] && (p.median || p.waves))
+    window_median(A, sm.ipeaks, np, L, p.pre, p.post, p.median ? p.median + w * K3_BEAT : nullptr,
+                  p.waves ? p.waves + w * K3_BEAT : nullptr);
+}
+
+// Stand-alone median beats for given peaks (the compute_median_sample_ecg shim):
+// one block per window, samples read from global memory.
+__global__ void __launch_bounds__(256) k4_median(const double* __restrict__ windows, int L, const int* __restrict__ peaks,
+                                                const long long* __restrict__ peak_off, int pre, int post,
+                                                double* __restrict__ median, double* __restrict__ aligned) {
+  const long long w = blockIdx.x;
+  const double* z = windows + w * (long long)L;
+  const int* pk = peaks + peak_off[w];
+  const int n = (int)(peak_off[w + 1] - peak_off[w]);
+  const int S = pre + post;
+  if (aligned) {
+    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+    double* al = aligned + peak_off[w] * S;
+    for (int i = threadIdx.x; i < n * S; i += blockDim.x) {
+      const int b = i / S, c = i - b * S;
+      const int p = pk[b];
+      const int s = p - pre < 0 ? 0 : p - pre, e = p + post > L ? L : p + post;
+      al[i] = (s + c < e) ? z[s + c] : qnan;
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int c = warp; c < S; c += nwarp) {
+    double m;
+    if (n <= 32) m = column_median<1>(z, pk, n, c, L, pre, post, lane);
+    else if (n <= 64) m = column_median<2>(z, pk, n, c, L, pre, post, lane);
+    else m = column_median<4>(z, pk, n, c, L, pre, post, lane);
+    if (lane == 0) median[w * S + c] = m;
+  }
+}
+
+}  // namespace
+
+extern "C" int aew_windows_max_peaks(void) { return K3_MAXP; }
+extern "C" int aew_windows_max_len(void) { return K3_MAXL; }
+
+extern "C" int aew_windows_beats_f64(const K3Params* hp, void* stream) {
+  if (!hp) return AEW_ERR_ARG;
+  K3Params p = *hp;
+  if (!p.y || !p.win_start || !p.keep || !p.has_nan || !p.n_peaks || !p.peaks || !p.stats || !p.status)
+    return AEW_ERR_ARG;
+  if (p.n_win == 0) return AEW_OK;
+  if (p.L < 16 || p.L > K3_MAXL || p.n_win < 0 || p.n_win > 0x7fffffffll) return AEW_ERR_UNSUPPORTED;
+  if (pw_depth(p.L) > 7 || p.pre + p.post != K3_BEAT || p.smooth_k < 1 || p.avg_k < 1 || p.smooth_k > p.L ||
+      p.avg_k > p.L || p.refractory < 1 || (p.L / (p.refractory + 1) + 1) > K3_MAXP)
+    return AEW_ERR_UNSUPPORTED;
+  const size_t smem = k3_smem_layout(nullptr, p.L, nullptr);
+  if (smem > 227 * 1024) return AEW_ERR_UNSUPPORTED;
+  static bool attr_done = false;
+  if (!attr_done) { AEW_SET_MAX_SMEM(k3_windows, 227 * 1024); attr_done = true; }
+  AEW_LAUNCH(k3_windows, (unsigned)p.n_win, K3_NT, smem, (cudaStream_t)stream, p);
+  return (int)cudaGetLastError();
+}
+
+// windows: [n_win][L] contiguous, peaks: CSR (peak_off[n_win+1]); at most 128 peaks per window.
+extern "C" int aew_median_beats_f64(const double* windows, long long n_win, int L, const int* peaks,
+                                    const long long* d_peak_off, int max_peaks_per_window, int pre, int post,
+                                    double* median, double* aligned, void* stream) {
+  if (!windows || !peaks || !d_peak_off || !median || n_win < 0 || L < 1) return AEW_ERR_ARG;
+  if (max_peaks_per_window > 128 || pre + post != K3_BEAT || n_win > 0x7fffffffll) return AEW_ERR_UNSUPPORTED;
+  if (n_win == 0) return AEW_OK;
+  AEW_LAUNCH(k4_median, (unsigned)n_win, 256, 0, (cudaStream_t)stream, windows, L, peaks, d_peak_off, pre, post,
+             median, aligned);
+  return (int)cudaGetLastError();
+}

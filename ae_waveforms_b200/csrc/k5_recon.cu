@@ -1,0 +1,305 @@
+// k5_recon.cu -- Gaussian fiducial-point reconstruction and the sigma-map search
+// objective, fused (K5).
+//
+// Replaces functions_traditional/signal_reconstruction.py:5-81 (gaussian_line,
+// extract_coordinates, reconstruct_gaussian) and the objective of
+// analysis_performance_traditional_vs_ae.py:63-90 evaluated for MANY sigma maps at
+// once: for every beat and every candidate map the beat is rebuilt as a chain of
+// half-Gaussian segments between consecutive fiducial points on the integer-ms
+// grid, resampled to the 320 beat samples with np.interp semantics, cast to
+// float32, and the squared float32 error against the float32 target is
+// accumulated (float64) per candidate.
+//
+// Mapping: persistent 320-thread blocks walk the beats; thread k owns output
+// sample k.  Everything that does not depend on sigma -- the 13-point coordinate
+// extraction (NaN drop, stable sort, duplicate bump: extract_coordinates), the
+// sigma_map slot walk with its NaN quirk, which two grid
+// points bracket sample k and which segments they belong to -- is computed once
+// per beat; per candidate the block evaluates 2 exps per segment (the affine
+// rescale of gaussian_line) and 2 exps per thread.  Candidates are processed four
+// at a time to amortise the two barriers.  Per-candidate sums go to a block-private
+// row of the workspace (no atomics) and a second kernel adds the rows in a fixed
+// order, so the result is deterministic.
+//
+// Bound: FP64/exp issue, not HBM -- ~664 double-precision exp per beat.candidate
+// against 1.46 KB read per beat.  No tensor cores: nothing
+// here is a contraction.
+#include "aew_rt.h"
+
+#define K5_NT 320
+#define K5_NPT 13            // 11 fiducials + 2 baseline end points
+#define K5_NSEG 12
+#define K5_CT 4              // candidates per inner iteration
+
+namespace {
+
+struct BeatPlan {
+  double x0[K5_NSEG], y0[K5_NSEG], x1[K5_NSEG], y1[K5_NSEG];
+  int slot[K5_NSEG];       // sigma_map index used by the segment
+  int forced[K5_NSEG];     // 1: divisor forced to 1 (next slot was NaN)
+  int emit[K5_NSEG];       // segment contributes samples
+  int start[K5_NSEG];      // first index in the concatenated signal
+  int gx0[K5_NSEG];        // int(x0): first grid value
+  int npts[K5_NSEG];
+  int nseg;                // compacted pairs
+  int total;               // len(ecg_syn2)
+  int invalid;             // the reference would raise (index error / empty signal)
+};
+
+struct SegCand {           // per (segment, candidate): the affine rescale of gaussian_line
+  double inv2s2;           // 1 / (2 s^2)
+  double amp;              // a = max(y1, y2)
+  double mu;
+  double c0, num, den, off;
+};
+
+__device__ void build_plan(const double* fx, const double* fy, double baseline, const double* xt, int nt,
+                           BeatPlan& P) {
+  double xs[K5_NPT], ys[K5_NPT];
+  bool missing[K5_NPT];
+  double cx[K5_NPT], cy[K5_NPT];
+  xs[0] = xt[0]; ys[0] = baseline;
+  for (int i = 0; i < 11; ++i) { xs[i + 1] = fx[i]; ys[i + 1] = fy[i]; }
+  xs[12] = xt[nt - 1]; ys[12] = baseline;
+  int m = 0;
+  for (int i = 0; i < K5_NPT; ++i) {
+    missing[i] = isnan(xs[i]) || isnan(ys[i]);
+    if (!missing[i]) { cx[m] = xs[i]; cy[m] = ys[i]; ++m; }
+  }
+  // np.argsort on <= 16 elements is an insertion sort: stable
+  for (int i = 1; i < m; ++i) {
+    const double vx = cx[i], vy = cy[i];
+    int j = i - 1;
+    while (j >= 0 && cx[j] > vx) { cx[j + 1] = cx[j]; cy[j + 1] = cy[j]; --j; }
+    cx[j + 1] = vx; cy[j + 1] = vy;
+  }
+  // duplicate x: every occurrence after the first gets += step, until unique (no re-sort)
+  const double step = xt[1] - xt[0];
+  for (int guard = 0; guard < 64; ++guard) {
+    double dup[K5_NPT];
+    int nd = 0;
+    for (int i = 0; i < m; ++i) {                      // duplicated values of this round, ascending
+      int count = 0;
+      bool seen = false;
+      for (int j = 0; j < m; ++j) count += (cx[j] == cx[i]);
+      for (int j = 0; j < nd; ++j) seen |= (dup[j] == cx[i]);
+      if (count > 1 && !seen) {
+        int at = nd++;
+        while (at > 0 && dup[at - 1] > cx[i]) { dup[at] = dup[at - 1]; --at; }
+        dup[at] = cx[i];
+      }
+    }
+    if (nd == 0) break;
+    for (int d = 0; d < nd; ++d) {
+      bool first = true;
+      for (int i = 0; i < m; ++i) {
+        if (cx[i] == dup[d]) {
+          if (!first) cx[i] += step;
+          first = false;
+        }
+      }
+    }
+  }
+  // segment chain with the sigma_map slot walk (signal_reconstruction.py:22-36)
+  P.invalid = 0;
+  P.nseg = m > 0 ? m - 1 : 0;
+  int slot = 0, total = 0;
+  const double lo = xt[0], hi = xt[nt - 1];
+  for (int i = 0; i + 1 < m; ++i) {
+    P.x0[i] = cx[i]; P.y0[i] = cy[i]; P.x1[i] = cx[i + 1]; P.y1[i] = cy[i + 1];
+    if (slot > 11) { P.invalid = 1; slot = 11; }      // sigma_map[slot] would raise IndexError
+    P.slot[i] = slot;
+    P.forced[i] = 0;
+    while (true) {
+      if (slot + 1 > 12) { P.invalid = 1; break; }    // nan_mask[slot + 1] would raise IndexError
+      if (!missing[slot + 1]) break;
+      P.forced[i] = 1;
+      ++slot;
+    }
+    const bool emit = (cx[i + 1] - cx[i] > 1.0) && (cx[i + 1] > lo) && (cx[i] < hi);
+    const int g0 = (int)cx[i], g1 = (int)cx[i + 1];   // int(): truncation toward zero
+    const int np = emit && g1 > g0 ? g1 - g0 : 0;
+    if (emit && np <= 0) P.invalid = 1;           // gaussian_line on an empty grid raises in the reference
+    P.emit[i] = emit && np > 0;
+    P.gx0[i] = g0;
+    P.npts[i] = np;
+    P.start[i] = total;
+    total += np;
+    ++slot;
+  }
+  P.total = total;
+  if (total == 0) P.invalid = 1;                       // np.interp on an empty signal raises
+}
+
+__global__ void __launch_bounds__(K5_NT) k5_recon(const double* __restrict__ fx, const double* __restrict__ fy,
+                                                  const double* __restrict__ baseline, const float* __restrict__ target,
+                                                  long long n_beats, const double* __restrict__ xt, int nt,
+                                                  const double* __restrict__ cand, long long n_cand,
+                                                  double* __restrict__ partial, double* __restrict__ pred_out) {
+  __shared__ BeatPlan P;
+  __shared__ SegCand SC[K5_CT][K5_NSEG];
+  __shared__ double s_red[K5_CT][K5_NT / 32];
+  __shared__ double s_sig[K5_CT][12];
+  const int k = threadIdx.x, lane = k & 31, warp = k >> 5;
+  double* my_row = partial + (long long)blockIdx.x * n_cand;
+  for (long long c = k; c < n_cand; c += K5_NT) my_row[c] = 0.0;
+  const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+  const double x = k < nt ? xt[k] : 0.0;
+
+  for (long long beat = blockIdx.x; beat < n_beats; beat += gridDim.x) {
+    __syncthreads();
+    if (k == 0) build_plan(fx + 11 * beat, fy + 11 * beat, baseline[beat], xt, nt, P);
+    __syncthreads();
+    const float tgt = (k < nt && target) ? target[beat * nt + k] : 0.f;
+    // ---- sigma-independent placement of output sample k (np.interp over np.linspace)
+    int ja = -1, jb = -1, sa = 0, sb = 0;             // grid indices / segments of the two bracketing points
+    double dxa = 0.0, dxb = 0.0;                      // grid x minus mu of the segment
+    double t1 = 0.0, den = 1.0;
+    const int total = P.total;
+    if (!P.invalid && k < nt) {
+      const double start = xt[0], stop = xt[nt - 1];
+      if (total == 1) { ja = 0; }
+      else {
+        const double stepv = (stop - start) / (double)(total - 1);
+        auto xp = [&](int j) { return j == total - 1 ? stop : (double)j * stepv + start; };
+        int j = (int)floor((x - start) / stepv);
+        j = j < 0 ? 0 : (j > total - 1 ? total - 1 : j);
+        while (j > 0 && xp(j) > x) --j;
+        while (j + 1 < total && xp(j + 1) <= x) ++j;
+        ja = j;
+        if (j < total - 1 && xp(j) != x) { jb = j + 1; t1 = x - xp(j); den = xp(j + 1) - xp(j); }
+      }
+      for (int s = 0; s < P.nseg; ++s) {
+        if (!P.emit[s]) continue;
+        if (ja >= P.start[s] && ja < P.start[s] + P.npts[s]) sa = s;
+        if (jb >= P.start[s] && jb < P.start[s] + P.npts[s]) sb = s;
+      }
+      const double mua = P.y1[sa] > P.y0[sa] ? P.x1[sa] : P.x0[sa];
+      const double mub = P.y1[sb] > P.y0[sb] ? P.x1[sb] : P.x0[sb];
+      dxa = (double)(P.gx0[sa] + (ja - P.start[sa])) - mua;
+      dxb = (double)(P.gx0[sb] + (jb - P.start[sb])) - mub;
+    }
+
+    for (long long c0 = 0; c0 < n_cand; c0 += K5_CT) {
+      const int nc = (int)(n_cand - c0 < K5_CT ? n_cand - c0 : K5_CT);
+      if (k < K5_CT * 12) {
+        const int ci = k / 12, si = k - 12 * ci;
+        if (ci < nc) s_sig[ci][si] = cand[(c0 + ci) * 12 + si];
+      }
+      __syncthreads();
+      // ---- per (candidate, segment): end values of the raw Gaussian and the rescale
+      if (k < K5_CT * K5_NSEG) {
+        const int ci = k / K5_NSEG, s = k - K5_NSEG * ci;
+        if (ci < nc && s < P.nseg && P.emit[s]) {
+          const double xa = P.x0[s], xb = P.x1[s], ya = P.y0[s], yb = P.y1[s];
+          const double width = fabs(xb - xa);
+          const double sg = P.forced[s] ? width / 1.0 : width / s_sig[ci][P.slot[s]];
+          const double amp = ya > yb ? ya : yb;          // max(y1, y2)
+          const bool rising = yb > ya;
+          const double mu = rising ? xb : xa;
+          const double two_s2 = 2.0 * (sg * sg);
+          const double gfirst_x = (double)P.gx0[s] - mu, glast_x = (double)(P.gx0[s] + P.npts[s] - 1) - mu;
+          const double gf = amp * exp(-(gfirst_x * gfirst_x) / two_s2);
+          const double gl = amp * exp(-(glast_x * glast_x) / two_s2);
+          SegCand q;
+          q.inv2s2 = two_s2; q.amp = amp; q.mu = mu;
+          if (rising) { q.c0 = gf; q.num = yb - ya; q.den = gl - gf; q.off = ya; }
+          else { q.c0 = gl; q.num = ya - yb; q.den = gf - gl; q.off = yb; }
+          SC[ci][s] = q;
+        }
+      }
+      __syncthreads();
+      // ---- my sample for each candidate of the tile
+      double acc[K5_CT];
+#pragma unroll
+      for (int ci = 0; ci < K5_CT; ++ci) {
+        acc[ci] = 0.0;
+        if (ci < nc && k < nt) {
+          double pred = qnan;
+          if (!P.invalid) {
+            const SegCand& qa = SC[ci][sa];
+            const double ga = qa.amp * exp(-(dxa * dxa) / qa.inv2s2);
+            const double fa = (ga - qa.c0) * qa.num / qa.den + qa.off;
+            pred = fa;
+            if (jb >= 0) {
+              const SegCand& qb = SC[ci][sb];
+              const double gb = qb.amp * exp(-(dxb * dxb) / qb.inv2s2);
+              const double fb = (gb - qb.c0) * qb.num / qb.den + qb.off;
+              const double slope = (fb - fa) / den;
+              pred = slope * t1 + fa;
+              if (isnan(pred)) {                         // np.interp's NaN rescue
+                pred = slope * (t1 - den) + fb;
+                if (isnan(pred) && fa == fb) pred = fa;
+              }
+            }
+          }
+          if (pred_out && c0 + ci == 0) pred_out[beat * nt + k] = pred;
+          const float d = __fsub_rn((float)pred, tgt);
+          acc[ci] = (double)__fmul_rn(d, d);
+        }
+      }
+#pragma unroll
+      for (int ci = 0; ci < K5_CT; ++ci) {
+        double v = acc[ci];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(AEW_FULL, v, o);
+        if (lane == 0) s_red[ci][warp] = v;
+      }
+      __syncthreads();
+      if (k < nc) {
+        double v = 0.0;
+        for (int w2 = 0; w2 < K5_NT / 32; ++w2) v += s_red[k][w2];
+        my_row[c0 + k] += v;
+      }
+    }
+  }
+}
+
+__global__ void k5_reduce(const double* __restrict__ partial, int n_rows, long long n_cand, double* __restrict__ sse) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cand) return;
+  double s = 0.0;
+  for (int r = 0; r < n_rows; ++r) s += partial[(long long)r * n_cand + c];
+  sse[c] = s;
+}
+
+int k5_grid(long long n_beats) {
+#ifdef AEW_EMUL
+  const long long cap = 2;
+#else
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long cap = (long long)sms * 4;
+#endif
+  return (int)(n_beats < cap ? (n_beats > 0 ? n_beats : 1) : cap);
+}
+
+}  // namespace
+
+extern "C" size_t aew_recon_workspace_bytes(long long n_beats, long long n_cand) {
+  return (size_t)k5_grid(n_beats) * (size_t)n_cand * sizeof(double) + 256;
+}
+
+// fx, fy: [n_beats][11] float64 (NaN = missing fiducial) in the order of
+// analysis_performance_traditional_vs_ae.py:40-44; baseline [n_beats]; target
+// [n_beats][n_t] float32 (may be NULL when only d_pred is wanted); xt [n_t] beat time
+// axis in ms; cand [n_cand][12] sigma maps; sse [n_cand] out: sum over beats and
+// samples of (float32(pred) - target)^2.  d_pred (optional) receives the float64
+// reconstructions [n_beats][n_t] of candidate 0.
+extern "C" int aew_recon_sse_f64(const double* d_fx, const double* d_fy, const double* d_baseline,
+                                 const float* d_target, long long n_beats, const double* d_xt, int n_t,
+                                 const double* d_cand, long long n_cand, double* d_sse, double* d_pred,
+                                 void* d_ws, size_t ws_bytes, void* stream) {
+  if (!d_fx || !d_fy || !d_baseline || !d_xt || !d_cand || !d_sse || !d_ws || n_beats < 0 || n_cand < 1)
+    return AEW_ERR_ARG;
+  if (n_t < 2 || n_t > K5_NT) return AEW_ERR_UNSUPPORTED;
+  if (ws_bytes < aew_recon_workspace_bytes(n_beats, n_cand)) return AEW_ERR_WORKSPACE;
+  const int grid = k5_grid(n_beats);
+  double* partial = (double*)(((size_t)d_ws + 127) & ~(size_t)127);
+  cudaStream_t st = (cudaStream_t)stream;
+  AEW_LAUNCH(k5_recon, grid, K5_NT, 0, st, d_fx, d_fy, d_baseline, d_target, n_beats, d_xt, n_t, d_cand, n_cand,
+             partial, d_pred);
+  AEW_LAUNCH(k5_reduce, (unsigned)((n_cand + 127) / 128), 128, 0, st, (const double*)partial, grid, n_cand, d_sse);
+  return (int)cudaGetLastError();
+}

@@ -1,0 +1,146 @@
+/* aewave.h -- C ABI of libaewave.so, the B200 (sm_100a) implementation of the
+ * ae_waveforms preprocessing hot path.
+ *
+ * The reference (Computational-Biology-TUe/ae_waveforms) is pure Python and has no
+ * FFI; its boundary for this path is the Python import surface
+ * (data_load_preprocess.*, functions_traditional.signal_reconstruction).  Each
+ * entry point below names the reference function(s) it replaces; the Python
+ * mirror in ae_waveforms_b200/ (and dropin/) binds them with ctypes, see
+ * INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes only.  Pointers marked `d_` / "device"
+ * are CUDA device pointers owned by the caller (PyTorch tensors on the Python
+ * side); `h_` are host pointers.  Calls are stateless, stream-ordered on
+ * `stream` (a cudaStream_t passed as void*), never allocate, free or
+ * synchronise, and return 0 on success, a negative AEW_ERR_* code for argument
+ * errors or a positive cudaError_t.  Device-side conditions (workspace overflow)
+ * are reported through a status word in the workspace / params, read back by the
+ * caller after the stream drains.  Ragged batches are one flat float64 array of
+ * all records back to back plus int64 offsets rec_off[n_rec + 1].
+ */
+#ifndef AEWAVE_H
+#define AEWAVE_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AEW_VERSION 100
+
+/* return codes */
+#define AEW_OK 0
+#define AEW_ERR_ARG (-1)
+#define AEW_ERR_WORKSPACE (-2)
+#define AEW_ERR_UNSUPPORTED (-3)
+#define AEW_ERR_NO_DEVICE (-4)
+/* bits of the device status word */
+#define AEW_DEV_SEG_OVERFLOW 1
+#define AEW_DEV_TILE_OVERFLOW 2
+#define AEW_DEV_LOOKBACK_TIMEOUT 4
+#define AEW_DEV_RUN_OVERFLOW 8
+
+int aew_version(void);
+/* 0 if a CUDA device of compute capability 10.x is current, AEW_ERR_NO_DEVICE otherwise */
+int aew_device_check(void);
+
+/* ---- K1: whole-record z-score statistics --------------------------------------
+ * replaces zscore() of data_load_preprocess/filters.py:5-12 as called on the whole
+ * track at data_extract_vitaldb.py:64: mean = np.nanmean, sd = np.nanstd, both
+ * bit-identical to NumPy (pairwise summation order reproduced). */
+long long aew_zscore_plan(const long long* h_rec_beg, const long long* h_rec_end, long long n_rec,
+                          long long* h_blk_start /* [n_rec+1] out */);
+size_t aew_zscore_workspace_bytes(long long n_rec, long long n_blocks);
+/* records are [rec_beg[r], rec_end[r]) in the flat array; a contiguous batch passes (off, off + 1) */
+int aew_zscore_stats_f64(const double* d_x, const long long* d_rec_beg, const long long* d_rec_end,
+                         const long long* d_blk_start, long long n_rec, long long n_blocks, double* d_mean,
+                         double* d_sd, long long* d_count /* non-NaN per record, may be NULL */, void* d_ws,
+                         size_t ws_bytes, void* stream);
+/* out[i] = (x[i] - mean[r]) / sd[r] over flat positions [lo, hi); NaN propagates, NaN between records */
+int aew_zscore_apply_f64(const double* d_x, const long long* d_rec_beg, const long long* d_rec_end, long long n_rec,
+                         const double* d_mean, const double* d_sd, double* d_out, long long lo, long long hi,
+                         void* stream);
+/* leading/trailing all-NaN trim of data_extract_vitaldb.py:53-57:
+ * d_trimmed[2r] = first non-NaN position, d_trimmed[2r+1] = one past the last (equal if all NaN) */
+int aew_trim_nan_edges_f64(const double* d_x, const long long* d_rec_beg, const long long* d_rec_end, long long n_rec,
+                           long long* d_trimmed, void* stream);
+
+/* ---- K2: zero-phase IIR filtering per non-NaN segment ----------------------------
+ * replaces butterworth() of data_load_preprocess/filters.py:15-55
+ * (= scipy.signal.filtfilt(b, a, seg) per maximal non-NaN segment longer than
+ * 3*max(len(a),len(b)); shorter segments copied; NaN stays NaN).  Filter design
+ * (scipy.signal.butter, lfilter_zi) stays on the host so b, a, zi carry SciPy's bits. */
+long long aew_filt_tables_len(void);
+int aew_filt_tables(const double* h_b, const double* h_a, const double* h_zi, int order, double* h_tab /* out */);
+long long aew_filt_max_tiles(long long n_rec, long long total_samples, long long max_seg);
+size_t aew_filt_workspace_bytes(long long n_rec, long long total_samples, long long max_seg);
+int aew_segments_find_f64(const double* d_x, const long long* d_rec_beg, const long long* d_rec_end,
+                          long long n_rec, long long total_samples,
+                          const long long* d_nonnan_count /* may be NULL */, double* d_nan_fill /* may be NULL */,
+                          void* d_ws, size_t ws_bytes, long long max_seg, void* stream);
+/* mode 0: tiled block scan (within 1e-6 relative of SciPy; measured ~1e-9);
+ * mode 1: literal sequential DF2T order, bit-identical to SciPy (parity suite). */
+int aew_filtfilt_f64(const double* d_src, const double* d_mean /* may be NULL */, const double* d_sd,
+                     double* d_out, double* d_tmp, const double* d_tab, long long n_rec, long long total_samples,
+                     void* d_ws, size_t ws_bytes, long long max_seg, int mode, void* stream);
+/* device address of the 8 x int64 workspace header: [0] segments found, [1] tiles, [4] status bits */
+int aew_filt_header(void* d_ws, long long** d_header_out);
+
+/* ---- K3 + K4: window screen and median beat ----------------------------------------
+ * replaces, per 20 s window: the per-window zscore (data_extract_vitaldb.py:93),
+ * remove_samples() (data_load_preprocess/remove_samples.py:8-82, including
+ * nk.ecg_findpeaks, estimate_hr :85-107 and rmssd :110-121) and
+ * compute_median_sample_ecg() (data_load_preprocess/median_sample.py:6-54). */
+typedef struct K3Params {
+  const double* y;            /* device: filtered samples, flat */
+  const long long* win_start; /* device: [n_win] flat offset of each window (sample_from_record.py:19-30) */
+  long long n_win;
+  int L;                      /* samples per window (fs * sample_length) */
+  int smooth_k, avg_k;        /* rint(0.1 fs), rint(0.75 fs) */
+  int refractory;             /* rint(0.3 fs) */
+  int pre, post;              /* 106, 214 (median_sample.py:20-25) */
+  double hr_num;              /* 60 * fs */
+  double rr_div;              /* fs * 1000 (remove_samples.py:119) */
+  double hr_lo, hr_hi, pvc_threshold, sd_threshold;   /* 30, 180, 150, 0.05 */
+  int mode;                   /* 0 fast + exact fallback on hazard windows, 1 exact everywhere, 2 fast only */
+  int zscore_windows;         /* 1: z-score each window first (data_extract_vitaldb.py:93); 0: windows are
+                                 already z-scored by the caller (the remove_samples() drop-in) */
+  unsigned char* keep;        /* device outputs, one entry per window */
+  unsigned char* has_nan;
+  int* n_peaks;
+  int* peaks;                 /* [n_win][aew_windows_max_peaks()], -1 padded */
+  double* stats;              /* [n_win][4]: ecg_hr, ecg_hrv_rmssd, ecg_sd, ecg_sd/hr */
+  double* median;             /* [n_win][320] float64 median beat of kept windows (may be NULL) */
+  float* waves;               /* [n_win][320] float32 copy = np_waves rows (may be NULL) */
+  double* zwin;               /* [n_win][L] z-scored windows = 'ecg_sample' column (may be NULL) */
+  int* status;                /* device status word */
+  unsigned long long* hazard_count; /* device counter of windows that took the exact fallback (may be NULL) */
+} K3Params;
+int aew_windows_max_peaks(void);
+int aew_windows_max_len(void);
+int aew_windows_beats_f64(const K3Params* h_params, void* stream);
+/* compute_median_sample_ecg for given peaks: windows [n_win][L], peaks CSR; aligned may be NULL */
+int aew_median_beats_f64(const double* d_windows, long long n_win, int L, const int* d_peaks,
+                         const long long* d_peak_off, int max_peaks_per_window, int pre, int post,
+                         double* d_median, double* d_aligned, void* stream);
+
+/* ---- K5: Gaussian fiducial reconstruction + sigma-map search objective --------------
+ * replaces gaussian_line / extract_coordinates / reconstruct_gaussian
+ * (functions_traditional/signal_reconstruction.py:5-81) and objective_function
+ * (analysis_performance_traditional_vs_ae.py:63-90) for n_cand sigma maps at once.
+ *   d_fx, d_fy   [n_beats][11] float64 fiducials (NaN = missing), order of analysis_...:40-44
+ *   d_target     [n_beats][n_t] float32 targets (may be NULL if only d_pred is wanted)
+ *   d_xt         [n_t] beat time axis in ms (analysis_...:48), n_t <= 320
+ *   d_cand       [n_cand][12] float64 sigma maps
+ *   d_sse        [n_cand] out: sum over beats and samples of (float32(pred) - target)^2
+ *   d_pred       optional [n_beats][n_t] float64 reconstruction for candidate 0 */
+size_t aew_recon_workspace_bytes(long long n_beats, long long n_cand);
+int aew_recon_sse_f64(const double* d_fx, const double* d_fy, const double* d_baseline, const float* d_target,
+                      long long n_beats, const double* d_xt, int n_t, const double* d_cand, long long n_cand,
+                      double* d_sse, double* d_pred, void* d_ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AEWAVE_H */

@@ -86,7 +86,7 @@ def main():
 
     # ---- screening (remove_samples) on windows with different fates
     rng = np.random.default_rng(7)
-    wins = []
+    wins, raws = [], []
     a = ecg_synth.synth_case(2, 50000)                      # regular case
     b = ecg_synth.synth_case(3, 30000, hr_bpm=60.0, jitter=0.0)   # 20 beats / window hazard (appendix C.1)
     c = ecg_synth.synth_case(4, 30000, hr_bpm=27.0)         # HR < 30  -> removed
@@ -100,9 +100,11 @@ def main():
         f = F.butterworth(F.butterworth(z, "high", 1), "low", 30)
         filtered.append(f)
         s, idx = S.sample_from_record(f[:, None], TRACKS, 500, 20)
+        raws.append(s[:, :, 0].copy())
         s[:, :, 0] = np.apply_along_axis(F.zscore, 1, s[:, :, 0])
         wins.append(s[:, :, 0])
     wins = np.concatenate(wins, axis=0)
+    raws = np.concatenate(raws, axis=0)
     idx = (np.arange(len(wins)) + 1).reshape(-1, 1) * 10000
     df = R.remove_samples(wins[:, :, None].copy(), idx, TRACKS, 500, 150)
     kept_rows = (np.array([int(v[0]) for v in df["indices_samples"]]) // 10000) - 1
@@ -121,7 +123,7 @@ def main():
         all_sd.append(np.std(w))
     apk, apk_off = ragged(all_pk, np.int64)
     med = np.stack([M.compute_median_sample_ecg(s_, p_, 500) for s_, p_ in zip(df["ecg_sample"], df["ECG_R_Peaks"])])
-    save("screen", windows=wins, kept_rows=kept_rows, kept_peaks=pk, kept_peaks_off=pk_off,
+    save("screen", windows=wins, windows_unscaled=raws, kept_rows=kept_rows, kept_peaks=pk, kept_peaks_off=pk_off,
          kept_hr=df["ecg_hr"].to_numpy(), kept_rmssd=df["ecg_hrv_rmssd"].to_numpy(),
          kept_sd=df["ecg_sd"].to_numpy(), kept_sd_per_beat=df["ecg_sd/hr"].to_numpy(),
          all_peaks=apk, all_peaks_off=apk_off, all_hr=np.array(all_hr), all_rmssd=np.array(all_rm),
