@@ -1,0 +1,305 @@
+"""Device-resident batched API of the preprocessing hot path.
+
+This is the throughput path: many cases per launch, every buffer a CUDA tensor,
+kernels called through the C ABI (``_cabi``).  The per-call drop-in functions in
+``ae_waveforms_b200.data_load_preprocess`` are thin wrappers over the same calls.
+
+Pipeline of ``Preprocessor.run`` = data_extract_vitaldb.py:53-106 for a batch:
+
+    trim all-NaN edges (:53-57)            aew_trim_nan_edges_f64
+    whole-record z-score statistics (:64)  aew_zscore_stats_f64        (K1)
+    NaN-delimited segments                 aew_segments_find_f64
+    high-pass, low-pass filtfilt (:66-76)  aew_filtfilt_f64 x 2        (K2; z-score fused into the load)
+    20 s windows (:85-86)                  window table built on the host (index arithmetic only)
+    per-window z-score, R-peaks, screen,
+    median beat (:93-106)                  aew_windows_beats_f64       (K3 + K4)
+    np_waves / np_info rows                compaction of the kept windows (data_create_arrays.py:41-46)
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _cabi
+
+BEAT_LEN, BEAT_PRE, BEAT_POST = 320, 106, 214
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _np_ptr(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+@dataclass
+class FilterDesign:
+    """Host-side design (SciPy, so b, a, zi carry SciPy's bits) + device table."""
+    btype: str
+    cutoff_hz: float
+    fs: float
+    order: int
+    b: np.ndarray = field(repr=False, default=None)
+    a: np.ndarray = field(repr=False, default=None)
+    zi: np.ndarray = field(repr=False, default=None)
+    table: object = field(repr=False, default=None)     # torch tensor on the device
+    fast_ok: bool = True
+
+    @property
+    def padlen(self) -> int:
+        return 3 * max(len(self.a), len(self.b))
+
+
+_design_cache: dict = {}
+
+
+def design_filter(btype: str, cutoff_hz: float, fs: float = 500, order: int = 4, device=None) -> FilterDesign:
+    """filters.py:29-31 -- butter(N, Wn, btype) in (b, a) form, plus lfilter_zi."""
+    torch, lib = _cabi.require_cuda()
+    device = torch.device(device or "cuda")
+    key = (btype, float(cutoff_hz), float(fs), int(order), str(device))
+    if key in _design_cache:
+        return _design_cache[key]
+    from scipy.signal import butter, lfilter_zi
+    b, a = butter(N=order, Wn=cutoff_hz / (0.5 * fs), btype=btype, analog=False)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    zi = np.ascontiguousarray(lfilter_zi(b, a), dtype=np.float64)
+    if len(b) != len(a) or len(a) - 1 > 4:
+        raise _cabi.AewError("only low/high-pass designs up to order 4 are supported")
+    tab = np.zeros(int(lib.aew_filt_tables_len()), dtype=np.float64)
+    rc = lib.aew_filt_tables(_np_ptr(b), _np_ptr(a), _np_ptr(zi), len(a) - 1, _np_ptr(tab))
+    if rc not in (0, -3):
+        _cabi.check(rc, "aew_filt_tables")
+    d = FilterDesign(btype, cutoff_hz, fs, order, b, a, zi, torch.from_numpy(tab).to(device), fast_ok=(rc == 0))
+    _design_cache[key] = d
+    return d
+
+
+def window_count(n_rows: int, L: int) -> int:
+    """len(np.arange(L, n_rows, L)) -- sample_from_record.py:21 (exclusive stop)."""
+    return max(0, (int(n_rows) - 1) // L) if n_rows > L else 0
+
+
+class RecordBatch:
+    """A ragged batch: one flat float64 CUDA tensor + host offsets."""
+
+    def __init__(self, flat, rec_off: np.ndarray, case_ids=None):
+        self.flat = flat
+        self.rec_off = np.ascontiguousarray(rec_off, dtype=np.int64)
+        n = len(self.rec_off) - 1
+        self.case_ids = np.arange(n, dtype=np.int64) if case_ids is None else np.asarray(case_ids, dtype=np.int64)
+
+    @classmethod
+    def from_host(cls, records, case_ids=None, device=None, pinned=None):
+        """records: list of 1-D float arrays (one lead each).  ``pinned`` may be a
+        pre-filled pinned flat tensor (then ``records`` is only used for lengths)."""
+        torch, _ = _cabi.require_cuda()
+        device = torch.device(device or "cuda")
+        lens = np.array([len(r) for r in records], dtype=np.int64)
+        off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        if pinned is None:
+            host = torch.empty(int(off[-1]), dtype=torch.float64, pin_memory=True)
+            hv = host.numpy()
+            for r, s in zip(records, off[:-1]):
+                hv[s:s + len(r)] = np.asarray(r, dtype=np.float64)
+        else:
+            host = pinned
+        return cls(host.to(device, non_blocking=True), off, case_ids)
+
+    @property
+    def n_rec(self) -> int:
+        return len(self.rec_off) - 1
+
+    @property
+    def total(self) -> int:
+        return int(self.rec_off[-1])
+
+
+class Preprocessor:
+    """filter -> windows -> R-peaks -> screen -> median beat for a RecordBatch."""
+
+    def __init__(self, fs: int = 500, sample_length: int = 20, hp: float = 1, lp: float = 30, order: int = 4,
+                 pvc_threshold: float = 150, sd_threshold: float = 0.05, filter_mode: str = "fast",
+                 screen_mode: str = "auto", max_segments: int | None = None, device=None):
+        self.torch, self.lib = _cabi.require_cuda()
+        self.device = self.torch.device(device or "cuda")
+        self.fs, self.L = int(fs), int(fs * sample_length)
+        self.hp, self.lp, self.order = hp, lp, order
+        self.pvc_threshold, self.sd_threshold = float(pvc_threshold), float(sd_threshold)
+        self.filter_mode = {"fast": 0, "exact": 1}[filter_mode]
+        self.screen_mode = {"auto": 0, "exact": 1, "fast": 2}[screen_mode]
+        self.max_segments = max_segments
+        self.launches = 0
+        if self.L > self.lib.aew_windows_max_len():
+            raise _cabi.AewError(f"window of {self.L} samples exceeds the kernel limit")
+
+    # ------------------------------------------------------------------ stages
+    def _ranges(self, batch: RecordBatch, trim: bool):
+        torch, lib = self.torch, self.lib
+        off = torch.from_numpy(batch.rec_off).to(self.device)
+        beg_h, end_h = batch.rec_off[:-1].copy(), batch.rec_off[1:].copy()
+        if trim and batch.n_rec:
+            trimmed = torch.empty(2 * batch.n_rec, dtype=torch.int64, device=self.device)
+            _cabi.check(lib.aew_trim_nan_edges_f64(_ptr(batch.flat), _ptr(off), _ptr(off[1:]), batch.n_rec,
+                                                   _ptr(trimmed), _cabi.stream_ptr(torch)), "trim")
+            self.launches += 1
+            t = trimmed.cpu().numpy().reshape(-1, 2)           # the one small D2H sync of the pipeline
+            beg_h, end_h = np.ascontiguousarray(t[:, 0]), np.ascontiguousarray(t[:, 1])
+        rng = torch.from_numpy(np.stack([beg_h, end_h])).to(self.device)
+        return beg_h, end_h, rng[0].contiguous(), rng[1].contiguous()
+
+    def zscore_stats(self, flat, beg_h, end_h, d_beg, d_end):
+        """K1: per-record mean, sd (NumPy bits) and non-NaN count."""
+        torch, lib = self.torch, self.lib
+        n_rec = len(beg_h)
+        blk = np.zeros(n_rec + 1, dtype=np.int64)
+        n_blocks = int(lib.aew_zscore_plan(_np_ptr(beg_h), _np_ptr(end_h), n_rec, _np_ptr(blk)))
+        d_blk = torch.from_numpy(blk).to(self.device)
+        mean = torch.empty(n_rec, dtype=torch.float64, device=self.device)
+        sd = torch.empty_like(mean)
+        cnt = torch.empty(n_rec, dtype=torch.int64, device=self.device)
+        ws_bytes = int(lib.aew_zscore_workspace_bytes(n_rec, n_blocks))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+        _cabi.check(lib.aew_zscore_stats_f64(_ptr(flat), _ptr(d_beg), _ptr(d_end), _ptr(d_blk), n_rec, n_blocks,
+                                             _ptr(mean), _ptr(sd), _ptr(cnt), _ptr(ws), ws_bytes,
+                                             _cabi.stream_ptr(torch)), "zscore_stats")
+        self.launches += 4
+        return mean, sd, cnt
+
+    def filter_records(self, flat, beg_h, end_h, d_beg, d_end, mean=None, sd=None, cnt=None, out=None, tmp=None):
+        """K2: z-score (fused) + high-pass + low-pass per NaN-delimited segment.
+        Returns (filtered, device header tensor)."""
+        torch, lib = self.torch, self.lib
+        n_rec, total = len(beg_h), flat.numel()
+        max_seg = self.max_segments or (4 * n_rec + 4096)
+        ws_bytes = int(lib.aew_filt_workspace_bytes(n_rec, total, max_seg))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+        y = torch.empty_like(flat) if out is None else out
+        tmp = torch.empty_like(flat) if tmp is None else tmp
+        st = _cabi.stream_ptr(torch)
+        _cabi.check(lib.aew_segments_find_f64(_ptr(flat), _ptr(d_beg), _ptr(d_end), n_rec, total, _ptr(cnt), _ptr(y),
+                                              _ptr(ws), ws_bytes, max_seg, st), "segments_find")
+        self.launches += 1
+        stages = [d for d in (self.hp and design_filter("high", self.hp, self.fs, self.order, self.device),
+                              self.lp and design_filter("low", self.lp, self.fs, self.order, self.device)) if d]
+        src, m, s = flat, mean, sd
+        for d in stages:
+            if self.filter_mode == 0 and not d.fast_ok:
+                raise _cabi.AewError(f"{d}: no modal form; use filter_mode='exact'")
+            _cabi.check(lib.aew_filtfilt_f64(_ptr(src), _ptr(m), _ptr(s), _ptr(y), _ptr(tmp), _ptr(d.table), n_rec,
+                                             total, _ptr(ws), ws_bytes, max_seg, self.filter_mode, st), "filtfilt")
+            self.launches += 1 if self.filter_mode else 2
+            src, m, s = y, None, None
+        if not stages:                                       # both cut-offs falsy: z-score only
+            if mean is not None:
+                _cabi.check(lib.aew_zscore_apply_f64(_ptr(flat), _ptr(d_beg), _ptr(d_end), n_rec, _ptr(mean),
+                                                     _ptr(sd), _ptr(y), 0, total, st), "zscore_apply")
+                self.launches += 1
+            else:
+                y.copy_(flat)
+        off = (-ws.data_ptr()) % 128
+        header = ws[off:off + 64].view(torch.int64)
+        return y, header
+
+    def window_table(self, beg_h, end_h, case_ids):
+        """sample_from_record.py:19-30 as index arithmetic: flat start, case and end
+        index of every window."""
+        L = self.L
+        counts = np.array([window_count(e - b, L) for b, e in zip(beg_h, end_h)], dtype=np.int64)
+        n_win = int(counts.sum())
+        rec_of = np.repeat(np.arange(len(counts)), counts)
+        first = np.concatenate([[0], np.cumsum(counts)])[:-1]
+        k = np.arange(n_win) - np.repeat(first, counts)
+        start = beg_h[rec_of] + k * L if n_win else np.zeros(0, np.int64)
+        return (np.ascontiguousarray(start, dtype=np.int64), np.asarray(case_ids)[rec_of] if n_win else np.zeros(0, np.int64),
+                ((k + 1) * L).astype(np.int64))
+
+    def screen_windows(self, y, win_start_h, want_median=True, want_zwin=False, zscore_windows=True,
+                       pvc_threshold=None, sd_threshold=None, L=None):
+        """K3 + K4 on the windows whose flat offsets are given."""
+        torch, lib = self.torch, self.lib
+        L = L or self.L
+        n_win = len(win_start_h)
+        maxp = lib.aew_windows_max_peaks()
+        dev = self.device
+        out = dict(
+            keep=torch.zeros(n_win, dtype=torch.uint8, device=dev),
+            has_nan=torch.zeros(n_win, dtype=torch.uint8, device=dev),
+            n_peaks=torch.zeros(n_win, dtype=torch.int32, device=dev),
+            peaks=torch.empty((n_win, maxp), dtype=torch.int32, device=dev),
+            stats=torch.empty((n_win, 4), dtype=torch.float64, device=dev),
+            median=torch.empty((n_win, BEAT_LEN), dtype=torch.float64, device=dev) if want_median else None,
+            waves=torch.empty((n_win, BEAT_LEN), dtype=torch.float32, device=dev) if want_median else None,
+            zwin=torch.empty((n_win, L), dtype=torch.float64, device=dev) if want_zwin else None,
+            status=torch.zeros(1, dtype=torch.int32, device=dev),
+            hazards=torch.zeros(1, dtype=torch.int64, device=dev))
+        if n_win == 0:
+            return out
+        d_start = torch.from_numpy(np.ascontiguousarray(win_start_h, dtype=np.int64)).to(dev)
+        fs = self.fs
+        p = _cabi.K3Params(
+            y=y.data_ptr(), win_start=d_start.data_ptr(), n_win=n_win, L=L,
+            smooth_k=int(np.rint(0.1 * fs)), avg_k=int(np.rint(0.75 * fs)), refractory=int(np.rint(0.3 * fs)),
+            pre=BEAT_PRE, post=BEAT_POST, hr_num=float(60 * fs), rr_div=float(fs * 1000), hr_lo=30.0, hr_hi=180.0,
+            pvc_threshold=float(self.pvc_threshold if pvc_threshold is None else pvc_threshold),
+            sd_threshold=float(self.sd_threshold if sd_threshold is None else sd_threshold),
+            mode=self.screen_mode, zscore_windows=1 if zscore_windows else 0,
+            keep=out["keep"].data_ptr(), has_nan=out["has_nan"].data_ptr(), n_peaks=out["n_peaks"].data_ptr(),
+            peaks=out["peaks"].data_ptr(), stats=out["stats"].data_ptr(),
+            median=out["median"].data_ptr() if want_median else None,
+            waves=out["waves"].data_ptr() if want_median else None,
+            zwin=out["zwin"].data_ptr() if want_zwin else None,
+            status=out["status"].data_ptr(), hazard_count=out["hazards"].data_ptr())
+        _cabi.check(lib.aew_windows_beats_f64(ctypes.byref(p), _cabi.stream_ptr(torch)), "windows_beats")
+        self.launches += 1
+        out["_win_start"] = d_start
+        return out
+
+    # ------------------------------------------------------------------ whole path
+    def run(self, batch: RecordBatch, trim: bool = True, keep_intermediates: bool = False,
+            scratch: dict | None = None) -> dict:
+        """Returns a dict of CUDA tensors: ``np_waves`` (n_keep, 320) float32,
+        ``np_info`` (n_keep, 2) float64 = [case_id, idx_end], ``medians`` float64,
+        plus per-window ``keep`` / ``has_nan`` / ``n_peaks`` / ``peaks`` / ``stats`` and
+        counters.  ``scratch`` may hold reusable 'y' / 'tmp' tensors shaped like the input."""
+        torch = self.torch
+        flat = batch.flat
+        beg_h, end_h, d_beg, d_end = self._ranges(batch, trim)
+        mean, sd, cnt = self.zscore_stats(flat, beg_h, end_h, d_beg, d_end)
+        y, header = self.filter_records(flat, beg_h, end_h, d_beg, d_end, mean, sd, cnt,
+                                        out=(scratch or {}).get("y"), tmp=(scratch or {}).get("tmp"))
+        win_start, win_case, win_end = self.window_table(beg_h, end_h, batch.case_ids)
+        scr = self.screen_windows(y, win_start)
+        keep_idx = torch.nonzero(scr["keep"]).squeeze(1)            # sync: number of kept windows
+        hdr = header.cpu().numpy()
+        _cabi.check_device_status(int(hdr[4]), "filter")
+        _cabi.check_device_status(int(scr["status"].item()), "window screen")
+        info_h = np.stack([win_case.astype(np.float64), win_end.astype(np.float64)], axis=1) if len(win_start) \
+            else np.zeros((0, 2))
+        info = torch.from_numpy(info_h).to(self.device)
+        res = dict(np_waves=scr["waves"].index_select(0, keep_idx), medians=scr["median"].index_select(0, keep_idx),
+                   np_info=info.index_select(0, keep_idx), keep=scr["keep"], has_nan=scr["has_nan"],
+                   n_peaks=scr["n_peaks"], peaks=scr["peaks"], stats=scr["stats"], keep_idx=keep_idx,
+                   n_windows=len(win_start), n_segments=int(hdr[0]), n_tiles=int(hdr[1]),
+                   hazard_windows=int(scr["hazards"].item()), mean=mean, sd=sd,
+                   n_beats=int(scr["n_peaks"].index_select(0, keep_idx).sum().item()) if len(win_start) else 0)
+        if keep_intermediates:
+            res.update(filtered=y, rec_beg=beg_h, rec_end=end_h, win_start=win_start)
+        return res
+
+
+def process_cases(records, case_ids=None, **kwargs) -> dict:
+    """Host convenience: list of 1-D float arrays -> NumPy ``np_waves`` (n,320) f32,
+    ``np_features`` (n,35) f64 (NaN: the wave delineator is not on this path yet),
+    ``np_info`` (n,2) f64, in case-major order like data_create_arrays.py:27-48."""
+    pre = Preprocessor(**kwargs)
+    batch = RecordBatch.from_host(records, case_ids, device=pre.device)
+    res = pre.run(batch)
+    waves = res["np_waves"].cpu().numpy()
+    info = res["np_info"].cpu().numpy()
+    return dict(np_waves=waves, np_features=np.full((len(waves), 35), np.nan), np_info=info,
+                n_windows=res["n_windows"], hazard_windows=res["hazard_windows"])

@@ -263,6 +263,50 @@ __global__ void k5_reduce(const double* __restrict__ partial, int n_rows, long l
   sse[c] = s;
 }
 
+// gaussian_line (signal_reconstruction.py:5-14) for one segment: out[i], i < int(x2)-int(x1)
+__global__ void k5_gaussian_line(double x1, double y1, double x2, double y2, double s, double* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double a = y1 > y2 ? y1 : y2;
+  const bool rising = y2 > y1;
+  const double mu = rising ? x2 : x1;
+  const int g0 = (int)x1;
+  const double two_s2 = 2.0 * (s * s);
+  auto g = [&](int j) { const double d = (double)(g0 + j) - mu; return a * exp(-(d * d) / two_s2); };
+  const double gi = g(i), gf = g(0), gl = g(n - 1);
+  out[i] = rising ? (gi - gf) * (y2 - y1) / (gl - gf) + y1 : (gi - gl) * (y1 - y2) / (gf - gl) + y2;
+}
+
+// extract_coordinates (signal_reconstruction.py:45-81) for one beat: coords[0..m) x, coords[13..13+m) y,
+// meta[0] = m, meta[1..14) = nan mask
+__global__ void k5_extract(const double* __restrict__ fx, const double* __restrict__ fy, double baseline,
+                           const double* __restrict__ xt, int nt, double* __restrict__ coords, int* __restrict__ meta) {
+  __shared__ BeatPlan P;
+  if (threadIdx.x != 0) return;
+  build_plan(fx, fy, baseline, xt, nt, P);
+  const int m = P.nseg + 1;
+  int cnt = 0;
+  for (int i = 0; i < K5_NPT; ++i) {
+    const double xv = i == 0 ? xt[0] : (i == 12 ? xt[nt - 1] : fx[i - 1]);
+    const double yv = (i == 0 || i == 12) ? baseline : fy[i - 1];
+    const int miss = isnan(xv) || isnan(yv);
+    meta[1 + i] = miss;
+    cnt += !miss;
+  }
+  meta[0] = cnt;
+  if (cnt >= 2) {
+    for (int i = 0; i < m - 1; ++i) { coords[i] = P.x0[i]; coords[13 + i] = P.y0[i]; }
+    coords[m - 1] = P.x1[m - 2];
+    coords[13 + m - 1] = P.y1[m - 2];
+  } else if (cnt == 1) {
+    for (int i = 0; i < K5_NPT; ++i)
+      if (!meta[1 + i]) {
+        coords[0] = i == 0 ? xt[0] : (i == 12 ? xt[nt - 1] : fx[i - 1]);
+        coords[13] = (i == 0 || i == 12) ? baseline : fy[i - 1];
+      }
+  }
+}
+
 int k5_grid(long long n_beats) {
 #ifdef AEW_EMUL
   const long long cap = 2;
@@ -301,5 +345,22 @@ extern "C" int aew_recon_sse_f64(const double* d_fx, const double* d_fy, const d
   AEW_LAUNCH(k5_recon, grid, K5_NT, 0, st, d_fx, d_fy, d_baseline, d_target, n_beats, d_xt, n_t, d_cand, n_cand,
              partial, d_pred);
   AEW_LAUNCH(k5_reduce, (unsigned)((n_cand + 127) / 128), 128, 0, st, (const double*)partial, grid, n_cand, d_sse);
+  return (int)cudaGetLastError();
+}
+
+// gaussian_line(x1, y1, x2, y2, s): n = int(x2) - int(x1) values into d_out
+extern "C" int aew_gaussian_line_f64(double x1, double y1, double x2, double y2, double s, double* d_out, int n,
+                                     void* stream) {
+  if (!d_out || n < 0) return AEW_ERR_ARG;
+  if (n == 0) return AEW_OK;
+  AEW_LAUNCH(k5_gaussian_line, (unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream, x1, y1, x2, y2, s, d_out, n);
+  return (int)cudaGetLastError();
+}
+
+// extract_coordinates for one beat: d_fx, d_fy [11]; d_coords [26] out (x then y), d_meta [14] out
+extern "C" int aew_extract_coordinates_f64(const double* d_fx, const double* d_fy, double baseline,
+                                           const double* d_xt, int n_t, double* d_coords, int* d_meta, void* stream) {
+  if (!d_fx || !d_fy || !d_xt || !d_coords || !d_meta || n_t < 2) return AEW_ERR_ARG;
+  AEW_LAUNCH(k5_extract, 1, 32, 0, (cudaStream_t)stream, d_fx, d_fy, baseline, d_xt, n_t, d_coords, d_meta);
   return (int)cudaGetLastError();
 }

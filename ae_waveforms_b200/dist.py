@@ -1,0 +1,65 @@
+"""Case sharding across the GPUs of one box (one process per GPU, torch.distributed).
+
+The path has no data-path collective: cases are independent
+(data_extract_vitaldb.py:194-199 maps them over a process pool), so every rank runs
+the whole pipeline on its own shard.  Two collectives exist and both are tiny:
+the variable-length all-gather of the final ``np_waves`` / ``np_info`` rows, and the
+all-reduce(sum) of the per-candidate error sums of the sigma search (beats sharded).
+Works with ``nccl`` (GPU tensors) and ``gloo`` (CPU tensors, used by the CPU tests).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_cases(lengths, world_size: int, rank: int | None = None):
+    """Greedy longest-processing-time assignment of cases to ranks by sample count.
+    Returns the list of case indices per rank (or the one for ``rank``)."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    order = np.argsort(-lengths, kind="stable")
+    load = np.zeros(world_size, dtype=np.int64)
+    shards = [[] for _ in range(world_size)]
+    for i in order:
+        r = int(np.argmin(load))
+        shards[r].append(int(i))
+        load[r] += lengths[i]
+    shards = [sorted(s) for s in shards]
+    return shards if rank is None else shards[rank]
+
+
+def allgather_rows(t, group=None):
+    """Variable-length all-gather along dim 0: gathers the row counts first, pads to the
+    maximum, gathers, and strips the padding.  Returns the list of per-rank tensors."""
+    import torch
+    import torch.distributed as dist
+    ws = dist.get_world_size(group)
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    counts = [torch.zeros_like(n) for _ in range(ws)]
+    dist.all_gather(counts, n, group=group)
+    counts = [int(c.item()) for c in counts]
+    m = max(counts) if counts else 0
+    pad = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[:t.shape[0]] = t
+    bufs = [torch.empty_like(pad) for _ in range(ws)]
+    dist.all_gather(bufs, pad, group=group)
+    return [b[:c] for b, c in zip(bufs, counts)]
+
+
+def gather_beat_arrays(np_waves, np_info, group=None):
+    """All-gather the per-rank ``np_waves`` (f32) and ``np_info`` (f64) and restore the
+    case-major order of data_create_arrays.py:27-48 by sorting on (case_id, idx_end)."""
+    import torch
+    waves = torch.cat(allgather_rows(np_waves, group), dim=0)
+    info = torch.cat(allgather_rows(np_info, group), dim=0)
+    if info.shape[0]:
+        key = info[:, 0].to(torch.int64) * (1 << 40) + info[:, 1].to(torch.int64)
+        order = torch.argsort(key, stable=True)
+        waves, info = waves.index_select(0, order), info.index_select(0, order)
+    return waves, info
+
+
+def allreduce_sse(sse, group=None):
+    """Sum the per-candidate error sums of all ranks (beats sharded by rank)."""
+    import torch.distributed as dist
+    dist.all_reduce(sse, op=dist.ReduceOp.SUM, group=group)
+    return sse

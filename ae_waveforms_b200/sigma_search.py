@@ -1,0 +1,98 @@
+"""Batched sigma-map search for the Gaussian fiducial reconstruction (K5).
+
+The reference drives ``objective_function`` (analysis_performance_traditional_vs_ae.py:63-90)
+through 2,000 sequential ``skopt.gp_minimize`` calls, each a Python loop over every test
+beat.  Here the objective of MANY candidate sigma maps is evaluated in one launch;
+``best`` is the argmin over the same candidate list.  With several ranks the beats are
+sharded and the per-candidate error sums are all-reduced (``dist.allreduce_sse``).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _cabi
+
+BEAT_LEN, BEAT_PRE, BEAT_POST = 320, 106, 214
+
+
+def beat_time_axis(n: int = BEAT_LEN, fs: float = 500) -> np.ndarray:
+    """analysis_performance_traditional_vs_ae.py:48."""
+    return np.linspace(-BEAT_PRE, BEAT_POST - 1, n) / fs * 1000
+
+
+def prepare_inputs(np_waves, np_features):
+    """analysis_...:33-46 -- float32 targets (median beat minus its row maximum), the
+    ten fiducials reordered by time of occurrence with the R peak inserted at slot 5 as
+    (0, -1e-10), and the baseline = nanmean of the six on/offset amplitudes.
+    Pure index shuffling on the host; the arithmetic heavy part runs on the device."""
+    import warnings
+    waves = np.asarray(np_waves)
+    feats = np.asarray(np_features, dtype=np.float64)
+    target = (waves - waves.max(axis=1, keepdims=True)).astype(np.float32)
+    fx = np.insert(feats[:, [2, 0, 4, 8, 6, 12, 10, 16, 14, 18]], 5, 0.0, axis=1)
+    fy = np.insert(feats[:, [3, 1, 5, 9, 7, 13, 11, 17, 15, 19]], 5, -1e-10, axis=1)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        baselines = np.nanmean(feats[:, [3, 5, 9, 11, 17, 19]], axis=1)
+    return target, fx, fy, baselines
+
+
+class SigmaSearch:
+    def __init__(self, features_x, features_y, baselines, target=None, x_time=None, device=None):
+        self.torch, self.lib = _cabi.require_cuda()
+        torch = self.torch
+        self.device = torch.device(device or "cuda")
+
+        def dev(a, dt):
+            if isinstance(a, torch.Tensor):
+                return a.to(self.device, dt).contiguous()
+            return torch.from_numpy(np.ascontiguousarray(a)).to(self.device, dt).contiguous()
+
+        self.fx, self.fy = dev(features_x, torch.float64), dev(features_y, torch.float64)
+        self.baselines = dev(baselines, torch.float64)
+        self.target = None if target is None else dev(target, torch.float32)
+        self.xt = dev(beat_time_axis() if x_time is None else x_time, torch.float64)
+        self.n_beats, self.n_t = self.fx.shape[0], self.xt.numel()
+        if self.fx.shape[1] != 11 or self.fy.shape != self.fx.shape:
+            raise _cabi.AewError("features_x / features_y must be (n_beats, 11)")
+        self.launches = 0
+
+    def _call(self, cand, want_pred):
+        torch, lib = self.torch, self.lib
+        cand = cand if isinstance(cand, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(cand, dtype=np.float64))
+        cand = cand.to(self.device, torch.float64).reshape(-1, 12).contiguous()
+        n_cand = cand.shape[0]
+        sse = torch.empty(n_cand, dtype=torch.float64, device=self.device)
+        pred = torch.empty((self.n_beats, self.n_t), dtype=torch.float64, device=self.device) if want_pred else None
+        ws_bytes = int(lib.aew_recon_workspace_bytes(self.n_beats, n_cand))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+        p = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+        _cabi.check(lib.aew_recon_sse_f64(p(self.fx), p(self.fy), p(self.baselines), p(self.target), self.n_beats,
+                                          p(self.xt), self.n_t, p(cand), n_cand, p(sse), p(pred), p(ws), ws_bytes,
+                                          _cabi.stream_ptr(torch)), "recon_sse")
+        self.launches += 2
+        return sse, pred
+
+    def sse(self, candidates):
+        """Sum over beats and samples of (float32(pred) - target)^2 per candidate (CUDA tensor)."""
+        if self.target is None:
+            raise _cabi.AewError("targets are needed for the objective")
+        return self._call(candidates, False)[0]
+
+    def mse(self, candidates):
+        """The reference's loss: torch.nn.MSELoss over all beats and samples."""
+        return self.sse(candidates) / float(self.n_beats * self.n_t)
+
+    def reconstruct(self, sigma_map):
+        """(n_beats, 320) float64 reconstructions for one sigma map (analysis_...:121-132)."""
+        return self._call(np.asarray(sigma_map, dtype=np.float64).reshape(1, 12), True)[1]
+
+    def best(self, candidates, sse=None):
+        """argmin over the candidate list (NaN losses never win)."""
+        torch = self.torch
+        s = self.sse(candidates) if sse is None else sse
+        s = torch.where(torch.isnan(s), torch.full_like(s, float("inf")), s)
+        i = int(torch.argmin(s).item())
+        return i, float(s[i].item()) / float(self.n_beats * self.n_t)

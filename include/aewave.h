@@ -139,6 +139,12 @@ size_t aew_recon_workspace_bytes(long long n_beats, long long n_cand);
 int aew_recon_sse_f64(const double* d_fx, const double* d_fy, const double* d_baseline, const float* d_target,
                       long long n_beats, const double* d_xt, int n_t, const double* d_cand, long long n_cand,
                       double* d_sse, double* d_pred, void* d_ws, size_t ws_bytes, void* stream);
+/* gaussian_line(x1, y1, x2, y2, s) (signal_reconstruction.py:5-14): n = int(x2) - int(x1) values */
+int aew_gaussian_line_f64(double x1, double y1, double x2, double y2, double s, double* d_out, int n, void* stream);
+/* extract_coordinates (signal_reconstruction.py:45-81) for one beat: d_fx, d_fy [11];
+ * d_coords [26] out = x[13] then y[13]; d_meta [14] out = count, nan_mask[13] */
+int aew_extract_coordinates_f64(const double* d_fx, const double* d_fy, double baseline, const double* d_xt, int n_t,
+                                double* d_coords, int* d_meta, void* stream);
 
 #ifdef __cplusplus
 }

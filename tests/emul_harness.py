@@ -1,0 +1,157 @@
+"""ctypes harness for the HOST EMULATION build of the kernel sources
+(tests/emul/libaewave_emul.so, built from ae_waveforms_b200/csrc/*.cu with -DAEW_EMUL).
+
+Test infrastructure only: it lets the CPU test-suite execute the very kernel code that
+nvcc compiles for sm_100a (one host thread per CUDA thread) against the golden vectors,
+so that logic errors are caught before a GPU is involved.  "Device" memory is NumPy."""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.abspath(os.path.join(HERE, ".."))
+sys.path.insert(0, ROOT)
+from ae_waveforms_b200 import _cabi  # noqa: E402
+
+LL = ctypes.c_longlong
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        subprocess.run([os.path.join(HERE, "emul", "build_emul.sh")], check=True, capture_output=True)
+        _lib = _cabi.load(os.path.join(HERE, "emul", "libaewave_emul.so"))
+    return _lib
+
+
+def ptr(a):
+    return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+def flatten(records):
+    lens = [len(r) for r in records]
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    flat = np.concatenate([np.asarray(r, dtype=np.float64) for r in records]) if records else np.zeros(0)
+    return np.ascontiguousarray(flat), off
+
+
+def zscore_stats(records):
+    L = lib()
+    flat, off = flatten(records)
+    n = len(records)
+    beg, end = np.ascontiguousarray(off[:-1]), np.ascontiguousarray(off[1:])
+    blk = np.zeros(n + 1, np.int64)
+    nb = L.aew_zscore_plan(ptr(beg), ptr(end), n, ptr(blk))
+    wsb = L.aew_zscore_workspace_bytes(n, nb)
+    ws = np.zeros(wsb, np.uint8)
+    mean, sd, cnt = np.zeros(n), np.zeros(n), np.zeros(n, np.int64)
+    rc = L.aew_zscore_stats_f64(ptr(flat), ptr(beg), ptr(end), ptr(blk), n, nb, ptr(mean), ptr(sd), ptr(cnt), ptr(ws),
+                                wsb, None)
+    assert rc == 0, rc
+    return mean, sd, cnt
+
+
+def trim(records):
+    L = lib()
+    flat, off = flatten(records)
+    n = len(records)
+    out = np.zeros(2 * n, np.int64)
+    rc = L.aew_trim_nan_edges_f64(ptr(flat), ptr(np.ascontiguousarray(off[:-1])), ptr(np.ascontiguousarray(off[1:])),
+                                  n, ptr(out), None)
+    assert rc == 0
+    return out.reshape(n, 2) - off[:-1, None]
+
+
+def filter_tables(btype, fc, fs=500, order=4):
+    from scipy.signal import butter, lfilter_zi
+    L = lib()
+    b, a = butter(order, fc / (0.5 * fs), btype)
+    b, a = np.ascontiguousarray(b), np.ascontiguousarray(a)
+    zi = np.ascontiguousarray(lfilter_zi(b, a))
+    tab = np.zeros(L.aew_filt_tables_len())
+    rc = L.aew_filt_tables(ptr(b), ptr(a), ptr(zi), order, ptr(tab))
+    return tab, rc
+
+
+def filtfilt(records, stages, mode, zscore=False, max_seg=None):
+    """stages: list of (btype, fc, order).  Returns (list of outputs, header)."""
+    L = lib()
+    flat, off = flatten(records)
+    n, total = len(records), len(flat)
+    beg, end = np.ascontiguousarray(off[:-1]), np.ascontiguousarray(off[1:])
+    max_seg = max_seg or n + 64
+    wsb = L.aew_filt_workspace_bytes(n, total, max_seg)
+    ws = np.zeros(wsb + 256, np.uint8)
+    out, tmp = np.full(total, -777.0), np.zeros(total)
+    mean = sd = cnt = None
+    if zscore:
+        mean, sd, cnt = zscore_stats(records)
+    rc = L.aew_segments_find_f64(ptr(flat), ptr(beg), ptr(end), n, total, ptr(cnt), ptr(out), ptr(ws), wsb, max_seg,
+                                 None)
+    assert rc == 0, rc
+    src, m, s = flat, mean, sd
+    for btype, fc, order in stages:
+        tab, trc = filter_tables(btype, fc, 500, order)
+        assert trc == 0
+        rc = L.aew_filtfilt_f64(ptr(src), ptr(m), ptr(s), ptr(out), ptr(tmp), ptr(tab), n, total, ptr(ws), wsb,
+                                max_seg, mode, None)
+        assert rc == 0, rc
+        src, m, s = out, None, None
+    hdr = ws[(-ws.ctypes.data) % 128:][:64].view(np.int64).copy()
+    return [out[off[i]:off[i + 1]] for i in range(n)], hdr
+
+
+def screen(flat, starts, Lw=10000, mode=0, zscore_windows=True, want_z=False, fs=500, pvc=150.0, sdt=0.05):
+    L = lib()
+    flat = np.ascontiguousarray(flat, dtype=np.float64)
+    starts = np.ascontiguousarray(starts, dtype=np.int64)
+    n, maxp = len(starts), L.aew_windows_max_peaks()
+    o = dict(keep=np.zeros(n, np.uint8), has_nan=np.zeros(n, np.uint8), n_peaks=np.zeros(n, np.int32),
+             peaks=np.zeros((n, maxp), np.int32), stats=np.zeros((n, 4)), median=np.full((n, 320), -5.0),
+             waves=np.zeros((n, 320), np.float32), zwin=np.zeros((n, Lw)), status=np.zeros(1, np.int32),
+             hazards=np.zeros(1, np.uint64))
+    p = _cabi.K3Params(
+        y=flat.ctypes.data, win_start=starts.ctypes.data, n_win=n, L=Lw, smooth_k=int(np.rint(0.1 * fs)),
+        avg_k=int(np.rint(0.75 * fs)), refractory=int(np.rint(0.3 * fs)), pre=106, post=214, hr_num=60.0 * fs,
+        rr_div=fs * 1000.0, hr_lo=30.0, hr_hi=180.0, pvc_threshold=pvc, sd_threshold=sdt, mode=mode,
+        zscore_windows=1 if zscore_windows else 0, keep=o["keep"].ctypes.data, has_nan=o["has_nan"].ctypes.data,
+        n_peaks=o["n_peaks"].ctypes.data, peaks=o["peaks"].ctypes.data, stats=o["stats"].ctypes.data,
+        median=o["median"].ctypes.data, waves=o["waves"].ctypes.data, zwin=o["zwin"].ctypes.data if want_z else None,
+        status=o["status"].ctypes.data, hazard_count=o["hazards"].ctypes.data)
+    rc = L.aew_windows_beats_f64(ctypes.byref(p), None)
+    assert rc == 0, rc
+    return o
+
+
+def median_beats(window, peaks, want_aligned=True):
+    L = lib()
+    w = np.ascontiguousarray(window, dtype=np.float64)
+    pk = np.ascontiguousarray(peaks, dtype=np.int32)
+    off = np.array([0, len(pk)], np.int64)
+    med = np.zeros(320)
+    al = np.zeros((len(pk), 320)) if want_aligned else None
+    rc = L.aew_median_beats_f64(ptr(w), 1, len(w), ptr(pk), ptr(off), len(pk), 106, 214, ptr(med), ptr(al), None)
+    assert rc == 0, rc
+    return med, al
+
+
+def recon(fx, fy, bl, target, xt, cands, want_pred=False):
+    L = lib()
+    fx, fy, bl, xt = [np.ascontiguousarray(a, dtype=np.float64) for a in (fx, fy, bl, xt)]
+    target = None if target is None else np.ascontiguousarray(target, dtype=np.float32)
+    cands = np.ascontiguousarray(cands, dtype=np.float64).reshape(-1, 12)
+    nb, nc = len(fx), len(cands)
+    sse = np.zeros(nc)
+    pred = np.zeros((nb, len(xt))) if want_pred else None
+    wsb = L.aew_recon_workspace_bytes(nb, nc)
+    ws = np.zeros(wsb, np.uint8)
+    rc = L.aew_recon_sse_f64(ptr(fx), ptr(fy), ptr(bl), ptr(target), nb, ptr(xt), len(xt), ptr(cands), nc, ptr(sse),
+                             ptr(pred), ptr(ws), wsb, None)
+    assert rc == 0, rc
+    return sse, pred

@@ -1,0 +1,123 @@
+"""The CUDA kernel SOURCES, executed on host threads (tests/emul_harness.py), against
+the golden vectors frozen from the reference and against the oracle.  CPU only.
+The same assertions run on the real GPU in tests/test_gpu_parity.py."""
+import warnings
+
+import numpy as np
+import pytest
+
+import emul_harness as eh
+from conftest import unragged
+from oracle import ref_port as rp
+
+warnings.simplefilter("ignore", RuntimeWarning)
+
+
+def same(a, b):
+    return np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True)
+
+
+def test_k1_stats_bit_exact():
+    rng = np.random.default_rng(0)
+    lens = [1, 5, 8, 100, 128, 129, 1000, 4999, 10000, 30011]
+    recs = [rng.standard_normal(n) * rng.uniform(0.5, 50) + rng.uniform(-5, 5) for n in lens]
+    recs[6][3:40] = np.nan
+    recs[8][::7] = np.nan
+    recs[4][:] = np.nan
+    mean, sd, cnt = eh.zscore_stats(recs)
+    for r, m, s, c in zip(recs, mean, sd, cnt):
+        assert same(m, np.nanmean(r)) and same(s, np.nanstd(r)) and c == (~np.isnan(r)).sum()
+
+
+def test_trim_edges():
+    a = np.arange(50.0); a[:7] = np.nan; a[-3:] = np.nan
+    b = np.full(20, np.nan)
+    c = np.arange(600.0); c[:300] = np.nan; c[577:] = np.nan; c[400] = np.nan
+    t = eh.trim([a, b, c, np.arange(5.0)])
+    assert t.tolist() == [[7, 47], [0, 0], [300, 577], [0, 5]]
+
+
+def test_k2_exact_mode_is_bit_identical_to_scipy(golden):
+    g = golden("filters")
+    recs = [g["gaps_z"], g["clean_z"][:9000]]
+    outs, hdr = eh.filtfilt(recs, [("high", 1, 4)], mode=1)
+    assert same(outs[0], g["gaps_hp"]) and same(outs[1], rp.butterworth(recs[1], "high", 1))
+    assert hdr[0] == 8 and hdr[4] == 0
+    outs, _ = eh.filtfilt([g["gaps_hp"]], [("low", 30, 4)], mode=1)
+    assert same(outs[0], g["gaps_lp"])
+
+
+def test_k2_tiled_scan_within_tolerance(golden):
+    g = golden("filters")
+    recs = [g["gaps_x"], g["clean_x"][:17000]]
+    outs, hdr = eh.filtfilt(recs, [("high", 1, 4), ("low", 30, 4)], mode=0, zscore=True)
+    for out, ref in zip(outs, (g["gaps_lp"], rp.butterworth(rp.butterworth(rp.zscore(recs[1]), "high", 1), "low", 30))):
+        assert same(np.isnan(out), np.isnan(ref))
+        m = ~np.isnan(ref)
+        assert np.max(np.abs(out[m] - ref[m])) <= 1e-6 * np.max(np.abs(ref[m]))   # north_star tolerance
+        assert np.max(np.abs(out[m] - ref[m])) <= 1e-7                              # what is actually achieved
+    assert hdr[4] == 0
+
+
+def test_k2_other_orders(golden):
+    g = golden("filters")
+    xs = g["short_x"]
+    for key, st in (("short_hp05_o2", ("high", 0.5, 2)), ("short_lp40_o3", ("low", 40, 3)), ("short_lp15_o1", ("low", 15, 1))):
+        exact, _ = eh.filtfilt([xs], [st], mode=1)
+        assert same(exact[0], g[key])
+        fast, _ = eh.filtfilt([xs], [st], mode=0)
+        assert np.max(np.abs(fast[0] - g[key])) <= 1e-6 * np.max(np.abs(g[key]))
+
+
+def test_k3_e2e_golden(golden):
+    g = golden("e2e")
+    nw = int(g["n_windows"])
+    for mode in (1, 0):
+        o = eh.screen(g["filtered"], np.arange(nw) * 10000, mode=mode)
+        kept = np.flatnonzero(o["keep"])
+        assert same((kept + 1) * 10000, g["kept_idx_end"])
+        for got, want in zip([o["peaks"][i, :o["n_peaks"][i]] for i in kept], unragged(g["kept_peaks"], g["kept_peaks_off"])):
+            assert same(got, want)
+        assert same(o["median"][kept], g["medians"]) and same(o["waves"][kept], g["np_waves"])
+        assert o["status"][0] == 0
+
+
+def test_k3_screen_golden(golden):
+    g = golden("screen")
+    raw = g["windows_unscaled"]
+    sel = [0, 4, 6, 8, 10, 12, 13]                     # one window of every fate
+    o = eh.screen(raw[sel].reshape(-1), np.arange(len(sel)) * 10000, mode=0, want_z=True)
+    want_peaks = unragged(g["all_peaks"], g["all_peaks_off"])
+    for j, w in enumerate(sel):
+        assert same(o["peaks"][j, :o["n_peaks"][j]], want_peaks[w])
+        assert bool(o["keep"][j]) == (w in g["kept_rows"])
+        if not np.isnan(g["all_sd"][w]):
+            assert same(o["zwin"][j], g["windows"][w])
+            assert same(o["stats"][j, :3], [g["all_hr"][w], g["all_rmssd"][w], g["all_sd"][w]])
+        else:
+            assert o["has_nan"][j] == 1
+    # pre-scaled windows, as the remove_samples() drop-in passes them
+    o2 = eh.screen(g["windows"][sel].reshape(-1), np.arange(len(sel)) * 10000, mode=0, zscore_windows=False)
+    assert same(o2["keep"], o["keep"]) and same(o2["peaks"], o["peaks"])
+
+
+def test_k4_median_golden(golden):
+    g = golden("median")
+    for name in ("edge", "even", "odd", "one", "far_right"):
+        med, al = eh.median_beats(g["window"], g[f"{name}_peaks"])
+        assert same(med, g[f"{name}_median"]) and same(al, g[f"{name}_aligned"])
+
+
+def test_k5_recon_golden(golden):
+    g = golden("recon")
+    for k, smap in enumerate(g["sigma_maps"]):
+        _, pred = eh.recon(g["fx"], g["fy"], g["baselines"], g["test_true"], g["x_t"], smap, want_pred=True)
+        ref = g["recon"][k]
+        assert same(np.isnan(pred), np.isnan(ref))
+        assert np.nanmax(np.abs(pred - ref)) <= 1e-6 * np.nanmax(np.abs(ref))
+    sse, _ = eh.recon(g["fx"], g["fy"], g["baselines"], g["test_true"], g["x_t"], g["sigma_maps"])
+    want = np.array([rp.sigma_objective(g["fx"], g["fy"], g["baselines"], g["test_true"], m, g["x_t"])[0] for m in g["sigma_maps"]])
+    assert np.all(np.abs(sse - want) <= 1e-6 * np.abs(want))
+    mse = sse / g["test_true"].size
+    assert np.all(np.abs(mse - g["mse_torch_f32"]) <= 1e-5 * g["mse_torch_f32"])
+    assert np.argmin(sse) == np.argmin(want)

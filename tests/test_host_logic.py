@@ -1,0 +1,140 @@
+"""Host-side logic: window arithmetic, sharding, sigma-search input preparation, the
+drop-in import surface, and the two collectives on world_size-2 gloo (CPU tensors)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from ae_waveforms_b200 import dist as awd
+from ae_waveforms_b200.batched import window_count
+from ae_waveforms_b200.sigma_search import beat_time_axis, prepare_inputs
+from oracle import ecg_synth, ref_port as rp
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def test_window_count_matches_reference(golden):
+    g = golden("windows")
+    for T, cnt in zip(g["lens"], g["counts"]):
+        assert window_count(int(T), 10000) == cnt
+    for T in (0, 1, 9999, 10000, 10001, 29999, 30000, 30001, 1800000, 7200000):
+        assert window_count(T, 10000) == len(np.arange(10000, T, 10000))
+
+
+def test_time_axis_and_sigma_inputs_match_oracle(golden):
+    g = golden("recon")
+    assert np.array_equal(beat_time_axis(), g["x_t"])
+    rng = np.random.default_rng(3)
+    waves = rng.standard_normal((7, 320)).astype(np.float32)
+    feats = rng.standard_normal((7, 35))
+    feats[2, 3] = np.nan
+    for a, b in zip(prepare_inputs(waves, feats), rp.prepare_sigma_inputs(waves, feats)):
+        assert np.array_equal(a, b, equal_nan=True)
+
+
+def test_shard_cases_balances_and_partitions():
+    lens = [7200000, 100, 1800000, 1800000, 5, 3600000, 900000, 900000]
+    shards = awd.shard_cases(lens, 4)
+    assert sorted(sum(shards, [])) == list(range(8))
+    loads = [sum(lens[i] for i in s) for s in shards]
+    assert max(loads) == 7200000 and min(loads) >= 2700000
+    assert awd.shard_cases(lens, 4, rank=2) == shards[2]
+
+
+def test_dropin_surface_has_the_reference_names():
+    sys.path.insert(0, os.path.join(ROOT, "dropin"))
+    try:
+        for k in [k for k in sys.modules if k.split(".")[0] in ("data_load_preprocess", "functions_traditional")]:
+            del sys.modules[k]
+        from data_load_preprocess.filters import zscore, butterworth  # noqa: F401
+        from data_load_preprocess.sample_from_record import sample_from_record  # noqa: F401
+        from data_load_preprocess.remove_samples import remove_samples, estimate_hr, rmssd  # noqa: F401
+        from data_load_preprocess.median_sample import (compute_median_sample_ecg, compute_median_features_ecg,  # noqa: F401
+                                                        plot_median_ecg)
+        from data_load_preprocess.feature_extraction.features_ecg import (compute_ecg_morphology_features,  # noqa: F401
+                                                                           ecg_features_relative_r)
+        from functions_traditional.signal_reconstruction import (reconstruct_gaussian, extract_coordinates,  # noqa: F401
+                                                                  gaussian_line)
+        import inspect
+        assert list(inspect.signature(butterworth).parameters) == [
+            "data", "btype", "cutoff_frequency", "sampling_frequency", "filter_order"]
+        assert list(inspect.signature(remove_samples).parameters) == [
+            "samples_wave_tracks", "indices_samples", "track_names", "sampling_frequency", "pvc_threshold",
+            "sd_threshold_ecg"]
+        assert inspect.signature(remove_samples).parameters["sd_threshold_ecg"].default == 0.05
+        assert list(inspect.signature(compute_median_sample_ecg).parameters) == [
+            "sample_ecg", "r_peaks", "sampling_frequency", "resample_ecg", "return_aligned"]
+        assert estimate_hr([], [100, 600, 1100], 500, mod="max") == 60.0
+        assert rmssd([100, 600, 1101], 500) == rp.rmssd([100, 600, 1101], 500)
+        with pytest.raises(NotImplementedError):
+            plot_median_ecg()
+    finally:
+        sys.path.remove(os.path.join(ROOT, "dropin"))
+        for k in [k for k in sys.modules if k.split(".")[0] in ("data_load_preprocess", "functions_traditional")]:
+            del sys.modules[k]
+
+
+def test_feature_helpers_match_golden(golden):
+    from ae_waveforms_b200.data_load_preprocess.feature_extraction.features_ecg import (
+        compute_ecg_morphology_features, ecg_features_relative_r)
+    from ae_waveforms_b200.data_load_preprocess.median_sample import compute_median_features_ecg
+    g = golden("features")
+    fid = {n: [np.nan if v < 0 else int(v) for v in g["fiducials"][k]] for k, n in enumerate(rp.FIDUCIALS)}
+    rel = ecg_features_relative_r(g["window"], fid, list(g["r_peaks"]), 500)
+    morph = compute_ecg_morphology_features(rel, len(g["r_peaks"]))
+    assert "ECG_R_Peaks" in rel
+    med = compute_median_features_ecg(rel, morph)
+    row = [v for n in rp.FIDUCIALS for v in (med[n]["x"], med[n]["y"])] + [med[n] for n in rp.MORPHOLOGY]
+    assert np.array_equal(np.array(row), g["row35"], equal_nan=True)
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(100 + rank)
+        n = 3 + 2 * rank
+        waves = torch.from_numpy(rng.standard_normal((n, 320)).astype(np.float32))
+        info = torch.from_numpy(np.stack([np.full(n, float(10 * (world - rank))), (np.arange(n) + 1) * 10000.0], 1))
+        parts = awd.allgather_rows(waves)
+        gw, gi = awd.gather_beat_arrays(waves, info)
+        sse = torch.tensor([1.0 + rank, 2.0, float("nan") if rank == 1 else 0.5], dtype=torch.float64)
+        awd.allreduce_sse(sse)
+        q.put((rank, [p.shape[0] for p in parts], gw.numpy(), gi.numpy(), sse.numpy(), waves.numpy(), info.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_collectives_world_size_2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+    assert res[0][1] == res[1][1] == [3, 5]
+    for r in res:
+        gw, gi, sse = r[2], r[3], r[4]
+        assert gw.shape == (8, 320) and gi.shape == (8, 2)
+        # case-major order: case 10 (rank 1) before case 20 (rank 0), idx_end ascending
+        assert np.array_equal(gi[:, 0], [10] * 5 + [20] * 3)
+        assert np.array_equal(gi[:5, 1], (np.arange(5) + 1) * 10000.0)
+        assert np.array_equal(gw[:5], res[1][5]) and np.array_equal(gw[5:], res[0][5])
+        assert sse[0] == 3.0 and sse[1] == 4.0 and np.isnan(sse[2])
+    assert np.array_equal(res[0][2], res[1][2])
+
+
+def test_synthetic_generator_is_seeded():
+    a, b = ecg_synth.synth_case(5, 20000), ecg_synth.synth_case(5, 20000)
+    assert np.array_equal(a, b) and not np.array_equal(a, ecg_synth.synth_case(6, 20000))
+    c = ecg_synth.sigma_candidates(64, "integer")
+    assert c.shape == (66, 12) and set(np.unique(c)) <= {1.0, 2.0, 3.0, 4.0, 5.0}
+    assert c[-2].tolist() == [1, 1, 1, 2, 2, 3, 3, 3, 4, 2, 2, 1]
