@@ -258,6 +258,7 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p) {
       p.keep[w] = 0; p.has_nan[w] = 2; p.n_peaks[w] = 0;
       for (int k = 0; k < 4; ++k) p.stats[4 * w + k] = qnan;
     }
+    for (int i = tid; i < K3_MAXP; i += K3_NT) p.peaks[w * K3_MAXP + i] = -1;
     return;
   }
   const double* src = p.y + p.win_start[w];
@@ -297,6 +298,7 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p) {
       p.keep[w] = 0; p.has_nan[w] = 1; p.n_peaks[w] = 0;
       for (int k = 0; k < 4; ++k) p.stats[4 * w + k] = qnan;
     }
+    for (int i = tid; i < K3_MAXP; i += K3_NT) p.peaks[w * K3_MAXP + i] = -1;
     return;
   }
 
