@@ -20,14 +20,20 @@
 // box filters with block-wide prefix sums instead (different rounding, ~1e-13),
 // flags a window as a HAZARD when any sample's comparison is closer to a tie than a
 // bound that dominates both evaluations' rounding error, and only for those
-// (about 1 window in 10^3) thread 0 re-runs SciPy's literal running sums.  Integer
+// (about 1 window in 10^5) thread 0 re-runs SciPy's literal running sums.  Integer
 // outputs are therefore identical to the sequential evaluation for every window.
 // mode 1 forces the sequential evaluation everywhere (parity suite); mode 2
 // disables the fallback (measurement only).
 //
+// Round-1 profile (profiles/r1_k3_before.txt) showed the kernel instruction-bound,
+// 48 % of the instructions in a branchy warp-shuffle median.  The median is now one
+// thread per beat column with a 32-input Batcher network held in registers
+// (191 compare-exchanges of DSETP + 4 FSEL); more than 32 beats per window fall back
+// to a branch-free warp-bitonic sort.  Leaf ranges of the NumPy tree are tabulated
+// once per block; HR / RMSSD are computed cooperatively instead of by thread 0.
+//
 // Algorithmic HBM bytes: 8 B per input sample read + (320*12 + 72*4 + 48) B per
-// window written.  Bound: B200's FP64 pipe, not HBM -- ~3 IEEE divisions and
-// ~40 other FP64 operations per sample.
+// window written.  Bound: instruction issue / FP64, not HBM.
 #include "aew_pairwise.cuh"
 #include "../../include/aewave.h"
 
@@ -46,8 +52,13 @@ struct K3Smem {
   double* pw_vals;      // [128]
   double* wtot;         // [16]
   double* scal;         // [16] scalars
+  double* dsq;          // [K3_MAXP] squared successive RR differences
   int* ipeaks;          // [K3_MAXP]
+  int* idiff;           // [K3_MAXP] RR intervals
+  int* isort;           // [K3_MAXP] RR intervals, sorted
   int* iscal;           // [16]
+  int* leaf_off;        // [128] NumPy-tree leaf ranges of a length-L vector
+  int* leaf_size;       // [128]
   unsigned short* beg;  // [L/2 + 2]
   unsigned short* end;
   unsigned short* cand;
@@ -64,8 +75,13 @@ __host__ __device__ inline size_t k3_smem_layout(unsigned char* base, int L, K3S
   t.pw_vals = (double*)take(sizeof(double) * 128);
   t.wtot = (double*)take(sizeof(double) * 16);
   t.scal = (double*)take(sizeof(double) * 16);
+  t.dsq = (double*)take(sizeof(double) * K3_MAXP);
   t.ipeaks = (int*)take(sizeof(int) * K3_MAXP);
+  t.idiff = (int*)take(sizeof(int) * K3_MAXP);
+  t.isort = (int*)take(sizeof(int) * K3_MAXP);
   t.iscal = (int*)take(sizeof(int) * 16);
+  t.leaf_off = (int*)take(sizeof(int) * 128);
+  t.leaf_size = (int*)take(sizeof(int) * 128);
   const int rmax = L / 2 + 2;
   t.beg = (unsigned short*)take(sizeof(unsigned short) * rmax);
   t.end = (unsigned short*)take(sizeof(unsigned short) * rmax);
@@ -90,6 +106,41 @@ struct SumDev2 {
   const double* a; double m;
   __device__ __forceinline__ double operator()(long long i, bool) { const double d = __dsub_rn(a[i], m); return __dmul_rn(d, d); }
 };
+
+// NumPy-order block sum with the leaf ranges tabulated (same tree as pw_block_sum)
+template <class F>
+__device__ __forceinline__ double block_sum_tab(F& f, int depth, const K3Smem& sm) {
+  const int nslots = 1 << depth;
+  const int group = threadIdx.x >> 3, g = threadIdx.x & 7, ngroups = blockDim.x >> 3;
+  for (int s0 = 0; s0 < nslots; s0 += ngroups) {
+    const int slot = s0 + group;
+    const int off = slot < nslots ? sm.leaf_off[slot] : 0;
+    const int size = slot < nslots ? sm.leaf_size[slot] : 0;
+    const int c8 = size >> 3;
+    double r = 0.0;
+    if (c8 > 0) {
+      r = f(off + g, true);
+#pragma unroll 5
+      for (int k = 1; k < c8; ++k) r = __dadd_rn(r, f(off + 8 * k + g, true));
+    }
+    double t = __shfl_xor_sync(AEW_FULL, r, 1);
+    r = __dadd_rn(r, t);
+    t = __shfl_xor_sync(AEW_FULL, r, 2);
+    r = __dadd_rn(r, t);
+    t = __shfl_xor_sync(AEW_FULL, r, 4);
+    r = __dadd_rn(r, t);
+    int i = c8 << 3;
+    if (size < 8) { r = 0.0; i = 0; }
+    for (; i < size; ++i) r = __dadd_rn(r, f(off + i, g == 0));
+    if (slot < nslots && g == 0) { sm.pw_vals[slot] = r; sm.pw_valid[slot] = size > 0; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) pw_warp_combine(sm.pw_vals, sm.pw_valid, depth, threadIdx.x);
+  __syncthreads();
+  const double r = sm.pw_vals[0];
+  __syncthreads();
+  return r;
+}
 
 // exclusive block scan of one double per thread (fast path; not order-sensitive)
 __device__ __forceinline__ double block_excl_scan(double v, double* wtot) {
@@ -126,6 +177,7 @@ __device__ __forceinline__ int block_excl_scan_int(int v, int* wtot) {
 // sum over a clamped ("nearest") window [lo, hi] from an inclusive prefix array
 __device__ __forceinline__ double clamped_window(const double* __restrict__ P, int lo, int hi, int L, double first,
                                                  double last) {
+  if (lo >= 1 && hi <= L - 1) return P[hi] - P[lo - 1];          // interior: no clamping
   const int nl = lo < 0 ? -lo : 0, nr = hi > L - 1 ? hi - (L - 1) : 0;
   const int lo2 = lo < 0 ? 0 : lo, hi2 = hi > L - 1 ? L - 1 : hi;
   double s = P[hi2] - (lo2 > 0 ? P[lo2 - 1] : 0.0);
@@ -133,7 +185,81 @@ __device__ __forceinline__ double clamped_window(const double* __restrict__ P, i
   return s;
 }
 
-// ---- warp bitonic sort of 32*K doubles, element e = k*32 + lane, ascending
+// ---------------------------------------------------------------------- medians
+__device__ __forceinline__ void cex(double& a, double& b) {          // a <- min, b <- max (DSETP + 4 FSEL)
+  const bool s = a > b;
+  const double lo = s ? b : a, hi = s ? a : b;
+  a = lo; b = hi;
+}
+
+// Batcher odd-even merge sort of N (power of two) values held in registers; the
+// recursion is unfolded by templates so that every index is a compile-time constant
+// (191 compare-exchanges for N = 32).  [LO, HI] inclusive.
+template <int LO, int HI, int R>
+struct OddEvenMerge {
+  template <int N>
+  static __device__ __forceinline__ void apply(double (&v)[N]) {
+    constexpr int STEP = R * 2;
+    if constexpr (STEP < HI - LO) {
+      OddEvenMerge<LO, HI, STEP>::apply(v);
+      OddEvenMerge<LO + R, HI, STEP>::apply(v);
+#pragma unroll
+      for (int i = LO + R; i < HI - R; i += STEP) cex(v[i], v[i + R]);
+    } else {
+      cex(v[LO], v[LO + R]);
+    }
+  }
+};
+template <int LO, int HI>
+struct OddEvenSort {
+  template <int N>
+  static __device__ __forceinline__ void apply(double (&v)[N]) {
+    if constexpr (HI - LO >= 1) {
+      constexpr int MID = LO + (HI - LO) / 2;
+      OddEvenSort<LO, MID>::apply(v);
+      OddEvenSort<MID + 1, HI>::apply(v);
+      OddEvenMerge<LO, HI, 1>::apply(v);
+    }
+  }
+};
+template <int N>
+__device__ __forceinline__ void sort_network(double (&v)[N]) { OddEvenSort<0, N - 1>::apply(v); }
+
+// value of beat b at column c (median_sample.py:30-41): short slices are LEFT-aligned
+// in a NaN row; +inf stands for the NaN padding
+__device__ __forceinline__ double beat_value(const double* __restrict__ z, int p, int c, int L, int pre, int post,
+                                             int& valid) {
+  const int s = p - pre < 0 ? 0 : p - pre;
+  const int e = p + post > L ? L : p + post;
+  const int idx = s + c;
+  if (idx < e) { ++valid; return z[idx]; }
+  return __longlong_as_double(0x7ff0000000000000ll);
+}
+
+// column c of a window with n <= 32 beats, by ONE thread: (lo + hi) / 2 with lo == hi for
+// odd counts, exactly as np.ma.median evaluates it; all-NaN column -> NaN
+__device__ __forceinline__ double column_median_thread(const double* __restrict__ z, const int* __restrict__ peaks,
+                                                       int n, int c, int L, int pre, int post) {
+  double v[32];
+  int valid = 0;
+#pragma unroll
+  for (int b = 0; b < 32; ++b)
+    v[b] = b < n ? beat_value(z, peaks[b], c, L, pre, post, valid) : __longlong_as_double(0x7ff0000000000000ll);
+  sort_network<32>(v);
+  const int h = valid >> 1;
+  const int rhi = h < 31 ? h : 31;
+  const int rlo = (valid & 1) ? h : (h > 0 ? h - 1 : 0);
+  double lo = 0.0, hi = 0.0;
+#pragma unroll
+  for (int b = 0; b < 32; ++b) {
+    lo = (b == rlo) ? v[b] : lo;
+    hi = (b == rhi) ? v[b] : hi;
+  }
+  if (valid == 0) return __longlong_as_double(0x7ff8000000000000ll);
+  return __dmul_rn(__dadd_rn(lo, hi), 0.5);
+}
+
+// ---- warp bitonic sort of 32*K doubles, element e = k*32 + lane, ascending (n > 32 beats)
 template <int K>
 __device__ __forceinline__ void warp_sort(double (&v)[K], int lane) {
 #pragma unroll
@@ -145,8 +271,7 @@ __device__ __forceinline__ void warp_sort(double (&v)[K], int lane) {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
           if ((k & ks) == 0) {
-            const int e = k * 32;                       // direction depends on bits >= 5 only here
-            const bool asc = ((e & size) == 0);
+            const bool asc = (((k * 32) & size) == 0);
             const double a = v[k], b = v[k | ks];
             const bool swap = asc ? (a > b) : (a < b);
             v[k] = swap ? b : a;
@@ -156,12 +281,11 @@ __device__ __forceinline__ void warp_sort(double (&v)[K], int lane) {
       } else {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-          const int e = k * 32 + lane;
-          const bool asc = ((e & size) == 0);
+          const bool asc = (((k * 32 + lane) & size) == 0);
           const double o = __shfl_xor_sync(AEW_FULL, v[k], stride);
-          const bool lower = (lane & stride) == 0;
-          const bool take_min = (lower == asc);
-          v[k] = take_min ? (o < v[k] ? o : v[k]) : (o > v[k] ? o : v[k]);
+          const bool take_min = (((lane & stride) == 0) == asc);
+          const bool o_lt = o < v[k];
+          v[k] = (take_min == o_lt) ? o : v[k];         // equal values: either copy is the same number
         }
       }
     }
@@ -169,57 +293,53 @@ __device__ __forceinline__ void warp_sort(double (&v)[K], int lane) {
 }
 
 template <int K>
-__device__ __forceinline__ double warp_pick(const double (&v)[K], int rank, int lane) {
+__device__ __forceinline__ double warp_pick(const double (&v)[K], int rank) {
   double r = 0.0;
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     const double c = __shfl_sync(AEW_FULL, v[k], rank & 31);
-    if ((rank >> 5) == k) r = c;
+    r = ((rank >> 5) == k) ? c : r;
   }
   return r;
 }
 
-// column-wise nanmedian over the beats of one window (median_sample.py:30-47).
-// z: window samples (shared or global), peaks: n beat positions.  One warp per
-// column; lane b holds beats b, b+32, ...  (lo+hi)/2 with lo == hi for odd counts,
-// exactly as np.ma.median evaluates it.
 template <int K>
-__device__ __forceinline__ double column_median(const double* __restrict__ z, const int* __restrict__ peaks, int n,
-                                                int c, int L, int pre, int post, int lane) {
+__device__ __forceinline__ double column_median_warp(const double* __restrict__ z, const int* __restrict__ peaks,
+                                                     int n, int c, int L, int pre, int post, int lane) {
   double v[K];
   int valid = 0;
-  const double inf = __longlong_as_double(0x7ff0000000000000ll);
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     const int b = k * 32 + lane;
-    v[k] = inf;
-    if (b < n) {
-      const int p = peaks[b];
-      const int s = p - pre < 0 ? 0 : p - pre;
-      const int e = p + post > L ? L : p + post;
-      const int idx = s + c;                           // short slices are left-aligned (appendix A.4)
-      if (idx < e) { v[k] = z[idx]; ++valid; }
-    }
+    v[k] = b < n ? beat_value(z, peaks[b], c, L, pre, post, valid) : __longlong_as_double(0x7ff0000000000000ll);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) valid += __shfl_xor_sync(AEW_FULL, valid, o);
   warp_sort<K>(v, lane);
   const int h = valid >> 1;
-  const double hi = warp_pick<K>(v, h < 32 * K - 1 ? h : 32 * K - 1, lane);
-  const double lo = warp_pick<K>(v, (valid & 1) ? h : (h > 0 ? h - 1 : 0), lane);
+  const double hi = warp_pick<K>(v, h < 32 * K - 1 ? h : 32 * K - 1);
+  const double lo = warp_pick<K>(v, (valid & 1) ? h : (h > 0 ? h - 1 : 0));
   if (valid == 0) return __longlong_as_double(0x7ff8000000000000ll);
   return __dmul_rn(__dadd_rn(lo, hi), 0.5);
 }
 
+// all pre+post columns of one window; every thread of the block calls it
 __device__ __forceinline__ void window_median(const double* __restrict__ z, const int* __restrict__ peaks, int n,
                                               int L, int pre, int post, double* __restrict__ med,
                                               float* __restrict__ waves) {
+  const int S = pre + post;
+  if (n <= 32) {
+    for (int c = threadIdx.x; c < S; c += blockDim.x) {
+      const double m = column_median_thread(z, peaks, n, c, L, pre, post);
+      if (med) med[c] = m;
+      if (waves) waves[c] = (float)m;
+    }
+    return;
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  for (int c = warp; c < pre + post; c += nwarp) {
-    double m;
-    if (n <= 32) m = column_median<1>(z, peaks, n, c, L, pre, post, lane);
-    else if (n <= 64) m = column_median<2>(z, peaks, n, c, L, pre, post, lane);
-    else m = column_median<4>(z, peaks, n, c, L, pre, post, lane);
+  for (int c = warp; c < S; c += nwarp) {
+    const double m = n <= 64 ? column_median_warp<2>(z, peaks, n, c, L, pre, post, lane)
+                             : column_median_warp<4>(z, peaks, n, c, L, pre, post, lane);
     if (lane == 0) {
       if (med) med[c] = m;
       if (waves) waves[c] = (float)m;
@@ -227,24 +347,7 @@ __device__ __forceinline__ void window_median(const double* __restrict__ z, cons
   }
 }
 
-// NumPy order sum of a short vector (n <= 128) by one thread
-__device__ inline double leaf_sum_seq(const double* v, int n) {
-  if (n < 8) {
-    double r = 0.0;
-    for (int i = 0; i < n; ++i) r = __dadd_rn(r, v[i]);
-    return r;
-  }
-  double r[8];
-  for (int k = 0; k < 8; ++k) r[k] = v[k];
-  int i = 8;
-  for (; i + 8 <= n; i += 8)
-    for (int k = 0; k < 8; ++k) r[k] = __dadd_rn(r[k], v[i + k]);
-  double s = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                       __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-  for (; i < n; ++i) s = __dadd_rn(s, v[i]);
-  return s;
-}
-
+// ---------------------------------------------------------------------- the window kernel
 __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p) {
   AEW_DYN_SMEM(smem_raw);
   K3Smem sm;
@@ -264,6 +367,13 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p) {
   const double* src = p.y + p.win_start[w];
   double* A = sm.A;
   double* B = sm.B;
+  const int depth = pw_depth(L);
+  if (tid < (1 << depth)) {
+    long long off, size;
+    pw_node(L, depth, (unsigned)tid, off, size);
+    sm.leaf_off[tid] = (int)off;
+    sm.leaf_size[tid] = (int)size;
+  }
 
   // ---- load, NaN screen (remove_samples.py:31-33)
   int bad = 0;
@@ -273,14 +383,13 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p) {
     bad |= isnan(v) ? 1 : 0;
   }
   bad = __syncthreads_or(bad);
-  const int depth = pw_depth(L);
   double mean = 0.0, sd0 = 0.0;
   if (!bad && p.zscore_windows) {
     // ---- per-window z-score (data_extract_vitaldb.py:93), NumPy summation order
     SumPlain f1{A};
-    mean = __ddiv_rn(pw_block_sum(f1, L, depth, sm.pw_vals, sm.pw_valid), (double)L);
+    mean = __ddiv_rn(block_sum_tab(f1, depth, sm), (double)L);
     SumDev2 f2{A, mean};
-    sd0 = __dsqrt_rn(__ddiv_rn(pw_block_sum(f2, L, depth, sm.pw_vals, sm.pw_valid), (double)L));
+    sd0 = __dsqrt_rn(__ddiv_rn(block_sum_tab(f2, depth, sm), (double)L));
     int nonfinite = 0;
     for (int i = tid; i < L; i += K3_NT) {
       const double z = __ddiv_rn(__dsub_rn(A[i], mean), sd0);
@@ -304,9 +413,9 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p) {
 
   // ---- ecg_sd = np.std(window) (remove_samples.py:62)
   SumPlain f3{A};
-  const double m2 = __ddiv_rn(pw_block_sum(f3, L, depth, sm.pw_vals, sm.pw_valid), (double)L);
+  const double m2 = __ddiv_rn(block_sum_tab(f3, depth, sm), (double)L);
   SumDev2 f4{A, m2};
-  const double sd = __dsqrt_rn(__ddiv_rn(pw_block_sum(f4, L, depth, sm.pw_vals, sm.pw_valid), (double)L));
+  const double sd = __dsqrt_rn(__ddiv_rn(block_sum_tab(f4, depth, sm), (double)L));
 
   // ---- QRS indicator: smoothgrad > 1.5 * avggrad
   const int ks = p.smooth_k, ka = p.avg_k;
@@ -399,27 +508,22 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p) {
   // ---- QRS runs: beg where ~q[i] & q[i+1], end where q[i] & ~q[i+1]  (ordered compaction)
   {
     const int i0 = tid * K3_ITEMS;
-    int nb = 0, ne = 0;
+    unsigned bbits = 0, ebits = 0;
+    int prev = (i0 < L) ? sm.Q[i0] : 0;
 #pragma unroll
     for (int k = 0; k < K3_ITEMS; ++k) {
       const int i = i0 + k;
+      const int nxt = (i + 1 < L) ? sm.Q[i + 1] : prev;    // beyond the window: no transition
       if (i < L - 1) {
-        const int a = sm.Q[i], b = sm.Q[i + 1];
-        nb += (!a && b);
-        ne += (a && !b);
+        bbits |= (unsigned)(!prev && nxt) << k;
+        ebits |= (unsigned)(prev && !nxt) << k;
       }
+      prev = nxt;
     }
-    const int packed = block_excl_scan_int(nb | (ne << 16), (int*)sm.wtot);
+    const int packed = block_excl_scan_int(__popc(bbits) | (__popc(ebits) << 16), (int*)sm.wtot);
     int ob = packed & 0xffff, oe = packed >> 16;
-#pragma unroll
-    for (int k = 0; k < K3_ITEMS; ++k) {
-      const int i = i0 + k;
-      if (i < L - 1) {
-        const int a = sm.Q[i], b = sm.Q[i + 1];
-        if (!a && b) sm.beg[ob++] = (unsigned short)i;
-        if (a && !b) sm.end[oe++] = (unsigned short)i;
-      }
-    }
+    while (bbits) { const int k = __ffs(bbits) - 1; bbits &= bbits - 1; sm.beg[ob++] = (unsigned short)(i0 + k); }
+    while (ebits) { const int k = __ffs(ebits) - 1; ebits &= ebits - 1; sm.end[oe++] = (unsigned short)(i0 + k); }
     if (tid == K3_NT - 1) { sm.iscal[0] = ob; sm.iscal[1] = oe; }
     __syncthreads();
   }
@@ -481,7 +585,7 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p) {
   }
   __syncthreads();
 
-  // ---- refractory chain, statistics, mask (thread 0)
+  // ---- refractory chain (sequential by definition; thread 0)
   if (tid == 0) {
     int np = 0, last = 0;
     for (int r = 0; r < num; ++r) {
@@ -494,46 +598,60 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p) {
       }
     }
     if (np > K3_MAXP) { atomicOr(p.status, AEW_DEV_RUN_OVERFLOW); np = K3_MAXP; }
-    // remove_samples.py:53-54 keeps 0 < p < L (always true here: p > refractory)
+    sm.iscal[2] = np;
+  }
+  __syncthreads();
+  const int np = sm.iscal[2];
+  // remove_samples.py:53-54 keeps 0 < p < L (always true here: p > refractory)
+
+  // ---- HR = 60 fs / median(RR) and RMSSD (remove_samples.py:85-121), cooperatively
+  const int nd = np - 1;
+  if (tid < nd) {
+    const int d0 = sm.ipeaks[tid + 1] - sm.ipeaks[tid];
+    sm.idiff[tid] = d0;
+    if (tid + 1 < nd) {
+      const double cur = __ddiv_rn((double)(sm.ipeaks[tid + 2] - sm.ipeaks[tid + 1]), p.rr_div);
+      const double prv = __ddiv_rn((double)d0, p.rr_div);
+      const double dd = __dsub_rn(cur, prv);
+      sm.dsq[tid] = __dmul_rn(dd, dd);
+    }
+  }
+  __syncthreads();
+  if (tid < nd) {                                        // rank sort of <= 71 integers
+    const int mine = sm.idiff[tid];
+    int rank = 0;
+    for (int j = 0; j < nd; ++j) {
+      const int o = sm.idiff[j];
+      rank += (o < mine) || (o == mine && j < tid);
+    }
+    sm.isort[rank] = mine;
+  }
+  double ssq = 0.0;
+  if (warp == 15) {                                      // NumPy leaf order over np-2 <= 70 values
+    SumPlain fq{sm.dsq};
+    ssq = pw_leaf_sum8(fq, 0, np >= 3 ? np - 2 : 0, lane & 7);
+    if (lane == 0) sm.scal[5] = ssq;
+  }
+  __syncthreads();
+  if (tid == 0) {
     double hr = qnan, rms = qnan;
     if (np >= 2) {
-      int diffs[K3_MAXP];
-      for (int i = 0; i + 1 < np; ++i) diffs[i] = sm.ipeaks[i + 1] - sm.ipeaks[i];
-      const int nd = np - 1;
-      for (int i = 1; i < nd; ++i) {                   // insertion sort, <= 71 values
-        const int v = diffs[i];
-        int j = i - 1;
-        while (j >= 0 && diffs[j] > v) { diffs[j + 1] = diffs[j]; --j; }
-        diffs[j + 1] = v;
-      }
-      const double med = (nd & 1) ? (double)diffs[nd / 2]
-                                  : __dmul_rn(__dadd_rn((double)diffs[nd / 2 - 1], (double)diffs[nd / 2]), 0.5);
+      const double med = (nd & 1) ? (double)sm.isort[nd / 2]
+                                  : __dmul_rn(__dadd_rn((double)sm.isort[nd / 2 - 1], (double)sm.isort[nd / 2]), 0.5);
       hr = __ddiv_rn(p.hr_num, med);
     }
-    if (np >= 3) {
-      double sq[K3_MAXP];
-      double prev = __ddiv_rn((double)(sm.ipeaks[1] - sm.ipeaks[0]), p.rr_div);
-      for (int i = 1; i + 1 < np; ++i) {
-        const double cur = __ddiv_rn((double)(sm.ipeaks[i + 1] - sm.ipeaks[i]), p.rr_div);
-        const double dd = __dsub_rn(cur, prev);
-        sq[i - 1] = __dmul_rn(dd, dd);
-        prev = cur;
-      }
-      rms = __dsqrt_rn(__ddiv_rn(leaf_sum_seq(sq, np - 2), (double)(np - 2)));
-    }
+    if (np >= 3) rms = __dsqrt_rn(__ddiv_rn(sm.scal[5], (double)(np - 2)));
     const double sdn = __ddiv_rn(sd, (double)np);
     const bool remove = (hr < p.hr_lo) || (hr > p.hr_hi) || isnan(hr) || (rms > p.pvc_threshold) ||
                         (sdn > p.sd_threshold);
-    sm.iscal[2] = np;
     sm.iscal[3] = remove ? 0 : 1;
     p.keep[w] = remove ? 0 : 1;
     p.has_nan[w] = 0;
     p.n_peaks[w] = np;
     p.stats[4 * w + 0] = hr; p.stats[4 * w + 1] = rms; p.stats[4 * w + 2] = sd; p.stats[4 * w + 3] = sdn;
   }
-  __syncthreads();
-  const int np = sm.iscal[2];
   for (int i = tid; i < K3_MAXP; i += K3_NT) p.peaks[w * K3_MAXP + i] = i < np ? sm.ipeaks[i] : -1;
+  __syncthreads();
 
   // ---- median beat of kept windows (median_sample.py:6-54) -> np_waves row
   if (sm.iscal[3] && (p.median || p.waves))
@@ -543,9 +661,10 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p) {
 
 // Stand-alone median beats for given peaks (the compute_median_sample_ecg shim):
 // one block per window, samples read from global memory.
-__global__ void __launch_bounds__(256) k4_median(const double* __restrict__ windows, int L, const int* __restrict__ peaks,
-                                                const long long* __restrict__ peak_off, int pre, int post,
-                                                double* __restrict__ median, double* __restrict__ aligned) {
+__global__ void __launch_bounds__(K3_NT, 1) k4_median(const double* __restrict__ windows, int L,
+                                                      const int* __restrict__ peaks,
+                                                      const long long* __restrict__ peak_off, int pre, int post,
+                                                      double* __restrict__ median, double* __restrict__ aligned) {
   const long long w = blockIdx.x;
   const double* z = windows + w * (long long)L;
   const int* pk = peaks + peak_off[w];
@@ -561,14 +680,7 @@ __global__ void __launch_bounds__(256) k4_median(const double* __restrict__ wind
       al[i] = (s + c < e) ? z[s + c] : qnan;
     }
   }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  for (int c = warp; c < S; c += nwarp) {
-    double m;
-    if (n <= 32) m = column_median<1>(z, pk, n, c, L, pre, post, lane);
-    else if (n <= 64) m = column_median<2>(z, pk, n, c, L, pre, post, lane);
-    else m = column_median<4>(z, pk, n, c, L, pre, post, lane);
-    if (lane == 0) median[w * S + c] = m;
-  }
+  window_median(z, pk, n, L, pre, post, median + w * S, nullptr);
 }
 
 }  // namespace
@@ -601,7 +713,7 @@ extern "C" int aew_median_beats_f64(const double* windows, long long n_win, int 
   if (!windows || !peaks || !d_peak_off || !median || n_win < 0 || L < 1) return AEW_ERR_ARG;
   if (max_peaks_per_window > 128 || pre + post != K3_BEAT || n_win > 0x7fffffffll) return AEW_ERR_UNSUPPORTED;
   if (n_win == 0) return AEW_OK;
-  AEW_LAUNCH(k4_median, (unsigned)n_win, 256, 0, (cudaStream_t)stream, windows, L, peaks, d_peak_off, pre, post,
+  AEW_LAUNCH(k4_median, (unsigned)n_win, K3_NT, 0, (cudaStream_t)stream, windows, L, peaks, d_peak_off, pre, post,
              median, aligned);
   return (int)cudaGetLastError();
 }
