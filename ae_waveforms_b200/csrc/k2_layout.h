@@ -2,10 +2,11 @@
 // kernel (k2_filtfilt.cu) and the host-side table builder (k2_tables.cpp).
 #pragma once
 
-#define K2_C 33                      // samples per thread chunk (odd: conflict-free stride in shared memory)
+#define K2_C 13                      // samples per thread chunk (odd: conflict-free stride in shared memory)
 #define K2_NT 256                    // threads per block
 #define K2_NW (K2_NT / 32)
-#define K2_T (K2_C * K2_NT)          // samples per tile = 8448
+#define K2_T (K2_C * K2_NT)          // samples per tile = 3328 (26 KB)
+#define K2_STAGES 4                  // ring of tile buffers per block: loading / recursion / correction / storing
 #define K2_MAXPAD 15                 // filtfilt padlen for order 4
 
 // Table of doubles (device copy is read by every block once per launch).
@@ -27,4 +28,5 @@
 #define K2_TAB_PK 52                 // [5][4]  p^(C 2^k)
 #define K2_TAB_PLANE 72              // [32][4] p^(C l)
 #define K2_TAB_G (K2_TAB_PLANE + 128)          // [C][4]  zero-input response: y_j += G[j] . s
-#define K2_TAB_LEN (K2_TAB_G + 4 * K2_C)
+#define K2_TAB_PWP (K2_TAB_G + 4 * K2_C)        // [NW+1][4] p^(32 C m), m = 0 .. NW
+#define K2_TAB_LEN (K2_TAB_PWP + 4 * (K2_NW + 1))

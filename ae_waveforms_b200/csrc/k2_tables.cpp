@@ -121,6 +121,7 @@ extern "C" int aew_filt_tables(const double* b, const double* a, const double* z
     for (int k = 0; k < 5; ++k) put(K2_TAB_PK + 4 * k, cpow(p, (long long)K2_C << k));
     cq pl = mk(1);
     for (int l = 0; l < 32; ++l) { put(K2_TAB_PLANE + 4 * l, pl); pl = pl * pc; }
+    for (int mm = 0; mm <= K2_NW; ++mm) put(K2_TAB_PWP + 4 * mm, cpow(p, 32ll * K2_C * mm));
     cq pj = mk(1);
     for (int j = 0; j < K2_C; ++j) {
       const cq gp = g * pj;
