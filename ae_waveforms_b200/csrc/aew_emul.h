@@ -223,6 +223,7 @@ inline double __dsub_rn(double a, double b) { volatile double r = a - b; return 
 inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
 inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
 inline double __dsqrt_rn(double a) { return std::sqrt(a); }
+inline double __drcp_rn(double a) { volatile double r = 1.0 / a; return r; }
 inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }

@@ -40,6 +40,7 @@
 // Algorithmic HBM bytes: 16 B/sample per pass, 32 B/sample per filtfilt
 // (SURVEY.md section 8d).  Roofline: HBM; FP64 work is ~17 FMA/sample/pass.
 #include "aew_rt.h"
+#include "aew_math.cuh"
 #include "k2_layout.h"
 
 namespace {
@@ -210,8 +211,9 @@ __device__ __forceinline__ void modal_initial(const double* tab, double scale, d
   }
 }
 
-__device__ __forceinline__ double zs(double v, bool on, double mean, double sd) {
-  return on ? __ddiv_rn(__dsub_rn(v, mean), sd) : v;
+// z-score on load: (v - mean) / sd with IEEE division (aew_math.cuh), bit-identical to NumPy
+__device__ __forceinline__ double zs(double v, bool on, double mean, const ExactDiv& sd) {
+  return on ? div_exact(__dsub_rn(v, mean), sd) : v;
 }
 
 // ------------------------------------------------------------ tiled pass
@@ -398,7 +400,8 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
       for (int i = 0; i < 4; ++i) rw[i] = a.ws.tile_desc[4 * tile + i];
       d = describe_tile<REV>(rw, a.bulk_ok, pad);
       const bool zon = (!REV) && a.mean != nullptr;
-      const double mean = zon ? a.mean[d.rec] : 0.0, sd = zon ? a.sd[d.rec] : 1.0;
+      const double mean = zon ? a.mean[d.rec] : 0.0;
+      const ExactDiv sd = make_exact_div(zon ? a.sd[d.rec] : 1.0);
       if (d.n <= pad) {                                // filters.py:50-51: too short, copy through
         if (!REV)
           for (long long i = tid; i < d.n; i += K2_NT) a.passthrough[d.g0 + i] = zs(a.src[d.g0 + i], zon, mean, sd);
@@ -539,7 +542,8 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
     // =================== B half: correct and store the pending tile ===================
     if (have_prev) {
       const bool zon = (!REV) && a.mean != nullptr;
-      const double mean = zon ? a.mean[dp.rec] : 0.0, sd = zon ? a.sd[dp.rec] : 1.0;
+      const double mean = zon ? a.mean[dp.rec] : 0.0;
+      const ExactDiv sd = make_exact_div(zon ? a.sd[dp.rec] : 1.0);
       const int dir = (REV && dp.bulk) ? -1 : 1;
       const int base = (REV && dp.bulk) ? K2_T - 1 : 0;
       // state entering my chunk = p^(C*lane) S_warp + end state of the lane before me
@@ -612,7 +616,8 @@ __global__ void __launch_bounds__(32) k2_exact(PassArgs a) {
   const long long* sg = a.ws.segs + 4 * seg;
   const long long g0 = sg[0], n = sg[1], rec = sg[2];
   const bool zon = a.mean != nullptr;
-  const double mean = zon ? a.mean[rec] : 0.0, sd = zon ? a.sd[rec] : 1.0;
+  const double mean = zon ? a.mean[rec] : 0.0;
+      const ExactDiv sd = make_exact_div(zon ? a.sd[rec] : 1.0);
   const int ord = (int)a.tab[K2_TAB_ORDER], pad = (int)a.tab[K2_TAB_PAD];
   double b[5], ac[5], zi[4], z[4];
   for (int i = 0; i < 5; ++i) { b[i] = a.tab[K2_TAB_B + i]; ac[i] = a.tab[K2_TAB_A + i]; }

@@ -35,6 +35,7 @@
 // Algorithmic HBM bytes: 8 B per input sample read + (320*12 + 72*4 + 48) B per
 // window written.  Bound: instruction issue / FP64, not HBM.
 #include "aew_pairwise.cuh"
+#include "aew_math.cuh"
 #include "../../include/aewave.h"
 
 #define K3_NT 512
@@ -101,10 +102,10 @@ __device__ __forceinline__ double absgrad(const double* __restrict__ z, int i, i
   return fabs(g);
 }
 
-struct SumPlain { const double* a; __device__ __forceinline__ double operator()(long long i, bool) { return a[i]; } };
+struct SumPlain { const double* a; __device__ __forceinline__ double operator()(int i, bool) { return a[i]; } };
 struct SumDev2 {
   const double* a; double m;
-  __device__ __forceinline__ double operator()(long long i, bool) { const double d = __dsub_rn(a[i], m); return __dmul_rn(d, d); }
+  __device__ __forceinline__ double operator()(int i, bool) { const double d = __dsub_rn(a[i], m); return __dmul_rn(d, d); }
 };
 
 // NumPy-order block sum with the leaf ranges tabulated (same tree as pw_block_sum)
@@ -391,8 +392,9 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p) {
     SumDev2 f2{A, mean};
     sd0 = __dsqrt_rn(__ddiv_rn(block_sum_tab(f2, depth, sm), (double)L));
     int nonfinite = 0;
+    const ExactDiv dv = make_exact_div(sd0);
     for (int i = tid; i < L; i += K3_NT) {
-      const double z = __ddiv_rn(__dsub_rn(A[i], mean), sd0);
+      const double z = div_exact(__dsub_rn(A[i], mean), dv);
       A[i] = z;
       nonfinite |= (isnan(z) || isinf(z)) ? 1 : 0;     // constant window: 0/0
     }
@@ -421,50 +423,94 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p) {
   const int ks = p.smooth_k, ka = p.avg_k;
   const int ls = ks / 2, la = ka / 2;                  // uniform_filter1d: window [i - k/2, i - k/2 + k)
   int hazard = 0;
+  unsigned qbits = 0;                                  // bit k: QRS indicator of sample tid * ITEMS + k
+  const int i0 = tid * K3_ITEMS;
   if (p.mode != 1) {
-    const int i0 = tid * K3_ITEMS;
     double loc[K3_ITEMS], smv[K3_ITEMS];
     double run = 0.0;
+    if (i0 >= 1 && i0 + K3_ITEMS < L) {                // strip away from both window edges
+      const double* zp = A + i0;
+      double prv = zp[-1], cur = zp[0];
 #pragma unroll
-    for (int k = 0; k < K3_ITEMS; ++k) {
-      const int i = i0 + k;
-      run += (i < L) ? absgrad(A, i, L) : 0.0;
-      loc[k] = run;
+      for (int k = 0; k < K3_ITEMS; ++k) {
+        const double nxt = zp[k + 1];
+        run += fabs(__dmul_rn(__dsub_rn(nxt, prv), 0.5));
+        loc[k] = run;
+        prv = cur; cur = nxt;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < K3_ITEMS; ++k) {
+        const int i = i0 + k;
+        run += (i < L) ? absgrad(A, i, L) : 0.0;
+        loc[k] = run;
+      }
     }
     double base = block_excl_scan(run, sm.wtot);
+    if (i0 + K3_ITEMS <= L) {
 #pragma unroll
-    for (int k = 0; k < K3_ITEMS; ++k) if (i0 + k < L) B[i0 + k] = base + loc[k];
+      for (int k = 0; k < K3_ITEMS; ++k) B[i0 + k] = base + loc[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < K3_ITEMS; ++k) if (i0 + k < L) B[i0 + k] = base + loc[k];
+    }
     if (tid == 0) { sm.scal[0] = absgrad(A, 0, L); sm.scal[1] = absgrad(A, L - 1, L); }
     __syncthreads();
     const double ag0 = sm.scal[0], agL = sm.scal[1], ptot = B[L - 1];
     const double inv_s = 1.0 / (double)ks, inv_a = 1.0 / (double)ka;
     run = 0.0;
+    if (i0 - ls >= 1 && i0 + K3_ITEMS - 1 - ls + ks - 1 <= L - 1) {   // no clamping anywhere in the strip
+      const double* pl = B + i0 - ls - 1;
+      const double* ph = B + i0 - ls + ks - 1;
 #pragma unroll
-    for (int k = 0; k < K3_ITEMS; ++k) {
-      const int i = i0 + k;
-      double s = 0.0;
-      if (i < L) s = clamped_window(B, i - ls, i - ls + ks - 1, L, ag0, agL) * inv_s;
-      smv[k] = s;
-      run += s;
-      loc[k] = run;
-      if (i == 0) sm.scal[2] = s;
-      if (i == L - 1) sm.scal[3] = s;
+      for (int k = 0; k < K3_ITEMS; ++k) {
+        const double s = (ph[k] - pl[k]) * inv_s;
+        smv[k] = s;
+        run += s;
+        loc[k] = run;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < K3_ITEMS; ++k) {
+        const int i = i0 + k;
+        double s = 0.0;
+        if (i < L) s = clamped_window(B, i - ls, i - ls + ks - 1, L, ag0, agL) * inv_s;
+        smv[k] = s;
+        run += s;
+        loc[k] = run;
+        if (i == 0) sm.scal[2] = s;
+        if (i == L - 1) sm.scal[3] = s;
+      }
     }
     base = block_excl_scan(run, sm.wtot);               // (its barriers also end all reads of B)
+    if (i0 + K3_ITEMS <= L) {
 #pragma unroll
-    for (int k = 0; k < K3_ITEMS; ++k) if (i0 + k < L) B[i0 + k] = base + loc[k];
+      for (int k = 0; k < K3_ITEMS; ++k) B[i0 + k] = base + loc[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < K3_ITEMS; ++k) if (i0 + k < L) B[i0 + k] = base + loc[k];
+    }
     __syncthreads();
     const double s0 = sm.scal[2], sL = sm.scal[3];
     const double tol_abs = 2e-12 * ptot * inv_s;
+    if (i0 - la >= 1 && i0 + K3_ITEMS - 1 - la + ka - 1 <= L - 1) {
+      const double* pl = B + i0 - la - 1;
+      const double* ph = B + i0 - la + ka - 1;
 #pragma unroll
-    for (int k = 0; k < K3_ITEMS; ++k) {
-      const int i = i0 + k;
-      if (i < L) {
-        const double a = clamped_window(B, i - la, i - la + ka - 1, L, s0, sL) * inv_a;
-        const double thr = 1.5 * a;
-        sm.Q[i] = smv[k] > thr;
-        const double tol = 1e-9 * (smv[k] + thr) + tol_abs;
-        hazard |= (fabs(smv[k] - thr) <= tol) ? 1 : 0;
+      for (int k = 0; k < K3_ITEMS; ++k) {
+        const double thr = 1.5 * ((ph[k] - pl[k]) * inv_a);
+        qbits |= (unsigned)(smv[k] > thr) << k;
+        hazard |= (fabs(smv[k] - thr) <= 1e-9 * (smv[k] + thr) + tol_abs) ? 1 : 0;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < K3_ITEMS; ++k) {
+        const int i = i0 + k;
+        if (i < L) {
+          const double thr = 1.5 * (clamped_window(B, i - la, i - la + ka - 1, L, s0, sL) * inv_a);
+          qbits |= (unsigned)(smv[k] > thr) << k;
+          hazard |= (fabs(smv[k] - thr) <= 1e-9 * (smv[k] + thr) + tol_abs) ? 1 : 0;
+        }
       }
     }
     hazard = __syncthreads_or(hazard);
@@ -503,23 +549,23 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p) {
       }
     }
     __syncthreads();
+    qbits = 0;
+#pragma unroll
+    for (int k = 0; k < K3_ITEMS; ++k) if (i0 + k < L) qbits |= (unsigned)(sm.Q[i0 + k] != 0) << k;
   }
 
-  // ---- QRS runs: beg where ~q[i] & q[i+1], end where q[i] & ~q[i+1]  (ordered compaction)
+  // ---- QRS runs: beg where ~q[i] & q[i+1], end where q[i] & ~q[i+1]  (ordered compaction);
+  //      the flags live in registers, only each strip's first flag is exchanged
   {
-    const int i0 = tid * K3_ITEMS;
-    unsigned bbits = 0, ebits = 0;
-    int prev = (i0 < L) ? sm.Q[i0] : 0;
-#pragma unroll
-    for (int k = 0; k < K3_ITEMS; ++k) {
-      const int i = i0 + k;
-      const int nxt = (i + 1 < L) ? sm.Q[i + 1] : prev;    // beyond the window: no transition
-      if (i < L - 1) {
-        bbits |= (unsigned)(!prev && nxt) << k;
-        ebits |= (unsigned)(prev && !nxt) << k;
-      }
-      prev = nxt;
-    }
+    __syncthreads();                                   // everyone is done with sm.Q of a sequential pass
+    sm.Q[tid] = (unsigned char)(qbits & 1u);
+    __syncthreads();
+    const unsigned nbr = (tid + 1 < K3_NT) ? sm.Q[tid + 1] : 0u;
+    const unsigned nextq = (qbits >> 1) | (nbr << (K3_ITEMS - 1));          // flag of sample i + 1
+    int nvalid = L - 1 - i0;                            // transitions exist for i < L - 1
+    nvalid = nvalid < 0 ? 0 : (nvalid > K3_ITEMS ? K3_ITEMS : nvalid);
+    const unsigned vmask = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
+    unsigned bbits = ~qbits & nextq & vmask, ebits = qbits & ~nextq & vmask;
     const int packed = block_excl_scan_int(__popc(bbits) | (__popc(ebits) << 16), (int*)sm.wtot);
     int ob = packed & 0xffff, oe = packed >> 16;
     while (bbits) { const int k = __ffs(bbits) - 1; bbits &= bbits - 1; sm.beg[ob++] = (unsigned short)(i0 + k); }
@@ -558,7 +604,79 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p) {
     const double* d = A + b;
     double best = -1.0;
     int best_i = 0x7fffffff;
-    if (!((double)n < min_len)) {
+    if (!((double)n < min_len) && n <= 128) {
+      // warp-cooperative evaluation (runs of at most 128 samples): lane l holds d[32 m + l]
+      double v[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) v[m] = (32 * m + lane < n) ? d[32 * m + lane] : 0.0;
+      unsigned peakmask[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int i = 32 * m + lane;
+        bool rise = false;
+        int pk = i;
+        if (i >= 1 && i < n - 1 && d[i - 1] < v[m]) {       // start of a plateau (usually one sample)
+          int ahead = i + 1;
+          while (ahead < n - 1 && d[ahead] == v[m]) ++ahead;
+          if (d[ahead] < v[m]) { rise = true; pk = (i + ahead - 1) / 2; }
+        }
+        // a plateau's midpoint may sit in another lane: publish the peak at its own position
+        const unsigned starts = __ballot_sync(AEW_FULL, rise);
+        unsigned mine_pk = 0;
+        for (unsigned s = starts; s; s &= s - 1) {
+          const int src = __ffs(s) - 1;
+          const int q = __shfl_sync(AEW_FULL, pk, src);
+          if (q == i) mine_pk = 1;
+          else if ((q >> 5) != m && (q & 31) == lane) mine_pk |= 2u << (q >> 5);   // lands in another chunk
+        }
+        peakmask[m] = mine_pk;
+      }
+      // fold "lands in another chunk" marks (plateaus longer than a chunk are vanishingly rare but legal)
+      unsigned pkbits[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        bool is_pk = (peakmask[m] & 1u) != 0;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) is_pk |= (peakmask[o] & (2u << m)) != 0;
+        pkbits[m] = __ballot_sync(AEW_FULL, is_pk);
+      }
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        for (unsigned s = pkbits[m]; s; s &= s - 1) {
+          const int src = __ffs(s) - 1;
+          const int pk = 32 * m + src;
+          const double h = __shfl_sync(AEW_FULL, v[m], src);
+          // nearest strictly higher sample on each side (walks of scipy's _peak_prominences stop there)
+          int nl = -1, nr = n;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int i = 32 * c + lane;
+            const unsigned hi = __ballot_sync(AEW_FULL, i < n && v[c] > h);
+            if (hi) {
+              const unsigned below = (32 * c + 31 < pk) ? hi : ((32 * c > pk) ? 0u : (hi & ((1u << (pk - 32 * c)) - 1u)));
+              const unsigned above = (32 * c > pk) ? hi : ((32 * c + 31 < pk) ? 0u : (hi & ~((2u << (pk - 32 * c)) - 1u)));
+              if (below) { const int q = 32 * c + 31 - __clz((int)below); nl = q > nl ? q : nl; }
+              if (above) { const int q = 32 * c + __ffs((int)above) - 1; nr = q < nr ? q : nr; }
+            }
+          }
+          double lmin = h, rmin = h;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int i = 32 * c + lane;
+            if (i > nl && i <= pk && v[c] < lmin) lmin = v[c];
+            if (i >= pk && i < nr && v[c] < rmin) rmin = v[c];
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const double ol = __shfl_xor_sync(AEW_FULL, lmin, o), orr = __shfl_xor_sync(AEW_FULL, rmin, o);
+            lmin = ol < lmin ? ol : lmin;
+            rmin = orr < rmin ? orr : rmin;
+          }
+          const double prom = __dsub_rn(h, lmin > rmin ? lmin : rmin);
+          if (prom > best) { best = prom; best_i = pk; }       // candidates come in ascending order: first max wins
+        }
+      }
+    } else if (!((double)n < min_len)) {
       for (int i = 1 + lane; i < n - 1; i += 32) {
         if (d[i - 1] < d[i]) {
           int ahead = i + 1;
