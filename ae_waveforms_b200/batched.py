@@ -292,6 +292,59 @@ class Preprocessor:
         return res
 
 
+def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chunk_cases: int = 100,
+                       to_host: bool = True) -> dict:
+    """End-to-end path for HOST data: ``host_flat`` is a (preferably pinned) CPU float64
+    tensor holding all records back to back.  Cases are fed in chunks through two device
+    input buffers: the host->device copy of chunk k+1 (copy stream) overlaps the kernels of
+    chunk k (current stream), so the wall time is max(PCIe, kernels) instead of their sum.
+    Returns ``np_waves`` (n,320) f32 and ``np_info`` (n,2) f64 in case order, as host tensors
+    (``to_host``) or left on the device (e.g. for a following all-gather)."""
+    torch = pre.torch
+    rec_off = np.ascontiguousarray(rec_off, dtype=np.int64)
+    n_rec = len(rec_off) - 1
+    case_ids = np.arange(n_rec, dtype=np.int64) if case_ids is None else np.asarray(case_ids, dtype=np.int64)
+    chunks = [(c0, min(n_rec, c0 + chunk_cases)) for c0 in range(0, n_rec, chunk_cases)]
+    sizes = [int(rec_off[c1] - rec_off[c0]) for c0, c1 in chunks]
+    cap = max(sizes) if sizes else 0
+    bufs = [torch.empty(cap, dtype=torch.float64, device=pre.device) for _ in range(2)]
+    scratch = {"y": torch.empty(cap, dtype=torch.float64, device=pre.device),
+               "tmp": torch.empty(cap, dtype=torch.float64, device=pre.device)}
+    copy_stream = torch.cuda.Stream(device=pre.device)
+    main = torch.cuda.current_stream(pre.device)
+    copied = [torch.cuda.Event() for _ in chunks]
+    freed = [torch.cuda.Event() for _ in chunks]
+
+    def start_copy(k):
+        c0, c1 = chunks[k]
+        with torch.cuda.stream(copy_stream):
+            if k >= 2:
+                copy_stream.wait_event(freed[k - 2])          # the buffer's previous chunk has been consumed
+            bufs[k % 2][:sizes[k]].copy_(host_flat[int(rec_off[c0]):int(rec_off[c1])], non_blocking=True)
+            copied[k].record(copy_stream)
+
+    waves, infos, hazards, n_windows, n_beats = [], [], 0, 0, 0
+    if chunks:
+        start_copy(0)
+    for k, (c0, c1) in enumerate(chunks):
+        if k + 1 < len(chunks):
+            start_copy(k + 1)
+        main.wait_event(copied[k])
+        sub = RecordBatch(bufs[k % 2][:sizes[k]], rec_off[c0:c1 + 1] - rec_off[c0], case_ids[c0:c1])
+        sc = {"y": scratch["y"][:sizes[k]], "tmp": scratch["tmp"][:sizes[k]]}
+        res = pre.run(sub, scratch=sc)
+        freed[k].record(main)
+        waves.append(res["np_waves"].cpu() if to_host else res["np_waves"])
+        infos.append(res["np_info"].cpu() if to_host else res["np_info"])
+        hazards += res["hazard_windows"]
+        n_windows += res["n_windows"]
+        n_beats += res["n_beats"]
+    dev = None if to_host else pre.device
+    np_waves = torch.cat(waves) if waves else torch.zeros((0, BEAT_LEN), dtype=torch.float32, device=dev)
+    np_info = torch.cat(infos) if infos else torch.zeros((0, 2), dtype=torch.float64, device=dev)
+    return dict(np_waves=np_waves, np_info=np_info, hazard_windows=hazards, n_windows=n_windows, n_beats=n_beats)
+
+
 def process_cases(records, case_ids=None, **kwargs) -> dict:
     """Host convenience: list of 1-D float arrays -> NumPy ``np_waves`` (n,320) f32,
     ``np_features`` (n,35) f64 (NaN: the wave delineator is not on this path yet),

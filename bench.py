@@ -340,17 +340,17 @@ def run_gpu(args):
         host = torch.empty(total, dtype=torch.float64, pin_memory=True)
         host.copy_(flat)
         torch.cuda.synchronize()
-        dflat = torch.empty_like(flat)
+        del flat, batch, scratch
+        torch.cuda.empty_cache()
 
         def step_host():
-            dflat.copy_(host, non_blocking=True)
-            r = pre.run(batched.RecordBatch(dflat, rec_off, case_ids), scratch=scratch)
+            r = batched.run_host_pipelined(pre, host, rec_off, case_ids, chunk_cases=max(1, n_cases // 10),
+                                           to_host=False)
             w, i = r["np_waves"], r["np_info"]
             if world > 1:
                 w, i = awd.gather_beat_arrays(w, i)
             return w.cpu(), i.cpu()
 
-        del flat, batch
         for _ in range(min(2, args.warmup)):
             w_h, i_h = step_host()
         barrier()

@@ -331,3 +331,19 @@ def test_sigma_search_against_oracle(gpu):
     order_gpu = np.argsort(np.where(ok, sse, np.inf), kind="stable")
     order_ref = np.argsort(np.where(ok, want, np.inf), kind="stable")
     assert order_gpu[0] == order_ref[0], "optimal sigma map differs"
+
+
+def test_host_pipelined_equals_single_batch(gpu):
+    """The chunked, double-buffered host feeder returns exactly what one resident batch returns."""
+    torch, B = gpu
+    cases = [ecg_synth.synth_case(90 + i, 40000 + 3000 * i, nan_gaps=(i % 3 == 0)) for i in range(7)]
+    ids = list(range(90, 97))
+    batch = B.RecordBatch.from_host(cases, ids)
+    pre = B.Preprocessor()
+    want = pre.run(batch)
+    host = torch.from_numpy(np.concatenate(cases)).pin_memory()
+    for chunk in (2, 3, 100):
+        got = B.run_host_pipelined(pre, host, batch.rec_off, ids, chunk_cases=chunk)
+        assert same(got["np_waves"].numpy(), want["np_waves"].cpu().numpy())
+        assert same(got["np_info"].numpy(), want["np_info"].cpu().numpy())
+        assert got["n_windows"] == want["n_windows"]
