@@ -131,7 +131,7 @@ class Preprocessor:
         self.hp, self.lp, self.order = hp, lp, order
         self.pvc_threshold, self.sd_threshold = float(pvc_threshold), float(sd_threshold)
         self.filter_mode = {"fast": 0, "exact": 1}[filter_mode]
-        self.screen_mode = {"auto": 0, "exact": 1, "fast": 2}[screen_mode]
+        self.screen_mode = {"auto": 0, "exact": 1, "fast": 2, "forced_fallback": 3}[screen_mode]
         self.max_segments = max_segments
         self.launches = 0
         if self.L > self.lib.aew_windows_max_len():

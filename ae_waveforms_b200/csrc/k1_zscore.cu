@@ -42,6 +42,52 @@ struct LoadDev2 {  // pass 2: squared deviation from the mean, NaN -> 0
   }
 };
 
+// Leaf sum of K1 with the 16 loads of a lane issued back to back (raw values first, the
+// NaN test / deviation afterwards in registers) so that up to 16 x 8 B are in flight per lane.
+template <int PASS>
+__device__ __forceinline__ double k1_leaf_sum8(const double* __restrict__ x, double mean, long long off, int size,
+                                               int g, int& cnt) {
+  double v[16];
+  const int n8 = size & ~7;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] = (8 * k < n8) ? __ldg(x + off + 8 * k + g) : 0.0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const bool ok = !isnan(v[k]);
+    if (PASS == 1) {
+      cnt += (8 * k < n8 && ok) ? 1 : 0;
+      v[k] = ok ? v[k] : 0.0;
+    } else {
+      const double d = __dsub_rn(v[k], mean);
+      v[k] = ok ? __dmul_rn(d, d) : 0.0;
+    }
+  }
+  double r = v[0];
+#pragma unroll
+  for (int k = 1; k < 16; ++k)
+    if (8 * k < n8) r = __dadd_rn(r, v[k]);
+  double t = __shfl_xor_sync(AEW_FULL, r, 1);
+  r = __dadd_rn(r, t);
+  t = __shfl_xor_sync(AEW_FULL, r, 2);
+  r = __dadd_rn(r, t);
+  t = __shfl_xor_sync(AEW_FULL, r, 4);
+  r = __dadd_rn(r, t);
+  int i = n8;
+  if (size < 8) { r = 0.0; i = 0; }
+  for (; i < size; ++i) {
+    const double w = __ldg(x + off + i);
+    const bool ok = !isnan(w);
+    if (PASS == 1) {
+      cnt += (g == 0 && ok) ? 1 : 0;
+      r = __dadd_rn(r, ok ? w : 0.0);
+    } else {
+      const double d = __dsub_rn(w, mean);
+      r = __dadd_rn(r, ok ? __dmul_rn(d, d) : 0.0);
+    }
+  }
+  return r;
+}
+
 __device__ __forceinline__ long long find_record(const long long* __restrict__ start, long long n_rec,
                                                  long long b) {
   long long lo = 0, hi = n_rec;  // start[lo] <= b < start[hi]
@@ -74,16 +120,8 @@ __global__ void __launch_bounds__(256) k1_leaf(const double* __restrict__ x, con
   const int group = threadIdx.x >> 3, g = threadIdx.x & 7;
   long long off = 0, size = 0;
   if (group < (1 << sub)) pw_node(n, depth, (j << sub) + (unsigned)group, off, size);
-  double v;
   int mycnt = 0;
-  if (PASS == 1) {
-    LoadSum f{x + base, 0};
-    v = pw_leaf_sum8(f, off, (int)size, g);
-    mycnt = f.cnt;
-  } else {
-    LoadDev2 f{x + base, mean[r], 0};
-    v = pw_leaf_sum8(f, off, (int)size, g);
-  }
+  const double v = k1_leaf_sum8<PASS>(x + base, PASS == 2 ? mean[r] : 0.0, off, (int)size, g, mycnt);
   if (g == 0) { s_vals[group] = v; s_valid[group] = size > 0; }
   if (PASS == 1) {
 #pragma unroll

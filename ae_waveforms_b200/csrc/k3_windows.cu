@@ -515,6 +515,7 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p) {
     }
     hazard = __syncthreads_or(hazard);
     if (p.mode == 2) hazard = 0;
+    if (p.mode == 3) hazard = 1;                        // test hook: every window takes the fallback transition
     if (hazard && tid == 0 && p.hazard_count) atomicAdd(p.hazard_count, 1ull);
   }
   if (p.mode == 1 || hazard) {

@@ -103,7 +103,8 @@ typedef struct K3Params {
   double hr_num;              /* 60 * fs */
   double rr_div;              /* fs * 1000 (remove_samples.py:119) */
   double hr_lo, hr_hi, pvc_threshold, sd_threshold;   /* 30, 180, 150, 0.05 */
-  int mode;                   /* 0 fast + exact fallback on hazard windows, 1 exact everywhere, 2 fast only */
+  int mode;                   /* 0 fast + exact fallback on hazard windows, 1 exact everywhere, 2 fast only,
+                                 3 fast then forced fallback (test hook for the hazard transition) */
   int zscore_windows;         /* 1: z-score each window first (data_extract_vitaldb.py:93); 0: windows are
                                  already z-scored by the caller (the remove_samples() drop-in) */
   unsigned char* keep;        /* device outputs, one entry per window */

@@ -347,3 +347,48 @@ def test_host_pipelined_equals_single_batch(gpu):
         assert same(got["np_waves"].numpy(), want["np_waves"].cpu().numpy())
         assert same(got["np_info"].numpy(), want["np_info"].cpu().numpy())
         assert got["n_windows"] == want["n_windows"]
+
+
+def test_screen_forced_fallback_transition(gpu, golden):
+    """mode 3 runs the parallel box filters and then the sequential fallback for every window
+    (the path a hazard window takes); results must equal both other modes."""
+    torch, B = gpu
+    g = golden("e2e")
+    nw = int(g["n_windows"])
+    ref = _screen(B, g["filtered"], np.arange(nw) * 10000, screen_mode="exact")
+    got = _screen(B, g["filtered"], np.arange(nw) * 10000, screen_mode="forced_fallback")
+    for k in ("keep", "has_nan", "n_peaks", "peaks", "stats"):
+        assert same(got[k], ref[k]), k
+    kept = np.flatnonzero(ref["keep"])
+    assert same(got["median"][kept], ref["median"][kept]) and int(got["hazards"][0]) == int((ref["has_nan"] == 0).sum())
+
+
+def test_filter_many_nan_islands(gpu):
+    """1 % random NaNs: thousands of tiny segments (pass-through and filtered), both modes; and the
+    segment-table overflow is reported, not ignored."""
+    torch, B = gpu
+    from ae_waveforms_b200 import _cabi
+    rng = np.random.default_rng(12)
+    x = ecg_synth.synth_case(95, 120000)
+    x[rng.random(x.size) < 0.01] = np.nan
+    x[40000:40100] = np.nan
+    ref = rp.butterworth(rp.butterworth(rp.zscore(x), "high", 1), "low", 30)
+    batch = B.RecordBatch.from_host([x])
+    for mode in ("exact", "fast"):
+        pre = B.Preprocessor(filter_mode=mode, max_segments=4096)
+        beg_h, end_h, d_beg, d_end = pre._ranges(batch, trim=False)
+        mean, sd, cnt = pre.zscore_stats(batch.flat, beg_h, end_h, d_beg, d_end)
+        y, hdr = pre.filter_records(batch.flat, beg_h, end_h, d_beg, d_end, mean, sd, cnt)
+        assert int(hdr[4].item()) == 0 and int(hdr[0].item()) > 1000
+        y = y.cpu().numpy()
+        assert same(y, ref) if mode == "exact" else close(y, ref)
+    small = B.Preprocessor(max_segments=64)
+    with pytest.raises(_cabi.AewError):
+        small.run(batch)
+
+
+def test_empty_and_windowless_batches(gpu):
+    torch, B = gpu
+    pre = B.Preprocessor()
+    res = pre.run(B.RecordBatch.from_host([ecg_synth.synth_case(1, 9000), np.full(300, np.nan)], [5, 6]))
+    assert res["np_waves"].shape == (0, 320) and res["np_info"].shape == (0, 2) and res["n_windows"] == 0
