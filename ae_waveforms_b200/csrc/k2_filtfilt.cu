@@ -337,9 +337,14 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
   long long n_tiles = a.ws.hdr[H_TILE_TOTAL];
   if (n_tiles > a.ws.max_tiles) n_tiles = a.ws.max_tiles;
 
-  // prologue: claim the first tile and start its copy
+  // prologue: claim the first tile and start its copy.  Thread 0 keeps a small software pipeline so that
+  // neither the claim (atomic) nor the tile-table read is waited for in the iteration that issues it:
+  // id1/raw1 = tile it+1 (table entry already loaded), id2 = tile it+2 (claimed)
+  long long id1 = 0, id2 = 0, raw1[4] = {0, 0, 0, 0};
   if (tid == 0) {
     const long long t = (long long)atomicAdd((unsigned long long*)work, 1ull);
+    id1 = (long long)atomicAdd((unsigned long long*)work, 1ull);
+    id2 = (long long)atomicAdd((unsigned long long*)work, 1ull);
     s_tile[0] = t;
     if (t < n_tiles) {
       long long rw[4];
@@ -347,6 +352,8 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
       const TileDesc d = describe_tile<REV>(rw, a.bulk_ok, pad);
       if (d.bulk) bulk_load(stage0, a.src + d.gstart, K2_T * 8u, &s_bar[0]);
     }
+    if (id1 < n_tiles)
+      for (int i = 0; i < 4; ++i) raw1[i] = a.ws.tile_desc[4 * id1 + i];
   }
   __syncthreads();
   unsigned parity_bits = 0;                          // bit s: phase parity of ring slot s's mbarrier
@@ -363,28 +370,30 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
     const int st = it % K2_STAGES;
     const long long tile = s_tile[st];
     const bool live = tile < n_tiles;
-    double Qe[2][4];                                   // thread 0: early look-back loads for the pending tile
-    bool qe_ok[2] = {false, false};
+    double Qe[3][4];                                   // thread 0: early look-back loads for the pending tile
+    bool qe_ok[3] = {false, false, false};
     if (tid == 0) {
       if (live) {
-        // claim the next tile and start its copy into the next ring slot; the slot's previous
-        // occupant was stored two iterations ago (one bulk group is committed per iteration)
+        // start the copy of the next tile into the next ring slot; the slot's previous occupant was
+        // handed to a bulk store two iterations ago (one bulk group is committed per iteration)
         const int nst = (it + 1) % K2_STAGES;
-        const long long t = (long long)atomicAdd((unsigned long long*)work, 1ull);
-        s_tile[nst] = t;
-        if (t < n_tiles) {
-          long long rw[4];
-          for (int i = 0; i < 4; ++i) rw[i] = a.ws.tile_desc[4 * t + i];
-          const TileDesc dn = describe_tile<REV>(rw, a.bulk_ok, pad);
+        s_tile[nst] = id1;
+        if (id1 < n_tiles) {
+          const TileDesc dn = describe_tile<REV>(raw1, a.bulk_ok, pad);
           if (dn.bulk) {
             bulk_store_wait_read(1);
             bulk_load(stage0 + nst * K2_T, a.src + dn.gstart, K2_T * 8u, &s_bar[nst]);
           }
         }
+        id1 = id2;                                     // advance the pipeline: results are consumed next iteration
+        if (id1 < n_tiles)
+          for (int i = 0; i < 4; ++i) raw1[i] = a.ws.tile_desc[4 * id1 + i];
+        id2 = (long long)atomicAdd((unsigned long long*)work, 1ull);
       }
       if (have_prev && dp.k > 0) {                     // issue the look-back loads now, use them after this tile's recursion
         qe_ok[0] = load_state(tstate + 4 * (tile_p - 1), Qe[0]);
         if (dp.k > 1 && lookback > 1) qe_ok[1] = load_state(tstate + 4 * (tile_p - 2), Qe[1]);
+        if (dp.k > 2 && lookback > 2) qe_ok[2] = load_state(tstate + 4 * (tile_p - 3), Qe[2]);
       }
     }
 
@@ -506,7 +515,7 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
           for (long long j = 0; j < depth; ++j) {
             double Q[4];
             bool ok = false;
-            if (j < 2 && qe_ok[j]) {
+            if (j < 3 && qe_ok[j]) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) Q[i] = Qe[j][i];
               ok = true;
