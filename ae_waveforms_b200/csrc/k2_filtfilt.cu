@@ -39,6 +39,7 @@
 //
 // Algorithmic HBM bytes: 16 B/sample per pass, 32 B/sample per filtfilt
 // (SURVEY.md section 8d).  Roofline: HBM; FP64 work is ~17 FMA/sample/pass.
+#include <stdlib.h>
 #include "aew_rt.h"
 #include "aew_math.cuh"
 #include "k2_layout.h"
@@ -226,6 +227,7 @@ struct PassArgs {
   const double* tab;      // device coefficient table (k2_layout.h)
   K2Ws ws;
   int bulk_ok;            // src and dst base pointers are 16-byte aligned: bulk (TMA) copies allowed
+  unsigned long long* dbg; // optional phase-cycle counters (AEW_K2_TIMING=1), else null
 };
 
 // ---- bulk asynchronous copies (TMA, 1-D) and their mbarrier; the emulation build copies synchronously
@@ -303,6 +305,7 @@ __device__ __forceinline__ TileDesc describe_tile(const long long raw[4], int bu
 // the all-ones bit pattern (the workspace is memset to 0xFF before each pass), so the values
 // are their own flags and no fence is needed on either side
 #define K2_EMPTY 0xffffffffffffffffull
+#define K2_PRODUCER 32               // thread that claims tiles and issues the bulk copies (warp 1, lane 0)
 
 __device__ __forceinline__ bool load_state(const double* p, double q[4]) {
   const volatile unsigned long long* v = (const volatile unsigned long long*)p;
@@ -312,14 +315,29 @@ __device__ __forceinline__ bool load_state(const double* p, double q[4]) {
   return b0 != K2_EMPTY && b1 != K2_EMPTY && b2 != K2_EMPTY && b3 != K2_EMPTY;
 }
 
+#ifdef AEW_EMUL
+#define K2_TICK(slot)
+#else
+#define K2_TICK(slot)                                                   \
+  if (a.dbg && tid == 0) {                                              \
+    const long long now_ = clock64();                                   \
+    atomicAdd(a.dbg + (slot), (unsigned long long)(now_ - tick_));      \
+    tick_ = now_;                                                       \
+  }
+#endif
+
 template <bool REV>
 __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
+  long long tick_ = 0;
+  (void)tick_;
   AEW_DYN_SMEM(smem_raw);
   double* stage0 = (double*)smem_raw;                 // [K2_STAGES][K2_T] tile ring
   double* s_tab = stage0 + K2_STAGES * K2_T;          // [K2_TAB_LEN]
   double* s_Wb = s_tab + K2_TAB_LEN;                  // [2][K2_NW][4] warp totals (double buffered)
   double* s_S = s_Wb + 8 * K2_NW;                     // [K2_NW][4] state entering each warp
   double* s_in = s_S + 4 * K2_NW;                     // [2][4] state entering a segment's first tile
+  double* s_X = s_in + 8;                             // [2][K2_NW][4] Horner prefixes: state entering each warp
+                                                      //   of a tile, up to the contribution of the look-back
   __shared__ unsigned long long s_bar[K2_STAGES];
   __shared__ long long s_tile[K2_STAGES];
 
@@ -341,7 +359,7 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
   // neither the claim (atomic) nor the tile-table read is waited for in the iteration that issues it:
   // id1/raw1 = tile it+1 (table entry already loaded), id2 = tile it+2 (claimed)
   long long id1 = 0, id2 = 0, raw1[4] = {0, 0, 0, 0};
-  if (tid == 0) {
+  if (tid == K2_PRODUCER) {
     const long long t = (long long)atomicAdd((unsigned long long*)work, 1ull);
     id1 = (long long)atomicAdd((unsigned long long*)work, 1ull);
     id2 = (long long)atomicAdd((unsigned long long*)work, 1ull);
@@ -366,36 +384,31 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
   double Ep[4] = {0.0, 0.0, 0.0, 0.0};
   double* sm_p = stage0;
 
+#ifndef AEW_EMUL
+  tick_ = clock64();
+#endif
   for (int it = 0;; ++it) {
     const int st = it % K2_STAGES;
     const long long tile = s_tile[st];
     const bool live = tile < n_tiles;
-    double Qe[3][4];                                   // thread 0: early look-back loads for the pending tile
-    bool qe_ok[3] = {false, false, false};
-    if (tid == 0) {
-      if (live) {
-        // start the copy of the next tile into the next ring slot; the slot's previous occupant was
-        // handed to a bulk store two iterations ago (one bulk group is committed per iteration)
-        const int nst = (it + 1) % K2_STAGES;
-        s_tile[nst] = id1;
-        if (id1 < n_tiles) {
-          const TileDesc dn = describe_tile<REV>(raw1, a.bulk_ok, pad);
-          if (dn.bulk) {
-            bulk_store_wait_read(1);
-            bulk_load(stage0 + nst * K2_T, a.src + dn.gstart, K2_T * 8u, &s_bar[nst]);
-          }
-        }
-        id1 = id2;                                     // advance the pipeline: results are consumed next iteration
-        if (id1 < n_tiles)
-          for (int i = 0; i < 4; ++i) raw1[i] = a.ws.tile_desc[4 * id1 + i];
-        id2 = (long long)atomicAdd((unsigned long long*)work, 1ull);
+    // thread 0: issue the look-back loads of the pending tile now (raw bits, no test yet) so that their
+    // round trip overlaps this tile's recursion; they are examined after the barrier
+    unsigned long long q0[4] = {K2_EMPTY, K2_EMPTY, K2_EMPTY, K2_EMPTY}, q1[4] = {K2_EMPTY, K2_EMPTY, K2_EMPTY, K2_EMPTY},
+                       q2[4] = {K2_EMPTY, K2_EMPTY, K2_EMPTY, K2_EMPTY};
+    if (tid == 0 && have_prev && dp.k > 0) {
+      const volatile unsigned long long* v0 = (const volatile unsigned long long*)(tstate + 4 * (tile_p - 1));
+#pragma unroll
+      for (int i = 0; i < 4; ++i) q0[i] = v0[i];
+      if (dp.k > 1 && lookback > 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) q1[i] = v0[i - 4];
       }
-      if (have_prev && dp.k > 0) {                     // issue the look-back loads now, use them after this tile's recursion
-        qe_ok[0] = load_state(tstate + 4 * (tile_p - 1), Qe[0]);
-        if (dp.k > 1 && lookback > 1) qe_ok[1] = load_state(tstate + 4 * (tile_p - 2), Qe[1]);
-        if (dp.k > 2 && lookback > 2) qe_ok[2] = load_state(tstate + 4 * (tile_p - 3), Qe[2]);
+      if (dp.k > 2 && lookback > 2) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) q2[i] = v0[i - 8];
       }
     }
+    K2_TICK(0)
 
     // =================== A half: recursion and scan of the current tile ===================
     TileDesc d;
@@ -423,7 +436,7 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
             atomicOr((int*)(a.ws.hdr + H_STATUS), AEW_DEV_LOOKBACK_TIMEOUT);
           parity_bits ^= 1u << st;
         } else {
-          if (tid == 0) bulk_store_wait_read(0);       // the slot may still be read by an earlier bulk store
+          if (tid == K2_PRODUCER) bulk_store_wait_read(0);   // the slot may still be read by an earlier bulk store
           __syncthreads();
           for (int j = tid; j < K2_T; j += K2_NT) {    // cooperative copy, zero padded
             double v = 0.0;
@@ -435,6 +448,7 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
           }
           __syncthreads();
         }
+        K2_TICK(6)   // tile data ready (mbarrier wait / cooperative copy)
         // first tile of a segment: run the odd extension (padlen samples) from SciPy's zi-scaled state
         if (d.k == 0 && tid == 0) {
           double z[4];
@@ -465,6 +479,7 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
 #pragma unroll
           for (int j = 0; j < K2_C; ++j) mine[dir * j] = modal_step(cf, mine[dir * j], E);
         }
+        K2_TICK(7)   // phase 1 recursion
         // phase 2a: warp scan of chunk end states (Kogge-Stone with p^(C*2^k))
 #pragma unroll
         for (int kk = 0; kk < 5; ++kk) {
@@ -480,19 +495,48 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
         }
       }
     }
+    K2_TICK(1)   // A half (thread 0's own work)
     __syncthreads();
+    K2_TICK(2)   // wait at the barrier after the A half
+
+    // producer thread (warp 1): runs while thread 0 works through its serial section below
+    if (tid == K2_PRODUCER) {
+      if (live) {
+        // start the copy of the next tile into the next ring slot; the slot's previous occupant was
+        // handed to a bulk store two iterations ago (one bulk group is committed per iteration)
+        const int nst = (it + 1) % K2_STAGES;
+        s_tile[nst] = id1;
+        if (id1 < n_tiles) {
+          const TileDesc dn = describe_tile<REV>(raw1, a.bulk_ok, pad);
+          if (dn.bulk) {
+            bulk_store_wait_read(1);
+            bulk_load(stage0 + nst * K2_T, a.src + dn.gstart, K2_T * 8u, &s_bar[nst]);
+          }
+        }
+        id1 = id2;                                     // advance the pipeline: results are consumed next iteration
+        if (id1 < n_tiles)
+          for (int i = 0; i < 4; ++i) raw1[i] = a.ws.tile_desc[4 * id1 + i];
+        id2 = (long long)atomicAdd((unsigned long long*)work, 1ull);
+      }
+    }
 
     // =================== thread 0: publish this tile, resolve the pending tile ===================
     if (tid == 0) {
       if (filt) {
+        // Horner chain over the warp totals.  Its prefixes are the states entering each warp (given the
+        // state entering the tile, which is known for a first tile and zero otherwise): keep them for the
+        // B half of the next iteration.  The last value is the tile's published end state.
         const double* W = s_Wb + (it & 1) * 4 * K2_NW;
-        double Z[4] = {0.0, 0.0, 0.0, 0.0};           // end state of the tile: inclusive for a first tile,
-        if (d.k == 0) {                               // zero-state aggregate otherwise
+        double* X = s_X + (it & 1) * 4 * K2_NW;
+        double Z[4] = {0.0, 0.0, 0.0, 0.0};
+        if (d.k == 0) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) Z[i] = s_in[4 * (it & 1) + i];
         }
         for (int w = 0; w < K2_NW; ++w) {
           double t[4] = {W[4 * w], W[4 * w + 1], W[4 * w + 2], W[4 * w + 3]};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) X[4 * w + i] = Z[i];
           cmul_acc(PW, Z, t);
 #pragma unroll
           for (int i = 0; i < 4; ++i) Z[i] = t[i];
@@ -502,51 +546,59 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
         for (int i = 0; i < 4; ++i) pub[i] = Z[i];
       }
       if (have_prev) {
-        const double* W = s_Wb + ((it + 1) & 1) * 4 * K2_NW;
+        const double* X = s_X + ((it + 1) & 1) * 4 * K2_NW;
         double S[4] = {0.0, 0.0, 0.0, 0.0};
-        if (dp.k == 0) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) S[i] = s_in[4 * ((it + 1) & 1) + i];
-        } else {
+        if (dp.k > 0) {
           // S = sum_j (p^T)^j Q[tile_p-1-j], j < min(lookback, k)
           const double* PT = s_tab + K2_TAB_PTILE;
           double Wm[4] = {1.0, 0.0, 1.0, 0.0};
           const long long depth = dp.k < lookback ? dp.k : lookback;
-          for (long long j = 0; j < depth; ++j) {
-            double Q[4];
-            bool ok = false;
-            if (j < 3 && qe_ok[j]) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) Q[i] = Qe[j][i];
-              ok = true;
-            }
-            unsigned spins = 0;
-            while (!ok) {
-              ok = load_state(tstate + 4 * (tile_p - 1 - j), Q);
-              if (!ok) {
-                __nanosleep(32);
-                if (++spins > (1u << 22)) { atomicOr((int*)(a.ws.hdr + H_STATUS), AEW_DEV_LOOKBACK_TIMEOUT); break; }
-              }
-            }
-            cmul_acc(Wm, Q, S);
-            if (j + 1 < depth) {                      // Wm <- Wm * p^T
-              const double w0 = Wm[0] * PT[0] - Wm[1] * PT[1], w1 = Wm[0] * PT[1] + Wm[1] * PT[0];
-              const double w2 = Wm[2] * PT[2] - Wm[3] * PT[3], w3 = Wm[2] * PT[3] + Wm[3] * PT[2];
-              Wm[0] = w0; Wm[1] = w1; Wm[2] = w2; Wm[3] = w3;
-            }
+          // the first three predecessors were loaded at the top of the iteration (registers q0..q2, no
+          // dynamic indexing: a pointer into them would push them to local memory and stall the loads)
+#define K2_LOOKBACK_STEP(J, QR)                                                                              \
+          if ((J) < depth) {                                                                                    \
+            double Q[4];                                                                                        \
+            bool ok = QR[0] != K2_EMPTY && QR[1] != K2_EMPTY && QR[2] != K2_EMPTY && QR[3] != K2_EMPTY;         \
+            Q[0] = __longlong_as_double((long long)QR[0]); Q[1] = __longlong_as_double((long long)QR[1]);       \
+            Q[2] = __longlong_as_double((long long)QR[2]); Q[3] = __longlong_as_double((long long)QR[3]);       \
+            unsigned spins = 0;                                                                                 \
+            while (!ok) {                                                                                       \
+              ok = load_state(tstate + 4 * (tile_p - 1 - (J)), Q);                                              \
+              if (!ok) {                                                                                        \
+                __nanosleep(32);                                                                                \
+                if (++spins > (1u << 22)) { atomicOr((int*)(a.ws.hdr + H_STATUS), AEW_DEV_LOOKBACK_TIMEOUT); break; } \
+              }                                                                                                 \
+            }                                                                                                   \
+            cmul_acc(Wm, Q, S);                                                                                 \
+            if ((J) + 1 < depth) {                                                                              \
+              const double w0 = Wm[0] * PT[0] - Wm[1] * PT[1], w1 = Wm[0] * PT[1] + Wm[1] * PT[0];              \
+              const double w2 = Wm[2] * PT[2] - Wm[3] * PT[3], w3 = Wm[2] * PT[3] + Wm[3] * PT[2];              \
+              Wm[0] = w0; Wm[1] = w1; Wm[2] = w2; Wm[3] = w3;                                                   \
+            }                                                                                                   \
           }
+          K2_LOOKBACK_STEP(0, q0)
+          K2_LOOKBACK_STEP(1, q1)
+          K2_LOOKBACK_STEP(2, q2)
+          for (long long j = 3; j < depth; ++j) {      // deeper look-backs (slowly decaying filters)
+            const unsigned long long none[4] = {K2_EMPTY, K2_EMPTY, K2_EMPTY, K2_EMPTY};
+            K2_LOOKBACK_STEP(j, none)
+          }
+#undef K2_LOOKBACK_STEP
         }
-        for (int w = 0; w < K2_NW; ++w) {             // state entering each warp
+        // state entering warp w = prefix kept from the tile's own chain + p^(32 C w) S  (independent terms)
+        const double* PWP = s_tab + K2_TAB_PWP;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) s_S[4 * w + i] = S[i];
-          double t[4] = {W[4 * w], W[4 * w + 1], W[4 * w + 2], W[4 * w + 3]};
-          cmul_acc(PW, S, t);
+        for (int w = 0; w < K2_NW; ++w) {
+          double t[4] = {X[4 * w], X[4 * w + 1], X[4 * w + 2], X[4 * w + 3]};
+          if (dp.k > 0) cmul_acc(PWP + 4 * w, S, t);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) S[i] = t[i];
+          for (int i = 0; i < 4; ++i) s_S[4 * w + i] = t[i];
         }
       }
     }
+    K2_TICK(3)   // publish / look-back / chains
     __syncthreads();
+    K2_TICK(4)
 
     // =================== B half: correct and store the pending tile ===================
     if (have_prev) {
@@ -585,18 +637,19 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
       if (dp.bulk) {
         fence_async_smem();                            // my shared-memory writes -> visible to the bulk engine
         __syncthreads();
-        if (tid == 0) bulk_store(a.dst + dp.gstart, sm_p, K2_T * 8u);
+        if (tid == K2_PRODUCER) bulk_store(a.dst + dp.gstart, sm_p, K2_T * 8u);
       } else {
         __syncthreads();
         for (int j = tid; j < dp.cnt; j += K2_NT) {
           const long long p = dp.t0 + j;
           a.dst[REV ? (dp.g0 + dp.n - 1 - p) : (dp.g0 + p)] = sm_p[j];
         }
-        if (tid == 0) bulk_commit_empty();
+        if (tid == K2_PRODUCER) bulk_commit_empty();
       }
-    } else if (tid == 0) {
+    } else if (tid == K2_PRODUCER) {
       bulk_commit_empty();                             // one bulk group per iteration keeps wait_group.read 1 exact
     }
+    K2_TICK(5)   // B half incl. its barrier and the store hand-off
     if (!live) break;
     have_prev = filt;
     dp = d;
@@ -605,7 +658,7 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) Ep[i] = E[i];
   }
-  if (tid == 0) bulk_store_wait_all();
+  if (tid == K2_PRODUCER) bulk_store_wait_all();
 }
 
 // ------------------------------------------------------------ exact sequential mode
@@ -652,6 +705,7 @@ __global__ void __launch_bounds__(32) k2_exact(PassArgs a) {
   for (long long i = n - 1; i >= 0; --i) out[i] = df2t_step_exact(b, ac, ord, tmp[i], z);
 }
 
+unsigned long long* g_dbg = nullptr;   // device counters, allocated once when AEW_K2_TIMING is set
 int g_sm_count = 0;
 inline int sm_count() {
 #ifdef AEW_EMUL
@@ -712,13 +766,20 @@ extern "C" int aew_filtfilt_f64(const double* src, const double* mean, const dou
   PassArgs a;
   a.src = src; a.mean = mean; a.sd = sd; a.dst = tmp; a.passthrough = out; a.tab = d_tab; a.ws = w;
   a.bulk_ok = ((((size_t)src | (size_t)out | (size_t)tmp) & 15) == 0) ? 1 : 0;
+  a.dbg = nullptr;
+#ifndef AEW_EMUL
+  if (getenv("AEW_K2_TIMING")) {
+    if (!g_dbg) { cudaMalloc(&g_dbg, 16 * sizeof(unsigned long long)); cudaMemset(g_dbg, 0, 16 * sizeof(unsigned long long)); }
+    a.dbg = g_dbg;
+  }
+#endif
   if (mode == 1) {
     const long long blocks = (max_seg + 31) / 32;
     AEW_LAUNCH(k2_exact, (unsigned)blocks, 32, 0, st, a);
     return (int)cudaGetLastError();
   }
   if (mode != 0) return AEW_ERR_ARG;
-  const size_t smem = (size_t)(K2_STAGES * K2_T + K2_TAB_LEN + 12 * K2_NW + 8) * sizeof(double);
+  const size_t smem = (size_t)(K2_STAGES * K2_T + K2_TAB_LEN + 20 * K2_NW + 8) * sizeof(double);
   static bool attr_done = false;
   if (!attr_done) {
     AEW_SET_MAX_SMEM(k2_pass<false>, smem);
@@ -744,4 +805,18 @@ extern "C" int aew_filt_header(void* ws, long long** d_header_out) {
   if (!ws || !d_header_out) return AEW_ERR_ARG;
   *d_header_out = (long long*)align_up((size_t)ws, 128);
   return AEW_OK;
+}
+
+// debugging aid (AEW_K2_TIMING=1): cycles thread 0 of every block spent in each phase of k2_pass, summed
+extern "C" int aew_filt_timing_dump(unsigned long long* h_out8) {
+#ifndef AEW_EMUL
+  if (!g_dbg || !h_out8) return AEW_ERR_ARG;
+  cudaDeviceSynchronize();
+  cudaMemcpy(h_out8, g_dbg, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaMemset(g_dbg, 0, 16 * sizeof(unsigned long long));
+  return AEW_OK;
+#else
+  (void)h_out8;
+  return AEW_ERR_UNSUPPORTED;
+#endif
 }

@@ -84,6 +84,9 @@ int aew_segments_find_f64(const double* d_x, const long long* d_rec_beg, const l
 int aew_filtfilt_f64(const double* d_src, const double* d_mean /* may be NULL */, const double* d_sd,
                      double* d_out, double* d_tmp, const double* d_tab, long long n_rec, long long total_samples,
                      void* d_ws, size_t ws_bytes, long long max_seg, int mode, void* stream);
+/* debugging aid: with AEW_K2_TIMING=1 in the environment, k2_pass accumulates the cycles thread 0 of every
+ * block spends per phase; this copies and clears the 8 counters (synchronises the device) */
+int aew_filt_timing_dump(unsigned long long* h_out8);
 /* device address of the 8 x int64 workspace header: [0] segments found, [1] tiles, [4] status bits */
 int aew_filt_header(void* d_ws, long long** d_header_out);
 
