@@ -520,35 +520,52 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
       }
     }
 
-    // =================== thread 0: publish this tile, resolve the pending tile ===================
-    if (tid == 0) {
+    // =================== warp 0: publish this tile, resolve the pending tile ===================
+    // Lane w < NW holds the total of warp w.  An inclusive Kogge-Stone scan with p^(32 C m) gives, shifted by
+    // one lane, the state entering every warp (up to the contribution of the state entering the tile);
+    // three dependent steps instead of an eight-step Horner chain.  Lane 0 resolves the look-back.
+    if (warp == 0) {
+      const double* PWP = s_tab + K2_TAB_PWP;
       if (filt) {
-        // Horner chain over the warp totals.  Its prefixes are the states entering each warp (given the
-        // state entering the tile, which is known for a first tile and zero otherwise): keep them for the
-        // B half of the next iteration.  The last value is the tile's published end state.
-        const double* W = s_Wb + (it & 1) * 4 * K2_NW;
-        double* X = s_X + (it & 1) * 4 * K2_NW;
-        double Z[4] = {0.0, 0.0, 0.0, 0.0};
-        if (d.k == 0) {
+        double I[4] = {0.0, 0.0, 0.0, 0.0};
+        if (lane < K2_NW) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) Z[i] = s_in[4 * (it & 1) + i];
+          for (int i = 0; i < 4; ++i) I[i] = s_Wb[(it & 1) * 4 * K2_NW + 4 * lane + i];
         }
-        for (int w = 0; w < K2_NW; ++w) {
-          double t[4] = {W[4 * w], W[4 * w + 1], W[4 * w + 2], W[4 * w + 3]};
 #pragma unroll
-          for (int i = 0; i < 4; ++i) X[4 * w + i] = Z[i];
-          cmul_acc(PW, Z, t);
+        for (int kk = 0; kk < 3; ++kk) {
+          const int dd = 1 << kk;
+          double o[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) Z[i] = t[i];
+          for (int i = 0; i < 4; ++i) o[i] = __shfl_up_sync(AEW_FULL, I[i], dd);
+          if (lane >= dd && lane < K2_NW) cmul_acc(PWP + 4 * dd, o, I);
         }
-        volatile double* pub = tstate + 4 * tile;
+        double Xw[4];                                  // exclusive scan = state entering warp `lane`
 #pragma unroll
-        for (int i = 0; i < 4; ++i) pub[i] = Z[i];
+        for (int i = 0; i < 4; ++i) {
+          const double up = __shfl_up_sync(AEW_FULL, I[i], 1);
+          Xw[i] = lane == 0 ? 0.0 : up;
+        }
+        if (lane < K2_NW) {
+          double Z[4] = {I[0], I[1], I[2], I[3]};
+          if (d.k == 0) {                              // first tile of a segment: the entering state is known
+            const double S0[4] = {s_in[4 * (it & 1)], s_in[4 * (it & 1) + 1], s_in[4 * (it & 1) + 2], s_in[4 * (it & 1) + 3]};
+            cmul_acc(PWP + 4 * lane, S0, Xw);
+            if (lane == K2_NW - 1) cmul_acc(PWP + 4 * K2_NW, S0, Z);
+          }
+          double* X = s_X + (it & 1) * 4 * K2_NW;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) X[4 * lane + i] = Xw[i];
+          if (lane == K2_NW - 1) {                     // publish the tile's end state
+            volatile double* pub = tstate + 4 * tile;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pub[i] = Z[i];
+          }
+        }
       }
       if (have_prev) {
-        const double* X = s_X + ((it + 1) & 1) * 4 * K2_NW;
         double S[4] = {0.0, 0.0, 0.0, 0.0};
-        if (dp.k > 0) {
+        if (lane == 0 && dp.k > 0) {
           // S = sum_j (p^T)^j Q[tile_p-1-j], j < min(lookback, k)
           const double* PT = s_tab + K2_TAB_PTILE;
           double Wm[4] = {1.0, 0.0, 1.0, 0.0};
@@ -562,6 +579,8 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
             Q[0] = __longlong_as_double((long long)QR[0]); Q[1] = __longlong_as_double((long long)QR[1]);       \
             Q[2] = __longlong_as_double((long long)QR[2]); Q[3] = __longlong_as_double((long long)QR[3]);       \
             unsigned spins = 0;                                                                                 \
+            if (!ok && a.dbg) atomicAdd(a.dbg + 9, 1ull);                                                       \
+            if (a.dbg) atomicAdd(a.dbg + 10, 1ull);                                                              \
             while (!ok) {                                                                                       \
               ok = load_state(tstate + 4 * (tile_p - 1 - (J)), Q);                                              \
               if (!ok) {                                                                                        \
@@ -585,14 +604,15 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
           }
 #undef K2_LOOKBACK_STEP
         }
-        // state entering warp w = prefix kept from the tile's own chain + p^(32 C w) S  (independent terms)
-        const double* PWP = s_tab + K2_TAB_PWP;
+        // state entering warp w = prefix kept from the tile's own scan + p^(32 C w) S
 #pragma unroll
-        for (int w = 0; w < K2_NW; ++w) {
-          double t[4] = {X[4 * w], X[4 * w + 1], X[4 * w + 2], X[4 * w + 3]};
-          if (dp.k > 0) cmul_acc(PWP + 4 * w, S, t);
+        for (int i = 0; i < 4; ++i) S[i] = __shfl_sync(AEW_FULL, S[i], 0);
+        if (lane < K2_NW) {
+          const double* X = s_X + ((it + 1) & 1) * 4 * K2_NW;
+          double t[4] = {X[4 * lane], X[4 * lane + 1], X[4 * lane + 2], X[4 * lane + 3]};
+          if (dp.k > 0) cmul_acc(PWP + 4 * lane, S, t);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) s_S[4 * w + i] = t[i];
+          for (int i = 0; i < 4; ++i) s_S[4 * lane + i] = t[i];
         }
       }
     }
