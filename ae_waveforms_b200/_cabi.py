@@ -63,6 +63,10 @@ SIGNATURES = {
     "aew_recon_workspace_bytes": (c_size_t, [c_longlong, c_longlong]),
     "aew_recon_sse_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_int, c_void_p,
                                   c_longlong, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "aew_recon_max_grid_values": (c_int, []),
+    "aew_recon_tables_workspace_bytes": (c_size_t, [c_longlong]),
+    "aew_recon_sse_grid_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_int, c_void_p,
+                                       c_int, c_void_p, c_longlong, c_void_p, c_void_p, c_size_t, c_void_p]),
     "aew_gaussian_line_f64": (c_int, [c_double, c_double, c_double, c_double, c_double, c_void_p, c_int, c_void_p]),
     "aew_extract_coordinates_f64": (c_int, [c_void_p, c_void_p, c_double, c_void_p, c_int, c_void_p, c_void_p,
                                             c_void_p]),

@@ -75,10 +75,49 @@ class SigmaSearch:
         self.launches += 2
         return sse, pred
 
-    def sse(self, candidates):
-        """Sum over beats and samples of (float32(pred) - target)^2 per candidate (CUDA tensor)."""
+    def sse_grid(self, values, index):
+        """Objective of candidates drawn from a discrete grid: candidate c uses sigma_map[s] = values[index[c, s]].
+        One pass over the beats builds the separable error tables, then every candidate is scored from them
+        (see aew_recon_sse_grid_f64) -- the cost no longer grows with beats x candidates."""
+        torch, lib = self.torch, self.lib
         if self.target is None:
             raise _cabi.AewError("targets are needed for the objective")
+        dev = lambda a, dt: (a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))).to(self.device, dt)
+        vals = dev(values, torch.float64).reshape(-1).contiguous()
+        idx = dev(index, torch.uint8).reshape(-1, 12).contiguous()
+        if vals.numel() < 1 or vals.numel() > int(lib.aew_recon_max_grid_values()):
+            raise _cabi.AewError(f"the table formulation takes 1..{lib.aew_recon_max_grid_values()} grid values")
+        n_cand = idx.shape[0]
+        sse = torch.empty(n_cand, dtype=torch.float64, device=self.device)
+        ws_bytes = int(lib.aew_recon_tables_workspace_bytes(self.n_beats))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        _cabi.check(lib.aew_recon_sse_grid_f64(p(self.fx), p(self.fy), p(self.baselines), p(self.target), self.n_beats,
+                                               p(self.xt), self.n_t, p(vals), vals.numel(), p(idx), n_cand, p(sse),
+                                               p(ws), ws_bytes, _cabi.stream_ptr(torch)), "recon_sse_grid")
+        self.launches += 3
+        return sse
+
+    def sse(self, candidates, method="auto"):
+        """Sum over beats and samples of (float32(pred) - target)^2 per candidate (CUDA tensor).
+        method "direct" evaluates every (beat, candidate) pair; "tables" requires the candidates to take at most
+        aew_recon_max_grid_values() distinct values (the reference's Integer(1, 5) space does) and goes through
+        sse_grid; "auto" picks tables whenever they apply and there are enough candidates to pay for them."""
+        torch = self.torch
+        if self.target is None:
+            raise _cabi.AewError("targets are needed for the objective")
+        if method not in ("auto", "direct", "tables"):
+            raise ValueError(method)
+        if method != "direct":
+            c = candidates if isinstance(candidates, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(candidates, dtype=np.float64))
+            c = c.to(self.device, torch.float64).reshape(-1, 12)
+            if method == "tables" or c.shape[0] >= 32:
+                vals = torch.unique(c)                 # sorted; NaN entries never compare equal, so they fail the test below
+                if vals.numel() <= int(self.lib.aew_recon_max_grid_values()) and not bool(torch.isnan(vals).any()):
+                    return self.sse_grid(vals, torch.searchsorted(vals, c.contiguous()).to(torch.uint8))
+                if method == "tables":
+                    raise _cabi.AewError("candidates take too many distinct values for the table formulation")
+            candidates = c
         return self._call(candidates, False)[0]
 
     def mse(self, candidates):

@@ -143,6 +143,19 @@ size_t aew_recon_workspace_bytes(long long n_beats, long long n_cand);
 int aew_recon_sse_f64(const double* d_fx, const double* d_fy, const double* d_baseline, const float* d_target,
                       long long n_beats, const double* d_xt, int n_t, const double* d_cand, long long n_cand,
                       double* d_sse, double* d_pred, void* d_ws, size_t ws_bytes, void* stream);
+/* The same objective for a DISCRETE sigma grid (the reference searches Integer(1, 5)^12,
+ * analysis_performance_traditional_vs_ae.py:58): every output sample depends on at most two entries of
+ * the sigma map, so per-(slot, value) and per-(slot pair, value pair) error tables are accumulated once
+ * over all beats and each candidate is then scored by 157 table look-ups.  Same per-sample float32
+ * squared errors as aew_recon_sse_f64; only the (float64) summation order differs.
+ *   d_vals [n_vals] the grid values, n_vals <= aew_recon_max_grid_values()
+ *   d_idx  [n_cand][12] uint8: index into d_vals of every candidate entry */
+int aew_recon_max_grid_values(void);
+size_t aew_recon_tables_workspace_bytes(long long n_beats);
+int aew_recon_sse_grid_f64(const double* d_fx, const double* d_fy, const double* d_baseline, const float* d_target,
+                           long long n_beats, const double* d_xt, int n_t, const double* d_vals, int n_vals,
+                           const unsigned char* d_idx, long long n_cand, double* d_sse, void* d_ws, size_t ws_bytes,
+                           void* stream);
 /* gaussian_line(x1, y1, x2, y2, s) (signal_reconstruction.py:5-14): n = int(x2) - int(x1) values */
 int aew_gaussian_line_f64(double x1, double y1, double x2, double y2, double s, double* d_out, int n, void* stream);
 /* extract_coordinates (signal_reconstruction.py:45-81) for one beat: d_fx, d_fy [11];

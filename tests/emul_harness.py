@@ -155,3 +155,18 @@ def recon(fx, fy, bl, target, xt, cands, want_pred=False):
                              ptr(pred), ptr(ws), wsb, None)
     assert rc == 0, rc
     return sse, pred
+
+
+def recon_grid(fx, fy, bl, target, xt, vals, idx):
+    L = lib()
+    fx, fy, bl, xt, vals = [np.ascontiguousarray(a, dtype=np.float64) for a in (fx, fy, bl, xt, vals)]
+    target = np.ascontiguousarray(target, dtype=np.float32)
+    idx = np.ascontiguousarray(idx, dtype=np.uint8).reshape(-1, 12)
+    nb, nc = len(fx), len(idx)
+    sse = np.zeros(nc)
+    wsb = L.aew_recon_tables_workspace_bytes(nb)
+    ws = np.zeros(wsb, np.uint8)
+    rc = L.aew_recon_sse_grid_f64(ptr(fx), ptr(fy), ptr(bl), ptr(target), nb, ptr(xt), len(xt), ptr(vals), len(vals),
+                                  ptr(idx), nc, ptr(sse), ptr(ws), wsb, None)
+    assert rc == 0, rc
+    return sse

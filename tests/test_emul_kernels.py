@@ -121,3 +121,25 @@ def test_k5_recon_golden(golden):
     mse = sse / g["test_true"].size
     assert np.all(np.abs(mse - g["mse_torch_f32"]) <= 1e-5 * g["mse_torch_f32"])
     assert np.argmin(sse) == np.argmin(want)
+
+
+def test_k5_grid_tables_match_bruteforce(golden):
+    """Separable tables for a discrete sigma grid == the per-candidate kernel == the oracle objective."""
+    g = golden("recon")
+    rng = np.random.default_rng(5)
+    vals = np.array([1.0, 2.0, 3.0, 4.0, 5.0])
+    idx = rng.integers(0, 5, size=(24, 12)).astype(np.uint8)
+    idx[0], idx[1] = 0, 4
+    cands = vals[idx]
+    grid = eh.recon_grid(g["fx"], g["fy"], g["baselines"], g["test_true"], g["x_t"], vals, idx)
+    brute, _ = eh.recon(g["fx"], g["fy"], g["baselines"], g["test_true"], g["x_t"], cands)
+    assert same(np.isnan(grid), np.isnan(brute))
+    assert np.all(np.abs(grid - brute) <= 1e-12 * np.abs(brute))
+    want = np.array([rp.sigma_objective(g["fx"], g["fy"], g["baselines"], g["test_true"], m, g["x_t"])[0] for m in cands[:6]])
+    assert np.all(np.abs(grid[:6] - want) <= 1e-6 * np.abs(want))
+    # non-integer grids work the same way (three values)
+    vals3 = np.array([0.75, 2.5, 6.0])
+    idx3 = rng.integers(0, 3, size=(8, 12)).astype(np.uint8)
+    grid3 = eh.recon_grid(g["fx"], g["fy"], g["baselines"], g["test_true"], g["x_t"], vals3, idx3)
+    brute3, _ = eh.recon(g["fx"], g["fy"], g["baselines"], g["test_true"], g["x_t"], vals3[idx3])
+    assert np.all(np.abs(grid3 - brute3) <= 1e-12 * np.abs(brute3))

@@ -333,6 +333,36 @@ def test_sigma_search_against_oracle(gpu):
     assert order_gpu[0] == order_ref[0], "optimal sigma map differs"
 
 
+def test_sigma_grid_tables_against_direct_and_oracle(gpu):
+    """The separable-table formulation for discrete grids gives the direct kernel's sums (different float64
+    summation order only), the oracle's objective and the same winner; sse() routes to it automatically."""
+    from ae_waveforms_b200 import _cabi
+    from ae_waveforms_b200.sigma_search import SigmaSearch
+    torch, _ = gpu
+    tt, fx, fy, bl = ecg_synth.synth_fiducials(700, seed=9, nan_frac=0.04)
+    cands = ecg_synth.sigma_candidates(300, "integer")
+    s = SigmaSearch(fx, fy, bl, tt)
+    direct = s.sse(cands, method="direct").cpu().numpy()
+    tables = s.sse(cands, method="tables").cpu().numpy()
+    auto = s.sse(cands).cpu().numpy()
+    assert same(auto, tables)
+    assert same(tables, s.sse(cands, method="tables").cpu().numpy()), "table sums must be run-to-run deterministic"
+    assert same(np.isnan(direct), np.isnan(tables))
+    ok = ~np.isnan(direct)
+    assert ok.any() and np.all(np.abs(tables[ok] - direct[ok]) <= 1e-12 * np.abs(direct[ok]))
+    want = np.array([rp.sigma_objective(fx, fy, bl, tt, c)[0] for c in cands[:12]])
+    assert np.all(np.abs(tables[:12] - want) <= RTOL * np.abs(want))
+    assert s.best(cands)[0] == int(np.argmin(np.where(ok, direct, np.inf)))
+    # fractional three-value grid, explicit (values, index) entry
+    vals = np.array([0.5, 2.25, 7.0])
+    idx = np.random.default_rng(2).integers(0, 3, size=(40, 12))
+    g3 = s.sse_grid(vals, idx).cpu().numpy()
+    d3 = s.sse(vals[idx], method="direct").cpu().numpy()
+    assert np.all(np.abs(g3 - d3) <= 1e-12 * np.abs(d3))
+    with pytest.raises(_cabi.AewError):
+        s.sse(ecg_synth.sigma_candidates(40, "continuous"), method="tables")
+
+
 def test_host_pipelined_equals_single_batch(gpu):
     """The chunked, double-buffered host feeder returns exactly what one resident batch returns."""
     torch, B = gpu
