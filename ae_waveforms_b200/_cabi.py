@@ -58,6 +58,7 @@ SIGNATURES = {
     "aew_windows_max_peaks": (c_int, []),
     "aew_windows_max_len": (c_int, []),
     "aew_windows_beats_f64": (c_int, [c_void_p, c_void_p]),
+    "aew_windows_timing_dump": (c_int, [c_void_p]),
     "aew_median_beats_f64": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
                                      c_void_p, c_void_p, c_void_p]),
     "aew_recon_workspace_bytes": (c_size_t, [c_longlong, c_longlong]),

@@ -29,6 +29,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __launch_bounds__(...)
 #define __shared__ static
 #define __restrict__ __restrict
@@ -189,6 +190,21 @@ inline unsigned __ballot_sync(unsigned, int pred) {
   w.bar.wait();
   return r;
 }
+inline unsigned aew_emul_reduce_u32(unsigned v, int op) {
+  auto& w = aew_emul::block_ctx()->warps[aew_emul::tctx().warp];
+  w.slot[aew_emul::tctx().lane] = v;
+  w.bar.wait();
+  unsigned r = (unsigned)w.slot[0];
+  for (int l = 1; l < 32; ++l) {
+    const unsigned o = (unsigned)w.slot[l];
+    r = op == 0 ? (o < r ? o : r) : (op == 1 ? (o > r ? o : r) : r + o);
+  }
+  w.bar.wait();
+  return r;
+}
+inline unsigned __reduce_min_sync(unsigned, unsigned v) { return aew_emul_reduce_u32(v, 0); }
+inline unsigned __reduce_max_sync(unsigned, unsigned v) { return aew_emul_reduce_u32(v, 1); }
+inline unsigned __reduce_add_sync(unsigned, unsigned v) { return aew_emul_reduce_u32(v, 2); }
 inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
 inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, pred) == 0xffffffffu; }
 

@@ -34,6 +34,7 @@
 //
 // Algorithmic HBM bytes: 8 B per input sample read + (320*12 + 72*4 + 48) B per
 // window written.  Bound: instruction issue / FP64, not HBM.
+#include <cstdlib>
 #include "aew_pairwise.cuh"
 #include "aew_math.cuh"
 #include "../../include/aewave.h"
@@ -44,13 +45,14 @@
 #define K3_MAXP 72                        // peaks are > 150 samples apart -> at most 71 in 10752
 #define K3_BEAT 320
 #define K3_NONE 0xffffu
+#define K3_PREFETCH_AHEAD 148                // one wave of blocks (one block per SM)
 
 namespace {
 
 struct K3Smem {
   double* A;            // [L]  z-scored window
-  double* B;            // [L]  prefix sums / sequential smoothgrad
-  double* pw_vals;      // [128]
+  double* B;            // [K3_MAXL]  prefix sums (edge-extended) / sequential smoothgrad
+  double* pw_vals;      // [2][128] leaf sums, double-buffered
   double* wtot;         // [16]
   double* scal;         // [16] scalars
   double* dsq;          // [K3_MAXP] squared successive RR differences
@@ -64,7 +66,7 @@ struct K3Smem {
   unsigned short* end;
   unsigned short* cand;
   unsigned char* Q;     // [L]
-  unsigned char* pw_valid;  // [128]
+  unsigned char* pw_valid;  // [2][128]
 };
 
 __host__ __device__ inline size_t k3_smem_layout(unsigned char* base, int L, K3Smem* s) {
@@ -72,8 +74,8 @@ __host__ __device__ inline size_t k3_smem_layout(unsigned char* base, int L, K3S
   auto take = [&](size_t bytes) { size_t at = o; o = (o + bytes + 15) & ~(size_t)15; return base ? base + at : (unsigned char*)0; };
   K3Smem t;
   t.A = (double*)take(sizeof(double) * L);
-  t.B = (double*)take(sizeof(double) * L);
-  t.pw_vals = (double*)take(sizeof(double) * 128);
+  t.B = (double*)take(sizeof(double) * K3_MAXL);   // prefix sums over the edge-extended window
+  t.pw_vals = (double*)take(sizeof(double) * 256);
   t.wtot = (double*)take(sizeof(double) * 16);
   t.scal = (double*)take(sizeof(double) * 16);
   t.dsq = (double*)take(sizeof(double) * K3_MAXP);
@@ -88,7 +90,7 @@ __host__ __device__ inline size_t k3_smem_layout(unsigned char* base, int L, K3S
   t.end = (unsigned short*)take(sizeof(unsigned short) * rmax);
   t.cand = (unsigned short*)take(sizeof(unsigned short) * rmax);
   t.Q = (unsigned char*)take(L);
-  t.pw_valid = (unsigned char*)take(128);
+  t.pw_valid = (unsigned char*)take(256);
   if (s) *s = t;
   return o;
 }
@@ -102,49 +104,119 @@ __device__ __forceinline__ double absgrad(const double* __restrict__ z, int i, i
   return fabs(g);
 }
 
-struct SumPlain { const double* a; __device__ __forceinline__ double operator()(int i, bool) { return a[i]; } };
-struct SumDev2 {
-  const double* a; double m;
-  __device__ __forceinline__ double operator()(int i, bool) { const double d = __dsub_rn(a[i], m); return __dmul_rn(d, d); }
-};
-
-// NumPy-order block sum with the leaf ranges tabulated (same tree as pw_block_sum)
-template <class F>
-__device__ __forceinline__ double block_sum_tab(F& f, int depth, const K3Smem& sm) {
-  const int nslots = 1 << depth;
-  const int group = threadIdx.x >> 3, g = threadIdx.x & 7, ngroups = blockDim.x >> 3;
-  for (int s0 = 0; s0 < nslots; s0 += ngroups) {
-    const int slot = s0 + group;
-    const int off = slot < nslots ? sm.leaf_off[slot] : 0;
-    const int size = slot < nslots ? sm.leaf_size[slot] : 0;
-    const int c8 = size >> 3;
-    double r = 0.0;
-    if (c8 > 0) {
-      r = f(off + g, true);
-#pragma unroll 5
-      for (int k = 1; k < c8; ++k) r = __dadd_rn(r, f(off + 8 * k + g, true));
-    }
-    double t = __shfl_xor_sync(AEW_FULL, r, 1);
-    r = __dadd_rn(r, t);
-    t = __shfl_xor_sync(AEW_FULL, r, 2);
-    r = __dadd_rn(r, t);
-    t = __shfl_xor_sync(AEW_FULL, r, 4);
-    r = __dadd_rn(r, t);
-    int i = c8 << 3;
-    if (size < 8) { r = 0.0; i = 0; }
-    for (; i < size; ++i) r = __dadd_rn(r, f(off + i, g == 0));
-    if (slot < nslots && g == 0) { sm.pw_vals[slot] = r; sm.pw_valid[slot] = size > 0; }
+#ifdef AEW_EMUL
+#define K3_TICK(slot)
+#else
+#define K3_TICK(slot)                                                              \
+  if (dbg && tid == 0) {                                                           \
+    const long long t_now = clock64();                                             \
+    atomicAdd(dbg + (slot), (unsigned long long)(t_now - t_last));                 \
+    t_last = t_now;                                                                \
   }
-  __syncthreads();
-  if (threadIdx.x < 32) pw_warp_combine(sm.pw_vals, sm.pw_valid, depth, threadIdx.x);
-  __syncthreads();
-  const double r = sm.pw_vals[0];
-  __syncthreads();
-  return r;
+#endif
+
+// ---- passes over the window in NumPy's summation order -------------------------------------------------------
+// Thread t owns lane j = t & 3 of leaf t >> 2 of the NumPy tree (128 leaves of 72..88 samples for a 10,000-sample
+// window, so one round of the 512 threads covers the window).  Lane j carries the stride-8 partial sums r_j and
+// r_{j+4}; ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) falls out of two xor steps and one local addition, the leaf's
+// tail is added sequentially.  A pass is described by a functor: load(i) fetches element i, apply(v, i, primary)
+// returns the term to accumulate and may have side effects (stores) when `primary` -- true on exactly one lane per
+// element.  Work that used to be separate sweeps rides along: the HBM load + NaN screen with the first sum, the
+// z-score transform with the sum of the transformed window.
+// The kernel is bound by INSTRUCTION FETCH (profiles/icache_bench.cu: straight-line code that does not fit the
+// 32 KB L1.5 instruction cache streams from L2 at about 5.5 cycles per instruction per SM, and every window runs
+// through the whole kernel once), so everything used more than once is one non-inlined function.
+enum { K3_PASS_PLAIN = 0, K3_PASS_DEV2 = 1, K3_PASS_ZSCORE = 2 };
+struct LeafOut { double r; int flag; };
+struct SumPlain { const double* a; __device__ __forceinline__ double operator()(int i, bool) { return a[i]; } };
+
+// One sweep over the thread's share of its leaf.  PLAIN: sum of the window, flag = saw a NaN
+// (remove_samples.py:31-33).  DEV2: sum of (x - m)^2.  ZSCORE: x <- (x - m) / sd in place, sum of the new values,
+// flag = produced a non-finite value (constant window: 0/0).
+__device__ __forceinline__ double leaf_term(int mode, double* A, int i, double v, bool store, double m, const ExactDiv& dv,
+                                            int& flag) {
+  if (mode == K3_PASS_PLAIN) { flag |= isnan(v) ? 1 : 0; return v; }
+  const double d = __dsub_rn(v, m);
+  if (mode == K3_PASS_DEV2) return __dmul_rn(d, d);
+  const double z = div_exact(d, dv);
+  if (store) A[i] = z;
+  flag |= (isnan(z) || isinf(z)) ? 1 : 0;
+  return z;
+}
+__device__ __noinline__ LeafOut leaf_pass(int mode, double* A, double m, double sd, int off, int size, int j) {
+  const ExactDiv dv = make_exact_div(sd);
+  const int c8 = size >> 3;
+  int flag = 0;
+  double r0 = 0.0, r1 = 0.0;
+#pragma unroll 1
+  for (int k = 0; k < c8; ++k) {
+    const int i0 = off + 8 * k + j;
+    const double a = A[i0], b = A[i0 + 4];
+    const double x0 = leaf_term(mode, A, i0, a, true, m, dv, flag), x1 = leaf_term(mode, A, i0 + 4, b, true, m, dv, flag);
+    r0 = k == 0 ? x0 : __dadd_rn(r0, x0);
+    r1 = k == 0 ? x1 : __dadd_rn(r1, x1);
+  }
+  r0 = __dadd_rn(r0, __shfl_xor_sync(AEW_FULL, r0, 1));
+  r1 = __dadd_rn(r1, __shfl_xor_sync(AEW_FULL, r1, 1));
+  r0 = __dadd_rn(r0, __shfl_xor_sync(AEW_FULL, r0, 2));
+  r1 = __dadd_rn(r1, __shfl_xor_sync(AEW_FULL, r1, 2));
+  double r = __dadd_rn(r0, r1);
+  int i = c8 << 3;
+  if (size < 8) { r = 0.0; i = 0; }
+  // the tail is added by all four lanes alike; each element is read by all before lane 0 may overwrite it
+  int left = size - i;
+  left = __reduce_max_sync(AEW_FULL, (unsigned)(left < 0 ? 0 : left));   // trip count uniform over the warp
+#pragma unroll 1
+  for (int u = 0; u < left; ++u) {
+    const bool in = i + u < size;
+    const double v = in ? A[off + i + u] : 0.0;
+    __syncwarp();
+    if (in) r = __dadd_rn(r, leaf_term(mode, A, off + i + u, v, j == 0, m, dv, flag));
+  }
+  LeafOut o;
+  o.r = r; o.flag = flag;
+  return o;
 }
 
+// Combine the leaf values up the tree.  depth 7: every warp folds the 128 leaves in registers (two local levels,
+// five xor steps) -- an invalid (empty) right node leaves its sibling untouched, exactly like pw_warp_combine --
+// so one barrier per sum is enough.  Two leaf buffers alternate: a slow warp may still be folding the previous
+// sum while the next one's leaves are stored.
+__device__ __noinline__ double block_combine(double r, int slot, int j, int size, int depth, const K3Smem& sm,
+                                             int& parity) {
+  double* vals = sm.pw_vals + 128 * parity;
+  unsigned char* valid = sm.pw_valid + 128 * parity;
+  parity ^= 1;
+  if (slot < (1 << depth) && j == 0) { vals[slot] = r; valid[slot] = size > 0; }
+  __syncthreads();
+  if (depth == 7) {
+    const int lane = threadIdx.x & 31;
+    const double a0 = vals[4 * lane], a1 = vals[4 * lane + 1], a2 = vals[4 * lane + 2], a3 = vals[4 * lane + 3];
+    const int v0 = valid[4 * lane], v1 = valid[4 * lane + 1], v2 = valid[4 * lane + 2], v3 = valid[4 * lane + 3];
+    const double n01 = (v0 && v1) ? __dadd_rn(a0, a1) : a0;
+    const double n23 = (v2 && v3) ? __dadd_rn(a2, a3) : a2;
+    double m = (v0 && v2) ? __dadd_rn(n01, n23) : n01;
+    int mv = v0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double other = __shfl_xor_sync(AEW_FULL, m, o);
+      const int ov = __shfl_xor_sync(AEW_FULL, mv, o);
+      if ((lane & o) == 0) { m = (mv && ov) ? __dadd_rn(m, other) : m; }
+      else { m = (ov && mv) ? __dadd_rn(other, m) : other; mv = ov; }
+    }
+    return m;
+  }
+  if (threadIdx.x < 32) pw_warp_combine(vals, valid, depth, threadIdx.x);
+  __syncthreads();
+  return vals[0];
+}
+
+// IEEE division / square root: ~40 instructions each when inlined, so one copy
+__device__ __noinline__ double k3_div(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __noinline__ double k3_sqrt(double a) { return __dsqrt_rn(a); }
+
 // exclusive block scan of one double per thread (fast path; not order-sensitive)
-__device__ __forceinline__ double block_excl_scan(double v, double* wtot) {
+__device__ __noinline__ double block_excl_scan(double v, double* wtot) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double incl = v;
 #pragma unroll
@@ -159,7 +231,7 @@ __device__ __forceinline__ double block_excl_scan(double v, double* wtot) {
   __syncthreads();
   return base + (incl - v);
 }
-__device__ __forceinline__ int block_excl_scan_int(int v, int* wtot) {
+__device__ __noinline__ int block_excl_scan_int(int v, int* wtot) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int incl = v;
 #pragma unroll
@@ -175,15 +247,21 @@ __device__ __forceinline__ int block_excl_scan_int(int v, int* wtot) {
   return base + (incl - v);
 }
 
-// sum over a clamped ("nearest") window [lo, hi] from an inclusive prefix array
-__device__ __forceinline__ double clamped_window(const double* __restrict__ P, int lo, int hi, int L, double first,
-                                                 double last) {
-  if (lo >= 1 && hi <= L - 1) return P[hi] - P[lo - 1];          // interior: no clamping
-  const int nl = lo < 0 ? -lo : 0, nr = hi > L - 1 ? hi - (L - 1) : 0;
-  const int lo2 = lo < 0 ? 0 : lo, hi2 = hi > L - 1 ? L - 1 : hi;
-  double s = P[hi2] - (lo2 > 0 ? P[lo2 - 1] : 0.0);
-  s += (double)nl * first + (double)nr * last;
-  return s;
+// order-preserving 64-bit key of a (non-NaN) double: unsigned comparison of keys == comparison of the values
+__device__ __forceinline__ unsigned long long dkey(double x) {
+  const long long b = __double_as_longlong(x);
+  return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ull));
+}
+__device__ __forceinline__ double dkey_inv(unsigned long long k) {
+  const long long t = (long long)k;
+  return __longlong_as_double(t ^ ((~t >> 63) | (long long)0x8000000000000000ull));
+}
+// minimum over the warp of per-lane keys (REDUX on the high words, then on the low words of the lanes that tie)
+__device__ __forceinline__ double warp_min_key(unsigned long long k) {
+  const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+  const unsigned mh = __reduce_min_sync(AEW_FULL, hi);
+  const unsigned ml = __reduce_min_sync(AEW_FULL, hi == mh ? lo : 0xffffffffu);
+  return dkey_inv(((unsigned long long)mh << 32) | ml);
 }
 
 // ---------------------------------------------------------------------- medians
@@ -237,90 +315,87 @@ __device__ __forceinline__ double beat_value(const double* __restrict__ z, int p
   return __longlong_as_double(0x7ff0000000000000ll);
 }
 
-// column c of a window with n <= 32 beats, by ONE thread: (lo + hi) / 2 with lo == hi for
-// odd counts, exactly as np.ma.median evaluates it; all-NaN column -> NaN
-__device__ __forceinline__ double column_median_thread(const double* __restrict__ z, const int* __restrict__ peaks,
-                                                       int n, int c, int L, int pre, int post) {
+// One column of <= 64 beats.  n <= 32: ONE thread sorts the column's values with the 32-input network.
+// 33..64 beats: a PAIR of adjacent lanes sorts 32 values each, a bitonic split across the pair leaves the 32
+// smallest of the 64 with the even lane and the 32 largest with the odd lane (min / max of v[i] against the
+// partner's v[31 - i]), and one 5-stage bitonic merge orders each half; 34 lane exchanges per column instead of
+// the hundreds a warp-wide sort needs.  The median is (lo + hi) / 2 with lo == hi for odd counts, exactly as
+// np.ma.median evaluates it; an all-NaN column gives NaN.  `paired` is uniform over the block; inactive
+// threads run along (their lanes take part in the exchanges) and return garbage.
+__device__ __forceinline__ double column_median_64(const double* __restrict__ z, const int* __restrict__ peaks,
+                                                   int n, int c, int half, bool active, bool paired, int L, int pre,
+                                                   int post) {
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
   double v[32];
   int valid = 0;
 #pragma unroll
-  for (int b = 0; b < 32; ++b)
-    v[b] = b < n ? beat_value(z, peaks[b], c, L, pre, post, valid) : __longlong_as_double(0x7ff0000000000000ll);
+  for (int b = 0; b < 32; ++b) {
+    const int bb = 32 * half + b;
+    v[b] = (active && bb < n) ? beat_value(z, peaks[bb], c, L, pre, post, valid) : inf;
+  }
   sort_network<32>(v);
+  if (paired) {
+    valid += __shfl_xor_sync(AEW_FULL, valid, 1);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const double o1 = __shfl_xor_sync(AEW_FULL, v[31 - i], 1);   // pairs with my v[i]
+      const double o2 = __shfl_xor_sync(AEW_FULL, v[i], 1);        // pairs with my v[31 - i]
+      const bool t1 = half ? (o1 > v[i]) : (o1 < v[i]);
+      const bool t2 = half ? (o2 > v[31 - i]) : (o2 < v[31 - i]);
+      v[i] = t1 ? o1 : v[i];
+      v[31 - i] = t2 ? o2 : v[31 - i];
+    }
+#pragma unroll
+    for (int stride = 16; stride > 0; stride >>= 1) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if ((i & stride) == 0) cex(v[i], v[i + stride]);
+    }
+  }
   const int h = valid >> 1;
-  const int rhi = h < 31 ? h : 31;
+  const int cap = paired ? 63 : 31;
+  const int rhi = h < cap ? h : cap;
   const int rlo = (valid & 1) ? h : (h > 0 ? h - 1 : 0);
   double lo = 0.0, hi = 0.0;
 #pragma unroll
   for (int b = 0; b < 32; ++b) {
-    lo = (b == rlo) ? v[b] : lo;
-    hi = (b == rhi) ? v[b] : hi;
+    lo = (b == (rlo & 31)) ? v[b] : lo;
+    hi = (b == (rhi & 31)) ? v[b] : hi;
+  }
+  if (paired) {
+    const double plo = __shfl_xor_sync(AEW_FULL, lo, 1), phi = __shfl_xor_sync(AEW_FULL, hi, 1);
+    lo = ((rlo >> 5) == half) ? lo : plo;
+    hi = ((rhi >> 5) == half) ? hi : phi;
   }
   if (valid == 0) return __longlong_as_double(0x7ff8000000000000ll);
   return __dmul_rn(__dadd_rn(lo, hi), 0.5);
 }
 
-// ---- warp bitonic sort of 32*K doubles, element e = k*32 + lane, ascending (n > 32 beats)
-template <int K>
-__device__ __forceinline__ void warp_sort(double (&v)[K], int lane) {
-#pragma unroll
-  for (int size = 2; size <= 32 * K; size <<= 1) {
-#pragma unroll
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      if (stride >= 32) {
-        const int ks = stride >> 5;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-          if ((k & ks) == 0) {
-            const bool asc = (((k * 32) & size) == 0);
-            const double a = v[k], b = v[k | ks];
-            const bool swap = asc ? (a > b) : (a < b);
-            v[k] = swap ? b : a;
-            v[k | ks] = swap ? a : b;
-          }
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-          const bool asc = (((k * 32 + lane) & size) == 0);
-          const double o = __shfl_xor_sync(AEW_FULL, v[k], stride);
-          const bool take_min = (((lane & stride) == 0) == asc);
-          const bool o_lt = o < v[k];
-          v[k] = (take_min == o_lt) ? o : v[k];         // equal values: either copy is the same number
-        }
-      }
-    }
-  }
-}
-
-template <int K>
-__device__ __forceinline__ double warp_pick(const double (&v)[K], int rank) {
-  double r = 0.0;
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-    const double c = __shfl_sync(AEW_FULL, v[k], rank & 31);
-    r = ((rank >> 5) == k) ? c : r;
-  }
-  return r;
-}
-
-template <int K>
-__device__ __forceinline__ double column_median_warp(const double* __restrict__ z, const int* __restrict__ peaks,
-                                                     int n, int c, int L, int pre, int post, int lane) {
-  double v[K];
+// Any number of beats, by one thread, by counting: the element of rank r is the one with <= r smaller values and
+// > r values that are smaller or equal.  O(n^2) but a dozen instructions of code; only reached beyond 64 beats
+// per window, which the 180 bpm screen of the reference rules out for its own window length.
+__device__ __noinline__ double column_median_count(const double* __restrict__ z, const int* __restrict__ peaks, int n,
+                                                   int c, int L, int pre, int post) {
   int valid = 0;
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-    const int b = k * 32 + lane;
-    v[k] = b < n ? beat_value(z, peaks[b], c, L, pre, post, valid) : __longlong_as_double(0x7ff0000000000000ll);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) valid += __shfl_xor_sync(AEW_FULL, valid, o);
-  warp_sort<K>(v, lane);
-  const int h = valid >> 1;
-  const double hi = warp_pick<K>(v, h < 32 * K - 1 ? h : 32 * K - 1);
-  const double lo = warp_pick<K>(v, (valid & 1) ? h : (h > 0 ? h - 1 : 0));
+  for (int b = 0; b < n; ++b) { int t = 0; (void)beat_value(z, peaks[b], c, L, pre, post, t); valid += t; }
   if (valid == 0) return __longlong_as_double(0x7ff8000000000000ll);
+  const int h = valid >> 1;
+  const int rhi = h, rlo = (valid & 1) ? h : h - 1;
+  double lo = 0.0, hi = 0.0;
+  for (int b = 0; b < n; ++b) {
+    int t = 0;
+    const double vb = beat_value(z, peaks[b], c, L, pre, post, t);
+    if (!t) continue;
+    int less = 0, leq = 0;
+    for (int j = 0; j < n; ++j) {
+      int u = 0;
+      const double vj = beat_value(z, peaks[j], c, L, pre, post, u);
+      less += (u && vj < vb) ? 1 : 0;
+      leq += (u && vj <= vb) ? 1 : 0;
+    }
+    if (less <= rlo && rlo < leq) lo = vb;
+    if (less <= rhi && rhi < leq) hi = vb;
+  }
   return __dmul_rn(__dadd_rn(lo, hi), 0.5);
 }
 
@@ -329,19 +404,23 @@ __device__ __forceinline__ void window_median(const double* __restrict__ z, cons
                                               int L, int pre, int post, double* __restrict__ med,
                                               float* __restrict__ waves) {
   const int S = pre + post;
-  if (n <= 32) {
+  if (n > 64) {
     for (int c = threadIdx.x; c < S; c += blockDim.x) {
-      const double m = column_median_thread(z, peaks, n, c, L, pre, post);
+      const double m = column_median_count(z, peaks, n, c, L, pre, post);
       if (med) med[c] = m;
       if (waves) waves[c] = (float)m;
     }
     return;
   }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  for (int c = warp; c < S; c += nwarp) {
-    const double m = n <= 64 ? column_median_warp<2>(z, peaks, n, c, L, pre, post, lane)
-                             : column_median_warp<4>(z, peaks, n, c, L, pre, post, lane);
-    if (lane == 0) {
+  const bool paired = n > 32;
+  const int per_pass = paired ? (int)(blockDim.x >> 1) : (int)blockDim.x;
+  for (int c0 = 0; c0 < S; c0 += per_pass) {             // warp-uniform trip count
+    const int c = c0 + (paired ? (int)(threadIdx.x >> 1) : (int)threadIdx.x);
+    const int half = paired ? (int)(threadIdx.x & 1) : 0;
+    const bool active = c < S;
+    if (!__any_sync(AEW_FULL, active)) continue;
+    const double m = column_median_64(z, peaks, n, active ? c : 0, half, active, paired, L, pre, post);
+    if (active && half == 0) {
       if (med) med[c] = m;
       if (waves) waves[c] = (float)m;
     }
@@ -349,7 +428,7 @@ __device__ __forceinline__ void window_median(const double* __restrict__ z, cons
 }
 
 // ---------------------------------------------------------------------- the window kernel
-__global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p) {
+__global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p, unsigned long long* dbg) {
   AEW_DYN_SMEM(smem_raw);
   K3Smem sm;
   k3_smem_layout(smem_raw, p.L, &sm);
@@ -357,6 +436,10 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p) {
   const int L = p.L;
   const long long w = blockIdx.x;
   const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+  long long t_last = 0;
+#ifndef AEW_EMUL
+  if (dbg) t_last = clock64();
+#endif
   if (p.win_start[w] < 0) {                             // padding slot of an over-allocated window table
     if (tid == 0) {
       p.keep[w] = 0; p.has_nan[w] = 2; p.n_peaks[w] = 0;
@@ -366,6 +449,22 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p) {
     return;
   }
   const double* src = p.y + p.win_start[w];
+#ifndef AEW_EMUL
+  {
+    // Blocks are dispatched in index order, one per SM: the window of block w + gridDim-of-one-wave is needed about
+    // one block lifetime from now.  Pull it into L2 so that its load phase does not wait on HBM.
+    const long long wn = w + K3_PREFETCH_AHEAD;
+    if (wn < p.n_win) {
+      const long long sn = p.win_start[wn];
+      if (sn >= 0) {
+        const char* nxt = (const char*)(p.y + sn);
+#pragma unroll 1
+        for (int off = tid * 128; off < L * 8; off += K3_NT * 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + off));
+      }
+    }
+  }
+#endif
   double* A = sm.A;
   double* B = sm.B;
   const int depth = pw_depth(L);
@@ -376,32 +475,34 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p) {
     sm.leaf_size[tid] = (int)size;
   }
 
-  // ---- load, NaN screen (remove_samples.py:31-33)
-  int bad = 0;
-  for (int i = tid; i < L; i += K3_NT) {
-    const double v = src[i];
-    A[i] = v;
-    bad |= isnan(v) ? 1 : 0;
-  }
-  bad = __syncthreads_or(bad);
-  double mean = 0.0, sd0 = 0.0;
+  __syncthreads();                                      // leaf table
+  const int slot = tid >> 2, lj = tid & 3;
+  const bool leaf_live = slot < (1 << depth);
+  const int loff = leaf_live ? sm.leaf_off[slot] : 0, lsize = leaf_live ? sm.leaf_size[slot] : 0;
+  int parity = 0;
+
+  // ---- load (coalesced), then NaN screen (remove_samples.py:31-33) + sum of the raw window in one sweep
+#pragma unroll 4
+  for (int i = tid; i < L; i += K3_NT) A[i] = src[i];
+  __syncthreads();
+  LeafOut lo = leaf_pass(K3_PASS_PLAIN, A, 0.0, 1.0, loff, lsize, lj);
+  const double sum_raw = block_combine(lo.r, slot, lj, lsize, depth, sm, parity);
+  int bad = __syncthreads_or(lo.flag);
+  K3_TICK(0)   // load + NaN screen + first sum
+  double sum_z = sum_raw;                               // windows that arrive z-scored: the same numbers
   if (!bad && p.zscore_windows) {
     // ---- per-window z-score (data_extract_vitaldb.py:93), NumPy summation order
-    SumPlain f1{A};
-    mean = __ddiv_rn(block_sum_tab(f1, depth, sm), (double)L);
-    SumDev2 f2{A, mean};
-    sd0 = __dsqrt_rn(__ddiv_rn(block_sum_tab(f2, depth, sm), (double)L));
-    int nonfinite = 0;
-    const ExactDiv dv = make_exact_div(sd0);
-    for (int i = tid; i < L; i += K3_NT) {
-      const double z = div_exact(__dsub_rn(A[i], mean), dv);
-      A[i] = z;
-      nonfinite |= (isnan(z) || isinf(z)) ? 1 : 0;     // constant window: 0/0
-    }
-    bad = __syncthreads_or(nonfinite);
+    const double mean = k3_div(sum_raw, (double)L);
+    lo = leaf_pass(K3_PASS_DEV2, A, mean, 1.0, loff, lsize, lj);
+    const double sd0 = k3_sqrt(k3_div(block_combine(lo.r, slot, lj, lsize, depth, sm, parity), (double)L));
+    lo = leaf_pass(K3_PASS_ZSCORE, A, mean, sd0, loff, lsize, lj);
+    sum_z = block_combine(lo.r, slot, lj, lsize, depth, sm, parity);
+    bad = __syncthreads_or(lo.flag);
   }
+  K3_TICK(1)   // window z-score (+ sum of the z-scored window)
   if (p.zwin) {
     double* zw = p.zwin + w * (long long)L;
+#pragma unroll 1
     for (int i = tid; i < L; i += K3_NT) zw[i] = A[i];  // NaN windows: as z-scored by the reference or raw
   }
   if (bad) {
@@ -414,21 +515,33 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p) {
   }
 
   // ---- ecg_sd = np.std(window) (remove_samples.py:62)
-  SumPlain f3{A};
-  const double m2 = __ddiv_rn(block_sum_tab(f3, depth, sm), (double)L);
-  SumDev2 f4{A, m2};
-  const double sd = __dsqrt_rn(__ddiv_rn(block_sum_tab(f4, depth, sm), (double)L));
+  lo = leaf_pass(K3_PASS_DEV2, A, k3_div(sum_z, (double)L), 1.0, loff, lsize, lj);
+  const double sd = k3_sqrt(k3_div(block_combine(lo.r, slot, lj, lsize, depth, sm, parity), (double)L));
 
+  K3_TICK(2)   // np.std
   // ---- QRS indicator: smoothgrad > 1.5 * avggrad
+  // Both box filters extend the signal by its edge value (scipy "nearest").  The prefix sums run over that
+  // EXTENDED sequence (pad samples in front, the filter overhang behind), so a box sum is P[hi] - P[lo - 1] for
+  // every sample and no thread branches on clamping.  Thread t owns extended positions e = 21 t .. 21 t + 20,
+  // i.e. samples i = e - pad.
   const int ks = p.smooth_k, ka = p.avg_k;
   const int ls = ks / 2, la = ka / 2;                  // uniform_filter1d: window [i - k/2, i - k/2 + k)
+  const int pad = (ls > la ? ls : la) + 1;
+  const int tail = (ks - 1 - ls > ka - 1 - la) ? ks - 1 - ls : ka - 1 - la;
+  const int Le = L + pad + tail;                       // <= K3_MAXL (checked at launch)
   int hazard = 0;
-  unsigned qbits = 0;                                  // bit k: QRS indicator of sample tid * ITEMS + k
-  const int i0 = tid * K3_ITEMS;
+  unsigned qbits = 0;                                  // bit k: QRS indicator of sample i0 + k
+  const int e0 = tid * K3_ITEMS;
+  const int i0 = e0 - pad;
+  int klo = -i0, khi = L - i0;                         // bits [klo, khi) are samples of the window
+  klo = klo < 0 ? 0 : (klo > K3_ITEMS ? K3_ITEMS : klo);
+  khi = khi < 0 ? 0 : (khi > K3_ITEMS ? K3_ITEMS : khi);
+  const unsigned smask = khi > klo ? (((1u << (khi - klo)) - 1u) << klo) : 0u;
   if (p.mode != 1) {
     double loc[K3_ITEMS], smv[K3_ITEMS];
     double run = 0.0;
-    if (i0 >= 1 && i0 + K3_ITEMS < L) {                // strip away from both window edges
+    // the path is chosen per WARP: a warp that straddles an edge runs the general form once instead of both
+    if (__all_sync(AEW_FULL, i0 >= 1 && i0 + K3_ITEMS < L)) {   // strips away from both window edges
       const double* zp = A + i0;
       double prv = zp[-1], cur = zp[0];
 #pragma unroll
@@ -439,29 +552,31 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p) {
         prv = cur; cur = nxt;
       }
     } else {
+      // branch-free general form: one-sided differences at (and, by edge extension, beyond) the two ends
+      const double g0 = fabs(__dsub_rn(A[1], A[0])), gL = fabs(__dsub_rn(A[L - 1], A[L - 2]));
 #pragma unroll
       for (int k = 0; k < K3_ITEMS; ++k) {
         const int i = i0 + k;
-        run += (i < L) ? absgrad(A, i, L) : 0.0;
+        const int im = i - 1 < 0 ? 0 : (i - 1 > L - 1 ? L - 1 : i - 1);
+        const int ip = i + 1 < 0 ? 0 : (i + 1 > L - 1 ? L - 1 : i + 1);
+        double g = fabs(__dmul_rn(__dsub_rn(A[ip], A[im]), 0.5));
+        g = i <= 0 ? g0 : g;
+        g = i >= L - 1 ? gL : g;
+        run += (e0 + k < Le) ? g : 0.0;
         loc[k] = run;
       }
     }
     double base = block_excl_scan(run, sm.wtot);
-    if (i0 + K3_ITEMS <= L) {
 #pragma unroll
-      for (int k = 0; k < K3_ITEMS; ++k) B[i0 + k] = base + loc[k];
-    } else {
-#pragma unroll
-      for (int k = 0; k < K3_ITEMS; ++k) if (i0 + k < L) B[i0 + k] = base + loc[k];
-    }
-    if (tid == 0) { sm.scal[0] = absgrad(A, 0, L); sm.scal[1] = absgrad(A, L - 1, L); }
+    for (int k = 0; k < K3_ITEMS; ++k) B[e0 + k] = base + loc[k];
     __syncthreads();
-    const double ag0 = sm.scal[0], agL = sm.scal[1], ptot = B[L - 1];
+    K3_TICK(3)   // |gradient| prefix
+    const double ptot = B[Le - 1];
     const double inv_s = 1.0 / (double)ks, inv_a = 1.0 / (double)ka;
     run = 0.0;
-    if (i0 - ls >= 1 && i0 + K3_ITEMS - 1 - ls + ks - 1 <= L - 1) {   // no clamping anywhere in the strip
-      const double* pl = B + i0 - ls - 1;
-      const double* ph = B + i0 - ls + ks - 1;
+    if (__all_sync(AEW_FULL, i0 >= 0 && i0 + K3_ITEMS <= L)) {   // every position of the strips is its own sample
+      const double* pl = B + e0 - ls - 1;              // (e - pad) - ls - 1 + pad
+      const double* ph = B + e0 - ls + ks - 1;
 #pragma unroll
       for (int k = 0; k < K3_ITEMS; ++k) {
         const double s = (ph[k] - pl[k]) * inv_s;
@@ -472,30 +587,24 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p) {
     } else {
 #pragma unroll
       for (int k = 0; k < K3_ITEMS; ++k) {
-        const int i = i0 + k;
-        double s = 0.0;
-        if (i < L) s = clamped_window(B, i - ls, i - ls + ks - 1, L, ag0, agL) * inv_s;
+        int i = i0 + k;
+        i = i < 0 ? 0 : (i > L - 1 ? L - 1 : i);       // edge value repeated
+        const int lo = i + pad - ls - 1;
+        const double s = (e0 + k < Le) ? (B[lo + ks] - B[lo]) * inv_s : 0.0;
         smv[k] = s;
         run += s;
         loc[k] = run;
-        if (i == 0) sm.scal[2] = s;
-        if (i == L - 1) sm.scal[3] = s;
       }
     }
     base = block_excl_scan(run, sm.wtot);               // (its barriers also end all reads of B)
-    if (i0 + K3_ITEMS <= L) {
 #pragma unroll
-      for (int k = 0; k < K3_ITEMS; ++k) B[i0 + k] = base + loc[k];
-    } else {
-#pragma unroll
-      for (int k = 0; k < K3_ITEMS; ++k) if (i0 + k < L) B[i0 + k] = base + loc[k];
-    }
+    for (int k = 0; k < K3_ITEMS; ++k) B[e0 + k] = base + loc[k];
     __syncthreads();
-    const double s0 = sm.scal[2], sL = sm.scal[3];
+    K3_TICK(4)   // smoothgrad + its prefix
     const double tol_abs = 2e-12 * ptot * inv_s;
-    if (i0 - la >= 1 && i0 + K3_ITEMS - 1 - la + ka - 1 <= L - 1) {
-      const double* pl = B + i0 - la - 1;
-      const double* ph = B + i0 - la + ka - 1;
+    if (__all_sync(AEW_FULL, smask == (1u << K3_ITEMS) - 1u)) {
+      const double* pl = B + e0 - la - 1;
+      const double* ph = B + e0 - la + ka - 1;
 #pragma unroll
       for (int k = 0; k < K3_ITEMS; ++k) {
         const double thr = 1.5 * ((ph[k] - pl[k]) * inv_a);
@@ -505,15 +614,16 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p) {
     } else {
 #pragma unroll
       for (int k = 0; k < K3_ITEMS; ++k) {
-        const int i = i0 + k;
-        if (i < L) {
-          const double thr = 1.5 * (clamped_window(B, i - la, i - la + ka - 1, L, s0, sL) * inv_a);
+        if ((smask >> k) & 1u) {
+          const int lo = e0 + k - la - 1;
+          const double thr = 1.5 * ((B[lo + ka] - B[lo]) * inv_a);
           qbits |= (unsigned)(smv[k] > thr) << k;
           hazard |= (fabs(smv[k] - thr) <= 1e-9 * (smv[k] + thr) + tol_abs) ? 1 : 0;
         }
       }
     }
     hazard = __syncthreads_or(hazard);
+    K3_TICK(5)   // indicator + hazard vote
     if (p.mode == 2) hazard = 0;
     if (p.mode == 3) hazard = 1;                        // test hook: every window takes the fallback transition
     if (hazard && tid == 0 && p.hazard_count) atomicAdd(p.hazard_count, 1ull);
@@ -552,9 +662,10 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p) {
     __syncthreads();
     qbits = 0;
 #pragma unroll
-    for (int k = 0; k < K3_ITEMS; ++k) if (i0 + k < L) qbits |= (unsigned)(sm.Q[i0 + k] != 0) << k;
+    for (int k = 0; k < K3_ITEMS; ++k) if ((smask >> k) & 1u) qbits |= (unsigned)(sm.Q[i0 + k] != 0) << k;
   }
 
+  K3_TICK(6)   // sequential fallback (hazard windows / mode 1)
   // ---- QRS runs: beg where ~q[i] & q[i+1], end where q[i] & ~q[i+1]  (ordered compaction);
   //      the flags live in registers, only each strip's first flag is exchanged
   {
@@ -563,9 +674,9 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p) {
     __syncthreads();
     const unsigned nbr = (tid + 1 < K3_NT) ? sm.Q[tid + 1] : 0u;
     const unsigned nextq = (qbits >> 1) | (nbr << (K3_ITEMS - 1));          // flag of sample i + 1
-    int nvalid = L - 1 - i0;                            // transitions exist for i < L - 1
-    nvalid = nvalid < 0 ? 0 : (nvalid > K3_ITEMS ? K3_ITEMS : nvalid);
-    const unsigned vmask = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
+    int kend = L - 1 - i0;                              // transitions exist for 0 <= i < L - 1
+    kend = kend < klo ? klo : (kend > K3_ITEMS ? K3_ITEMS : kend);
+    const unsigned vmask = ((1u << (kend - klo)) - 1u) << klo;
     unsigned bbits = ~qbits & nextq & vmask, ebits = qbits & ~nextq & vmask;
     const int packed = block_excl_scan_int(__popc(bbits) | (__popc(ebits) << 16), (int*)sm.wtot);
     int ob = packed & 0xffff, oe = packed >> 16;
@@ -574,6 +685,7 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p) {
     if (tid == K3_NT - 1) { sm.iscal[0] = ob; sm.iscal[1] = oe; }
     __syncthreads();
   }
+  K3_TICK(7)   // run compaction
   const int nbeg = sm.iscal[0], nend = sm.iscal[1];
   // ends that precede the first beg are dropped (at most one, runs alternate)
   const int skip = (nbeg > 0 && nend > 0 && sm.end[0] <= sm.beg[0]) ? 1 : 0;
@@ -581,22 +693,15 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p) {
   if (nbeg == 0) num = 0;
   const unsigned short* endp = sm.end + skip;
 
-  // ---- min_len = mean(end - beg) * 0.4 (integer sum is exact in any order)
+  // ---- min_len = mean(end - beg) * 0.4 (integer sum is exact in any order); every warp computes it for itself
+  double min_len = 0.0;
   {
-    long long part = 0;
-    for (int i = tid; i < num; i += K3_NT) part += (long long)endp[i] - (long long)sm.beg[i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(AEW_FULL, part, o);
-    if (lane == 0) ((long long*)sm.wtot)[warp] = part;
-    __syncthreads();
-    if (tid == 0) {
-      long long tot = 0;
-      for (int k = 0; k < K3_NT / 32; ++k) tot += ((long long*)sm.wtot)[k];
-      sm.scal[4] = num > 0 ? __dmul_rn(__ddiv_rn((double)tot, (double)num), 0.4) : 0.0;
-    }
-    __syncthreads();
+    unsigned part = 0;                                  // <= num * L < 2^31
+    for (int i = lane; i < num; i += 32) part += (unsigned)(endp[i] - sm.beg[i]);
+    const unsigned tot = __reduce_add_sync(AEW_FULL, part);
+    if (num > 0) min_len = __dmul_rn(k3_div((double)tot, (double)num), 0.4);
   }
-  const double min_len = sm.scal[4];
+  K3_TICK(8)   // min_len
 
   // ---- per run: most prominent strict local maximum (scipy.signal.find_peaks semantics)
   for (int r = warp; r < num; r += K3_NT / 32) {
@@ -610,6 +715,9 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p) {
       double v[4];
 #pragma unroll
       for (int m = 0; m < 4; ++m) v[m] = (32 * m + lane < n) ? d[32 * m + lane] : 0.0;
+      unsigned long long kv[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) kv[m] = dkey(v[m]);
       unsigned peakmask[4];
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
@@ -651,32 +759,32 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p) {
           int nl = -1, nr = n;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            const int i = 32 * c + lane;
-            const unsigned hi = __ballot_sync(AEW_FULL, i < n && v[c] > h);
-            if (hi) {
-              const unsigned below = (32 * c + 31 < pk) ? hi : ((32 * c > pk) ? 0u : (hi & ((1u << (pk - 32 * c)) - 1u)));
-              const unsigned above = (32 * c > pk) ? hi : ((32 * c + 31 < pk) ? 0u : (hi & ~((2u << (pk - 32 * c)) - 1u)));
-              if (below) { const int q = 32 * c + 31 - __clz((int)below); nl = q > nl ? q : nl; }
-              if (above) { const int q = 32 * c + __ffs((int)above) - 1; nr = q < nr ? q : nr; }
+            if (32 * c < n) {                                  // (uniform) chunks beyond the run hold nothing
+              const int i = 32 * c + lane;
+              const unsigned hi = __ballot_sync(AEW_FULL, i < n && v[c] > h);
+              if (hi) {
+                const unsigned below = (32 * c + 31 < pk) ? hi : ((32 * c > pk) ? 0u : (hi & ((1u << (pk - 32 * c)) - 1u)));
+                const unsigned above = (32 * c > pk) ? hi : ((32 * c + 31 < pk) ? 0u : (hi & ~((2u << (pk - 32 * c)) - 1u)));
+                if (below) { const int q = 32 * c + 31 - __clz((int)below); nl = q > nl ? q : nl; }
+                if (above) { const int q = 32 * c + __ffs((int)above) - 1; nr = q < nr ? q : nr; }
+              }
             }
           }
-          double lmin = h, rmin = h;
+          // minima of (nl, pk] and [pk, nr) as order-preserving integer keys: two 32-bit warp reductions each
+          unsigned long long kl = ~0ull, kr = ~0ull;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const int i = 32 * c + lane;
-            if (i > nl && i <= pk && v[c] < lmin) lmin = v[c];
-            if (i >= pk && i < nr && v[c] < rmin) rmin = v[c];
+            if (i > nl && i <= pk && kv[c] < kl) kl = kv[c];
+            if (i >= pk && i < nr && kv[c] < kr) kr = kv[c];
           }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const double ol = __shfl_xor_sync(AEW_FULL, lmin, o), orr = __shfl_xor_sync(AEW_FULL, rmin, o);
-            lmin = ol < lmin ? ol : lmin;
-            rmin = orr < rmin ? orr : rmin;
-          }
+          const double lmin = warp_min_key(kl), rmin = warp_min_key(kr);
           const double prom = __dsub_rn(h, lmin > rmin ? lmin : rmin);
           if (prom > best) { best = prom; best_i = pk; }       // candidates come in ascending order: first max wins
         }
       }
+      if (lane == 0) sm.cand[r] = best_i == 0x7fffffff ? (unsigned short)K3_NONE : (unsigned short)(b + best_i);
+      continue;                                                // every lane holds the same best: nothing to reduce
     } else if (!((double)n < min_len)) {
       for (int i = 1 + lane; i < n - 1; i += 32) {
         if (d[i - 1] < d[i]) {
@@ -703,79 +811,78 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p) {
     if (lane == 0) sm.cand[r] = best_i == 0x7fffffff ? (unsigned short)K3_NONE : (unsigned short)(b + best_i);
   }
   __syncthreads();
+  K3_TICK(9)   // most prominent peak per run
 
-  // ---- refractory chain (sequential by definition; thread 0)
-  if (tid == 0) {
+  // ---- everything between the candidates and the keep decision is a few hundred operations on <= 72 numbers:
+  //      warp 0 does it alone, ordered by warp barriers, while the other warps wait at ONE block barrier
+  if (warp == 0) {
+    // refractory chain (sequential by definition); all lanes walk it alike so that all of them know np
     int np = 0, last = 0;
     for (int r = 0; r < num; ++r) {
       const int c = sm.cand[r];
-      if (c == (int)K3_NONE) continue;
-      if (c - last > p.refractory) {
-        if (np < K3_MAXP) sm.ipeaks[np] = c;
+      if (c != (int)K3_NONE && c - last > p.refractory) {
+        if (np < K3_MAXP && lane == 0) sm.ipeaks[np] = c;
         ++np;
         last = c;
       }
     }
-    if (np > K3_MAXP) { atomicOr(p.status, AEW_DEV_RUN_OVERFLOW); np = K3_MAXP; }
-    sm.iscal[2] = np;
+    if (np > K3_MAXP) { if (lane == 0) atomicOr(p.status, AEW_DEV_RUN_OVERFLOW); np = K3_MAXP; }
+    __syncwarp();
+    // remove_samples.py:53-54 keeps 0 < p < L (always true here: p > refractory)
+    // HR = 60 fs / median(RR) and RMSSD (remove_samples.py:85-121)
+    const int nd = np - 1;
+    for (int t = lane; t < nd; t += 32) {
+      const int d0 = sm.ipeaks[t + 1] - sm.ipeaks[t];
+      sm.idiff[t] = d0;
+      if (t + 1 < nd) {
+        const double cur = k3_div((double)(sm.ipeaks[t + 2] - sm.ipeaks[t + 1]), p.rr_div);
+        const double prv = k3_div((double)d0, p.rr_div);
+        const double dd = __dsub_rn(cur, prv);
+        sm.dsq[t] = __dmul_rn(dd, dd);
+      }
+    }
+    __syncwarp();
+    for (int t = lane; t < nd; t += 32) {                  // rank sort of <= 71 integers
+      const int mine = sm.idiff[t];
+      int rank = 0;
+      for (int j = 0; j < nd; ++j) {
+        const int o = sm.idiff[j];
+        rank += (o < mine) || (o == mine && j < t);
+      }
+      sm.isort[rank] = mine;
+    }
+    SumPlain fq{sm.dsq};                                   // NumPy leaf order over np-2 <= 70 values
+    const double ssq = pw_leaf_sum8(fq, 0, np >= 3 ? np - 2 : 0, lane & 7);
+    __syncwarp();
+    if (lane == 0) {
+      double hr = qnan, rms = qnan;
+      if (np >= 2) {
+        const double med = (nd & 1) ? (double)sm.isort[nd / 2]
+                                    : __dmul_rn(__dadd_rn((double)sm.isort[nd / 2 - 1], (double)sm.isort[nd / 2]), 0.5);
+        hr = k3_div(p.hr_num, med);
+      }
+      if (np >= 3) rms = k3_sqrt(k3_div(ssq, (double)(np - 2)));
+      const double sdn = k3_div(sd, (double)np);
+      const bool remove = (hr < p.hr_lo) || (hr > p.hr_hi) || isnan(hr) || (rms > p.pvc_threshold) ||
+                          (sdn > p.sd_threshold);
+      sm.iscal[2] = np;
+      sm.iscal[3] = remove ? 0 : 1;
+      p.keep[w] = remove ? 0 : 1;
+      p.has_nan[w] = 0;
+      p.n_peaks[w] = np;
+      p.stats[4 * w + 0] = hr; p.stats[4 * w + 1] = rms; p.stats[4 * w + 2] = sd; p.stats[4 * w + 3] = sdn;
+    }
   }
   __syncthreads();
   const int np = sm.iscal[2];
-  // remove_samples.py:53-54 keeps 0 < p < L (always true here: p > refractory)
-
-  // ---- HR = 60 fs / median(RR) and RMSSD (remove_samples.py:85-121), cooperatively
-  const int nd = np - 1;
-  if (tid < nd) {
-    const int d0 = sm.ipeaks[tid + 1] - sm.ipeaks[tid];
-    sm.idiff[tid] = d0;
-    if (tid + 1 < nd) {
-      const double cur = __ddiv_rn((double)(sm.ipeaks[tid + 2] - sm.ipeaks[tid + 1]), p.rr_div);
-      const double prv = __ddiv_rn((double)d0, p.rr_div);
-      const double dd = __dsub_rn(cur, prv);
-      sm.dsq[tid] = __dmul_rn(dd, dd);
-    }
-  }
-  __syncthreads();
-  if (tid < nd) {                                        // rank sort of <= 71 integers
-    const int mine = sm.idiff[tid];
-    int rank = 0;
-    for (int j = 0; j < nd; ++j) {
-      const int o = sm.idiff[j];
-      rank += (o < mine) || (o == mine && j < tid);
-    }
-    sm.isort[rank] = mine;
-  }
-  double ssq = 0.0;
-  if (warp == 15) {                                      // NumPy leaf order over np-2 <= 70 values
-    SumPlain fq{sm.dsq};
-    ssq = pw_leaf_sum8(fq, 0, np >= 3 ? np - 2 : 0, lane & 7);
-    if (lane == 0) sm.scal[5] = ssq;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    double hr = qnan, rms = qnan;
-    if (np >= 2) {
-      const double med = (nd & 1) ? (double)sm.isort[nd / 2]
-                                  : __dmul_rn(__dadd_rn((double)sm.isort[nd / 2 - 1], (double)sm.isort[nd / 2]), 0.5);
-      hr = __ddiv_rn(p.hr_num, med);
-    }
-    if (np >= 3) rms = __dsqrt_rn(__ddiv_rn(sm.scal[5], (double)(np - 2)));
-    const double sdn = __ddiv_rn(sd, (double)np);
-    const bool remove = (hr < p.hr_lo) || (hr > p.hr_hi) || isnan(hr) || (rms > p.pvc_threshold) ||
-                        (sdn > p.sd_threshold);
-    sm.iscal[3] = remove ? 0 : 1;
-    p.keep[w] = remove ? 0 : 1;
-    p.has_nan[w] = 0;
-    p.n_peaks[w] = np;
-    p.stats[4 * w + 0] = hr; p.stats[4 * w + 1] = rms; p.stats[4 * w + 2] = sd; p.stats[4 * w + 3] = sdn;
-  }
   for (int i = tid; i < K3_MAXP; i += K3_NT) p.peaks[w * K3_MAXP + i] = i < np ? sm.ipeaks[i] : -1;
-  __syncthreads();
-
+  K3_TICK(11)  // refractory chain, HR / RMSSD / keep decision, peaks out
   // ---- median beat of kept windows (median_sample.py:6-54) -> np_waves row
   if (sm.iscal[3] && (p.median || p.waves))
     window_median(A, sm.ipeaks, np, L, p.pre, p.post, p.median ? p.median + w * K3_BEAT : nullptr,
                   p.waves ? p.waves + w * K3_BEAT : nullptr);
+  __syncthreads();
+  K3_TICK(12)  // median beat
 }
 
 // Stand-alone median beats for given peaks (the compute_median_sample_ecg shim):
@@ -804,6 +911,17 @@ __global__ void __launch_bounds__(K3_NT, 1) k4_median(const double* __restrict__
 
 }  // namespace
 
+static unsigned long long* g_k3_dbg = nullptr;   // device counters, allocated once when AEW_K3_TIMING is set
+static unsigned long long* k3_timing_buffer() {
+#ifndef AEW_EMUL
+  if (!g_k3_dbg && getenv("AEW_K3_TIMING")) {
+    cudaMalloc(&g_k3_dbg, 16 * sizeof(unsigned long long));
+    cudaMemset(g_k3_dbg, 0, 16 * sizeof(unsigned long long));
+  }
+#endif
+  return g_k3_dbg;
+}
+
 extern "C" int aew_windows_max_peaks(void) { return K3_MAXP; }
 extern "C" int aew_windows_max_len(void) { return K3_MAXL; }
 
@@ -814,6 +932,14 @@ extern "C" int aew_windows_beats_f64(const K3Params* hp, void* stream) {
     return AEW_ERR_ARG;
   if (p.n_win == 0) return AEW_OK;
   if (p.L < 16 || p.L > K3_MAXL || p.n_win < 0 || p.n_win > 0x7fffffffll) return AEW_ERR_UNSUPPORTED;
+  if (p.smooth_k < 1 || p.avg_k < 1) return AEW_ERR_UNSUPPORTED;
+  {
+    // the box filters' prefix sums run over the window extended by its edge values (see the kernel)
+    const int ls = p.smooth_k / 2, la = p.avg_k / 2;
+    const int pad = (ls > la ? ls : la) + 1;
+    const int tail = (p.smooth_k - 1 - ls > p.avg_k - 1 - la) ? p.smooth_k - 1 - ls : p.avg_k - 1 - la;
+    if ((long long)p.L + pad + tail > K3_MAXL) return AEW_ERR_UNSUPPORTED;
+  }
   if (pw_depth(p.L) > 7 || p.pre + p.post != K3_BEAT || p.smooth_k < 1 || p.avg_k < 1 || p.smooth_k > p.L ||
       p.avg_k > p.L || p.refractory < 1 || (p.L / (p.refractory + 1) + 1) > K3_MAXP)
     return AEW_ERR_UNSUPPORTED;
@@ -821,8 +947,23 @@ extern "C" int aew_windows_beats_f64(const K3Params* hp, void* stream) {
   if (smem > 227 * 1024) return AEW_ERR_UNSUPPORTED;
   static bool attr_done = false;
   if (!attr_done) { AEW_SET_MAX_SMEM(k3_windows, 227 * 1024); attr_done = true; }
-  AEW_LAUNCH(k3_windows, (unsigned)p.n_win, K3_NT, smem, (cudaStream_t)stream, p);
+  AEW_LAUNCH(k3_windows, (unsigned)p.n_win, K3_NT, smem, (cudaStream_t)stream, p, k3_timing_buffer());
   return (int)cudaGetLastError();
+}
+
+// debugging aid (AEW_K3_TIMING=1): cycles thread 0 of every block spent per phase of k3_windows, summed over
+// blocks; copies and clears the 16 counters (synchronises the device)
+extern "C" int aew_windows_timing_dump(unsigned long long* h_out16) {
+#ifndef AEW_EMUL
+  if (!g_k3_dbg || !h_out16) return AEW_ERR_ARG;
+  cudaDeviceSynchronize();
+  cudaMemcpy(h_out16, g_k3_dbg, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaMemset(g_k3_dbg, 0, 16 * sizeof(unsigned long long));
+  return AEW_OK;
+#else
+  (void)h_out16;
+  return AEW_ERR_UNSUPPORTED;
+#endif
 }
 
 // windows: [n_win][L] contiguous, peaks: CSR (peak_off[n_win+1]); at most 128 peaks per window.

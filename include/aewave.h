@@ -124,6 +124,9 @@ typedef struct K3Params {
 int aew_windows_max_peaks(void);
 int aew_windows_max_len(void);
 int aew_windows_beats_f64(const K3Params* h_params, void* stream);
+/* debugging aid: with AEW_K3_TIMING=1 in the environment the window kernel accumulates the cycles thread 0 of
+ * every block spends per phase; this copies and clears the 16 counters (synchronises the device) */
+int aew_windows_timing_dump(unsigned long long* h_out16);
 /* compute_median_sample_ecg for given peaks: windows [n_win][L], peaks CSR; aligned may be NULL */
 int aew_median_beats_f64(const double* d_windows, long long n_win, int L, const int* d_peaks,
                          const long long* d_peak_off, int max_peaks_per_window, int pre, int post,

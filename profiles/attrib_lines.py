@@ -1,32 +1,36 @@
+"""Per-source-line attribution of an ncu capture: aligns the SASS page of the report (ncu -i X.ncu-rep --page source
+--csv --print-source sass) with nvdisasm -g -c of the cubin (same build), then sums samples, executed
+instructions and the main stall reasons per source line.
+usage: attrib_lines.py <nvdisasm.txt> <sass.csv> <mangled-name-fragment> [top_n]"""
 import csv, re, sys, collections
-dis, sasscsv, func, srcfile = sys.argv[1:5]
-# parse nvdisasm: per function list of (line, file) per instruction in order
-lines=open(dis).read().split('\n')
-cur=None; cur_line=None; cur_file=None; ins=[]
-infunc=False
-for l in lines:
-    m=re.match(r'\s*\.text\.(\S+):',l)
-    if m:
-        infunc = func in m.group(1); continue
+dis, sasscsv, func = sys.argv[1:4]
+top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+ins = []; cur = None; infunc = False
+for l in open(dis).read().split('\n'):
+    m = re.match(r'\s*\.text\.(\S+):', l)
+    if m: infunc = func in m.group(1); continue
     if not infunc: continue
-    m=re.match(r'\s*//## File "(.*)", line (\d+)',l)
-    if m: cur_file=m.group(1); cur_line=int(m.group(2)); continue
-    if re.match(r'\s*/\*[0-9a-f]{4,6}\*/',l):
-        ins.append((cur_file,cur_line,l.strip()))
-rows=list(csv.reader(open(sasscsv)))
-hdr=rows[1]; data=[r for r in rows[2:] if len(r)>=10]
-ixs=hdr.index('# Samples'); ixi=hdr.index('Instructions Executed')
-print("sass rows",len(data),"disasm ins",len(ins))
-n=min(len(data),len(ins))
-agg=collections.defaultdict(lambda:[0,0])
-for k in range(n):
-    f,ln,_=ins[k]; key=(f.split('/')[-1] if f else '?',ln)
-    agg[key][0]+=int(data[k][ixs]); agg[key][1]+=int(data[k][ixi])
-ts=sum(v[0] for v in agg.values()); ti=sum(v[1] for v in agg.values())
-src={}
-for fn in set(k[0] for k in agg):
-    try: src[fn]=open('/root/repo/ae_waveforms_b200/csrc/'+fn).read().split('\n')
-    except Exception: src[fn]=[]
-for (f,ln),v in sorted(agg.items(), key=lambda kv:-kv[1][0])[:int(sys.argv[5]) if len(sys.argv)>5 else 40]:
-    text = src.get(f,[])[ln-1].strip()[:100] if ln and ln-1 < len(src.get(f,[])) else ''
-    print(f"{f}:{ln:<4} smp={v[0]/ts*100:5.1f}% inst={v[1]/ti*100:5.1f}%  {text}")
+    m = re.match(r'\s*//## File "(.*)", line (\d+)', l)
+    if m: cur = (m.group(1).split('/')[-1], int(m.group(2))); continue
+    if re.match(r'\s*/\*[0-9a-f]{4,6}\*/', l): ins.append((cur, l.strip()))
+rows = list(csv.reader(open(sasscsv))); hdr = rows[1]; data = [r for r in rows[2:] if len(r) >= 46]
+print("sass rows", len(data), "disasm instructions", len(ins))
+assert len(data) == len(ins), "report and cubin are different builds"
+cols = ['# Samples', 'Instructions Executed', 'stall_barrier', 'stall_no_inst', 'stall_wait', 'stall_short_sb',
+        'stall_long_sb', 'stall_math', 'stall_branch_resolving', 'stall_mio']
+ix = [hdr.index(c) for c in cols]
+agg = collections.defaultdict(lambda: [0] * len(cols))
+for (key, _), r in zip(ins, data):
+    a = agg[key]
+    for k, i in enumerate(ix): a[k] += int(r[i])
+ts = sum(v[0] for v in agg.values()); ti = sum(v[1] for v in agg.values())
+src = {}
+def text(f, ln):
+    if f not in src:
+        try: src[f] = open('/root/repo/ae_waveforms_b200/csrc/' + f).read().split('\n')
+        except Exception: src[f] = []
+    return src[f][ln - 1].strip()[:80] if 0 < ln <= len(src[f]) else ''
+print("line  samples%  inst%  [barrier no_inst wait short_sb long_sb math branch mio as % of the line's samples]")
+for (f, ln), v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+    rs = ' '.join(f"{100 * x / max(v[0], 1):3.0f}" for x in v[2:])
+    print(f"{f}:{ln:<4} {v[0] / ts * 100:5.1f}% {v[1] / ti * 100:5.1f}%  [{rs}]  {text(f, ln)}")

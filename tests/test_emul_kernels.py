@@ -108,6 +108,20 @@ def test_k4_median_golden(golden):
         assert same(med, g[f"{name}_median"]) and same(al, g[f"{name}_aligned"])
 
 
+def test_k4_median_all_beat_counts(golden):
+    """One thread per column (<= 32 beats), lane pairs (33..64) and the counting fallback (> 64) against the oracle,
+    with edge peaks (short, left-aligned slices) and ties (a coarsely quantised window)."""
+    g = golden("median")
+    rng = np.random.default_rng(3)
+    quant = np.round(g["window"] * 4) / 4
+    for n in (2, 31, 32, 33, 34, 47, 63, 64, 65, 70):
+        for win in (g["window"], quant):
+            peaks = np.sort(rng.choice(np.arange(120, len(win) - 230), n - 2, replace=False))
+            peaks = np.concatenate([[40], peaks, [len(win) - 30]])          # both edges clipped
+            med, _ = eh.median_beats(win, peaks, want_aligned=False)
+            assert same(med, rp.compute_median_sample_ecg(win, list(peaks), 500)), n
+
+
 def test_k5_recon_golden(golden):
     g = golden("recon")
     for k, smap in enumerate(g["sigma_maps"]):

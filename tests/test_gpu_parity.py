@@ -217,6 +217,13 @@ def test_median_dropin_golden(gpu, golden):
     a = compute_median_sample_ecg(g["window"], list(peaks), 500)
     b = compute_median_sample_ecg(g["window"], list(rng.permutation(peaks)), 500)
     assert same(a, b) and same(a, rp.compute_median_sample_ecg(g["window"], list(peaks), 500))
+    quant = np.round(g["window"] * 4) / 4                            # ties; every code path of the column median
+    for n in (2, 31, 32, 33, 34, 47, 63, 64, 65, 100):
+        for win in (g["window"], quant):
+            peaks = np.sort(rng.choice(np.arange(120, len(win) - 230), n - 2, replace=False))
+            peaks = np.concatenate([[40], peaks, [len(win) - 30]])
+            assert same(compute_median_sample_ecg(win, list(peaks), 500),
+                        rp.compute_median_sample_ecg(win, list(peaks), 500)), n
 
 
 def test_remove_samples_dropin(gpu, golden):
