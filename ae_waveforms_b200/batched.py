@@ -180,6 +180,7 @@ class Preprocessor:
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
         y = torch.empty_like(flat) if out is None else out
         tmp = torch.empty_like(flat) if tmp is None else tmp
+        self._filter_tmp = tmp                  # free again once the filter is done: scratch for the window kernels
         st = _cabi.stream_ptr(torch)
         _cabi.check(lib.aew_segments_find_f64(_ptr(flat), _ptr(d_beg), _ptr(d_end), n_rec, total, _ptr(cnt), _ptr(y),
                                               _ptr(ws), ws_bytes, max_seg, st), "segments_find")
@@ -219,8 +220,10 @@ class Preprocessor:
                 ((k + 1) * L).astype(np.int64))
 
     def screen_windows(self, y, win_start_h, want_median=True, want_zwin=False, zscore_windows=True,
-                       pvc_threshold=None, sd_threshold=None, L=None):
-        """K3 + K4 on the windows whose flat offsets are given."""
+                       pvc_threshold=None, sd_threshold=None, L=None, zwin_scratch=None):
+        """K3 + K4 on the windows whose flat offsets are given.  ``zwin_scratch``: optional float64 tensor of at
+        least n_win * L elements; the screen kernel parks the z-scored windows there for the median kernel (which
+        otherwise re-derives them from ``y`` and the per-window mean / sd)."""
         torch, lib = self.torch, self.lib
         L = L or self.L
         n_win = len(win_start_h)
@@ -235,11 +238,17 @@ class Preprocessor:
             median=torch.empty((n_win, BEAT_LEN), dtype=torch.float64, device=dev) if want_median else None,
             waves=torch.empty((n_win, BEAT_LEN), dtype=torch.float32, device=dev) if want_median else None,
             zwin=torch.empty((n_win, L), dtype=torch.float64, device=dev) if want_zwin else None,
+            zparams=torch.empty((n_win, 2), dtype=torch.float64, device=dev) if want_median else None,
             status=torch.zeros(1, dtype=torch.int32, device=dev),
             hazards=torch.zeros(1, dtype=torch.int64, device=dev))
         if n_win == 0:
             return out
         d_start = torch.from_numpy(np.ascontiguousarray(win_start_h, dtype=np.int64)).to(dev)
+        zwin_ptr = out["zwin"].data_ptr() if want_zwin else None
+        if zwin_ptr is None and want_median and zscore_windows and zwin_scratch is not None \
+                and zwin_scratch.dtype == torch.float64 and zwin_scratch.numel() >= n_win * L \
+                and zwin_scratch.data_ptr() != y.data_ptr():
+            zwin_ptr = zwin_scratch.data_ptr()
         fs = self.fs
         p = _cabi.K3Params(
             y=y.data_ptr(), win_start=d_start.data_ptr(), n_win=n_win, L=L,
@@ -252,10 +261,11 @@ class Preprocessor:
             peaks=out["peaks"].data_ptr(), stats=out["stats"].data_ptr(),
             median=out["median"].data_ptr() if want_median else None,
             waves=out["waves"].data_ptr() if want_median else None,
-            zwin=out["zwin"].data_ptr() if want_zwin else None,
+            zwin=zwin_ptr,
+            zparams=out["zparams"].data_ptr() if want_median else None,
             status=out["status"].data_ptr(), hazard_count=out["hazards"].data_ptr())
         _cabi.check(lib.aew_windows_beats_f64(ctypes.byref(p), _cabi.stream_ptr(torch)), "windows_beats")
-        self.launches += 1
+        self.launches += 2 if want_median else 1
         out["_win_start"] = d_start
         return out
 
@@ -273,7 +283,7 @@ class Preprocessor:
         y, header = self.filter_records(flat, beg_h, end_h, d_beg, d_end, mean, sd, cnt,
                                         out=(scratch or {}).get("y"), tmp=(scratch or {}).get("tmp"))
         win_start, win_case, win_end = self.window_table(beg_h, end_h, batch.case_ids)
-        scr = self.screen_windows(y, win_start)
+        scr = self.screen_windows(y, win_start, zwin_scratch=getattr(self, "_filter_tmp", None))
         keep_idx = torch.nonzero(scr["keep"]).squeeze(1)            # sync: number of kept windows
         hdr = header.cpu().numpy()
         _cabi.check_device_status(int(hdr[4]), "filter")

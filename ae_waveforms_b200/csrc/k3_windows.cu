@@ -306,12 +306,23 @@ __device__ __forceinline__ void sort_network(double (&v)[N]) { OddEvenSort<0, N 
 
 // value of beat b at column c (median_sample.py:30-41): short slices are LEFT-aligned
 // in a NaN row; +inf stands for the NaN padding
-__device__ __forceinline__ double beat_value(const double* __restrict__ z, int p, int c, int L, int pre, int post,
-                                             int& valid) {
+// where the samples of a window come from: as stored, or z-scored on the fly with the window's own mean / sd --
+// the same two roundings as the in-place transform of the screen kernel, so the bits agree
+struct BeatSrc {
+  const double* z;
+  double mean;
+  ExactDiv dv;
+  int zs;
+  __device__ __forceinline__ double at(int idx) const {
+    const double x = z[idx];
+    return zs ? div_exact(__dsub_rn(x, mean), dv) : x;
+  }
+};
+__device__ __forceinline__ double beat_value(const BeatSrc& z, int p, int c, int L, int pre, int post, int& valid) {
   const int s = p - pre < 0 ? 0 : p - pre;
   const int e = p + post > L ? L : p + post;
   const int idx = s + c;
-  if (idx < e) { ++valid; return z[idx]; }
+  if (idx < e) { ++valid; return z.at(idx); }
   return __longlong_as_double(0x7ff0000000000000ll);
 }
 
@@ -322,17 +333,32 @@ __device__ __forceinline__ double beat_value(const double* __restrict__ z, int p
 // the hundreds a warp-wide sort needs.  The median is (lo + hi) / 2 with lo == hi for odd counts, exactly as
 // np.ma.median evaluates it; an all-NaN column gives NaN.  `paired` is uniform over the block; inactive
 // threads run along (their lanes take part in the exchanges) and return garbage.
-__device__ __forceinline__ double column_median_64(const double* __restrict__ z, const int* __restrict__ peaks,
+__device__ __forceinline__ double column_median_64(const BeatSrc& z, const int* __restrict__ peaks,
                                                    int n, int c, int half, bool active, bool paired, int L, int pre,
                                                    int post) {
   const double inf = __longlong_as_double(0x7ff0000000000000ll);
   double v[32];
-  int valid = 0;
+  // all loads first (no control flow between them: from global memory each one is a full round trip), then
+  // the optional z-score of the values that exist
+  unsigned okmask = 0;
 #pragma unroll
   for (int b = 0; b < 32; ++b) {
     const int bb = 32 * half + b;
-    v[b] = (active && bb < n) ? beat_value(z, peaks[bb], c, L, pre, post, valid) : inf;
+    const bool have = active && bb < n;
+    const int pk = have ? peaks[bb] : 0;
+    const int s0 = pk - pre < 0 ? 0 : pk - pre;
+    const int e0 = pk + post > L ? L : pk + post;
+    const bool ok = have && s0 + c < e0;                 // short slices are left-aligned, NaN-padded on the right
+    v[b] = ok ? z.z[s0 + c] : inf;
+    okmask |= (unsigned)ok << b;
   }
+  if (z.zs) {
+#pragma unroll
+    for (int b = 0; b < 32; ++b) {
+      if ((okmask >> b) & 1u) v[b] = div_exact(__dsub_rn(v[b], z.mean), z.dv);   // (padding stays +inf)
+    }
+  }
+  int valid = __popc(okmask);
   sort_network<32>(v);
   if (paired) {
     valid += __shfl_xor_sync(AEW_FULL, valid, 1);
@@ -374,7 +400,7 @@ __device__ __forceinline__ double column_median_64(const double* __restrict__ z,
 // Any number of beats, by one thread, by counting: the element of rank r is the one with <= r smaller values and
 // > r values that are smaller or equal.  O(n^2) but a dozen instructions of code; only reached beyond 64 beats
 // per window, which the 180 bpm screen of the reference rules out for its own window length.
-__device__ __noinline__ double column_median_count(const double* __restrict__ z, const int* __restrict__ peaks, int n,
+__device__ __noinline__ double column_median_count(const BeatSrc& z, const int* __restrict__ peaks, int n,
                                                    int c, int L, int pre, int post) {
   int valid = 0;
   for (int b = 0; b < n; ++b) { int t = 0; (void)beat_value(z, peaks[b], c, L, pre, post, t); valid += t; }
@@ -400,7 +426,7 @@ __device__ __noinline__ double column_median_count(const double* __restrict__ z,
 }
 
 // all pre+post columns of one window; every thread of the block calls it
-__device__ __forceinline__ void window_median(const double* __restrict__ z, const int* __restrict__ peaks, int n,
+__device__ __forceinline__ void window_median(const BeatSrc& z, const int* __restrict__ peaks, int n,
                                               int L, int pre, int post, double* __restrict__ med,
                                               float* __restrict__ waves) {
   const int S = pre + post;
@@ -498,6 +524,7 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p, unsigned long
     lo = leaf_pass(K3_PASS_ZSCORE, A, mean, sd0, loff, lsize, lj);
     sum_z = block_combine(lo.r, slot, lj, lsize, depth, sm, parity);
     bad = __syncthreads_or(lo.flag);
+    if (tid == 0 && p.zparams) { p.zparams[2 * w] = mean; p.zparams[2 * w + 1] = sd0; }   // for the median kernel
   }
   K3_TICK(1)   // window z-score (+ sum of the z-scored window)
   if (p.zwin) {
@@ -877,12 +904,57 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p, unsigned long
   const int np = sm.iscal[2];
   for (int i = tid; i < K3_MAXP; i += K3_NT) p.peaks[w * K3_MAXP + i] = i < np ? sm.ipeaks[i] : -1;
   K3_TICK(11)  // refractory chain, HR / RMSSD / keep decision, peaks out
-  // ---- median beat of kept windows (median_sample.py:6-54) -> np_waves row
-  if (sm.iscal[3] && (p.median || p.waves))
-    window_median(A, sm.ipeaks, np, L, p.pre, p.post, p.median ? p.median + w * K3_BEAT : nullptr,
-                  p.waves ? p.waves + w * K3_BEAT : nullptr);
+}
+
+// ---- K3b: median beat of kept windows (median_sample.py:6-54) -> np_waves row.
+// A kernel of its own: the 32-input sorting network is 25 KB of straight-line code; inside the screen kernel it
+// was fetched from L2 once per window (see the note on instruction fetch above), here it stays in the
+// instruction cache while the blocks stream through the windows.  One thread per beat column; the samples are
+// re-read from global memory (L2 for the most part: the screen kernel has just read them) and z-scored on the
+// fly with the window's mean / sd saved by the screen kernel.
+// Blocks of 160 threads take half of a window's 320 columns each: three of them fit an SM (registers), and their
+// start-up round trips to global memory overlap.
+#define K3B_NT 160
+__global__ void __launch_bounds__(K3B_NT, 3) k3_median(K3Params p) {
+  __shared__ int s_peaks[K3_MAXP];
+  const long long w = blockIdx.x >> 1;
+  const int c_lo = (int)(blockIdx.x & 1) * K3B_NT;
+  // everything the block needs to get going, in one round trip
+  const int keep = p.keep[w];
+  const int n = p.n_peaks[w];
+  const long long start = p.win_start[w];
+  const bool derive = p.zscore_windows && !p.zwin;
+  const double mean = derive ? p.zparams[2 * w] : 0.0;
+  const double sd0 = derive ? p.zparams[2 * w + 1] : 1.0;
+  if (threadIdx.x < K3_MAXP) s_peaks[threadIdx.x] = p.peaks[w * K3_MAXP + threadIdx.x];
+  if (!keep) return;                                     // rows of removed windows stay undefined, as before
   __syncthreads();
-  K3_TICK(12)  // median beat
+  BeatSrc src;                                           // the z-scored window if the screen kernel parked it
+  src.z = p.zwin ? p.zwin + w * (long long)p.L : p.y + start;
+  src.zs = p.zscore_windows && !p.zwin;
+  src.mean = mean;
+  src.dv = make_exact_div(sd0);
+  double* med = p.median ? p.median + w * K3_BEAT : nullptr;
+  float* waves = p.waves ? p.waves + w * K3_BEAT : nullptr;
+  if (n > 64) {
+    const int c = c_lo + threadIdx.x;
+    const double m = column_median_count(src, s_peaks, n, c, p.L, p.pre, p.post);
+    if (med) med[c] = m;
+    if (waves) waves[c] = (float)m;
+    return;
+  }
+  const bool paired = n > 32;
+  const int per_pass = paired ? K3B_NT / 2 : K3B_NT;
+#pragma unroll 1
+  for (int c0 = 0; c0 < K3B_NT; c0 += per_pass) {
+    const int c = c_lo + c0 + (paired ? (int)(threadIdx.x >> 1) : (int)threadIdx.x);
+    const int half = paired ? (int)(threadIdx.x & 1) : 0;
+    const double m = column_median_64(src, s_peaks, n, c, half, true, paired, p.L, p.pre, p.post);
+    if (half == 0) {
+      if (med) med[c] = m;
+      if (waves) waves[c] = (float)m;
+    }
+  }
 }
 
 // Stand-alone median beats for given peaks (the compute_median_sample_ecg shim):
@@ -906,7 +978,9 @@ __global__ void __launch_bounds__(K3_NT, 1) k4_median(const double* __restrict__
       al[i] = (s + c < e) ? z[s + c] : qnan;
     }
   }
-  window_median(z, pk, n, L, pre, post, median + w * S, nullptr);
+  BeatSrc src;
+  src.z = z; src.zs = 0; src.mean = 0.0; src.dv = make_exact_div(1.0);
+  window_median(src, pk, n, L, pre, post, median + w * S, nullptr);
 }
 
 }  // namespace
@@ -941,13 +1015,15 @@ extern "C" int aew_windows_beats_f64(const K3Params* hp, void* stream) {
     if ((long long)p.L + pad + tail > K3_MAXL) return AEW_ERR_UNSUPPORTED;
   }
   if (pw_depth(p.L) > 7 || p.pre + p.post != K3_BEAT || p.smooth_k < 1 || p.avg_k < 1 || p.smooth_k > p.L ||
-      p.avg_k > p.L || p.refractory < 1 || (p.L / (p.refractory + 1) + 1) > K3_MAXP)
+      p.avg_k > p.L || p.refractory < 1 || (p.L / (p.refractory + 1) + 1) > K3_MAXP || p.n_win > 0x3fffffffll)
     return AEW_ERR_UNSUPPORTED;
   const size_t smem = k3_smem_layout(nullptr, p.L, nullptr);
   if (smem > 227 * 1024) return AEW_ERR_UNSUPPORTED;
   static bool attr_done = false;
   if (!attr_done) { AEW_SET_MAX_SMEM(k3_windows, 227 * 1024); attr_done = true; }
+  if ((p.median || p.waves) && p.zscore_windows && !p.zparams && !p.zwin) return AEW_ERR_ARG;
   AEW_LAUNCH(k3_windows, (unsigned)p.n_win, K3_NT, smem, (cudaStream_t)stream, p, k3_timing_buffer());
+  if (p.median || p.waves) AEW_LAUNCH(k3_median, (unsigned)(2 * p.n_win), K3B_NT, 0, (cudaStream_t)stream, p);
   return (int)cudaGetLastError();
 }
 

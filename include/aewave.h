@@ -118,6 +118,10 @@ typedef struct K3Params {
   double* median;             /* [n_win][320] float64 median beat of kept windows (may be NULL) */
   float* waves;               /* [n_win][320] float32 copy = np_waves rows (may be NULL) */
   double* zwin;               /* [n_win][L] z-scored windows = 'ecg_sample' column (may be NULL) */
+  double* zparams;            /* [n_win][2] scratch: mean, sd of each window's z-score.  With zscore_windows = 1 the
+                                 median kernel needs the z-scored samples again: it reads them from zwin if that is
+                                 given (fastest), else re-derives them from y and zparams; one of the two is required
+                                 when median / waves are requested */
   int* status;                /* device status word */
   unsigned long long* hazard_count; /* device counter of windows that took the exact fallback (may be NULL) */
 } K3Params;

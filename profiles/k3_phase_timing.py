@@ -31,15 +31,18 @@ names = ["load+nan", "zscore", "np.std", "grad prefix", "smooth+prefix", "indica
 for rep in range(3):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    scr = pre.screen_windows(y, win_start)
+    scr = pre.screen_windows(y, win_start, zwin_scratch=pre._filter_tmp)
     e1.record()
+    e2 = torch.cuda.Event(enable_timing=True)
+    pre.screen_windows(y, win_start, want_median=False)
+    e2.record()
     torch.cuda.synchronize()
     if os.environ.get('NO_TICKS'):
-        print(rep, f'{e0.elapsed_time(e1):.2f} ms')
+        print(rep, f'{e0.elapsed_time(e1):.2f} ms (screen alone {e1.elapsed_time(e2):.2f} ms)')
         continue
     lib.aew_windows_timing_dump(ctypes.c_void_p(out.ctypes.data))
     tot = float(out[:16].sum())
     nw = len(win_start)
-    print(rep, f"{e0.elapsed_time(e1):.2f} ms, {nw} windows, {tot / nw:.0f} cycles/window, kept {int(scr['keep'].sum())}, "
+    print(rep, f"{e0.elapsed_time(e1):.2f} ms (screen alone {e1.elapsed_time(e2):.2f} ms), {nw} windows, {tot / nw / 2:.0f} cycles/window, kept {int(scr['keep'].sum())}, "
           f"n_peaks>32: {int((scr['n_peaks'] > 32).sum())}")
     print("   ", {n: f"{100 * float(v) / tot:.1f}%" for n, v in zip(names, out[:16])})

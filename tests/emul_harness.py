@@ -114,7 +114,8 @@ def screen(flat, starts, Lw=10000, mode=0, zscore_windows=True, want_z=False, fs
     n, maxp = len(starts), L.aew_windows_max_peaks()
     o = dict(keep=np.zeros(n, np.uint8), has_nan=np.zeros(n, np.uint8), n_peaks=np.zeros(n, np.int32),
              peaks=np.zeros((n, maxp), np.int32), stats=np.zeros((n, 4)), median=np.full((n, 320), -5.0),
-             waves=np.zeros((n, 320), np.float32), zwin=np.zeros((n, Lw)), status=np.zeros(1, np.int32),
+             waves=np.zeros((n, 320), np.float32), zwin=np.zeros((n, Lw)), zparams=np.zeros((n, 2)),
+             status=np.zeros(1, np.int32),
              hazards=np.zeros(1, np.uint64))
     p = _cabi.K3Params(
         y=flat.ctypes.data, win_start=starts.ctypes.data, n_win=n, L=Lw, smooth_k=int(np.rint(0.1 * fs)),
@@ -122,7 +123,7 @@ def screen(flat, starts, Lw=10000, mode=0, zscore_windows=True, want_z=False, fs
         rr_div=fs * 1000.0, hr_lo=30.0, hr_hi=180.0, pvc_threshold=pvc, sd_threshold=sdt, mode=mode,
         zscore_windows=1 if zscore_windows else 0, keep=o["keep"].ctypes.data, has_nan=o["has_nan"].ctypes.data,
         n_peaks=o["n_peaks"].ctypes.data, peaks=o["peaks"].ctypes.data, stats=o["stats"].ctypes.data,
-        median=o["median"].ctypes.data, waves=o["waves"].ctypes.data, zwin=o["zwin"].ctypes.data if want_z else None,
+        median=o["median"].ctypes.data, waves=o["waves"].ctypes.data, zwin=o["zwin"].ctypes.data if want_z else None, zparams=o["zparams"].ctypes.data,
         status=o["status"].ctypes.data, hazard_count=o["hazards"].ctypes.data)
     rc = L.aew_windows_beats_f64(ctypes.byref(p), None)
     assert rc == 0, rc
