@@ -30,6 +30,7 @@
 #define __host__
 #define __forceinline__ inline
 #define __noinline__
+struct alignas(16) double2 { double x, y; };
 #define __launch_bounds__(...)
 #define __shared__ static
 #define __restrict__ __restrict

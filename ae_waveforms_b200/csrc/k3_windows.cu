@@ -39,19 +39,22 @@
 #include "aew_math.cuh"
 #include "../../include/aewave.h"
 
-#define K3_NT 512
-#define K3_ITEMS 21                       // odd -> conflict-free per-thread strips
-#define K3_MAXL (K3_NT * K3_ITEMS)        // 10752 samples per window at most
+#define K3_NT 256                         // two blocks per SM: their barrier waits and load latencies overlap
+#define K3_ITEMS 13                       // extended positions per thread and segment (odd: conflict-free strips)
+#define K3_SEGS 4                         // the QRS indicator is evaluated in segments (prefix sums fit 24 KB)
+#define K3_CAP (K3_NT * K3_ITEMS)         // 3328 extended positions per segment
+#define K3_RING 512                       // ring of smoothgrad values in the sequential evaluation (> avg_k + 1)
+#define K3_MAXL 10240                     // samples per window at most (80 KB of shared memory)
 #define K3_MAXP 72                        // peaks are > 150 samples apart -> at most 71 in 10752
 #define K3_BEAT 320
 #define K3_NONE 0xffffu
-#define K3_PREFETCH_AHEAD 148                // one wave of blocks (one block per SM)
+#define K3_PREFETCH_AHEAD 296             // one wave of blocks (two blocks per SM)
 
 namespace {
 
 struct K3Smem {
   double* A;            // [L]  z-scored window
-  double* B;            // [K3_MAXL]  prefix sums (edge-extended) / sequential smoothgrad
+  double* B;            // [K3_CAP] prefix sums of one segment; later the run tables; ring of the sequential pass
   double* pw_vals;      // [2][128] leaf sums, double-buffered
   double* wtot;         // [16]
   double* scal;         // [16] scalars
@@ -62,10 +65,9 @@ struct K3Smem {
   int* iscal;           // [16]
   int* leaf_off;        // [128] NumPy-tree leaf ranges of a length-L vector
   int* leaf_size;       // [128]
-  unsigned short* beg;  // [L/2 + 2]
+  unsigned* Qw;         // [L/32 + 2] QRS indicator, one bit per sample
+  unsigned short* beg;  // [L/2 + 2] run tables (alias B: the prefix sums are dead by then); cand overwrites beg
   unsigned short* end;
-  unsigned short* cand;
-  unsigned char* Q;     // [L]
   unsigned char* pw_valid;  // [2][128]
 };
 
@@ -74,7 +76,7 @@ __host__ __device__ inline size_t k3_smem_layout(unsigned char* base, int L, K3S
   auto take = [&](size_t bytes) { size_t at = o; o = (o + bytes + 15) & ~(size_t)15; return base ? base + at : (unsigned char*)0; };
   K3Smem t;
   t.A = (double*)take(sizeof(double) * L);
-  t.B = (double*)take(sizeof(double) * K3_MAXL);   // prefix sums over the edge-extended window
+  t.B = (double*)take(sizeof(double) * K3_CAP);
   t.pw_vals = (double*)take(sizeof(double) * 256);
   t.wtot = (double*)take(sizeof(double) * 16);
   t.scal = (double*)take(sizeof(double) * 16);
@@ -85,12 +87,11 @@ __host__ __device__ inline size_t k3_smem_layout(unsigned char* base, int L, K3S
   t.iscal = (int*)take(sizeof(int) * 16);
   t.leaf_off = (int*)take(sizeof(int) * 128);
   t.leaf_size = (int*)take(sizeof(int) * 128);
-  const int rmax = L / 2 + 2;
-  t.beg = (unsigned short*)take(sizeof(unsigned short) * rmax);
-  t.end = (unsigned short*)take(sizeof(unsigned short) * rmax);
-  t.cand = (unsigned short*)take(sizeof(unsigned short) * rmax);
-  t.Q = (unsigned char*)take(L);
+  t.Qw = (unsigned*)take(sizeof(unsigned) * (L / 32 + 2));
   t.pw_valid = (unsigned char*)take(256);
+  const int rmax = L / 2 + 2;                            // 2 * rmax * 2 B <= K3_CAP * 8 B for L <= K3_MAXL
+  t.beg = base ? (unsigned short*)t.B : (unsigned short*)0;
+  t.end = base ? (unsigned short*)t.B + ((rmax + 7) & ~7) : (unsigned short*)0;
   if (s) *s = t;
   return o;
 }
@@ -133,13 +134,11 @@ struct SumPlain { const double* a; __device__ __forceinline__ double operator()(
 // One sweep over the thread's share of its leaf.  PLAIN: sum of the window, flag = saw a NaN
 // (remove_samples.py:31-33).  DEV2: sum of (x - m)^2.  ZSCORE: x <- (x - m) / sd in place, sum of the new values,
 // flag = produced a non-finite value (constant window: 0/0).
-__device__ __forceinline__ double leaf_term(int mode, double* A, int i, double v, bool store, double m, const ExactDiv& dv,
-                                            int& flag) {
+__device__ __forceinline__ double leaf_term(int mode, double v, double m, const ExactDiv& dv, int& flag) {
   if (mode == K3_PASS_PLAIN) { flag |= isnan(v) ? 1 : 0; return v; }
   const double d = __dsub_rn(v, m);
   if (mode == K3_PASS_DEV2) return __dmul_rn(d, d);
   const double z = div_exact(d, dv);
-  if (store) A[i] = z;
   flag |= (isnan(z) || isinf(z)) ? 1 : 0;
   return z;
 }
@@ -147,20 +146,23 @@ __device__ __noinline__ LeafOut leaf_pass(int mode, double* A, double m, double 
   const ExactDiv dv = make_exact_div(sd);
   const int c8 = size >> 3;
   int flag = 0;
+  // lane j carries the stride-8 partial sums r_{2j} and r_{2j+1}: one 16-byte access per round (the leaf offsets
+  // are multiples of 8 samples), and ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) is a local addition and two xor steps
   double r0 = 0.0, r1 = 0.0;
 #pragma unroll 1
   for (int k = 0; k < c8; ++k) {
-    const int i0 = off + 8 * k + j;
-    const double a = A[i0], b = A[i0 + 4];
-    const double x0 = leaf_term(mode, A, i0, a, true, m, dv, flag), x1 = leaf_term(mode, A, i0 + 4, b, true, m, dv, flag);
-    r0 = k == 0 ? x0 : __dadd_rn(r0, x0);
-    r1 = k == 0 ? x1 : __dadd_rn(r1, x1);
+    const int i0 = off + 8 * k + 2 * j;
+    const double2 v = *reinterpret_cast<const double2*>(A + i0);
+    double2 t;
+    t.x = leaf_term(mode, v.x, m, dv, flag);
+    t.y = leaf_term(mode, v.y, m, dv, flag);
+    if (mode == K3_PASS_ZSCORE) *reinterpret_cast<double2*>(A + i0) = t;
+    r0 = k == 0 ? t.x : __dadd_rn(r0, t.x);
+    r1 = k == 0 ? t.y : __dadd_rn(r1, t.y);
   }
-  r0 = __dadd_rn(r0, __shfl_xor_sync(AEW_FULL, r0, 1));
-  r1 = __dadd_rn(r1, __shfl_xor_sync(AEW_FULL, r1, 1));
-  r0 = __dadd_rn(r0, __shfl_xor_sync(AEW_FULL, r0, 2));
-  r1 = __dadd_rn(r1, __shfl_xor_sync(AEW_FULL, r1, 2));
   double r = __dadd_rn(r0, r1);
+  r = __dadd_rn(r, __shfl_xor_sync(AEW_FULL, r, 1));
+  r = __dadd_rn(r, __shfl_xor_sync(AEW_FULL, r, 2));
   int i = c8 << 3;
   if (size < 8) { r = 0.0; i = 0; }
   // the tail is added by all four lanes alike; each element is read by all before lane 0 may overwrite it
@@ -171,23 +173,29 @@ __device__ __noinline__ LeafOut leaf_pass(int mode, double* A, double m, double 
     const bool in = i + u < size;
     const double v = in ? A[off + i + u] : 0.0;
     __syncwarp();
-    if (in) r = __dadd_rn(r, leaf_term(mode, A, off + i + u, v, j == 0, m, dv, flag));
+    if (in) {
+      const double t = leaf_term(mode, v, m, dv, flag);
+      if (mode == K3_PASS_ZSCORE && j == 0) A[off + i + u] = t;
+      r = __dadd_rn(r, t);
+    }
   }
   LeafOut o;
   o.r = r; o.flag = flag;
   return o;
 }
 
-// Combine the leaf values up the tree.  depth 7: every warp folds the 128 leaves in registers (two local levels,
-// five xor steps) -- an invalid (empty) right node leaves its sibling untouched, exactly like pw_warp_combine --
-// so one barrier per sum is enough.  Two leaf buffers alternate: a slow warp may still be folding the previous
-// sum while the next one's leaves are stored.
-__device__ __noinline__ double block_combine(double r, int slot, int j, int size, int depth, const K3Smem& sm,
-                                             int& parity) {
-  double* vals = sm.pw_vals + 128 * parity;
-  unsigned char* valid = sm.pw_valid + 128 * parity;
-  parity ^= 1;
-  if (slot < (1 << depth) && j == 0) { vals[slot] = r; valid[slot] = size > 0; }
+// Combine the leaf values up the tree.  With 256 threads a sweep takes two rounds: thread t serves leaf t >> 2
+// and leaf 64 + (t >> 2).  depth 7: every warp folds the 128 leaves in registers (two local levels, five xor
+// steps) -- an invalid (empty) right node leaves its sibling untouched, exactly like pw_warp_combine -- so one
+// barrier per sum is enough.  Two leaf buffers alternate (the caller flips `buf`): a slow warp may still be
+// folding the previous sum while the next one's leaves are stored.
+__device__ __noinline__ double block_combine(double ra, int size_a, double rb, int size_b, int slot, int j, int depth,
+                                             double* vals, unsigned char* valid) {
+  const int nslots = 1 << depth;
+  if (j == 0) {
+    if (slot < nslots) { vals[slot] = ra; valid[slot] = size_a > 0; }
+    if (slot + 64 < nslots) { vals[slot + 64] = rb; valid[slot + 64] = size_b > 0; }
+  }
   __syncthreads();
   if (depth == 7) {
     const int lane = threadIdx.x & 31;
@@ -454,7 +462,121 @@ __device__ __forceinline__ void window_median(const BeatSrc& z, const int* __res
 }
 
 // ---------------------------------------------------------------------- the window kernel
-__global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p, unsigned long long* dbg) {
+// Most prominent strict local maximum of one QRS run d[0..n) (scipy.signal.find_peaks + peak_prominences
+// semantics), by one warp.  Returns the index inside the run, or 0x7fffffff if the run has no peak.
+__device__ __noinline__ int run_peak(const double* __restrict__ d, int n, int lane) {
+  double best = -1.0;
+  int best_i = 0x7fffffff;
+  if (n <= 128) {
+    // warp-cooperative evaluation (runs of at most 128 samples): lane l holds d[32 m + l]
+    double v[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) v[m] = (32 * m + lane < n) ? d[32 * m + lane] : 0.0;
+    unsigned long long kv[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) kv[m] = dkey(v[m]);
+    unsigned peakmask[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int i = 32 * m + lane;
+      bool rise = false;
+      int pk = i;
+      if (i >= 1 && i < n - 1 && d[i - 1] < v[m]) {       // start of a plateau (usually one sample)
+        int ahead = i + 1;
+        while (ahead < n - 1 && d[ahead] == v[m]) ++ahead;
+        if (d[ahead] < v[m]) { rise = true; pk = (i + ahead - 1) / 2; }
+      }
+      // a plateau's midpoint may sit in another lane: publish the peak at its own position
+      const unsigned starts = __ballot_sync(AEW_FULL, rise);
+      unsigned mine_pk = 0;
+      for (unsigned s = starts; s; s &= s - 1) {
+        const int src = __ffs(s) - 1;
+        const int q = __shfl_sync(AEW_FULL, pk, src);
+        if (q == i) mine_pk = 1;
+        else if ((q >> 5) != m && (q & 31) == lane) mine_pk |= 2u << (q >> 5);   // lands in another chunk
+      }
+      peakmask[m] = mine_pk;
+    }
+    // fold "lands in another chunk" marks (plateaus longer than a chunk are vanishingly rare but legal)
+    unsigned pkbits[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      bool is_pk = (peakmask[m] & 1u) != 0;
+#pragma unroll
+      for (int o = 0; o < 4; ++o) is_pk |= (peakmask[o] & (2u << m)) != 0;
+      pkbits[m] = __ballot_sync(AEW_FULL, is_pk);
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      for (unsigned s = pkbits[m]; s; s &= s - 1) {
+        const int src = __ffs(s) - 1;
+        const int pk = 32 * m + src;
+        const double h = __shfl_sync(AEW_FULL, v[m], src);
+        // nearest strictly higher sample on each side (walks of scipy's _peak_prominences stop there)
+        int nl = -1, nr = n;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (32 * c < n) {                                  // (uniform) chunks beyond the run hold nothing
+            const int i = 32 * c + lane;
+            const unsigned hi = __ballot_sync(AEW_FULL, i < n && v[c] > h);
+            if (hi) {
+              const unsigned below = (32 * c + 31 < pk) ? hi : ((32 * c > pk) ? 0u : (hi & ((1u << (pk - 32 * c)) - 1u)));
+              const unsigned above = (32 * c > pk) ? hi : ((32 * c + 31 < pk) ? 0u : (hi & ~((2u << (pk - 32 * c)) - 1u)));
+              if (below) { const int q = 32 * c + 31 - __clz((int)below); nl = q > nl ? q : nl; }
+              if (above) { const int q = 32 * c + __ffs((int)above) - 1; nr = q < nr ? q : nr; }
+            }
+          }
+        }
+        // minima of (nl, pk] and [pk, nr) as order-preserving integer keys: two 32-bit warp reductions each
+        unsigned long long kl = ~0ull, kr = ~0ull;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int i = 32 * c + lane;
+          if (i > nl && i <= pk && kv[c] < kl) kl = kv[c];
+          if (i >= pk && i < nr && kv[c] < kr) kr = kv[c];
+        }
+        const double lmin = warp_min_key(kl), rmin = warp_min_key(kr);
+        const double prom = __dsub_rn(h, lmin > rmin ? lmin : rmin);
+        if (prom > best) { best = prom; best_i = pk; }       // candidates come in ascending order: first max wins
+      }
+    }
+    return best_i;                                           // every lane holds the same best
+  }
+  for (int i = 1 + lane; i < n - 1; i += 32) {               // long runs (noise): one candidate per lane, walks
+    if (d[i - 1] < d[i]) {
+      int ahead = i + 1;
+      while (ahead < n - 1 && d[ahead] == d[i]) ++ahead;
+      if (d[ahead] < d[i]) {
+        const int pk = (i + ahead - 1) / 2;                  // plateau midpoint
+        const double h = d[pk];
+        double lmin = h, rmin = h;
+        for (int j = pk; j >= 0 && d[j] <= h; --j) lmin = d[j] < lmin ? d[j] : lmin;
+        for (int j = pk; j <= n - 1 && d[j] <= h; ++j) rmin = d[j] < rmin ? d[j] : rmin;
+        const double prom = __dsub_rn(h, lmin > rmin ? lmin : rmin);
+        if (prom > best || (prom == best && pk < best_i)) { best = prom; best_i = pk; }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_xor_sync(AEW_FULL, best, o);
+    const int oi = __shfl_xor_sync(AEW_FULL, best_i, o);
+    if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+  }
+  return best_i;
+}
+
+// |gradient| of sample i of the edge-extended window: i < 0 repeats sample 0, i >= L repeats sample L - 1
+// (np.gradient is one-sided at the two ends); branch-free
+__device__ __forceinline__ double absgrad_ext(const double* __restrict__ A, int i, int L, double g0, double gL) {
+  const int im = i - 1 < 0 ? 0 : (i - 1 > L - 1 ? L - 1 : i - 1);
+  const int ip = i + 1 < 0 ? 0 : (i + 1 > L - 1 ? L - 1 : i + 1);
+  double g = fabs(__dmul_rn(__dsub_rn(A[ip], A[im]), 0.5));
+  g = i <= 0 ? g0 : g;
+  return i >= L - 1 ? gL : g;
+}
+
+__global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, unsigned long long* dbg) {
   AEW_DYN_SMEM(smem_raw);
   K3Smem sm;
   k3_smem_layout(smem_raw, p.L, &sm);
@@ -477,8 +599,8 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p, unsigned long
   const double* src = p.y + p.win_start[w];
 #ifndef AEW_EMUL
   {
-    // Blocks are dispatched in index order, one per SM: the window of block w + gridDim-of-one-wave is needed about
-    // one block lifetime from now.  Pull it into L2 so that its load phase does not wait on HBM.
+    // Blocks are dispatched in index order, two per SM: the window of the block one wave ahead is needed about one
+    // block lifetime from now.  Pull it into L2 so that its load phase does not wait on HBM.
     const long long wn = w + K3_PREFETCH_AHEAD;
     if (wn < p.n_win) {
       const long long sn = p.win_start[wn];
@@ -500,36 +622,48 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p, unsigned long
     sm.leaf_off[tid] = (int)off;
     sm.leaf_size[tid] = (int)size;
   }
+  for (int i = tid; i < L / 32 + 2; i += K3_NT) sm.Qw[i] = 0u;
 
-  __syncthreads();                                      // leaf table
-  const int slot = tid >> 2, lj = tid & 3;
-  const bool leaf_live = slot < (1 << depth);
-  const int loff = leaf_live ? sm.leaf_off[slot] : 0, lsize = leaf_live ? sm.leaf_size[slot] : 0;
-  int parity = 0;
-
-  // ---- load (coalesced), then NaN screen (remove_samples.py:31-33) + sum of the raw window in one sweep
-#pragma unroll 4
+  // ---- load (coalesced)
+#pragma unroll 8
   for (int i = tid; i < L; i += K3_NT) A[i] = src[i];
-  __syncthreads();
-  LeafOut lo = leaf_pass(K3_PASS_PLAIN, A, 0.0, 1.0, loff, lsize, lj);
-  const double sum_raw = block_combine(lo.r, slot, lj, lsize, depth, sm, parity);
-  int bad = __syncthreads_or(lo.flag);
+  __syncthreads();                                      // window, leaf table
+  // two leaves per thread: slot and slot + 64
+  const int slot = tid >> 2, lj = tid & 3;
+  const int nslots = 1 << depth;
+  const int offa = slot < nslots ? sm.leaf_off[slot] : 0, sza = slot < nslots ? sm.leaf_size[slot] : 0;
+  const int offb = slot + 64 < nslots ? sm.leaf_off[slot + 64] : 0, szb = slot + 64 < nslots ? sm.leaf_size[slot + 64] : 0;
+  int buf = 0;
+#define K3_SWEEP(MODE, M, SD, SUM, FLAG)                                                                   \
+  {                                                                                                        \
+    const LeafOut la_ = leaf_pass(MODE, A, M, SD, offa, sza, lj);                                          \
+    const LeafOut lb_ = leaf_pass(MODE, A, M, SD, offb, szb, lj);                                          \
+    SUM = block_combine(la_.r, sza, lb_.r, szb, slot, lj, depth, sm.pw_vals + 128 * buf, sm.pw_valid + 128 * buf); \
+    FLAG = la_.flag | lb_.flag;                                                                            \
+    buf ^= 1;                                                                                              \
+  }
+
+  // ---- NaN screen (remove_samples.py:31-33) + sum of the raw window in one sweep
+  double sum_raw;
+  int flag;
+  K3_SWEEP(K3_PASS_PLAIN, 0.0, 1.0, sum_raw, flag)
+  int bad = __syncthreads_or(flag);
   K3_TICK(0)   // load + NaN screen + first sum
   double sum_z = sum_raw;                               // windows that arrive z-scored: the same numbers
   if (!bad && p.zscore_windows) {
     // ---- per-window z-score (data_extract_vitaldb.py:93), NumPy summation order
     const double mean = k3_div(sum_raw, (double)L);
-    lo = leaf_pass(K3_PASS_DEV2, A, mean, 1.0, loff, lsize, lj);
-    const double sd0 = k3_sqrt(k3_div(block_combine(lo.r, slot, lj, lsize, depth, sm, parity), (double)L));
-    lo = leaf_pass(K3_PASS_ZSCORE, A, mean, sd0, loff, lsize, lj);
-    sum_z = block_combine(lo.r, slot, lj, lsize, depth, sm, parity);
-    bad = __syncthreads_or(lo.flag);
+    double ssq;
+    K3_SWEEP(K3_PASS_DEV2, mean, 1.0, ssq, flag)
+    const double sd0 = k3_sqrt(k3_div(ssq, (double)L));
+    K3_SWEEP(K3_PASS_ZSCORE, mean, sd0, sum_z, flag)
+    bad = __syncthreads_or(flag);
     if (tid == 0 && p.zparams) { p.zparams[2 * w] = mean; p.zparams[2 * w + 1] = sd0; }   // for the median kernel
   }
   K3_TICK(1)   // window z-score (+ sum of the z-scored window)
   if (p.zwin) {
     double* zw = p.zwin + w * (long long)L;
-#pragma unroll 1
+#pragma unroll 4
     for (int i = tid; i < L; i += K3_NT) zw[i] = A[i];  // NaN windows: as z-scored by the reference or raw
   }
   if (bad) {
@@ -542,110 +676,111 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p, unsigned long
   }
 
   // ---- ecg_sd = np.std(window) (remove_samples.py:62)
-  lo = leaf_pass(K3_PASS_DEV2, A, k3_div(sum_z, (double)L), 1.0, loff, lsize, lj);
-  const double sd = k3_sqrt(k3_div(block_combine(lo.r, slot, lj, lsize, depth, sm, parity), (double)L));
-
+  double ssq2;
+  K3_SWEEP(K3_PASS_DEV2, k3_div(sum_z, (double)L), 1.0, ssq2, flag)
+  const double sd = k3_sqrt(k3_div(ssq2, (double)L));
+#undef K3_SWEEP
   K3_TICK(2)   // np.std
-  // ---- QRS indicator: smoothgrad > 1.5 * avggrad
-  // Both box filters extend the signal by its edge value (scipy "nearest").  The prefix sums run over that
-  // EXTENDED sequence (pad samples in front, the filter overhang behind), so a box sum is P[hi] - P[lo - 1] for
-  // every sample and no thread branches on clamping.  Thread t owns extended positions e = 21 t .. 21 t + 20,
-  // i.e. samples i = e - pad.
+
+  // ---- QRS indicator: smoothgrad > 1.5 * avggrad, smoothgrad / avggrad = box filters (scipy "nearest" edges)
+  // of |gradient| / smoothgrad.  Evaluated with prefix sums, one SEGMENT of the window at a time: for output
+  // samples [a, b) the sums run over the extended positions e = 0 .. Le-1 that stand for samples G0 + e,
+  // G0 = a - la - ls - 1, clamped into the window (edge value repeated), so that a box sum is P[hi] - P[lo]
+  // everywhere and nothing branches on clamping.  Thread t owns e = 13 t .. 13 t + 12 in all three passes.
   const int ks = p.smooth_k, ka = p.avg_k;
   const int ls = ks / 2, la = ka / 2;                  // uniform_filter1d: window [i - k/2, i - k/2 + k)
-  const int pad = (ls > la ? ls : la) + 1;
-  const int tail = (ks - 1 - ls > ka - 1 - la) ? ks - 1 - ls : ka - 1 - la;
-  const int Le = L + pad + tail;                       // <= K3_MAXL (checked at launch)
   int hazard = 0;
-  unsigned qbits = 0;                                  // bit k: QRS indicator of sample i0 + k
-  const int e0 = tid * K3_ITEMS;
-  const int i0 = e0 - pad;
-  int klo = -i0, khi = L - i0;                         // bits [klo, khi) are samples of the window
-  klo = klo < 0 ? 0 : (klo > K3_ITEMS ? K3_ITEMS : klo);
-  khi = khi < 0 ? 0 : (khi > K3_ITEMS ? K3_ITEMS : khi);
-  const unsigned smask = khi > klo ? (((1u << (khi - klo)) - 1u) << klo) : 0u;
   if (p.mode != 1) {
-    double loc[K3_ITEMS], smv[K3_ITEMS];
-    double run = 0.0;
-    // the path is chosen per WARP: a warp that straddles an edge runs the general form once instead of both
-    if (__all_sync(AEW_FULL, i0 >= 1 && i0 + K3_ITEMS < L)) {   // strips away from both window edges
-      const double* zp = A + i0;
-      double prv = zp[-1], cur = zp[0];
-#pragma unroll
-      for (int k = 0; k < K3_ITEMS; ++k) {
-        const double nxt = zp[k + 1];
-        run += fabs(__dmul_rn(__dsub_rn(nxt, prv), 0.5));
-        loc[k] = run;
-        prv = cur; cur = nxt;
-      }
-    } else {
-      // branch-free general form: one-sided differences at (and, by edge extension, beyond) the two ends
-      const double g0 = fabs(__dsub_rn(A[1], A[0])), gL = fabs(__dsub_rn(A[L - 1], A[L - 2]));
-#pragma unroll
-      for (int k = 0; k < K3_ITEMS; ++k) {
-        const int i = i0 + k;
-        const int im = i - 1 < 0 ? 0 : (i - 1 > L - 1 ? L - 1 : i - 1);
-        const int ip = i + 1 < 0 ? 0 : (i + 1 > L - 1 ? L - 1 : i + 1);
-        double g = fabs(__dmul_rn(__dsub_rn(A[ip], A[im]), 0.5));
-        g = i <= 0 ? g0 : g;
-        g = i >= L - 1 ? gL : g;
-        run += (e0 + k < Le) ? g : 0.0;
-        loc[k] = run;
-      }
-    }
-    double base = block_excl_scan(run, sm.wtot);
-#pragma unroll
-    for (int k = 0; k < K3_ITEMS; ++k) B[e0 + k] = base + loc[k];
-    __syncthreads();
-    K3_TICK(3)   // |gradient| prefix
-    const double ptot = B[Le - 1];
+    const double g0 = fabs(__dsub_rn(A[1], A[0])), gL = fabs(__dsub_rn(A[L - 1], A[L - 2]));
     const double inv_s = 1.0 / (double)ks, inv_a = 1.0 / (double)ka;
-    run = 0.0;
-    if (__all_sync(AEW_FULL, i0 >= 0 && i0 + K3_ITEMS <= L)) {   // every position of the strips is its own sample
-      const double* pl = B + e0 - ls - 1;              // (e - pad) - ls - 1 + pad
-      const double* ph = B + e0 - ls + ks - 1;
+    const int Ls = (L + K3_SEGS - 1) / K3_SEGS;
+    const int e0 = tid * K3_ITEMS;
+#pragma unroll 1
+    for (int a = 0; a < L; a += Ls) {
+      const int b = a + Ls < L ? a + Ls : L;
+      const int G0 = a - la - ls - 1;
+      const int Le = b - a + ka + ks - 1;               // <= K3_CAP (checked at launch)
+      const int i0 = G0 + e0;
+      double loc[K3_ITEMS], smv[K3_ITEMS];
+      double run = 0.0;
+      // the path is chosen per WARP: a warp that straddles an edge runs the general form once instead of both
+      if (__all_sync(AEW_FULL, i0 >= 1 && i0 + K3_ITEMS < L && e0 + K3_ITEMS <= Le)) {
+        const double* zp = A + i0;
+        double prv = zp[-1], cur = zp[0];
 #pragma unroll
-      for (int k = 0; k < K3_ITEMS; ++k) {
-        const double s = (ph[k] - pl[k]) * inv_s;
-        smv[k] = s;
-        run += s;
-        loc[k] = run;
+        for (int k = 0; k < K3_ITEMS; ++k) {
+          const double nxt = zp[k + 1];
+          run += fabs(__dmul_rn(__dsub_rn(nxt, prv), 0.5));
+          loc[k] = run;
+          prv = cur; cur = nxt;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < K3_ITEMS; ++k) {
+          const double g = absgrad_ext(A, i0 + k, L, g0, gL);
+          run += (e0 + k < Le) ? g : 0.0;
+          loc[k] = run;
+        }
       }
-    } else {
+      double base = block_excl_scan(run, sm.wtot);      // (its barriers also end the previous segment's reads of B)
 #pragma unroll
-      for (int k = 0; k < K3_ITEMS; ++k) {
-        int i = i0 + k;
-        i = i < 0 ? 0 : (i > L - 1 ? L - 1 : i);       // edge value repeated
-        const int lo = i + pad - ls - 1;
-        const double s = (e0 + k < Le) ? (B[lo + ks] - B[lo]) * inv_s : 0.0;
-        smv[k] = s;
-        run += s;
-        loc[k] = run;
+      for (int k = 0; k < K3_ITEMS; ++k) B[e0 + k] = base + loc[k];
+      __syncthreads();
+      const double ptot = B[Le - 1];
+      // smoothgrad at position e = box sum over positions [e' + 1, e' + ks], e' = clamp(sample) - ls - 1 - G0;
+      // positions whose box leaves the segment are not needed by any output of the segment: 0
+      run = 0.0;
+      if (__all_sync(AEW_FULL, i0 >= 0 && i0 + K3_ITEMS <= L && e0 - ls - 1 >= 0 && e0 + K3_ITEMS - ls - 1 + ks <= Le)) {
+        const double* pl = B + e0 - ls - 1;
+        const double* ph = pl + ks;
+#pragma unroll
+        for (int k = 0; k < K3_ITEMS; ++k) {
+          const double sv = (ph[k] - pl[k]) * inv_s;
+          smv[k] = sv;
+          run += sv;
+          loc[k] = run;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < K3_ITEMS; ++k) {
+          int i = i0 + k;
+          i = i < 0 ? 0 : (i > L - 1 ? L - 1 : i);       // edge value repeated
+          const int lo = i - ls - 1 - G0;
+          const bool ok = e0 + k < Le && lo >= 0 && lo + ks < Le;
+          const int lc = ok ? lo : 0;
+          const double sv = ok ? (B[lc + ks] - B[lc]) * inv_s : 0.0;
+          smv[k] = sv;
+          run += sv;
+          loc[k] = run;
+        }
       }
-    }
-    base = block_excl_scan(run, sm.wtot);               // (its barriers also end all reads of B)
+      base = block_excl_scan(run, sm.wtot);             // (its barriers also end all reads of B)
 #pragma unroll
-    for (int k = 0; k < K3_ITEMS; ++k) B[e0 + k] = base + loc[k];
-    __syncthreads();
-    K3_TICK(4)   // smoothgrad + its prefix
-    const double tol_abs = 2e-12 * ptot * inv_s;
-    if (__all_sync(AEW_FULL, smask == (1u << K3_ITEMS) - 1u)) {
-      const double* pl = B + e0 - la - 1;
-      const double* ph = B + e0 - la + ka - 1;
+      for (int k = 0; k < K3_ITEMS; ++k) B[e0 + k] = base + loc[k];
+      __syncthreads();
+      // outputs: samples a <= i < b, i.e. positions e = i - G0; avggrad box = P2[e - la - 1 + ka] - P2[e - la - 1]
+      const double tol_abs = 2e-12 * ptot * inv_s;
+      int klo = a - i0, khi = b - i0;
+      klo = klo < 0 ? 0 : (klo > K3_ITEMS ? K3_ITEMS : klo);
+      khi = khi < klo ? klo : (khi > K3_ITEMS ? K3_ITEMS : khi);
+      unsigned qbits = 0;
+      if (khi > klo) {
+        const int pl = e0 - la - 1;
 #pragma unroll
-      for (int k = 0; k < K3_ITEMS; ++k) {
-        const double thr = 1.5 * ((ph[k] - pl[k]) * inv_a);
-        qbits |= (unsigned)(smv[k] > thr) << k;
-        hazard |= (fabs(smv[k] - thr) <= 1e-9 * (smv[k] + thr) + tol_abs) ? 1 : 0;
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < K3_ITEMS; ++k) {
-        if ((smask >> k) & 1u) {
-          const int lo = e0 + k - la - 1;
-          const double thr = 1.5 * ((B[lo + ka] - B[lo]) * inv_a);
-          qbits |= (unsigned)(smv[k] > thr) << k;
-          hazard |= (fabs(smv[k] - thr) <= 1e-9 * (smv[k] + thr) + tol_abs) ? 1 : 0;
+        for (int k = 0; k < K3_ITEMS; ++k) {
+          if (k >= klo && k < khi) {
+            const double thr = 1.5 * ((B[pl + k + ka] - B[pl + k]) * inv_a);
+            qbits |= (unsigned)(smv[k] > thr) << k;
+            hazard |= (fabs(smv[k] - thr) <= 1e-9 * (smv[k] + thr) + tol_abs) ? 1 : 0;
+          }
+        }
+        // the strip's bits (13 at most) land in one or two words of the bit array
+        const int s0 = i0 + klo;                          // first sample of the strip that is an output
+        const unsigned bits = qbits >> klo;
+        if (bits) {
+          const int wq = s0 >> 5, sh = s0 & 31;
+          atomicOr((int*)sm.Qw + wq, (int)(bits << sh));
+          if (sh > 32 - K3_ITEMS && (bits >> (32 - sh))) atomicOr((int*)sm.Qw + wq + 1, (int)(bits >> (32 - sh)));
         }
       }
     }
@@ -656,64 +791,82 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p, unsigned long
     if (hazard && tid == 0 && p.hazard_count) atomicAdd(p.hazard_count, 1ull);
   }
   if (p.mode == 1 || hazard) {
-    // SciPy's literal evaluation: one undivided running sum per box filter (appendix B.3)
+    // SciPy's literal evaluation: one undivided running sum per box filter (appendix B.3), by thread 0.  The
+    // second filter reads smoothgrad ka/2 ahead of and behind its position: a ring of the last K3_RING values.
     if (tid == 0) {
       const double dks = (double)ks, dka = (double)ka;
+      double* ring = B;
       double t = 0.0;
       for (int e = 0; e < ks; ++e) {
         int j = e - ls; j = j < 0 ? 0 : (j > L - 1 ? L - 1 : j);
         t = __dadd_rn(t, absgrad(A, j, L));
       }
-      B[0] = __ddiv_rn(t, dks);
-      for (int i = 1; i < L; ++i) {
-        int jin = i + ks - 1 - ls, jout = i - 1 - ls;
-        jin = jin > L - 1 ? L - 1 : jin;
-        jout = jout < 0 ? 0 : jout;
-        t = __dadd_rn(t, __dsub_rn(absgrad(A, jin, L), absgrad(A, jout, L)));
-        B[i] = __ddiv_rn(t, dks);
-      }
+      int js = 0;                                        // smoothgrad is known up to sample js
+      ring[0] = __ddiv_rn(t, dks);
+      auto smooth_at = [&](int j) -> double {            // advances the first filter as far as needed
+        while (js < j) {
+          ++js;
+          int jin = js + ks - 1 - ls, jout = js - 1 - ls;
+          jin = jin > L - 1 ? L - 1 : jin;
+          jout = jout < 0 ? 0 : jout;
+          t = __dadd_rn(t, __dsub_rn(absgrad(A, jin, L), absgrad(A, jout, L)));
+          ring[js & (K3_RING - 1)] = __ddiv_rn(t, dks);
+        }
+        return ring[j & (K3_RING - 1)];
+      };
       double t2 = 0.0;
       for (int e = 0; e < ka; ++e) {
         int j = e - la; j = j < 0 ? 0 : (j > L - 1 ? L - 1 : j);
-        t2 = __dadd_rn(t2, B[j]);
+        t2 = __dadd_rn(t2, smooth_at(j));
       }
-      sm.Q[0] = B[0] > __dmul_rn(1.5, __ddiv_rn(t2, dka));
+      unsigned acc = smooth_at(0) > __dmul_rn(1.5, __ddiv_rn(t2, dka)) ? 1u : 0u;
       for (int i = 1; i < L; ++i) {
         int jin = i + ka - 1 - la, jout = i - 1 - la;
         jin = jin > L - 1 ? L - 1 : jin;
         jout = jout < 0 ? 0 : jout;
-        t2 = __dadd_rn(t2, __dsub_rn(B[jin], B[jout]));
-        sm.Q[i] = B[i] > __dmul_rn(1.5, __ddiv_rn(t2, dka));
+        const double sin_ = smooth_at(jin);              // (advance first: jout and i are then inside the ring)
+        t2 = __dadd_rn(t2, __dsub_rn(sin_, smooth_at(jout)));
+        const unsigned q = smooth_at(i) > __dmul_rn(1.5, __ddiv_rn(t2, dka)) ? 1u : 0u;
+        if ((i & 31) == 0) { sm.Qw[(i >> 5) - 1] = acc; acc = 0u; }
+        acc |= q << (i & 31);
       }
+      sm.Qw[(L - 1) >> 5] = acc;
     }
     __syncthreads();
-    qbits = 0;
-#pragma unroll
-    for (int k = 0; k < K3_ITEMS; ++k) if ((smask >> k) & 1u) qbits |= (unsigned)(sm.Q[i0 + k] != 0) << k;
   }
-
   K3_TICK(6)   // sequential fallback (hazard windows / mode 1)
-  // ---- QRS runs: beg where ~q[i] & q[i+1], end where q[i] & ~q[i+1]  (ordered compaction);
-  //      the flags live in registers, only each strip's first flag is exchanged
+
+  // ---- QRS runs: beg where ~q[i] & q[i+1], end where q[i] & ~q[i+1]  (ordered compaction, one word of the
+  //      bit array per thread and round); the run tables take over the prefix-sum buffer
+  int nbeg, nend;
   {
-    __syncthreads();                                   // everyone is done with sm.Q of a sequential pass
-    sm.Q[tid] = (unsigned char)(qbits & 1u);
-    __syncthreads();
-    const unsigned nbr = (tid + 1 < K3_NT) ? sm.Q[tid + 1] : 0u;
-    const unsigned nextq = (qbits >> 1) | (nbr << (K3_ITEMS - 1));          // flag of sample i + 1
-    int kend = L - 1 - i0;                              // transitions exist for 0 <= i < L - 1
-    kend = kend < klo ? klo : (kend > K3_ITEMS ? K3_ITEMS : kend);
-    const unsigned vmask = ((1u << (kend - klo)) - 1u) << klo;
-    unsigned bbits = ~qbits & nextq & vmask, ebits = qbits & ~nextq & vmask;
-    const int packed = block_excl_scan_int(__popc(bbits) | (__popc(ebits) << 16), (int*)sm.wtot);
-    int ob = packed & 0xffff, oe = packed >> 16;
-    while (bbits) { const int k = __ffs(bbits) - 1; bbits &= bbits - 1; sm.beg[ob++] = (unsigned short)(i0 + k); }
-    while (ebits) { const int k = __ffs(ebits) - 1; ebits &= ebits - 1; sm.end[oe++] = (unsigned short)(i0 + k); }
-    if (tid == K3_NT - 1) { sm.iscal[0] = ob; sm.iscal[1] = oe; }
-    __syncthreads();
+    const int nwords = (L + 31) >> 5;
+    int tot_b = 0, tot_e = 0;
+#pragma unroll 1
+    for (int w0 = 0; w0 < nwords; w0 += K3_NT) {
+      const int wi = w0 + tid;
+      unsigned qb = 0, nx = 0;
+      if (wi < nwords) { qb = sm.Qw[wi]; nx = sm.Qw[wi + 1] & 1u; }
+      const unsigned nextq = (qb >> 1) | (nx << 31);      // flag of sample i + 1
+      int nval = L - 1 - 32 * wi;                         // transitions exist for 0 <= i < L - 1
+      nval = nval < 0 ? 0 : (nval > 32 ? 32 : nval);
+      const unsigned vmask = nval >= 32 ? 0xffffffffu : ((1u << nval) - 1u);
+      unsigned bbits = ~qb & nextq & vmask, ebits = qb & ~nextq & vmask;
+      const int mine = __popc(bbits) | (__popc(ebits) << 16);
+      const int packed = block_excl_scan_int(mine, (int*)sm.wtot);
+      int ob = tot_b + (packed & 0xffff), oe = tot_e + (packed >> 16);
+      if (tid == K3_NT - 1) sm.iscal[4] = packed + mine;  // round totals
+      while (bbits) { const int k = __ffs(bbits) - 1; bbits &= bbits - 1; sm.beg[ob++] = (unsigned short)(32 * wi + k); }
+      while (ebits) { const int k = __ffs(ebits) - 1; ebits &= ebits - 1; sm.end[oe++] = (unsigned short)(32 * wi + k); }
+      __syncthreads();
+      const int tot = sm.iscal[4];
+      tot_b += tot & 0xffff;
+      tot_e += tot >> 16;
+    }
+    nbeg = tot_b;
+    nend = tot_e;
   }
   K3_TICK(7)   // run compaction
-  const int nbeg = sm.iscal[0], nend = sm.iscal[1];
   // ends that precede the first beg are dropped (at most one, runs alternate)
   const int skip = (nbeg > 0 && nend > 0 && sm.end[0] <= sm.beg[0]) ? 1 : 0;
   int num = nend - skip < nbeg ? nend - skip : nbeg;
@@ -728,117 +881,21 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p, unsigned long
     const unsigned tot = __reduce_add_sync(AEW_FULL, part);
     if (num > 0) min_len = __dmul_rn(k3_div((double)tot, (double)num), 0.4);
   }
+  __syncthreads();                                      // beg[] is overwritten by the candidates below
   K3_TICK(8)   // min_len
 
-  // ---- per run: most prominent strict local maximum (scipy.signal.find_peaks semantics)
+  // ---- per run: most prominent strict local maximum (scipy.signal.find_peaks semantics); cand[r] replaces beg[r]
   for (int r = warp; r < num; r += K3_NT / 32) {
     const int b = sm.beg[r], e = endp[r];
     const int n = e - b;
-    const double* d = A + b;
-    double best = -1.0;
     int best_i = 0x7fffffff;
-    if (!((double)n < min_len) && n <= 128) {
-      // warp-cooperative evaluation (runs of at most 128 samples): lane l holds d[32 m + l]
-      double v[4];
-#pragma unroll
-      for (int m = 0; m < 4; ++m) v[m] = (32 * m + lane < n) ? d[32 * m + lane] : 0.0;
-      unsigned long long kv[4];
-#pragma unroll
-      for (int m = 0; m < 4; ++m) kv[m] = dkey(v[m]);
-      unsigned peakmask[4];
-#pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        const int i = 32 * m + lane;
-        bool rise = false;
-        int pk = i;
-        if (i >= 1 && i < n - 1 && d[i - 1] < v[m]) {       // start of a plateau (usually one sample)
-          int ahead = i + 1;
-          while (ahead < n - 1 && d[ahead] == v[m]) ++ahead;
-          if (d[ahead] < v[m]) { rise = true; pk = (i + ahead - 1) / 2; }
-        }
-        // a plateau's midpoint may sit in another lane: publish the peak at its own position
-        const unsigned starts = __ballot_sync(AEW_FULL, rise);
-        unsigned mine_pk = 0;
-        for (unsigned s = starts; s; s &= s - 1) {
-          const int src = __ffs(s) - 1;
-          const int q = __shfl_sync(AEW_FULL, pk, src);
-          if (q == i) mine_pk = 1;
-          else if ((q >> 5) != m && (q & 31) == lane) mine_pk |= 2u << (q >> 5);   // lands in another chunk
-        }
-        peakmask[m] = mine_pk;
-      }
-      // fold "lands in another chunk" marks (plateaus longer than a chunk are vanishingly rare but legal)
-      unsigned pkbits[4];
-#pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        bool is_pk = (peakmask[m] & 1u) != 0;
-#pragma unroll
-        for (int o = 0; o < 4; ++o) is_pk |= (peakmask[o] & (2u << m)) != 0;
-        pkbits[m] = __ballot_sync(AEW_FULL, is_pk);
-      }
-#pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        for (unsigned s = pkbits[m]; s; s &= s - 1) {
-          const int src = __ffs(s) - 1;
-          const int pk = 32 * m + src;
-          const double h = __shfl_sync(AEW_FULL, v[m], src);
-          // nearest strictly higher sample on each side (walks of scipy's _peak_prominences stop there)
-          int nl = -1, nr = n;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if (32 * c < n) {                                  // (uniform) chunks beyond the run hold nothing
-              const int i = 32 * c + lane;
-              const unsigned hi = __ballot_sync(AEW_FULL, i < n && v[c] > h);
-              if (hi) {
-                const unsigned below = (32 * c + 31 < pk) ? hi : ((32 * c > pk) ? 0u : (hi & ((1u << (pk - 32 * c)) - 1u)));
-                const unsigned above = (32 * c > pk) ? hi : ((32 * c + 31 < pk) ? 0u : (hi & ~((2u << (pk - 32 * c)) - 1u)));
-                if (below) { const int q = 32 * c + 31 - __clz((int)below); nl = q > nl ? q : nl; }
-                if (above) { const int q = 32 * c + __ffs((int)above) - 1; nr = q < nr ? q : nr; }
-              }
-            }
-          }
-          // minima of (nl, pk] and [pk, nr) as order-preserving integer keys: two 32-bit warp reductions each
-          unsigned long long kl = ~0ull, kr = ~0ull;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int i = 32 * c + lane;
-            if (i > nl && i <= pk && kv[c] < kl) kl = kv[c];
-            if (i >= pk && i < nr && kv[c] < kr) kr = kv[c];
-          }
-          const double lmin = warp_min_key(kl), rmin = warp_min_key(kr);
-          const double prom = __dsub_rn(h, lmin > rmin ? lmin : rmin);
-          if (prom > best) { best = prom; best_i = pk; }       // candidates come in ascending order: first max wins
-        }
-      }
-      if (lane == 0) sm.cand[r] = best_i == 0x7fffffff ? (unsigned short)K3_NONE : (unsigned short)(b + best_i);
-      continue;                                                // every lane holds the same best: nothing to reduce
-    } else if (!((double)n < min_len)) {
-      for (int i = 1 + lane; i < n - 1; i += 32) {
-        if (d[i - 1] < d[i]) {
-          int ahead = i + 1;
-          while (ahead < n - 1 && d[ahead] == d[i]) ++ahead;
-          if (d[ahead] < d[i]) {
-            const int pk = (i + ahead - 1) / 2;        // plateau midpoint
-            const double h = d[pk];
-            double lmin = h, rmin = h;
-            for (int j = pk; j >= 0 && d[j] <= h; --j) lmin = d[j] < lmin ? d[j] : lmin;
-            for (int j = pk; j <= n - 1 && d[j] <= h; ++j) rmin = d[j] < rmin ? d[j] : rmin;
-            const double prom = __dsub_rn(h, lmin > rmin ? lmin : rmin);
-            if (prom > best || (prom == best && pk < best_i)) { best = prom; best_i = pk; }
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ob = __shfl_xor_sync(AEW_FULL, best, o);
-      const int oi = __shfl_xor_sync(AEW_FULL, best_i, o);
-      if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
-    }
-    if (lane == 0) sm.cand[r] = best_i == 0x7fffffff ? (unsigned short)K3_NONE : (unsigned short)(b + best_i);
+    if (!((double)n < min_len)) best_i = run_peak(A + b, n, lane);
+    __syncwarp();
+    if (lane == 0) sm.beg[r] = best_i == 0x7fffffff ? (unsigned short)K3_NONE : (unsigned short)(b + best_i);
   }
   __syncthreads();
   K3_TICK(9)   // most prominent peak per run
+  const unsigned short* cand = sm.beg;
 
   // ---- everything between the candidates and the keep decision is a few hundred operations on <= 72 numbers:
   //      warp 0 does it alone, ordered by warp barriers, while the other warps wait at ONE block barrier
@@ -846,7 +903,7 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p, unsigned long
     // refractory chain (sequential by definition); all lanes walk it alike so that all of them know np
     int np = 0, last = 0;
     for (int r = 0; r < num; ++r) {
-      const int c = sm.cand[r];
+      const int c = cand[r];
       if (c != (int)K3_NONE && c - last > p.refractory) {
         if (np < K3_MAXP && lane == 0) sm.ipeaks[np] = c;
         ++np;
@@ -893,7 +950,6 @@ __global__ void __launch_bounds__(K3_NT, 1) k3_windows(K3Params p, unsigned long
       const bool remove = (hr < p.hr_lo) || (hr > p.hr_hi) || isnan(hr) || (rms > p.pvc_threshold) ||
                           (sdn > p.sd_threshold);
       sm.iscal[2] = np;
-      sm.iscal[3] = remove ? 0 : 1;
       p.keep[w] = remove ? 0 : 1;
       p.has_nan[w] = 0;
       p.n_peaks[w] = np;
@@ -1008,19 +1064,19 @@ extern "C" int aew_windows_beats_f64(const K3Params* hp, void* stream) {
   if (p.L < 16 || p.L > K3_MAXL || p.n_win < 0 || p.n_win > 0x7fffffffll) return AEW_ERR_UNSUPPORTED;
   if (p.smooth_k < 1 || p.avg_k < 1) return AEW_ERR_UNSUPPORTED;
   {
-    // the box filters' prefix sums run over the window extended by its edge values (see the kernel)
-    const int ls = p.smooth_k / 2, la = p.avg_k / 2;
-    const int pad = (ls > la ? ls : la) + 1;
-    const int tail = (p.smooth_k - 1 - ls > p.avg_k - 1 - la) ? p.smooth_k - 1 - ls : p.avg_k - 1 - la;
-    if ((long long)p.L + pad + tail > K3_MAXL) return AEW_ERR_UNSUPPORTED;
+    // one segment of the QRS evaluation (see the kernel) must fit the prefix-sum buffer, the sequential
+    // evaluation's ring must span the second box filter
+    const int seg = (p.L + K3_SEGS - 1) / K3_SEGS;
+    if ((long long)seg + p.avg_k + p.smooth_k - 1 > K3_CAP || p.avg_k + 2 > K3_RING || p.L < 2 * K3_SEGS)
+      return AEW_ERR_UNSUPPORTED;
   }
   if (pw_depth(p.L) > 7 || p.pre + p.post != K3_BEAT || p.smooth_k < 1 || p.avg_k < 1 || p.smooth_k > p.L ||
       p.avg_k > p.L || p.refractory < 1 || (p.L / (p.refractory + 1) + 1) > K3_MAXP || p.n_win > 0x3fffffffll)
     return AEW_ERR_UNSUPPORTED;
   const size_t smem = k3_smem_layout(nullptr, p.L, nullptr);
-  if (smem > 227 * 1024) return AEW_ERR_UNSUPPORTED;
+  if (smem > 113 * 1024) return AEW_ERR_UNSUPPORTED;    // two blocks per SM
   static bool attr_done = false;
-  if (!attr_done) { AEW_SET_MAX_SMEM(k3_windows, 227 * 1024); attr_done = true; }
+  if (!attr_done) { AEW_SET_MAX_SMEM(k3_windows, 113 * 1024); attr_done = true; }
   if ((p.median || p.waves) && p.zscore_windows && !p.zparams && !p.zwin) return AEW_ERR_ARG;
   AEW_LAUNCH(k3_windows, (unsigned)p.n_win, K3_NT, smem, (cudaStream_t)stream, p, k3_timing_buffer());
   if (p.median || p.waves) AEW_LAUNCH(k3_median, (unsigned)(2 * p.n_win), K3B_NT, 0, (cudaStream_t)stream, p);
