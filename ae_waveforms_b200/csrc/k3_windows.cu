@@ -147,18 +147,46 @@ __device__ __noinline__ LeafOut leaf_pass(int mode, double* A, double m, double 
   const int c8 = size >> 3;
   int flag = 0;
   // lane j carries the stride-8 partial sums r_{2j} and r_{2j+1}: one 16-byte access per round (the leaf offsets
-  // are multiples of 8 samples), and ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) is a local addition and two xor steps
+  // are multiples of 8 samples), and ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) is a local addition and two xor steps.
+  // One loop per mode: the mode test inside the loop cost more instructions than the arithmetic.
   double r0 = 0.0, r1 = 0.0;
-#pragma unroll 1
-  for (int k = 0; k < c8; ++k) {
-    const int i0 = off + 8 * k + 2 * j;
-    const double2 v = *reinterpret_cast<const double2*>(A + i0);
+  double* Aj = A + off + 2 * j;
+  if (c8 > 0) {
+    const double2 v = *reinterpret_cast<const double2*>(Aj);
     double2 t;
     t.x = leaf_term(mode, v.x, m, dv, flag);
     t.y = leaf_term(mode, v.y, m, dv, flag);
-    if (mode == K3_PASS_ZSCORE) *reinterpret_cast<double2*>(A + i0) = t;
-    r0 = k == 0 ? t.x : __dadd_rn(r0, t.x);
-    r1 = k == 0 ? t.y : __dadd_rn(r1, t.y);
+    if (mode == K3_PASS_ZSCORE) *reinterpret_cast<double2*>(Aj) = t;
+    r0 = t.x; r1 = t.y;
+  }
+  if (mode == K3_PASS_PLAIN) {
+#pragma unroll 2
+    for (int k = 1; k < c8; ++k) {
+      const double2 v = *reinterpret_cast<const double2*>(Aj + 8 * k);
+      flag |= (isnan(v.x) || isnan(v.y)) ? 1 : 0;
+      r0 = __dadd_rn(r0, v.x);
+      r1 = __dadd_rn(r1, v.y);
+    }
+  } else if (mode == K3_PASS_DEV2) {
+#pragma unroll 2
+    for (int k = 1; k < c8; ++k) {
+      const double2 v = *reinterpret_cast<const double2*>(Aj + 8 * k);
+      const double dx = __dsub_rn(v.x, m), dy = __dsub_rn(v.y, m);
+      r0 = __dadd_rn(r0, __dmul_rn(dx, dx));
+      r1 = __dadd_rn(r1, __dmul_rn(dy, dy));
+    }
+  } else {
+#pragma unroll 1
+    for (int k = 1; k < c8; ++k) {
+      const double2 v = *reinterpret_cast<const double2*>(Aj + 8 * k);
+      double2 t;
+      t.x = div_exact(__dsub_rn(v.x, m), dv);
+      t.y = div_exact(__dsub_rn(v.y, m), dv);
+      flag |= (isnan(t.x) || isinf(t.x) || isnan(t.y) || isinf(t.y)) ? 1 : 0;
+      *reinterpret_cast<double2*>(Aj + 8 * k) = t;
+      r0 = __dadd_rn(r0, t.x);
+      r1 = __dadd_rn(r1, t.y);
+    }
   }
   double r = __dadd_rn(r0, r1);
   r = __dadd_rn(r, __shfl_xor_sync(AEW_FULL, r, 1));
@@ -223,7 +251,9 @@ __device__ __noinline__ double block_combine(double ra, int size_a, double rb, i
 __device__ __noinline__ double k3_div(double a, double b) { return __ddiv_rn(a, b); }
 __device__ __noinline__ double k3_sqrt(double a) { return __dsqrt_rn(a); }
 
-// exclusive block scan of one double per thread (fast path; not order-sensitive)
+// exclusive block scan of one double per thread (fast path; not order-sensitive).  ONE barrier: consecutive scans
+// alternate between two scratch rows (the caller flips `row`), so the warp totals of one scan cannot be
+// overwritten before every warp has read them.
 __device__ __noinline__ double block_excl_scan(double v, double* wtot) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double incl = v;
@@ -236,7 +266,6 @@ __device__ __noinline__ double block_excl_scan(double v, double* wtot) {
   __syncthreads();
   double base = 0.0;
   for (int w = 0; w < warp; ++w) base += wtot[w];
-  __syncthreads();
   return base + (incl - v);
 }
 __device__ __noinline__ int block_excl_scan_int(int v, int* wtot) {
@@ -251,7 +280,6 @@ __device__ __noinline__ int block_excl_scan_int(int v, int* wtot) {
   __syncthreads();
   int base = 0;
   for (int w = 0; w < warp; ++w) base += wtot[w];
-  __syncthreads();
   return base + (incl - v);
 }
 
@@ -722,7 +750,7 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, unsigned long
           loc[k] = run;
         }
       }
-      double base = block_excl_scan(run, sm.wtot);      // (its barriers also end the previous segment's reads of B)
+      double base = block_excl_scan(run, sm.wtot);      // (its barrier also ends the previous segment's reads of B)
 #pragma unroll
       for (int k = 0; k < K3_ITEMS; ++k) B[e0 + k] = base + loc[k];
       __syncthreads();
@@ -754,7 +782,7 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, unsigned long
           loc[k] = run;
         }
       }
-      base = block_excl_scan(run, sm.wtot);             // (its barriers also end all reads of B)
+      base = block_excl_scan(run, sm.wtot + 8);         // (its barrier also ends all reads of B)
 #pragma unroll
       for (int k = 0; k < K3_ITEMS; ++k) B[e0 + k] = base + loc[k];
       __syncthreads();
