@@ -503,43 +503,58 @@ __device__ __noinline__ int run_peak(const double* __restrict__ d, int n, int la
     unsigned long long kv[4];
 #pragma unroll
     for (int m = 0; m < 4; ++m) kv[m] = dkey(v[m]);
-    unsigned peakmask[4];
+    // strict local maxima; a plateau (two equal neighbours after a rise) takes the general detector below
+    unsigned pkbits[4];
+    int plateau = 0;
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
       const int i = 32 * m + lane;
-      bool rise = false;
-      int pk = i;
-      if (i >= 1 && i < n - 1 && d[i - 1] < v[m]) {       // start of a plateau (usually one sample)
-        int ahead = i + 1;
-        while (ahead < n - 1 && d[ahead] == v[m]) ++ahead;
-        if (d[ahead] < v[m]) { rise = true; pk = (i + ahead - 1) / 2; }
-      }
-      // a plateau's midpoint may sit in another lane: publish the peak at its own position
-      const unsigned starts = __ballot_sync(AEW_FULL, rise);
-      unsigned mine_pk = 0;
-      for (unsigned s = starts; s; s &= s - 1) {
-        const int src = __ffs(s) - 1;
-        const int q = __shfl_sync(AEW_FULL, pk, src);
-        if (q == i) mine_pk = 1;
-        else if ((q >> 5) != m && (q & 31) == lane) mine_pk |= 2u << (q >> 5);   // lands in another chunk
-      }
-      peakmask[m] = mine_pk;
+      const bool inner = i >= 1 && i < n - 1;
+      const double lft = inner ? d[i - 1] : 0.0, rgt = inner ? d[i + 1] : 0.0;
+      pkbits[m] = __ballot_sync(AEW_FULL, inner && lft < v[m] && rgt < v[m]);
+      plateau |= (inner && lft < v[m] && rgt == v[m]) ? 1 : 0;
     }
-    // fold "lands in another chunk" marks (plateaus longer than a chunk are vanishingly rare but legal)
-    unsigned pkbits[4];
+    if (__any_sync(AEW_FULL, plateau)) {
+      unsigned peakmask[4];
+#pragma unroll 1
+      for (int m = 0; m < 4; ++m) {
+        const int i = 32 * m + lane;
+        const double vm = (i < n) ? d[i] : 0.0;
+        bool rise = false;
+        int pk = i;
+        if (i >= 1 && i < n - 1 && d[i - 1] < vm) {          // start of a plateau
+          int ahead = i + 1;
+          while (ahead < n - 1 && d[ahead] == vm) ++ahead;
+          if (d[ahead] < vm) { rise = true; pk = (i + ahead - 1) / 2; }
+        }
+        // a plateau's midpoint may sit in another lane: publish the peak at its own position
+        const unsigned starts = __ballot_sync(AEW_FULL, rise);
+        unsigned mine_pk = 0;
+        for (unsigned s = starts; s; s &= s - 1) {
+          const int src = __ffs(s) - 1;
+          const int q = __shfl_sync(AEW_FULL, pk, src);
+          if (q == i) mine_pk = 1;
+          else if ((q >> 5) != m && (q & 31) == lane) mine_pk |= 2u << (q >> 5);   // lands in another chunk
+        }
+        peakmask[m] = mine_pk;
+      }
+      // fold "lands in another chunk" marks (plateaus longer than a chunk are vanishingly rare but legal)
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      bool is_pk = (peakmask[m] & 1u) != 0;
+      for (int m = 0; m < 4; ++m) {
+        bool is_pk = (peakmask[m] & 1u) != 0;
 #pragma unroll
-      for (int o = 0; o < 4; ++o) is_pk |= (peakmask[o] & (2u << m)) != 0;
-      pkbits[m] = __ballot_sync(AEW_FULL, is_pk);
+        for (int o = 0; o < 4; ++o) is_pk |= (peakmask[o] & (2u << m)) != 0;
+        pkbits[m] = __ballot_sync(AEW_FULL, is_pk);
+      }
     }
-#pragma unroll
+    // candidates in ascending order; ONE copy of the prominence code
+#pragma unroll 1
     for (int m = 0; m < 4; ++m) {
-      for (unsigned s = pkbits[m]; s; s &= s - 1) {
-        const int src = __ffs(s) - 1;
-        const int pk = 32 * m + src;
-        const double h = __shfl_sync(AEW_FULL, v[m], src);
+      unsigned s = m == 0 ? pkbits[0] : (m == 1 ? pkbits[1] : (m == 2 ? pkbits[2] : pkbits[3]));
+#pragma unroll 1
+      for (; s; s &= s - 1) {
+        const int pk = 32 * m + __ffs(s) - 1;
+        const double h = d[pk];
         // nearest strictly higher sample on each side (walks of scipy's _peak_prominences stop there)
         int nl = -1, nr = n;
 #pragma unroll
@@ -689,12 +704,12 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, unsigned long
     if (tid == 0 && p.zparams) { p.zparams[2 * w] = mean; p.zparams[2 * w + 1] = sd0; }   // for the median kernel
   }
   K3_TICK(1)   // window z-score (+ sum of the z-scored window)
-  if (p.zwin) {
-    double* zw = p.zwin + w * (long long)L;
-#pragma unroll 4
-    for (int i = tid; i < L; i += K3_NT) zw[i] = A[i];  // NaN windows: as z-scored by the reference or raw
-  }
   if (bad) {
+    if (p.zwin) {
+      double* zw = p.zwin + w * (long long)L;
+#pragma unroll 4
+      for (int i = tid; i < L; i += K3_NT) zw[i] = A[i];  // NaN windows: as z-scored by the reference or raw
+    }
     if (tid == 0) {
       p.keep[w] = 0; p.has_nan[w] = 1; p.n_peaks[w] = 0;
       for (int k = 0; k < 4; ++k) p.stats[4 * w + k] = qnan;
@@ -983,6 +998,11 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, unsigned long
       p.n_peaks[w] = np;
       p.stats[4 * w + 0] = hr; p.stats[4 * w + 1] = rms; p.stats[4 * w + 2] = sd; p.stats[4 * w + 3] = sdn;
     }
+  } else if (p.zwin) {
+    // meanwhile the other warps park the z-scored window for the median kernel / the 'ecg_sample' column
+    double* zw = p.zwin + w * (long long)L;
+#pragma unroll 4
+    for (int i = tid - 32; i < L; i += K3_NT - 32) zw[i] = A[i];
   }
   __syncthreads();
   const int np = sm.iscal[2];
