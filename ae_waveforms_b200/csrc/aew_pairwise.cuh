@@ -32,11 +32,9 @@ __host__ __device__ inline int pw_depth(long long n) {
   return d;
 }
 
-// (offset, size) of node `idx` at `depth` levels below the root of a range of n.
-__host__ __device__ inline void pw_node(long long n, int depth, unsigned idx, long long& off, long long& size) {
-  off = 0;
-  size = n;
-  for (int lvl = depth - 1; lvl >= 0; --lvl) {
+// Descend `levels` levels from the node (off, size) along the bits of idx (most significant first).
+__host__ __device__ inline void pw_walk(long long& off, long long& size, int levels, unsigned idx) {
+  for (int lvl = levels - 1; lvl >= 0; --lvl) {
     const unsigned bit = (idx >> lvl) & 1u;
     if (size > AEW_PW_LEAF) {
       long long h = size / 2;
@@ -47,6 +45,13 @@ __host__ __device__ inline void pw_node(long long n, int depth, unsigned idx, lo
       return;
     }
   }
+}
+
+// (offset, size) of node `idx` at `depth` levels below the root of a range of n.
+__host__ __device__ inline void pw_node(long long n, int depth, unsigned idx, long long& off, long long& size) {
+  off = 0;
+  size = n;
+  pw_walk(off, size, depth, idx);
 }
 
 // Sum of f(off .. off+size) for one leaf (size <= 128) by the 8 lanes of a group

@@ -42,20 +42,24 @@ struct LoadDev2 {  // pass 2: squared deviation from the mean, NaN -> 0
   }
 };
 
-// Leaf sum of K1 with the 16 loads of a lane issued back to back (raw values first, the
-// NaN test / deviation afterwards in registers) so that up to 16 x 8 B are in flight per lane.
+// Leaf sum of K1 with the loads of a lane issued back to back (up to 16 x 8 B in flight per lane).
+// The kernel used to be bound by instruction issue, not by HBM (ncu: issue slots 75 % busy), so the common case is
+// kept to a load and an addition per sample: the sums are formed WITHOUT looking for NaN -- a NaN poisons its
+// partial sum, the xor steps spread it to all eight lanes -- and only a leaf whose plain sum is NaN is redone
+// with the NaN -> 0 / counting arithmetic of np.nanmean / np.nanstd.  Same additions in the same order either way.
+// the literal nan-aware leaf sum (values re-read: the fast path below does not keep them)
 template <int PASS>
-__device__ __forceinline__ double k1_leaf_sum8(const double* __restrict__ x, double mean, long long off, int size,
-                                               int g, int& cnt) {
+__device__ __noinline__ double k1_leaf_nan(const double* __restrict__ x, double mean, long long off, int size, int g,
+                                           int& cnt) {
   double v[16];
-  const int n8 = size & ~7;
+  const int c8 = size >> 3;
 #pragma unroll
-  for (int k = 0; k < 16; ++k) v[k] = (8 * k < n8) ? __ldg(x + off + 8 * k + g) : 0.0;
+  for (int k = 0; k < 16; ++k) v[k] = (k < c8) ? __ldg(x + off + 8 * k + g) : 0.0;
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
     const bool ok = !isnan(v[k]);
     if (PASS == 1) {
-      cnt += (8 * k < n8 && ok) ? 1 : 0;
+      cnt += (k < c8 && ok) ? 1 : 0;
       v[k] = ok ? v[k] : 0.0;
     } else {
       const double d = __dsub_rn(v[k], mean);
@@ -65,14 +69,11 @@ __device__ __forceinline__ double k1_leaf_sum8(const double* __restrict__ x, dou
   double r = v[0];
 #pragma unroll
   for (int k = 1; k < 16; ++k)
-    if (8 * k < n8) r = __dadd_rn(r, v[k]);
-  double t = __shfl_xor_sync(AEW_FULL, r, 1);
-  r = __dadd_rn(r, t);
-  t = __shfl_xor_sync(AEW_FULL, r, 2);
-  r = __dadd_rn(r, t);
-  t = __shfl_xor_sync(AEW_FULL, r, 4);
-  r = __dadd_rn(r, t);
-  int i = n8;
+    if (k < c8) r = __dadd_rn(r, v[k]);
+  r = __dadd_rn(r, __shfl_xor_sync(AEW_FULL, r, 1));
+  r = __dadd_rn(r, __shfl_xor_sync(AEW_FULL, r, 2));
+  r = __dadd_rn(r, __shfl_xor_sync(AEW_FULL, r, 4));
+  int i = c8 << 3;
   if (size < 8) { r = 0.0; i = 0; }
   for (; i < size; ++i) {
     const double w = __ldg(x + off + i);
@@ -86,6 +87,54 @@ __device__ __forceinline__ double k1_leaf_sum8(const double* __restrict__ x, dou
     }
   }
   return r;
+}
+
+template <int PASS>
+__device__ __forceinline__ double k1_leaf_sum8(const double* __restrict__ x, double mean, long long off, int size,
+                                               int g, int& cnt) {
+  double v[16];
+  const int c8 = size >> 3;
+  const double* xg = x + off + g;
+  if (c8 >= 12) {                                       // (uniform over the 8 lanes; leaves of long records: 13 or 14)
+#pragma unroll
+    for (int k = 0; k < 12; ++k) v[k] = __ldg(xg + 8 * k);
+#pragma unroll
+    for (int k = 12; k < 16; ++k) v[k] = (k < c8) ? __ldg(xg + 8 * k) : 0.0;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = (k < c8) ? __ldg(xg + 8 * k) : 0.0;
+  }
+  if (PASS == 2) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { const double d = __dsub_rn(v[k], mean); v[k] = __dmul_rn(d, d); }
+  }
+  double r = v[0];
+  if (c8 >= 12) {
+#pragma unroll
+    for (int k = 1; k < 12; ++k) r = __dadd_rn(r, v[k]);
+#pragma unroll
+    for (int k = 12; k < 16; ++k) if (k < c8) r = __dadd_rn(r, v[k]);
+  } else {
+#pragma unroll
+    for (int k = 1; k < 16; ++k) if (k < c8) r = __dadd_rn(r, v[k]);
+  }
+  r = __dadd_rn(r, __shfl_xor_sync(AEW_FULL, r, 1));
+  r = __dadd_rn(r, __shfl_xor_sync(AEW_FULL, r, 2));
+  r = __dadd_rn(r, __shfl_xor_sync(AEW_FULL, r, 4));
+  int i = c8 << 3;
+  if (size < 8) { r = 0.0; i = 0; }
+  for (; i < size; ++i) {
+    const double w = __ldg(x + off + i);
+    if (PASS == 1) r = __dadd_rn(r, w);
+    else { const double d = __dsub_rn(w, mean); r = __dadd_rn(r, __dmul_rn(d, d)); }
+  }
+  // (the eight lanes of a leaf hold the same r; the four leaves of a warp go through the redo together because
+  //  its exchanges involve the whole warp -- a leaf without NaN just obtains the same sum again)
+  if (!__any_sync(AEW_FULL, isnan(r))) {
+    if (PASS == 1) cnt += (g == 0) ? size : 0;
+    return r;
+  }
+  return k1_leaf_nan<PASS>(x, mean, off, size, g, cnt);
 }
 
 __device__ __forceinline__ long long find_record(const long long* __restrict__ start, long long n_rec,
@@ -107,19 +156,26 @@ __global__ void __launch_bounds__(256) k1_leaf(const double* __restrict__ x, con
                                                unsigned long long* __restrict__ cnt) {
   __shared__ double s_vals[32];
   __shared__ unsigned char s_valid[32];
-  __shared__ long long s_rec;
-  __shared__ int s_cnt;
+  __shared__ long long s_rec, s_base, s_off, s_size;
+  __shared__ int s_cnt, s_sub;
   const long long b = blockIdx.x;
-  if (threadIdx.x == 0) { s_rec = find_record(blk_start, n_rec, b); s_cnt = 0; }
+  if (threadIdx.x == 0) {
+    // the record, and the subtree of its NumPy tree that this block sums: walked once, not by every thread
+    const long long r0 = find_record(blk_start, n_rec, b);
+    const long long base0 = rec_beg[r0], n0 = rec_end[r0] - base0;
+    const int depth = pw_depth(n0);
+    const int sub0 = depth < 5 ? depth : 5;
+    long long o, sz;
+    pw_node(n0, depth - sub0, (unsigned)(b - blk_start[r0]), o, sz);
+    s_rec = r0; s_base = base0; s_off = o; s_size = sz; s_sub = sub0; s_cnt = 0;
+  }
   __syncthreads();
   const long long r = s_rec;
-  const long long base = rec_beg[r], n = rec_end[r] - base;
-  const int depth = pw_depth(n);
-  const int sub = depth < 5 ? depth : 5;
-  const unsigned j = (unsigned)(b - blk_start[r]);
+  const long long base = s_base;
+  const int sub = s_sub;
   const int group = threadIdx.x >> 3, g = threadIdx.x & 7;
-  long long off = 0, size = 0;
-  if (group < (1 << sub)) pw_node(n, depth, (j << sub) + (unsigned)group, off, size);
+  long long off = s_off, size = s_size;
+  if (group < (1 << sub)) pw_walk(off, size, sub, (unsigned)group); else size = 0;
   int mycnt = 0;
   const double v = k1_leaf_sum8<PASS>(x + base, PASS == 2 ? mean[r] : 0.0, off, (int)size, g, mycnt);
   if (g == 0) { s_vals[group] = v; s_valid[group] = size > 0; }

@@ -1,0 +1,19 @@
+"""Runs the whole-record z-score statistics (K1) on NC synthetic cases; used under ncu."""
+import os, sys, numpy as np
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
+import torch, bench
+from ae_waveforms_b200 import batched
+dev = torch.device('cuda')
+n_cases = int(os.environ.get("NC", "200")); ns = 1800000
+flat = bench.synth_cases_gpu(np.arange(n_cases), ns, dev)
+rec_off = np.arange(n_cases + 1, dtype=np.int64) * ns
+batch = batched.RecordBatch(flat, rec_off)
+pre = batched.Preprocessor()
+beg_h, end_h, d_beg, d_end = pre._ranges(batch, trim=False)
+for rep in range(3):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    mean, sd, cnt = pre.zscore_stats(flat, beg_h, end_h, d_beg, d_end)
+    e1.record()
+    torch.cuda.synchronize()
+    print(rep, f"{e0.elapsed_time(e1):.3f} ms for {n_cases} cases, {2 * flat.numel() * 8 / e0.elapsed_time(e1) / 1e6:.0f} GB/s (two reads)")
