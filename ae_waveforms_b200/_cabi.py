@@ -51,7 +51,7 @@ SIGNATURES = {
     "aew_filt_workspace_bytes": (c_size_t, [c_longlong, c_longlong, c_longlong]),
     "aew_segments_find_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_longlong, c_void_p, c_void_p,
                                       c_void_p, c_size_t, c_longlong, c_void_p]),
-    "aew_filtfilt_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong,
+    "aew_filtfilt_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong,
                                  c_longlong, c_void_p, c_size_t, c_longlong, c_int, c_void_p]),
     "aew_filt_header": (c_int, [c_void_p, c_void_p]),
     "aew_filt_timing_dump": (c_int, [c_void_p]),

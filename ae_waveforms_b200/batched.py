@@ -46,6 +46,7 @@ class FilterDesign:
     a: np.ndarray = field(repr=False, default=None)
     zi: np.ndarray = field(repr=False, default=None)
     table: object = field(repr=False, default=None)     # torch tensor on the device
+    table_host: np.ndarray = field(repr=False, default=None)   # the same table on the host (kernel parameters)
     fast_ok: bool = True
 
     @property
@@ -74,7 +75,7 @@ def design_filter(btype: str, cutoff_hz: float, fs: float = 500, order: int = 4,
     rc = lib.aew_filt_tables(_np_ptr(b), _np_ptr(a), _np_ptr(zi), len(a) - 1, _np_ptr(tab))
     if rc not in (0, -3):
         _cabi.check(rc, "aew_filt_tables")
-    d = FilterDesign(btype, cutoff_hz, fs, order, b, a, zi, torch.from_numpy(tab).to(device), fast_ok=(rc == 0))
+    d = FilterDesign(btype, cutoff_hz, fs, order, b, a, zi, torch.from_numpy(tab).to(device), tab, fast_ok=(rc == 0))
     _design_cache[key] = d
     return d
 
@@ -191,8 +192,9 @@ class Preprocessor:
         for d in stages:
             if self.filter_mode == 0 and not d.fast_ok:
                 raise _cabi.AewError(f"{d}: no modal form; use filter_mode='exact'")
-            _cabi.check(lib.aew_filtfilt_f64(_ptr(src), _ptr(m), _ptr(s), _ptr(y), _ptr(tmp), _ptr(d.table), n_rec,
-                                             total, _ptr(ws), ws_bytes, max_seg, self.filter_mode, st), "filtfilt")
+            _cabi.check(lib.aew_filtfilt_f64(_ptr(src), _ptr(m), _ptr(s), _ptr(y), _ptr(tmp), _ptr(d.table),
+                                             _np_ptr(d.table_host), n_rec, total, _ptr(ws), ws_bytes, max_seg,
+                                             self.filter_mode, st), "filtfilt")
             self.launches += 1 if self.filter_mode else 2
             src, m, s = y, None, None
         if not stages:                                       # both cut-offs falsy: z-score only

@@ -70,6 +70,26 @@ class Barrier {
   unsigned gen_ = 0;
 };
 
+// named barrier (bar.sync / bar.arrive id, count): completes when `count` threads have arrived either way
+class NamedBarrier {
+ public:
+  void arrive(int count) {
+    std::unique_lock<std::mutex> lk(m_);
+    if (++n_ >= count) { n_ = 0; ++gen_; cv_.notify_all(); }
+  }
+  void sync(int count) {
+    std::unique_lock<std::mutex> lk(m_);
+    const unsigned g = gen_;
+    if (++n_ >= count) { n_ = 0; ++gen_; cv_.notify_all(); return; }
+    cv_.wait(lk, [&] { return gen_ != g; });
+  }
+ private:
+  std::mutex m_;
+  std::condition_variable cv_;
+  int n_ = 0;
+  unsigned gen_ = 0;
+};
+
 struct WarpCtx {
   Barrier bar;
   unsigned long long slot[32];
@@ -78,6 +98,7 @@ struct WarpCtx {
 
 struct BlockCtx {
   Barrier bar;
+  NamedBarrier named[16];
   std::vector<WarpCtx> warps;
   std::atomic<int> or_acc{0};
   std::vector<unsigned char> dyn;
@@ -143,6 +164,8 @@ inline int __syncthreads_or(int pred) {
   b->bar.wait();
   return r;
 }
+inline void aew_named_sync(int id, int count) { aew_emul::block_ctx()->named[id].sync(count); }
+inline void aew_named_arrive(int id, int count) { aew_emul::block_ctx()->named[id].arrive(count); }
 inline void __syncwarp(unsigned = 0xffffffffu) {
   aew_emul::block_ctx()->warps[aew_emul::tctx().warp].bar.wait();
 }

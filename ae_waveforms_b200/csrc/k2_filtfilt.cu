@@ -227,6 +227,11 @@ struct PassArgs {
   const double* tab;      // device coefficient table (k2_layout.h)
   K2Ws ws;
   int bulk_ok;            // src and dst base pointers are 16-byte aligned: bulk (TMA) copies allowed
+  // Coefficients every thread uses with compile-time indices travel in the kernel parameters: they become
+  // constant-bank operands of the FMAs instead of shared-memory loads (52 + 20 broadcast loads per thread and tile)
+  Modal cf;               // the filter in modal form
+  double cG[4 * K2_C];    // zero-input response rows G[j] (K2_TAB_G)
+  double cPK[20];         // p^(C 2^k), k = 0..4 (K2_TAB_PK)
   unsigned long long* dbg; // optional phase-cycle counters (AEW_K2_TIMING=1), else null
 };
 
@@ -346,7 +351,7 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
   if (tid == 0)
     for (int s = 0; s < K2_STAGES; ++s) mbar_init(&s_bar[s], 1);
   __syncthreads();
-  const Modal cf = load_modal(s_tab);
+  const Modal& cf = a.cf;
   const int pad = (int)s_tab[K2_TAB_PAD];
   const int lookback = (int)s_tab[K2_TAB_LOOKBACK];
   const double* PW = s_tab + K2_TAB_PWARP;
@@ -487,7 +492,7 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
           double o[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) o[i] = __shfl_up_sync(AEW_FULL, E[i], dd);
-          if (lane >= dd) cmul_acc(s_tab + K2_TAB_PK + 4 * kk, o, E);
+          if (lane >= dd) cmul_acc(a.cPK + 4 * kk, o, E);
         }
         if (lane == 31) {
 #pragma unroll
@@ -650,7 +655,7 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
       }
       // phase 3: add the zero-input response of the entering state
       double* mine = sm_p + base + dir * (tid * K2_C);
-      const double* G = s_tab + K2_TAB_G;
+      const double* G = a.cG;
 #pragma unroll
       for (int j = 0; j < K2_C; ++j)
         mine[dir * j] += fma(G[4 * j + 3], s[3], fma(G[4 * j + 2], s[2], fma(G[4 * j + 1], s[1], G[4 * j] * s[0])));
@@ -776,9 +781,9 @@ extern "C" int aew_segments_find_f64(const double* x, const long long* d_rec_beg
 //   out  filtered output (may alias src); tmp: scratch of the same length
 //   mode 0 = tiled scan (fast), 1 = exact sequential SciPy order (parity suite)
 extern "C" int aew_filtfilt_f64(const double* src, const double* mean, const double* sd, double* out, double* tmp,
-                                const double* d_tab, long long n_rec, long long total_samples, void* ws,
-                                size_t ws_bytes, long long max_seg, int mode, void* stream) {
-  if (!src || !out || !tmp || !d_tab || !ws || (mean && !sd)) return AEW_ERR_ARG;
+                                const double* d_tab, const double* h_tab, long long n_rec, long long total_samples,
+                                void* ws, size_t ws_bytes, long long max_seg, int mode, void* stream) {
+  if (!src || !out || !tmp || !d_tab || !h_tab || !ws || (mean && !sd)) return AEW_ERR_ARG;
   if (ws_bytes < aew_filt_workspace_bytes(n_rec, total_samples, max_seg)) return AEW_ERR_WORKSPACE;
   K2Ws w;
   k2_ws_layout((void*)align_up((size_t)ws, 128), max_seg, aew_filt_max_tiles(n_rec, total_samples, max_seg), &w);
@@ -787,6 +792,11 @@ extern "C" int aew_filtfilt_f64(const double* src, const double* mean, const dou
   a.src = src; a.mean = mean; a.sd = sd; a.dst = tmp; a.passthrough = out; a.tab = d_tab; a.ws = w;
   a.bulk_ok = ((((size_t)src | (size_t)out | (size_t)tmp) & 15) == 0) ? 1 : 0;
   a.dbg = nullptr;
+  a.cf.d = h_tab[K2_TAB_D];
+  a.cf.p1r = h_tab[K2_TAB_P + 0]; a.cf.p1i = h_tab[K2_TAB_P + 1]; a.cf.p2r = h_tab[K2_TAB_P + 2]; a.cf.p2i = h_tab[K2_TAB_P + 3];
+  a.cf.g0 = h_tab[K2_TAB_GC + 0]; a.cf.g1 = h_tab[K2_TAB_GC + 1]; a.cf.g2 = h_tab[K2_TAB_GC + 2]; a.cf.g3 = h_tab[K2_TAB_GC + 3];
+  for (int i = 0; i < 4 * K2_C; ++i) a.cG[i] = h_tab[K2_TAB_G + i];
+  for (int i = 0; i < 20; ++i) a.cPK[i] = h_tab[K2_TAB_PK + i];
 #ifndef AEW_EMUL
   if (getenv("AEW_K2_TIMING")) {
     if (!g_dbg) { cudaMalloc(&g_dbg, 16 * sizeof(unsigned long long)); cudaMemset(g_dbg, 0, 16 * sizeof(unsigned long long)); }

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AEW_VERSION 100
+#define AEW_VERSION 101
 
 /* return codes */
 #define AEW_OK 0
@@ -82,8 +82,9 @@ int aew_segments_find_f64(const double* d_x, const long long* d_rec_beg, const l
 /* mode 0: tiled block scan (within 1e-6 relative of SciPy; measured ~1e-9);
  * mode 1: literal sequential DF2T order, bit-identical to SciPy (parity suite). */
 int aew_filtfilt_f64(const double* d_src, const double* d_mean /* may be NULL */, const double* d_sd,
-                     double* d_out, double* d_tmp, const double* d_tab, long long n_rec, long long total_samples,
-                     void* d_ws, size_t ws_bytes, long long max_seg, int mode, void* stream);
+                     double* d_out, double* d_tmp, const double* d_tab, const double* h_tab /* host copy of d_tab */,
+                     long long n_rec, long long total_samples, void* d_ws, size_t ws_bytes, long long max_seg, int mode,
+                     void* stream);
 /* debugging aid: with AEW_K2_TIMING=1 in the environment, k2_pass accumulates the cycles thread 0 of every
  * block spends per phase; this copies and clears the 8 counters (synchronises the device) */
 int aew_filt_timing_dump(unsigned long long* h_out8);

@@ -99,7 +99,7 @@ def filtfilt(records, stages, mode, zscore=False, max_seg=None):
     for btype, fc, order in stages:
         tab, trc = filter_tables(btype, fc, 500, order)
         assert trc == 0
-        rc = L.aew_filtfilt_f64(ptr(src), ptr(m), ptr(s), ptr(out), ptr(tmp), ptr(tab), n, total, ptr(ws), wsb,
+        rc = L.aew_filtfilt_f64(ptr(src), ptr(m), ptr(s), ptr(out), ptr(tmp), ptr(tab), ptr(tab), n, total, ptr(ws), wsb,
                                 max_seg, mode, None)
         assert rc == 0, rc
         src, m, s = out, None, None

@@ -25,7 +25,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), f"{name} declared in aewave.h but not exported"
     assert sorted(_cabi.SIGNATURES) == names, "ctypes prototypes and header out of sync"
-    assert lib.aew_version() == 100
+    assert lib.aew_version() == 101
 
 
 def test_sass_is_sm100a_only():
