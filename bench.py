@@ -61,7 +61,9 @@ def synth_cases_gpu(case_ids, n_samples, device, chunk=25):
             rr = 60.0 / rs.uniform(50.0, 110.0)
             nb = int(np.ceil((dur + 2.0) / (rr * 0.8))) + 2
             iv = rr * (1.0 + 0.03 * torch.randn(nb, dtype=torch.float64, device=device, generator=g))
-            tr = -1.0 + rs.uniform(0.0, rr) + torch.cumsum(iv.clamp_min(0.25), 0)
+            # (cumulative sum on the host: the device scan adds in a run-dependent order, and the benchmark input
+            #  should be the same bits every time -- profiles/determinism_check.py)
+            tr = -1.0 + rs.uniform(0.0, rr) + torch.cumsum(iv.clamp_min(0.25).cpu(), 0).to(device)
             nxt = torch.searchsorted(tr, t).clamp_(1, nb - 1)
             sig = torch.zeros(n_samples, dtype=torch.float64, device=device)
             for beat in (tr[nxt - 1], tr[nxt]):
