@@ -304,14 +304,29 @@ class Preprocessor:
         return res
 
 
+COPY_PIECE = 4 * 1024 * 1024        # samples per host->device copy piece (32 MB)
+_pinned_pool: dict = {}             # reusable page-locked result buffers (cudaHostAlloc is far too slow per call)
+
+
+def _pinned(key: str, shape, dtype, torch):
+    """A page-locked host tensor of at least `shape[0]` rows, kept and grown across calls."""
+    t = _pinned_pool.get(key)
+    if t is None or t.shape[0] < shape[0] or t.dtype != dtype or tuple(t.shape[1:]) != tuple(shape[1:]):
+        t = torch.empty(shape, dtype=dtype, pin_memory=True)
+        _pinned_pool[key] = t
+    return t
+
+
 def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chunk_cases: int = 100,
-                       to_host: bool = True) -> dict:
+                       to_host: bool = True, pinned_results: bool = False) -> dict:
     """End-to-end path for HOST data: ``host_flat`` is a (preferably pinned) CPU float64
     tensor holding all records back to back.  Cases are fed in chunks through two device
     input buffers: the host->device copy of chunk k+1 (copy stream) overlaps the kernels of
-    chunk k (current stream), so the wall time is max(PCIe, kernels) instead of their sum.
+    chunk k (current stream), and the device->host copy of chunk k's rows (third stream, into
+    page-locked memory) overlaps both, so the wall time is max(PCIe, kernels) instead of their sum.
     Returns ``np_waves`` (n,320) f32 and ``np_info`` (n,2) f64 in case order, as host tensors
-    (``to_host``) or left on the device (e.g. for a following all-gather)."""
+    (``to_host``) or left on the device (e.g. for a following all-gather).  With ``pinned_results`` the host
+    tensors are views of a reusable page-locked pool (valid until the next call) instead of fresh copies."""
     torch = pre.torch
     rec_off = np.ascontiguousarray(rec_off, dtype=np.int64)
     n_rec = len(rec_off) - 1
@@ -326,16 +341,27 @@ def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chu
     main = torch.cuda.current_stream(pre.device)
     copied = [torch.cuda.Event() for _ in chunks]
     freed = [torch.cuda.Event() for _ in chunks]
+    if to_host:
+        # every window can be kept at most: an upper bound on the rows, known from the record lengths alone
+        max_rows = int(sum(window_count(int(rec_off[r + 1] - rec_off[r]), pre.L) for r in range(n_rec)))
+        h_waves = _pinned("waves", (max(max_rows, 1), BEAT_LEN), torch.float32, torch)
+        h_info = _pinned("info", (max(max_rows, 1), 2), torch.float64, torch)
+        back_stream = torch.cuda.Stream(device=pre.device)
 
     def start_copy(k):
         c0, c1 = chunks[k]
         with torch.cuda.stream(copy_stream):
             if k >= 2:
                 copy_stream.wait_event(freed[k - 2])          # the buffer's previous chunk has been consumed
-            bufs[k % 2][:sizes[k]].copy_(host_flat[int(rec_off[c0]):int(rec_off[c1])], non_blocking=True)
+            # in pieces: the small host->device copies the kernels of the previous chunk need (offset tables,
+            # window starts) share the copy engine with this transfer and would otherwise queue behind all of it
+            lo, hi = int(rec_off[c0]), int(rec_off[c1])
+            for p0 in range(lo, hi, COPY_PIECE):
+                p1 = min(hi, p0 + COPY_PIECE)
+                bufs[k % 2][p0 - lo:p1 - lo].copy_(host_flat[p0:p1], non_blocking=True)
             copied[k].record(copy_stream)
 
-    waves, infos, hazards, n_windows, n_beats = [], [], 0, 0, 0
+    waves, infos, hazards, n_windows, n_beats, rows = [], [], 0, 0, 0, 0
     if chunks:
         start_copy(0)
     for k, (c0, c1) in enumerate(chunks):
@@ -346,14 +372,28 @@ def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chu
         sc = {"y": scratch["y"][:sizes[k]], "tmp": scratch["tmp"][:sizes[k]]}
         res = pre.run(sub, scratch=sc)
         freed[k].record(main)
-        waves.append(res["np_waves"].cpu() if to_host else res["np_waves"])
-        infos.append(res["np_info"].cpu() if to_host else res["np_info"])
+        waves.append(res["np_waves"])
+        infos.append(res["np_info"])
+        if to_host:
+            n = res["np_waves"].shape[0]
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(back_stream):
+                back_stream.wait_event(done)
+                h_waves[rows:rows + n].copy_(res["np_waves"], non_blocking=True)
+                h_info[rows:rows + n].copy_(res["np_info"], non_blocking=True)
+            rows += n
         hazards += res["hazard_windows"]
         n_windows += res["n_windows"]
         n_beats += res["n_beats"]
-    dev = None if to_host else pre.device
-    np_waves = torch.cat(waves) if waves else torch.zeros((0, BEAT_LEN), dtype=torch.float32, device=dev)
-    np_info = torch.cat(infos) if infos else torch.zeros((0, 2), dtype=torch.float64, device=dev)
+    if to_host:
+        back_stream.synchronize()
+        np_waves, np_info = h_waves[:rows], h_info[:rows]
+        if not pinned_results:
+            np_waves, np_info = np_waves.clone(), np_info.clone()
+    else:
+        np_waves = torch.cat(waves) if waves else torch.zeros((0, BEAT_LEN), dtype=torch.float32, device=pre.device)
+        np_info = torch.cat(infos) if infos else torch.zeros((0, 2), dtype=torch.float64, device=pre.device)
     return dict(np_waves=np_waves, np_info=np_info, hazard_windows=hazards, n_windows=n_windows, n_beats=n_beats)
 
 

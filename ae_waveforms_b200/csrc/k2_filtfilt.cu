@@ -317,6 +317,7 @@ __device__ __forceinline__ TileDesc describe_tile(const long long raw[4], int bu
 // are their own flags and no fence is needed on either side
 #define K2_EMPTY 0xffffffffffffffffull
 #define K2_PRODUCER 32               // thread that claims tiles and issues the bulk copies (warp 1, lane 0)
+#define K2_LOOKER 64                 // thread that resolves the look-back of the pending tile (warp 2, lane 0)
 
 __device__ __forceinline__ bool load_state(const double* p, double q[4]) {
   const volatile unsigned long long* v = (const volatile unsigned long long*)p;
@@ -328,7 +329,15 @@ __device__ __forceinline__ bool load_state(const double* p, double q[4]) {
 
 #ifdef AEW_EMUL
 #define K2_TICK(slot)
+#define K2_TICK_T(thread, slot, reset)
 #else
+// cycles a given thread spends between a reset point and here
+#define K2_TICK_T(thread, slot, reset)                                  \
+  if (a.dbg && tid == (thread)) {                                       \
+    const long long now_ = clock64();                                   \
+    if (!(reset)) atomicAdd(a.dbg + (slot), (unsigned long long)(now_ - tick_)); \
+    tick_ = now_;                                                       \
+  }
 #define K2_TICK(slot)                                                   \
   if (a.dbg && tid == 0) {                                              \
     const long long now_ = clock64();                                   \
@@ -351,6 +360,7 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
                                                       //   of a tile, up to the contribution of the look-back
   __shared__ unsigned long long s_bar[K2_STAGES];
   __shared__ long long s_tile[K2_STAGES];
+  __shared__ double s_pt2[4];                        // (p^T)^2
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < K2_TAB_LEN; i += K2_NT) s_tab[i] = a.tab[i];
@@ -358,6 +368,11 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
     for (int s = 0; s < K2_STAGES; ++s) mbar_init(&s_bar[s], 1);
   __syncthreads();
   const Modal& cf = a.cf;
+  if (tid == 0) {
+    const double* PT0 = s_tab + K2_TAB_PTILE;
+    s_pt2[0] = PT0[0] * PT0[0] - PT0[1] * PT0[1]; s_pt2[1] = 2.0 * PT0[0] * PT0[1];
+    s_pt2[2] = PT0[2] * PT0[2] - PT0[3] * PT0[3]; s_pt2[3] = 2.0 * PT0[2] * PT0[3];
+  }
   const int pad = (int)s_tab[K2_TAB_PAD];
   const int lookback = (int)s_tab[K2_TAB_LOOKBACK];
   const double* PW = s_tab + K2_TAB_PWARP;
@@ -402,11 +417,11 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
     const int st = it % K2_STAGES;
     const long long tile = s_tile[st];
     const bool live = tile < n_tiles;
-    // thread 0: issue the look-back loads of the pending tile now (raw bits, no test yet) so that their
+    // look-back thread: issue the look-back loads of the pending tile now (raw bits, no test yet) so that their
     // round trip overlaps this tile's recursion; they are examined after the barrier
     unsigned long long q0[4] = {K2_EMPTY, K2_EMPTY, K2_EMPTY, K2_EMPTY}, q1[4] = {K2_EMPTY, K2_EMPTY, K2_EMPTY, K2_EMPTY},
                        q2[4] = {K2_EMPTY, K2_EMPTY, K2_EMPTY, K2_EMPTY};
-    if (tid == 0 && have_prev && dp.k > 0) {
+    if (tid == K2_LOOKER && have_prev && dp.k > 0) {
       const volatile unsigned long long* v0 = (const volatile unsigned long long*)(tstate + 4 * (tile_p - 1));
 #pragma unroll
       for (int i = 0; i < 4; ++i) q0[i] = v0[i];
@@ -485,11 +500,14 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
 #pragma unroll
           for (int j = 0; j < K2_C; ++j) {
             const bool inside = tid * K2_C + j < d.cnt;   // zero padding stays zero under the z-score
-            mine[dir * j] = modal_step(cf, inside ? zsf(mine[dir * j], true, mean, inv_sd) : 0.0, E);
+            mine[j] = modal_step(cf, inside ? zsf(mine[j], true, mean, inv_sd) : 0.0, E);   // (forward: dir = +1)
           }
+        } else if (dir > 0) {                            // the offsets are compile-time constants in either branch
+#pragma unroll
+          for (int j = 0; j < K2_C; ++j) mine[j] = modal_step(cf, mine[j], E);
         } else {
 #pragma unroll
-          for (int j = 0; j < K2_C; ++j) mine[dir * j] = modal_step(cf, mine[dir * j], E);
+          for (int j = 0; j < K2_C; ++j) mine[-j] = modal_step(cf, mine[-j], E);
         }
         K2_TICK(7)   // phase 1 recursion
         // phase 2a: warp scan of chunk end states (Kogge-Stone with p^(C*2^k))
@@ -510,6 +528,8 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
     K2_TICK(1)   // A half (thread 0's own work)
     __syncthreads();
     K2_TICK(2)   // wait at the barrier after the A half
+    K2_TICK_T(K2_PRODUCER, 0, true)
+    K2_TICK_T(K2_LOOKER, 0, true)
 
     // producer thread (warp 1): runs while thread 0 works through its serial section below
     if (tid == K2_PRODUCER) {
@@ -530,6 +550,7 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
           for (int i = 0; i < 4; ++i) raw1[i] = a.ws.tile_desc[4 * id1 + i];
         id2 = (long long)atomicAdd((unsigned long long*)work, 1ull);
       }
+      K2_TICK_T(K2_PRODUCER, 12, false)
     }
 
     // =================== warp 0: publish this tile, resolve the pending tile ===================
@@ -575,16 +596,20 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
           }
         }
       }
+    }
+    // =================== warp 2, at the same time: resolve the pending tile ===================
+    // (independent of the scan above: it combines the PREVIOUS iteration's prefixes with the look-back)
+    if (warp == K2_LOOKER / 32) {
+      const double* PWP = s_tab + K2_TAB_PWP;
       if (have_prev) {
         double S[4] = {0.0, 0.0, 0.0, 0.0};
         if (lane == 0 && dp.k > 0) {
           // S = sum_j (p^T)^j Q[tile_p-1-j], j < min(lookback, k)
           const double* PT = s_tab + K2_TAB_PTILE;
-          double Wm[4] = {1.0, 0.0, 1.0, 0.0};
           const long long depth = dp.k < lookback ? dp.k : lookback;
           // the first three predecessors were loaded at the top of the iteration (registers q0..q2, no
           // dynamic indexing: a pointer into them would push them to local memory and stall the loads)
-#define K2_LOOKBACK_STEP(J, QR)                                                                              \
+#define K2_LOOKBACK_STEP(J, QR, WJ)                                                                          \
           if ((J) < depth) {                                                                                    \
             double Q[4];                                                                                        \
             bool ok = QR[0] != K2_EMPTY && QR[1] != K2_EMPTY && QR[2] != K2_EMPTY && QR[3] != K2_EMPTY;         \
@@ -600,19 +625,20 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
                 if (++spins > (1u << 22)) { atomicOr((int*)(a.ws.hdr + H_STATUS), AEW_DEV_LOOKBACK_TIMEOUT); break; } \
               }                                                                                                 \
             }                                                                                                   \
-            cmul_acc(Wm, Q, S);                                                                                 \
-            if ((J) + 1 < depth) {                                                                              \
-              const double w0 = Wm[0] * PT[0] - Wm[1] * PT[1], w1 = Wm[0] * PT[1] + Wm[1] * PT[0];              \
-              const double w2 = Wm[2] * PT[2] - Wm[3] * PT[3], w3 = Wm[2] * PT[3] + Wm[3] * PT[2];              \
-              Wm[0] = w0; Wm[1] = w1; Wm[2] = w2; Wm[3] = w3;                                                   \
-            }                                                                                                   \
+            cmul_acc(WJ, Q, S);                                                                                 \
           }
-          K2_LOOKBACK_STEP(0, q0)
-          K2_LOOKBACK_STEP(1, q1)
-          K2_LOOKBACK_STEP(2, q2)
+          // three independent products with tabulated powers 1, p^T, p^2T (no chain through a running power)
+          const double one[4] = {1.0, 0.0, 1.0, 0.0};
+          K2_LOOKBACK_STEP(0, q0, one)
+          K2_LOOKBACK_STEP(1, q1, PT)
+          K2_LOOKBACK_STEP(2, q2, s_pt2)
+          double Wm[4] = {s_pt2[0], s_pt2[1], s_pt2[2], s_pt2[3]};
           for (long long j = 3; j < depth; ++j) {      // deeper look-backs (slowly decaying filters)
             const unsigned long long none[4] = {K2_EMPTY, K2_EMPTY, K2_EMPTY, K2_EMPTY};
-            K2_LOOKBACK_STEP(j, none)
+            const double w0 = Wm[0] * PT[0] - Wm[1] * PT[1], w1 = Wm[0] * PT[1] + Wm[1] * PT[0];
+            const double w2 = Wm[2] * PT[2] - Wm[3] * PT[3], w3 = Wm[2] * PT[3] + Wm[3] * PT[2];
+            Wm[0] = w0; Wm[1] = w1; Wm[2] = w2; Wm[3] = w3;
+            K2_LOOKBACK_STEP(j, none, Wm)
           }
 #undef K2_LOOKBACK_STEP
         }
@@ -629,6 +655,7 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
       }
     }
     K2_TICK(3)   // publish / look-back / chains
+    K2_TICK_T(K2_LOOKER, 11, false)
     __syncthreads();
     K2_TICK(4)
 
@@ -663,9 +690,15 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
       // phase 3: add the zero-input response of the entering state
       double* mine = sm_p + base + dir * (tid * K2_C);
       const double* G = a.cG;
+      if (dir > 0) {
 #pragma unroll
-      for (int j = 0; j < K2_C; ++j)
-        mine[dir * j] += fma(G[4 * j + 3], s[3], fma(G[4 * j + 2], s[2], fma(G[4 * j + 1], s[1], G[4 * j] * s[0])));
+        for (int j = 0; j < K2_C; ++j)
+          mine[j] = fma(G[4 * j + 3], s[3], fma(G[4 * j + 2], s[2], fma(G[4 * j + 1], s[1], fma(G[4 * j], s[0], mine[j]))));
+      } else {
+#pragma unroll
+        for (int j = 0; j < K2_C; ++j)
+          mine[-j] = fma(G[4 * j + 3], s[3], fma(G[4 * j + 2], s[2], fma(G[4 * j + 1], s[1], fma(G[4 * j], s[0], mine[-j]))));
+      }
       if (dp.bulk) {
         fence_async_smem();                            // my shared-memory writes -> visible to the bulk engine
         __syncthreads();

@@ -361,11 +361,13 @@ def run_gpu(args):
         torch.cuda.empty_cache()
 
         def step_host():
+            if world == 1:                             # rows land in page-locked host memory chunk by chunk
+                r = batched.run_host_pipelined(pre, host, rec_off, case_ids, chunk_cases=max(1, n_cases // 10),
+                                               to_host=True, pinned_results=True)
+                return r["np_waves"], r["np_info"]
             r = batched.run_host_pipelined(pre, host, rec_off, case_ids, chunk_cases=max(1, n_cases // 10),
                                            to_host=False)
-            w, i = r["np_waves"], r["np_info"]
-            if world > 1:
-                w, i = awd.gather_beat_arrays(w, i)
+            w, i = awd.gather_beat_arrays(r["np_waves"], r["np_info"])
             return w.cpu(), i.cpu()
 
         for _ in range(min(2, args.warmup)):
