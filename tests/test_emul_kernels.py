@@ -8,7 +8,7 @@ import pytest
 
 import emul_harness as eh
 from conftest import unragged
-from oracle import ref_port as rp
+from oracle import ecg_synth, ref_port as rp
 
 warnings.simplefilter("ignore", RuntimeWarning)
 
@@ -99,6 +99,22 @@ def test_k3_screen_golden(golden):
     # pre-scaled windows, as the remove_samples() drop-in passes them
     o2 = eh.screen(g["windows"][sel].reshape(-1), np.arange(len(sel)) * 10000, mode=0, zscore_windows=False)
     assert same(o2["keep"], o["keep"]) and same(o2["peaks"], o["peaks"])
+
+
+def test_k3_other_window_lengths():
+    """The segmented box filters, the bit-packed indicator and the run tables at window lengths / sampling rates
+    other than 10,000 @ 500 Hz, against the oracle (fast and exact evaluation)."""
+    for fs, Lw, seed in ((250, 5000, 3), (360, 7200, 4), (500, 6000, 5), (100, 2000, 6), (500, 10240, 7)):
+        x = ecg_synth.synth_case(seed, 4 * Lw + 17)
+        y = rp.butterworth(rp.butterworth(rp.zscore(x), "high", 1.0, fs), "low", 30.0, fs)
+        wins = np.stack([rp.zscore(y[k * Lw:(k + 1) * Lw]) for k in range(4)])
+        want = rp.window_screen(wins, fs=fs)
+        for mode in (0, 1):
+            o = eh.screen(y[:4 * Lw], np.arange(4) * Lw, Lw=Lw, mode=mode, fs=fs)
+            for j in range(4):
+                assert same(o["peaks"][j, :o["n_peaks"][j]], want["peaks"][j]), (fs, Lw, mode, j)
+                assert bool(o["keep"][j]) == bool(want["keep"][j])
+                assert same(o["stats"][j, :3], [want["hr"][j], want["rmssd"][j], want["sd"][j]])
 
 
 def test_k4_median_golden(golden):

@@ -204,6 +204,29 @@ def test_screen_many_windows_against_oracle(gpu):
         assert o["status"][0] == 0
 
 
+def test_screen_other_window_lengths(gpu):
+    """Window lengths / sampling rates other than 10,000 @ 500 Hz (segmented box filters, bit-packed indicator,
+    run tables, both median kernels' addressing) against the oracle."""
+    import torch
+    torch_, B = gpu
+    for fs, secs, seed in ((250, 20, 3), (360, 20, 4), (500, 12, 5), (100, 20, 6), (512, 20, 7)):
+        Lw = fs * secs
+        x = ecg_synth.synth_case(seed, 6 * Lw + 17)
+        y = rp.butterworth(rp.butterworth(rp.zscore(x), "high", 1.0, fs), "low", 30.0, fs)
+        wins = np.stack([rp.zscore(y[k * Lw:(k + 1) * Lw]) for k in range(6)])
+        want = rp.window_screen(wins, fs=fs)
+        for mode in ("auto", "exact"):
+            pre = B.Preprocessor(fs=fs, sample_length=secs, screen_mode=mode)
+            out = pre.screen_windows(torch.from_numpy(np.ascontiguousarray(y[:6 * Lw])).cuda(), np.arange(6, dtype=np.int64) * Lw)
+            o = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in out.items()}
+            assert same(o["keep"].astype(bool), want["keep"]), (fs, mode)
+            for j in range(6):
+                assert same(o["peaks"][j, :o["n_peaks"][j]], want["peaks"][j]), (fs, mode, j)
+                assert same(o["stats"][j, :3], [want["hr"][j], want["rmssd"][j], want["sd"][j]])
+            for j in np.flatnonzero(want["keep"]):
+                assert same(o["median"][j], rp.compute_median_sample_ecg(wins[j], want["peaks"][j], fs))
+
+
 def test_median_dropin_golden(gpu, golden):
     from ae_waveforms_b200.data_load_preprocess.median_sample import compute_median_sample_ecg
     g = golden("median")
