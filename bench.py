@@ -181,7 +181,7 @@ def run_reference(args):
         tot_s += r["seconds"]; tot_n += r["samples"]; beats += r["beats"]
     val = tot_n / tot_s / 1e6
     sample = f"{cores} x 1 h cases per step (one per core), {args.steps} steps, oracle port of the reference's NumPy/SciPy path"
-    print(json.dumps({
+    print_json(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": tot_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -448,7 +448,7 @@ def run_gpu(args):
                                    "sample": f"{4 * cores} x 1 h cases (4 per core, process pool over case IDs) "
                                              f"through the oracle port of the reference's NumPy/SciPy path, "
                                              f"{r['seconds']:.1f} s wall = {r['seconds'] * cores:.0f} core-seconds"}
-        print(json.dumps(out))
+        print_json(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
@@ -461,6 +461,14 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON: libraries that print to file descriptor 1 while the job runs (NCCL
+    # announces its version there) are pointed at stderr, and the descriptor is restored for the final print
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    out_stream = os.fdopen(real_stdout, "w")
+    global print_json
+    print_json = lambda text: (out_stream.write(text + "\n"), out_stream.flush())
     if args.impl == "reference":
         run_reference(args)
     else:
