@@ -285,14 +285,14 @@ class Preprocessor:
         y, header = self.filter_records(flat, beg_h, end_h, d_beg, d_end, mean, sd, cnt,
                                         out=(scratch or {}).get("y"), tmp=(scratch or {}).get("tmp"))
         win_start, win_case, win_end = self.window_table(beg_h, end_h, batch.case_ids)
+        info_h = np.stack([win_case.astype(np.float64), win_end.astype(np.float64)], axis=1) if len(win_start) \
+            else np.zeros((0, 2))
+        info = torch.from_numpy(info_h).to(self.device)             # (uploaded while the filter is still running)
         scr = self.screen_windows(y, win_start, zwin_scratch=getattr(self, "_filter_tmp", None))
         keep_idx = torch.nonzero(scr["keep"]).squeeze(1)            # sync: number of kept windows
         hdr = header.cpu().numpy()
         _cabi.check_device_status(int(hdr[4]), "filter")
         _cabi.check_device_status(int(scr["status"].item()), "window screen")
-        info_h = np.stack([win_case.astype(np.float64), win_end.astype(np.float64)], axis=1) if len(win_start) \
-            else np.zeros((0, 2))
-        info = torch.from_numpy(info_h).to(self.device)
         res = dict(np_waves=scr["waves"].index_select(0, keep_idx), medians=scr["median"].index_select(0, keep_idx),
                    np_info=info.index_select(0, keep_idx), keep=scr["keep"], has_nan=scr["has_nan"],
                    n_peaks=scr["n_peaks"], peaks=scr["peaks"], stats=scr["stats"], keep_idx=keep_idx,

@@ -143,7 +143,7 @@ __device__ __forceinline__ double leaf_term(int mode, double v, double m, const 
   return z;
 }
 __device__ __noinline__ LeafOut leaf_pass(int mode, double* A, double m, double sd, int off, int size, int j) {
-  const ExactDiv dv = make_exact_div(sd);
+  const ExactDiv dv = make_exact_div(mode == K3_PASS_ZSCORE ? sd : 1.0);
   const int c8 = size >> 3;
   int flag = 0;
   // lane j carries the stride-8 partial sums r_{2j} and r_{2j+1}: one 16-byte access per round (the leaf offsets
@@ -667,9 +667,20 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, unsigned long
   }
   for (int i = tid; i < L / 32 + 2; i += K3_NT) sm.Qw[i] = 0u;
 
-  // ---- load (coalesced)
-#pragma unroll 8
+  // ---- load (coalesced).  Asynchronous copies straight into shared memory: all 40 requests of a thread are in
+  //      flight at once and no registers are staged (8-byte form: a window start is only 8-byte aligned)
+#ifdef AEW_EMUL
   for (int i = tid; i < L; i += K3_NT) A[i] = src[i];
+#else
+  {
+    const unsigned a0 = (unsigned)__cvta_generic_to_shared(A);
+#pragma unroll 8
+    for (int i = tid; i < L; i += K3_NT)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(a0 + 8u * (unsigned)i), "l"(src + i) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
+#endif
   __syncthreads();                                      // window, leaf table
   // two leaves per thread: slot and slot + 64
   const int slot = tid >> 2, lj = tid & 3;
