@@ -15,7 +15,8 @@ LIB_PATH = os.path.join(HERE, "csrc", "libaewave.so")
 
 ERRORS = {-1: "bad argument", -2: "workspace too small", -3: "unsupported parameter", -4: "no sm_100 CUDA device"}
 DEV_STATUS = {1: "more NaN-delimited segments than max_segments", 2: "more filter tiles than the workspace holds",
-              4: "filter look-back timed out", 8: "more than max_peaks R-peaks in a window"}
+              4: "filter look-back timed out", 8: "more than max_peaks R-peaks in a window",
+              16: "a fiducial index lies outside its window"}
 
 
 class AewError(RuntimeError):
@@ -61,6 +62,8 @@ SIGNATURES = {
     "aew_windows_timing_dump": (c_int, [c_void_p]),
     "aew_median_beats_f64": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
                                      c_void_p, c_void_p, c_void_p]),
+    "aew_fiducial_features_f64": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                                          c_void_p, c_double, c_void_p, c_void_p, c_void_p]),
     "aew_recon_workspace_bytes": (c_size_t, [c_longlong, c_longlong]),
     "aew_recon_sse_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_int, c_void_p,
                                   c_longlong, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -22,6 +22,7 @@ PER_FILE = {
     "k1_zscore.cu": ["-fmad=false"],
     "k3_windows.cu": ["-fmad=false"],
     "k5_recon.cu": [],
+    "k6_features.cu": ["-fmad=false"],
     "k2_filtfilt.cu": [],
     "cabi_misc.cu": [],
 }

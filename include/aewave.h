@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AEW_VERSION 101
+#define AEW_VERSION 102
 
 /* return codes */
 #define AEW_OK 0
@@ -40,6 +40,7 @@ extern "C" {
 #define AEW_DEV_TILE_OVERFLOW 2
 #define AEW_DEV_LOOKBACK_TIMEOUT 4
 #define AEW_DEV_RUN_OVERFLOW 8
+#define AEW_DEV_FID_RANGE 16 /* a fiducial index outside [0, L) was treated as missing */
 
 int aew_version(void);
 /* 0 if a CUDA device of compute capability 10.x is current, AEW_ERR_NO_DEVICE otherwise */
@@ -136,6 +137,24 @@ int aew_windows_timing_dump(unsigned long long* h_out16);
 int aew_median_beats_f64(const double* d_windows, long long n_win, int L, const int* d_peaks,
                          const long long* d_peak_off, int max_peaks_per_window, int pre, int post,
                          double* d_median, double* d_aligned, void* stream);
+
+/* ---- K6: the 35 np_features of a window from per-beat fiducial indices ----------------
+ * replaces ecg_features_relative_r + compute_ecg_morphology_features
+ * (data_load_preprocess/feature_extraction/features_ecg.py:56-136) and
+ * compute_median_features_ecg (data_load_preprocess/median_sample.py:57-82) as called at
+ * data_extract_vitaldb.py:146-162, flattened like data_create_arrays.py:34-36:
+ * [x, y of P_Peaks, P_Onsets, P_Offsets, Q_Peaks, R_Onsets, R_Offsets, S_Peaks, T_Peaks, T_Onsets,
+ *  T_Offsets | 10 durations | 5 prominences], bit-identical to the reference's arithmetic.
+ *   d_sig, d_sig_off  window w's samples are d_sig[d_sig_off[w] .. + L) (the z-scored 'ecg_sample')
+ *   d_peaks           [n_win][max_peaks] R-peak indices, d_n_peaks [n_win]
+ *   d_fid             [n_win][10][max_peaks] int32 fiducial indices in the order above, AEW_FID_NAN = np.nan
+ *   d_valid           optional [n_win]: 0 = delineation failed -> NaN row (data_extract_vitaldb.py:132-135)
+ *   d_features        [n_win][35] out */
+#define AEW_FID_NAN (-2147483647 - 1)
+int aew_fiducial_features_f64(const double* d_sig, const long long* d_sig_off, long long n_win, int L,
+                              const int* d_peaks, const int* d_n_peaks, int max_peaks, const int* d_fid,
+                              const unsigned char* d_valid, double fs, double* d_features, int* d_status,
+                              void* stream);
 
 /* ---- K5: Gaussian fiducial reconstruction + sigma-map search objective --------------
  * replaces gaussian_line / extract_coordinates / reconstruct_gaussian

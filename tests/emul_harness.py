@@ -171,3 +171,30 @@ def recon_grid(fx, fy, bl, target, xt, vals, idx):
                                   ptr(idx), nc, ptr(sse), ptr(ws), wsb, None)
     assert rc == 0, rc
     return sse
+
+
+FID_NAN = -2147483648
+
+
+def fiducial_features(windows, peaks_list, fid_list, valid=None, fs=500.0):
+    """windows (n, L); peaks_list: per window int list; fid_list: per window (10, n_beats) float array, NaN = missing."""
+    L = lib()
+    w = np.ascontiguousarray(windows, dtype=np.float64)
+    n, Lw = w.shape
+    maxp = L.aew_windows_max_peaks()
+    pk = np.full((n, maxp), -1, np.int32)
+    npk = np.zeros(n, np.int32)
+    fid = np.full((n, 10, maxp), FID_NAN, np.int32)
+    for i, (p, f) in enumerate(zip(peaks_list, fid_list)):
+        npk[i] = len(p)
+        pk[i, :len(p)] = p
+        f = np.asarray(f, dtype=np.float64).reshape(10, -1)
+        fid[i, :, :f.shape[1]] = np.where(np.isnan(f), FID_NAN, f).astype(np.int64)
+    off = (np.arange(n, dtype=np.int64) * Lw)
+    out = np.full((n, 35), -9.0)
+    status = np.zeros(1, np.int32)
+    v = None if valid is None else np.ascontiguousarray(valid, dtype=np.uint8)
+    rc = L.aew_fiducial_features_f64(ptr(w), ptr(off), n, Lw, ptr(pk), ptr(npk), maxp, ptr(fid), ptr(v), float(fs),
+                                     ptr(out), ptr(status), None)
+    assert rc == 0, rc
+    return out, int(status[0])

@@ -173,3 +173,39 @@ def test_k5_grid_tables_match_bruteforce(golden):
     grid3 = eh.recon_grid(g["fx"], g["fy"], g["baselines"], g["test_true"], g["x_t"], vals3, idx3)
     brute3, _ = eh.recon(g["fx"], g["fy"], g["baselines"], g["test_true"], g["x_t"], vals3[idx3])
     assert np.all(np.abs(grid3 - brute3) <= 1e-12 * np.abs(brute3))
+
+
+def _random_fiducials(rng, peaks, L, p_nan=0.15):
+    """plausible fiducial indices around each R peak, with missing entries"""
+    offs = np.array([-100, -125, -75, -12, -20, 22, 15, 125, 90, 170])
+    f = np.asarray(peaks)[None, :] + offs[:, None] + rng.integers(-6, 7, size=(10, len(peaks)))
+    f = np.clip(f, 1, L - 1).astype(np.float64)
+    f[rng.random(f.shape) < p_nan] = np.nan
+    return f
+
+
+def _oracle_row(window, peaks, f):
+    fid = {k: [np.nan if np.isnan(v) else int(v) for v in f[i]] for i, k in enumerate(rp.FIDUCIALS)}
+    return rp.features_row_from_fiducials(window, [int(p) for p in peaks], fid)
+
+
+def test_k6_features_golden_and_oracle(golden):
+    g = golden("features")
+    gf = np.where(g["fiducials"] < 0, np.nan, g["fiducials"])       # the fixture stores np.nan as -1
+    rows, st = eh.fiducial_features(g["window"][None, :], [g["r_peaks"]], [gf])
+    assert st == 0 and same(rows[0], g["row35"])           # frozen from the reference's own three functions
+    rng = np.random.default_rng(5)
+    wins, pks, fids = [], [], []
+    for n_beats in (1, 2, 3, 10, 24, 33, 47, 64, 72):
+        w = rng.standard_normal(10000)
+        p = np.sort(rng.choice(np.arange(150, 9800), n_beats, replace=False))
+        f = _random_fiducials(rng, p, 10000, p_nan=0.3 if n_beats % 2 else 0.1)
+        if n_beats == 10:
+            f[1, :] = np.nan                               # an all-NaN fiducial: NaN medians, nanmax of one side
+            f[4, ::2] = f[4, 1]                            # ties
+        wins.append(w); pks.append(p); fids.append(f)
+    rows, st = eh.fiducial_features(np.stack(wins), pks, fids, valid=[1] * 8 + [0])
+    assert st == 0
+    for i in range(8):
+        assert same(rows[i], _oracle_row(wins[i], pks[i], fids[i])), i
+    assert np.isnan(rows[8]).all()                         # delineation failed: NaN row, window kept
