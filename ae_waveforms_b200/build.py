@@ -23,6 +23,7 @@ PER_FILE = {
     "k3_windows.cu": ["-fmad=false"],
     "k5_recon.cu": [],
     "k6_features.cu": ["-fmad=false"],
+    "k7_delineate.cu": [],
     "k2_filtfilt.cu": [],
     "cabi_misc.cu": [],
 }

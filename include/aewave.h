@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AEW_VERSION 102
+#define AEW_VERSION 103
 
 /* return codes */
 #define AEW_OK 0
@@ -137,6 +137,24 @@ int aew_windows_timing_dump(unsigned long long* h_out16);
 int aew_median_beats_f64(const double* d_windows, long long n_win, int L, const int* d_peaks,
                          const long long* d_peak_off, int max_peaks_per_window, int pre, int post,
                          double* d_median, double* d_aligned, void* stream);
+
+/* ---- K7: wavelet delineation of the beats of a window --------------------------------
+ * replaces nk.ecg_delineate(ecg_sample, r_peaks, sampling_rate=fs)[1] (neurokit2, default method
+ * "dwt") as called at data_extract_vitaldb.py:131, including the wrapper's sanitising and the
+ * caller's validity rules (data_extract_vitaldb.py:130-144).  neurokit2 is not vendored in the
+ * reference and version-unpinned: the kernel follows the restatement in oracle/nk_delineate.py.
+ *   d_sig, d_sig_off  window w's samples are d_sig[d_sig_off[w] .. + L) (the z-scored 'ecg_sample')
+ *   d_peaks           [n_win][max_peaks] R-peak indices, d_n_peaks [n_win]
+ *   d_select          optional [n_win]: only windows with a non-zero entry are processed
+ *   d_fid             [n_win][10][max_peaks] int32 out, order P_Peaks, P_Onsets, P_Offsets, Q_Peaks,
+ *                     R_Onsets, R_Offsets, S_Peaks, T_Peaks, T_Onsets, T_Offsets; AEW_FID_NAN = np.nan
+ *   d_flags           [n_win] out: 0 ok; 1 the library would raise (NaN features, window kept);
+ *                     2 a list would lose an entry (lengths differ -> the caller drops the window) */
+int aew_delineate_blocks(long long n_win);
+size_t aew_delineate_workspace_bytes(long long n_win, int L, double fs);
+int aew_delineate_f64(const double* d_sig, const long long* d_sig_off, long long n_win, int L, double fs,
+                      const int* d_peaks, const int* d_n_peaks, int max_peaks, const unsigned char* d_select,
+                      int* d_fid, unsigned char* d_flags, void* d_ws, size_t ws_bytes, void* stream);
 
 /* ---- K6: the 35 np_features of a window from per-beat fiducial indices ----------------
  * replaces ecg_features_relative_r + compute_ecg_morphology_features

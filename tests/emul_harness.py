@@ -198,3 +198,26 @@ def fiducial_features(windows, peaks_list, fid_list, valid=None, fs=500.0):
                                      ptr(out), ptr(status), None)
     assert rc == 0, rc
     return out, int(status[0])
+
+
+def delineate(windows, peaks_list, fs=500.0, select=None):
+    """K7 on (n, L) windows -> fid (n, 10, max_peaks) int32 (FID_NAN = missing), flags (n,) uint8."""
+    L = lib()
+    w = np.ascontiguousarray(windows, dtype=np.float64)
+    n, Lw = w.shape
+    maxp = L.aew_windows_max_peaks()
+    pk = np.full((n, maxp), -1, np.int32)
+    npk = np.zeros(n, np.int32)
+    for i, p in enumerate(peaks_list):
+        npk[i] = len(p)
+        pk[i, :len(p)] = p
+    off = np.arange(n, dtype=np.int64) * Lw
+    fid = np.zeros((n, 10, maxp), np.int32)
+    flags = np.full(n, 3, np.uint8)
+    wsb = L.aew_delineate_workspace_bytes(n, Lw, float(fs))
+    ws = np.zeros(wsb, np.uint8)
+    sel = None if select is None else np.ascontiguousarray(select, dtype=np.uint8)
+    rc = L.aew_delineate_f64(ptr(w), ptr(off), n, Lw, float(fs), ptr(pk), ptr(npk), maxp, ptr(sel), ptr(fid),
+                             ptr(flags), ptr(ws), wsb, None)
+    assert rc == 0, rc
+    return fid, flags
