@@ -13,6 +13,8 @@ Pipeline of ``Preprocessor.run`` = data_extract_vitaldb.py:53-106 for a batch:
     20 s windows (:85-86)                  window table built on the host (index arithmetic only)
     per-window z-score, R-peaks, screen,
     median beat (:93-106)                  aew_windows_beats_f64       (K3 + K4)
+    wave delineation (:131)                aew_delineate_f64           (K7; nk.ecg_delineate, "dwt")
+    35 features per window (:146-162)      aew_fiducial_features_f64   (K6)
     np_waves / np_info rows                compaction of the kept windows (data_create_arrays.py:41-46)
 """
 from __future__ import annotations
@@ -271,9 +273,58 @@ class Preprocessor:
         out["_win_start"] = d_start
         return out
 
+    def delineate_windows(self, sig, sig_off, peaks, n_peaks, select=None, L=None):
+        """K7: nk.ecg_delineate(window, r_peaks, fs)[1] (data_extract_vitaldb.py:131) for every selected window.
+        ``sig`` flat float64 CUDA tensor, ``sig_off`` int64 CUDA tensor of window offsets into it, ``peaks``
+        (n_win, max_peaks) int32, ``n_peaks`` (n_win,) int32, ``select`` optional uint8 mask.
+        Returns ``fid`` (n_win, 10, max_peaks) int32 (FID_NAN = np.nan) and ``flags`` (n_win,) uint8:
+        0 ok, 1 NaN features / window kept, 2 window dropped, 3 not selected."""
+        torch, lib = self.torch, self.lib
+        L = L or self.L
+        n_win, maxp = int(peaks.shape[0]), int(peaks.shape[1])
+        fid = torch.empty((n_win, 10, maxp), dtype=torch.int32, device=self.device)
+        flags = torch.full((n_win,), 3, dtype=torch.uint8, device=self.device)
+        if n_win == 0:
+            return fid, flags
+        ws_bytes = int(lib.aew_delineate_workspace_bytes(n_win, L, float(self.fs)))
+        ws = getattr(self, "_k7_ws", None)
+        if ws is None or ws.numel() < ws_bytes:
+            ws = self._k7_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+        _cabi.check(lib.aew_delineate_f64(_ptr(sig), _ptr(sig_off), n_win, L, float(self.fs), _ptr(peaks),
+                                          _ptr(n_peaks), maxp, _ptr(select), _ptr(fid), _ptr(flags), _ptr(ws),
+                                          ws.numel(), _cabi.stream_ptr(torch)), "delineate")
+        self.launches += 1
+        return fid, flags
+
+    def fiducial_features(self, sig, sig_off, peaks, n_peaks, fid, valid=None, L=None):
+        """K6: ecg_features_relative_r + compute_ecg_morphology_features + compute_median_features_ecg
+        (data_extract_vitaldb.py:146-162) -> (n_win, 35) float64 in np_features column order."""
+        torch, lib = self.torch, self.lib
+        L = L or self.L
+        n_win, maxp = int(peaks.shape[0]), int(peaks.shape[1])
+        out = torch.empty((n_win, 35), dtype=torch.float64, device=self.device)
+        status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        if n_win:
+            _cabi.check(lib.aew_fiducial_features_f64(_ptr(sig), _ptr(sig_off), n_win, L, _ptr(peaks), _ptr(n_peaks),
+                                                      maxp, _ptr(fid), _ptr(valid), float(self.fs), _ptr(out),
+                                                      _ptr(status), _cabi.stream_ptr(torch)), "fiducial_features")
+            self.launches += 1
+        return out, status
+
+    def window_features(self, zwin_flat, n_win, scr, L=None):
+        """K7 + K6 on the kept windows of a screen result; ``zwin_flat`` holds the z-scored windows back to back.
+        Returns (features (n_win, 35), flags (n_win,))."""
+        torch = self.torch
+        L = L or self.L
+        off = torch.arange(n_win, dtype=torch.int64, device=self.device) * L
+        fid, flags = self.delineate_windows(zwin_flat, off, scr["peaks"], scr["n_peaks"], select=scr["keep"], L=L)
+        valid = (flags == 0).to(torch.uint8)
+        feats, status = self.fiducial_features(zwin_flat, off, scr["peaks"], scr["n_peaks"], fid, valid, L=L)
+        return feats, flags, fid, status
+
     # ------------------------------------------------------------------ whole path
     def run(self, batch: RecordBatch, trim: bool = True, keep_intermediates: bool = False,
-            scratch: dict | None = None) -> dict:
+            scratch: dict | None = None, features: bool = False) -> dict:
         """Returns a dict of CUDA tensors: ``np_waves`` (n_keep, 320) float32,
         ``np_info`` (n_keep, 2) float64 = [case_id, idx_end], ``medians`` float64,
         plus per-window ``keep`` / ``has_nan`` / ``n_peaks`` / ``peaks`` / ``stats`` and
@@ -288,8 +339,17 @@ class Preprocessor:
         info_h = np.stack([win_case.astype(np.float64), win_end.astype(np.float64)], axis=1) if len(win_start) \
             else np.zeros((0, 2))
         info = torch.from_numpy(info_h).to(self.device)             # (uploaded while the filter is still running)
-        scr = self.screen_windows(y, win_start, zwin_scratch=getattr(self, "_filter_tmp", None))
-        keep_idx = torch.nonzero(scr["keep"]).squeeze(1)            # sync: number of kept windows
+        tmp = getattr(self, "_filter_tmp", None)
+        scr = self.screen_windows(y, win_start, zwin_scratch=tmp)
+        keep_mask = scr["keep"]
+        feats = None
+        if features and len(win_start):
+            # the screen kernel parked the z-scored windows ('ecg_sample') back to back in the filter scratch
+            if tmp is None or tmp.numel() < len(win_start) * self.L or tmp.data_ptr() == y.data_ptr():
+                raise _cabi.AewError("features=True needs the filter scratch buffer for the z-scored windows")
+            feats, fl, fid, fstat = self.window_features(tmp, len(win_start), scr)
+            keep_mask = scr["keep"] & (fl != 2).to(torch.uint8)      # list-length rule, data_extract_vitaldb.py:140-144
+        keep_idx = torch.nonzero(keep_mask).squeeze(1)              # sync: number of kept windows
         hdr = header.cpu().numpy()
         _cabi.check_device_status(int(hdr[4]), "filter")
         _cabi.check_device_status(int(scr["status"].item()), "window screen")
@@ -299,6 +359,11 @@ class Preprocessor:
                    n_windows=len(win_start), n_segments=int(hdr[0]), n_tiles=int(hdr[1]),
                    hazard_windows=int(scr["hazards"].item()), mean=mean, sd=sd,
                    n_beats=int(scr["n_peaks"].index_select(0, keep_idx).sum().item()) if len(win_start) else 0)
+        if feats is not None:
+            _cabi.check_device_status(int(fstat.item()), "fiducial features")
+            res.update(np_features=feats.index_select(0, keep_idx), delineation_flags=fl, fiducials=fid)
+        elif features:
+            res.update(np_features=torch.zeros((0, 35), dtype=torch.float64, device=self.device))
         if keep_intermediates:
             res.update(filtered=y, rec_beg=beg_h, rec_end=end_h, win_start=win_start)
         return res
@@ -399,12 +464,12 @@ def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chu
 
 def process_cases(records, case_ids=None, **kwargs) -> dict:
     """Host convenience: list of 1-D float arrays -> NumPy ``np_waves`` (n,320) f32,
-    ``np_features`` (n,35) f64 (NaN: the wave delineator is not on this path yet),
-    ``np_info`` (n,2) f64, in case-major order like data_create_arrays.py:27-48."""
+    ``np_features`` (n,35) f64, ``np_info`` (n,2) f64, in case-major order like
+    data_create_arrays.py:27-48."""
     pre = Preprocessor(**kwargs)
     batch = RecordBatch.from_host(records, case_ids, device=pre.device)
-    res = pre.run(batch)
+    res = pre.run(batch, features=True)
     waves = res["np_waves"].cpu().numpy()
     info = res["np_info"].cpu().numpy()
-    return dict(np_waves=waves, np_features=np.full((len(waves), 35), np.nan), np_info=info,
+    return dict(np_waves=waves, np_features=res["np_features"].cpu().numpy(), np_info=info,
                 n_windows=res["n_windows"], hazard_windows=res["hazard_windows"])

@@ -209,3 +209,38 @@ def test_k6_features_golden_and_oracle(golden):
     for i in range(8):
         assert same(rows[i], _oracle_row(wins[i], pks[i], fids[i])), i
     assert np.isnan(rows[8]).all()                         # delineation failed: NaN row, window kept
+
+
+def _delineation_cases():
+    """(windows, peak lists): three heart rates (wavelet scales 2+d, 3+d for d = 1, 2, 3), too few peaks
+    (the library raises -> NaN row), a peak next to the window start (negative slice bounds -> dropped
+    window) and next to its end (entries >= L blanked)."""
+    wins, pks = [], []
+    for cid, hr in ((12, 52.0), (14, 95.0), (15, 140.0)):
+        out = rp.process_case(ecg_synth.synth_case(cid, 20001, hr_bpm=hr), cid)
+        wins.append(out["windows"][0]); pks.append([int(p) for p in out["peaks"][0]])
+    wins.append(wins[0]); pks.append(pks[0][:3])
+    wins.append(wins[1]); pks.append([20] + [p for p in pks[1] if p > 300])
+    wins.append(wins[0]); pks.append([p for p in pks[0] if p < 9700] + [9990])
+    return wins, pks
+
+
+def test_k7_delineation_matches_restatement():
+    from oracle import nk_delineate as nd
+    wins, pks = _delineation_cases()
+    fid, flags = eh.delineate(np.stack(wins), pks, select=[1, 1, 1, 1, 1, 1])
+    want_flag = {"ok": 0, "nan": 1, "drop": 2}
+    seen = set()
+    for i, (w, p) in enumerate(zip(wins, pks)):
+        st, ref = nd.window_fiducials(w, p)
+        seen.add(st)
+        assert flags[i] == want_flag[st], (i, st, flags[i])
+        if st == "ok":
+            got = fid[i, :, :len(p)].astype(np.float64)
+            got[got == eh.FID_NAN] = np.nan
+            assert same(got, ref), i                       # every fiducial index identical
+            rows, status = eh.fiducial_features(w[None, :], [p], [got])
+            assert status == 0 and same(rows[0], rp.window_features(w, p)[1])
+    assert seen == {"ok", "nan", "drop"}
+    _, fl = eh.delineate(np.stack(wins[:2]), pks[:2], select=[0, 1])
+    assert fl.tolist() == [3, 0]                           # unselected windows are left alone

@@ -452,3 +452,138 @@ def test_empty_and_windowless_batches(gpu):
     pre = B.Preprocessor()
     res = pre.run(B.RecordBatch.from_host([ecg_synth.synth_case(1, 9000), np.full(300, np.nan)], [5, 6]))
     assert res["np_waves"].shape == (0, 320) and res["np_info"].shape == (0, 2) and res["n_windows"] == 0
+
+
+# ------------------------------------------------------------------------- K6 / K7: features
+FID_NAN = -2147483648
+
+
+def _gpu_features(gpu, windows, peaks_list, fids):
+    torch, B = gpu
+    pre = B.Preprocessor()
+    n, L = windows.shape
+    maxp = pre.lib.aew_windows_max_peaks()
+    pk = np.full((n, maxp), -1, np.int32)
+    fid = np.full((n, 10, maxp), FID_NAN, np.int32)
+    for i, (p, f) in enumerate(zip(peaks_list, fids)):
+        pk[i, :len(p)] = p
+        f = np.asarray(f, dtype=np.float64).reshape(10, -1)
+        fid[i, :, :f.shape[1]] = np.where(np.isnan(f), FID_NAN, f).astype(np.int64)
+    dev = pre.device
+    sig = torch.from_numpy(np.ascontiguousarray(windows.reshape(-1))).to(dev)
+    off = torch.arange(n, dtype=torch.int64, device=dev) * L
+    npk = torch.tensor([len(p) for p in peaks_list], dtype=torch.int32, device=dev)
+    out, status = pre.fiducial_features(sig, off, torch.from_numpy(pk).to(dev), npk, torch.from_numpy(fid).to(dev), L=L)
+    return out.cpu().numpy(), int(status.item())
+
+
+def test_fiducial_features_bit_exact(gpu, golden):
+    g = golden("features")
+    gf = np.where(g["fiducials"] < 0, np.nan, g["fiducials"])
+    rows, st = _gpu_features(gpu, g["window"][None, :], [g["r_peaks"]], [gf])
+    assert st == 0 and same(rows[0], g["row35"])            # frozen from the reference's own functions
+    rng = np.random.default_rng(5)
+    wins, pks, fids = [], [], []
+    offs = np.array([-100, -125, -75, -12, -20, 22, 15, 125, 90, 170])
+    for n_beats in (1, 2, 3, 10, 24, 33, 47, 64, 72) * 4:
+        w = rng.standard_normal(10000)
+        p = np.sort(rng.choice(np.arange(150, 9800), n_beats, replace=False))
+        f = np.clip(p[None, :] + offs[:, None] + rng.integers(-6, 7, size=(10, n_beats)), 1, 9999).astype(float)
+        f[rng.random(f.shape) < 0.2] = np.nan
+        if n_beats == 10:
+            f[1, :] = np.nan
+            f[4, ::2] = f[4, 1]
+        wins.append(w); pks.append(p); fids.append(f)
+    rows, st = _gpu_features(gpu, np.stack(wins), pks, fids)
+    assert st == 0
+    for i in range(len(wins)):
+        fid = {k: [np.nan if np.isnan(v) else int(v) for v in fids[i][j]] for j, k in enumerate(rp.FIDUCIALS)}
+        assert same(rows[i], rp.features_row_from_fiducials(wins[i], [int(p) for p in pks[i]], fid)), i
+
+
+def _delineation_cases():
+    wins, pks = [], []
+    for cid, hr in ((11, 38.0), (12, 52.0), (13, 60.0), (14, 95.0), (15, 130.0), (16, 170.0), (17, None)):
+        out = rp.process_case(ecg_synth.synth_case(cid, 50001, hr_bpm=hr), cid)
+        for w, p in zip(out["windows"], out["peaks"]):
+            wins.append(w); pks.append([int(v) for v in p])
+    wins.append(wins[0]); pks.append(pks[0][:3])                                    # the library raises
+    wins.append(wins[1]); pks.append([20] + [p for p in pks[1] if p > 300])         # negative slice bounds
+    wins.append(wins[2]); pks.append([p for p in pks[2] if p < 9700] + [9990])      # entries >= L
+    rng = np.random.default_rng(3)
+    wins.append(rng.standard_normal(10000))                                          # pure noise
+    pks.append(sorted(rng.choice(np.arange(5, 9995, 160), 40, replace=False).tolist()))
+    return wins, pks
+
+
+def test_delineation_matches_restatement(gpu):
+    """K7 against oracle/nk_delineate.py (restatement of neurokit2's DWT delineator; parity unpinned at
+    the library).  Every fiducial index must be identical: the two sides differ by float64 rounding only
+    (chunked spline prefilter, summation order), which can flip an index only at an exact tie."""
+    from oracle import nk_delineate as nd
+    torch, B = gpu
+    wins, pks = _delineation_cases()
+    pre = B.Preprocessor()
+    n, L, dev = len(wins), 10000, pre.device
+    maxp = pre.lib.aew_windows_max_peaks()
+    pk = np.full((n, maxp), -1, np.int32)
+    for i, p in enumerate(pks):
+        pk[i, :len(p)] = p
+    sig = torch.from_numpy(np.ascontiguousarray(np.stack(wins).reshape(-1))).to(dev)
+    off = torch.arange(n, dtype=torch.int64, device=dev) * L
+    d_pk = torch.from_numpy(pk).to(dev)
+    npk = torch.tensor([len(p) for p in pks], dtype=torch.int32, device=dev)
+    fid, flags = pre.delineate_windows(sig, off, d_pk, npk)
+    feats, st = pre.fiducial_features(sig, off, d_pk, npk, fid, (flags == 0).to(torch.uint8))
+    fid, flags, feats = fid.cpu().numpy(), flags.cpu().numpy(), feats.cpu().numpy()
+    assert int(st.item()) == 0
+    want_flag = {"ok": 0, "nan": 1, "drop": 2}
+    total = 0
+    for i, (w, p) in enumerate(zip(wins, pks)):
+        status, ref = nd.window_fiducials(w, p)
+        assert flags[i] == want_flag[status], (i, status, flags[i])
+        if status == "ok":
+            got = fid[i, :, :len(p)].astype(np.float64)
+            got[got == FID_NAN] = np.nan
+            assert same(got, ref), i
+            assert same(feats[i], rp.window_features(w, p)[1]), i
+            total += ref.size
+        else:
+            assert np.isnan(feats[i]).all()
+    assert total > 5000
+
+
+def test_pipeline_with_features_exact_filter(gpu):
+    """np_waves, np_features, np_info of the whole path (exact filter mode) against the oracle's process_case."""
+    torch, B = gpu
+    cases = [ecg_synth.synth_case(c, 120000 + 977 * c, hr_bpm=hr, nan_gaps=g)
+             for c, hr, g in ((0, None, 0), (1, 58.0, 0), (2, 118.0, 1), (3, None, 2))]
+    refs = [rp.process_case(c, case_id=i, features=True) for i, c in enumerate(cases)]
+    res = B.Preprocessor(filter_mode="exact").run(B.RecordBatch.from_host(cases, list(range(len(cases)))),
+                                                  features=True)
+    assert same(res["np_info"].cpu().numpy(), np.concatenate([r["np_info"] for r in refs]))
+    assert same(res["np_waves"].cpu().numpy(), np.concatenate([r["np_waves"] for r in refs]))
+    assert same(res["np_features"].cpu().numpy(), np.concatenate([r["np_features"] for r in refs]))
+    assert res["np_features"].shape[1] == 35 and res["np_features"].shape[0] > 15
+    fast = B.process_cases(cases, list(range(len(cases))))
+    ref_f = np.concatenate([r["np_features"] for r in refs])
+    assert fast["np_features"].shape == ref_f.shape
+    # fast filter: windows differ by ~1e-9, so a fiducial may move by a sample in rare windows; the medians
+    # over beats must still agree closely almost everywhere
+    ok = np.isclose(fast["np_features"], ref_f, rtol=1e-6, atol=1e-6, equal_nan=True)
+    assert ok.mean() > 0.97
+
+
+def test_neurokit_shim(gpu):
+    from ae_waveforms_b200 import neurokit_shim as nk
+    from oracle import nk_delineate as nd
+    out = rp.process_case(ecg_synth.synth_case(21, 30001, hr_bpm=72.0), 21)
+    w, p = out["windows"][0], [int(v) for v in out["peaks"][0]]
+    got = nk.ecg_delineate(w, p, sampling_rate=500)[1]
+    want = nd.ecg_delineate(w, p, 500)
+    assert list(got) == nd.KEYS
+    for k in nd.KEYS:
+        assert len(got[k]) == len(want[k])
+        assert all((a is np.nan and b is np.nan) or a == b for a, b in zip(got[k], want[k])), k
+    with pytest.raises(ValueError):
+        nk.ecg_delineate(w, p[:3], sampling_rate=500)
