@@ -25,12 +25,13 @@
 // restatement's by rounding only (chunked prefilter, summation order), so indices can differ only
 // where a comparison is within ~1e-15 of a tie.
 #include "aew_rt.h"
+#include "aew_pairwise.cuh"
 #include <math.h>
 
 #define K7_THREADS 256
 #define K7_WARPS (K7_THREADS / 32)
 #define K7_MAXP 72
-#define K7_TAIL 512            // low-pass cascade is evaluated this far past the end of the 2 kHz signal
+#define K7_TILE 5120           // positions per shared-memory tile of the cascade (two buffers: 80 KB)
 #define K7_RUNIN 32
 #define K7_NANI (-0x7fffffffffffffffLL - 1)
 #define K7_RATE 2000.0
@@ -38,8 +39,13 @@
 namespace {
 
 struct K7Scratch {
-  double *coef, *e2k, *ta, *tb, *wa, *wb;
+  double *coef, *cplus, *e2k, *wa, *wb;
 };
+
+#define MUL(a, b) __dmul_rn((a), (b))
+#define ADD(a, b) __dadd_rn((a), (b))
+#define SUB(a, b) __dsub_rn((a), (b))
+#define DIV(a, b) __ddiv_rn((a), (b))
 
 __device__ __forceinline__ double warp_sum(double v) {
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(AEW_FULL, v, o);
@@ -277,6 +283,31 @@ __device__ __forceinline__ int int_log2(double x) {
   return m == 0.5 ? fl : fl + 1;          // truncation toward zero for negative logarithms
 }
 
+// 60 / period at sample i of the window: scipy PPoly evaluation of the PCHIP through (peak, period), constant
+// outside the first / last peak (signal_interpolate's out-of-bounds rule), NumPy's operation order
+struct RateAt {
+  const int* pk;
+  const double (*c)[K7_MAXP];
+  int nb;
+  __device__ __forceinline__ double operator()(long long i, bool) const {
+    const int p_first = pk[0], p_last = pk[nb - 1];
+    const int xe = i < p_first ? p_first : (i > p_last ? p_last : (int)i);
+    int lo = 0, hi = nb - 2;                     // interval k with pk[k] <= xe < pk[k+1] (last knot: nb - 2)
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (pk[mid] <= xe) lo = mid; else hi = mid - 1;
+    }
+    const double s = (double)(xe - pk[lo]);
+    double res = c[3][lo], z = s;
+    res = ADD(res, MUL(c[2][lo], z));
+    z = MUL(z, s);
+    res = ADD(res, MUL(c[1][lo], z));
+    z = MUL(z, s);
+    res = ADD(res, MUL(c[0][lo], z));
+    return DIV(60.0, res);
+  }
+};
+
 // ------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(K7_THREADS)
 k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ sig_off, long long n_win, int L,
@@ -287,18 +318,18 @@ k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ s
   __shared__ long long s_r2k[K7_MAXP];
   __shared__ double s_y[K7_MAXP], s_d[K7_MAXP], s_c[4][K7_MAXP];
   __shared__ double s_red[K7_WARPS];
+  __shared__ double s_vals[128];               // leaf slots of np.mean's pairwise tree (L <= 16,384)
+  __shared__ unsigned char s_valid[128];
   __shared__ double s_par[8];
   __shared__ int s_ipar[4];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   K7Scratch S;
   {
     double* base = scratch + (long long)blockIdx.x * scratch_stride;
-    const long long np_ = n2k + K7_TAIL;
     S.coef = base;
-    S.e2k = S.coef + ((L + 7) & ~7);
-    S.ta = S.e2k + ((n2k + 7) & ~7LL);
-    S.tb = S.ta + ((np_ + 7) & ~7LL);
-    S.wa = S.tb + ((np_ + 7) & ~7LL);
+    S.cplus = S.coef + ((L + 7) & ~7);
+    S.e2k = S.cplus + ((L + 7) & ~7);
+    S.wa = S.e2k + ((n2k + 7) & ~7LL);
     S.wb = S.wa + ((n2k + 7) & ~7LL);
   }
   const double zp = sqrt(3.0) - 2.0;             // pole of the cubic B-spline prefilter
@@ -322,28 +353,31 @@ k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ s
     }
     __syncthreads();
 
-    // ---- A: mean heart rate (signal_rate with desired_length = L) and median rate at 2 kHz
-    if (tid >= 1 && tid < nb) s_y[tid] = (double)(s_pk[tid] - s_pk[tid - 1]) / fs;
+    // ---- A: mean heart rate (signal_rate with desired_length = L) and median rate at 2 kHz.
+    // Bit-identical to NumPy / SciPy (explicit round-to-nearest operations in their order, np.mean's
+    // pairwise tree): the epoch labels below hit 0.0 EXACTLY whenever 0.35 (n - 1) is an integer, so the
+    // slice decisions depend on the last bit of this mean.
+    if (tid >= 1 && tid < nb) s_y[tid] = DIV((double)(s_pk[tid] - s_pk[tid - 1]), fs);
     __syncthreads();
-    if (tid == 0) s_y[0] = np_sum_small(s_y + 1, nb - 1) / (double)(nb - 1);
+    if (tid == 0) s_y[0] = DIV(np_sum_small(s_y + 1, nb - 1), (double)(nb - 1));
     __syncthreads();
-    if (tid < nb) {                               // PCHIP end-point and interior derivatives
+    if (tid < nb) {                               // PCHIP end-point and interior derivatives (scipy _find_derivatives)
       const int i = tid;
       double d;
       if (i == 0 || i == nb - 1) {
         const int k0 = i == 0 ? 0 : nb - 2, k1 = i == 0 ? 1 : nb - 3;
         const double h0 = (double)(s_pk[k0 + 1] - s_pk[k0]), h1 = (double)(s_pk[k1 + 1] - s_pk[k1]);
-        const double m0 = (s_y[k0 + 1] - s_y[k0]) / h0, m1 = (s_y[k1 + 1] - s_y[k1]) / h1;
-        d = ((2.0 * h0 + h1) * m0 - h0 * m1) / (h0 + h1);
+        const double m0 = DIV(SUB(s_y[k0 + 1], s_y[k0]), h0), m1 = DIV(SUB(s_y[k1 + 1], s_y[k1]), h1);
+        d = DIV(SUB(MUL(ADD(MUL(2.0, h0), h1), m0), MUL(h0, m1)), ADD(h0, h1));
         if (sgn(d) != sgn(m0)) d = 0.0;
-        else if (sgn(m0) != sgn(m1) && fabs(d) > 3.0 * fabs(m0)) d = 3.0 * m0;
+        else if (sgn(m0) != sgn(m1) && fabs(d) > MUL(3.0, fabs(m0))) d = MUL(3.0, m0);
       } else {
         const double h0 = (double)(s_pk[i] - s_pk[i - 1]), h1 = (double)(s_pk[i + 1] - s_pk[i]);
-        const double m0 = (s_y[i] - s_y[i - 1]) / h0, m1 = (s_y[i + 1] - s_y[i]) / h1;
+        const double m0 = DIV(SUB(s_y[i], s_y[i - 1]), h0), m1 = DIV(SUB(s_y[i + 1], s_y[i]), h1);
         if (sgn(m0) != sgn(m1) || m0 == 0.0 || m1 == 0.0) d = 0.0;
         else {
-          const double w1 = 2.0 * h1 + h0, w2 = h1 + 2.0 * h0;
-          d = 1.0 / ((w1 / m0 + w2 / m1) / (w1 + w2));
+          const double w1 = ADD(MUL(2.0, h1), h0), w2 = ADD(h1, MUL(2.0, h0));
+          d = DIV(1.0, DIV(ADD(DIV(w1, m0), DIV(w2, m1)), ADD(w1, w2)));
         }
       }
       s_d[i] = d;
@@ -351,52 +385,35 @@ k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ s
     __syncthreads();
     if (tid < nb - 1) {                           // CubicHermiteSpline coefficients, power basis at the left knot
       const double dx = (double)(s_pk[tid + 1] - s_pk[tid]);
-      const double slope = (s_y[tid + 1] - s_y[tid]) / dx;
-      const double t = (s_d[tid] + s_d[tid + 1] - 2.0 * slope) / dx;
-      s_c[0][tid] = t / dx;
-      s_c[1][tid] = (slope - s_d[tid]) / dx - t;
+      const double slope = DIV(SUB(s_y[tid + 1], s_y[tid]), dx);
+      const double t = DIV(SUB(ADD(s_d[tid], s_d[tid + 1]), MUL(2.0, slope)), dx);
+      s_c[0][tid] = DIV(t, dx);
+      s_c[1][tid] = SUB(DIV(SUB(slope, s_d[tid]), dx), t);
       s_c[2][tid] = s_d[tid];
       s_c[3][tid] = s_y[tid];
     }
     __syncthreads();
     {
-      double acc = 0.0;
-      const int p_first = s_pk[0], p_last = s_pk[nb - 1];
-      for (int x = tid; x < L; x += K7_THREADS) {
-        int xe = x < p_first ? p_first : (x > p_last ? p_last : x);
-        int lo = 0, hi = nb - 2;                  // interval k with pk[k] <= xe < pk[k+1] (last knot: nb-2)
-        while (lo < hi) {
-          const int mid = (lo + hi + 1) >> 1;
-          if (s_pk[mid] <= xe) lo = mid; else hi = mid - 1;
-        }
-        const double s = (double)(xe - s_pk[lo]);
-        double res = s_c[3][lo], z = s;
-        res = res + s_c[2][lo] * z;
-        z *= s;
-        res = res + s_c[1][lo] * z;
-        z *= s;
-        res = res + s_c[0][lo] * z;
-        acc += 60.0 / res;
-      }
-      acc = warp_sum(acc);
-      if (lane == 0) s_red[warp] = acc;
+      RateAt f{s_pk, s_c, nb};
+      const double tot = pw_block_sum(f, L, pw_depth(L), s_vals, s_valid);   // np.mean's summation order
+      if (tid == 0) s_red[0] = tot;
     }
     __syncthreads();
     if (warp == 0) {
-      // median of 60 / period at 2 kHz (np.median; first period = mean of the others)
+      // median of 60 / period at 2 kHz (np.median; first period = mean of the others);
       // s_d becomes the period list (the PCHIP derivatives are consumed)
       for (int i = lane; i < nb; i += 32)
-        if (i > 0) s_d[i] = (double)(s_r2k[i] - s_r2k[i - 1]) / K7_RATE;
+        if (i > 0) s_d[i] = DIV((double)(s_r2k[i] - s_r2k[i - 1]), K7_RATE);
       __syncwarp();
-      if (lane == 0) s_d[0] = np_sum_small(s_d + 1, nb - 1) / (double)(nb - 1);
+      if (lane == 0) s_d[0] = DIV(np_sum_small(s_d + 1, nb - 1), (double)(nb - 1));
       __syncwarp();
       double lo_v = 0.0, hi_v = 0.0;
       const int klo = (nb - 1) >> 1, khi = nb >> 1;
       for (int i = lane; i < nb; i += 32) {
-        const double v = 60.0 / s_d[i];
+        const double v = DIV(60.0, s_d[i]);
         int rank = 0;
         for (int j = 0; j < nb; ++j) {
-          const double u = 60.0 / s_d[j];
+          const double u = DIV(60.0, s_d[j]);
           rank += (u < v) || (u == v && j < i);
         }
         if (rank == klo) lo_v = v;
@@ -405,19 +422,18 @@ k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ s
       lo_v = warp_sum(lo_v);                       // exactly one lane holds each (others add 0)
       hi_v = warp_sum(hi_v);
       if (lane == 0) {
-        double tot = 0.0;
-        for (int k = 0; k < K7_WARPS; ++k) tot += s_red[k];
-        const double heart_rate = tot / (double)L;
-        const double window_size = 60.0 / heart_rate;
-        s_par[0] = -(0.35 * window_size);          // epochs_start
-        s_par[1] = (1.0 - 0.35) * window_size;     // epochs_end
-        const double avg = klo == khi ? lo_v : (lo_v + hi_v) / 2.0;
-        const int deg = int_log2((K7_RATE / 250.0) / (avg / 60.0));
+        const double heart_rate = DIV(s_red[0], (double)L);
+        const double window_size = DIV(60.0, heart_rate);
+        s_par[0] = -MUL(0.35, window_size);        // epochs_start
+        s_par[1] = MUL(SUB(1.0, 0.35), window_size);   // epochs_end
+        const double avg = klo == khi ? lo_v : DIV(ADD(lo_v, hi_v), 2.0);
+        const double beat = DIV(60.0, avg);
+        const int deg = int_log2(DIV(DIV(K7_RATE, 250.0), DIV(avg, 60.0)));
         s_ipar[0] = deg;
-        s_par[2] = k7_round3(0.2 * (60.0 / avg));  // p2r_duration
-        s_par[3] = k7_round3(0.25 * (60.0 / avg)); // rt_duration
-        s_par[4] = k7_round3(0.3 * (60.0 / avg));  // duration_onset / duration_offset
-        s_par[5] = k7_round3(0.6 * (60.0 / avg));  // T duration_onset
+        s_par[2] = k7_round3(MUL(0.2, beat));      // p2r_duration
+        s_par[3] = k7_round3(MUL(0.25, beat));     // rt_duration
+        s_par[4] = k7_round3(MUL(0.3, beat));      // duration_onset / duration_offset
+        s_par[5] = k7_round3(MUL(0.6, beat));      // T duration_onset
         s_ipar[1] = (isnan(avg) || isnan(heart_rate) || deg < 0 || deg > 5) ? 1 : 0;   // rows 2+d, 3+d of 9
       }
     }
@@ -430,23 +446,23 @@ k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ s
     // ---- B: Q and S peaks (warp per beat) on the signal at fs
     {
       const double start_s = s_par[0], end_s = s_par[1];
-      const long long buf = (long long)((end_s - start_s) * fs);
+      const long long buf = (long long)MUL(SUB(end_s, start_s), fs);
       int bad = 0;
       for (int b = warp; b < nb; b += K7_WARPS) {
         const long long r = s_pk[b];
-        const long long ea = (long long)((double)(r + buf) + start_s * fs);
-        const long long eb = (long long)((double)(r + buf) + end_s * fs);
+        const long long ea = (long long)ADD((double)(r + buf), MUL(start_s, fs));
+        const long long eb = (long long)ADD((double)(r + buf), MUL(end_s, fs));
         const long long n = eb - ea;
         long long n_left = 0, right0 = 0;
         if (n >= 2) {                              // labels = np.linspace(start_s, end_s, n)
-          const double step = (end_s - start_s) / (double)(n - 1);
+          const double step = DIV(SUB(end_s, start_s), (double)(n - 1));
           long long j = (long long)floor(-start_s / step);
           if (j > n - 2) j = n - 2;
           if (j < 0) j = 0;
-          while (j + 1 <= n - 2 && (double)(j + 1) * step + start_s <= 0.0) ++j;
-          while (j >= 0 && (double)j * step + start_s > 0.0) --j;
+          while (j + 1 <= n - 2 && ADD(MUL((double)(j + 1), step), start_s) <= 0.0) ++j;
+          while (j >= 0 && ADD(MUL((double)j, step), start_s) > 0.0) --j;
           n_left = j + 1;                          // the last label is end_s > 0
-          right0 = n_left - ((j >= 0 && (double)j * step + start_s == 0.0) ? 1 : 0);
+          right0 = n_left - ((j >= 0 && ADD(MUL((double)j, step), start_s) == 0.0) ? 1 : 0);
         } else {
           n_left = n;                              // no label above 0 -> np.min([]) raises
         }
@@ -467,11 +483,11 @@ k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ s
       }
     }
 
-    // ---- C: cubic-spline resampling to 2 kHz (scipy.ndimage.zoom, order 3, mirror prefilter)
+    // ---- C: cubic B-spline coefficients of the window (scipy.ndimage.zoom, order 3, mirror prefilter)
     {
       const int ch = (L + K7_THREADS - 1) / K7_THREADS;
       const int c0 = tid * ch, c1 = c0 + ch < L ? c0 + ch : L;
-      double* cplus = S.ta;
+      double* cplus = S.cplus;
       if (c0 < c1) {
         double c = 0.0;
         for (int i = c0 - K7_RUNIN; i < c1; ++i) {
@@ -499,72 +515,93 @@ k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ s
         }
       }
       __syncthreads();
-      const double ratio = (double)(L - 1) / (double)(n2k - 1);
-      for (long long j = tid; j < n2k; j += K7_THREADS) {
-        const double cc = (double)j * ratio;
-        const double fl = floor(cc);
-        const double y = cc - fl, z = 1.0 - y;
-        const double w1 = (y * y * (y - 2.0) * 3.0 + 4.0) / 6.0;
-        const double w2 = (z * z * (z - 2.0) * 3.0 + 4.0) / 6.0;
-        const double w0 = z * z * z / 6.0;
-        const double w3 = 1.0 - w0 - w1 - w2;
-        const int i0 = (int)fl - 1;
-        double t = 0.0;
-#pragma unroll
-        for (int hh = 0; hh < 4; ++hh) {
-          int idx = i0 + hh;
-          if (idx < 0) idx = -idx;
-          if (idx >= L) idx = 2 * L - 2 - idx;
-          t += S.coef[idx] * (hh == 0 ? w0 : hh == 1 ? w1 : hh == 2 ? w2 : w3);
-        }
-        S.e2k[j] = t;
-      }
-      __syncthreads();
     }
 
-    // ---- D: a-trous cascade; rows qa = 2 + d and qb = 3 + d
+    // ---- D: 2 kHz samples and the a-trous cascade, tile by tile in shared memory.  A tile holds K7_TILE
+    // consecutive positions of every level; level p is valid 2 * 2^p less far to the left and 2^p less far to
+    // the right than level p - 1, so the halo is sized for the rows qa = 2 + d and qb = 3 + d that are kept.
     {
+      AEW_DYN_SMEM(dyn);
+      double* bufs[2] = {reinterpret_cast<double*>(dyn), reinterpret_cast<double*>(dyn) + K7_TILE};
       const int deg = s_ipar[0];
       const int qa = 2 + deg, qb = 3 + deg;
-      const long long np_ = n2k + K7_TAIL;
-      const double* prev = S.e2k;
-      long long len_prev = n2k;                    // true length of the previous level (it grows by 3 * 2^p)
-      long long av_prev = n2k;                     // entries of it that are stored (cut at n2k + K7_TAIL: enough)
-      for (int p = 0; p <= qa; ++p) {
-        const long long d = 1LL << p;
-        if (p == qa) {                             // row qa = G_qa(T_{qa-1})
-          const long long dq = 1LL << qa;
-          for (long long n = tid; n < n2k; n += K7_THREADS) {
-            const double ahead = n + dq < av_prev ? prev[n + dq] : 0.0;
-            S.wa[n] = 2.0 * ahead - 2.0 * prev[n];
-          }
-        }
-        double* cur = (p & 1) ? S.tb : S.ta;
-        const long long len_cur = len_prev + 3 * d;
-        const long long shifted = len_cur - d;
-        const long long upto = len_cur < np_ ? len_cur : np_;
-        for (long long n = tid; n < upto; n += K7_THREADS) {
-          const long long m = n < shifted ? n + d : n;
-          double acc = 0.0;
+      const int halo_l = 2 * ((1 << (qa + 1)) - 1), halo_r = (1 << (qa + 2)) - 1;
+      const int ts = K7_TILE - halo_l - halo_r;
+      const double ratio = (double)(L - 1) / (double)(n2k - 1);
+      const long long dqa = 1LL << qa, dqb = 1LL << qb;
+      for (long long t0 = 0; t0 < n2k; t0 += ts) {
+        const long long base = t0 - halo_l;
+        const long long t1 = t0 + ts < n2k ? t0 + ts : n2k;
+        double* prev = bufs[0];
+        double* cur = bufs[1];
+        for (int i = tid; i < K7_TILE; i += K7_THREADS) {   // level -1: the resampled signal
+          const long long j = base + i;
+          double t = 0.0;
+          if (j >= 0 && j < n2k) {
+            const double cc = (double)j * ratio;
+            const double fl = floor(cc);
+            const double y = cc - fl, z = 1.0 - y;
+            const double w1 = (y * y * (y - 2.0) * 3.0 + 4.0) / 6.0;
+            const double w2 = (z * z * (z - 2.0) * 3.0 + 4.0) / 6.0;
+            const double w0 = z * z * z / 6.0;
+            const double w3 = 1.0 - w0 - w1 - w2;
+            const int i0 = (int)fl - 1;
+            if (i0 >= 0 && i0 + 3 < L) {
+              t = S.coef[i0] * w0;
+              t += S.coef[i0 + 1] * w1;
+              t += S.coef[i0 + 2] * w2;
+              t += S.coef[i0 + 3] * w3;
+            } else {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const long long x = m - k * d;
-            const double v = (x >= 0 && x < av_prev) ? prev[x] : 0.0;
-            acc += ((k == 0 || k == 3) ? 0.125 : 0.375) * v;
+              for (int hh = 0; hh < 4; ++hh) {
+                int idx = i0 + hh;
+                if (idx < 0) idx = -idx;
+                if (idx >= L) idx = 2 * L - 2 - idx;
+                t += S.coef[idx] * (hh == 0 ? w0 : hh == 1 ? w1 : hh == 2 ? w2 : w3);
+              }
+            }
+            if (j >= t0 && j < t1) S.e2k[j] = t;
           }
-          cur[n] = acc;
+          prev[i] = t;
         }
         __syncthreads();
-        prev = cur;
-        len_prev = len_cur;
-        av_prev = upto;                            // entries past np_ are never needed (look-ahead < 2^(qb+1) <= 512)
+        long long len_prev = n2k;                  // true length of the previous level (it grows by 3 * 2^p)
+        for (int p = 0; p <= qa; ++p) {
+          const int d = 1 << p;
+          if (p == qa) {                           // row qa = G_qa(T_{qa-1})
+            for (long long n = t0 + tid; n < t1; n += K7_THREADS) {
+              const double ahead = n + dqa < len_prev ? prev[n + dqa - base] : 0.0;
+              S.wa[n] = 2.0 * ahead - 2.0 * prev[n - base];
+            }
+          }
+          const long long len_cur = len_prev + 3 * d;
+          const long long shifted = len_cur - d;
+          for (int i = tid; i < K7_TILE; i += K7_THREADS) {
+            const long long n = base + i;
+            double acc = 0.0;
+            if (n >= 0 && n < len_cur) {
+              const long long m = n < shifted ? n + d : n;
+              const int im = (int)(m - base);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int ix = im - k * d;
+                const long long x = m - (long long)k * d;
+                const double v = (ix >= 0 && ix < K7_TILE && x >= 0 && x < len_prev) ? prev[ix] : 0.0;
+                acc += ((k == 0 || k == 3) ? 0.125 : 0.375) * v;
+              }
+            }
+            cur[i] = acc;
+          }
+          __syncthreads();
+          double* sw = prev; prev = cur; cur = sw;
+          len_prev = len_cur;
+        }
+        for (long long n = t0 + tid; n < t1; n += K7_THREADS) {    // row qb = G_qb(T_qa)
+          const double ahead = n + dqb < len_prev ? prev[n + dqb - base] : 0.0;
+          S.wb[n] = 2.0 * ahead - 2.0 * prev[n - base];
+        }
+        __syncthreads();
       }
-      const long long dq = 1LL << qb;
-      for (long long n = tid; n < n2k; n += K7_THREADS) {
-        const double ahead = n + dq < av_prev ? prev[n + dq] : 0.0;
-        S.wb[n] = 2.0 * ahead - 2.0 * prev[n];
-      }
-      __syncthreads();
     }
 
     // ---- E: per-beat searches at 2 kHz (warp per beat)
@@ -625,10 +662,7 @@ extern "C" int aew_delineate_blocks(long long n_win) {
 
 static long long k7_n2k(int L, double fs) { return (long long)rint((double)L * K7_RATE / fs); }
 
-static long long k7_stride(int L, long long n2k) {
-  const long long np_ = n2k + K7_TAIL;
-  return ((L + 7) & ~7) + 3 * ((n2k + 7) & ~7LL) + 2 * ((np_ + 7) & ~7LL);
-}
+static long long k7_stride(int L, long long n2k) { return 2 * ((L + 7) & ~7) + 3 * ((n2k + 7) & ~7LL); }
 
 extern "C" size_t aew_delineate_workspace_bytes(long long n_win, int L, double fs) {
   if (L <= 0 || !(fs > 0)) return 0;
@@ -639,14 +673,16 @@ extern "C" int aew_delineate_f64(const double* d_sig, const long long* d_sig_off
                                  const int* d_peaks, const int* d_n_peaks, int max_peaks,
                                  const unsigned char* d_select, int* d_fid, unsigned char* d_flags, void* d_ws,
                                  size_t ws_bytes, void* stream) {
-  if (n_win < 0 || L < 64 || max_peaks <= 0 || max_peaks > K7_MAXP || !(fs > 0)) return AEW_ERR_ARG;
+  if (n_win < 0 || L < 64 || L > 16384 || max_peaks <= 0 || max_peaks > K7_MAXP || !(fs > 0)) return AEW_ERR_ARG;
   if (n_win == 0) return AEW_OK;
   if (!d_sig || !d_sig_off || !d_peaks || !d_n_peaks || !d_fid || !d_flags || !d_ws) return AEW_ERR_ARG;
   if (ws_bytes < aew_delineate_workspace_bytes(n_win, L, fs)) return AEW_ERR_WORKSPACE;
   const long long n2k = k7_n2k(L, fs);
   if (n2k < 4 || n2k > (1LL << 30)) return AEW_ERR_UNSUPPORTED;
   double* ws = (double*)(((uintptr_t)d_ws + 127) & ~(uintptr_t)127);
-  AEW_LAUNCH(k7_delineate, (unsigned)aew_delineate_blocks(n_win), K7_THREADS, 0, stream, d_sig, d_sig_off, n_win, L,
+  const size_t smem = 2 * K7_TILE * sizeof(double);
+  if (AEW_SET_MAX_SMEM(k7_delineate, smem) != 0) return AEW_ERR_UNSUPPORTED;
+  AEW_LAUNCH(k7_delineate, (unsigned)aew_delineate_blocks(n_win), K7_THREADS, smem, stream, d_sig, d_sig_off, n_win, L,
              n2k, fs, d_peaks, d_n_peaks, max_peaks, d_select, d_fid, d_flags, ws, k7_stride(L, n2k));
   return (int)cudaGetLastError();
 }

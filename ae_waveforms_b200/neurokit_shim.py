@@ -40,3 +40,19 @@ def ecg_delineate(ecg_cleaned, rpeaks=None, sampling_rate=1000, method="dwt", **
     f = fid[0, :, :len(rpeaks)].cpu().numpy()
     waves = {k: [np.nan if v == FID_NAN else int(v) for v in f[i]] for i, k in enumerate(KEYS)}
     return None, {k: [x for x in v if x > 0 or x is np.nan] for k, v in waves.items()}
+
+
+def ecg_findpeaks(ecg_cleaned, sampling_rate=1000, method="neurokit", **kwargs):
+    """``nk.ecg_findpeaks(x, sampling_rate)["ECG_R_Peaks"]`` (remove_samples.py:50-51) on the window kernel
+    (K3): gradient-energy QRS runs, most prominent maximum per run, 0.3 s refractory."""
+    if method != "neurokit":
+        raise _cabi.AewError("only the default 'neurokit' method is implemented")
+    torch, _ = _cabi.require_cuda()
+    sig = np.ascontiguousarray(ecg_cleaned, dtype=np.float64)
+    L = len(sig)
+    pre = Preprocessor(fs=sampling_rate, sample_length=L / sampling_rate)
+    scr = pre.screen_windows(torch.from_numpy(sig).to(pre.device), np.zeros(1, np.int64), want_median=False,
+                             zscore_windows=False, L=L)
+    _cabi.check_device_status(int(scr["status"].item()), "ecg_findpeaks")
+    n = int(scr["n_peaks"][0].item())
+    return {"ECG_R_Peaks": scr["peaks"][0, :n].cpu().numpy().astype(np.int64)}

@@ -25,7 +25,8 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), f"{name} declared in aewave.h but not exported"
     assert sorted(_cabi.SIGNATURES) == names, "ctypes prototypes and header out of sync"
-    assert lib.aew_version() == 101
+    want = int(re.search(r"#define AEW_VERSION (\d+)", open(os.path.join(ROOT, "include", "aewave.h")).read()).group(1))
+    assert lib.aew_version() == want
 
 
 def test_sass_is_sm100a_only():

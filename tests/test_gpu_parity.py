@@ -503,7 +503,8 @@ def test_fiducial_features_bit_exact(gpu, golden):
 
 def _delineation_cases():
     wins, pks = [], []
-    for cid, hr in ((11, 38.0), (12, 52.0), (13, 60.0), (14, 95.0), (15, 130.0), (16, 170.0), (17, None)):
+    for cid, hr in ((11, 38.0), (12, 52.0), (13, 60.0), (14, 95.0), (15, 130.0), (16, 170.0), (17, None),
+                    (18, 57.7), (19, 62.5), (20, 60.0), (21, 60.0)):   # 0.35 (n - 1) integral: an epoch label is exactly 0
         out = rp.process_case(ecg_synth.synth_case(cid, 50001, hr_bpm=hr), cid)
         for w, p in zip(out["windows"], out["peaks"]):
             wins.append(w); pks.append([int(v) for v in p])
@@ -587,3 +588,6 @@ def test_neurokit_shim(gpu):
         assert all((a is np.nan and b is np.nan) or a == b for a, b in zip(got[k], want[k])), k
     with pytest.raises(ValueError):
         nk.ecg_delineate(w, p[:3], sampling_rate=500)
+    from oracle import nk_peaks
+    assert nk.ecg_findpeaks(w, sampling_rate=500)["ECG_R_Peaks"].tolist() == \
+        [int(v) for v in nk_peaks.ecg_findpeaks(w, sampling_rate=500)["ECG_R_Peaks"] if 0 < v < len(w)]
