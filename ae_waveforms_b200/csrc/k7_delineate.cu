@@ -92,16 +92,16 @@ __device__ __forceinline__ int sgn(double v) { return (v > 0.0) - (v < 0.0); }
 struct Epoch {
   const double* sig;
   int L;
-  long long s0;
-  __device__ __forceinline__ double at(long long j) const {   // epoch sample j; 0 outside the signal (buffer)
-    const long long i = s0 + j;
-    return (i < 0 || i >= L) ? 0.0 : sig[i];
+  int s0;
+  __device__ __forceinline__ double at(int j) const {         // epoch sample j; 0 outside the signal (buffer)
+    const int i = s0 + j;
+    return (unsigned)i < (unsigned)L ? sig[i] : 0.0;
   }
 };
 
 // local maximum of x = -E over the segment [lo, lo + len) at position i (plateau start); returns the
 // plateau's middle or -1 (scipy _local_maxima_1d)
-__device__ __forceinline__ int seg_peak(const Epoch& e, long long lo, int len, int i) {
+__device__ __forceinline__ int seg_peak(const Epoch& e, int lo, int len, int i) {
   if (i < 1 || i > len - 2) return -1;
   const double x = -e.at(lo + i);
   if (!(-e.at(lo + i - 1) < x)) return -1;
@@ -111,25 +111,33 @@ __device__ __forceinline__ int seg_peak(const Epoch& e, long long lo, int len, i
   return (i + ahead - 1) / 2;
 }
 
-__device__ __forceinline__ double seg_prominence(const Epoch& e, long long lo, int len, int p) {
+// scipy peak_prominences (wlen = None) of the peak p of x = -E, evaluated by the whole warp: 32 samples per
+// step in each direction up to the first one that is higher than the peak (or the segment's end)
+__device__ double seg_prominence(const Epoch& e, int lo, int len, int p, int lane) {
   const double xp = -e.at(lo + p);
   double lmin = xp, rmin = xp;
-  for (int i = p; i >= 0; --i) {
-    const double v = -e.at(lo + i);
-    if (!(v <= xp)) break;
-    if (v < lmin) lmin = v;
+  for (int pos = p - 1;; pos -= 32) {
+    const int i = pos - lane;
+    const double v = i >= 0 ? -e.at(lo + i) : 0.0;
+    const unsigned stop = __ballot_sync(AEW_FULL, i < 0 || !(v <= xp));
+    const int first = stop ? __ffs((int)stop) - 1 : 32;
+    lmin = fmin(lmin, warp_min(lane < first ? v : INFINITY));
+    if (stop) break;
   }
-  for (int i = p; i <= len - 1; ++i) {
-    const double v = -e.at(lo + i);
-    if (!(v <= xp)) break;
-    if (v < rmin) rmin = v;
+  for (int pos = p + 1;; pos += 32) {
+    const int i = pos + lane;
+    const double v = i < len ? -e.at(lo + i) : 0.0;
+    const unsigned stop = __ballot_sync(AEW_FULL, i >= len || !(v <= xp));
+    const int first = stop ? __ffs((int)stop) - 1 : 32;
+    rmin = fmin(rmin, warp_min(lane < first ? v : INFINITY));
+    if (stop) break;
   }
   return xp - fmax(lmin, rmin);
 }
 
 // first (which = 0) or last (which = 1) local minimum of the segment whose prominence is at least 5 % of
 // the segment's range; -1 if none.  Executed by a whole warp.
-__device__ int prominent_minimum(const Epoch& e, long long lo, int len, int which, int lane) {
+__device__ int prominent_minimum(const Epoch& e, int lo, int len, int which, int lane) {
   if (len < 3) return -1;
   double mx = -INFINITY, mn = INFINITY;
   for (int i = lane; i < len; i += 32) {
@@ -142,29 +150,33 @@ __device__ int prominent_minimum(const Epoch& e, long long lo, int len, int whic
   for (int c = 0; c < n_chunks; ++c) {
     const int base = (which ? n_chunks - 1 - c : c) * 32;
     const int p = seg_peak(e, lo, len, base + lane);
-    const bool ok = p >= 0 && !(seg_prominence(e, lo, len, p) < thr);
-    const unsigned m = __ballot_sync(AEW_FULL, ok);
-    if (m) return __shfl_sync(AEW_FULL, p, which ? hi_bit(m) : __ffs((int)m) - 1);
+    unsigned m = __ballot_sync(AEW_FULL, p >= 0);
+    while (m) {                                    // candidates of this chunk in search order
+      const int src = which ? hi_bit(m) : __ffs((int)m) - 1;
+      m &= ~(1u << src);
+      const int pp = __shfl_sync(AEW_FULL, p, src);
+      if (!(seg_prominence(e, lo, len, pp, lane) < thr)) return pp;
+    }
   }
   return -1;
 }
 
 // ------------------------------------------------------------------ E: searches on a wavelet row
-struct Row {
+struct Row {                    // a slice of a wavelet row, optionally negated
   const double* w;
   double sign;
-  __device__ __forceinline__ double at(long long i) const { return sign * w[i]; }
+  __device__ __forceinline__ double at(int i) const { return sign * w[i]; }
 };
 
 // local maximum of r over [a0, a0 + len) at plateau start i -> plateau middle or -1
-__device__ __forceinline__ long long row_peak(const Row& r, long long a0, long long len, long long i, bool use_abs) {
+__device__ __forceinline__ int row_peak(const Row& r, int len, int i, bool use_abs) {
   if (i < 1 || i > len - 2) return -1;
-  double x = r.at(a0 + i), l = r.at(a0 + i - 1);
+  double x = r.at(i), l = r.at(i - 1);
   if (use_abs) { x = fabs(x); l = fabs(l); }
   if (!(l < x)) return -1;
-  long long ahead = i + 1;
-  while (ahead < len - 1 && (use_abs ? fabs(r.at(a0 + ahead)) : r.at(a0 + ahead)) == x) ++ahead;
-  const double nx = use_abs ? fabs(r.at(a0 + ahead)) : r.at(a0 + ahead);
+  int ahead = i + 1;
+  while (ahead < len - 1 && (use_abs ? fabs(r.at(ahead)) : r.at(ahead)) == x) ++ahead;
+  const double nx = use_abs ? fabs(r.at(ahead)) : r.at(ahead);
   if (!(nx < x)) return -1;
   return (i + ahead - 1) / 2;
 }
@@ -173,71 +185,79 @@ __device__ __forceinline__ long long row_peak(const Row& r, long long a0, long l
 // significant negative extremum with the best score.  mode 0: T (score = y - (t - ref)), 1: P (y - |t - ref|).
 __device__ long long tp_peak(const double* row, const double* e2k, long long n2k, long long a, long long b,
                              double height_w, int mode, double ref, int lane) {
-  long long a0, len;
-  py_slice(a, b, n2k, a0, len);
-  if (len == 0) return K7_NANI;
-  const Row r{row, 1.0};
+  long long a0, len64;
+  py_slice(a, b, n2k, a0, len64);
+  if (len64 == 0) return K7_NANI;
+  const int len = (int)len64;
+  const Row r{row + a0, 1.0};
+  const double* ecg = e2k + a0;
   double ss = 0.0, mx = -INFINITY;
-  for (long long i = lane; i < len; i += 32) {
-    const double v = r.at(a0 + i);
+  for (int i = lane; i < len; i += 32) {
+    const double v = r.at(i);
     ss += v * v;
     mx = fmax(mx, v);
   }
   const double height = height_w * sqrt(warp_sum(ss) / (double)len);
   const double floor_abs = 0.025 * warp_max(mx);
-  long long carry = r.at(a0) > 0.0 ? 0 : -1;
+  int carry = r.at(0) > 0.0 ? 0 : -1;
   double best = -INFINITY;
-  long long best_z = -1;
-  for (long long base = 0; base < len; base += 32) {
-    long long p = row_peak(r, a0, len, base + lane, true);
+  int best_z = -1;
+  for (int base = 0; base < len; base += 32) {
+    int p = row_peak(r, len, base + lane, true);
     if (p >= 0) {
-      const double h = fabs(r.at(a0 + p));
+      const double h = fabs(r.at(p));
       if (!(h >= height) || !(h > floor_abs)) p = -1;
     }
     const unsigned m = __ballot_sync(AEW_FULL, p >= 0);
     const unsigned lower = m & ((1u << lane) - 1u);
-    const long long from_lane = __shfl_sync(AEW_FULL, p, lower ? hi_bit(lower) : 0);
-    const long long prev = lower ? from_lane : carry;
-    if (p >= 0 && prev >= 0 && r.at(a0 + prev) > 0.0 && r.at(a0 + p) < 0.0) {
-      long long z = prev;
-      while (z < p && sgn(r.at(a0 + z + 1)) == sgn(r.at(a0 + z))) ++z;
+    const int from_lane = __shfl_sync(AEW_FULL, p, lower ? hi_bit(lower) : 0);
+    const int prev = lower ? from_lane : carry;
+    if (p >= 0 && prev >= 0 && r.at(prev) > 0.0 && r.at(p) < 0.0) {
+      int z = prev;
+      int sz = sgn(r.at(z));
+      while (z < p) {                              // first sample whose successor has another sign
+        const int sn = sgn(r.at(z + 1));
+        if (sn != sz) break;
+        ++z;
+      }
       const double t = (double)z / K7_RATE;
-      const double y = e2k[a0 + z];
+      const double y = ecg[z];
       const double sc = mode == 0 ? y - (t - ref) : y - fabs(t - ref);
       if (sc > best) { best = sc; best_z = z; }          // this lane's candidates come in increasing z
     }
-    const long long last = __shfl_sync(AEW_FULL, p, m ? hi_bit(m) : 0);
+    const int last = __shfl_sync(AEW_FULL, p, m ? hi_bit(m) : 0);
     if (m) carry = last;
   }
   // np.argmax: first maximum = the smallest z among equal scores
   for (int o = 16; o; o >>= 1) {
     const double ob = __shfl_xor_sync(AEW_FULL, best, o);
-    const long long oz = __shfl_xor_sync(AEW_FULL, best_z, o);
+    const int oz = __shfl_xor_sync(AEW_FULL, best_z, o);
     if (oz >= 0 && (best_z < 0 || ob > best || (ob == best && oz < best_z))) { best = ob; best_z = oz; }
   }
-  return best_z < 0 ? K7_NANI : best_z + a;
+  return best_z < 0 ? K7_NANI : (long long)best_z + a;
 }
 
 // last sample before the last local maximum of sign*row[a:b] that is below weight * that maximum
 __device__ long long onset_search(const double* row, long long n2k, long long a, long long b, double sign,
                                   double weight, int lane) {
   if (a == K7_NANI || b == K7_NANI) return K7_NANI;
-  long long a0, len;
-  py_slice(a, b, n2k, a0, len);
-  if (len < 3) return K7_NANI;
-  const Row r{row, sign};
-  long long pk = -1;
-  for (long long base = ((len - 1) / 32) * 32; base >= 0 && pk < 0; base -= 32) {
-    const long long p = row_peak(r, a0, len, base + lane, false);
+  long long a0, len64;
+  py_slice(a, b, n2k, a0, len64);
+  if (len64 < 3) return K7_NANI;
+  const int len = (int)len64;
+  const Row r{row + a0, sign};
+  int pk = -1;
+  for (int base = ((len - 1) / 32) * 32; base >= 0 && pk < 0; base -= 32) {
+    const int p = row_peak(r, len, base + lane, false);
     const unsigned m = __ballot_sync(AEW_FULL, p >= 0);
     if (m) pk = __shfl_sync(AEW_FULL, p, hi_bit(m));
   }
   if (pk < 0) return K7_NANI;
-  const double eps = weight * r.at(a0 + pk);
-  for (long long base = ((pk - 1) / 32) * 32; pk > 0 && base >= 0; base -= 32) {
-    const long long i = base + lane;
-    const unsigned m = __ballot_sync(AEW_FULL, i < pk && r.at(a0 + i) < eps);
-    if (m) return base + hi_bit(m) + a;
+  const double eps = weight * r.at(pk);
+  for (int base = ((pk - 1) / 32) * 32; pk > 0 && base >= 0; base -= 32) {
+    const int i = base + lane;
+    const unsigned m = __ballot_sync(AEW_FULL, i < pk && r.at(i) < eps);
+    if (m) return (long long)(base + hi_bit(m)) + a;
   }
   return K7_NANI;
 }
@@ -246,22 +266,23 @@ __device__ long long onset_search(const double* row, long long n2k, long long a,
 __device__ long long offset_search(const double* row, long long n2k, long long a, long long b, double sign,
                                    double weight, int lane) {
   if (a == K7_NANI || b == K7_NANI) return K7_NANI;
-  long long a0, len;
-  py_slice(a, b, n2k, a0, len);
-  if (len < 3) return K7_NANI;
-  const Row r{row, sign};
-  long long pk = -1;
-  for (long long base = 0; base < len && pk < 0; base += 32) {
-    const long long p = row_peak(r, a0, len, base + lane, false);
+  long long a0, len64;
+  py_slice(a, b, n2k, a0, len64);
+  if (len64 < 3) return K7_NANI;
+  const int len = (int)len64;
+  const Row r{row + a0, sign};
+  int pk = -1;
+  for (int base = 0; base < len && pk < 0; base += 32) {
+    const int p = row_peak(r, len, base + lane, false);
     const unsigned m = __ballot_sync(AEW_FULL, p >= 0);
     if (m) pk = __shfl_sync(AEW_FULL, p, __ffs((int)m) - 1);
   }
   if (pk < 0) return K7_NANI;
-  const double eps = weight * r.at(a0 + pk);
-  for (long long base = (pk / 32) * 32; base < len; base += 32) {
-    const long long i = base + lane;
-    const unsigned m = __ballot_sync(AEW_FULL, i >= pk && i < len && r.at(a0 + i) < eps);
-    if (m) return base + (__ffs((int)m) - 1) + a;
+  const double eps = weight * r.at(pk);
+  for (int base = (pk / 32) * 32; base < len; base += 32) {
+    const int i = base + lane;
+    const unsigned m = __ballot_sync(AEW_FULL, i >= pk && i < len && r.at(i) < eps);
+    if (m) return (long long)(base + (__ffs((int)m) - 1)) + a;
   }
   return K7_NANI;
 }
@@ -467,11 +488,11 @@ k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ s
           n_left = n;                              // no label above 0 -> np.min([]) raises
         }
         if (n_left >= n) { bad = 1; continue; }
-        const Epoch e{sig, L, ea - buf};
+        const Epoch e{sig, L, (int)(ea - buf)};
         const int qi = prominent_minimum(e, 0, (int)n_left, 1, lane);
         long long n_right = n - right0;
         if (b == nb - 1 && e.s0 + n > L) n_right = (long long)L - e.s0 - right0;   // last beat: NaN past the end
-        const int si = n_right > 0 ? prominent_minimum(e, right0, (int)n_right, 0, lane) : -1;
+        const int si = n_right > 0 ? prominent_minimum(e, (int)right0, (int)n_right, 0, lane) : -1;
         if (lane == 0) {
           fw[3 * max_peaks + b] = qi < 0 ? AEW_FID_NAN : (int)(r - (n_left - qi));
           fw[6 * max_peaks + b] = si < 0 ? AEW_FID_NAN : (int)(r + si);
@@ -541,9 +562,9 @@ k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ s
             const double cc = (double)j * ratio;
             const double fl = floor(cc);
             const double y = cc - fl, z = 1.0 - y;
-            const double w1 = (y * y * (y - 2.0) * 3.0 + 4.0) / 6.0;
-            const double w2 = (z * z * (z - 2.0) * 3.0 + 4.0) / 6.0;
-            const double w0 = z * z * z / 6.0;
+            const double w1 = (y * y * (y - 2.0) * 3.0 + 4.0) * (1.0 / 6.0);
+            const double w2 = (z * z * (z - 2.0) * 3.0 + 4.0) * (1.0 / 6.0);
+            const double w0 = z * z * z * (1.0 / 6.0);
             const double w3 = 1.0 - w0 - w1 - w2;
             const int i0 = (int)fl - 1;
             if (i0 >= 0 && i0 + 3 < L) {
@@ -576,6 +597,19 @@ k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ s
           }
           const long long len_cur = len_prev + 3 * d;
           const long long shifted = len_cur - d;
+          if (base >= 0 && base + K7_TILE <= n2k) {
+            // interior tile: every tap lies inside the signal and inside the shifted part of the level
+            for (int i = tid; i < K7_TILE; i += K7_THREADS) {
+              double acc = 0.0;
+              if (i >= 2 * d && i + d < K7_TILE) {
+                acc = 0.125 * prev[i + d];
+                acc += 0.375 * prev[i];
+                acc += 0.375 * prev[i - d];
+                acc += 0.125 * prev[i - 2 * d];
+              }
+              cur[i] = acc;
+            }
+          } else
           for (int i = tid; i < K7_TILE; i += K7_THREADS) {
             const long long n = base + i;
             double acc = 0.0;
