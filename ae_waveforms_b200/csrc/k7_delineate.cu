@@ -39,7 +39,7 @@
 namespace {
 
 struct K7Scratch {
-  double *coef, *cplus, *e2k, *wa, *wb;
+  double *coef, *e2k, *wa, *wb;
 };
 
 #define MUL(a, b) __dmul_rn((a), (b))
@@ -341,6 +341,7 @@ k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ s
   __shared__ double s_red[K7_WARPS];
   __shared__ double s_vals[128];               // leaf slots of np.mean's pairwise tree (L <= 16,384)
   __shared__ unsigned char s_valid[128];
+  __shared__ long long s_tp[2][K7_MAXP];        // T and P peaks at 2 kHz
   __shared__ double s_par[8];
   __shared__ int s_ipar[4];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -348,12 +349,13 @@ k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ s
   {
     double* base = scratch + (long long)blockIdx.x * scratch_stride;
     S.coef = base;
-    S.cplus = S.coef + ((L + 7) & ~7);
-    S.e2k = S.cplus + ((L + 7) & ~7);
+    S.e2k = S.coef + ((L + 7) & ~7);
     S.wa = S.e2k + ((n2k + 7) & ~7LL);
     S.wb = S.wa + ((n2k + 7) & ~7LL);
   }
   const double zp = sqrt(3.0) - 2.0;             // pole of the cubic B-spline prefilter
+  AEW_DYN_SMEM(dyn);
+  double* const sm = reinterpret_cast<double*>(dyn);   // 2 * K7_TILE doubles: the window, then the cascade tiles
 
   for (long long w = blockIdx.x; w < n_win; w += gridDim.x) {
     if (select && !select[w]) continue;
@@ -368,6 +370,7 @@ k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ s
       if (tid == 0) flags[w] = 1;
       continue;
     }
+    for (int i = tid; i < L; i += K7_THREADS) sm[i] = sig[i];   // the window stays in shared memory for A - C
     for (int i = tid; i < nb; i += K7_THREADS) {
       s_pk[i] = peaks[w * (long long)max_peaks + i];
       s_r2k[i] = (long long)((double)((long long)s_pk[i] * 2000LL) / fs);
@@ -488,7 +491,7 @@ k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ s
           n_left = n;                              // no label above 0 -> np.min([]) raises
         }
         if (n_left >= n) { bad = 1; continue; }
-        const Epoch e{sig, L, (int)(ea - buf)};
+        const Epoch e{sm, L, (int)(ea - buf)};
         const int qi = prominent_minimum(e, 0, (int)n_left, 1, lane);
         long long n_right = n - right0;
         if (b == nb - 1 && e.s0 + n > L) n_right = (long long)L - e.s0 - right0;   // last beat: NaN past the end
@@ -504,37 +507,48 @@ k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ s
       }
     }
 
-    // ---- C: cubic B-spline coefficients of the window (scipy.ndimage.zoom, order 3, mirror prefilter)
+    // ---- C: cubic B-spline coefficients of the window (scipy.ndimage.zoom, order 3, mirror prefilter), in place
+    // in shared memory: every thread owns a chunk; the state entering a chunk comes from a 32-sample run-in
+    // over its neighbour's samples (read before anybody writes), then the chunk is overwritten.
     {
       const int ch = (L + K7_THREADS - 1) / K7_THREADS;
       const int c0 = tid * ch, c1 = c0 + ch < L ? c0 + ch : L;
-      double* cplus = S.cplus;
-      if (c0 < c1) {
-        double c = 0.0;
-        for (int i = c0 - K7_RUNIN; i < c1; ++i) {
+      double c = 0.0;
+      if (c0 < c1)
+        for (int i = c0 - K7_RUNIN; i < c0; ++i) {
           int k = i < 0 ? -i : i;
           if (k >= L) k = L - 1;
-          c = fma(zp, c, 6.0 * sig[k]);
-          if (i >= c0) cplus[i] = c;
+          c = fma(zp, c, 6.0 * sm[k]);
         }
+      __syncthreads();
+      for (int i = c0; i < c1; ++i) {
+        c = fma(zp, c, 6.0 * sm[i]);
+        sm[i] = c;
       }
       __syncthreads();
+      // anticausal pass: c[i] = zp (c[i+1] - c+[i]), c[L-1] = zp / (zp^2 - 1) (c+[L-1] + zp c+[L-2])
       if (c0 < c1) {
-        double c;
         int i;
         if (c1 + K7_RUNIN >= L) {
-          c = (zp / (zp * zp - 1.0)) * (cplus[L - 1] + zp * cplus[L - 2]);
+          c = (zp / (zp * zp - 1.0)) * (sm[L - 1] + zp * sm[L - 2]);
           i = L - 1;
-          if (i < c1) S.coef[i] = c;
         } else {
           c = 0.0;
           i = c1 + K7_RUNIN;
         }
-        for (--i; i >= c0; --i) {
-          c = zp * (c - cplus[i]);
-          if (i < c1) S.coef[i] = c;
+        for (--i; i >= c1 - 1 && i >= c0; --i) c = zp * (c - sm[i]);   // c = coefficient at c1 - 1 (or L - 1 itself)
+      }
+      __syncthreads();
+      if (c0 < c1) {
+        // here c is the coefficient of position c1 - 1
+        sm[c1 - 1] = c;
+        for (int i = c1 - 2; i >= c0; --i) {
+          c = zp * (c - sm[i]);
+          sm[i] = c;
         }
       }
+      __syncthreads();
+      for (int i = tid; i < L; i += K7_THREADS) S.coef[i] = sm[i];
       __syncthreads();
     }
 
@@ -542,8 +556,7 @@ k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ s
     // consecutive positions of every level; level p is valid 2 * 2^p less far to the left and 2^p less far to
     // the right than level p - 1, so the halo is sized for the rows qa = 2 + d and qb = 3 + d that are kept.
     {
-      AEW_DYN_SMEM(dyn);
-      double* bufs[2] = {reinterpret_cast<double*>(dyn), reinterpret_cast<double*>(dyn) + K7_TILE};
+      double* bufs[2] = {sm, sm + K7_TILE};
       const int deg = s_ipar[0];
       const int qa = 2 + deg, qb = 3 + deg;
       const int halo_l = 2 * ((1 << (qa + 1)) - 1), halo_r = (1 << (qa + 2)) - 1;
@@ -555,6 +568,18 @@ k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ s
         const long long t1 = t0 + ts < n2k ? t0 + ts : n2k;
         double* prev = bufs[0];
         double* cur = bufs[1];
+        // the spline coefficients this tile touches, mirrored at the ends, staged in the other buffer
+        const long long j_lo = base > 0 ? base : 0;
+        const long long j_hi = (base + K7_TILE < n2k ? base + K7_TILE : n2k) - 1;
+        const int i_lo = (int)floor((double)j_lo * ratio) - 1;
+        const int i_cnt = (int)floor((double)j_hi * ratio) + 3 - i_lo;
+        for (int k = tid; k < i_cnt; k += K7_THREADS) {
+          int idx = i_lo + k;
+          if (idx < 0) idx = -idx;
+          if (idx >= L) idx = 2 * L - 2 - idx;
+          cur[k] = S.coef[idx];
+        }
+        __syncthreads();
         for (int i = tid; i < K7_TILE; i += K7_THREADS) {   // level -1: the resampled signal
           const long long j = base + i;
           double t = 0.0;
@@ -566,21 +591,11 @@ k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ s
             const double w2 = (z * z * (z - 2.0) * 3.0 + 4.0) * (1.0 / 6.0);
             const double w0 = z * z * z * (1.0 / 6.0);
             const double w3 = 1.0 - w0 - w1 - w2;
-            const int i0 = (int)fl - 1;
-            if (i0 >= 0 && i0 + 3 < L) {
-              t = S.coef[i0] * w0;
-              t += S.coef[i0 + 1] * w1;
-              t += S.coef[i0 + 2] * w2;
-              t += S.coef[i0 + 3] * w3;
-            } else {
-#pragma unroll
-              for (int hh = 0; hh < 4; ++hh) {
-                int idx = i0 + hh;
-                if (idx < 0) idx = -idx;
-                if (idx >= L) idx = 2 * L - 2 - idx;
-                t += S.coef[idx] * (hh == 0 ? w0 : hh == 1 ? w1 : hh == 2 ? w2 : w3);
-              }
-            }
+            const double* cs = cur + ((int)fl - 1 - i_lo);
+            t = cs[0] * w0;
+            t += cs[1] * w1;
+            t += cs[2] * w2;
+            t += cs[3] * w3;
             if (j >= t0 && j < t1) S.e2k[j] = t;
           }
           prev[i] = t;
@@ -597,23 +612,16 @@ k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ s
           }
           const long long len_cur = len_prev + 3 * d;
           const long long shifted = len_cur - d;
-          if (base >= 0 && base + K7_TILE <= n2k) {
-            // interior tile: every tap lies inside the signal and inside the shifted part of the level
-            for (int i = tid; i < K7_TILE; i += K7_THREADS) {
-              double acc = 0.0;
-              if (i >= 2 * d && i + d < K7_TILE) {
-                acc = 0.125 * prev[i + d];
-                acc += 0.375 * prev[i];
-                acc += 0.375 * prev[i - d];
-                acc += 0.125 * prev[i - 2 * d];
-              }
-              cur[i] = acc;
-            }
-          } else
           for (int i = tid; i < K7_TILE; i += K7_THREADS) {
             const long long n = base + i;
             double acc = 0.0;
-            if (n >= 0 && n < len_cur) {
+            if (i >= 2 * d && i + d < K7_TILE && n >= 2 * d && n + d < n2k) {
+              // interior: every tap lies inside the signal, the buffer and the shifted part of the level
+              acc = 0.125 * prev[i + d];
+              acc += 0.375 * prev[i];
+              acc += 0.375 * prev[i - d];
+              acc += 0.125 * prev[i - 2 * d];
+            } else if (n >= 0 && n < len_cur) {
               const long long m = n < shifted ? n + d : n;
               const int im = (int)(m - base);
 #pragma unroll
@@ -638,36 +646,52 @@ k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ s
       }
     }
 
-    // ---- E: per-beat searches at 2 kHz (warp per beat)
+    // ---- E: per-beat searches at 2 kHz, a warp per task: first the T and P peaks, then the six bounds
     {
       const double p2r = s_par[2], rt = s_par[3], d_on = s_par[4], d_on_t = s_par[5];
       const long long bndry = (long long)(0.5 * 0.13 * K7_RATE);
-      for (int b = warp; b < nb; b += K7_WARPS) {
+      for (int task = warp; task < 2 * nb; task += K7_WARPS) {
+        const int b = task >> 1;
         const long long r = s_r2k[b];
-        const long long t = tp_peak(S.wb, S.e2k, n2k, r + bndry, r + 2 * (long long)(rt * K7_RATE), 0.25, 0,
-                                    rt - 0.5 * 0.13, lane);
-        const long long p = tp_peak(S.wa, S.e2k, n2k, r - 2 * (long long)(p2r * K7_RATE), r - bndry, 0.02, 1, p2r,
-                                    lane);
-        const int q500 = fw[3 * max_peaks + b];    // written by lane 0 of this same warp in phase B
-        const long long q2k = q500 == AEW_FID_NAN ? K7_NANI
-                                                  : (long long)((double)((long long)q500 * 2000LL) / fs);
-        const long long r_on = onset_search(S.wa, n2k, p, q2k, -1.0, 0.5, lane);
-        const long long r_off = offset_search(S.wa, n2k, r, t, 1.0, 0.5, lane);
-        const long long n_on = (long long)(d_on * K7_RATE), n_on_t = (long long)(d_on_t * K7_RATE);
-        const long long p_on = onset_search(S.wa, n2k, p == K7_NANI ? K7_NANI : p - n_on, p, 1.0, 0.4, lane);
-        const long long p_off = offset_search(S.wa, n2k, p, p == K7_NANI ? K7_NANI : p + n_on, -1.0, 0.4, lane);
-        const long long t_on = onset_search(S.wa, n2k, t == K7_NANI ? K7_NANI : t - n_on_t, t, 1.0, 0.6, lane);
-        const long long t_off = offset_search(S.wa, n2k, t, t == K7_NANI ? K7_NANI : t + n_on, -1.0, 0.4, lane);
+        long long v;
+        if ((task & 1) == 0)
+          v = tp_peak(S.wb, S.e2k, n2k, r + bndry, r + 2 * (long long)(rt * K7_RATE), 0.25, 0, rt - 0.5 * 0.13, lane);
+        else
+          v = tp_peak(S.wa, S.e2k, n2k, r - 2 * (long long)(p2r * K7_RATE), r - bndry, 0.02, 1, p2r, lane);
         if (lane == 0) {
-          fw[0 * max_peaks + b] = back_to_fs(p, fs);
-          fw[1 * max_peaks + b] = back_to_fs(p_on, fs);
-          fw[2 * max_peaks + b] = back_to_fs(p_off, fs);
-          fw[4 * max_peaks + b] = back_to_fs(r_on, fs);
-          fw[5 * max_peaks + b] = back_to_fs(r_off, fs);
-          fw[7 * max_peaks + b] = back_to_fs(t, fs);
-          fw[8 * max_peaks + b] = back_to_fs(t_on, fs);
-          fw[9 * max_peaks + b] = back_to_fs(t_off, fs);
+          s_tp[task & 1][b] = v;
+          fw[((task & 1) ? 0 : 7) * max_peaks + b] = back_to_fs(v, fs);
         }
+      }
+      __syncthreads();
+      const long long n_on = (long long)(d_on * K7_RATE), n_on_t = (long long)(d_on_t * K7_RATE);
+      for (int task = warp; task < 6 * nb; task += K7_WARPS) {
+        const int b = task / 6, kind = task - 6 * b;
+        const long long r = s_r2k[b], t = s_tp[0][b], p = s_tp[1][b];
+        long long v;
+        int slot;
+        if (kind == 0) {                           // QRS onset: between the P peak and the Q peak
+          const int q500 = fw[3 * max_peaks + b];
+          const long long q2k = q500 == AEW_FID_NAN ? K7_NANI : (long long)((double)((long long)q500 * 2000LL) / fs);
+          v = onset_search(S.wa, n2k, p, q2k, -1.0, 0.5, lane);
+          slot = 4;
+        } else if (kind == 1) {                    // QRS offset: between the R peak and the T peak
+          v = offset_search(S.wa, n2k, r, t, 1.0, 0.5, lane);
+          slot = 5;
+        } else if (kind == 2) {
+          v = onset_search(S.wa, n2k, p == K7_NANI ? K7_NANI : p - n_on, p, 1.0, 0.4, lane);
+          slot = 1;
+        } else if (kind == 3) {
+          v = offset_search(S.wa, n2k, p, p == K7_NANI ? K7_NANI : p + n_on, -1.0, 0.4, lane);
+          slot = 2;
+        } else if (kind == 4) {
+          v = onset_search(S.wa, n2k, t == K7_NANI ? K7_NANI : t - n_on_t, t, 1.0, 0.6, lane);
+          slot = 8;
+        } else {
+          v = offset_search(S.wa, n2k, t, t == K7_NANI ? K7_NANI : t + n_on, -1.0, 0.4, lane);
+          slot = 9;
+        }
+        if (lane == 0) fw[slot * max_peaks + b] = back_to_fs(v, fs);
       }
     }
     __syncthreads();
@@ -696,7 +720,7 @@ extern "C" int aew_delineate_blocks(long long n_win) {
 
 static long long k7_n2k(int L, double fs) { return (long long)rint((double)L * K7_RATE / fs); }
 
-static long long k7_stride(int L, long long n2k) { return 2 * ((L + 7) & ~7) + 3 * ((n2k + 7) & ~7LL); }
+static long long k7_stride(int L, long long n2k) { return ((L + 7) & ~7) + 3 * ((n2k + 7) & ~7LL); }
 
 extern "C" size_t aew_delineate_workspace_bytes(long long n_win, int L, double fs) {
   if (L <= 0 || !(fs > 0)) return 0;
@@ -707,7 +731,7 @@ extern "C" int aew_delineate_f64(const double* d_sig, const long long* d_sig_off
                                  const int* d_peaks, const int* d_n_peaks, int max_peaks,
                                  const unsigned char* d_select, int* d_fid, unsigned char* d_flags, void* d_ws,
                                  size_t ws_bytes, void* stream) {
-  if (n_win < 0 || L < 64 || L > 16384 || max_peaks <= 0 || max_peaks > K7_MAXP || !(fs > 0)) return AEW_ERR_ARG;
+  if (n_win < 0 || L < 64 || L > 2 * K7_TILE || max_peaks <= 0 || max_peaks > K7_MAXP || !(fs > 0)) return AEW_ERR_ARG;
   if (n_win == 0) return AEW_OK;
   if (!d_sig || !d_sig_off || !d_peaks || !d_n_peaks || !d_fid || !d_flags || !d_ws) return AEW_ERR_ARG;
   if (ws_bytes < aew_delineate_workspace_bytes(n_win, L, fs)) return AEW_ERR_WORKSPACE;
