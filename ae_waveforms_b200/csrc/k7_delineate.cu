@@ -192,10 +192,23 @@ __device__ long long tp_peak(const double* row, const double* e2k, long long n2k
   const Row r{row + a0, 1.0};
   const double* ecg = e2k + a0;
   double ss = 0.0, mx = -INFINITY;
-  for (int i = lane; i < len; i += 32) {
-    const double v = r.at(i);
-    ss += v * v;
-    mx = fmax(mx, v);
+  {
+    double ss2 = 0.0, mx2 = -INFINITY;
+    int i = lane;
+    for (; i + 32 < len; i += 64) {
+      const double v = r.at(i), u = r.at(i + 32);
+      ss += v * v;
+      ss2 += u * u;
+      mx = fmax(mx, v);
+      mx2 = fmax(mx2, u);
+    }
+    if (i < len) {
+      const double v = r.at(i);
+      ss += v * v;
+      mx = fmax(mx, v);
+    }
+    ss += ss2;
+    mx = fmax(mx, mx2);
   }
   const double height = height_w * sqrt(warp_sum(ss) / (double)len);
   const double floor_abs = 0.025 * warp_max(mx);
@@ -612,24 +625,30 @@ k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ s
           }
           const long long len_cur = len_prev + 3 * d;
           const long long shifted = len_cur - d;
+          // interior positions [f_lo, f_hi): every tap lies inside the signal, the buffer and the shifted part
+          long long lo64 = 2LL * d - base, hi64 = n2k - d - base;
+          const int f_lo = lo64 > 2 * d ? (int)(lo64 < K7_TILE ? lo64 : K7_TILE) : 2 * d;
+          const int f_hi = hi64 < K7_TILE - d ? (int)(hi64 > 0 ? hi64 : 0) : K7_TILE - d;
+#pragma unroll 4
           for (int i = tid; i < K7_TILE; i += K7_THREADS) {
-            const long long n = base + i;
             double acc = 0.0;
-            if (i >= 2 * d && i + d < K7_TILE && n >= 2 * d && n + d < n2k) {
-              // interior: every tap lies inside the signal, the buffer and the shifted part of the level
+            if (i >= f_lo && i < f_hi) {
               acc = 0.125 * prev[i + d];
               acc += 0.375 * prev[i];
               acc += 0.375 * prev[i - d];
               acc += 0.125 * prev[i - 2 * d];
-            } else if (n >= 0 && n < len_cur) {
-              const long long m = n < shifted ? n + d : n;
-              const int im = (int)(m - base);
+            } else {
+              const long long n = base + i;
+              if (n >= 0 && n < len_cur) {
+                const long long m = n < shifted ? n + d : n;
+                const int im = (int)(m - base);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int ix = im - k * d;
-                const long long x = m - (long long)k * d;
-                const double v = (ix >= 0 && ix < K7_TILE && x >= 0 && x < len_prev) ? prev[ix] : 0.0;
-                acc += ((k == 0 || k == 3) ? 0.125 : 0.375) * v;
+                for (int k = 0; k < 4; ++k) {
+                  const int ix = im - k * d;
+                  const long long x = m - (long long)k * d;
+                  const double v = (ix >= 0 && ix < K7_TILE && x >= 0 && x < len_prev) ? prev[ix] : 0.0;
+                  acc += ((k == 0 || k == 3) ? 0.125 : 0.375) * v;
+                }
               }
             }
             cur[i] = acc;
