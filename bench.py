@@ -146,6 +146,30 @@ def _cpu_worker(args):
     return time.perf_counter() - t0, len(case_ids) * n_samples, beats, rows
 
 
+def _cpu_feature_worker(args):
+    """One host core: delineation + 35 features (data_extract_vitaldb.py:129-162) of the kept windows of one
+    short case through the oracle; only that stage is timed."""
+    case_id, n_samples = args
+    import warnings
+    warnings.simplefilter("ignore")
+    from oracle import ecg_synth, ref_port
+    r = ref_port.process_case(ecg_synth.synth_case(case_id, n_samples), case_id=case_id)
+    sel = np.flatnonzero(r["keep"])
+    t0 = time.perf_counter()
+    for i in sel:
+        ref_port.window_features(r["windows"][i], r["peaks"][i])
+    return time.perf_counter() - t0, len(sel)
+
+
+def cpu_feature_pass(cores, n_samples=400001):
+    import multiprocessing as mp
+    with mp.get_context("spawn").Pool(cores) as pool:
+        res = pool.map(_cpu_feature_worker, [(5000 + i, n_samples) for i in range(cores)])
+    wall = max(r[0] for r in res)
+    n = sum(r[1] for r in res)
+    return {"windows_per_s": n / wall if wall > 0 else None, "windows": n, "seconds": wall, "cores": cores}
+
+
 def cpu_reference_pass(cores, cases_per_core=1, n_samples=CASE_SAMPLES, first_id=0):
     """Reference CPU implementation (oracle port), parallelised as the reference does:
     a process pool over case IDs (data_extract_vitaldb.py:194-199)."""
@@ -471,6 +495,15 @@ def run_gpu(args):
         else:
             out["e2e"] = {"value": None, "unit": UNIT, "error": e2e.get("error")}
         if feat is not None:
+            if "error" not in feat and not args.no_cpu:
+                try:
+                    c = cpu_feature_pass(min(usable_cores(), 64))
+                    feat["cpu_baseline"] = {"value": c["windows_per_s"], "unit": "windows/s", "cores": c["cores"],
+                                            "kind": "port", "sample": f"{c['windows']} kept windows (one 800 s case per "
+                                            f"core) through oracle/nk_delineate.py + the feature functions, "
+                                            f"{c['seconds']:.1f} s wall"}
+                except Exception as exc:
+                    feat["cpu_baseline"] = {"error": str(exc)[:200]}
             out["with_features"] = feat
         if world == 1:
             try:

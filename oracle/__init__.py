@@ -8,13 +8,17 @@ checker (or as the timed CPU baseline), never as a fallback for the CUDA path.
 Contents
 --------
 ``ref_port``    NumPy/SciPy restatement of the reference functions on the path
-                (SURVEY.md section 8a rows a1-a14, a16-a18), each citing the
+                (a15 via ``nk_delineate``), each citing the
                 reference file:line it follows.
 ``nk_peaks``    restatement of ``neurokit2.ecg_findpeaks(method="neurokit")``
                 (third-party, un-vendored, version-unpinned in the reference's
                 requirements.txt:10, absent from this image) -- PARITY UNPINNED
                 at that boundary: no copy of the library exists offline, the
                 reference holds no test or golden vector for it.
+``nk_delineate`` restatement of ``neurokit2.ecg_delineate`` (default method "dwt": HR-sized
+                epochs for Q/S, 2 kHz cubic-spline resampling, a-trous wavelet rows, per-beat
+                searches) -- PARITY UNPINNED for the same reason; the functions that
+                consume its output (a16-a18) are pinned by ``tests/golden/features.npz``.
 ``np_pairwise`` restatement of NumPy's pairwise float64 summation order, the
                 order the CUDA reductions reproduce bit-for-bit.
 ``ecg_synth``   seeded sum-of-Gaussians ECG generator.
@@ -23,8 +27,8 @@ Contents
                 ``tests/golden/make_golden.py`` to freeze golden vectors and by
                 the CPU tests to cross-check ``ref_port`` when the tree is there.
 
-Pinning status: every function in ``ref_port`` except the R-peak detector is
-pinned against outputs of the reference's own code (fixtures under
+Pinning status: every function in ``ref_port`` except the two neurokit2 calls
+(R-peak detector, wave delineator) is pinned against outputs of the reference's own code (fixtures under
 ``tests/golden/`` made by ``tests/golden/make_golden.py``).  The R-peak
 detector is pinned only against SciPy primitives it is built from.
 """
