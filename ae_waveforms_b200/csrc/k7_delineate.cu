@@ -6,7 +6,7 @@
 // reference; restated in oracle/nk_delineate.py from the published "dwt" method -- PARITY UNPINNED
 // at that boundary, the kernel is checked against that restatement).
 //
-// One 256-thread block per window, persistent over windows, with a private slab of global scratch
+// One 512-thread block per window (two per SM: 64 registers, 88 KB shared memory), persistent, with a slab of global scratch
 // (L2-resident: 1.7 MB per block) for the 2 kHz signal, the low-pass cascade and two wavelet rows:
 //   A  mean heart rate over the window: period between R peaks, monotone cubic (PCHIP) to every
 //      sample, 60 / period, mean  -> epoch size for the Q / S search (ecg_segment)
@@ -28,7 +28,9 @@
 #include "aew_pairwise.cuh"
 #include <math.h>
 
-#define K7_THREADS 256
+#ifndef K7_THREADS
+#define K7_THREADS 512
+#endif
 #define K7_WARPS (K7_THREADS / 32)
 #define K7_MAXP 72
 #define K7_TILE 5120           // positions per shared-memory tile of the cascade (two buffers: 80 KB)
@@ -343,7 +345,7 @@ struct RateAt {
 };
 
 // ------------------------------------------------------------------ the kernel
-__global__ void __launch_bounds__(K7_THREADS)
+__global__ void __launch_bounds__(K7_THREADS, 2)
 k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ sig_off, long long n_win, int L,
              long long n2k, double fs, const int* __restrict__ peaks, const int* __restrict__ n_peaks, int max_peaks,
              const unsigned char* __restrict__ select, int* __restrict__ fid, unsigned char* __restrict__ flags,
