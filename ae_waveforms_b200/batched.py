@@ -382,10 +382,27 @@ def _pinned(key: str, shape, dtype, torch):
     return t
 
 
+def widen_to_f64(src, out=None, gain: float = 1.0, offset: float = 0.0, sentinel: int | None = None):
+    """K8: a float32 or int16 CUDA tensor -> float64 (``x.astype(np.float64)``, resp. ``v * gain + offset`` with
+    ``sentinel`` -> NaN): the device half of the input feeder (load_record.py:7-37 delivers float64; the source
+    stores narrower)."""
+    torch, lib = _cabi.require_cuda()
+    code = {torch.float32: 0, torch.int16: 1}.get(src.dtype)
+    if code is None:
+        raise _cabi.AewError(f"cannot widen {src.dtype}")
+    out = torch.empty(src.numel(), dtype=torch.float64, device=src.device) if out is None else out
+    _cabi.check(lib.aew_widen_f64(_ptr(src), code, src.numel(), float(gain), float(offset),
+                                  0 if sentinel is None else 1, 0 if sentinel is None else int(sentinel), _ptr(out),
+                                  _cabi.stream_ptr(torch)), "widen")
+    return out
+
+
 def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chunk_cases: int = 100,
-                       to_host: bool = True, pinned_results: bool = False) -> dict:
-    """End-to-end path for HOST data: ``host_flat`` is a (preferably pinned) CPU float64
-    tensor holding all records back to back.  Cases are fed in chunks through two device
+                       to_host: bool = True, pinned_results: bool = False, gain: float = 1.0, offset: float = 0.0,
+                       sentinel: int | None = None) -> dict:
+    """End-to-end path for HOST data: ``host_flat`` is a (preferably pinned) CPU tensor holding all records back
+    to back -- float64, or the narrower source type (float32; int16 with ``gain`` / ``offset`` and an optional
+    ``sentinel`` for missing samples), which then crosses PCIe as it is and is widened on the device (K8).  Cases are fed in chunks through two device
     input buffers: the host->device copy of chunk k+1 (copy stream) overlaps the kernels of
     chunk k (current stream), and the device->host copy of chunk k's rows (third stream, into
     page-locked memory) overlaps both, so the wall time is max(PCIe, kernels) instead of their sum.
@@ -399,7 +416,10 @@ def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chu
     chunks = [(c0, min(n_rec, c0 + chunk_cases)) for c0 in range(0, n_rec, chunk_cases)]
     sizes = [int(rec_off[c1] - rec_off[c0]) for c0, c1 in chunks]
     cap = max(sizes) if sizes else 0
-    bufs = [torch.empty(cap, dtype=torch.float64, device=pre.device) for _ in range(2)]
+    narrow = host_flat.dtype != torch.float64
+    cap_al = (cap + 7) & ~7                                    # keeps every buffer 16-byte aligned
+    bufs = [torch.empty(cap_al, dtype=host_flat.dtype, device=pre.device) for _ in range(2)]
+    wide = torch.empty(cap_al, dtype=torch.float64, device=pre.device) if narrow else None
     scratch = {"y": torch.empty(cap, dtype=torch.float64, device=pre.device),
                "tmp": torch.empty(cap, dtype=torch.float64, device=pre.device)}
     copy_stream = torch.cuda.Stream(device=pre.device)
@@ -433,10 +453,18 @@ def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chu
         if k + 1 < len(chunks):
             start_copy(k + 1)
         main.wait_event(copied[k])
-        sub = RecordBatch(bufs[k % 2][:sizes[k]], rec_off[c0:c1 + 1] - rec_off[c0], case_ids[c0:c1])
+        if narrow:
+            widen_to_f64(bufs[k % 2][:sizes[k]], wide, gain, offset, sentinel)
+            pre.launches += 1
+            freed[k].record(main)                              # the narrow buffer is free as soon as it is widened
+            chunk_in = wide[:sizes[k]]
+        else:
+            chunk_in = bufs[k % 2][:sizes[k]]
+        sub = RecordBatch(chunk_in, rec_off[c0:c1 + 1] - rec_off[c0], case_ids[c0:c1])
         sc = {"y": scratch["y"][:sizes[k]], "tmp": scratch["tmp"][:sizes[k]]}
         res = pre.run(sub, scratch=sc)
-        freed[k].record(main)
+        if not narrow:
+            freed[k].record(main)
         waves.append(res["np_waves"])
         infos.append(res["np_info"])
         if to_host:

@@ -24,6 +24,7 @@ PER_FILE = {
     "k5_recon.cu": [],
     "k6_features.cu": ["-fmad=false"],
     "k7_delineate.cu": [],
+    "k8_convert.cu": ["-fmad=false"],
     "k2_filtfilt.cu": [],
     "cabi_misc.cu": [],
 }

@@ -6,8 +6,8 @@
 // reference; restated in oracle/nk_delineate.py from the published "dwt" method -- PARITY UNPINNED
 // at that boundary, the kernel is checked against that restatement).
 //
-// One 512-thread block per window (two per SM: 64 registers, 88 KB shared memory), persistent, with a slab of global scratch
-// (L2-resident: 1.7 MB per block) for the 2 kHz signal, the low-pass cascade and two wavelet rows:
+// One 512-thread block per window (two per SM: 64 registers, 88 KB shared memory), persistent, with a
+// 1 MB slab of global scratch per block for the spline coefficients, the 2 kHz signal and two wavelet rows:
 //   A  mean heart rate over the window: period between R peaks, monotone cubic (PCHIP) to every
 //      sample, 60 / period, mean  -> epoch size for the Q / S search (ecg_segment)
 //   B  warp per beat: Q = right-most prominent minimum left of R, S = left-most one from R on

@@ -441,6 +441,38 @@ def run_gpu(args):
     except RuntimeError as exc:                        # e.g. not enough pinned host memory
         e2e = {"error": str(exc)[:200]}
 
+    # ---- secondary: the same end-to-end call fed from the source's narrower sample type (float32 crosses PCIe,
+    # K8 widens on the device; results are those of x.astype(np.float64))
+    e2e32 = None
+    if world == 1 and "seconds" in e2e:
+        try:
+            del host
+            flat32 = synth_cases_gpu(case_ids, n_samp, dev).to(torch.float32)
+            host32 = torch.empty(total, dtype=torch.float32, pin_memory=True)
+            host32.copy_(flat32)
+            torch.cuda.synchronize()
+            del flat32
+            torch.cuda.empty_cache()
+            n32 = max(2, min(3, args.steps))
+            for _ in range(1):
+                r32 = batched.run_host_pipelined(pre, host32, rec_off, case_ids, chunk_cases=max(1, n_cases // 10),
+                                                 to_host=True, pinned_results=True)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(n32):
+                r32 = batched.run_host_pipelined(pre, host32, rec_off, case_ids, chunk_cases=max(1, n_cases // 10),
+                                                 to_host=True, pinned_results=True)
+            torch.cuda.synchronize()
+            s32 = (time.perf_counter() - t0) / n32
+            e2e32 = {"value": total / s32 / 1e6, "unit": UNIT, "source_dtype": "float32",
+                     "h2d_bytes_per_step": total * 4,
+                     "d2h_bytes_per_step": r32["np_waves"].numel() * 4 + r32["np_info"].numel() * 8,
+                     "np_waves_rows": int(r32["np_waves"].shape[0]),
+                     "note": "float32 host buffers (the recordings' storage type), widened to float64 on the device"}
+            del host32
+        except Exception as exc:
+            e2e32 = {"error": str(exc)[:200]}
+
     # ---- reduce over ranks (max time, summed work)
     t = torch.tensor([ms, e2e.get("seconds", float("nan")) * 1e3], dtype=torch.float64, device=dev)
     work = torch.tensor([float(total), float(res["n_beats"]), float(res["np_waves"].shape[0]), float(launches)],
@@ -494,6 +526,8 @@ def run_gpu(args):
                           "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"]}
         else:
             out["e2e"] = {"value": None, "unit": UNIT, "error": e2e.get("error")}
+        if e2e32 is not None:
+            out["e2e_narrow_source"] = e2e32
         if feat is not None:
             if "error" not in feat and not args.no_cpu:
                 try:

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AEW_VERSION 103
+#define AEW_VERSION 104
 
 /* return codes */
 #define AEW_OK 0
@@ -137,6 +137,17 @@ int aew_windows_timing_dump(unsigned long long* h_out16);
 int aew_median_beats_f64(const double* d_windows, long long n_win, int L, const int* d_peaks,
                          const long long* d_peak_off, int max_peaks_per_window, int pre, int post,
                          double* d_median, double* d_aligned, void* stream);
+
+/* ---- K8: narrow source samples -> float64 (the input side) ----------
+ * the float64 frame that data_load_preprocess/load_record.py:7-37 hands to process_case_id
+ * (data_extract_vitaldb.py:45-51) is stored narrower at the source; the end-to-end feeder moves the narrow
+ * type over PCIe and widens on the device.  AEW_SRC_F32: out = (double)x, exactly x.astype(np.float64);
+ * AEW_SRC_I16: out = v * gain + offset (one multiplication, one addition), v == sentinel -> NaN when
+ * use_sentinel.  d_src and d_out must be 16-byte aligned. */
+#define AEW_SRC_F32 0
+#define AEW_SRC_I16 1
+int aew_widen_f64(const void* d_src, int src_type, long long n, double gain, double offset, int use_sentinel,
+                  int sentinel, double* d_out, void* stream);
 
 /* ---- K7: wavelet delineation of the beats of a window --------------------------------
  * replaces nk.ecg_delineate(ecg_sample, r_peaks, sampling_rate=fs)[1] (neurokit2, default method

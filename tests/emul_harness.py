@@ -221,3 +221,14 @@ def delineate(windows, peaks_list, fs=500.0, select=None):
                              ptr(flags), ptr(ws), wsb, None)
     assert rc == 0, rc
     return fid, flags
+
+
+def widen(src, gain=1.0, offset=0.0, sentinel=None):
+    L = lib()
+    src = np.ascontiguousarray(src)
+    code = {np.dtype(np.float32): 0, np.dtype(np.int16): 1}[src.dtype]
+    out = np.full(len(src), -7.0)
+    rc = L.aew_widen_f64(ptr(src), code, len(src), float(gain), float(offset), 0 if sentinel is None else 1,
+                         0 if sentinel is None else int(sentinel), ptr(out), None)
+    assert rc == 0, rc
+    return out

@@ -244,3 +244,19 @@ def test_k7_delineation_matches_restatement():
     assert seen == {"ok", "nan", "drop"}
     _, fl = eh.delineate(np.stack(wins[:2]), pks[:2], select=[0, 1])
     assert fl.tolist() == [3, 0]                           # unselected windows are left alone
+
+
+def test_k8_widen_matches_numpy():
+    rng = np.random.default_rng(8)
+    for n in (0, 1, 7, 8, 1000, 4099):
+        x = (rng.standard_normal(n) * 3).astype(np.float32)
+        if n > 5:
+            x[3] = np.nan
+        assert same(eh.widen(x), x.astype(np.float64))
+        v = rng.integers(-32768, 32767, n).astype(np.int16)
+        if n > 5:
+            v[2] = -32768
+        want = v.astype(np.float64) * 0.00244 + (-1.25)
+        want[v == -32768] = np.nan
+        assert same(eh.widen(v, 0.00244, -1.25, sentinel=-32768), want)
+        assert same(eh.widen(v, 0.5, 0.0), v.astype(np.float64) * 0.5 + 0.0)

@@ -591,3 +591,34 @@ def test_neurokit_shim(gpu):
     from oracle import nk_peaks
     assert nk.ecg_findpeaks(w, sampling_rate=500)["ECG_R_Peaks"].tolist() == \
         [int(v) for v in nk_peaks.ecg_findpeaks(w, sampling_rate=500)["ECG_R_Peaks"] if 0 < v < len(w)]
+
+
+# ------------------------------------------------------------------------- K8: input feeder
+def test_widen_and_narrow_source_feeder(gpu):
+    torch, B = gpu
+    rng = np.random.default_rng(8)
+    for n in (1, 7, 8, 1000, 4099, 1 << 20):
+        x = (rng.standard_normal(n) * 3).astype(np.float32)
+        x[n // 2] = np.nan
+        assert same(B.widen_to_f64(torch.from_numpy(x).cuda()).cpu().numpy(), x.astype(np.float64))
+        v = rng.integers(-32768, 32767, n).astype(np.int16)
+        v[n // 3] = -32768
+        want = v.astype(np.float64) * 0.00244 + (-1.25)
+        want[v == -32768] = np.nan
+        got = B.widen_to_f64(torch.from_numpy(v).cuda(), gain=0.00244, offset=-1.25, sentinel=-32768)
+        assert same(got.cpu().numpy(), want)
+    # the end-to-end feeder on float32 / int16 host buffers == the device-resident path on the widened values
+    cases = [ecg_synth.synth_case(c, 90000 + 1000 * c) for c in range(5)]
+    off = np.concatenate([[0], np.cumsum([len(c) for c in cases])]).astype(np.int64)
+    flat32 = np.concatenate(cases).astype(np.float32)
+    pre = B.Preprocessor()
+    ref = pre.run(B.RecordBatch.from_host([flat32[off[i]:off[i + 1]].astype(np.float64) for i in range(5)]))
+    got = B.run_host_pipelined(pre, torch.from_numpy(flat32).pin_memory(), off, chunk_cases=2)
+    assert same(got["np_waves"].numpy(), ref["np_waves"].cpu().numpy())
+    assert same(got["np_info"].numpy(), ref["np_info"].cpu().numpy())
+    gain = 1.0 / 4096
+    flat16 = np.clip(np.rint(np.concatenate(cases) / gain), -32767, 32767).astype(np.int16)
+    ref = pre.run(B.RecordBatch.from_host([flat16[off[i]:off[i + 1]].astype(np.float64) * gain + 0.0
+                                           for i in range(5)]))
+    got = B.run_host_pipelined(pre, torch.from_numpy(flat16).pin_memory(), off, chunk_cases=2, gain=gain)
+    assert same(got["np_waves"].numpy(), ref["np_waves"].cpu().numpy()) and len(got["np_waves"]) > 10
