@@ -25,6 +25,7 @@ PER_FILE = {
     "k6_features.cu": ["-fmad=false"],
     "k7_delineate.cu": [],
     "k8_convert.cu": ["-fmad=false"],
+    "k9_metrics.cu": ["-fmad=false"],
     "k2_filtfilt.cu": [],
     "cabi_misc.cu": [],
 }

@@ -128,6 +128,33 @@ class SigmaSearch:
         """(n_beats, 320) float64 reconstructions for one sigma map (analysis_...:121-132)."""
         return self._call(np.asarray(sigma_map, dtype=np.float64).reshape(1, 12), True)[1]
 
+    def metrics(self, sigma_map, medians, compression_ratio: float = 320 / 20):
+        """Per-beat RMSE, PRD and quality score of the reconstruction for one sigma map against the float64
+        median beats (K9; analysis_...:178-197, functions_ae/loss_functions.py:8-20) plus the summary the
+        reference prints: median / quartiles / mean / sd of RMSE and QS (np.percentile = linear interpolation)."""
+        torch = self.torch
+        med = torch.as_tensor(np.ascontiguousarray(medians, dtype=np.float64) if not torch.is_tensor(medians)
+                              else medians, dtype=torch.float64, device=self.device).contiguous()
+        if tuple(med.shape) != (self.n_beats, self.n_t):
+            raise _cabi.AewError("medians must be (n_beats, n_t)")
+        recon = self.reconstruct(sigma_map)
+        out = [torch.empty(self.n_beats, dtype=torch.float32, device=self.device) for _ in range(3)]
+        _cabi.check(self.lib.aew_beat_metrics_f32(
+            ctypes.c_void_p(recon.data_ptr()), ctypes.c_void_p(med.data_ptr()), self.n_beats, self.n_t,
+            float(compression_ratio), *[ctypes.c_void_p(t.data_ptr()) for t in out],
+            _cabi.stream_ptr(torch)), "beat_metrics")
+        rmse, prd, qs = out
+        q = torch.tensor([0.25, 0.5, 0.75], dtype=torch.float64, device=self.device)
+
+        def summary(v):
+            v = v.to(torch.float64)
+            ok = v[~torch.isnan(v)]
+            qq = torch.quantile(ok, q) if ok.numel() else torch.full((3,), float("nan"), device=self.device)
+            return {"q1": float(qq[0]), "median": float(qq[1]), "q3": float(qq[2]),
+                    "mean": float(v.mean()), "sd": float(v.std(unbiased=False))}
+        return {"rmse": rmse, "prd": prd, "qs": qs, "recon": recon,
+                "summary": {"rmse": summary(rmse), "qs": summary(qs), "prd_mean": float(prd.mean())}}
+
     def best(self, candidates, sse=None):
         """argmin over the candidate list (NaN losses never win)."""
         torch = self.torch

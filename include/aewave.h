@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AEW_VERSION 104
+#define AEW_VERSION 105
 
 /* return codes */
 #define AEW_OK 0
@@ -137,6 +137,15 @@ int aew_windows_timing_dump(unsigned long long* h_out16);
 int aew_median_beats_f64(const double* d_windows, long long n_win, int L, const int* d_peaks,
                          const long long* d_peak_off, int max_peaks_per_window, int pre, int post,
                          double* d_median, double* d_aligned, void* stream);
+
+/* ---- K9: per-beat error metrics of a reconstruction ------------------
+ * replaces sample_rmse_loss / sample_prd_loss (functions_ae/loss_functions.py:8-20) and the quality score
+ * as used at analysis_performance_traditional_vs_ae.py:178-197: true = float32(median beat),
+ * pred = float32(y_gauss + rowmax(median beat)); rmse = sqrt(mean((pred-true)^2)),
+ * prd = 100 sqrt(sum((true-pred)^2) / sum(true^2)), qs = compression_ratio / prd (320 / 20 in the reference).
+ *   d_recon, d_median [n_beats][n_t] float64; outputs [n_beats] float32 */
+int aew_beat_metrics_f32(const double* d_recon, const double* d_median, long long n_beats, int n_t,
+                         double compression_ratio, float* d_rmse, float* d_prd, float* d_qs, void* stream);
 
 /* ---- K8: narrow source samples -> float64 (the input side) ----------
  * the float64 frame that data_load_preprocess/load_record.py:7-37 hands to process_case_id

@@ -232,3 +232,14 @@ def widen(src, gain=1.0, offset=0.0, sentinel=None):
                          0 if sentinel is None else int(sentinel), ptr(out), None)
     assert rc == 0, rc
     return out
+
+
+def beat_metrics(recon, median, cr=16.0):
+    L = lib()
+    recon = np.ascontiguousarray(recon, dtype=np.float64)
+    median = np.ascontiguousarray(median, dtype=np.float64)
+    n, nt = recon.shape
+    out = [np.zeros(n, np.float32) for _ in range(3)]
+    rc = L.aew_beat_metrics_f32(ptr(recon), ptr(median), n, nt, float(cr), ptr(out[0]), ptr(out[1]), ptr(out[2]), None)
+    assert rc == 0, rc
+    return out

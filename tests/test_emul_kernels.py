@@ -260,3 +260,16 @@ def test_k8_widen_matches_numpy():
         want[v == -32768] = np.nan
         assert same(eh.widen(v, 0.00244, -1.25, sentinel=-32768), want)
         assert same(eh.widen(v, 0.5, 0.0), v.astype(np.float64) * 0.5 + 0.0)
+
+
+def test_k9_beat_metrics_match_torch():
+    rng = np.random.default_rng(9)
+    med = rng.standard_normal((37, 320)).cumsum(axis=1) * 0.1
+    y = med - med.max(axis=1, keepdims=True) + 0.05 * rng.standard_normal((37, 320))
+    y[5, 17] = np.nan                                     # a NaN reconstruction poisons that beat only
+    rmse, prd, qs = eh.beat_metrics(y, med)
+    w_rmse, w_prd, w_qs = rp.beat_metrics(y, med)
+    for got, want in ((rmse, w_rmse), (prd, w_prd), (qs, w_qs)):
+        assert same(np.isnan(got), np.isnan(want))
+        ok = ~np.isnan(want)
+        assert np.all(np.abs(got[ok] - want[ok]) <= 1e-5 * np.abs(want[ok]))     # float32 outputs: SURVEY.md C.5

@@ -622,3 +622,26 @@ def test_widen_and_narrow_source_feeder(gpu):
                                            for i in range(5)]))
     got = B.run_host_pipelined(pre, torch.from_numpy(flat16).pin_memory(), off, chunk_cases=2, gain=gain)
     assert same(got["np_waves"].numpy(), ref["np_waves"].cpu().numpy()) and len(got["np_waves"]) > 10
+
+
+# ------------------------------------------------------------------------- K9: post-search metrics
+def test_beat_metrics_match_reference_torch(gpu):
+    from ae_waveforms_b200.sigma_search import SigmaSearch
+    torch, B = gpu
+    tt, fx, fy, bl = ecg_synth.synth_fiducials(300, seed=4)
+    rng = np.random.default_rng(4)
+    med = tt.astype(np.float64) + rng.uniform(0.5, 3.0, size=(len(tt), 1))      # medians whose row max is not 0
+    sigma_map = [1, 2, 2, 3, 2, 3, 3, 2, 3, 2, 2, 1]                            # analysis_...:121
+    s = SigmaSearch(fx, fy, bl, tt)
+    m = s.metrics(sigma_map, med)
+    y = np.array([rp.reconstruct_gaussian(fx[i], fy[i], rp.beat_time_axis(), bl[i], sigma_map) for i in range(len(tt))])
+    assert close(m["recon"].cpu().numpy(), y)
+    want = rp.beat_metrics(y, med)
+    for key, w in zip(("rmse", "prd", "qs"), want):
+        g = m[key].cpu().numpy()
+        assert same(np.isnan(g), np.isnan(w))
+        ok = ~np.isnan(w)
+        assert np.all(np.abs(g[ok] - w[ok]) <= 1e-5 * np.abs(w[ok])), key
+    ok = ~np.isnan(want[0])
+    assert abs(m["summary"]["rmse"]["median"] - np.median(want[0][ok])) <= 1e-5 * np.median(want[0][ok])
+    assert abs(m["summary"]["qs"]["q3"] - np.percentile(want[2][ok], 75)) <= 1e-5 * np.percentile(want[2][ok], 75)
