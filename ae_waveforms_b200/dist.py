@@ -45,17 +45,21 @@ def allgather_rows(t, group=None):
     return [b[:c] for b, c in zip(bufs, counts)]
 
 
-def gather_beat_arrays(np_waves, np_info, group=None):
-    """All-gather the per-rank ``np_waves`` (f32) and ``np_info`` (f64) and restore the
-    case-major order of data_create_arrays.py:27-48 by sorting on (case_id, idx_end)."""
+def gather_beat_arrays(np_waves, np_info, group=None, np_features=None):
+    """All-gather the per-rank ``np_waves`` (f32) and ``np_info`` (f64) -- and ``np_features`` (f64, n x 35)
+    when given -- and restore the case-major order of data_create_arrays.py:27-48 by sorting on
+    (case_id, idx_end).  Returns (waves, info) or (waves, info, features)."""
     import torch
     waves = torch.cat(allgather_rows(np_waves, group), dim=0)
     info = torch.cat(allgather_rows(np_info, group), dim=0)
+    feats = None if np_features is None else torch.cat(allgather_rows(np_features, group), dim=0)
     if info.shape[0]:
         key = info[:, 0].to(torch.int64) * (1 << 40) + info[:, 1].to(torch.int64)
         order = torch.argsort(key, stable=True)
         waves, info = waves.index_select(0, order), info.index_select(0, order)
-    return waves, info
+        if feats is not None:
+            feats = feats.index_select(0, order)
+    return (waves, info) if np_features is None else (waves, info, feats)
 
 
 def allreduce_sse(sse, group=None):

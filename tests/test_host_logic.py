@@ -103,6 +103,11 @@ def _gloo_worker(rank, world, port, q):
         info = torch.from_numpy(np.stack([np.full(n, float(10 * (world - rank))), (np.arange(n) + 1) * 10000.0], 1))
         parts = awd.allgather_rows(waves)
         gw, gi = awd.gather_beat_arrays(waves, info)
+        feats = torch.from_numpy(np.repeat(info.numpy()[:, 1:2] + rank, 35, axis=1))       # rows tagged by idx_end + rank
+        gw2, gi2, gf = awd.gather_beat_arrays(waves, info, np_features=feats)
+        assert torch.equal(gw2, gw) and torch.equal(gi2, gi) and gf.shape == (gi.shape[0], 35)
+        src_rank = world - (gi[:, 0] / 10).to(torch.int64)                                 # case id encodes the rank
+        assert torch.equal(gf[:, 0], gi[:, 1] + src_rank.to(torch.float64))                # features follow their rows
         sse = torch.tensor([1.0 + rank, 2.0, float("nan") if rank == 1 else 0.5], dtype=torch.float64)
         awd.allreduce_sse(sse)
         q.put((rank, [p.shape[0] for p in parts], gw.numpy(), gi.numpy(), sse.numpy(), waves.numpy(), info.numpy()))
