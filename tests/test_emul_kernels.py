@@ -273,3 +273,27 @@ def test_k9_beat_metrics_match_torch():
         assert same(np.isnan(got), np.isnan(want))
         ok = ~np.isnan(want)
         assert np.all(np.abs(got[ok] - want[ok]) <= 1e-5 * np.abs(want[ok]))     # float32 outputs: SURVEY.md C.5
+
+
+def _other_geometry_windows():
+    """10 s strips at 500 Hz (the configs[2] adaptation, L = 5,000) and 20 s windows at 250 Hz."""
+    from oracle import nk_peaks
+    case = ecg_synth.synth_case(31, 40000, hr_bpm=80.0)
+    f = rp.butterworth(rp.butterworth(rp.zscore(case), "high", 1, 500, 4), "low", 30, 500, 4)
+    out = []
+    for sig, fs in ((f[10000:15000], 500), (f[::2][5000:10000], 250)):
+        w = rp.zscore(sig)
+        p = [int(v) for v in nk_peaks.ecg_findpeaks(w, fs)["ECG_R_Peaks"] if 0 < v < len(w)]
+        out.append((w, p, fs))
+    return out
+
+
+def test_k7_other_window_lengths_and_rates():
+    from oracle import nk_delineate as nd
+    for w, p, fs in _other_geometry_windows():
+        fid, flags = eh.delineate(w[None, :], [p], fs=float(fs))
+        st, ref = nd.window_fiducials(w, p, fs)
+        assert st == "ok" and flags[0] == 0
+        got = fid[0, :, :len(p)].astype(np.float64)
+        got[got == eh.FID_NAN] = np.nan
+        assert same(got, ref), fs

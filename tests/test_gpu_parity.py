@@ -645,3 +645,33 @@ def test_beat_metrics_match_reference_torch(gpu):
     ok = ~np.isnan(want[0])
     assert abs(m["summary"]["rmse"]["median"] - np.median(want[0][ok])) <= 1e-5 * np.median(want[0][ok])
     assert abs(m["summary"]["qs"]["q3"] - np.percentile(want[2][ok], 75)) <= 1e-5 * np.percentile(want[2][ok], 75)
+
+
+def test_delineation_other_window_lengths_and_rates(gpu):
+    """10 s strips at 500 Hz (configs[2] adaptation, L = 5,000) and 20 s windows at 250 Hz."""
+    from oracle import nk_delineate as nd, nk_peaks
+    torch, B = gpu
+    case = ecg_synth.synth_case(31, 90000, hr_bpm=80.0)
+    f = rp.butterworth(rp.butterworth(rp.zscore(case), "high", 1, 500, 4), "low", 30, 500, 4)
+    for fs, sig in ((500, f[10000:]), (250, f[::2][5000:])):
+        n = len(sig) // 5000
+        wins = [rp.zscore(sig[k * 5000:(k + 1) * 5000]) for k in range(n)]
+        pks = [[int(v) for v in nk_peaks.ecg_findpeaks(w, fs)["ECG_R_Peaks"] if 0 < v < 5000] for w in wins]
+        pre = B.Preprocessor(fs=fs, sample_length=5000 / fs)
+        maxp = pre.lib.aew_windows_max_peaks()
+        pk = np.full((n, maxp), -1, np.int32)
+        for i, p in enumerate(pks):
+            pk[i, :len(p)] = p
+        dev = pre.device
+        d_sig = torch.from_numpy(np.ascontiguousarray(np.stack(wins).reshape(-1))).to(dev)
+        off = torch.arange(n, dtype=torch.int64, device=dev) * 5000
+        fid, flags = pre.delineate_windows(d_sig, off, torch.from_numpy(pk).to(dev),
+                                           torch.tensor([len(p) for p in pks], dtype=torch.int32, device=dev), L=5000)
+        fid, flags = fid.cpu().numpy(), flags.cpu().numpy()
+        for i, (w, p) in enumerate(zip(wins, pks)):
+            st, ref = nd.window_fiducials(w, p, fs)
+            assert flags[i] == {"ok": 0, "nan": 1, "drop": 2}[st], (fs, i)
+            if st == "ok":
+                got = fid[i, :, :len(p)].astype(np.float64)
+                got[got == FID_NAN] = np.nan
+                assert same(got, ref), (fs, i)
