@@ -279,6 +279,28 @@ def bench_sigma_search(device, n_beats=65536, n_cand=256, steps=3):
     big = torch.from_numpy(lhs(16 * n_cand)).to(device)
     big[:n_cand] = torch.from_numpy(cand).to(device)
     sse_t, ms_t = timed(big, "tables")
+    # BASELINE configs[3] at its full size: 1,000,000 beats x 4,096 Latin-hypercube integer maps (tables kernel)
+    full = None
+    try:
+        del s
+        tf, fxf, fyf, blf = synth_fiducials_gpu(1000000, device, seed=3)
+        sf = SigmaSearch(fxf, fyf, blf, tf, device=device)
+        for _ in range(1):
+            sse_f = sf.sse(big, method="tables")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        sse_f = sf.sse(big, method="tables")
+        e1.record()
+        torch.cuda.synchronize()
+        ms_f = e0.elapsed_time(e1)
+        fin = torch.where(torch.isnan(sse_f), torch.full_like(sse_f, float("inf")), sse_f)
+        full = {"n_beats": 1000000, "n_candidates": int(big.shape[0]), "ms": ms_f,
+                "beat_candidates_per_s": 1e6 * big.shape[0] / (ms_f / 1e3), "best_candidate": int(torch.argmin(fin).item()),
+                "best_mse": float(fin.min().item()) / (1e6 * 320)}
+        del sf, tf, fxf, fyf, blf
+    except Exception as exc:
+        full = {"error": str(exc)[:200]}
     ok = torch.isfinite(sse)
     dev_rel = float(((sse_t[:n_cand][ok] - sse[ok]).abs() / sse[ok]).max().item()) if bool(ok.any()) else None
     return {"beat_candidates_per_s": n_beats * n_cand / (ms / 1e3), "n_beats": n_beats, "n_candidates": n_cand,
@@ -288,7 +310,8 @@ def bench_sigma_search(device, n_beats=65536, n_cand=256, steps=3):
             "tables": {"n_candidates": 16 * n_cand, "ms": ms_t,
                        "beat_candidates_per_s": n_beats * 16 * n_cand / (ms_t / 1e3),
                        "max_rel_diff_vs_direct": dev_rel,
-                       "formulation": "separable error tables over the 5-value grid + 157 look-ups per candidate"}}
+                       "formulation": "separable error tables over the 5-value grid + 157 look-ups per candidate"},
+            "configs3_full_size": full}
 
 
 # ----------------------------------------------------------------------------- GPU arm

@@ -675,3 +675,62 @@ def test_delineation_other_window_lengths_and_rates(gpu):
                 got = fid[i, :, :len(p)].astype(np.float64)
                 got[got == FID_NAN] = np.nan
                 assert same(got, ref), (fs, i)
+
+
+# ------------------------------------------------------------------------- full-size properties (BASELINE configs[1])
+def test_full_size_properties_1000_cases(gpu):
+    """configs[1] at its full size (1,000 cases x 1 h, 1.8e9 samples, 14.4 GB): properties that do not need
+    the oracle -- the result must not depend on how the cases are batched or ordered, rows are case-major,
+    every case contributes at most 179 windows, R peaks sit where the beat window puts them, and the
+    delineation + feature stage is reproducible and complete on every kept window."""
+    import bench
+    torch, B = gpu
+    if torch.cuda.mem_get_info()[1] < 90e9:
+        pytest.skip("needs a full B200 (about 60 GB of HBM)")
+    n_cases, ns = 1000, 1800000
+    dev = torch.device("cuda")
+    ids = np.arange(n_cases)
+    flat = bench.synth_cases_gpu(ids, ns, dev)
+    off = np.arange(n_cases + 1, dtype=np.int64) * ns
+    pre = B.Preprocessor()
+    scratch = {"y": torch.empty_like(flat), "tmp": torch.empty_like(flat)}
+    res = pre.run(B.RecordBatch(flat, off, ids), scratch=scratch, features=True)
+    waves, info, feats = res["np_waves"].clone(), res["np_info"].clone(), res["np_features"].clone()
+    n = waves.shape[0]
+    assert 100000 < n <= 179 * n_cases and feats.shape == (n, 35) and res["n_windows"] == 179 * n_cases
+    case, end = info[:, 0].to(torch.int64), info[:, 1].to(torch.int64)
+    key = case * (1 << 40) + end
+    assert bool((key[1:] > key[:-1]).all())                                  # case-major, idx_end ascending
+    assert bool((end % 10000 == 0).all()) and int(end.min()) >= 10000 and int(end.max()) <= 1790000
+    assert int(torch.bincount(case, minlength=n_cases).max()) <= 179
+    assert bool((waves.argmax(dim=1) == 106).float().mean() > 0.999)         # the R peak's column (median_sample.py:20-25)
+    assert not bool(torch.isnan(waves).any())
+    assert float(torch.isnan(feats).double().mean()) < 1e-3                  # nearly every fiducial found on clean ECG
+    ok = ~torch.isnan(feats[:, 0])
+    assert bool((feats[ok, 0] < 0).all())                                    # P peak before R ...
+    ok = ~torch.isnan(feats[:, 14])
+    assert bool((feats[ok, 14] > 0).all())                                   # ... T peak after it
+    # batching independence: the second half of the cases alone, and 100-case chunks, give the same rows bit for bit
+    h = n_cases // 2
+    sub = pre.run(B.RecordBatch(flat[h * ns:], off[h:] - off[h], ids[h:]),
+                  scratch={"y": scratch["y"][:(n_cases - h) * ns], "tmp": scratch["tmp"][:(n_cases - h) * ns]},
+                  features=True)
+    sel = case >= h
+    assert torch.equal(sub["np_waves"], waves[sel]) and torch.equal(sub["np_info"], info[sel])
+    assert torch.equal(torch.nan_to_num(sub["np_features"], nan=-1e300), torch.nan_to_num(feats[sel], nan=-1e300))
+    del sub
+    rows = 0
+    for c0 in range(0, n_cases, 100):
+        part = pre.run(B.RecordBatch(flat[c0 * ns:(c0 + 100) * ns], off[c0:c0 + 101] - off[c0], ids[c0:c0 + 100]),
+                       scratch={"y": scratch["y"][:100 * ns], "tmp": scratch["tmp"][:100 * ns]})
+        k = part["np_waves"].shape[0]
+        assert torch.equal(part["np_waves"], waves[rows:rows + k]) and torch.equal(part["np_info"], info[rows:rows + k])
+        rows += k
+    assert rows == n
+    # affine invariance of the z-scored path: 3 x + 7 gives the same windows and (to rounding) the same beats
+    flat.mul_(3.0).add_(7.0)
+    aff = pre.run(B.RecordBatch(flat, off, ids), scratch=scratch)
+    assert aff["np_waves"].shape[0] >= n - 5 and aff["np_waves"].shape[0] <= n + 5     # sd/n_peaks ulp hazard only
+    if aff["np_waves"].shape[0] == n:
+        assert torch.equal(aff["np_info"], info)
+        assert float((aff["np_waves"] - waves).abs().max()) < 1e-5
