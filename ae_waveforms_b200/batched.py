@@ -324,7 +324,7 @@ class Preprocessor:
 
     # ------------------------------------------------------------------ whole path
     def run(self, batch: RecordBatch, trim: bool = True, keep_intermediates: bool = False,
-            scratch: dict | None = None, features: bool = False) -> dict:
+            scratch: dict | None = None, features: bool = False, strips: bool = False) -> dict:
         """Returns a dict of CUDA tensors: ``np_waves`` (n_keep, 320) float32,
         ``np_info`` (n_keep, 2) float64 = [case_id, idx_end], ``medians`` float64,
         plus per-window ``keep`` / ``has_nan`` / ``n_peaks`` / ``peaks`` / ``stats`` and
@@ -335,7 +335,16 @@ class Preprocessor:
         mean, sd, cnt = self.zscore_stats(flat, beg_h, end_h, d_beg, d_end)
         y, header = self.filter_records(flat, beg_h, end_h, d_beg, d_end, mean, sd, cnt,
                                         out=(scratch or {}).get("y"), tmp=(scratch or {}).get("tmp"))
-        win_start, win_case, win_end = self.window_table(beg_h, end_h, batch.case_ids)
+        if strips:
+            # BASELINE configs[2] (10 s 12-lead strips): sample_from_record's exclusive stop would cut no window
+            # from a record of exactly L samples, so every (record, lead) strip IS one window
+            if np.any(end_h - beg_h != self.L):
+                raise _cabi.AewError(f"strips=True needs records of exactly {self.L} samples")
+            win_start = np.ascontiguousarray(beg_h, dtype=np.int64)
+            win_case = np.asarray(batch.case_ids)
+            win_end = np.full(len(beg_h), self.L, dtype=np.int64)
+        else:
+            win_start, win_case, win_end = self.window_table(beg_h, end_h, batch.case_ids)
         info_h = np.stack([win_case.astype(np.float64), win_end.astype(np.float64)], axis=1) if len(win_start) \
             else np.zeros((0, 2))
         info = torch.from_numpy(info_h).to(self.device)             # (uploaded while the filter is still running)

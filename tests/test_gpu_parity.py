@@ -734,3 +734,32 @@ def test_full_size_properties_1000_cases(gpu):
     if aff["np_waves"].shape[0] == n:
         assert torch.equal(aff["np_info"], info)
         assert float((aff["np_waves"] - waves).abs().max()) < 1e-5
+
+
+# ------------------------------------------------------------------------- configs[2]: 12-lead 10 s strips
+def test_strips_mode_12_lead_records(gpu):
+    """BASELINE configs[2] shape (records x 12 leads x 5,000 samples): every (record, lead) strip is filtered on
+    its own and taken as ONE window (the reference's windowing cuts none from a record of exactly L samples).
+    The sd/n_peaks threshold is 0.05 for 20 s windows (n_peaks >= 20); a 10 s strip needs 0.1 for the same rate."""
+    torch, B = gpu
+    n_rec, n_lead, L = 24, 12, 5000
+    strips, ids = [], []
+    for r in range(n_rec):
+        base = ecg_synth.synth_case(400 + r, L, hr_bpm=66.0 + 4 * r)
+        for l in range(n_lead):
+            x = base * (0.4 + 0.1 * l) + 0.01 * np.random.default_rng(r * 12 + l).standard_normal(L)
+            if r == 5 and l == 3:
+                x[1000:1040] = np.nan                      # a gap: the strip is removed (NaN window)
+            strips.append(x); ids.append(r * n_lead + l)
+    pre = B.Preprocessor(sample_length=10, sd_threshold=0.1, filter_mode="exact")
+    res = pre.run(B.RecordBatch.from_host(strips, ids), strips=True, features=True)
+    refs = [rp.process_case(x, case_id=i, sample_length=10, strip=True, sd_threshold_ecg=0.1, features=True)
+            for x, i in zip(strips, ids)]
+    want_w = np.concatenate([r["np_waves"] for r in refs])
+    want_i = np.concatenate([r["np_info"] for r in refs])
+    want_f = np.concatenate([r["np_features"] for r in refs])
+    assert len(want_w) > 200
+    assert same(res["np_info"].cpu().numpy(), want_i) and same(res["np_waves"].cpu().numpy(), want_w)
+    assert same(res["np_features"].cpu().numpy(), want_f)
+    with pytest.raises(Exception):
+        pre.run(B.RecordBatch.from_host([strips[0][:4000]], [0]), strips=True)
