@@ -408,13 +408,14 @@ def widen_to_f64(src, out=None, gain: float = 1.0, offset: float = 0.0, sentinel
 
 def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chunk_cases: int = 100,
                        to_host: bool = True, pinned_results: bool = False, gain: float = 1.0, offset: float = 0.0,
-                       sentinel: int | None = None) -> dict:
+                       sentinel: int | None = None, features: bool = False) -> dict:
     """End-to-end path for HOST data: ``host_flat`` is a (preferably pinned) CPU tensor holding all records back
     to back -- float64, or the narrower source type (float32; int16 with ``gain`` / ``offset`` and an optional
     ``sentinel`` for missing samples), which then crosses PCIe as it is and is widened on the device (K8).  Cases are fed in chunks through two device
     input buffers: the host->device copy of chunk k+1 (copy stream) overlaps the kernels of
     chunk k (current stream), and the device->host copy of chunk k's rows (third stream, into
     page-locked memory) overlaps both, so the wall time is max(PCIe, kernels) instead of their sum.
+    With ``features`` the wave delineation and the 35 features per window run as well (``np_features`` (n,35) f64).
     Returns ``np_waves`` (n,320) f32 and ``np_info`` (n,2) f64 in case order, as host tensors
     (``to_host``) or left on the device (e.g. for a following all-gather).  With ``pinned_results`` the host
     tensors are views of a reusable page-locked pool (valid until the next call) instead of fresh copies."""
@@ -440,6 +441,7 @@ def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chu
         max_rows = int(sum(window_count(int(rec_off[r + 1] - rec_off[r]), pre.L) for r in range(n_rec)))
         h_waves = _pinned("waves", (max(max_rows, 1), BEAT_LEN), torch.float32, torch)
         h_info = _pinned("info", (max(max_rows, 1), 2), torch.float64, torch)
+        h_feat = _pinned("feat", (max(max_rows, 1), 35), torch.float64, torch) if features else None
         back_stream = torch.cuda.Stream(device=pre.device)
 
     def start_copy(k):
@@ -455,7 +457,7 @@ def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chu
                 bufs[k % 2][p0 - lo:p1 - lo].copy_(host_flat[p0:p1], non_blocking=True)
             copied[k].record(copy_stream)
 
-    waves, infos, hazards, n_windows, n_beats, rows = [], [], 0, 0, 0, 0
+    waves, infos, feats, hazards, n_windows, n_beats, rows = [], [], [], 0, 0, 0, 0
     if chunks:
         start_copy(0)
     for k, (c0, c1) in enumerate(chunks):
@@ -471,11 +473,13 @@ def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chu
             chunk_in = bufs[k % 2][:sizes[k]]
         sub = RecordBatch(chunk_in, rec_off[c0:c1 + 1] - rec_off[c0], case_ids[c0:c1])
         sc = {"y": scratch["y"][:sizes[k]], "tmp": scratch["tmp"][:sizes[k]]}
-        res = pre.run(sub, scratch=sc)
+        res = pre.run(sub, scratch=sc, features=features)
         if not narrow:
             freed[k].record(main)
         waves.append(res["np_waves"])
         infos.append(res["np_info"])
+        if features:
+            feats.append(res["np_features"])
         if to_host:
             n = res["np_waves"].shape[0]
             done = torch.cuda.Event()
@@ -484,6 +488,8 @@ def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chu
                 back_stream.wait_event(done)
                 h_waves[rows:rows + n].copy_(res["np_waves"], non_blocking=True)
                 h_info[rows:rows + n].copy_(res["np_info"], non_blocking=True)
+                if features:
+                    h_feat[rows:rows + n].copy_(res["np_features"], non_blocking=True)
             rows += n
         hazards += res["hazard_windows"]
         n_windows += res["n_windows"]
@@ -491,12 +497,19 @@ def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chu
     if to_host:
         back_stream.synchronize()
         np_waves, np_info = h_waves[:rows], h_info[:rows]
+        np_feat = h_feat[:rows] if features else None
         if not pinned_results:
             np_waves, np_info = np_waves.clone(), np_info.clone()
+            np_feat = np_feat.clone() if features else None
     else:
+        np_feat = (torch.cat(feats) if feats else torch.zeros((0, 35), dtype=torch.float64, device=pre.device)) \
+            if features else None
         np_waves = torch.cat(waves) if waves else torch.zeros((0, BEAT_LEN), dtype=torch.float32, device=pre.device)
         np_info = torch.cat(infos) if infos else torch.zeros((0, 2), dtype=torch.float64, device=pre.device)
-    return dict(np_waves=np_waves, np_info=np_info, hazard_windows=hazards, n_windows=n_windows, n_beats=n_beats)
+    out = dict(np_waves=np_waves, np_info=np_info, hazard_windows=hazards, n_windows=n_windows, n_beats=n_beats)
+    if features:
+        out["np_features"] = np_feat
+    return out
 
 
 def process_cases(records, case_ids=None, **kwargs) -> dict:

@@ -461,6 +461,25 @@ def run_gpu(args):
         barrier()
         e2e_s = time.perf_counter() - t0
         e2e = {"seconds": e2e_s, "h2d": total * 8, "d2h": w_h.numel() * 4 + i_h.numel() * 8}
+        if world == 1:                                 # the same call with delineation + features switched on
+            try:
+                rf = batched.run_host_pipelined(pre, host, rec_off, case_ids, chunk_cases=max(1, n_cases // 10),
+                                                to_host=True, pinned_results=True, features=True)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(2):
+                    rf = batched.run_host_pipelined(pre, host, rec_off, case_ids, chunk_cases=max(1, n_cases // 10),
+                                                    to_host=True, pinned_results=True, features=True)
+                torch.cuda.synchronize()
+                sf = (time.perf_counter() - t0) / 2
+                e2e["with_features"] = {"value": total / sf / 1e6, "unit": UNIT, "h2d_bytes_per_step": total * 8,
+                                        "d2h_bytes_per_step": rf["np_waves"].numel() * 4 + rf["np_info"].numel() * 8
+                                        + rf["np_features"].numel() * 8,
+                                        "np_features_rows": int(rf["np_features"].shape[0])}
+                del rf
+                pre._k7_ws = None
+            except Exception as exc:
+                e2e["with_features"] = {"error": str(exc)[:200]}
     except RuntimeError as exc:                        # e.g. not enough pinned host memory
         e2e = {"error": str(exc)[:200]}
 
@@ -547,6 +566,8 @@ def run_gpu(args):
         if "seconds" in e2e:
             out["e2e"] = {"value": tot_samples * args.steps / (e2e_ms_all / 1e3) / 1e6, "unit": UNIT,
                           "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"]}
+            if "with_features" in e2e:
+                out["e2e_with_features"] = e2e["with_features"]
         else:
             out["e2e"] = {"value": None, "unit": UNIT, "error": e2e.get("error")}
         if e2e32 is not None:

@@ -616,6 +616,11 @@ def test_widen_and_narrow_source_feeder(gpu):
     got = B.run_host_pipelined(pre, torch.from_numpy(flat32).pin_memory(), off, chunk_cases=2)
     assert same(got["np_waves"].numpy(), ref["np_waves"].cpu().numpy())
     assert same(got["np_info"].numpy(), ref["np_info"].cpu().numpy())
+    gotf = B.run_host_pipelined(pre, torch.from_numpy(flat32).pin_memory(), off, chunk_cases=2, features=True)
+    reff = pre.run(B.RecordBatch.from_host([flat32[off[i]:off[i + 1]].astype(np.float64) for i in range(5)]),
+                   features=True)
+    assert same(gotf["np_waves"].numpy(), reff["np_waves"].cpu().numpy())
+    assert same(gotf["np_features"].numpy(), reff["np_features"].cpu().numpy()) and gotf["np_features"].shape[1] == 35
     gain = 1.0 / 4096
     flat16 = np.clip(np.rint(np.concatenate(cases) / gain), -32767, 32767).astype(np.int16)
     ref = pre.run(B.RecordBatch.from_host([flat16[off[i]:off[i + 1]].astype(np.float64) * gain + 0.0
