@@ -768,3 +768,26 @@ def test_strips_mode_12_lead_records(gpu):
     assert same(res["np_features"].cpu().numpy(), want_f)
     with pytest.raises(Exception):
         pre.run(B.RecordBatch.from_host([strips[0][:4000]], [0]), strips=True)
+
+
+# ------------------------------------------------------------------------- on-disk store + resume
+def test_process_to_store_resumes(gpu, tmp_path):
+    from ae_waveforms_b200.store import ArrayStore, process_to_store
+    torch, B = gpu
+    cases = {c: ecg_synth.synth_case(c, 60000 + 500 * c) for c in (3, 5, 6, 9, 10)}
+    pre = B.Preprocessor()
+    calls = []
+
+    def records_of(ids):
+        calls.append(list(ids))
+        return [cases[c] for c in ids]
+
+    root = str(tmp_path / "store")
+    process_to_store(ArrayStore(root), pre, records_of, [3, 5], chunk_cases=2)          # a first, interrupted run
+    process_to_store(ArrayStore(root), pre, records_of, sorted(cases), chunk_cases=2)   # the resumed run
+    assert calls == [[3, 5], [6, 9], [10]]                                              # finished cases are not redone
+    out = ArrayStore(root).finalize()
+    ref = pre.run(B.RecordBatch.from_host([cases[c] for c in sorted(cases)], sorted(cases)), features=True)
+    assert same(out["np_waves"], ref["np_waves"].cpu().numpy()) and same(out["np_info"], ref["np_info"].cpu().numpy())
+    assert same(out["np_features"], ref["np_features"].cpu().numpy())
+    assert same(np.load(os.path.join(root, "np_features.npy")), out["np_features"])

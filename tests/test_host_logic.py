@@ -143,3 +143,36 @@ def test_synthetic_generator_is_seeded():
     c = ecg_synth.sigma_candidates(64, "integer")
     assert c.shape == (66, 12) and set(np.unique(c)) <= {1.0, 2.0, 3.0, 4.0, 5.0}
     assert c[-2].tolist() == [1, 1, 1, 2, 2, 3, 3, 3, 4, 2, 2, 1]
+
+
+def test_array_store_resume_and_final_arrays(tmp_path):
+    """per-chunk shards + manifest: resume skips finished cases, a half-written shard is ignored, the final
+    arrays are case-major with the reference's dtypes and file names (data_create_arrays.py:17-58)."""
+    from ae_waveforms_b200.store import ArrayStore
+    rng = np.random.default_rng(1)
+
+    def rows(case, n):
+        info = np.stack([np.full(n, float(case)), (np.arange(n) + 1) * 10000.0], 1)
+        return rng.standard_normal((n, 320)).astype(np.float32), info, rng.standard_normal((n, 35))
+
+    root = str(tmp_path / "out")
+    st = ArrayStore(root)
+    a = [rows(7, 3), rows(9, 0), rows(8, 2)]
+    st.add_chunk([7, 9, 8], np.concatenate([x[0] for x in a]), np.concatenate([x[1] for x in a]),
+                 np.concatenate([x[2] for x in a]))
+    b = [rows(2, 4)]
+    st.add_chunk([2], b[0][0], b[0][1])                                       # no features: NaN rows
+    with pytest.raises(ValueError):
+        st.add_chunk([8], *rows(8, 1))                                         # already stored
+    open(os.path.join(root, "shards", "50_60.npz.tmp"), "wb").write(b"partial")  # a killed run's leftover
+    st2 = ArrayStore(root)                                                     # a new process resumes
+    assert st2.pending([2, 7, 8, 9, 11, 12]) == [11, 12]
+    st2.add_chunk([11, 12], *rows(12, 2))
+    out = st2.finalize()
+    assert out["np_waves"].dtype == np.float32 and out["np_features"].dtype == np.float64
+    assert out["np_info"][:, 0].tolist() == [2] * 4 + [7] * 3 + [8] * 2 + [12] * 2
+    assert out["case_ids"] == [2, 7, 8, 12] and out["samples_total"] == 11     # case 9 and 11: no rows
+    assert np.array_equal(out["np_waves"][4:7], a[0][0]) and np.array_equal(out["np_features"][7:9], a[2][2])
+    assert np.isnan(out["np_features"][:4]).all()
+    for name, shape in (("np_waves", (11, 320)), ("np_features", (11, 35)), ("np_info", (11, 2))):
+        assert np.load(os.path.join(root, name + ".npy")).shape == shape
