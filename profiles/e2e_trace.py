@@ -11,7 +11,8 @@ host = torch.empty(flat.numel(), dtype=torch.float64, pin_memory=True); host.cop
 del flat; torch.cuda.empty_cache()
 rec_off = np.arange(n_cases + 1, dtype=np.int64) * ns
 pre = batched.Preprocessor()
-for rep in range(8):
+FEAT = os.environ.get("FEAT", "0") == "1"          # FEAT=1: delineation + features switched on
+for rep in range(8 if not FEAT else 0):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     r = batched.run_host_pipelined(pre, host, rec_off, None, chunk_cases=n_cases // 10, to_host=False)
     w = r["np_waves"].cpu(); torch.cuda.synchronize(); t1 = time.perf_counter()
@@ -43,7 +44,7 @@ for k, (c0, c1) in enumerate(chunks):
     k_beg[k].record(main)
     sub = batched.RecordBatch(bufs[k % 2][:(c1 - c0) * ns], rec_off[c0:c1 + 1] - rec_off[c0], np.arange(c0, c1))
     th = time.perf_counter()
-    res = pre.run(sub, scratch={"y": scratch["y"][:(c1 - c0) * ns], "tmp": scratch["tmp"][:(c1 - c0) * ns]})
+    res = pre.run(sub, scratch={"y": scratch["y"][:(c1 - c0) * ns], "tmp": scratch["tmp"][:(c1 - c0) * ns]}, features=FEAT)
     host_t.append(1e3 * (time.perf_counter() - th))
     k_end[k].record(main); freed[k].record(main)
 torch.cuda.synchronize()
@@ -52,6 +53,12 @@ for k in range(len(chunks)):
     print(f"{k:3d}   {origin.elapsed_time(c_beg[k]):7.1f} .. {origin.elapsed_time(c_end[k]):7.1f} ({c_beg[k].elapsed_time(c_end[k]):5.1f})   "
           f"{origin.elapsed_time(k_beg[k]):7.1f} .. {origin.elapsed_time(k_end[k]):7.1f} ({k_beg[k].elapsed_time(k_end[k]):5.1f})   {host_t[k]:6.1f}")
 
+if FEAT:
+    for rep in range(3):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        r = batched.run_host_pipelined(pre, host, rec_off, None, chunk_cases=n_cases // 10, to_host=True, pinned_results=True, features=True)
+        torch.cuda.synchronize(); print(f"library call with features: {1e3 * (time.perf_counter() - t0):.1f} ms")
+    sys.exit(0)
 # the library function with different copy piece sizes
 for piece in (1 << 40, 4 * 1024 * 1024, 1024 * 1024):
     batched.COPY_PIECE = piece
