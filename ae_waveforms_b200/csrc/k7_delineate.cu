@@ -757,7 +757,8 @@ extern "C" int aew_delineate_f64(const double* d_sig, const long long* d_sig_off
   if (!d_sig || !d_sig_off || !d_peaks || !d_n_peaks || !d_fid || !d_flags || !d_ws) return AEW_ERR_ARG;
   if (ws_bytes < aew_delineate_workspace_bytes(n_win, L, fs)) return AEW_ERR_WORKSPACE;
   const long long n2k = k7_n2k(L, fs);
-  if (n2k < 4 || n2k > (1LL << 30)) return AEW_ERR_UNSUPPORTED;
+  // the analysis rate must be at least twice the input rate (a tile stages K7_TILE * L / n2k + 6 coefficients)
+  if (n2k < 2LL * L || n2k > (1LL << 30)) return AEW_ERR_UNSUPPORTED;
   double* ws = (double*)(((uintptr_t)d_ws + 127) & ~(uintptr_t)127);
   const size_t smem = 2 * K7_TILE * sizeof(double);
   if (AEW_SET_MAX_SMEM(k7_delineate, smem) != 0) return AEW_ERR_UNSUPPORTED;

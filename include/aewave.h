@@ -168,6 +168,7 @@ int aew_widen_f64(const void* d_src, int src_type, long long n, double gain, dou
  *   d_select          optional [n_win]: only windows with a non-zero entry are processed
  *   d_fid             [n_win][10][max_peaks] int32 out, order P_Peaks, P_Onsets, P_Offsets, Q_Peaks,
  *                     R_Onsets, R_Offsets, S_Peaks, T_Peaks, T_Onsets, T_Offsets; AEW_FID_NAN = np.nan
+ *   limits            64 <= L <= 10,240 samples, fs <= 1,000 Hz (the analysis runs at 2,000 Hz), max_peaks <= 72
  *   d_flags           [n_win] out: 0 ok; 1 the library would raise (NaN features, window kept);
  *                     2 a list would lose an entry (lengths differ -> the caller drops the window) */
 int aew_delineate_blocks(long long n_win);
