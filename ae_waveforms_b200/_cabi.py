@@ -69,6 +69,7 @@ SIGNATURES = {
     "aew_delineate_workspace_bytes": (c_size_t, [c_longlong, c_int, c_double]),
     "aew_delineate_f64": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_double, c_void_p, c_void_p, c_int,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "aew_delineate_timing_dump": (c_int, [c_void_p]),
     "aew_fiducial_features_f64": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_int, c_void_p,
                                           c_void_p, c_double, c_void_p, c_void_p, c_void_p]),
     "aew_recon_workspace_bytes": (c_size_t, [c_longlong, c_longlong]),

@@ -27,6 +27,7 @@
 #include "aew_rt.h"
 #include "aew_pairwise.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 #ifndef K7_THREADS
 #define K7_THREADS 512
@@ -39,6 +40,22 @@
 #define K7_RATE 2000.0
 
 namespace {
+
+// debugging aid (AEW_K7_TIMING=1): thread 0 of every block adds the cycles since the previous mark to counter `slot`
+#ifdef AEW_EMUL
+#define K7_TICK(slot)
+#define K7_CLOCK() 0
+#else
+#define K7_CLOCK() clock64()
+#define K7_TICK(slot)                                                        \
+  do {                                                                       \
+    if (dbg && threadIdx.x == 0) {                                           \
+      const long long t_now = clock64();                                     \
+      atomicAdd(dbg + (slot), (unsigned long long)(t_now - t_last));         \
+      t_last = t_now;                                                        \
+    }                                                                        \
+  } while (0)
+#endif
 
 struct K7Scratch {
   double *coef, *e2k, *wa, *wb;
@@ -349,7 +366,7 @@ __global__ void __launch_bounds__(K7_THREADS, 2)
 k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ sig_off, long long n_win, int L,
              long long n2k, double fs, const int* __restrict__ peaks, const int* __restrict__ n_peaks, int max_peaks,
              const unsigned char* __restrict__ select, int* __restrict__ fid, unsigned char* __restrict__ flags,
-             double* __restrict__ scratch, long long scratch_stride) {
+             double* __restrict__ scratch, long long scratch_stride, unsigned long long* __restrict__ dbg) {
   __shared__ int s_pk[K7_MAXP];
   __shared__ long long s_r2k[K7_MAXP];
   __shared__ double s_y[K7_MAXP], s_d[K7_MAXP], s_c[4][K7_MAXP];
@@ -374,6 +391,8 @@ k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ s
 
   for (long long w = blockIdx.x; w < n_win; w += gridDim.x) {
     if (select && !select[w]) continue;
+    long long t_last = dbg ? K7_CLOCK() : 0;
+    (void)t_last;
     const double* sig = sig_all + sig_off[w];
     int nb = n_peaks[w];
     if (nb > max_peaks) nb = max_peaks;
@@ -482,6 +501,7 @@ k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ s
       continue;
     }
 
+    K7_TICK(0);
     // ---- B: Q and S peaks (warp per beat) on the signal at fs
     {
       const double start_s = s_par[0], end_s = s_par[1];
@@ -522,6 +542,7 @@ k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ s
       }
     }
 
+    K7_TICK(1);
     // ---- C: cubic B-spline coefficients of the window (scipy.ndimage.zoom, order 3, mirror prefilter), in place
     // in shared memory: every thread owns a chunk; the state entering a chunk comes from a 32-sample run-in
     // over its neighbour's samples (read before anybody writes), then the chunk is overwritten.
@@ -567,6 +588,7 @@ k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ s
       __syncthreads();
     }
 
+    K7_TICK(2);
     // ---- D: 2 kHz samples and the a-trous cascade, tile by tile in shared memory.  A tile holds K7_TILE
     // consecutive positions of every level; level p is valid 2 * 2^p less far to the left and 2^p less far to
     // the right than level p - 1, so the halo is sized for the rows qa = 2 + d and qb = 3 + d that are kept.
@@ -616,6 +638,7 @@ k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ s
           prev[i] = t;
         }
         __syncthreads();
+        K7_TICK(3);
         long long len_prev = n2k;                  // true length of the previous level (it grows by 3 * 2^p)
         for (int p = 0; p <= qa; ++p) {
           const int d = 1 << p;
@@ -664,6 +687,7 @@ k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ s
           S.wb[n] = 2.0 * ahead - 2.0 * prev[n - base];
         }
         __syncthreads();
+        K7_TICK(4);
       }
     }
 
@@ -685,6 +709,7 @@ k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ s
         }
       }
       __syncthreads();
+      K7_TICK(5);
       const long long n_on = (long long)(d_on * K7_RATE), n_on_t = (long long)(d_on_t * K7_RATE);
       for (int task = warp; task < 6 * nb; task += K7_WARPS) {
         const int b = task / 6, kind = task - 6 * b;
@@ -716,6 +741,7 @@ k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ s
       }
     }
     __syncthreads();
+    K7_TICK(6);
 
     // ---- F: wrapper rules of ecg_delineate
     {
@@ -729,10 +755,40 @@ k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ s
       drop = __syncthreads_or(drop);
       if (tid == 0) flags[w] = drop ? 2 : 0;
     }
+    K7_TICK(7);
   }
 }
 
 }  // namespace
+
+static unsigned long long* g_k7_dbg = nullptr;   // device counters, allocated once when AEW_K7_TIMING is set
+static unsigned long long* k7_timing_buffer() {
+#ifndef AEW_EMUL
+  if (!g_k7_dbg && getenv("AEW_K7_TIMING")) {
+    if (cudaMalloc(&g_k7_dbg, 8 * sizeof(unsigned long long)) != cudaSuccess) g_k7_dbg = nullptr;
+    else cudaMemset(g_k7_dbg, 0, 8 * sizeof(unsigned long long));
+  }
+#endif
+  return g_k7_dbg;
+}
+
+// debugging aid (AEW_K7_TIMING=1): cycles thread 0 of every block spent per phase of k7_delineate, summed over
+// blocks and windows: A heart rate, B Q/S peaks, C prefilter, D coefficient staging + resampling, D cascade + rows,
+// E T/P peaks, E bounds, F wrapper rules.  Copies and clears the 8 counters (synchronises the device).
+extern "C" int aew_delineate_timing_dump(unsigned long long* h_out8) {
+#ifdef AEW_EMUL
+  for (int i = 0; i < 8; ++i) h_out8[i] = 0;
+  return AEW_OK;
+#else
+  if (!g_k7_dbg) {
+    for (int i = 0; i < 8; ++i) h_out8[i] = 0;
+    return AEW_OK;
+  }
+  cudaError_t e = cudaMemcpy(h_out8, g_k7_dbg, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemset(g_k7_dbg, 0, 8 * sizeof(unsigned long long));
+  return (int)e;
+#endif
+}
 
 extern "C" int aew_delineate_blocks(long long n_win) {
   const long long cap = 148LL * 2;
@@ -763,6 +819,7 @@ extern "C" int aew_delineate_f64(const double* d_sig, const long long* d_sig_off
   const size_t smem = 2 * K7_TILE * sizeof(double);
   if (AEW_SET_MAX_SMEM(k7_delineate, smem) != 0) return AEW_ERR_UNSUPPORTED;
   AEW_LAUNCH(k7_delineate, (unsigned)aew_delineate_blocks(n_win), K7_THREADS, smem, stream, d_sig, d_sig_off, n_win, L,
-             n2k, fs, d_peaks, d_n_peaks, max_peaks, d_select, d_fid, d_flags, ws, k7_stride(L, n2k));
+             n2k, fs, d_peaks, d_n_peaks, max_peaks, d_select, d_fid, d_flags, ws, k7_stride(L, n2k),
+             k7_timing_buffer());
   return (int)cudaGetLastError();
 }

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AEW_VERSION 105
+#define AEW_VERSION 106
 
 /* return codes */
 #define AEW_OK 0
@@ -176,6 +176,10 @@ size_t aew_delineate_workspace_bytes(long long n_win, int L, double fs);
 int aew_delineate_f64(const double* d_sig, const long long* d_sig_off, long long n_win, int L, double fs,
                       const int* d_peaks, const int* d_n_peaks, int max_peaks, const unsigned char* d_select,
                       int* d_fid, unsigned char* d_flags, void* d_ws, size_t ws_bytes, void* stream);
+
+/* debugging aid: with AEW_K7_TIMING=1 in the environment k7_delineate accumulates the cycles thread 0 of every block
+ * spends per phase; this copies and clears the 8 counters (synchronises the device) */
+int aew_delineate_timing_dump(unsigned long long* h_out8);
 
 /* ---- K6: the 35 np_features of a window from per-beat fiducial indices ----------------
  * replaces ecg_features_relative_r + compute_ecg_morphology_features
