@@ -141,9 +141,40 @@ class Preprocessor:
             raise _cabi.AewError(f"window of {self.L} samples exceeds the kernel limit")
 
     # ------------------------------------------------------------------ stages
+    UPLOAD_RING_BYTES = 32 << 20
+
+    def _upload(self, arr: np.ndarray):
+        """Host table -> device tensor WITHOUT the copy engine: the bytes go into a page-locked ring and a small
+        kernel (``aew_fetch_host``) reads them over PCIe.  A ``.to(device)`` here would queue behind whatever bulk
+        host->device transfer is in flight (``run_host_pipelined`` keeps one in flight all the time) and stall
+        the kernels waiting for the table until that transfer has finished."""
+        torch = self.torch
+        arr = np.ascontiguousarray(arr)
+        out = torch.empty(arr.shape, dtype=torch.from_numpy(arr[:0].reshape(-1)).dtype, device=self.device)
+        nb = arr.nbytes
+        if nb == 0:
+            return out
+        if nb > self.UPLOAD_RING_BYTES // 2 or out.data_ptr() % 16:
+            out.copy_(torch.from_numpy(arr))
+            return out
+        ring = getattr(self, "_up_ring", None)
+        if ring is None:
+            ring = self._up_ring = torch.empty(self.UPLOAD_RING_BYTES, dtype=torch.uint8, pin_memory=True)
+            self._up_ring_np = ring.numpy()
+            self._up_pos = 0
+        if self._up_pos + nb > self.UPLOAD_RING_BYTES:        # wrap: everything issued so far must have been read
+            torch.cuda.synchronize(self.device)
+            self._up_pos = 0
+        pos = self._up_pos
+        self._up_ring_np[pos:pos + nb] = arr.reshape(-1).view(np.uint8)
+        _cabi.check(self.lib.aew_fetch_host(ring.data_ptr() + pos, nb, out.data_ptr(), _cabi.stream_ptr(torch)),
+                    "fetch_host")
+        self._up_pos = (pos + nb + 15) & ~15
+        return out
+
     def _ranges(self, batch: RecordBatch, trim: bool):
         torch, lib = self.torch, self.lib
-        off = torch.from_numpy(batch.rec_off).to(self.device)
+        off = self._upload(batch.rec_off)
         beg_h, end_h = batch.rec_off[:-1].copy(), batch.rec_off[1:].copy()
         if trim and batch.n_rec:
             trimmed = torch.empty(2 * batch.n_rec, dtype=torch.int64, device=self.device)
@@ -152,8 +183,9 @@ class Preprocessor:
             self.launches += 1
             t = trimmed.cpu().numpy().reshape(-1, 2)           # the one small D2H sync of the pipeline
             beg_h, end_h = np.ascontiguousarray(t[:, 0]), np.ascontiguousarray(t[:, 1])
-        rng = torch.from_numpy(np.stack([beg_h, end_h])).to(self.device)
-        return beg_h, end_h, rng[0].contiguous(), rng[1].contiguous()
+            tr = trimmed.view(-1, 2)                           # already on the device: no upload of the bounds
+            return beg_h, end_h, tr[:, 0].contiguous(), tr[:, 1].contiguous()
+        return beg_h, end_h, off[:-1].contiguous(), off[1:].contiguous()
 
     def zscore_stats(self, flat, beg_h, end_h, d_beg, d_end):
         """K1: per-record mean, sd (NumPy bits) and non-NaN count."""
@@ -161,7 +193,7 @@ class Preprocessor:
         n_rec = len(beg_h)
         blk = np.zeros(n_rec + 1, dtype=np.int64)
         n_blocks = int(lib.aew_zscore_plan(_np_ptr(beg_h), _np_ptr(end_h), n_rec, _np_ptr(blk)))
-        d_blk = torch.from_numpy(blk).to(self.device)
+        d_blk = self._upload(blk)
         mean = torch.empty(n_rec, dtype=torch.float64, device=self.device)
         sd = torch.empty_like(mean)
         cnt = torch.empty(n_rec, dtype=torch.int64, device=self.device)
@@ -247,7 +279,7 @@ class Preprocessor:
             hazards=torch.zeros(1, dtype=torch.int64, device=dev))
         if n_win == 0:
             return out
-        d_start = torch.from_numpy(np.ascontiguousarray(win_start_h, dtype=np.int64)).to(dev)
+        d_start = self._upload(np.ascontiguousarray(win_start_h, dtype=np.int64))
         zwin_ptr = out["zwin"].data_ptr() if want_zwin else None
         if zwin_ptr is None and want_median and zscore_windows and zwin_scratch is not None \
                 and zwin_scratch.dtype == torch.float64 and zwin_scratch.numel() >= n_win * L \
@@ -347,7 +379,7 @@ class Preprocessor:
             win_start, win_case, win_end = self.window_table(beg_h, end_h, batch.case_ids)
         info_h = np.stack([win_case.astype(np.float64), win_end.astype(np.float64)], axis=1) if len(win_start) \
             else np.zeros((0, 2))
-        info = torch.from_numpy(info_h).to(self.device)             # (uploaded while the filter is still running)
+        info = self._upload(info_h)
         tmp = getattr(self, "_filter_tmp", None)
         scr = self.screen_windows(y, win_start, zwin_scratch=tmp)
         keep_mask = scr["keep"]
@@ -378,7 +410,8 @@ class Preprocessor:
         return res
 
 
-COPY_PIECE = 4 * 1024 * 1024        # samples per host->device copy piece (32 MB)
+COPY_PIECE = 1 << 40                # samples per host->device copy piece (whole chunks: the tables the kernels need
+                                    # no longer use the copy engine, see Preprocessor._upload)
 _pinned_pool: dict = {}             # reusable page-locked result buffers (cudaHostAlloc is far too slow per call)
 
 
@@ -449,8 +482,8 @@ def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chu
         with torch.cuda.stream(copy_stream):
             if k >= 2:
                 copy_stream.wait_event(freed[k - 2])          # the buffer's previous chunk has been consumed
-            # in pieces: the small host->device copies the kernels of the previous chunk need (offset tables,
-            # window starts) share the copy engine with this transfer and would otherwise queue behind all of it
+            # the copy engine serves its queue in order whatever the stream (measured: pieces do not let a small copy
+            # of another stream overtake), so nothing the kernels need may go through it: see Preprocessor._upload
             lo, hi = int(rec_off[c0]), int(rec_off[c1])
             for p0 in range(lo, hi, COPY_PIECE):
                 p1 = min(hi, p0 + COPY_PIECE)

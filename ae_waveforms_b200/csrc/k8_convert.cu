@@ -69,7 +69,38 @@ k8_from_i16(const short* __restrict__ src, long long n, double gain, double offs
   }
 }
 
+// Small tables (record bounds, window starts, np_info rows) fetched by the SMs straight from page-locked host
+// memory: a cudaMemcpyAsync of them would queue on the host->device copy engine BEHIND the next chunk's
+// 1.4 GB transfer (the engine serves its queue in order, whatever the stream), stalling the kernels that need them.
+__global__ void __launch_bounds__(256)
+k8_fetch_host(const unsigned char* __restrict__ src, long long n_bytes, unsigned char* __restrict__ dst) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n16 = n_bytes >> 4;
+#ifndef AEW_EMUL
+  const int4* s = reinterpret_cast<const int4*>(src);
+  int4* d = reinterpret_cast<int4*>(dst);
+  for (long long i = t; i < n16; i += stride) d[i] = s[i];
+#else
+  for (long long i = t; i < n16; i += stride)
+    for (int k = 0; k < 16; ++k) dst[16 * i + k] = src[16 * i + k];
+#endif
+  for (long long i = 16 * n16 + t; i < n_bytes; i += stride) dst[i] = src[i];
+}
+
 }  // namespace
+
+extern "C" int aew_fetch_host(const void* h_pinned, long long n_bytes, void* d_out, void* stream) {
+  if (n_bytes < 0) return AEW_ERR_ARG;
+  if (n_bytes == 0) return AEW_OK;
+  if (!h_pinned || !d_out) return AEW_ERR_ARG;
+  if (((uintptr_t)h_pinned & 15) || ((uintptr_t)d_out & 15)) return AEW_ERR_ARG;   // 16-byte accesses
+  long long grid = (n_bytes + 256 * 16 - 1) / (256 * 16);
+  if (grid > 148LL * 4) grid = 148LL * 4;
+  AEW_LAUNCH(k8_fetch_host, (unsigned)grid, 256, 0, stream, (const unsigned char*)h_pinned, n_bytes,
+             (unsigned char*)d_out);
+  return (int)cudaGetLastError();
+}
 
 extern "C" int aew_widen_f64(const void* d_src, int src_type, long long n, double gain, double offset,
                              int use_sentinel, int sentinel, double* d_out, void* stream) {

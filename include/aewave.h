@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AEW_VERSION 106
+#define AEW_VERSION 107
 
 /* return codes */
 #define AEW_OK 0
@@ -157,6 +157,13 @@ int aew_beat_metrics_f32(const double* d_recon, const double* d_median, long lon
 #define AEW_SRC_I16 1
 int aew_widen_f64(const void* d_src, int src_type, long long n, double gain, double offset, int use_sentinel,
                   int sentinel, double* d_out, void* stream);
+
+/* The path's small host tables (record bounds as in data_extract_vitaldb.py:53-57, window starts of
+ * sample_from_record.py:19-30, the np_info rows of data_create_arrays.py:37-38) read by the SMs directly from
+ * PAGE-LOCKED host memory (unified addressing: the host pointer is the device pointer) instead of a copy-engine
+ * transfer, which would wait behind the next chunk's bulk host->device copy.  Both pointers 16-byte aligned;
+ * the host buffer must stay untouched until the stream has passed this call. */
+int aew_fetch_host(const void* h_pinned, long long n_bytes, void* d_out, void* stream);
 
 /* ---- K7: wavelet delineation of the beats of a window --------------------------------
  * replaces nk.ecg_delineate(ecg_sample, r_peaks, sampling_rate=fs)[1] (neurokit2, default method

@@ -234,6 +234,23 @@ def widen(src, gain=1.0, offset=0.0, sentinel=None):
     return out
 
 
+def fetch_host(src):
+    """aew_fetch_host under emulation: a 16-byte aligned copy of ``src``'s bytes."""
+    L = lib()
+    raw = np.ascontiguousarray(src).reshape(-1).view(np.uint8)
+    buf = np.zeros(len(raw) + 32, np.uint8)
+    a = (-buf.ctypes.data) % 16
+    h = buf[a:a + len(raw)]
+    h[:] = raw
+    obuf = np.full(len(raw) + 32, 0xAB, np.uint8)
+    b = (-obuf.ctypes.data) % 16
+    out = obuf[b:b + len(raw)]
+    rc = L.aew_fetch_host(h.ctypes.data if len(raw) else None, len(raw), out.ctypes.data if len(raw) else None, None)
+    assert rc == 0, rc
+    assert np.all(obuf[b + len(raw):] == 0xAB)
+    return out.copy()
+
+
 def beat_metrics(recon, median, cr=16.0):
     L = lib()
     recon = np.ascontiguousarray(recon, dtype=np.float64)

@@ -246,6 +246,15 @@ def test_k7_delineation_matches_restatement():
     assert fl.tolist() == [3, 0]                           # unselected windows are left alone
 
 
+def test_k8_fetch_host_copies_bytes():
+    rng = np.random.default_rng(81)
+    for n in (0, 1, 15, 16, 17, 808, 4099, 300000):
+        raw = rng.integers(0, 256, n).astype(np.uint8)
+        assert np.array_equal(eh.fetch_host(raw), raw)
+    t = rng.standard_normal((1790, 2))
+    assert np.array_equal(eh.fetch_host(t).view(np.float64).reshape(t.shape), t)
+
+
 def test_k8_widen_matches_numpy():
     rng = np.random.default_rng(8)
     for n in (0, 1, 7, 8, 1000, 4099):

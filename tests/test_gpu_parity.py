@@ -629,6 +629,30 @@ def test_widen_and_narrow_source_feeder(gpu):
     assert same(got["np_waves"].numpy(), ref["np_waves"].cpu().numpy()) and len(got["np_waves"]) > 10
 
 
+def test_host_tables_reach_the_device_without_the_copy_engine(gpu):
+    """Preprocessor._upload: bytes identical for every dtype / size, across ring wrap-arounds, and with a bulk
+    host->device transfer in flight (the situation it exists for)."""
+    torch, B = gpu
+    pre = B.Preprocessor()
+    pre.UPLOAD_RING_BYTES = 1 << 20                                  # small ring: many wraps
+    rng = np.random.default_rng(12)
+    big_h = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
+    big_d = torch.empty_like(big_h, device="cuda")
+    side = torch.cuda.Stream()
+    for i in range(60):
+        if i % 10 == 0:
+            with torch.cuda.stream(side):
+                big_d.copy_(big_h, non_blocking=True)
+        n = int(rng.integers(0, 40000))
+        for a in (rng.integers(-2 ** 62, 2 ** 62, n), rng.standard_normal((n // 2, 2)), rng.integers(0, 255, n).astype(np.uint8),
+                  rng.integers(-9, 9, n).astype(np.int32)):
+            d = pre._upload(a)
+            assert d.shape == a.shape and same(d.cpu().numpy(), a)
+    large = rng.standard_normal(200000)                               # > half the ring: the ordinary copy
+    assert same(pre._upload(large).cpu().numpy(), large)
+    torch.cuda.synchronize()
+
+
 # ------------------------------------------------------------------------- K9: post-search metrics
 def test_beat_metrics_match_reference_torch(gpu):
     from ae_waveforms_b200.sigma_search import SigmaSearch
