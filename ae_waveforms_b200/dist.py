@@ -62,6 +62,27 @@ def gather_beat_arrays(np_waves, np_info, group=None, np_features=None):
     return (waves, info) if np_features is None else (waves, info, feats)
 
 
+def rows_to_host(*arrays, dst_rank: int = 0, group=None):
+    """The final arrays of data_create_arrays.py:56-58 live on ONE host: after the all-gather only ``dst_rank``
+    moves them off its device, into reusable page-locked buffers (a pageable ``.cpu()`` of N x 190 MB on every rank
+    was the slowest part of the multi-GPU end-to-end step).  Returns host tensors on ``dst_rank`` (views of the
+    pool, valid until the next call), None elsewhere."""
+    import torch
+    import torch.distributed as dist
+    from . import batched
+    rank = dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
+    if rank != dst_rank:
+        return tuple(None for _ in arrays)
+    out = []
+    for k, a in enumerate(arrays):
+        shape = tuple(a.shape) if a.dim() > 1 else (a.shape[0], 1)
+        h = batched._pinned(f"gathered{k}", (max(shape[0], 1),) + shape[1:], a.dtype, torch)[:shape[0]]
+        h.copy_(a.reshape(shape), non_blocking=True)
+        out.append(h if a.dim() > 1 else h[:, 0])
+    torch.cuda.current_stream(arrays[0].device).synchronize() if arrays else None
+    return tuple(out)
+
+
 def allreduce_sse(sse, group=None):
     """Sum the per-candidate error sums of all ranks (beats sharded by rank)."""
     import torch.distributed as dist
