@@ -169,6 +169,7 @@ class Preprocessor:
         self._up_ring_np[pos:pos + nb] = arr.reshape(-1).view(np.uint8)
         _cabi.check(self.lib.aew_fetch_host(ring.data_ptr() + pos, nb, out.data_ptr(), _cabi.stream_ptr(torch)),
                     "fetch_host")
+        self.launches += 1
         self._up_pos = (pos + nb + 15) & ~15
         return out
 
@@ -391,20 +392,27 @@ class Preprocessor:
             feats, fl, fid, fstat = self.window_features(tmp, len(win_start), scr)
             keep_mask = scr["keep"] & (fl != 2).to(torch.uint8)      # list-length rule, data_extract_vitaldb.py:140-144
         keep_idx = torch.nonzero(keep_mask).squeeze(1)              # sync: number of kept windows
-        hdr = header.cpu().numpy()
-        _cabi.check_device_status(int(hdr[4]), "filter")
-        _cabi.check_device_status(int(scr["status"].item()), "window screen")
+        # every counter and status word of the batch in ONE device->host read (each .item() is a round trip with
+        # the device idle, which the end-to-end feeder pays once per chunk)
+        i64 = torch.int64
+        words = [header[0:1], header[1:2], header[4:5], scr["status"].to(i64), scr["hazards"].to(i64),
+                 scr["n_peaks"].index_select(0, keep_idx).sum(dtype=i64).reshape(1)]
+        if feats is not None:
+            words.append(fstat.to(i64))
         res = dict(np_waves=scr["waves"].index_select(0, keep_idx), medians=scr["median"].index_select(0, keep_idx),
                    np_info=info.index_select(0, keep_idx), keep=scr["keep"], has_nan=scr["has_nan"],
                    n_peaks=scr["n_peaks"], peaks=scr["peaks"], stats=scr["stats"], keep_idx=keep_idx,
-                   n_windows=len(win_start), n_segments=int(hdr[0]), n_tiles=int(hdr[1]),
-                   hazard_windows=int(scr["hazards"].item()), mean=mean, sd=sd,
-                   n_beats=int(scr["n_peaks"].index_select(0, keep_idx).sum().item()) if len(win_start) else 0)
+                   n_windows=len(win_start), mean=mean, sd=sd)
         if feats is not None:
-            _cabi.check_device_status(int(fstat.item()), "fiducial features")
             res.update(np_features=feats.index_select(0, keep_idx), delineation_flags=fl, fiducials=fid)
         elif features:
             res.update(np_features=torch.zeros((0, 35), dtype=torch.float64, device=self.device))
+        w = torch.cat(words).cpu().numpy()
+        _cabi.check_device_status(int(w[2]), "filter")
+        _cabi.check_device_status(int(w[3]), "window screen")
+        if feats is not None:
+            _cabi.check_device_status(int(w[6]), "fiducial features")
+        res.update(n_segments=int(w[0]), n_tiles=int(w[1]), hazard_windows=int(w[4]), n_beats=int(w[5]))
         if keep_intermediates:
             res.update(filtered=y, rec_beg=beg_h, rec_end=end_h, win_start=win_start)
         return res
@@ -439,9 +447,28 @@ def widen_to_f64(src, out=None, gain: float = 1.0, offset: float = 0.0, sentinel
     return out
 
 
+def chunk_schedule(n_rec: int, chunk_cases: int, taper: bool = True):
+    """[(first, last+1)] case ranges of the end-to-end feeder.  The call takes (copy of the first chunk) +
+    max(all copies, all kernels) + (kernels of the last chunk): with ``taper`` the chunks grow from an eighth of
+    ``chunk_cases`` at the start and shrink back to it at the end, so that both unoverlapped pieces are small while
+    the bulk of the cases still moves in full-size chunks.  The result does not depend on the schedule."""
+    chunk_cases = max(1, int(chunk_cases))
+    ramp = [c for c in (chunk_cases // 8, chunk_cases // 4, chunk_cases // 2) if c >= 1]
+    if not taper or not ramp or n_rec < 2 * sum(ramp) + 2 * chunk_cases:
+        return [(c0, min(n_rec, c0 + chunk_cases)) for c0 in range(0, n_rec, chunk_cases)]
+    rest = n_rec - 2 * sum(ramp)
+    n_mid = -(-rest // chunk_cases)
+    mid = [rest // n_mid + (1 if i < rest % n_mid else 0) for i in range(n_mid)]
+    out, c0 = [], 0
+    for c in ramp + mid + ramp[::-1]:
+        out.append((c0, c0 + c))
+        c0 += c
+    return out
+
+
 def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chunk_cases: int = 100,
                        to_host: bool = True, pinned_results: bool = False, gain: float = 1.0, offset: float = 0.0,
-                       sentinel: int | None = None, features: bool = False) -> dict:
+                       sentinel: int | None = None, features: bool = False, taper: bool = True) -> dict:
     """End-to-end path for HOST data: ``host_flat`` is a (preferably pinned) CPU tensor holding all records back
     to back -- float64, or the narrower source type (float32; int16 with ``gain`` / ``offset`` and an optional
     ``sentinel`` for missing samples), which then crosses PCIe as it is and is widened on the device (K8).  Cases are fed in chunks through two device
@@ -456,7 +483,7 @@ def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chu
     rec_off = np.ascontiguousarray(rec_off, dtype=np.int64)
     n_rec = len(rec_off) - 1
     case_ids = np.arange(n_rec, dtype=np.int64) if case_ids is None else np.asarray(case_ids, dtype=np.int64)
-    chunks = [(c0, min(n_rec, c0 + chunk_cases)) for c0 in range(0, n_rec, chunk_cases)]
+    chunks = chunk_schedule(n_rec, chunk_cases, taper)
     sizes = [int(rec_off[c1] - rec_off[c0]) for c0, c1 in chunks]
     cap = max(sizes) if sizes else 0
     narrow = host_flat.dtype != torch.float64

@@ -379,7 +379,7 @@ k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ s
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   K7Scratch S;
   {
-    double* base = scratch + (long long)blockIdx.x * scratch_stride;
+    double* base = scratch + 16 + (long long)blockIdx.x * scratch_stride;   // 128 bytes: the window counter
     S.coef = base;
     S.e2k = S.coef + ((L + 7) & ~7);
     S.wa = S.e2k + ((n2k + 7) & ~7LL);
@@ -389,7 +389,16 @@ k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ s
   AEW_DYN_SMEM(dyn);
   double* const sm = reinterpret_cast<double*>(dyn);   // 2 * K7_TILE doubles: the window, then the cascade tiles
 
-  for (long long w = blockIdx.x; w < n_win; w += gridDim.x) {
+  // Windows are CLAIMED, not strided over: the screen drops ~16 % of them and the cost of a kept one grows with its
+  // beat count, so a fixed share per block leaves the slowest block ~17 % behind the mean at 60 windows per block.
+  unsigned long long* const next_window = reinterpret_cast<unsigned long long*>(scratch);
+  __shared__ long long s_w;
+  for (;;) {
+    __syncthreads();                              // previous window's shared state (and s_w) is no longer read
+    if (tid == 0) s_w = (long long)atomicAdd(next_window, 1ull);
+    __syncthreads();
+    const long long w = s_w;
+    if (w >= n_win) break;
     if (select && !select[w]) continue;
     long long t_last = dbg ? K7_CLOCK() : 0;
     (void)t_last;
@@ -801,7 +810,7 @@ static long long k7_stride(int L, long long n2k) { return ((L + 7) & ~7) + 3 * (
 
 extern "C" size_t aew_delineate_workspace_bytes(long long n_win, int L, double fs) {
   if (L <= 0 || !(fs > 0)) return 0;
-  return (size_t)aew_delineate_blocks(n_win) * (size_t)k7_stride(L, k7_n2k(L, fs)) * sizeof(double) + 256;
+  return (size_t)aew_delineate_blocks(n_win) * (size_t)k7_stride(L, k7_n2k(L, fs)) * sizeof(double) + 512;
 }
 
 extern "C" int aew_delineate_f64(const double* d_sig, const long long* d_sig_off, long long n_win, int L, double fs,
@@ -818,6 +827,7 @@ extern "C" int aew_delineate_f64(const double* d_sig, const long long* d_sig_off
   double* ws = (double*)(((uintptr_t)d_ws + 127) & ~(uintptr_t)127);
   const size_t smem = 2 * K7_TILE * sizeof(double);
   if (AEW_SET_MAX_SMEM(k7_delineate, smem) != 0) return AEW_ERR_UNSUPPORTED;
+  cudaMemsetAsync(ws, 0, 128, (cudaStream_t)stream);                  // the kernel's window counter
   AEW_LAUNCH(k7_delineate, (unsigned)aew_delineate_blocks(n_win), K7_THREADS, smem, stream, d_sig, d_sig_off, n_win, L,
              n2k, fs, d_peaks, d_n_peaks, max_peaks, d_select, d_fid, d_flags, ws, k7_stride(L, n2k),
              k7_timing_buffer());

@@ -35,6 +35,23 @@ def test_time_axis_and_sigma_inputs_match_oracle(golden):
         assert np.array_equal(a, b, equal_nan=True)
 
 
+def test_chunk_schedule_partitions_the_cases():
+    """The feeder's tapered chunks: contiguous, complete, never larger than asked, small at both ends."""
+    from ae_waveforms_b200.batched import chunk_schedule
+    for n, c in ((1000, 100), (400, 40), (5, 2), (0, 10), (37, 5), (1000, 1), (64, 8), (17, 100), (250, 100), (1000, 7)):
+        for taper in (True, False):
+            ch = chunk_schedule(n, c, taper)
+            if n == 0:
+                assert ch == []
+                continue
+            assert ch[0][0] == 0 and ch[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(ch, ch[1:]))
+            assert all(0 < b - a <= c for a, b in ch)
+    sizes = [b - a for a, b in chunk_schedule(1000, 100)]
+    assert sizes[:3] == [12, 25, 50] and sizes[-3:] == [50, 25, 12] and max(sizes) <= 100
+    assert [b - a for a, b in chunk_schedule(1000, 100, taper=False)] == [100] * 10
+
+
 def test_shard_cases_balances_and_partitions():
     lens = [7200000, 100, 1800000, 1800000, 5, 3600000, 900000, 900000]
     shards = awd.shard_cases(lens, 4)
