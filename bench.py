@@ -345,7 +345,7 @@ def run_gpu(args):
     def step_resident():
         res = pre.run(batch, scratch=scratch)
         if world > 1:
-            awd.gather_beat_arrays(res["np_waves"], res["np_info"])
+            awd.gather_beat_arrays(res["np_waves"], res["np_info"], dst=0)   # the final arrays live on one rank
         return res
 
     # ---- stage timing (CUDA events on the launching stream) wraps the stage methods
@@ -449,9 +449,10 @@ def run_gpu(args):
                 return r["np_waves"], r["np_info"]
             r = batched.run_host_pipelined(pre, host, rec_off, case_ids, chunk_cases=max(1, n_cases // 10),
                                            to_host=False)
-            w, i = awd.gather_beat_arrays(r["np_waves"], r["np_info"])
-            hw, hi = awd.rows_to_host(w, i)            # rank 0 only, page-locked (the arrays end up on one host)
-            return (hw, hi) if hw is not None else (w, i)
+            w, i = awd.gather_beat_arrays(r["np_waves"], r["np_info"], dst=0)
+            if w is None:                              # not rank 0: its rows have been sent
+                return r["np_waves"], r["np_info"]
+            return awd.rows_to_host(w, i)              # rank 0: page-locked (the arrays end up on one host)
 
         for _ in range(min(2, args.warmup)):
             w_h, i_h = step_host()

@@ -125,6 +125,14 @@ def _gloo_worker(rank, world, port, q):
         assert torch.equal(gw2, gw) and torch.equal(gi2, gi) and gf.shape == (gi.shape[0], 35)
         src_rank = world - (gi[:, 0] / 10).to(torch.int64)                                 # case id encodes the rank
         assert torch.equal(gf[:, 0], gi[:, 1] + src_rank.to(torch.float64))                # features follow their rows
+        dw, di, df = awd.gather_beat_arrays(waves, info, np_features=feats, dst=1)         # to one rank only
+        if rank == 1:
+            assert torch.equal(dw, gw) and torch.equal(di, gi) and torch.equal(df, gf)
+        else:
+            assert dw is None and di is None and df is None
+        ew, ei = awd.gather_beat_arrays(waves[:0] if rank == 0 else waves, info[:0] if rank == 0 else info, dst=0)
+        if rank == 0:                                                                       # a rank without rows
+            assert ew.shape[0] == ei.shape[0] == 3 + 2 * (world - 1)
         sse = torch.tensor([1.0 + rank, 2.0, float("nan") if rank == 1 else 0.5], dtype=torch.float64)
         awd.allreduce_sse(sse)
         q.put((rank, [p.shape[0] for p in parts], gw.numpy(), gi.numpy(), sse.numpy(), waves.numpy(), info.numpy()))
