@@ -468,12 +468,12 @@ def run_gpu(args):
         if world == 1:                                 # the same call with delineation + features switched on
             try:
                 rf = batched.run_host_pipelined(pre, host, rec_off, case_ids, chunk_cases=max(1, n_cases // 10),
-                                                to_host=True, pinned_results=True, features=True)
+                                                to_host=True, pinned_results=True, features=True, taper=False)
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
                 for _ in range(2):
                     rf = batched.run_host_pipelined(pre, host, rec_off, case_ids, chunk_cases=max(1, n_cases // 10),
-                                                    to_host=True, pinned_results=True, features=True)
+                                                    to_host=True, pinned_results=True, features=True, taper=False)
                 torch.cuda.synchronize()
                 sf = (time.perf_counter() - t0) / 2
                 e2e["with_features"] = {"value": total / sf / 1e6, "unit": UNIT, "h2d_bytes_per_step": total * 8,
