@@ -107,20 +107,6 @@ __device__ __forceinline__ void py_slice(long long a, long long b, long long n, 
 
 __device__ __forceinline__ int sgn(double v) { return (v > 0.0) - (v < 0.0); }
 
-// The rows a search reads were written to the block's slab a whole cascade ago and have left L2 by now (296 slabs of
-// 1 MB against 126 MB): the warp asks for the slice of its NEXT task, one 128-byte line per lane and step, before it
-// works on the current one, so that the dependent loads of a search find their lines in L2 instead of paying the DRAM
-// latency one after the other.
-__device__ __forceinline__ void prefetch_slice(const double* row, long long n2k, long long a, long long b, int lane) {
-#ifndef AEW_EMUL
-  long long a0, len;
-  py_slice(a, b, n2k, a0, len);
-  const char* lo = reinterpret_cast<const char*>(row + a0);
-  const char* hi = reinterpret_cast<const char*>(row + a0 + len);
-  for (const char* q = lo + 128 * lane; q < hi; q += 128 * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
-#endif
-}
-
 // ------------------------------------------------------------------ B: Q / S peaks
 struct Epoch {
   const double* sig;
@@ -718,20 +704,9 @@ k7_delineate(const double* __restrict__ sig_all, const long long* __restrict__ s
     {
       const double p2r = s_par[2], rt = s_par[3], d_on = s_par[4], d_on_t = s_par[5];
       const long long bndry = (long long)(0.5 * 0.13 * K7_RATE);
-      const long long t_hi = 2 * (long long)(rt * K7_RATE), p_lo = 2 * (long long)(p2r * K7_RATE);
-      if (warp < 2 * nb) {
-        const long long r0 = s_r2k[warp >> 1];
-        if ((warp & 1) == 0) prefetch_slice(S.wb, n2k, r0 + bndry, r0 + t_hi, lane);
-        else prefetch_slice(S.wa, n2k, r0 - p_lo, r0 - bndry, lane);
-      }
       for (int task = warp; task < 2 * nb; task += K7_WARPS) {
         const int b = task >> 1;
         const long long r = s_r2k[b];
-        if (task + K7_WARPS < 2 * nb) {              // K7_WARPS is even: the next task is of the same kind
-          const long long rn = s_r2k[(task + K7_WARPS) >> 1];
-          if ((task & 1) == 0) prefetch_slice(S.wb, n2k, rn + bndry, rn + t_hi, lane);
-          else prefetch_slice(S.wa, n2k, rn - p_lo, rn - bndry, lane);
-        }
         long long v;
         if ((task & 1) == 0)
           v = tp_peak(S.wb, S.e2k, n2k, r + bndry, r + 2 * (long long)(rt * K7_RATE), 0.25, 0, rt - 0.5 * 0.13, lane);
