@@ -49,7 +49,7 @@ def gather_rows_to(arrays, dst: int = 0, group=None):
     """Variable-length gather of several row arrays to ONE rank: the row counts are all-gathered once, then every
     other rank sends its rows as they are (no padding) and ``dst`` receives them into exact-size buffers -- a
     quarter of the all-gather's bytes per link at eight ranks, and nothing lands where it is not needed.
-    Returns, on ``dst``, one list of per-rank tensors per array; None elsewhere."""
+    Returns, on ``dst``, one tensor per array with the ranks' rows in rank order; None elsewhere."""
     import torch
     import torch.distributed as dist
     ws, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -60,10 +60,15 @@ def gather_rows_to(arrays, dst: int = 0, group=None):
     counts = [int(c) for c in torch.cat(counts).cpu()]
     ops, parts = [], None
     if rank == dst:
-        parts = [[a if r == rank else torch.empty((counts[r],) + tuple(a.shape[1:]), dtype=a.dtype, device=a.device)
-                  for r in range(ws)] for a in arrays]
-        for per_rank in parts:
-            ops += [dist.P2POp(dist.irecv, per_rank[r], glob(r), group) for r in range(ws) if r != rank and counts[r]]
+        # every array is received straight into its slice of ONE buffer (no concatenation pass afterwards)
+        first = [sum(counts[:r]) for r in range(ws)]
+        parts = []
+        for a in arrays:
+            full = torch.empty((sum(counts),) + tuple(a.shape[1:]), dtype=a.dtype, device=a.device)
+            full[first[rank]:first[rank] + counts[rank]].copy_(a)
+            ops += [dist.P2POp(dist.irecv, full[first[r]:first[r] + counts[r]], glob(r), group)
+                    for r in range(ws) if r != rank and counts[r]]
+            parts.append(full)
     elif counts[rank]:
         ops = [dist.P2POp(dist.isend, a.contiguous(), glob(dst), group) for a in arrays]
     if ops:
@@ -83,8 +88,8 @@ def gather_beat_arrays(np_waves, np_info, group=None, np_features=None, dst: int
         parts = gather_rows_to(arrays, dst, group)
         if parts is None:
             return (None, None) if np_features is None else (None, None, None)
-        waves, info = torch.cat(parts[0], dim=0), torch.cat(parts[1], dim=0)
-        feats = None if np_features is None else torch.cat(parts[2], dim=0)
+        waves, info = parts[0], parts[1]
+        feats = None if np_features is None else parts[2]
     else:
         waves = torch.cat(allgather_rows(np_waves, group), dim=0)
         info = torch.cat(allgather_rows(np_info, group), dim=0)
