@@ -567,6 +567,19 @@ def run_gpu(args):
                          "algorithmic_bytes_per_launch": 16.0 * total, "launch_ms": k2_launch_ms},
             "clocks": clocks.summary(),
         }
+        # the other two stages against the same HBM peak (algorithmic bytes of DESIGN.md section 3): K3 is the largest
+        # stage of the step and is NOT near this roofline -- it is bound by issue latency at 16 warps per SM
+        try:
+            out["roofline_other_stages"] = {
+                "k1_zscore_stats": {"bound": "hbm", "bytes_per_sample": 16.0, "ms": stages["k1_zscore_stats"],
+                                    "achieved": 16.0 * total / (stages["k1_zscore_stats"] / 1e3) / 1e9, "unit": "GB/s",
+                                    "frac": 16.0 * total / (stages["k1_zscore_stats"] / 1e3) / 1e9 / hbm},
+                "k3_windows_beats": {"bound": "issue latency (hbm shown for scale)", "bytes_per_sample": 8.0,
+                                     "ms": stages["k3_windows_beats"],
+                                     "achieved": 8.0 * total / (stages["k3_windows_beats"] / 1e3) / 1e9, "unit": "GB/s",
+                                     "frac": 8.0 * total / (stages["k3_windows_beats"] / 1e3) / 1e9 / hbm}}
+        except Exception:
+            pass
         if "seconds" in e2e:
             out["e2e"] = {"value": tot_samples * args.steps / (e2e_ms_all / 1e3) / 1e6, "unit": UNIT,
                           "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"]}
