@@ -73,6 +73,12 @@ SIGNATURES = {
     "aew_delineate_timing_dump": (c_int, [c_void_p]),
     "aew_fiducial_features_f64": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_int, c_void_p,
                                           c_void_p, c_double, c_void_p, c_void_p, c_void_p]),
+    "aew_fiducial_relative_f64": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_double, c_void_p,
+                                          c_void_p, c_void_p]),
+    "aew_morphology_f64": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "aew_nanmedian_rows_f64": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "aew_peak_stats_f64": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_double, c_double, c_void_p, c_void_p,
+                                   c_void_p]),
     "aew_recon_workspace_bytes": (c_size_t, [c_longlong, c_longlong]),
     "aew_recon_sse_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_int, c_void_p,
                                   c_longlong, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -132,4 +138,22 @@ def require_cuda():
 
 
 def stream_ptr(torch) -> int:
+    """The current stream of the CURRENT device: the C ABI launches on the current device, so every caller runs
+    inside ``on_device`` (below), which makes the object's device current first."""
     return torch.cuda.current_stream().cuda_stream
+
+
+def on_device(fn):
+    """Method decorator: run with ``self.device`` as the current CUDA device.  The library never calls
+    cudaSetDevice; tensors of ``device='cuda:1'`` with cuda:0 current would otherwise meet kernels launched on
+    cuda:0's stream."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        torch, dev = self.torch, self.device
+        if dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(self, *args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(self, *args, **kwargs)
+    return wrapper

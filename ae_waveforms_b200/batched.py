@@ -26,7 +26,15 @@ import numpy as np
 
 from . import _cabi
 
-BEAT_LEN, BEAT_PRE, BEAT_POST = 320, 106, 214
+BEAT_LEN, BEAT_PRE, BEAT_POST = 320, 106, 214        # at 500 Hz
+
+
+def beat_geometry(fs):
+    """median_sample.py:20-25 -- (section, pre, post) = int(0.8 * (60 / 75) * fs) samples, a third (rounded down)
+    before the R peak: 320 / 106 / 214 at 500 Hz, 160 / 53 / 107 at 250 Hz."""
+    section = int(0.8 * (60 / 75) * fs)
+    pre = int(1 / 3 * section)
+    return section, pre, section - pre
 
 
 def _ptr(t):
@@ -130,7 +138,10 @@ class Preprocessor:
                  screen_mode: str = "auto", max_segments: int | None = None, device=None):
         self.torch, self.lib = _cabi.require_cuda()
         self.device = self.torch.device(device or "cuda")
+        if self.device.index is None:                      # bind to the device that is current NOW
+            self.device = self.torch.device("cuda", self.torch.cuda.current_device())
         self.fs, self.L = int(fs), int(fs * sample_length)
+        self.beat_len, self.beat_pre, self.beat_post = beat_geometry(self.fs)
         self.hp, self.lp, self.order = hp, lp, order
         self.pvc_threshold, self.sd_threshold = float(pvc_threshold), float(sd_threshold)
         self.filter_mode = {"fast": 0, "exact": 1}[filter_mode]
@@ -143,6 +154,7 @@ class Preprocessor:
     # ------------------------------------------------------------------ stages
     UPLOAD_RING_BYTES = 32 << 20
 
+    @_cabi.on_device
     def _upload(self, arr: np.ndarray):
         """Host table -> device tensor WITHOUT the copy engine: the bytes go into a page-locked ring and a small
         kernel (``aew_fetch_host``) reads them over PCIe.  A ``.to(device)`` here would queue behind whatever bulk
@@ -173,6 +185,7 @@ class Preprocessor:
         self._up_pos = (pos + nb + 15) & ~15
         return out
 
+    @_cabi.on_device
     def _ranges(self, batch: RecordBatch, trim: bool):
         torch, lib = self.torch, self.lib
         off = self._upload(batch.rec_off)
@@ -188,6 +201,7 @@ class Preprocessor:
             return beg_h, end_h, tr[:, 0].contiguous(), tr[:, 1].contiguous()
         return beg_h, end_h, off[:-1].contiguous(), off[1:].contiguous()
 
+    @_cabi.on_device
     def zscore_stats(self, flat, beg_h, end_h, d_beg, d_end):
         """K1: per-record mean, sd (NumPy bits) and non-NaN count."""
         torch, lib = self.torch, self.lib
@@ -206,6 +220,7 @@ class Preprocessor:
         self.launches += 4
         return mean, sd, cnt
 
+    @_cabi.on_device
     def filter_records(self, flat, beg_h, end_h, d_beg, d_end, mean=None, sd=None, cnt=None, out=None, tmp=None):
         """K2: z-score (fused) + high-pass + low-pass per NaN-delimited segment.
         Returns (filtered, device header tensor)."""
@@ -256,6 +271,7 @@ class Preprocessor:
         return (np.ascontiguousarray(start, dtype=np.int64), np.asarray(case_ids)[rec_of] if n_win else np.zeros(0, np.int64),
                 ((k + 1) * L).astype(np.int64))
 
+    @_cabi.on_device
     def screen_windows(self, y, win_start_h, want_median=True, want_zwin=False, zscore_windows=True,
                        pvc_threshold=None, sd_threshold=None, L=None, zwin_scratch=None):
         """K3 + K4 on the windows whose flat offsets are given.  ``zwin_scratch``: optional float64 tensor of at
@@ -272,8 +288,8 @@ class Preprocessor:
             n_peaks=torch.zeros(n_win, dtype=torch.int32, device=dev),
             peaks=torch.empty((n_win, maxp), dtype=torch.int32, device=dev),
             stats=torch.empty((n_win, 4), dtype=torch.float64, device=dev),
-            median=torch.empty((n_win, BEAT_LEN), dtype=torch.float64, device=dev) if want_median else None,
-            waves=torch.empty((n_win, BEAT_LEN), dtype=torch.float32, device=dev) if want_median else None,
+            median=torch.empty((n_win, self.beat_len), dtype=torch.float64, device=dev) if want_median else None,
+            waves=torch.empty((n_win, self.beat_len), dtype=torch.float32, device=dev) if want_median else None,
             zwin=torch.empty((n_win, L), dtype=torch.float64, device=dev) if want_zwin else None,
             zparams=torch.empty((n_win, 2), dtype=torch.float64, device=dev) if want_median else None,
             status=torch.zeros(1, dtype=torch.int32, device=dev),
@@ -290,7 +306,7 @@ class Preprocessor:
         p = _cabi.K3Params(
             y=y.data_ptr(), win_start=d_start.data_ptr(), n_win=n_win, L=L,
             smooth_k=int(np.rint(0.1 * fs)), avg_k=int(np.rint(0.75 * fs)), refractory=int(np.rint(0.3 * fs)),
-            pre=BEAT_PRE, post=BEAT_POST, hr_num=float(60 * fs), rr_div=float(fs * 1000), hr_lo=30.0, hr_hi=180.0,
+            pre=self.beat_pre, post=self.beat_post, hr_num=float(60 * fs), rr_div=float(fs * 1000), hr_lo=30.0, hr_hi=180.0,
             pvc_threshold=float(self.pvc_threshold if pvc_threshold is None else pvc_threshold),
             sd_threshold=float(self.sd_threshold if sd_threshold is None else sd_threshold),
             mode=self.screen_mode, zscore_windows=1 if zscore_windows else 0,
@@ -306,6 +322,7 @@ class Preprocessor:
         out["_win_start"] = d_start
         return out
 
+    @_cabi.on_device
     def delineate_windows(self, sig, sig_off, peaks, n_peaks, select=None, L=None):
         """K7: nk.ecg_delineate(window, r_peaks, fs)[1] (data_extract_vitaldb.py:131) for every selected window.
         ``sig`` flat float64 CUDA tensor, ``sig_off`` int64 CUDA tensor of window offsets into it, ``peaks``
@@ -329,6 +346,7 @@ class Preprocessor:
         self.launches += 1
         return fid, flags
 
+    @_cabi.on_device
     def fiducial_features(self, sig, sig_off, peaks, n_peaks, fid, valid=None, L=None):
         """K6: ecg_features_relative_r + compute_ecg_morphology_features + compute_median_features_ecg
         (data_extract_vitaldb.py:146-162) -> (n_win, 35) float64 in np_features column order."""
@@ -344,6 +362,7 @@ class Preprocessor:
             self.launches += 1
         return out, status
 
+    @_cabi.on_device
     def window_features(self, zwin_flat, n_win, scr, L=None):
         """K7 + K6 on the kept windows of a screen result; ``zwin_flat`` holds the z-scored windows back to back.
         Returns (features (n_win, 35), flags (n_win,))."""
@@ -356,6 +375,7 @@ class Preprocessor:
         return feats, flags, fid, status
 
     # ------------------------------------------------------------------ whole path
+    @_cabi.on_device
     def run(self, batch: RecordBatch, trim: bool = True, keep_intermediates: bool = False,
             scratch: dict | None = None, features: bool = False, strips: bool = False) -> dict:
         """Returns a dict of CUDA tensors: ``np_waves`` (n_keep, 320) float32,
@@ -385,12 +405,26 @@ class Preprocessor:
         scr = self.screen_windows(y, win_start, zwin_scratch=tmp)
         keep_mask = scr["keep"]
         feats = None
-        if features and len(win_start):
+        if features and len(win_start) and not (self.hp and self.lp):
+            # data_extract_vitaldb.py:118,166-170: without both filters no delineation, NaN features, every screened
+            # window kept -- and data_create_arrays.py:37-40 then writes zeros for such a case (a NaN cell where a
+            # {'x', 'y'} dict is expected raises its TypeError branch)
+            feats = torch.zeros((len(win_start), 35), dtype=torch.float64, device=self.device)
+            fl = torch.ones(len(win_start), dtype=torch.uint8, device=self.device)
+            fid, fstat = None, torch.zeros(1, dtype=torch.int32, device=self.device)
+        elif features and len(win_start):
             # the screen kernel parked the z-scored windows ('ecg_sample') back to back in the filter scratch
             if tmp is None or tmp.numel() < len(win_start) * self.L or tmp.data_ptr() == y.data_ptr():
                 raise _cabi.AewError("features=True needs the filter scratch buffer for the z-scored windows")
             feats, fl, fid, fstat = self.window_features(tmp, len(win_start), scr)
             keep_mask = scr["keep"] & (fl != 2).to(torch.uint8)      # list-length rule, data_extract_vitaldb.py:140-144
+            # a kept window whose delineation RAISED (flag 1) has np.nan cells where data_create_arrays.py:34-35
+            # expects {'x', 'y'} dicts: its TypeError branch (:37-40) zeroes all 35 features of EVERY row of that case
+            raised = (fl == 1) & scr["keep"].bool()
+            if bool(raised.any()):
+                d_case = info[:, 0]
+                hit = torch.isin(d_case, torch.unique(d_case[raised]))
+                feats = torch.where(hit[:, None], torch.zeros_like(feats), feats)
         keep_idx = torch.nonzero(keep_mask).squeeze(1)              # sync: number of kept windows
         # every counter and status word of the batch in ONE device->host read (each .item() is a round trip with
         # the device idle, which the end-to-end feeder pays once per chunk)
@@ -441,9 +475,10 @@ def widen_to_f64(src, out=None, gain: float = 1.0, offset: float = 0.0, sentinel
     if code is None:
         raise _cabi.AewError(f"cannot widen {src.dtype}")
     out = torch.empty(src.numel(), dtype=torch.float64, device=src.device) if out is None else out
-    _cabi.check(lib.aew_widen_f64(_ptr(src), code, src.numel(), float(gain), float(offset),
-                                  0 if sentinel is None else 1, 0 if sentinel is None else int(sentinel), _ptr(out),
-                                  _cabi.stream_ptr(torch)), "widen")
+    with torch.cuda.device(src.device):
+        _cabi.check(lib.aew_widen_f64(_ptr(src), code, src.numel(), float(gain), float(offset),
+                                      0 if sentinel is None else 1, 0 if sentinel is None else int(sentinel),
+                                      _ptr(out), _cabi.stream_ptr(torch)), "widen")
     return out
 
 
@@ -480,6 +515,10 @@ def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chu
     (``to_host``) or left on the device (e.g. for a following all-gather).  With ``pinned_results`` the host
     tensors are views of a reusable page-locked pool (valid until the next call) instead of fresh copies."""
     torch = pre.torch
+    if pre.device.index is not None and pre.device.index != torch.cuda.current_device():
+        with torch.cuda.device(pre.device):            # streams, events and launches below belong to this device
+            return run_host_pipelined(pre, host_flat, rec_off, case_ids, chunk_cases, to_host, pinned_results, gain,
+                                      offset, sentinel, features, taper)
     rec_off = np.ascontiguousarray(rec_off, dtype=np.int64)
     n_rec = len(rec_off) - 1
     case_ids = np.arange(n_rec, dtype=np.int64) if case_ids is None else np.asarray(case_ids, dtype=np.int64)
@@ -499,7 +538,7 @@ def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chu
     if to_host:
         # every window can be kept at most: an upper bound on the rows, known from the record lengths alone
         max_rows = int(sum(window_count(int(rec_off[r + 1] - rec_off[r]), pre.L) for r in range(n_rec)))
-        h_waves = _pinned("waves", (max(max_rows, 1), BEAT_LEN), torch.float32, torch)
+        h_waves = _pinned("waves", (max(max_rows, 1), pre.beat_len), torch.float32, torch)
         h_info = _pinned("info", (max(max_rows, 1), 2), torch.float64, torch)
         h_feat = _pinned("feat", (max(max_rows, 1), 35), torch.float64, torch) if features else None
         back_stream = torch.cuda.Stream(device=pre.device)
@@ -564,7 +603,8 @@ def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chu
     else:
         np_feat = (torch.cat(feats) if feats else torch.zeros((0, 35), dtype=torch.float64, device=pre.device)) \
             if features else None
-        np_waves = torch.cat(waves) if waves else torch.zeros((0, BEAT_LEN), dtype=torch.float32, device=pre.device)
+        np_waves = torch.cat(waves) if waves else torch.zeros((0, pre.beat_len), dtype=torch.float32,
+                                                              device=pre.device)
         np_info = torch.cat(infos) if infos else torch.zeros((0, 2), dtype=torch.float64, device=pre.device)
     out = dict(np_waves=np_waves, np_info=np_info, hazard_windows=hazards, n_windows=n_windows, n_beats=n_beats)
     if features:

@@ -771,18 +771,14 @@ __global__ void __launch_bounds__(32) k2_exact(PassArgs a) {
 }
 
 unsigned long long* g_dbg = nullptr;   // device counters, allocated once when AEW_K2_TIMING is set
-int g_sm_count = 0;
-inline int sm_count() {
+inline int sm_count() {                 // of the CURRENT device (queried per call: devices may differ)
 #ifdef AEW_EMUL
   return 2;
 #else
-  if (!g_sm_count) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    if (g_sm_count <= 0) g_sm_count = 148;
-  }
-  return g_sm_count;
+  int dev = 0, n = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n > 0 ? n : 148;
 #endif
 }
 
@@ -810,7 +806,7 @@ extern "C" int aew_segments_find_f64(const double* x, const long long* d_rec_beg
   K2Ws w;
   k2_ws_layout((void*)align_up((size_t)ws, 128), max_seg, aew_filt_max_tiles(n_rec, total_samples, max_seg), &w);
   cudaStream_t st = (cudaStream_t)stream;
-  cudaMemsetAsync(w.hdr, 0, H_SLOTS * sizeof(long long), st);
+  if (cudaMemsetAsync(w.hdr, 0, H_SLOTS * sizeof(long long), st) != 0) return (int)cudaGetLastError();
   if (n_rec == 0) return AEW_OK;
   AEW_LAUNCH(k2_seg_find, (unsigned)n_rec, SEG_THREADS, 0, st, x, d_rec_beg, d_rec_end, d_nonnan_count, nan_fill, w);
   return (int)cudaGetLastError();
@@ -850,15 +846,13 @@ extern "C" int aew_filtfilt_f64(const double* src, const double* mean, const dou
   }
   if (mode != 0) return AEW_ERR_ARG;
   const size_t smem = (size_t)(K2_STAGES * K2_T + K2_TAB_LEN + 20 * K2_NW + 8) * sizeof(double);
-  static bool attr_done = false;
-  if (!attr_done) {
-    AEW_SET_MAX_SMEM(k2_pass<false>, smem);
-    AEW_SET_MAX_SMEM(k2_pass<true>, smem);
-    attr_done = true;
-  }
-  cudaMemsetAsync(w.hdr + H_WORK_FWD, 0, 2 * sizeof(long long), st);
-  cudaMemsetAsync(w.tstate_fwd, 0xFF, (size_t)w.max_tiles * 4 * sizeof(double), st);
-  cudaMemsetAsync(w.tstate_bwd, 0xFF, (size_t)w.max_tiles * 4 * sizeof(double), st);
+  // (per call: the attribute is per DEVICE)
+  if (AEW_SET_MAX_SMEM(k2_pass<false>, smem) != 0 || AEW_SET_MAX_SMEM(k2_pass<true>, smem) != 0)
+    return (int)cudaGetLastError();
+  if (cudaMemsetAsync(w.hdr + H_WORK_FWD, 0, 2 * sizeof(long long), st) != 0 ||
+      cudaMemsetAsync(w.tstate_fwd, 0xFF, (size_t)w.max_tiles * 4 * sizeof(double), st) != 0 ||
+      cudaMemsetAsync(w.tstate_bwd, 0xFF, (size_t)w.max_tiles * 4 * sizeof(double), st) != 0)
+    return (int)cudaGetLastError();
   const long long cap = (long long)sm_count() * 2;
   const long long grid = w.max_tiles < cap ? w.max_tiles : cap;
   AEW_LAUNCH(k2_pass<false>, (unsigned)grid, K2_NT, smem, st, a);

@@ -46,7 +46,7 @@
 #define K3_RING 512                       // ring of smoothgrad values in the sequential evaluation (> avg_k + 1)
 #define K3_MAXL 10240                     // samples per window at most (80 KB of shared memory)
 #define K3_MAXP 72                        // peaks are > 150 samples apart -> at most 71 in 10752
-#define K3_BEAT 320
+#define K3_MAXS 512                       // beat section int(0.64 fs) at most (320 at 500 Hz; median_sample.py:20-21)
 #define K3_NONE 0xffffu
 #define K3_PREFETCH_AHEAD 296             // one wave of blocks (two blocks per SM)
 
@@ -1030,10 +1030,11 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, unsigned long
 // Blocks of 160 threads take half of a window's 320 columns each: three of them fit an SM (registers), and their
 // start-up round trips to global memory overlap.
 #define K3B_NT 160
-__global__ void __launch_bounds__(K3B_NT, 3) k3_median(K3Params p) {
+__global__ void __launch_bounds__(K3B_NT, 3) k3_median(K3Params p, int nparts) {
   __shared__ int s_peaks[K3_MAXP];
-  const long long w = blockIdx.x >> 1;
-  const int c_lo = (int)(blockIdx.x & 1) * K3B_NT;
+  const int S = p.pre + p.post;                          // section length int(0.64 fs): nparts = ceil(S / K3B_NT)
+  const long long w = blockIdx.x / nparts;
+  const int c_lo = (int)(blockIdx.x - w * nparts) * K3B_NT;
   // everything the block needs to get going, in one round trip
   const int keep = p.keep[w];
   const int n = p.n_peaks[w];
@@ -1049,10 +1050,11 @@ __global__ void __launch_bounds__(K3B_NT, 3) k3_median(K3Params p) {
   src.zs = p.zscore_windows && !p.zwin;
   src.mean = mean;
   src.dv = make_exact_div(sd0);
-  double* med = p.median ? p.median + w * K3_BEAT : nullptr;
-  float* waves = p.waves ? p.waves + w * K3_BEAT : nullptr;
+  double* med = p.median ? p.median + w * S : nullptr;
+  float* waves = p.waves ? p.waves + w * S : nullptr;
   if (n > 64) {
     const int c = c_lo + threadIdx.x;
+    if (c >= S) return;
     const double m = column_median_count(src, s_peaks, n, c, p.L, p.pre, p.post);
     if (med) med[c] = m;
     if (waves) waves[c] = (float)m;
@@ -1064,8 +1066,10 @@ __global__ void __launch_bounds__(K3B_NT, 3) k3_median(K3Params p) {
   for (int c0 = 0; c0 < K3B_NT; c0 += per_pass) {
     const int c = c_lo + c0 + (paired ? (int)(threadIdx.x >> 1) : (int)threadIdx.x);
     const int half = paired ? (int)(threadIdx.x & 1) : 0;
-    const double m = column_median_64(src, s_peaks, n, c, half, true, paired, p.L, p.pre, p.post);
-    if (half == 0) {
+    const bool active = c < S;                           // (the last part of a section that is no multiple of 160)
+    if (!__any_sync(AEW_FULL, active)) continue;
+    const double m = column_median_64(src, s_peaks, n, active ? c : 0, half, active, paired, p.L, p.pre, p.post);
+    if (active && half == 0) {
       if (med) med[c] = m;
       if (waves) waves[c] = (float)m;
     }
@@ -1129,16 +1133,19 @@ extern "C" int aew_windows_beats_f64(const K3Params* hp, void* stream) {
     if ((long long)seg + p.avg_k + p.smooth_k - 1 > K3_CAP || p.avg_k + 2 > K3_RING || p.L < 2 * K3_SEGS)
       return AEW_ERR_UNSUPPORTED;
   }
-  if (pw_depth(p.L) > 7 || p.pre + p.post != K3_BEAT || p.smooth_k < 1 || p.avg_k < 1 || p.smooth_k > p.L ||
+  if (pw_depth(p.L) > 7 || p.pre < 0 || p.post < 1 || p.pre + p.post > K3_MAXS || p.smooth_k < 1 || p.avg_k < 1 || p.smooth_k > p.L ||
       p.avg_k > p.L || p.refractory < 1 || (p.L / (p.refractory + 1) + 1) > K3_MAXP || p.n_win > 0x3fffffffll)
     return AEW_ERR_UNSUPPORTED;
   const size_t smem = k3_smem_layout(nullptr, p.L, nullptr);
   if (smem > 113 * 1024) return AEW_ERR_UNSUPPORTED;    // two blocks per SM
-  static bool attr_done = false;
-  if (!attr_done) { AEW_SET_MAX_SMEM(k3_windows, 113 * 1024); attr_done = true; }
+  // (per call: the attribute is per DEVICE, and the call costs a fraction of a microsecond)
+  if (AEW_SET_MAX_SMEM(k3_windows, 113 * 1024) != 0) return (int)cudaGetLastError();
   if ((p.median || p.waves) && p.zscore_windows && !p.zparams && !p.zwin) return AEW_ERR_ARG;
   AEW_LAUNCH(k3_windows, (unsigned)p.n_win, K3_NT, smem, (cudaStream_t)stream, p, k3_timing_buffer());
-  if (p.median || p.waves) AEW_LAUNCH(k3_median, (unsigned)(2 * p.n_win), K3B_NT, 0, (cudaStream_t)stream, p);
+  if (p.median || p.waves) {
+    const int nparts = (p.pre + p.post + K3B_NT - 1) / K3B_NT;
+    AEW_LAUNCH(k3_median, (unsigned)(nparts * p.n_win), K3B_NT, 0, (cudaStream_t)stream, p, nparts);
+  }
   return (int)cudaGetLastError();
 }
 
@@ -1162,7 +1169,8 @@ extern "C" int aew_median_beats_f64(const double* windows, long long n_win, int 
                                     const long long* d_peak_off, int max_peaks_per_window, int pre, int post,
                                     double* median, double* aligned, void* stream) {
   if (!windows || !peaks || !d_peak_off || !median || n_win < 0 || L < 1) return AEW_ERR_ARG;
-  if (max_peaks_per_window > 128 || pre + post != K3_BEAT || n_win > 0x7fffffffll) return AEW_ERR_UNSUPPORTED;
+  if (max_peaks_per_window > 128 || pre < 0 || post < 1 || pre + post > K3_MAXS || n_win > 0x7fffffffll)
+    return AEW_ERR_UNSUPPORTED;
   if (n_win == 0) return AEW_OK;
   AEW_LAUNCH(k4_median, (unsigned)n_win, K3_NT, 0, (cudaStream_t)stream, windows, L, peaks, d_peak_off, pre, post,
              median, aligned);

@@ -1,6 +1,8 @@
 """Drop-in for data_load_preprocess/remove_samples.py (reference lines 8-121)."""
 from __future__ import annotations
 
+import ctypes
+
 import numpy as np
 
 from .. import _cabi
@@ -49,22 +51,34 @@ def remove_samples(samples_wave_tracks, indices_samples, track_names, sampling_f
         "ecg_hr": stats[sel, 0], "ecg_hrv_rmssd": stats[sel, 1], "ecg_sd": stats[sel, 2], "ecg_sd/hr": stats[sel, 3]})
 
 
+def _peak_stats(min_peaks, max_peaks, sampling_frequency, mode):
+    """(hr, rmssd) of peak lists on the device (``aew_peak_stats_f64``: the arithmetic the window kernel uses)."""
+    torch, lib = _cabi.require_cuda()
+    lo = np.ascontiguousarray(np.asarray(min_peaks, dtype=np.int64).reshape(-1))
+    hi = np.ascontiguousarray(np.asarray(max_peaks, dtype=np.int64).reshape(-1))
+    d_lo = torch.from_numpy(lo).cuda() if lo.size else None
+    d_hi = torch.from_numpy(hi).cuda() if hi.size else None
+    scratch = torch.empty(2 * (lo.size + hi.size) + 8, dtype=torch.float64, device="cuda")
+    out = torch.empty(2, dtype=torch.float64, device="cuda")
+    p = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+    _cabi.check(lib.aew_peak_stats_f64(p(d_lo), lo.size, p(d_hi), hi.size, mode, float(60 * sampling_frequency),
+                                       float(sampling_frequency * 1000), p(scratch), p(out),
+                                       _cabi.stream_ptr(torch)), "peak_stats")
+    return out.cpu().numpy()
+
+
 def estimate_hr(min_peaks, max_peaks, sampling_frequency, mod='mean'):
-    """remove_samples.py:85-107 -- 60*fs / median(peak intervals); scalar host arithmetic
-    (the batched path computes it inside the window kernel)."""
-    lo, hi = np.diff(min_peaks), np.diff(max_peaks)
-    if mod == 'min':
-        med = np.median(lo)
-    elif mod == 'mean':
-        med = np.median(np.concatenate([lo, hi]))
-    else:
-        if not mod == 'max':
-            print('mod selection got wrong parameter: {}, Use "max" as default settings'.format(mod))
-        med = np.median(hi)
-    return 60 * sampling_frequency / med
+    """remove_samples.py:85-107 -- 60 * fs / median of the peak-to-peak intervals of the chosen list(s):
+    'min' -> min_peaks, 'mean' -> both lists pooled, anything else -> max_peaks (the reference prints a notice for
+    an unknown ``mod`` and goes on with 'max'; so does this).  NaN below two peaks."""
+    mode = {'min': 0, 'mean': 1, 'max': 2}.get(mod)
+    if mode is None:
+        print(f'estimate_hr: unknown mod {mod!r}, using "max"')
+        mode = 2
+    return np.float64(_peak_stats(min_peaks, max_peaks, sampling_frequency, mode)[0])
 
 
 def rmssd(peaks, sampling_frequency=500):
-    """remove_samples.py:110-121 (divisor fs*1000 as in the reference)."""
-    rr = np.diff(peaks) / (sampling_frequency * 1000)
-    return np.sqrt(np.mean(np.diff(rr) ** 2))
+    """remove_samples.py:110-121 -- sqrt(mean(diff(diff(peaks) / (fs * 1000)) ** 2)); the divisor is the
+    reference's.  NaN below three peaks."""
+    return np.float64(_peak_stats([], peaks, sampling_frequency, 2)[1])

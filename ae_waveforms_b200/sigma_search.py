@@ -44,6 +44,8 @@ class SigmaSearch:
         self.torch, self.lib = _cabi.require_cuda()
         torch = self.torch
         self.device = torch.device(device or "cuda")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
 
         def dev(a, dt):
             if isinstance(a, torch.Tensor):
@@ -59,6 +61,7 @@ class SigmaSearch:
             raise _cabi.AewError("features_x / features_y must be (n_beats, 11)")
         self.launches = 0
 
+    @_cabi.on_device
     def _call(self, cand, want_pred):
         torch, lib = self.torch, self.lib
         cand = cand if isinstance(cand, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(cand, dtype=np.float64))
@@ -75,6 +78,7 @@ class SigmaSearch:
         self.launches += 2
         return sse, pred
 
+    @_cabi.on_device
     def sse_grid(self, values, index):
         """Objective of candidates drawn from a discrete grid: candidate c uses sigma_map[s] = values[index[c, s]].
         One pass over the beats builds the separable error tables, then every candidate is scored from them
@@ -98,6 +102,7 @@ class SigmaSearch:
         self.launches += 3
         return sse
 
+    @_cabi.on_device
     def sse(self, candidates, method="auto"):
         """Sum over beats and samples of (float32(pred) - target)^2 per candidate (CUDA tensor).
         method "direct" evaluates every (beat, candidate) pair; "tables" requires the candidates to take at most
@@ -124,10 +129,12 @@ class SigmaSearch:
         """The reference's loss: torch.nn.MSELoss over all beats and samples."""
         return self.sse(candidates) / float(self.n_beats * self.n_t)
 
+    @_cabi.on_device
     def reconstruct(self, sigma_map):
         """(n_beats, 320) float64 reconstructions for one sigma map (analysis_...:121-132)."""
         return self._call(np.asarray(sigma_map, dtype=np.float64).reshape(1, 12), True)[1]
 
+    @_cabi.on_device
     def metrics(self, sigma_map, medians, compression_ratio: float = 320 / 20):
         """Per-beat RMSE, PRD and quality score of the reconstruction for one sigma map against the float64
         median beats (K9; analysis_...:178-197, functions_ae/loss_functions.py:8-20) plus the summary the
@@ -155,6 +162,7 @@ class SigmaSearch:
         return {"rmse": rmse, "prd": prd, "qs": qs, "recon": recon,
                 "summary": {"rmse": summary(rmse), "qs": summary(qs), "prd_mean": float(prd.mean())}}
 
+    @_cabi.on_device
     def best(self, candidates, sse=None):
         """argmin over the candidate list (NaN losses never win)."""
         torch = self.torch

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AEW_VERSION 107
+#define AEW_VERSION 108
 
 /* return codes */
 #define AEW_OK 0
@@ -117,8 +117,9 @@ typedef struct K3Params {
   int* n_peaks;
   int* peaks;                 /* [n_win][aew_windows_max_peaks()], -1 padded */
   double* stats;              /* [n_win][4]: ecg_hr, ecg_hrv_rmssd, ecg_sd, ecg_sd/hr */
-  double* median;             /* [n_win][320] float64 median beat of kept windows (may be NULL) */
-  float* waves;               /* [n_win][320] float32 copy = np_waves rows (may be NULL) */
+  double* median;             /* [n_win][pre + post] float64 median beat of kept windows (may be NULL); the section
+                                 is int(0.64 fs) samples, 320 at 500 Hz (median_sample.py:20-25) */
+  float* waves;               /* [n_win][pre + post] float32 copy = np_waves rows (may be NULL) */
   double* zwin;               /* [n_win][L] z-scored windows = 'ecg_sample' column (may be NULL) */
   double* zparams;            /* [n_win][2] scratch: mean, sd of each window's z-score.  With zscore_windows = 1 the
                                  median kernel needs the z-scored samples again: it reads them from zwin if that is
@@ -205,6 +206,23 @@ int aew_fiducial_features_f64(const double* d_sig, const long long* d_sig_off, l
                               const int* d_peaks, const int* d_n_peaks, int max_peaks, const int* d_fid,
                               const unsigned char* d_valid, double fs, double* d_features, int* d_status,
                               void* stream);
+
+/* The three stages of K6 as calls of their own, for the per-call drop-ins (any number of beats):
+ *   aew_fiducial_relative_f64  ecg_features_relative_r (features_ecg.py:56-86): d_fid [n_fid][n_beats] int32 indices
+ *                              (AEW_FID_NAN = np.nan) -> d_xy [n_fid][2][n_beats] = x (ms) then y per fiducial
+ *   aew_morphology_f64         compute_ecg_morphology_features (features_ecg.py:89-136): d_x, d_y [11][n_beats]
+ *                              (the ten fiducials in np_features order, then the inserted R peak) -> d_out [15][n_beats]
+ *   aew_nanmedian_rows_f64     compute_median_features_ecg (median_sample.py:57-82): np.nanmedian of every row of
+ *                              d_vals [rows][n]; d_scratch [rows][n]
+ *   aew_peak_stats_f64         estimate_hr / rmssd (remove_samples.py:85-121): d_out[0] = hr_num / median(intervals)
+ *                              (mode 0 'min', 1 'mean', 2 'max' picks the lists), d_out[1] = RMSSD of d_max_peaks with
+ *                              the reference's divisor rr_div = fs * 1000; d_scratch [2 * (n_min + n_max) + 4] */
+int aew_fiducial_relative_f64(const double* d_sig, int L, const int* d_peaks, const int* d_fid, int n_fid,
+                              int n_beats, double fs, double* d_xy, int* d_status, void* stream);
+int aew_morphology_f64(const double* d_x, const double* d_y, int n_beats, double* d_out, void* stream);
+int aew_nanmedian_rows_f64(const double* d_vals, int rows, int n, double* d_scratch, double* d_out, void* stream);
+int aew_peak_stats_f64(const long long* d_min_peaks, int n_min, const long long* d_max_peaks, int n_max, int mode,
+                       double hr_num, double rr_div, double* d_scratch, double* d_out, void* stream);
 
 /* ---- K5: Gaussian fiducial reconstruction + sigma-map search objective --------------
  * replaces gaussian_line / extract_coordinates / reconstruct_gaussian

@@ -1,9 +1,10 @@
-"""Import the REAL reference modules from /root/reference (TEST INFRASTRUCTURE).
+"""Import the REAL reference modules (TEST INFRASTRUCTURE).
 
-Only works in the build container, where the reference tree is mounted
-read-only; the GPU box has no such tree, so nothing that runs there may call
-this.  Used by tests/golden/make_golden.py to freeze golden vectors and by the
-CPU tests (skipped when the tree is absent) to cross-check ``oracle.ref_port``.
+In the build container the reference tree is mounted read-only at /root/reference.  The GPU box has no such
+tree: there the modules come from ``oracle/_ref/`` -- the reference's own files byte-compiled by
+``oracle/build_ref.py`` (git-ignored build output that travels with the snapshot, like the repo's ``.so``).
+Used by tests/golden/make_golden.py to freeze golden vectors, by the tests to cross-check ``oracle.ref_port``
+and the drop-ins, and by ``bench.py``'s CPU arm (``cpu_baseline.kind = "reference"``).
 
 The reference imports matplotlib (absent here) at module level and
 ``neurokit2`` (absent, un-vendored) inside remove_samples.py; both are replaced
@@ -17,11 +18,26 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = "/root/reference"
+SOURCE_ROOT = "/root/reference"
+COMPILED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def root() -> str | None:
+    """The live tree if present, else the byte-compiled copy, else None."""
+    if os.path.isdir(os.path.join(SOURCE_ROOT, "data_load_preprocess")):
+        return SOURCE_ROOT
+    if os.path.exists(os.path.join(COMPILED_ROOT, "data_load_preprocess", "filters.pyc")):
+        return COMPILED_ROOT
+    return None
 
 
 def available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "data_load_preprocess"))
+    return root() is not None
+
+
+def install_stubs():
+    """matplotlib stub + neurokit2 -> oracle restatements (both absent from this image)."""
+    _install_stubs()
 
 
 def _install_stubs():
@@ -35,6 +51,12 @@ def _install_stubs():
         from . import nk_peaks
         nk = types.ModuleType("neurokit2")
         nk.ecg_findpeaks = nk_peaks.ecg_findpeaks
+        try:
+            from . import nk_delineate
+            nk.ecg_delineate = lambda sig, rpeaks=None, sampling_rate=1000, **kw: (
+                None, nk_delineate.ecg_delineate(sig, rpeaks, sampling_rate))
+        except Exception:                                   # pragma: no cover
+            pass
         sys.modules["neurokit2"] = nk
 
 
@@ -43,8 +65,10 @@ class _Ref:
 
 
 def load() -> _Ref:
-    if not available():
-        raise RuntimeError("reference tree not present (only exists in the build container)")
+    ref_root = root()
+    if ref_root is None:
+        raise RuntimeError("reference modules not present: neither /root/reference nor oracle/_ref "
+                           "(run oracle/build_ref.py in the build container)")
     _install_stubs()
     # the drop-in packages of this repo use the same dotted names; make sure the
     # reference's win for this import and are not cached under those names after
@@ -53,7 +77,7 @@ def load() -> _Ref:
                   if k.split(".")[0] in ("data_load_preprocess", "functions_traditional")}
     for k in saved_mods:
         del sys.modules[k]
-    sys.path.insert(0, REFERENCE_ROOT)
+    sys.path.insert(0, ref_root)
     try:
         ref = _Ref()
         ref.filters = importlib.import_module("data_load_preprocess.filters")

@@ -112,14 +112,16 @@ def screen(flat, starts, Lw=10000, mode=0, zscore_windows=True, want_z=False, fs
     flat = np.ascontiguousarray(flat, dtype=np.float64)
     starts = np.ascontiguousarray(starts, dtype=np.int64)
     n, maxp = len(starts), L.aew_windows_max_peaks()
+    sec = int(0.8 * (60 / 75) * fs)                        # median_sample.py:20-25
+    pre = int(1 / 3 * sec)
     o = dict(keep=np.zeros(n, np.uint8), has_nan=np.zeros(n, np.uint8), n_peaks=np.zeros(n, np.int32),
-             peaks=np.zeros((n, maxp), np.int32), stats=np.zeros((n, 4)), median=np.full((n, 320), -5.0),
-             waves=np.zeros((n, 320), np.float32), zwin=np.zeros((n, Lw)), zparams=np.zeros((n, 2)),
+             peaks=np.zeros((n, maxp), np.int32), stats=np.zeros((n, 4)), median=np.full((n, sec), -5.0),
+             waves=np.zeros((n, sec), np.float32), zwin=np.zeros((n, Lw)), zparams=np.zeros((n, 2)),
              status=np.zeros(1, np.int32),
              hazards=np.zeros(1, np.uint64))
     p = _cabi.K3Params(
         y=flat.ctypes.data, win_start=starts.ctypes.data, n_win=n, L=Lw, smooth_k=int(np.rint(0.1 * fs)),
-        avg_k=int(np.rint(0.75 * fs)), refractory=int(np.rint(0.3 * fs)), pre=106, post=214, hr_num=60.0 * fs,
+        avg_k=int(np.rint(0.75 * fs)), refractory=int(np.rint(0.3 * fs)), pre=pre, post=sec - pre, hr_num=60.0 * fs,
         rr_div=fs * 1000.0, hr_lo=30.0, hr_hi=180.0, pvc_threshold=pvc, sd_threshold=sdt, mode=mode,
         zscore_windows=1 if zscore_windows else 0, keep=o["keep"].ctypes.data, has_nan=o["has_nan"].ctypes.data,
         n_peaks=o["n_peaks"].ctypes.data, peaks=o["peaks"].ctypes.data, stats=o["stats"].ctypes.data,
@@ -259,4 +261,38 @@ def beat_metrics(recon, median, cr=16.0):
     out = [np.zeros(n, np.float32) for _ in range(3)]
     rc = L.aew_beat_metrics_f32(ptr(recon), ptr(median), n, nt, float(cr), ptr(out[0]), ptr(out[1]), ptr(out[2]), None)
     assert rc == 0, rc
+    return out
+
+
+def feature_stages(window, peaks, fid, fs=500.0):
+    """The three K6 stage entries (the per-call drop-ins' kernels): returns rel x, y (10, n), morph (15, n),
+    medians (35,) in np_features order."""
+    L = lib()
+    w = np.ascontiguousarray(window, dtype=np.float64)
+    pk = np.ascontiguousarray(peaks, dtype=np.int32)
+    nb = len(pk)
+    f = np.asarray(fid, dtype=np.float64).reshape(10, nb)
+    idx = np.ascontiguousarray(np.where(np.isnan(f), FID_NAN, f).astype(np.int64).astype(np.int32))
+    xy = np.zeros((10, 2, nb))
+    status = np.zeros(1, np.int32)
+    assert L.aew_fiducial_relative_f64(ptr(w), len(w), ptr(pk), ptr(idx), 10, nb, float(fs), ptr(xy), ptr(status),
+                                       None) == 0 and status[0] == 0
+    X = np.ascontiguousarray(np.concatenate([xy[:, 0, :], np.zeros((1, nb))]))
+    Y = np.ascontiguousarray(np.concatenate([xy[:, 1, :], np.zeros((1, nb))]))
+    morph = np.zeros((15, nb))
+    assert L.aew_morphology_f64(ptr(X), ptr(Y), nb, ptr(morph), None) == 0
+    rows = np.ascontiguousarray(np.concatenate([xy.reshape(20, nb), morph]))
+    med, scratch = np.zeros(35), np.zeros_like(rows)
+    assert L.aew_nanmedian_rows_f64(ptr(rows), 35, nb, ptr(scratch), ptr(med), None) == 0
+    return xy[:, 0, :], xy[:, 1, :], morph, med
+
+
+def peak_stats(min_peaks, max_peaks, fs=500, mode=2):
+    L = lib()
+    lo = np.ascontiguousarray(min_peaks, dtype=np.int64)
+    hi = np.ascontiguousarray(max_peaks, dtype=np.int64)
+    scratch = np.zeros(2 * (len(lo) + len(hi)) + 8)
+    out = np.zeros(2)
+    assert L.aew_peak_stats_f64(ptr(lo) if len(lo) else None, len(lo), ptr(hi) if len(hi) else None, len(hi), mode,
+                                float(60 * fs), float(fs * 1000), ptr(scratch), ptr(out), None) == 0
     return out

@@ -115,6 +115,9 @@ def test_k3_other_window_lengths():
                 assert same(o["peaks"][j, :o["n_peaks"][j]], want["peaks"][j]), (fs, Lw, mode, j)
                 assert bool(o["keep"][j]) == bool(want["keep"][j])
                 assert same(o["stats"][j, :3], [want["hr"][j], want["rmssd"][j], want["sd"][j]])
+                if want["keep"][j]:                        # the section scales with the rate (median_sample.py:20-25)
+                    m = rp.compute_median_sample_ecg(wins[j], want["peaks"][j], fs)
+                    assert m.shape == (int(0.8 * (60 / 75) * fs),) and same(o["median"][j], m), (fs, Lw, mode, j)
 
 
 def test_k4_median_golden(golden):
@@ -209,6 +212,35 @@ def test_k6_features_golden_and_oracle(golden):
     for i in range(8):
         assert same(rows[i], _oracle_row(wins[i], pks[i], fids[i])), i
     assert np.isnan(rows[8]).all()                         # delineation failed: NaN row, window kept
+
+
+def test_k6_stage_entries_golden(golden):
+    """The per-call drop-ins' kernels against the outputs of the reference's own three functions."""
+    g = golden("features")
+    gf = np.where(g["fiducials"] < 0, np.nan, g["fiducials"])
+    x, y, morph, med = eh.feature_stages(g["window"], g["r_peaks"], gf)
+    assert same(x, g["rel_x"]) and same(y, g["rel_y"]) and same(morph, g["morph"]) and same(med, g["row35"])
+    rng = np.random.default_rng(11)
+    for n in (1, 2, 5, 37, 90, 200):                       # any number of beats, NaN-heavy
+        w = rng.standard_normal(10000)
+        p = np.sort(rng.choice(np.arange(150, 9800), n, replace=False))
+        f = _random_fiducials(rng, p, 10000, p_nan=0.4)
+        _, _, _, med = eh.feature_stages(w, p, f)
+        assert same(med, _oracle_row(w, p, f)), n
+
+
+def test_k6_peak_stats_match_the_reference_formulas():
+    import warnings
+    rng = np.random.default_rng(3)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for n in (0, 1, 2, 3, 4, 9, 26, 71, 140, 300):
+            hi = np.cumsum(rng.integers(160, 700, n)) if n else np.zeros(0, np.int64)
+            lo = np.cumsum(rng.integers(160, 700, max(0, n - 1))) if n > 1 else np.zeros(0, np.int64)
+            for mode, mod in ((0, "min"), (1, "mean"), (2, "max")):
+                got = eh.peak_stats(lo, hi, 500, mode)
+                assert same(got[0], rp.estimate_hr(lo, hi, 500, mod)), (n, mod)
+                assert same(got[1], rp.rmssd(hi, 500)), n
 
 
 def _delineation_cases():
