@@ -135,7 +135,8 @@ class Preprocessor:
 
     def __init__(self, fs: int = 500, sample_length: int = 20, hp: float = 1, lp: float = 30, order: int = 4,
                  pvc_threshold: float = 150, sd_threshold: float = 0.05, filter_mode: str = "fast",
-                 screen_mode: str = "auto", max_segments: int | None = None, device=None):
+                 screen_mode: str = "auto", max_segments: int | None = None, device=None,
+                 exact_masks: bool = False):
         self.torch, self.lib = _cabi.require_cuda()
         self.device = self.torch.device(device or "cuda")
         if self.device.index is None:                      # bind to the device that is current NOW
@@ -147,6 +148,11 @@ class Preprocessor:
         self.filter_mode = {"fast": 0, "exact": 1}[filter_mode]
         self.screen_mode = {"auto": 0, "exact": 1, "fast": 2, "forced_fallback": 3}[screen_mode]
         self.max_segments = max_segments
+        # With the tiled (fast) filter the windows are ~1e-9 from SciPy's, which flips the last bit of np.std in a
+        # z-scored window and with it the rule sd / n_peaks > 0.05 exactly when n_peaks == 20.
+        # exact_masks: the records that hold such windows are filtered AGAIN in SciPy's literal order and those
+        # windows re-screened from that output, so every keep / remove decision is the reference's bit for bit.
+        self.exact_masks = bool(exact_masks) and self.filter_mode == 0
         self.launches = 0
         if self.L > self.lib.aew_windows_max_len():
             raise _cabi.AewError(f"window of {self.L} samples exceeds the kernel limit")
@@ -221,9 +227,10 @@ class Preprocessor:
         return mean, sd, cnt
 
     @_cabi.on_device
-    def filter_records(self, flat, beg_h, end_h, d_beg, d_end, mean=None, sd=None, cnt=None, out=None, tmp=None):
+    def filter_records(self, flat, beg_h, end_h, d_beg, d_end, mean=None, sd=None, cnt=None, out=None, tmp=None,
+                       mode=None):
         """K2: z-score (fused) + high-pass + low-pass per NaN-delimited segment.
-        Returns (filtered, device header tensor)."""
+        Returns (filtered, device header tensor).  ``mode`` overrides the object's filter mode (0 tiled, 1 exact)."""
         torch, lib = self.torch, self.lib
         n_rec, total = len(beg_h), flat.numel()
         max_seg = self.max_segments or (4 * n_rec + 4096)
@@ -231,7 +238,9 @@ class Preprocessor:
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
         y = torch.empty_like(flat) if out is None else out
         tmp = torch.empty_like(flat) if tmp is None else tmp
-        self._filter_tmp = tmp                  # free again once the filter is done: scratch for the window kernels
+        if mode is None:
+            self._filter_tmp = tmp              # free again once the filter is done: scratch for the window kernels
+        filter_mode = self.filter_mode if mode is None else mode
         st = _cabi.stream_ptr(torch)
         _cabi.check(lib.aew_segments_find_f64(_ptr(flat), _ptr(d_beg), _ptr(d_end), n_rec, total, _ptr(cnt), _ptr(y),
                                               _ptr(ws), ws_bytes, max_seg, st), "segments_find")
@@ -240,12 +249,12 @@ class Preprocessor:
                               self.lp and design_filter("low", self.lp, self.fs, self.order, self.device)) if d]
         src, m, s = flat, mean, sd
         for d in stages:
-            if self.filter_mode == 0 and not d.fast_ok:
+            if filter_mode == 0 and not d.fast_ok:
                 raise _cabi.AewError(f"{d}: no modal form; use filter_mode='exact'")
             _cabi.check(lib.aew_filtfilt_f64(_ptr(src), _ptr(m), _ptr(s), _ptr(y), _ptr(tmp), _ptr(d.table),
                                              _np_ptr(d.table_host), n_rec, total, _ptr(ws), ws_bytes, max_seg,
-                                             self.filter_mode, st), "filtfilt")
-            self.launches += 1 if self.filter_mode else 2
+                                             filter_mode, st), "filtfilt")
+            self.launches += 1 if filter_mode else 2
             src, m, s = y, None, None
         if not stages:                                       # both cut-offs falsy: z-score only
             if mean is not None:
@@ -374,6 +383,58 @@ class Preprocessor:
         feats, status = self.fiducial_features(zwin_flat, off, scr["peaks"], scr["n_peaks"], fid, valid, L=L)
         return feats, flags, fid, status
 
+    def hazard_peak_count(self):
+        """The beat count at which ``sd / n_peaks > sd_threshold`` hangs on the last bit of np.std of a z-scored
+        window (sd = 1 +- a few ulp): n with n * threshold == 1 (20 for the reference's 0.05); None if there is none."""
+        if not self.sd_threshold > 0:
+            return None
+        n = int(round(1.0 / self.sd_threshold))
+        return n if n >= 1 and abs(n * self.sd_threshold - 1.0) < 1e-9 else None
+
+    @_cabi.on_device
+    def resolve_hazards(self, flat, beg_h, end_h, mean, sd, cnt, win_start, win_rec, scr, zwin_main=None):
+        """exact_masks: windows whose keep / remove decision depends on the last bit of np.std (n_peaks ==
+        hazard_peak_count(), every other rule passed) are decided from SciPy-order filter output.  The records that
+        hold such windows are gathered into a compact batch, filtered by the sequential kernel (bit-identical to
+        scipy.signal.filtfilt), the hazard windows screened again from that output and their rows of ``scr``
+        replaced -- keep, peaks, stats, median beat: for these windows everything is the reference's bit for bit.
+        Returns the number of windows re-decided and the number whose decision changed."""
+        torch = self.torch
+        nh = self.hazard_peak_count()
+        if nh is None or not len(win_start):
+            return 0, 0
+        st = scr["stats"]
+        hr, rms = st[:, 0], st[:, 1]
+        hz = (scr["n_peaks"] == nh) & (scr["has_nan"] == 0) & (hr >= 30.0) & (hr <= 180.0) & ~(rms > self.pvc_threshold)
+        hz_idx = torch.nonzero(hz).squeeze(1)
+        if hz_idx.numel() == 0:                                  # (sync: the list of hazard windows)
+            return 0, 0
+        hz_h = hz_idx.cpu().numpy()
+        recs = np.unique(win_rec[hz_h])
+        lens = (end_h[recs] - beg_h[recs]).astype(np.int64)
+        coff = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        xc = torch.cat([flat[int(b):int(e)] for b, e in zip(beg_h[recs], end_h[recs])])
+        d_rec = self._upload(recs.astype(np.int64))
+        d_off = self._upload(coff)
+        yc, tc = torch.empty_like(xc), torch.empty_like(xc)
+        self.filter_records(xc, coff[:-1].copy(), coff[1:].copy(), d_off[:-1].contiguous(), d_off[1:].contiguous(),
+                            mean.index_select(0, d_rec), sd.index_select(0, d_rec), cnt.index_select(0, d_rec),
+                            out=yc, tmp=tc, mode=1)
+        pos = np.searchsorted(recs, win_rec[hz_h])
+        start_c = win_start[hz_h] - beg_h[win_rec[hz_h]] + coff[pos]
+        L = self.L
+        scr2 = self.screen_windows(yc, np.ascontiguousarray(start_c, dtype=np.int64),
+                                   zwin_scratch=tc if tc.numel() >= len(hz_h) * L else None)
+        changed = int((scr2["keep"] != scr["keep"].index_select(0, hz_idx)).sum().item())
+        for k in ("keep", "has_nan", "n_peaks", "peaks", "stats", "median", "waves", "zparams"):
+            if scr.get(k) is not None and scr2.get(k) is not None:
+                scr[k].index_copy_(0, hz_idx, scr2[k])
+        if zwin_main is not None and tc.numel() >= len(hz_h) * L:   # the parked z-scored windows (features path)
+            zwin_main[:scr["keep"].shape[0] * L].view(-1, L).index_copy_(0, hz_idx, tc[:len(hz_h) * L].view(-1, L))
+        scr["status"] |= scr2["status"]
+        scr["hazards"] += scr2["hazards"]
+        return len(hz_h), changed
+
     # ------------------------------------------------------------------ whole path
     @_cabi.on_device
     def run(self, batch: RecordBatch, trim: bool = True, keep_intermediates: bool = False,
@@ -396,13 +457,19 @@ class Preprocessor:
             win_start = np.ascontiguousarray(beg_h, dtype=np.int64)
             win_case = np.asarray(batch.case_ids)
             win_end = np.full(len(beg_h), self.L, dtype=np.int64)
+            win_rec = np.arange(len(beg_h))
         else:
             win_start, win_case, win_end = self.window_table(beg_h, end_h, batch.case_ids)
+            win_rec = np.repeat(np.arange(len(beg_h)), [window_count(e - b, self.L) for b, e in zip(beg_h, end_h)])
         info_h = np.stack([win_case.astype(np.float64), win_end.astype(np.float64)], axis=1) if len(win_start) \
             else np.zeros((0, 2))
         info = self._upload(info_h)
         tmp = getattr(self, "_filter_tmp", None)
         scr = self.screen_windows(y, win_start, zwin_scratch=tmp)
+        n_hazard = n_flipped = 0
+        if self.exact_masks:
+            n_hazard, n_flipped = self.resolve_hazards(flat, beg_h, end_h, mean, sd, cnt, win_start, win_rec, scr,
+                                                       zwin_main=tmp if features else None)
         keep_mask = scr["keep"]
         feats = None
         if features and len(win_start) and not (self.hp and self.lp):
@@ -446,7 +513,8 @@ class Preprocessor:
         _cabi.check_device_status(int(w[3]), "window screen")
         if feats is not None:
             _cabi.check_device_status(int(w[6]), "fiducial features")
-        res.update(n_segments=int(w[0]), n_tiles=int(w[1]), hazard_windows=int(w[4]), n_beats=int(w[5]))
+        res.update(n_segments=int(w[0]), n_tiles=int(w[1]), hazard_windows=int(w[4]), n_beats=int(w[5]),
+                   mask_hazard_windows=n_hazard, mask_flips_resolved=n_flipped)
         if keep_intermediates:
             res.update(filtered=y, rec_beg=beg_h, rec_end=end_h, win_start=win_start)
         return res

@@ -727,7 +727,14 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
 }
 
 // ------------------------------------------------------------ exact sequential mode
-// scipy's evaluation order, separate multiply and add, runtime order.
+// SciPy's evaluation order (lfilter's direct form II transposed, one sample at a time, separate multiply and add):
+// bit-identical to scipy.signal.filtfilt.  The recursion cannot be re-associated without changing the bits
+// (profiles/README.md: two DF2T trajectories that start one ulp apart do not merge again), so ONE lane walks each
+// segment; what the kernel can do is keep that lane's dependent chain -- DADD, DMUL, DADD per sample, 3 x 8
+// cycles -- free of everything else.  One WARP per segment: all lanes load the next 32 samples (coalesced, one
+// block ahead), z-score them (the correctly rounded division of the first pass) and form the products b[k] x
+// into shared memory; lane 0 runs the 32 steps from there; all lanes store the 32 outputs.  ~30 cycles per sample
+// and pass instead of the ~250 of a single thread that waits for each global load in turn.
 __device__ __forceinline__ double df2t_step_exact(const double* b, const double* a, int ord, double x, double* z) {
   const double y = __dadd_rn(z[0], __dmul_rn(b[0], x));
   for (int k = 0; k < ord - 1; ++k)
@@ -736,38 +743,81 @@ __device__ __forceinline__ double df2t_step_exact(const double* b, const double*
   return y;
 }
 
-__global__ void __launch_bounds__(32) k2_exact(PassArgs a) {
+#define K2E_BLK 32
+// one pass over n samples: logical sample i is in[i] (REV: in[n - 1 - i]); lane 0 owns the state z
+template <int ORD, bool REV>
+__device__ __forceinline__ void exact_stream(const double* in, double* out, long long n, const double* b,
+                                             const double* a, double* z, bool zon, double mean, const ExactDiv& sd,
+                                             double (*sp)[K2E_BLK], double* sy, int lane) {
+  double v = 0.0;
+  if (lane < n) v = in[REV ? n - 1 - lane : lane];
+  for (long long i0 = 0; i0 < n; i0 += K2E_BLK) {
+    const long long j = i0 + K2E_BLK + lane;             // the block after this one is in flight while lane 0 works
+    double vn = 0.0;
+    if (j < n) vn = in[REV ? n - 1 - j : j];
+    const double x = zs(v, zon, mean, sd);
+#pragma unroll
+    for (int k = 0; k <= ORD; ++k) sp[k][lane] = __dmul_rn(b[k], x);
+    __syncwarp();
+    if (lane == 0) {
+      const int cnt = (int)(n - i0 < K2E_BLK ? n - i0 : K2E_BLK);
+#pragma unroll 4
+      for (int t = 0; t < cnt; ++t) {
+        const double y = __dadd_rn(z[0], sp[0][t]);
+#pragma unroll
+        for (int k = 0; k < ORD - 1; ++k) z[k] = __dsub_rn(__dadd_rn(z[k + 1], sp[k + 1][t]), __dmul_rn(y, a[k + 1]));
+        z[ORD - 1] = __dsub_rn(sp[ORD][t], __dmul_rn(y, a[ORD]));
+        sy[t] = y;
+      }
+    }
+    __syncwarp();
+    if (i0 + lane < n) out[REV ? n - 1 - (i0 + lane) : i0 + lane] = sy[lane];
+    __syncwarp();
+    v = vn;
+  }
+}
+
+template <int ORD>
+__global__ void __launch_bounds__(K2E_BLK) k2_exact(PassArgs a) {
+  __shared__ double sp[ORD + 1][K2E_BLK];
+  __shared__ double sy[K2E_BLK];
   const long long n_seg = a.ws.hdr[H_SEG_COUNT] < a.ws.max_seg ? a.ws.hdr[H_SEG_COUNT] : a.ws.max_seg;
-  const long long seg = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long seg = blockIdx.x;
+  const int lane = threadIdx.x;
   if (seg >= n_seg) return;
   const long long* sg = a.ws.segs + 4 * seg;
   const long long g0 = sg[0], n = sg[1], rec = sg[2];
   const bool zon = a.mean != nullptr;
   const double mean = zon ? a.mean[rec] : 0.0;
-      const ExactDiv sd = make_exact_div(zon ? a.sd[rec] : 1.0);
-  const int ord = (int)a.tab[K2_TAB_ORDER], pad = (int)a.tab[K2_TAB_PAD];
-  double b[5], ac[5], zi[4], z[4];
+  const ExactDiv sd = make_exact_div(zon ? a.sd[rec] : 1.0);
+  const int pad = (int)a.tab[K2_TAB_PAD];
+  double b[5], ac[5], zi[4], z[4] = {0.0, 0.0, 0.0, 0.0};
   for (int i = 0; i < 5; ++i) { b[i] = a.tab[K2_TAB_B + i]; ac[i] = a.tab[K2_TAB_A + i]; }
   for (int i = 0; i < 4; ++i) zi[i] = a.tab[K2_TAB_ZI + i];
   const double* xs = a.src + g0;
   double* out = a.passthrough + g0;
   double* tmp = a.dst + g0;
-  if (n <= pad) {
-    for (long long i = 0; i < n; ++i) out[i] = zs(xs[i], zon, mean, sd);
+  if (n <= pad) {                                        // filters.py:50-51: too short to filter, copied through
+    for (long long i = lane; i < n; i += K2E_BLK) out[i] = zs(xs[i], zon, mean, sd);
     return;
   }
   double ve[K2_MAXPAD];
   const double x0 = zs(xs[0], zon, mean, sd), xl = zs(xs[n - 1], zon, mean, sd);
-  const double e0 = __dsub_rn(__dmul_rn(2.0, x0), zs(xs[pad], zon, mean, sd));
-  for (int i = 0; i < ord; ++i) z[i] = __dmul_rn(zi[i], e0);
-  for (int e = 0; e < pad; ++e)
-    df2t_step_exact(b, ac, ord, __dsub_rn(__dmul_rn(2.0, x0), zs(xs[pad - e], zon, mean, sd)), z);
-  for (long long i = 0; i < n; ++i) tmp[i] = df2t_step_exact(b, ac, ord, zs(xs[i], zon, mean, sd), z);
-  for (int m = 0; m < pad; ++m)
-    ve[m] = df2t_step_exact(b, ac, ord, __dsub_rn(__dmul_rn(2.0, xl), zs(xs[n - 2 - m], zon, mean, sd)), z);
-  for (int i = 0; i < ord; ++i) z[i] = __dmul_rn(zi[i], ve[pad - 1]);
-  for (int e = 0; e < pad; ++e) df2t_step_exact(b, ac, ord, ve[pad - 1 - e], z);
-  for (long long i = n - 1; i >= 0; --i) out[i] = df2t_step_exact(b, ac, ord, tmp[i], z);
+  if (lane == 0) {                                       // odd extension on the left, zi scaled by its first sample
+    const double e0 = __dsub_rn(__dmul_rn(2.0, x0), zs(xs[pad], zon, mean, sd));
+    for (int i = 0; i < ORD; ++i) z[i] = __dmul_rn(zi[i], e0);
+    for (int e = 0; e < pad; ++e)
+      df2t_step_exact(b, ac, ORD, __dsub_rn(__dmul_rn(2.0, x0), zs(xs[pad - e], zon, mean, sd)), z);
+  }
+  exact_stream<ORD, false>(xs, tmp, n, b, ac, z, zon, mean, sd, sp, sy, lane);
+  if (lane == 0) {                                       // right extension, then the backward pass starts inside it
+    for (int m = 0; m < pad; ++m)
+      ve[m] = df2t_step_exact(b, ac, ORD, __dsub_rn(__dmul_rn(2.0, xl), zs(xs[n - 2 - m], zon, mean, sd)), z);
+    for (int i = 0; i < ORD; ++i) z[i] = __dmul_rn(zi[i], ve[pad - 1]);
+    for (int e = 0; e < pad; ++e) df2t_step_exact(b, ac, ORD, ve[pad - 1 - e], z);
+  }
+  __syncwarp();                                          // (orders the warp's stores to tmp before the reads below)
+  exact_stream<ORD, true>(tmp, out, n, b, ac, z, false, 0.0, sd, sp, sy, lane);
 }
 
 unsigned long long* g_dbg = nullptr;   // device counters, allocated once when AEW_K2_TIMING is set
@@ -839,9 +889,15 @@ extern "C" int aew_filtfilt_f64(const double* src, const double* mean, const dou
     a.dbg = g_dbg;
   }
 #endif
-  if (mode == 1) {
-    const long long blocks = (max_seg + 31) / 32;
-    AEW_LAUNCH(k2_exact, (unsigned)blocks, 32, 0, st, a);
+  if (mode == 1) {                                       // one warp per segment (blocks beyond the count exit)
+    const long long blocks = max_seg;
+    switch ((int)h_tab[K2_TAB_ORDER]) {
+      case 1: AEW_LAUNCH(k2_exact<1>, (unsigned)blocks, K2E_BLK, 0, st, a); break;
+      case 2: AEW_LAUNCH(k2_exact<2>, (unsigned)blocks, K2E_BLK, 0, st, a); break;
+      case 3: AEW_LAUNCH(k2_exact<3>, (unsigned)blocks, K2E_BLK, 0, st, a); break;
+      case 4: AEW_LAUNCH(k2_exact<4>, (unsigned)blocks, K2E_BLK, 0, st, a); break;
+      default: return AEW_ERR_UNSUPPORTED;
+    }
     return (int)cudaGetLastError();
   }
   if (mode != 0) return AEW_ERR_ARG;

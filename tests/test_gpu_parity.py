@@ -569,10 +569,49 @@ def test_pipeline_with_features_exact_filter(gpu):
     fast = B.process_cases(cases, list(range(len(cases))))
     ref_f = np.concatenate([r["np_features"] for r in refs])
     assert fast["np_features"].shape == ref_f.shape
-    # fast filter: windows differ by ~1e-9, so a fiducial may move by a sample in rare windows; the medians
-    # over beats must still agree closely almost everywhere
-    ok = np.isclose(fast["np_features"], ref_f, rtol=1e-6, atol=1e-6, equal_nan=True)
-    assert ok.mean() > 0.97
+    # fast filter: windows differ by ~1e-9 from SciPy's; no row of these cases changes, and the entries are within
+    # 1e-6 of the reference's on the scale of their row wherever no fiducial moved (a moved fiducial changes a
+    # median over beats by a sample step and is counted by test_parity_64_cases_against_the_oracle, not tolerated here)
+    scale = np.nanmax(np.abs(ref_f), axis=1, keepdims=True)
+    err = np.abs(fast["np_features"] - ref_f) / scale
+    moved = np.nanmax(err, axis=1) > 1e-6
+    assert same(np.isnan(fast["np_features"]), np.isnan(ref_f))
+    assert moved.sum() <= max(1, len(ref_f) // 100), (int(moved.sum()), len(ref_f))
+    # the same call with exact_masks re-decides the 20-peak windows from SciPy-order filter output: same rows
+    fast_x = B.process_cases(cases, list(range(len(cases))), exact_masks=True)
+    assert same(fast_x["np_info"], np.concatenate([r["np_info"] for r in refs]))
+
+
+def test_parity_64_cases_against_the_oracle(gpu):
+    """>= 64 HOST-generated 1 h cases (BASELINE configs[1] subsample) through the benchmarked
+    configuration (tiled filter) against the oracle, with hard bounds.  Every tenth case is pinned to 60 bpm so that
+    the n_peaks == 20 rounding hazard is well represented.
+      R peaks identical in every window; keep / remove differs only on 20-peak windows, and not at all with
+      exact_masks; median beats within 1e-6; fiducials identical in > 99.9 % of the entries; the 35 features
+      within 1e-6 (row scale) on windows whose fiducials are identical."""
+    torch, B = gpu
+    from oracle import parity
+    n_cases, n_samp = 64, 1800000
+    ids = list(range(3000, 3000 + n_cases))
+    hr = [60.0 if k % 10 == 0 else float(np.random.default_rng(k).uniform(50, 110)) for k in range(n_cases)]
+    exp = parity.expected(ids, n_samp, features=True, hr=hr)
+    cases = [e["x"] for e in exp]
+    for exact_masks in (False, True):
+        pre = B.Preprocessor(exact_masks=exact_masks)
+        res = pre.run(B.RecordBatch.from_host(cases, ids), features=True)
+        rep = parity.compare(exp, parity.gpu_result_to_numpy(res))
+        print("parity", "exact_masks" if exact_masks else "fast masks", rep,
+              {k: res[k] for k in ("mask_hazard_windows", "mask_flips_resolved")})
+        assert rep["windows"] == 64 * 179 and rep["windows_rpeaks_differ"] == 0
+        assert rep["mask_flips_off_hazard"] == 0
+        assert rep["median_max_rel_err"] <= 1e-6
+        assert rep["delineation_fate_differs"] == 0
+        assert rep["fiducials_identical_fraction"] > 0.999
+        assert rep["features_max_rel_err"] <= 1e-6 and rep["features_compared"] > 10000
+        assert rep["hazard_windows"] > 200
+        if exact_masks:
+            assert rep["mask_flips"] == 0 and rep["rows_gpu"] == rep["rows_reference"]
+            assert res["mask_hazard_windows"] >= rep["hazard_windows"] * 0.9
 
 
 def test_neurokit_shim(gpu):

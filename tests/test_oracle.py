@@ -146,3 +146,41 @@ def test_port_against_live_reference():
     assert same(z, rp.zscore(x))
     f = ref.filters.butterworth(ref.filters.butterworth(z, "high", 1), "low", 30)
     assert same(f, rp.butterworth(rp.butterworth(z, "high", 1), "low", 30))
+
+
+def test_parity_report_selfcheck():
+    """oracle.parity.compare on a GPU-shaped result built from the oracle itself: nothing differs; a flipped
+    hazard window and a moved fiducial are counted where they belong."""
+    from oracle import parity
+    exp = parity.expected([7, 3], 60000, features=True, cores=2)
+    keep, npk, pk, med, feat, fid, flags = [], [], [], [], [], [], []
+    for e in exp:
+        ks = 0
+        for j, k in enumerate(e["keep"]):
+            p = e["peaks"][j]
+            row = np.full(72, -1, np.int32)
+            row[:len(p)] = p
+            f, fl = np.full((10, 72), -2147483648, np.int64), 3
+            if k:
+                fr = e["fid"][ks]
+                if fr is None:
+                    fl = 1 if e["valid"][ks] else 2
+                else:
+                    fl = 0
+                    f[:, :len(p)] = np.where(np.isnan(fr), -2147483648, fr).astype(np.int64)
+                if fl != 2:
+                    med.append(e["medians"][ks]); feat.append(e["rows"][ks])
+                ks += 1
+            keep.append(k); npk.append(len(p)); pk.append(row); fid.append(f); flags.append(fl)
+    res = dict(keep=np.array(keep), n_peaks=np.array(npk), peaks=np.stack(pk), medians=np.stack(med),
+               np_features=np.stack(feat), fiducials=np.stack(fid), delineation_flags=np.array(flags))
+    rep = parity.compare(exp, res)
+    assert rep["windows"] == 10 and rep["mask_flips"] == 0 and rep["windows_rpeaks_differ"] == 0
+    assert rep["median_max_rel_err"] == 0 and rep["features_max_rel_err"] == 0
+    assert rep["fiducials_identical_fraction"] == 1.0 and rep["delineation_fate_differs"] == 0
+    assert rep["windows_fiducials_identical"] == rep["windows_delineated"] > 0
+    w = int(np.flatnonzero(res["delineation_flags"] == 0)[0])
+    res["fiducials"][w, 3, 1] += 1                          # one Q peak moved by a sample
+    rep = parity.compare(exp, res)
+    assert rep["fiducials_identical"] == rep["fiducials_compared"] - 1
+    assert rep["windows_fiducials_identical"] == rep["windows_delineated"] - 1
