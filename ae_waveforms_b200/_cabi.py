@@ -32,7 +32,7 @@ class K3Params(ctypes.Structure):
         ("pvc_threshold", c_double), ("sd_threshold", c_double), ("mode", c_int), ("zscore_windows", c_int),
         ("keep", c_void_p), ("has_nan", c_void_p), ("n_peaks", c_void_p), ("peaks", c_void_p),
         ("stats", c_void_p), ("median", c_void_p), ("waves", c_void_p), ("zwin", c_void_p),
-        ("zparams", c_void_p), ("status", c_void_p), ("hazard_count", c_void_p)]
+        ("zparams", c_void_p), ("status", c_void_p), ("hazard_count", c_void_p), ("lazy_sd", c_int)]
 
 
 # name -> (restype, argtypes); every symbol include/aewave.h declares

@@ -153,6 +153,9 @@ class Preprocessor:
         # exact_masks: the records that hold such windows are filtered AGAIN in SciPy's literal order and those
         # windows re-screened from that output, so every keep / remove decision is the reference's bit for bit.
         self.exact_masks = bool(exact_masks) and self.filter_mode == 0
+        self.defer_chunks = 6               # run_host_pipelined: chunks finished this many chunks late (exact_masks)
+        self.lazy_sd = True                 # run(): 'ecg_sd' is not an output; evaluate it only where it decides
+        self.park_windows = bool(int(__import__("os").environ.get("AEW_K3_PARK", "0")))   # measurement switch
         self.launches = 0
         if self.L > self.lib.aew_windows_max_len():
             raise _cabi.AewError(f"window of {self.L} samples exceeds the kernel limit")
@@ -282,7 +285,8 @@ class Preprocessor:
 
     @_cabi.on_device
     def screen_windows(self, y, win_start_h, want_median=True, want_zwin=False, zscore_windows=True,
-                       pvc_threshold=None, sd_threshold=None, L=None, zwin_scratch=None):
+                       pvc_threshold=None, sd_threshold=None, L=None, zwin_scratch=None, lazy_sd=False,
+                       d_start=None):
         """K3 + K4 on the windows whose flat offsets are given.  ``zwin_scratch``: optional float64 tensor of at
         least n_win * L elements; the screen kernel parks the z-scored windows there for the median kernel (which
         otherwise re-derives them from ``y`` and the per-window mean / sd)."""
@@ -305,7 +309,8 @@ class Preprocessor:
             hazards=torch.zeros(1, dtype=torch.int64, device=dev))
         if n_win == 0:
             return out
-        d_start = self._upload(np.ascontiguousarray(win_start_h, dtype=np.int64))
+        if d_start is None:
+            d_start = self._upload(np.ascontiguousarray(win_start_h, dtype=np.int64))
         zwin_ptr = out["zwin"].data_ptr() if want_zwin else None
         if zwin_ptr is None and want_median and zscore_windows and zwin_scratch is not None \
                 and zwin_scratch.dtype == torch.float64 and zwin_scratch.numel() >= n_win * L \
@@ -325,7 +330,8 @@ class Preprocessor:
             waves=out["waves"].data_ptr() if want_median else None,
             zwin=zwin_ptr,
             zparams=out["zparams"].data_ptr() if want_median else None,
-            status=out["status"].data_ptr(), hazard_count=out["hazards"].data_ptr())
+            status=out["status"].data_ptr(), hazard_count=out["hazards"].data_ptr(),
+            lazy_sd=1 if (lazy_sd and zscore_windows) else 0)
         _cabi.check(lib.aew_windows_beats_f64(ctypes.byref(p), _cabi.stream_ptr(torch)), "windows_beats")
         self.launches += 2 if want_median else 1
         out["_win_start"] = d_start
@@ -398,51 +404,72 @@ class Preprocessor:
         hold such windows are gathered into a compact batch, filtered by the sequential kernel (bit-identical to
         scipy.signal.filtfilt), the hazard windows screened again from that output and their rows of ``scr``
         replaced -- keep, peaks, stats, median beat: for these windows everything is the reference's bit for bit.
-        Returns the number of windows re-decided and the number whose decision changed."""
+
+        The sequential filter is a dependent chain of ~25 cycles per sample and pass: ~100 ms for a 1 h record
+        whatever the batch.  It needs a handful of warps, so it runs on a SIDE stream next to the kernels of the
+        following batches; this call only launches it.  Returns None (no such window) or a dict with ``event``
+        (recorded on the side stream after the rows of ``scr`` have been replaced), ``n`` and ``changed`` (device)."""
         torch = self.torch
         nh = self.hazard_peak_count()
         if nh is None or not len(win_start):
-            return 0, 0
+            return None
         st = scr["stats"]
         hr, rms = st[:, 0], st[:, 1]
         hz = (scr["n_peaks"] == nh) & (scr["has_nan"] == 0) & (hr >= 30.0) & (hr <= 180.0) & ~(rms > self.pvc_threshold)
         hz_idx = torch.nonzero(hz).squeeze(1)
         if hz_idx.numel() == 0:                                  # (sync: the list of hazard windows)
-            return 0, 0
+            return None
         hz_h = hz_idx.cpu().numpy()
         recs = np.unique(win_rec[hz_h])
         lens = (end_h[recs] - beg_h[recs]).astype(np.int64)
         coff = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        # main stream: the hazard records' samples and statistics are copied out, so that the side stream touches
+        # nothing the next batch may overwrite (input buffers, filter scratch)
         xc = torch.cat([flat[int(b):int(e)] for b, e in zip(beg_h[recs], end_h[recs])])
         d_rec = self._upload(recs.astype(np.int64))
         d_off = self._upload(coff)
-        yc, tc = torch.empty_like(xc), torch.empty_like(xc)
-        self.filter_records(xc, coff[:-1].copy(), coff[1:].copy(), d_off[:-1].contiguous(), d_off[1:].contiguous(),
-                            mean.index_select(0, d_rec), sd.index_select(0, d_rec), cnt.index_select(0, d_rec),
-                            out=yc, tmp=tc, mode=1)
+        m_c, s_c, n_c = mean.index_select(0, d_rec), sd.index_select(0, d_rec), cnt.index_select(0, d_rec)
         pos = np.searchsorted(recs, win_rec[hz_h])
-        start_c = win_start[hz_h] - beg_h[win_rec[hz_h]] + coff[pos]
+        start_c = np.ascontiguousarray(win_start[hz_h] - beg_h[win_rec[hz_h]] + coff[pos], dtype=np.int64)
+        d_start_c = self._upload(start_c)
         L = self.L
-        scr2 = self.screen_windows(yc, np.ascontiguousarray(start_c, dtype=np.int64),
-                                   zwin_scratch=tc if tc.numel() >= len(hz_h) * L else None)
-        changed = int((scr2["keep"] != scr["keep"].index_select(0, hz_idx)).sum().item())
-        for k in ("keep", "has_nan", "n_peaks", "peaks", "stats", "median", "waves", "zparams"):
-            if scr.get(k) is not None and scr2.get(k) is not None:
-                scr[k].index_copy_(0, hz_idx, scr2[k])
-        if zwin_main is not None and tc.numel() >= len(hz_h) * L:   # the parked z-scored windows (features path)
-            zwin_main[:scr["keep"].shape[0] * L].view(-1, L).index_copy_(0, hz_idx, tc[:len(hz_h) * L].view(-1, L))
-        scr["status"] |= scr2["status"]
-        scr["hazards"] += scr2["hazards"]
-        return len(hz_h), changed
+        main = torch.cuda.current_stream(self.device)
+        side = getattr(self, "_side_stream", None)
+        if side is None:
+            side = self._side_stream = torch.cuda.Stream(device=self.device, priority=-1)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
+            yc, tc = torch.empty_like(xc), torch.empty_like(xc)
+            self.filter_records(xc, coff[:-1].copy(), coff[1:].copy(), d_off[:-1].contiguous(), d_off[1:].contiguous(),
+                                m_c, s_c, n_c, out=yc, tmp=tc, mode=1)
+            scr2 = self.screen_windows(yc, start_c, zwin_scratch=tc if tc.numel() >= len(hz_h) * L else None,
+                                       d_start=d_start_c)
+            changed = (scr2["keep"] != scr["keep"].index_select(0, hz_idx)).sum()
+            for k in ("keep", "has_nan", "n_peaks", "peaks", "stats", "median", "waves", "zparams"):
+                if scr.get(k) is not None and scr2.get(k) is not None:
+                    scr[k].index_copy_(0, hz_idx, scr2[k])
+            if zwin_main is not None and tc.numel() >= len(hz_h) * L:   # the parked z-scored windows (features path)
+                zwin_main[:scr["keep"].shape[0] * L].view(-1, L).index_copy_(0, hz_idx, tc[:len(hz_h) * L].view(-1, L))
+            scr["status"] |= scr2["status"]
+            scr["hazards"] += scr2["hazards"]
+            done = torch.cuda.Event()
+            done.record(side)
+        return dict(event=done, n=len(hz_h), changed=changed, hold=(xc, yc, tc, scr2, m_c, s_c, n_c, d_rec, d_off,
+                                                                  d_start_c, hz_idx))
 
     # ------------------------------------------------------------------ whole path
     @_cabi.on_device
     def run(self, batch: RecordBatch, trim: bool = True, keep_intermediates: bool = False,
-            scratch: dict | None = None, features: bool = False, strips: bool = False) -> dict:
+            scratch: dict | None = None, features: bool = False, strips: bool = False, defer: bool = False):
         """Returns a dict of CUDA tensors: ``np_waves`` (n_keep, 320) float32,
         ``np_info`` (n_keep, 2) float64 = [case_id, idx_end], ``medians`` float64,
         plus per-window ``keep`` / ``has_nan`` / ``n_peaks`` / ``peaks`` / ``stats`` and
-        counters.  ``scratch`` may hold reusable 'y' / 'tmp' tensors shaped like the input."""
+        counters.  ``scratch`` may hold reusable 'y' / 'tmp' tensors shaped like the input.
+        ``defer``: return a pending handle right after the kernels have been launched; ``finish(handle)`` gives the
+        result.  With exact_masks the sequential re-filtering of the 20-peak records (side stream, ~100 ms of
+        latency whatever the batch size) then overlaps the NEXT batches' kernels instead of idling the device."""
         torch = self.torch
         flat = batch.flat
         beg_h, end_h, d_beg, d_end = self._ranges(batch, trim)
@@ -465,25 +492,44 @@ class Preprocessor:
             else np.zeros((0, 2))
         info = self._upload(info_h)
         tmp = getattr(self, "_filter_tmp", None)
-        scr = self.screen_windows(y, win_start, zwin_scratch=tmp)
-        n_hazard = n_flipped = 0
+        # the z-scored windows are parked (filter scratch) only for the delineation kernel; the median kernel alone
+        # re-derives its samples from y and the per-window mean / sd.  np.std is evaluated where it decides the mask.
+        scr = self.screen_windows(y, win_start, zwin_scratch=tmp if (features or self.park_windows) else None,
+                                  lazy_sd=self.lazy_sd)
+        hz = None
         if self.exact_masks:
-            n_hazard, n_flipped = self.resolve_hazards(flat, beg_h, end_h, mean, sd, cnt, win_start, win_rec, scr,
-                                                       zwin_main=tmp if features else None)
+            hz = self.resolve_hazards(flat, beg_h, end_h, mean, sd, cnt, win_start, win_rec, scr,
+                                      zwin_main=tmp if features else None)
+        pend = dict(scr=scr, hz=hz, info=info, header=header, features=features, tmp=tmp, y=y, n_win=len(win_start),
+                    mean=mean, sd=sd, keep_intermediates=keep_intermediates, beg_h=beg_h, end_h=end_h,
+                    win_start=win_start, flat=flat, cnt=cnt)
+        if defer and not features:                             # (the delineation reads the shared filter scratch)
+            return pend
+        return self.finish(pend)
+
+    @_cabi.on_device
+    def finish(self, pend) -> dict:
+        """Second half of ``run``: waits (on the stream, not the host) for the batch's exact-mask pass, compacts the
+        kept windows and reads the counters back."""
+        torch = self.torch
+        scr, hz, info, header, features, tmp = (pend[k] for k in ("scr", "hz", "info", "header", "features", "tmp"))
+        n_win, y = pend["n_win"], pend["y"]
+        if hz is not None:
+            torch.cuda.current_stream(self.device).wait_event(hz["event"])
         keep_mask = scr["keep"]
         feats = None
-        if features and len(win_start) and not (self.hp and self.lp):
+        if features and n_win and not (self.hp and self.lp):
             # data_extract_vitaldb.py:118,166-170: without both filters no delineation, NaN features, every screened
             # window kept -- and data_create_arrays.py:37-40 then writes zeros for such a case (a NaN cell where a
             # {'x', 'y'} dict is expected raises its TypeError branch)
-            feats = torch.zeros((len(win_start), 35), dtype=torch.float64, device=self.device)
-            fl = torch.ones(len(win_start), dtype=torch.uint8, device=self.device)
+            feats = torch.zeros((n_win, 35), dtype=torch.float64, device=self.device)
+            fl = torch.ones(n_win, dtype=torch.uint8, device=self.device)
             fid, fstat = None, torch.zeros(1, dtype=torch.int32, device=self.device)
-        elif features and len(win_start):
+        elif features and n_win:
             # the screen kernel parked the z-scored windows ('ecg_sample') back to back in the filter scratch
-            if tmp is None or tmp.numel() < len(win_start) * self.L or tmp.data_ptr() == y.data_ptr():
+            if tmp is None or tmp.numel() < n_win * self.L or tmp.data_ptr() == y.data_ptr():
                 raise _cabi.AewError("features=True needs the filter scratch buffer for the z-scored windows")
-            feats, fl, fid, fstat = self.window_features(tmp, len(win_start), scr)
+            feats, fl, fid, fstat = self.window_features(tmp, n_win, scr)
             keep_mask = scr["keep"] & (fl != 2).to(torch.uint8)      # list-length rule, data_extract_vitaldb.py:140-144
             # a kept window whose delineation RAISED (flag 1) has np.nan cells where data_create_arrays.py:34-35
             # expects {'x', 'y'} dicts: its TypeError branch (:37-40) zeroes all 35 features of EVERY row of that case
@@ -497,13 +543,14 @@ class Preprocessor:
         # the device idle, which the end-to-end feeder pays once per chunk)
         i64 = torch.int64
         words = [header[0:1], header[1:2], header[4:5], scr["status"].to(i64), scr["hazards"].to(i64),
-                 scr["n_peaks"].index_select(0, keep_idx).sum(dtype=i64).reshape(1)]
+                 scr["n_peaks"].index_select(0, keep_idx).sum(dtype=i64).reshape(1),
+                 (hz["changed"] if hz is not None else torch.zeros((), dtype=i64, device=self.device)).reshape(1).to(i64)]
         if feats is not None:
             words.append(fstat.to(i64))
         res = dict(np_waves=scr["waves"].index_select(0, keep_idx), medians=scr["median"].index_select(0, keep_idx),
                    np_info=info.index_select(0, keep_idx), keep=scr["keep"], has_nan=scr["has_nan"],
                    n_peaks=scr["n_peaks"], peaks=scr["peaks"], stats=scr["stats"], keep_idx=keep_idx,
-                   n_windows=len(win_start), mean=mean, sd=sd)
+                   n_windows=n_win, mean=pend["mean"], sd=pend["sd"])
         if feats is not None:
             res.update(np_features=feats.index_select(0, keep_idx), delineation_flags=fl, fiducials=fid)
         elif features:
@@ -512,11 +559,11 @@ class Preprocessor:
         _cabi.check_device_status(int(w[2]), "filter")
         _cabi.check_device_status(int(w[3]), "window screen")
         if feats is not None:
-            _cabi.check_device_status(int(w[6]), "fiducial features")
+            _cabi.check_device_status(int(w[7]), "fiducial features")
         res.update(n_segments=int(w[0]), n_tiles=int(w[1]), hazard_windows=int(w[4]), n_beats=int(w[5]),
-                   mask_hazard_windows=n_hazard, mask_flips_resolved=n_flipped)
-        if keep_intermediates:
-            res.update(filtered=y, rec_beg=beg_h, rec_end=end_h, win_start=win_start)
+                   mask_hazard_windows=0 if hz is None else hz["n"], mask_flips_resolved=int(w[6]))
+        if pend["keep_intermediates"]:
+            res.update(filtered=y, rec_beg=pend["beg_h"], rec_end=pend["end_h"], win_start=pend["win_start"])
         return res
 
 
@@ -624,7 +671,37 @@ def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chu
                 bufs[k % 2][p0 - lo:p1 - lo].copy_(host_flat[p0:p1], non_blocking=True)
             copied[k].record(copy_stream)
 
-    waves, infos, feats, hazards, n_windows, n_beats, rows = [], [], [], 0, 0, 0, 0
+    waves, infos, feats = [], [], []
+    tot = dict(hazards=0, n_windows=0, n_beats=0, rows=0, mask_hazard=0, mask_flips=0)
+    # exact_masks: the sequential re-filtering of a chunk's 20-peak records takes ~100 ms on a side stream whatever
+    # the chunk size; chunks are therefore finished `depth` chunks late, so that it overlaps the following chunks
+    depth = pre.defer_chunks if (pre.exact_masks and not features) else 0
+    pending = []
+
+    def finish_one(item):
+        res = pre.finish(item) if depth else item
+        waves.append(res["np_waves"])
+        infos.append(res["np_info"])
+        if features:
+            feats.append(res["np_features"])
+        if to_host:
+            n = res["np_waves"].shape[0]
+            rows = tot["rows"]
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(back_stream):
+                back_stream.wait_event(done)
+                h_waves[rows:rows + n].copy_(res["np_waves"], non_blocking=True)
+                h_info[rows:rows + n].copy_(res["np_info"], non_blocking=True)
+                if features:
+                    h_feat[rows:rows + n].copy_(res["np_features"], non_blocking=True)
+            tot["rows"] += n
+        tot["hazards"] += res["hazard_windows"]
+        tot["n_windows"] += res["n_windows"]
+        tot["n_beats"] += res["n_beats"]
+        tot["mask_hazard"] += res["mask_hazard_windows"]
+        tot["mask_flips"] += res["mask_flips_resolved"]
+
     if chunks:
         start_copy(0)
     for k, (c0, c1) in enumerate(chunks):
@@ -640,27 +717,14 @@ def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chu
             chunk_in = bufs[k % 2][:sizes[k]]
         sub = RecordBatch(chunk_in, rec_off[c0:c1 + 1] - rec_off[c0], case_ids[c0:c1])
         sc = {"y": scratch["y"][:sizes[k]], "tmp": scratch["tmp"][:sizes[k]]}
-        res = pre.run(sub, scratch=sc, features=features)
+        pending.append(pre.run(sub, scratch=sc, features=features, defer=depth > 0))
         if not narrow:
-            freed[k].record(main)
-        waves.append(res["np_waves"])
-        infos.append(res["np_info"])
-        if features:
-            feats.append(res["np_features"])
-        if to_host:
-            n = res["np_waves"].shape[0]
-            done = torch.cuda.Event()
-            done.record(main)
-            with torch.cuda.stream(back_stream):
-                back_stream.wait_event(done)
-                h_waves[rows:rows + n].copy_(res["np_waves"], non_blocking=True)
-                h_info[rows:rows + n].copy_(res["np_info"], non_blocking=True)
-                if features:
-                    h_feat[rows:rows + n].copy_(res["np_features"], non_blocking=True)
-            rows += n
-        hazards += res["hazard_windows"]
-        n_windows += res["n_windows"]
-        n_beats += res["n_beats"]
+            freed[k].record(main)                              # (the hazard records have been copied out by now)
+        while len(pending) > depth:
+            finish_one(pending.pop(0))
+    while pending:
+        finish_one(pending.pop(0))
+    hazards, n_windows, n_beats, rows = tot["hazards"], tot["n_windows"], tot["n_beats"], tot["rows"]
     if to_host:
         back_stream.synchronize()
         np_waves, np_info = h_waves[:rows], h_info[:rows]
@@ -674,7 +738,8 @@ def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chu
         np_waves = torch.cat(waves) if waves else torch.zeros((0, pre.beat_len), dtype=torch.float32,
                                                               device=pre.device)
         np_info = torch.cat(infos) if infos else torch.zeros((0, 2), dtype=torch.float64, device=pre.device)
-    out = dict(np_waves=np_waves, np_info=np_info, hazard_windows=hazards, n_windows=n_windows, n_beats=n_beats)
+    out = dict(np_waves=np_waves, np_info=np_info, hazard_windows=hazards, n_windows=n_windows, n_beats=n_beats,
+               mask_hazard_windows=tot["mask_hazard"], mask_flips_resolved=tot["mask_flips"])
     if features:
         out["np_features"] = np_feat
     return out

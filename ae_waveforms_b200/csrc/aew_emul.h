@@ -164,6 +164,7 @@ inline int __syncthreads_or(int pred) {
   b->bar.wait();
   return r;
 }
+inline int __syncthreads_and(int pred) { return !__syncthreads_or(!pred); }
 inline void aew_named_sync(int id, int count) { aew_emul::block_ctx()->named[id].sync(count); }
 inline void aew_named_arrive(int id, int count) { aew_emul::block_ctx()->named[id].arrive(count); }
 inline void __syncwarp(unsigned = 0xffffffffu) {
@@ -272,6 +273,7 @@ inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
 inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 inline long long __double_as_longlong(double d) { long long r; memcpy(&r, &d, 8); return r; }
+inline int __double2hiint(double d) { long long r; memcpy(&r, &d, 8); return (int)(r >> 32); }
 inline double __longlong_as_double(long long v) { double r; memcpy(&r, &v, 8); return r; }
 template <class T> inline T __ldg(const T* p) { return *p; }
 using std::isnan;

@@ -743,43 +743,57 @@ __device__ __forceinline__ double df2t_step_exact(const double* b, const double*
   return y;
 }
 
-#define K2E_BLK 32
+#define K2E_NT 32                       // one warp per segment
+#define K2E_BLK 64                      // samples per round: two per lane (halves the rounds' fixed cost)
 // one pass over n samples: logical sample i is in[i] (REV: in[n - 1 - i]); lane 0 owns the state z
 template <int ORD, bool REV>
 __device__ __forceinline__ void exact_stream(const double* in, double* out, long long n, const double* b,
                                              const double* a, double* z, bool zon, double mean, const ExactDiv& sd,
-                                             double (*sp)[K2E_BLK], double* sy, int lane) {
-  double v = 0.0;
-  if (lane < n) v = in[REV ? n - 1 - lane : lane];
+                                             double (*sp)[K2E_BLK + 2], double* sy, int lane) {
+  double v0 = 0.0, v1 = 0.0;
+  if (lane < n) v0 = in[REV ? n - 1 - lane : lane];
+  if (lane + 32 < n) v1 = in[REV ? n - 1 - (lane + 32) : lane + 32];
   for (long long i0 = 0; i0 < n; i0 += K2E_BLK) {
-    const long long j = i0 + K2E_BLK + lane;             // the block after this one is in flight while lane 0 works
-    double vn = 0.0;
-    if (j < n) vn = in[REV ? n - 1 - j : j];
-    const double x = zs(v, zon, mean, sd);
+    const long long j0 = i0 + K2E_BLK + lane, j1 = j0 + 32;   // the next round is in flight while lane 0 works
+    double w0 = 0.0, w1 = 0.0;
+    if (j0 < n) w0 = in[REV ? n - 1 - j0 : j0];
+    if (j1 < n) w1 = in[REV ? n - 1 - j1 : j1];
+    const double x0 = zs(v0, zon, mean, sd), x1 = zs(v1, zon, mean, sd);
 #pragma unroll
-    for (int k = 0; k <= ORD; ++k) sp[k][lane] = __dmul_rn(b[k], x);
+    for (int k = 0; k <= ORD; ++k) { sp[k][lane] = __dmul_rn(b[k], x0); sp[k][lane + 32] = __dmul_rn(b[k], x1); }
     __syncwarp();
     if (lane == 0) {
       const int cnt = (int)(n - i0 < K2E_BLK ? n - i0 : K2E_BLK);
+      // the products of the next two samples are fetched BEFORE this sample's dependent chain (DADD, DMUL, DADD)
+      // is issued: an in-order warp would otherwise expose one shared-memory latency per sample
+      double c[ORD + 1], c1[ORD + 1];
+#pragma unroll
+      for (int k = 0; k <= ORD; ++k) { c[k] = sp[k][0]; c1[k] = sp[k][1]; }
 #pragma unroll 4
       for (int t = 0; t < cnt; ++t) {
-        const double y = __dadd_rn(z[0], sp[0][t]);
+        double c2[ORD + 1];
 #pragma unroll
-        for (int k = 0; k < ORD - 1; ++k) z[k] = __dsub_rn(__dadd_rn(z[k + 1], sp[k + 1][t]), __dmul_rn(y, a[k + 1]));
-        z[ORD - 1] = __dsub_rn(sp[ORD][t], __dmul_rn(y, a[ORD]));
+        for (int k = 0; k <= ORD; ++k) c2[k] = sp[k][t + 2];          // (the two pad columns keep this in bounds)
+        const double y = __dadd_rn(z[0], c[0]);
+#pragma unroll
+        for (int k = 0; k < ORD - 1; ++k) z[k] = __dsub_rn(__dadd_rn(z[k + 1], c[k + 1]), __dmul_rn(y, a[k + 1]));
+        z[ORD - 1] = __dsub_rn(c[ORD], __dmul_rn(y, a[ORD]));
         sy[t] = y;
+#pragma unroll
+        for (int k = 0; k <= ORD; ++k) { c[k] = c1[k]; c1[k] = c2[k]; }
       }
     }
     __syncwarp();
     if (i0 + lane < n) out[REV ? n - 1 - (i0 + lane) : i0 + lane] = sy[lane];
+    if (i0 + lane + 32 < n) out[REV ? n - 1 - (i0 + lane + 32) : i0 + lane + 32] = sy[lane + 32];
     __syncwarp();
-    v = vn;
+    v0 = w0; v1 = w1;
   }
 }
 
 template <int ORD>
-__global__ void __launch_bounds__(K2E_BLK) k2_exact(PassArgs a) {
-  __shared__ double sp[ORD + 1][K2E_BLK];
+__global__ void __launch_bounds__(K2E_NT) k2_exact(PassArgs a) {
+  __shared__ double sp[ORD + 1][K2E_BLK + 2];
   __shared__ double sy[K2E_BLK];
   const long long n_seg = a.ws.hdr[H_SEG_COUNT] < a.ws.max_seg ? a.ws.hdr[H_SEG_COUNT] : a.ws.max_seg;
   const long long seg = blockIdx.x;
@@ -798,7 +812,7 @@ __global__ void __launch_bounds__(K2E_BLK) k2_exact(PassArgs a) {
   double* out = a.passthrough + g0;
   double* tmp = a.dst + g0;
   if (n <= pad) {                                        // filters.py:50-51: too short to filter, copied through
-    for (long long i = lane; i < n; i += K2E_BLK) out[i] = zs(xs[i], zon, mean, sd);
+    for (long long i = lane; i < n; i += K2E_NT) out[i] = zs(xs[i], zon, mean, sd);
     return;
   }
   double ve[K2_MAXPAD];
@@ -892,10 +906,10 @@ extern "C" int aew_filtfilt_f64(const double* src, const double* mean, const dou
   if (mode == 1) {                                       // one warp per segment (blocks beyond the count exit)
     const long long blocks = max_seg;
     switch ((int)h_tab[K2_TAB_ORDER]) {
-      case 1: AEW_LAUNCH(k2_exact<1>, (unsigned)blocks, K2E_BLK, 0, st, a); break;
-      case 2: AEW_LAUNCH(k2_exact<2>, (unsigned)blocks, K2E_BLK, 0, st, a); break;
-      case 3: AEW_LAUNCH(k2_exact<3>, (unsigned)blocks, K2E_BLK, 0, st, a); break;
-      case 4: AEW_LAUNCH(k2_exact<4>, (unsigned)blocks, K2E_BLK, 0, st, a); break;
+      case 1: AEW_LAUNCH(k2_exact<1>, (unsigned)blocks, K2E_NT, 0, st, a); break;
+      case 2: AEW_LAUNCH(k2_exact<2>, (unsigned)blocks, K2E_NT, 0, st, a); break;
+      case 3: AEW_LAUNCH(k2_exact<3>, (unsigned)blocks, K2E_NT, 0, st, a); break;
+      case 4: AEW_LAUNCH(k2_exact<4>, (unsigned)blocks, K2E_NT, 0, st, a); break;
       default: return AEW_ERR_UNSUPPORTED;
     }
     return (int)cudaGetLastError();

@@ -39,10 +39,12 @@
 #include "aew_math.cuh"
 #include "../../include/aewave.h"
 
-#define K3_NT 256                         // two blocks per SM: their barrier waits and load latencies overlap
-#define K3_ITEMS 13                       // extended positions per thread and segment (odd: conflict-free strips)
+#define K3_NT 512                         // two blocks per SM = 32 warps (64 registers per thread): the kernel is bound by
+                                          // issue latency, not by a pipe (profiles/r1_k3_screen.txt: 16 warps, 45 % issue)
+#define K3_NW (K3_NT / 32)
+#define K3_ITEMS 7                        // extended positions per thread and segment (odd: conflict-free strips)
 #define K3_SEGS 4                         // the QRS indicator is evaluated in segments (prefix sums fit 24 KB)
-#define K3_CAP (K3_NT * K3_ITEMS)         // 3328 extended positions per segment
+#define K3_CAP (K3_NT * K3_ITEMS)         // 3584 extended positions per segment at most
 #define K3_RING 512                       // ring of smoothgrad values in the sequential evaluation (> avg_k + 1)
 #define K3_MAXL 10240                     // samples per window at most (80 KB of shared memory)
 #define K3_MAXP 72                        // peaks are > 150 samples apart -> at most 71 in 10752
@@ -71,14 +73,26 @@ struct K3Smem {
   unsigned char* pw_valid;  // [2][128]
 };
 
-__host__ __device__ inline size_t k3_smem_layout(unsigned char* base, int L, K3Smem* s) {
+// entries of B: one segment of the indicator evaluation (ceil(L / K3_SEGS) outputs + the two box filters' halo),
+// the ring of the sequential evaluation and the run tables, whichever is largest
+__host__ __device__ inline int k3_bcap(int L, int ext) {
+  const int seg = (L + K3_SEGS - 1) / K3_SEGS + ext;
+  const int rmax = L / 2 + 2;
+  const int runs = (2 * ((rmax + 7) & ~7) * 2 + 7) / 8;
+  int c = seg > runs ? seg : runs;
+  c = c > K3_RING ? c : K3_RING;
+  return (c + K3_ITEMS + 1) & ~1;
+}
+
+// Everything of fixed size comes FIRST, at compile-time offsets from the base of the dynamic shared memory (with
+// L-dependent offsets the compiler re-derived these pointers at their uses under the 64-register cap: 7.6 % of all
+// executed instructions in profiles/r2_k3_512_before_diet.txt), then the window, then B right behind it.
+__host__ __device__ inline size_t k3_smem_layout(unsigned char* base, int L, int ext, K3Smem* s) {
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t at = o; o = (o + bytes + 15) & ~(size_t)15; return base ? base + at : (unsigned char*)0; };
   K3Smem t;
-  t.A = (double*)take(sizeof(double) * L);
-  t.B = (double*)take(sizeof(double) * K3_CAP);
   t.pw_vals = (double*)take(sizeof(double) * 256);
-  t.wtot = (double*)take(sizeof(double) * 16);
+  t.wtot = (double*)take(sizeof(double) * 2 * K3_NW);
   t.scal = (double*)take(sizeof(double) * 16);
   t.dsq = (double*)take(sizeof(double) * K3_MAXP);
   t.ipeaks = (int*)take(sizeof(int) * K3_MAXP);
@@ -87,9 +101,11 @@ __host__ __device__ inline size_t k3_smem_layout(unsigned char* base, int L, K3S
   t.iscal = (int*)take(sizeof(int) * 16);
   t.leaf_off = (int*)take(sizeof(int) * 128);
   t.leaf_size = (int*)take(sizeof(int) * 128);
-  t.Qw = (unsigned*)take(sizeof(unsigned) * (L / 32 + 2));
   t.pw_valid = (unsigned char*)take(256);
-  const int rmax = L / 2 + 2;                            // 2 * rmax * 2 B <= K3_CAP * 8 B for L <= K3_MAXL
+  t.Qw = (unsigned*)take(sizeof(unsigned) * (K3_MAXL / 32 + 2));
+  t.A = (double*)take(sizeof(double) * L);
+  t.B = (double*)take(sizeof(double) * k3_bcap(L, ext));
+  const int rmax = L / 2 + 2;                            // (k3_bcap covers both tables)
   t.beg = base ? (unsigned short*)t.B : (unsigned short*)0;
   t.end = base ? (unsigned short*)t.B + ((rmax + 7) & ~7) : (unsigned short*)0;
   if (s) *s = t;
@@ -142,51 +158,25 @@ __device__ __forceinline__ double leaf_term(int mode, double v, double m, const 
   flag |= (isnan(z) || isinf(z)) ? 1 : 0;
   return z;
 }
-__device__ __noinline__ LeafOut leaf_pass(int mode, double* A, double m, double sd, int off, int size, int j) {
+// The general form: every element tested (NaN / non-finite result), IEEE division through div_exact.  `S` is where
+// the untransformed samples are read from: the window in shared memory, or -- when the fast form below has already
+// overwritten part of it -- the same samples in global memory.
+__device__ __noinline__ LeafOut leaf_pass_checked(int mode, double* A, const double* S, double m, double sd, int off,
+                                                  int size, int j) {
   const ExactDiv dv = make_exact_div(mode == K3_PASS_ZSCORE ? sd : 1.0);
   const int c8 = size >> 3;
   int flag = 0;
-  // lane j carries the stride-8 partial sums r_{2j} and r_{2j+1}: one 16-byte access per round (the leaf offsets
-  // are multiples of 8 samples), and ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) is a local addition and two xor steps.
-  // One loop per mode: the mode test inside the loop cost more instructions than the arithmetic.
   double r0 = 0.0, r1 = 0.0;
   double* Aj = A + off + 2 * j;
-  if (c8 > 0) {
-    const double2 v = *reinterpret_cast<const double2*>(Aj);
-    double2 t;
-    t.x = leaf_term(mode, v.x, m, dv, flag);
-    t.y = leaf_term(mode, v.y, m, dv, flag);
-    if (mode == K3_PASS_ZSCORE) *reinterpret_cast<double2*>(Aj) = t;
-    r0 = t.x; r1 = t.y;
-  }
-  if (mode == K3_PASS_PLAIN) {
-#pragma unroll 2
-    for (int k = 1; k < c8; ++k) {
-      const double2 v = *reinterpret_cast<const double2*>(Aj + 8 * k);
-      flag |= (isnan(v.x) || isnan(v.y)) ? 1 : 0;
-      r0 = __dadd_rn(r0, v.x);
-      r1 = __dadd_rn(r1, v.y);
-    }
-  } else if (mode == K3_PASS_DEV2) {
-#pragma unroll 2
-    for (int k = 1; k < c8; ++k) {
-      const double2 v = *reinterpret_cast<const double2*>(Aj + 8 * k);
-      const double dx = __dsub_rn(v.x, m), dy = __dsub_rn(v.y, m);
-      r0 = __dadd_rn(r0, __dmul_rn(dx, dx));
-      r1 = __dadd_rn(r1, __dmul_rn(dy, dy));
-    }
-  } else {
+  const double* Sj = S + off + 2 * j;
 #pragma unroll 1
-    for (int k = 1; k < c8; ++k) {
-      const double2 v = *reinterpret_cast<const double2*>(Aj + 8 * k);
-      double2 t;
-      t.x = div_exact(__dsub_rn(v.x, m), dv);
-      t.y = div_exact(__dsub_rn(v.y, m), dv);
-      flag |= (isnan(t.x) || isinf(t.x) || isnan(t.y) || isinf(t.y)) ? 1 : 0;
-      *reinterpret_cast<double2*>(Aj + 8 * k) = t;
-      r0 = __dadd_rn(r0, t.x);
-      r1 = __dadd_rn(r1, t.y);
-    }
+  for (int k = 0; k < c8; ++k) {
+    double2 t;
+    t.x = leaf_term(mode, Sj[8 * k], m, dv, flag);
+    t.y = leaf_term(mode, Sj[8 * k + 1], m, dv, flag);
+    if (mode == K3_PASS_ZSCORE) *reinterpret_cast<double2*>(Aj + 8 * k) = t;
+    r0 = k == 0 ? t.x : __dadd_rn(r0, t.x);
+    r1 = k == 0 ? t.y : __dadd_rn(r1, t.y);
   }
   double r = __dadd_rn(r0, r1);
   r = __dadd_rn(r, __shfl_xor_sync(AEW_FULL, r, 1));
@@ -199,7 +189,7 @@ __device__ __noinline__ LeafOut leaf_pass(int mode, double* A, double m, double 
 #pragma unroll 1
   for (int u = 0; u < left; ++u) {
     const bool in = i + u < size;
-    const double v = in ? A[off + i + u] : 0.0;
+    const double v = in ? S[off + i + u] : 0.0;
     __syncwarp();
     if (in) {
       const double t = leaf_term(mode, v, m, dv, flag);
@@ -212,19 +202,99 @@ __device__ __noinline__ LeafOut leaf_pass(int mode, double* A, double m, double 
   return o;
 }
 
-// Combine the leaf values up the tree.  With 256 threads a sweep takes two rounds: thread t serves leaf t >> 2
-// and leaf 64 + (t >> 2).  depth 7: every warp folds the 128 leaves in registers (two local levels, five xor
-// steps) -- an invalid (empty) right node leaves its sibling untouched, exactly like pw_warp_combine -- so one
-// barrier per sum is enough.  Two leaf buffers alternate (the caller flips `buf`): a slow warp may still be
-// folding the previous sum while the next one's leaves are stored.
-__device__ __noinline__ double block_combine(double ra, int size_a, double rb, int size_b, int slot, int j, int depth,
-                                             double* vals, unsigned char* valid) {
-  const int nslots = 1 << depth;
-  if (j == 0) {
-    if (slot < nslots) { vals[slot] = ra; valid[slot] = size_a > 0; }
-    if (slot + 64 < nslots) { vals[slot + 64] = rb; valid[slot + 64] = size_b > 0; }
+// |q| outside [2^-300, 2^300]: zero, denormal-ish, huge, infinite or NaN (one shift, one add, one compare)
+__device__ __forceinline__ unsigned odd_exponent(double q) {
+  const unsigned e = ((unsigned)__double2hiint(q) >> 20) & 0x7ffu;
+  return (e - 723u) > 600u ? 1u : 0u;
+}
+
+// The sweep proper.  Lane j carries the stride-8 partial sums r_{2j} and r_{2j+1}: one 16-byte access per round
+// (the leaf offsets are multiples of 8 samples), and ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) is a local addition and
+// two xor steps.  The common case runs WITHOUT per-element tests or branches (they were more instructions than the
+// arithmetic: profiles/r2_k3_512_before_diet.txt): a NaN poisons the plain sum, and the Markstein division is
+// applied to every element while an integer test on the first quotient's exponent collects the ones it must not be
+// trusted with (zero, tiny, huge, non-finite).  Only a warp that saw such a thing repeats its leaves in the checked
+// form above -- same operations on the same operands in the same order, so the bits do not depend on the path.
+__device__ __noinline__ LeafOut leaf_pass(int mode, double* A, const double* raw, double m, double sd, int off,
+                                          int size, int j) {
+  const int c8 = size >> 3;
+  double r0 = 0.0, r1 = 0.0;
+  double* Aj = A + off + 2 * j;
+  unsigned odd = 0;
+  if (mode == K3_PASS_PLAIN) {
+    if (c8 > 0) { const double2 v = *reinterpret_cast<const double2*>(Aj); r0 = v.x; r1 = v.y; }
+#pragma unroll 3
+    for (int k = 1; k < c8; ++k) {
+      const double2 v = *reinterpret_cast<const double2*>(Aj + 8 * k);
+      r0 = __dadd_rn(r0, v.x);
+      r1 = __dadd_rn(r1, v.y);
+    }
+  } else if (mode == K3_PASS_DEV2) {
+    if (c8 > 0) {
+      const double2 v = *reinterpret_cast<const double2*>(Aj);
+      const double dx = __dsub_rn(v.x, m), dy = __dsub_rn(v.y, m);
+      r0 = __dmul_rn(dx, dx); r1 = __dmul_rn(dy, dy);
+    }
+#pragma unroll 3
+    for (int k = 1; k < c8; ++k) {
+      const double2 v = *reinterpret_cast<const double2*>(Aj + 8 * k);
+      const double dx = __dsub_rn(v.x, m), dy = __dsub_rn(v.y, m);
+      r0 = __dadd_rn(r0, __dmul_rn(dx, dx));
+      r1 = __dadd_rn(r1, __dmul_rn(dy, dy));
+    }
+  } else {
+    const ExactDiv dv = make_exact_div(sd);
+    odd = dv.fast ? 0u : 1u;
+    if (dv.fast) {
+#pragma unroll 2
+      for (int k = 0; k < c8; ++k) {
+        const double2 v = *reinterpret_cast<const double2*>(Aj + 8 * k);
+        const double ax = __dsub_rn(v.x, m), ay = __dsub_rn(v.y, m);
+        const double px = __dmul_rn(ax, dv.r), py = __dmul_rn(ay, dv.r);
+        odd |= odd_exponent(px) | odd_exponent(py);
+        const double qx = __fma_rn(__fma_rn(-px, dv.b, ax), dv.r, px), qy = __fma_rn(__fma_rn(-py, dv.b, ay), dv.r, py);
+        double2 t;
+        t.x = __fma_rn(__fma_rn(-qx, dv.b, ax), dv.r, qx);
+        t.y = __fma_rn(__fma_rn(-qy, dv.b, ay), dv.r, qy);
+        *reinterpret_cast<double2*>(Aj + 8 * k) = t;
+        r0 = k == 0 ? t.x : __dadd_rn(r0, t.x);
+        r1 = k == 0 ? t.y : __dadd_rn(r1, t.y);
+      }
+    }
   }
+  double r = __dadd_rn(r0, r1);
+  r = __dadd_rn(r, __shfl_xor_sync(AEW_FULL, r, 1));
+  r = __dadd_rn(r, __shfl_xor_sync(AEW_FULL, r, 2));
+  if (mode != K3_PASS_ZSCORE) odd = (size >= 8 && odd_exponent(r)) ? 1u : 0u;   // NaN / overflow shows in the sum
+  if ((size & 7) != 0 || size < 8) odd = 1u;             // leaves with a tail (not at L = 10,000) take the general form
+  if (__any_sync(AEW_FULL, odd != 0)) {
+    // (a zero sum or quotient is "odd" too: harmless, the checked form gives the same bits)
+    return leaf_pass_checked(mode, A, (mode == K3_PASS_ZSCORE && raw) ? raw : A, m, sd, off, size, j);
+  }
+  LeafOut o;
+  o.r = r; o.flag = 0;
+  return o;
+}
+
+// Combine the leaf values up the tree: thread t has served leaf t >> 2 (512 threads = 128 leaves x 4 lanes).
+// depth 7: every warp folds the 128 leaves in registers (two local levels, five xor steps) -- an invalid (empty)
+// right node leaves its sibling untouched, exactly like pw_warp_combine -- so one barrier per sum is enough.  Two
+// leaf buffers alternate (the caller flips `buf`): a slow warp may still be folding the previous sum while the next
+// one's leaves are stored.
+__device__ __noinline__ double block_combine(double ra, int size_a, int slot, int j, int depth,
+                                             double* vals, unsigned char* valid, bool all_leaves) {
+  const int nslots = 1 << depth;
+  if (j == 0 && slot < nslots) { vals[slot] = ra; valid[slot] = size_a > 0; }
   __syncthreads();
+  if (depth == 7 && all_leaves) {                         // every one of the 128 leaves exists: plain pairwise adds
+    const int lane = threadIdx.x & 31;
+    const double2 a01 = *reinterpret_cast<const double2*>(vals + 4 * lane);
+    const double2 a23 = *reinterpret_cast<const double2*>(vals + 4 * lane + 2);
+    double m = __dadd_rn(__dadd_rn(a01.x, a01.y), __dadd_rn(a23.x, a23.y));
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) m = __dadd_rn(m, __shfl_xor_sync(AEW_FULL, m, o));   // (IEEE + commutes)
+    return m;
+  }
   if (depth == 7) {
     const int lane = threadIdx.x & 31;
     const double a0 = vals[4 * lane], a1 = vals[4 * lane + 1], a2 = vals[4 * lane + 2], a3 = vals[4 * lane + 3];
@@ -264,9 +334,14 @@ __device__ __noinline__ double block_excl_scan(double v, double* wtot) {
   }
   if (lane == 31) wtot[warp] = incl;
   __syncthreads();
-  double base = 0.0;
-  for (int w = 0; w < warp; ++w) base += wtot[w];
-  return base + (incl - v);
+  double t = lane < K3_NW ? wtot[lane] : 0.0;            // every warp scans the K3_NW warp totals for itself
+#pragma unroll
+  for (int d = 1; d < K3_NW; d <<= 1) {
+    const double o = __shfl_up_sync(AEW_FULL, t, d);
+    if (lane >= d) t += o;
+  }
+  const double before = __shfl_sync(AEW_FULL, t, warp > 0 ? warp - 1 : 0);
+  return (warp > 0 ? before : 0.0) + (incl - v);
 }
 __device__ __noinline__ int block_excl_scan_int(int v, int* wtot) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -278,9 +353,14 @@ __device__ __noinline__ int block_excl_scan_int(int v, int* wtot) {
   }
   if (lane == 31) wtot[warp] = incl;
   __syncthreads();
-  int base = 0;
-  for (int w = 0; w < warp; ++w) base += wtot[w];
-  return base + (incl - v);
+  int t = lane < K3_NW ? wtot[lane] : 0;
+#pragma unroll
+  for (int d = 1; d < K3_NW; d <<= 1) {
+    const int o = __shfl_up_sync(AEW_FULL, t, d);
+    if (lane >= d) t += o;
+  }
+  const int before = __shfl_sync(AEW_FULL, t, warp > 0 ? warp - 1 : 0);
+  return (warp > 0 ? before : 0) + (incl - v);
 }
 
 // order-preserving 64-bit key of a (non-NaN) double: unsigned comparison of keys == comparison of the values
@@ -622,7 +702,7 @@ __device__ __forceinline__ double absgrad_ext(const double* __restrict__ A, int 
 __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, unsigned long long* dbg) {
   AEW_DYN_SMEM(smem_raw);
   K3Smem sm;
-  k3_smem_layout(smem_raw, p.L, &sm);
+  k3_smem_layout(smem_raw, p.L, p.avg_k + p.smooth_k, &sm);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int L = p.L;
   const long long w = blockIdx.x;
@@ -682,18 +762,17 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, unsigned long
   }
 #endif
   __syncthreads();                                      // window, leaf table
-  // two leaves per thread: slot and slot + 64
+  // one leaf per group of four threads
   const int slot = tid >> 2, lj = tid & 3;
   const int nslots = 1 << depth;
   const int offa = slot < nslots ? sm.leaf_off[slot] : 0, sza = slot < nslots ? sm.leaf_size[slot] : 0;
-  const int offb = slot + 64 < nslots ? sm.leaf_off[slot + 64] : 0, szb = slot + 64 < nslots ? sm.leaf_size[slot + 64] : 0;
+  const bool all_leaves = nslots == K3_NT / 4 && __syncthreads_and(sza > 0);
   int buf = 0;
 #define K3_SWEEP(MODE, M, SD, SUM, FLAG)                                                                   \
   {                                                                                                        \
-    const LeafOut la_ = leaf_pass(MODE, A, M, SD, offa, sza, lj);                                          \
-    const LeafOut lb_ = leaf_pass(MODE, A, M, SD, offb, szb, lj);                                          \
-    SUM = block_combine(la_.r, sza, lb_.r, szb, slot, lj, depth, sm.pw_vals + 128 * buf, sm.pw_valid + 128 * buf); \
-    FLAG = la_.flag | lb_.flag;                                                                            \
+    const LeafOut la_ = leaf_pass(MODE, A, src, M, SD, offa, sza, lj);                                     \
+    SUM = block_combine(la_.r, sza, slot, lj, depth, sm.pw_vals + 128 * buf, sm.pw_valid + 128 * buf, all_leaves); \
+    FLAG = la_.flag;                                                                                       \
     buf ^= 1;                                                                                              \
   }
 
@@ -729,12 +808,9 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, unsigned long
     return;
   }
 
-  // ---- ecg_sd = np.std(window) (remove_samples.py:62)
-  double ssq2;
-  K3_SWEEP(K3_PASS_DEV2, k3_div(sum_z, (double)L), 1.0, ssq2, flag)
-  const double sd = k3_sqrt(k3_div(ssq2, (double)L));
-#undef K3_SWEEP
-  K3_TICK(2)   // np.std
+  // (ecg_sd = np.std(window), remove_samples.py:62, is formed at the END of the kernel: of a z-scored window it is
+  //  1 up to a few ulp, so it decides sd / n_peaks > threshold only when n_peaks * threshold == 1 -- SURVEY.md
+  //  C.1 -- and with p.lazy_sd the sweep is run only for those windows)
 
   // ---- QRS indicator: smoothgrad > 1.5 * avggrad, smoothgrad / avggrad = box filters (scipy "nearest" edges)
   // of |gradient| / smoothgrad.  Evaluated with prefix sums, one SEGMENT of the window at a time: for output
@@ -777,8 +853,10 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, unsigned long
         }
       }
       double base = block_excl_scan(run, sm.wtot);      // (its barrier also ends the previous segment's reads of B)
+      if (e0 < Le) {
 #pragma unroll
-      for (int k = 0; k < K3_ITEMS; ++k) B[e0 + k] = base + loc[k];
+        for (int k = 0; k < K3_ITEMS; ++k) B[e0 + k] = base + loc[k];
+      }
       __syncthreads();
       const double ptot = B[Le - 1];
       // smoothgrad at position e = box sum over positions [e' + 1, e' + ks], e' = clamp(sample) - ls - 1 - G0;
@@ -808,9 +886,11 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, unsigned long
           loc[k] = run;
         }
       }
-      base = block_excl_scan(run, sm.wtot + 8);         // (its barrier also ends all reads of B)
+      base = block_excl_scan(run, sm.wtot + K3_NW);     // (its barrier also ends all reads of B)
+      if (e0 < Le) {
 #pragma unroll
-      for (int k = 0; k < K3_ITEMS; ++k) B[e0 + k] = base + loc[k];
+        for (int k = 0; k < K3_ITEMS; ++k) B[e0 + k] = base + loc[k];
+      }
       __syncthreads();
       // outputs: samples a <= i < b, i.e. positions e = i - G0; avggrad box = P2[e - la - 1 + ka] - P2[e - la - 1]
       const double tol_abs = 2e-12 * ptot * inv_s;
@@ -1000,17 +1080,12 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, unsigned long
         hr = k3_div(p.hr_num, med);
       }
       if (np >= 3) rms = k3_sqrt(k3_div(ssq, (double)(np - 2)));
-      const double sdn = k3_div(sd, (double)np);
-      const bool remove = (hr < p.hr_lo) || (hr > p.hr_hi) || isnan(hr) || (rms > p.pvc_threshold) ||
-                          (sdn > p.sd_threshold);
       sm.iscal[2] = np;
-      p.keep[w] = remove ? 0 : 1;
-      p.has_nan[w] = 0;
-      p.n_peaks[w] = np;
-      p.stats[4 * w + 0] = hr; p.stats[4 * w + 1] = rms; p.stats[4 * w + 2] = sd; p.stats[4 * w + 3] = sdn;
+      sm.scal[0] = hr;
+      sm.scal[1] = rms;
     }
   } else if (p.zwin) {
-    // meanwhile the other warps park the z-scored window for the median kernel / the 'ecg_sample' column
+    // meanwhile the other warps park the z-scored window for the delineation kernel / the 'ecg_sample' column
     double* zw = p.zwin + w * (long long)L;
 #pragma unroll 4
     for (int i = tid - 32; i < L; i += K3_NT - 32) zw[i] = A[i];
@@ -1018,7 +1093,33 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, unsigned long
   __syncthreads();
   const int np = sm.iscal[2];
   for (int i = tid; i < K3_MAXP; i += K3_NT) p.peaks[w * K3_MAXP + i] = i < np ? sm.ipeaks[i] : -1;
-  K3_TICK(11)  // refractory chain, HR / RMSSD / keep decision, peaks out
+  K3_TICK(11)  // refractory chain, HR / RMSSD, peaks out
+
+  // ---- ecg_sd = np.std(window) (remove_samples.py:62) and the keep decision (:70-74).  The window is z-scored
+  // (here, or by the caller), so sd = 1 up to a few ulp and sd / n_peaks > threshold is decided by n_peaks alone
+  // unless n_peaks * threshold == 1 (20 beats at 0.05: SURVEY.md C.1).  lazy_sd: the fourth NumPy-order sweep
+  // over the window runs only for those windows; the others report sd = NaN and take the decision that every
+  // sd within 1e-6 of 1 gives.  (A window the CALLER z-scored is trusted to be z-scored only with lazy_sd set.)
+  const double npt = __dmul_rn((double)np, p.sd_threshold);
+  const bool need_sd = !p.lazy_sd || np == 0 || fabs(npt - 1.0) < 1e-6;
+  double sd = qnan;
+  if (need_sd) {
+    double ssq2;
+    K3_SWEEP(K3_PASS_DEV2, k3_div(sum_z, (double)L), 1.0, ssq2, flag)
+    sd = k3_sqrt(k3_div(ssq2, (double)L));
+  }
+#undef K3_SWEEP
+  if (tid == 0) {
+    const double hr = sm.scal[0], rms = sm.scal[1];
+    const double sdn = need_sd ? k3_div(sd, (double)np) : qnan;
+    const bool sd_rule = need_sd ? (sdn > p.sd_threshold) : (npt < 1.0);      // 1 / np > threshold
+    const bool remove = (hr < p.hr_lo) || (hr > p.hr_hi) || isnan(hr) || (rms > p.pvc_threshold) || sd_rule;
+    p.keep[w] = remove ? 0 : 1;
+    p.has_nan[w] = 0;
+    p.n_peaks[w] = np;
+    p.stats[4 * w + 0] = hr; p.stats[4 * w + 1] = rms; p.stats[4 * w + 2] = sd; p.stats[4 * w + 3] = sdn;
+  }
+  K3_TICK(2)   // np.std (when needed) + keep decision
 }
 
 // ---- K3b: median beat of kept windows (median_sample.py:6-54) -> np_waves row.
@@ -1136,7 +1237,7 @@ extern "C" int aew_windows_beats_f64(const K3Params* hp, void* stream) {
   if (pw_depth(p.L) > 7 || p.pre < 0 || p.post < 1 || p.pre + p.post > K3_MAXS || p.smooth_k < 1 || p.avg_k < 1 || p.smooth_k > p.L ||
       p.avg_k > p.L || p.refractory < 1 || (p.L / (p.refractory + 1) + 1) > K3_MAXP || p.n_win > 0x3fffffffll)
     return AEW_ERR_UNSUPPORTED;
-  const size_t smem = k3_smem_layout(nullptr, p.L, nullptr);
+  const size_t smem = k3_smem_layout(nullptr, p.L, p.avg_k + p.smooth_k, nullptr);
   if (smem > 113 * 1024) return AEW_ERR_UNSUPPORTED;    // two blocks per SM
   // (per call: the attribute is per DEVICE, and the call costs a fraction of a microsecond)
   if (AEW_SET_MAX_SMEM(k3_windows, 113 * 1024) != 0) return (int)cudaGetLastError();

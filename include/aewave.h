@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AEW_VERSION 108
+#define AEW_VERSION 109
 
 /* return codes */
 #define AEW_OK 0
@@ -127,6 +127,9 @@ typedef struct K3Params {
                                  when median / waves are requested */
   int* status;                /* device status word */
   unsigned long long* hazard_count; /* device counter of windows that took the exact fallback (may be NULL) */
+  int lazy_sd;                /* 1: np.std of the (z-scored) window is evaluated only where it decides the mask
+                                 (n_peaks * sd_threshold == 1); stats[2], stats[3] are NaN elsewhere.
+                                 0: always (the 'ecg_sd' / 'ecg_sd/hr' columns of remove_samples()) */
 } K3Params;
 int aew_windows_max_peaks(void);
 int aew_windows_max_len(void);

@@ -1,9 +1,10 @@
 """Recipe for ``oracle/_ref`` (TEST INFRASTRUCTURE): the reference's own modules, compiled.
 
 The reference is pure Python, so its "build" is byte-compilation: every module on the hot path (and the two
-caller scripts) is compiled FROM WHERE IT LIES under ``/root/reference`` to a sourceless ``.pyc`` under
-``oracle/_ref/`` -- no reference source is copied into the repo, ``oracle/_ref/`` is git-ignored (so it stays out
-of history) but not gpurun-ignored (so it travels to the GPU box like the repo's own built ``.so``).  There the
+caller scripts) is compiled FROM WHERE IT LIES under ``/root/reference`` to sourceless bytecode, packed into
+``oracle/_ref/reference_modules.zip`` (importable as it is: zipimport) -- no reference source is copied into the
+repo, ``oracle/_ref/`` is git-ignored (so it stays out of history) but not gpurun-ignored (so it travels to the
+GPU box like the repo's own built ``.so``; loose ``*.pyc`` files do not travel, an archive does).  There the
 CPU arm of ``bench.py`` times the reference's OWN functions (``cpu_baseline.kind = "reference"``) and the tests
 cross-check the oracle port and the drop-ins against them.
 
@@ -14,6 +15,8 @@ from __future__ import annotations
 import os
 import py_compile
 import sys
+import tempfile
+import zipfile
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REFERENCE_ROOT = "/root/reference"
@@ -36,25 +39,31 @@ MODULES = [
 ]
 
 
+ARCHIVE = os.path.join(OUT, "reference_modules.zip")
+
+
 def build(verbose: bool = False) -> str | None:
     if not os.path.isdir(os.path.join(REFERENCE_ROOT, "data_load_preprocess")):
-        return OUT if os.path.isdir(OUT) else None
-    for rel in MODULES:
-        src = os.path.join(REFERENCE_ROOT, rel)
-        if not os.path.exists(src):
-            continue
-        dst = os.path.join(OUT, rel[:-3] + ".pyc")
-        os.makedirs(os.path.dirname(dst), exist_ok=True)
-        if os.path.exists(dst) and os.path.getmtime(dst) >= os.path.getmtime(src):
-            continue
-        # dfile: the path tracebacks show; UNCHECKED_HASH: the .pyc is valid without its source next to it
-        py_compile.compile(src, cfile=dst, dfile=src, doraise=True,
-                           invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
-        if verbose:
-            print("compiled", rel, "->", os.path.relpath(dst, HERE))
-    with open(os.path.join(OUT, "PYTHON_VERSION"), "w") as f:
-        f.write(sys.version.split()[0] + "\n")
-    return OUT
+        return ARCHIVE if os.path.exists(ARCHIVE) else None
+    srcs = [os.path.join(REFERENCE_ROOT, rel) for rel in MODULES if os.path.exists(os.path.join(REFERENCE_ROOT, rel))]
+    if os.path.exists(ARCHIVE) and all(os.path.getmtime(ARCHIVE) >= os.path.getmtime(p) for p in srcs + [__file__]):
+        return ARCHIVE
+    os.makedirs(OUT, exist_ok=True)
+    with tempfile.TemporaryDirectory() as tmp, zipfile.ZipFile(ARCHIVE + ".tmp", "w", zipfile.ZIP_DEFLATED) as z:
+        for rel in MODULES:
+            src = os.path.join(REFERENCE_ROOT, rel)
+            if not os.path.exists(src):
+                continue
+            pyc = os.path.join(tmp, rel.replace("/", "_") + "c")
+            # dfile: the path tracebacks show; UNCHECKED_HASH: valid without its source next to it
+            py_compile.compile(src, cfile=pyc, dfile=src, doraise=True,
+                               invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
+            z.write(pyc, rel[:-3] + ".pyc")
+            if verbose:
+                print("compiled", rel)
+        z.writestr("PYTHON_VERSION", sys.version.split()[0] + "\n")
+    os.replace(ARCHIVE + ".tmp", ARCHIVE)
+    return ARCHIVE
 
 
 if __name__ == "__main__":

@@ -19,14 +19,14 @@ import sys
 import types
 
 SOURCE_ROOT = "/root/reference"
-COMPILED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+COMPILED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "reference_modules.zip")
 
 
 def root() -> str | None:
     """The live tree if present, else the byte-compiled copy, else None."""
     if os.path.isdir(os.path.join(SOURCE_ROOT, "data_load_preprocess")):
         return SOURCE_ROOT
-    if os.path.exists(os.path.join(COMPILED_ROOT, "data_load_preprocess", "filters.pyc")):
+    if os.path.exists(COMPILED_ROOT):                    # importable as a sys.path entry (zipimport)
         return COMPILED_ROOT
     return None
 

@@ -26,7 +26,7 @@ for mode in (0, 1):
     print('  mode', mode, 'kept', int(scr['keep'].sum()), 'hazards', int(scr['hazards'].item()), 'peaks checksum', int(scr['peaks'].to(torch.int64).sum().item()), 'median checksum', int(torch.nan_to_num(scr['median'][scr['keep'].bool()]).view(torch.int64).sum().item()))
 pre.screen_mode = 0
 out = np.zeros(16, np.uint64)
-names = ["load+nan+sum", "zscore", "np.std", "-", "-", "QRS indicator (4 segments)", "seq fallback", "run compaction",
+names = ["load+nan+sum", "zscore", "np.std (lazy) + decision", "-", "-", "QRS indicator (4 segments)", "seq fallback", "run compaction",
          "min_len", "peak per run", "(unused)", "warp0 chain+stats, peaks out", "median", "t13 leaf table", "t14 load pass", "t15 combine"]
 for rep in range(3):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -107,7 +107,8 @@ def filtfilt(records, stages, mode, zscore=False, max_seg=None):
     return [out[off[i]:off[i + 1]] for i in range(n)], hdr
 
 
-def screen(flat, starts, Lw=10000, mode=0, zscore_windows=True, want_z=False, fs=500, pvc=150.0, sdt=0.05):
+def screen(flat, starts, Lw=10000, mode=0, zscore_windows=True, want_z=False, fs=500, pvc=150.0, sdt=0.05,
+           lazy_sd=0):
     L = lib()
     flat = np.ascontiguousarray(flat, dtype=np.float64)
     starts = np.ascontiguousarray(starts, dtype=np.int64)
@@ -126,7 +127,7 @@ def screen(flat, starts, Lw=10000, mode=0, zscore_windows=True, want_z=False, fs
         zscore_windows=1 if zscore_windows else 0, keep=o["keep"].ctypes.data, has_nan=o["has_nan"].ctypes.data,
         n_peaks=o["n_peaks"].ctypes.data, peaks=o["peaks"].ctypes.data, stats=o["stats"].ctypes.data,
         median=o["median"].ctypes.data, waves=o["waves"].ctypes.data, zwin=o["zwin"].ctypes.data if want_z else None, zparams=o["zparams"].ctypes.data,
-        status=o["status"].ctypes.data, hazard_count=o["hazards"].ctypes.data)
+        status=o["status"].ctypes.data, hazard_count=o["hazards"].ctypes.data, lazy_sd=lazy_sd)
     rc = L.aew_windows_beats_f64(ctypes.byref(p), None)
     assert rc == 0, rc
     return o

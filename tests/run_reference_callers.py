@@ -96,8 +96,8 @@ def main():
     real_to_numpy = pd.DataFrame.to_numpy
     pd.DataFrame.to_numpy = lambda self, *a, **k: np.array(real_to_numpy(self, *a, **k))
 
-    ext = ".py" if ref_root == ref_import.SOURCE_ROOT else ".pyc"
-    runpy.run_path(os.path.join(ref_root, "data_extract_vitaldb" + ext), run_name="__main__")
+    # (the reference root is on sys.path -- a directory in the build container, the bytecode archive on the GPU box)
+    runpy.run_module("data_extract_vitaldb", run_name="__main__")
     import data_load_preprocess.filters as f
     import data_load_preprocess.load_record as lr
     import neurokit2 as nk
@@ -105,7 +105,7 @@ def main():
         assert "ae_waveforms_b200" in f.zscore.__module__, f.zscore.__module__
         assert "ae_waveforms_b200" in nk.ecg_delineate.__module__, nk.ecg_delineate.__module__
     assert lr.__file__.startswith(ref_root), lr.__file__          # the reference's own load_record ran
-    runpy.run_path(os.path.join(ref_root, "data_create_arrays" + ext), run_name="__main__")
+    runpy.run_module("data_create_arrays", run_name="__main__")
 
 
 if __name__ == "__main__":

@@ -101,6 +101,43 @@ def test_k3_screen_golden(golden):
     assert same(o2["keep"], o["keep"]) and same(o2["peaks"], o["peaks"])
 
 
+def test_k3_lazy_sd_takes_the_same_decisions():
+    """lazy_sd: np.std is evaluated only where n_peaks * 0.05 == 1; every keep / remove decision, the peaks and the
+    median beats are those of the full evaluation, sd is reported only for the 20-peak windows."""
+    x = ecg_synth.synth_case(7, 8 * 10000 + 5, hr_bpm=60.0)          # 19 / 20 / 21 peaks per window
+    y = rp.butterworth(rp.butterworth(rp.zscore(x), "high", 1.0), "low", 30.0)
+    full = eh.screen(y, np.arange(8) * 10000)
+    lazy = eh.screen(y, np.arange(8) * 10000, lazy_sd=1)
+    assert same(full["keep"], lazy["keep"]) and same(full["peaks"], lazy["peaks"])
+    assert same(full["stats"][:, :2], lazy["stats"][:, :2])
+    k = full["keep"].astype(bool)
+    assert same(full["median"][k], lazy["median"][k])
+    n20 = full["n_peaks"] == 20
+    assert n20.any() and (~n20).any()
+    assert same(lazy["stats"][n20, 2:], full["stats"][n20, 2:]) and np.isnan(lazy["stats"][~n20, 2:]).all()
+    want = rp.window_screen(np.stack([rp.zscore(y[i * 10000:(i + 1) * 10000]) for i in range(8)]))
+    assert same(lazy["keep"].astype(bool), want["keep"])
+
+
+def test_k3_zscore_sweep_general_form():
+    """Samples that equal the window mean exactly (zero quotients) send a warp of the z-score sweep through its
+    checked form after the branch-free one has already overwritten part of the window: same bits as NumPy."""
+    x = ecg_synth.synth_case(9, 30000)
+    y = rp.butterworth(rp.butterworth(rp.zscore(x), "high", 1.0), "low", 30.0)
+    half = y[10000:15000].copy()
+    half[[7, 1234, 4999]] = 0.0
+    win = np.concatenate([half, -half])                   # NumPy's pairwise sum of this is exactly 0
+    assert np.add.reduce(win) == 0.0
+    flat = np.concatenate([win, y[:10000]])
+    o = eh.screen(flat, np.array([0, 10000]), want_z=True)
+    want = rp.window_screen(np.stack([rp.zscore(win), rp.zscore(y[:10000])]))
+    assert same(o["zwin"][0], rp.zscore(win)) and same(o["zwin"][1], rp.zscore(y[:10000]))
+    assert same(o["keep"].astype(bool), want["keep"])
+    for j in range(2):
+        assert same(o["peaks"][j, :o["n_peaks"][j]], want["peaks"][j])
+        assert same(o["stats"][j, :3], [want["hr"][j], want["rmssd"][j], want["sd"][j]])
+
+
 def test_k3_other_window_lengths():
     """The segmented box filters, the bit-packed indicator and the run tables at window lengths / sampling rates
     other than 10,000 @ 500 Hz, against the oracle (fast and exact evaluation)."""
