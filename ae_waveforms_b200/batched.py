@@ -136,7 +136,7 @@ class Preprocessor:
     def __init__(self, fs: int = 500, sample_length: int = 20, hp: float = 1, lp: float = 30, order: int = 4,
                  pvc_threshold: float = 150, sd_threshold: float = 0.05, filter_mode: str = "fast",
                  screen_mode: str = "auto", max_segments: int | None = None, device=None,
-                 exact_masks: bool = False):
+                 exact_masks: bool = True):
         self.torch, self.lib = _cabi.require_cuda()
         self.device = self.torch.device(device or "cuda")
         if self.device.index is None:                      # bind to the device that is current NOW
@@ -155,7 +155,9 @@ class Preprocessor:
         self.exact_masks = bool(exact_masks) and self.filter_mode == 0
         self.defer_chunks = 6               # run_host_pipelined: chunks finished this many chunks late (exact_masks)
         self.lazy_sd = True                 # run(): 'ecg_sd' is not an output; evaluate it only where it decides
-        self.park_windows = bool(int(__import__("os").environ.get("AEW_K3_PARK", "0")))   # measurement switch
+        # the screen kernel parks the z-scored windows in the filter scratch for the median kernel (measured: 30.1 ms
+        # per 179,000 windows against 32.5 when the median kernel re-derives them; profiles/k3_variants.py)
+        self.park_windows = bool(int(__import__("os").environ.get("AEW_K3_PARK", "1")))
         self.launches = 0
         if self.L > self.lib.aew_windows_max_len():
             raise _cabi.AewError(f"window of {self.L} samples exceeds the kernel limit")
@@ -231,12 +233,12 @@ class Preprocessor:
 
     @_cabi.on_device
     def filter_records(self, flat, beg_h, end_h, d_beg, d_end, mean=None, sd=None, cnt=None, out=None, tmp=None,
-                       mode=None):
+                       mode=None, max_seg=None):
         """K2: z-score (fused) + high-pass + low-pass per NaN-delimited segment.
         Returns (filtered, device header tensor).  ``mode`` overrides the object's filter mode (0 tiled, 1 exact)."""
         torch, lib = self.torch, self.lib
         n_rec, total = len(beg_h), flat.numel()
-        max_seg = self.max_segments or (4 * n_rec + 4096)
+        max_seg = max_seg or self.max_segments or (4 * n_rec + 4096)
         ws_bytes = int(lib.aew_filt_workspace_bytes(n_rec, total, max_seg))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
         y = torch.empty_like(flat) if out is None else out
@@ -422,6 +424,9 @@ class Preprocessor:
         hz_h = hz_idx.cpu().numpy()
         recs = np.unique(win_rec[hz_h])
         lens = (end_h[recs] - beg_h[recs]).astype(np.int64)
+        # records without NaN are one segment each: the sequential kernel then gets exactly the blocks it needs
+        # (every block keeps an SM to itself; see K2E_HOG in k2_filtfilt.cu)
+        clean = bool((cnt.cpu().numpy()[recs] == lens).all())
         coff = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
         # main stream: the hazard records' samples and statistics are copied out, so that the side stream touches
         # nothing the next batch may overwrite (input buffers, filter scratch)
@@ -434,16 +439,21 @@ class Preprocessor:
         d_start_c = self._upload(start_c)
         L = self.L
         main = torch.cuda.current_stream(self.device)
-        side = getattr(self, "_side_stream", None)
-        if side is None:
-            side = self._side_stream = torch.cuda.Stream(device=self.device, priority=-1)
+        # a POOL of side streams, round robin: one pass takes ~150 ms however few records it holds, so the passes of
+        # consecutive batches / chunks must run next to each other, not queue behind each other on one stream
+        pool = getattr(self, "_side_streams", None)
+        if pool is None:
+            pool = self._side_streams = [torch.cuda.Stream(device=self.device, priority=-1) for _ in range(8)]
+            self._side_next = 0
+        side = pool[self._side_next % len(pool)]
+        self._side_next += 1
         ready = torch.cuda.Event()
         ready.record(main)
         with torch.cuda.stream(side):
             side.wait_event(ready)
             yc, tc = torch.empty_like(xc), torch.empty_like(xc)
             self.filter_records(xc, coff[:-1].copy(), coff[1:].copy(), d_off[:-1].contiguous(), d_off[1:].contiguous(),
-                                m_c, s_c, n_c, out=yc, tmp=tc, mode=1)
+                                m_c, s_c, n_c, out=yc, tmp=tc, mode=1, max_seg=len(recs) if clean else None)
             scr2 = self.screen_windows(yc, start_c, zwin_scratch=tc if tc.numel() >= len(hz_h) * L else None,
                                        d_start=d_start_c)
             changed = (scr2["keep"] != scr["keep"].index_select(0, hz_idx)).sum()

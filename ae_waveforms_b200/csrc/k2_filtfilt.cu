@@ -743,8 +743,15 @@ __device__ __forceinline__ double df2t_step_exact(const double* b, const double*
   return y;
 }
 
-#define K2E_NT 32                       // one warp per segment
+#define K2E_WARPS 8                     // one warp per segment, eight segments per block: two chains per SM sub-partition
+                                        // (each needs ~24 of its ~44 cycles per sample on the FP64 pipe)
+#define K2E_NT (32 * K2E_WARPS)
 #define K2E_BLK 64                      // samples per round: two per lane (halves the rounds' fixed cost)
+#define K2E_HOG (150 * 1024)            // dynamic shared memory the block asks for and never touches: keeps the SM
+                                        // to itself.  The chain is a latency race -- next to the window or filter
+                                        // kernels' warps every one of its ~22 instructions per sample waits for an
+                                        // issue slot (measured: 3 passes in flight next to the main kernels took
+                                        // 185 ms per batch, against 66 ms + the 13 SMs given up here)
 // one pass over n samples: logical sample i is in[i] (REV: in[n - 1 - i]); lane 0 owns the state z
 template <int ORD, bool REV>
 __device__ __forceinline__ void exact_stream(const double* in, double* out, long long n, const double* b,
@@ -793,12 +800,14 @@ __device__ __forceinline__ void exact_stream(const double* in, double* out, long
 
 template <int ORD>
 __global__ void __launch_bounds__(K2E_NT) k2_exact(PassArgs a) {
-  __shared__ double sp[ORD + 1][K2E_BLK + 2];
-  __shared__ double sy[K2E_BLK];
+  __shared__ double sp_all[K2E_WARPS][ORD + 1][K2E_BLK + 2];
+  __shared__ double sy_all[K2E_WARPS][K2E_BLK];
   const long long n_seg = a.ws.hdr[H_SEG_COUNT] < a.ws.max_seg ? a.ws.hdr[H_SEG_COUNT] : a.ws.max_seg;
-  const long long seg = blockIdx.x;
-  const int lane = threadIdx.x;
-  if (seg >= n_seg) return;
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long seg = (long long)blockIdx.x * K2E_WARPS + wib;
+  double (*sp)[K2E_BLK + 2] = sp_all[wib];
+  double* sy = sy_all[wib];
+  if (seg >= n_seg) return;                              // (warps never meet at a block barrier)
   const long long* sg = a.ws.segs + 4 * seg;
   const long long g0 = sg[0], n = sg[1], rec = sg[2];
   const bool zon = a.mean != nullptr;
@@ -812,7 +821,7 @@ __global__ void __launch_bounds__(K2E_NT) k2_exact(PassArgs a) {
   double* out = a.passthrough + g0;
   double* tmp = a.dst + g0;
   if (n <= pad) {                                        // filters.py:50-51: too short to filter, copied through
-    for (long long i = lane; i < n; i += K2E_NT) out[i] = zs(xs[i], zon, mean, sd);
+    for (long long i = lane; i < n; i += 32) out[i] = zs(xs[i], zon, mean, sd);
     return;
   }
   double ve[K2_MAXPAD];
@@ -903,15 +912,19 @@ extern "C" int aew_filtfilt_f64(const double* src, const double* mean, const dou
     a.dbg = g_dbg;
   }
 #endif
-  if (mode == 1) {                                       // one warp per segment (blocks beyond the count exit)
-    const long long blocks = max_seg;
+  if (mode == 1) {                                       // one warp per segment (warps beyond the count exit)
+    const long long blocks = (max_seg + K2E_WARPS - 1) / K2E_WARPS;
+#define K2E_GO(O)                                                                       \
+    if (AEW_SET_MAX_SMEM(k2_exact<O>, K2E_HOG) != 0) return (int)cudaGetLastError();     \
+    AEW_LAUNCH(k2_exact<O>, (unsigned)blocks, K2E_NT, K2E_HOG, st, a);
     switch ((int)h_tab[K2_TAB_ORDER]) {
-      case 1: AEW_LAUNCH(k2_exact<1>, (unsigned)blocks, K2E_NT, 0, st, a); break;
-      case 2: AEW_LAUNCH(k2_exact<2>, (unsigned)blocks, K2E_NT, 0, st, a); break;
-      case 3: AEW_LAUNCH(k2_exact<3>, (unsigned)blocks, K2E_NT, 0, st, a); break;
-      case 4: AEW_LAUNCH(k2_exact<4>, (unsigned)blocks, K2E_NT, 0, st, a); break;
+      case 1: K2E_GO(1) break;
+      case 2: K2E_GO(2) break;
+      case 3: K2E_GO(3) break;
+      case 4: K2E_GO(4) break;
       default: return AEW_ERR_UNSUPPORTED;
     }
+#undef K2E_GO
     return (int)cudaGetLastError();
   }
   if (mode != 0) return AEW_ERR_ARG;

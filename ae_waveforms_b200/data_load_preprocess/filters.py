@@ -9,9 +9,10 @@ import numpy as np
 from .. import _cabi
 from ..batched import Preprocessor, RecordBatch, _ptr
 
-# "fast": tiled block scan (within 1e-6 relative of SciPy, measured ~1e-9);
-# "exact": literal sequential DF2T order, bit-identical to scipy.signal.filtfilt
-FILTER_MODE = os.environ.get("AEW_FILTER_MODE", "fast")
+# "exact" (default of the per-call drop-in): SciPy's sequential DF2T order, one warp per segment -- bit-identical to
+# scipy.signal.filtfilt, so the reference's scripts produce the reference's arrays (tests/test_callers.py);
+# "fast": the tiled block scan of the batched path (within 1e-6 relative of SciPy, measured ~1e-9)
+FILTER_MODE = os.environ.get("AEW_FILTER_MODE", "exact")
 
 
 def _as_record(data):

@@ -68,7 +68,7 @@ def test_zscore_dropin(gpu, golden):
 def test_butterworth_dropin_exact_mode_bit_identical(gpu, golden):
     from ae_waveforms_b200.data_load_preprocess import filters
     g = golden("filters")
-    filters.FILTER_MODE = "exact"
+    saved, filters.FILTER_MODE = filters.FILTER_MODE, "exact"
     try:
         for tag in ("clean", "gaps"):
             hp = filters.butterworth(g[f"{tag}_z"], "high", 1, 500, 4)
@@ -78,11 +78,13 @@ def test_butterworth_dropin_exact_mode_bit_identical(gpu, golden):
         assert same(filters.butterworth(g["short_x"], "low", 40, 500, 3), g["short_lp40_o3"])
         assert same(filters.butterworth(g["short_x"], "low", 15, 500, 1), g["short_lp15_o1"])
     finally:
-        filters.FILTER_MODE = "fast"
+        filters.FILTER_MODE = saved
 
 
-def test_butterworth_dropin_fast_mode(gpu, golden):
+def test_butterworth_dropin_fast_mode(gpu, golden, monkeypatch):
+    from ae_waveforms_b200.data_load_preprocess import filters
     from ae_waveforms_b200.data_load_preprocess.filters import butterworth
+    monkeypatch.setattr(filters, "FILTER_MODE", "fast")
     g = golden("filters")
     for tag in ("clean", "gaps"):
         hp = butterworth(g[f"{tag}_z"], "high", 1)
