@@ -648,8 +648,21 @@ def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chu
     n_rec = len(rec_off) - 1
     case_ids = np.arange(n_rec, dtype=np.int64) if case_ids is None else np.asarray(case_ids, dtype=np.int64)
     chunks = chunk_schedule(n_rec, chunk_cases, taper)
+    lens_rec = rec_off[1:] - rec_off[:-1]
+    # exact_masks: the sequential pass of a chunk's 20-peak records takes ~150 ms however small the chunk; if such
+    # a record sits in one of the LAST chunks the call ends with that wait.  So records that look like holding
+    # 20-peak windows (a preview of their first windows, below) are fed FIRST, right after the first two chunks;
+    # the rows are put back into case order on the device at the end.  A wrong guess costs time, never results.
+    hazard_first = bool(pre.exact_masks and not features and len(chunks) > 3 and pre.hazard_peak_count()
+                        and len(np.unique(case_ids)) == n_rec)
+    order = np.arange(n_rec)
     sizes = [int(rec_off[c1] - rec_off[c0]) for c0, c1 in chunks]
-    cap = max(sizes) if sizes else 0
+    if hazard_first:                               # any chunk may end up holding the longest records
+        srt = np.sort(lens_rec)[::-1]
+        sizes_cap = [int(srt[:c1 - c0].sum()) for c0, c1 in chunks]
+    else:
+        sizes_cap = sizes
+    cap = max(sizes_cap) if sizes_cap else 0
     narrow = host_flat.dtype != torch.float64
     cap_al = (cap + 7) & ~7                                    # keeps every buffer 16-byte aligned
     bufs = [torch.empty(cap_al, dtype=host_flat.dtype, device=pre.device) for _ in range(2)]
@@ -670,16 +683,55 @@ def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chu
 
     def start_copy(k):
         c0, c1 = chunks[k]
+        recs = order[c0:c1]
         with torch.cuda.stream(copy_stream):
             if k >= 2:
                 copy_stream.wait_event(freed[k - 2])          # the buffer's previous chunk has been consumed
             # the copy engine serves its queue in order whatever the stream (measured: pieces do not let a small copy
             # of another stream overtake), so nothing the kernels need may go through it: see Preprocessor._upload
-            lo, hi = int(rec_off[c0]), int(rec_off[c1])
-            for p0 in range(lo, hi, COPY_PIECE):
-                p1 = min(hi, p0 + COPY_PIECE)
-                bufs[k % 2][p0 - lo:p1 - lo].copy_(host_flat[p0:p1], non_blocking=True)
+            if len(recs) and np.array_equal(recs, np.arange(recs[0], recs[0] + len(recs))):
+                lo, hi = int(rec_off[recs[0]]), int(rec_off[recs[-1] + 1])        # records in a row: one copy
+                bufs[k % 2][:hi - lo].copy_(host_flat[lo:hi], non_blocking=True)
+            else:
+                at = 0
+                for r in recs:                                                   # one copy per record
+                    lo, hi = int(rec_off[r]), int(rec_off[r + 1])
+                    bufs[k % 2][at:at + hi - lo].copy_(host_flat[lo:hi], non_blocking=True)
+                    at += hi - lo
             copied[k].record(copy_stream)
+
+    def preview_order():
+        """Records 0 .. first-1 stay where they are (their chunks are already on their way); of the others, those
+        whose first windows hold hazard_peak_count() +- 2 beats come first.  The preview (the first two windows of
+        every remaining record) crosses PCIe behind the first two chunks and goes through K1 / K2 / K3 once."""
+        first = chunks[1][1]
+        rest = np.arange(first, n_rec)
+        take = np.minimum(lens_rec[rest], 2 * pre.L + 1)
+        poff = np.concatenate([[0], np.cumsum(take)]).astype(np.int64)
+        pbuf = torch.empty(int(poff[-1]), dtype=host_flat.dtype, device=pre.device)
+        with torch.cuda.stream(copy_stream):
+            for j, r in enumerate(rest):
+                lo = int(rec_off[r])
+                pbuf[int(poff[j]):int(poff[j + 1])].copy_(host_flat[lo:lo + int(take[j])], non_blocking=True)
+            got = torch.cuda.Event()
+            got.record(copy_stream)
+        return rest, poff, pbuf, got
+
+    def rank_preview(rest, poff, pbuf, got):
+        main.wait_event(got)
+        pw = widen_to_f64(pbuf, None, gain, offset, sentinel) if narrow else pbuf
+        sub = RecordBatch(pw, poff, rest)
+        beg_h, end_h, d_beg, d_end = pre._ranges(sub, trim=False)
+        mean, sd, cnt = pre.zscore_stats(pw, beg_h, end_h, d_beg, d_end)
+        y, _ = pre.filter_records(pw, beg_h, end_h, d_beg, d_end, mean, sd, cnt, mode=0)
+        wstart, wcase, _ = pre.window_table(beg_h, end_h, rest)
+        if not len(wstart):
+            return rest
+        scr = pre.screen_windows(y, wstart, want_median=False, lazy_sd=True)
+        npk = scr["n_peaks"].cpu().numpy()
+        prone = np.zeros(n_rec, dtype=bool)
+        prone[wcase[np.abs(npk - pre.hazard_peak_count()) <= 2]] = True
+        return np.concatenate([rest[prone[rest]], rest[~prone[rest]]])
 
     waves, infos, feats = [], [], []
     tot = dict(hazards=0, n_windows=0, n_beats=0, rows=0, mask_hazard=0, mask_flips=0)
@@ -694,7 +746,7 @@ def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chu
         infos.append(res["np_info"])
         if features:
             feats.append(res["np_features"])
-        if to_host:
+        if to_host and not hazard_first:
             n = res["np_waves"].shape[0]
             rows = tot["rows"]
             done = torch.cuda.Event()
@@ -714,8 +766,16 @@ def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chu
 
     if chunks:
         start_copy(0)
+    preview = None
     for k, (c0, c1) in enumerate(chunks):
-        if k + 1 < len(chunks):
+        if hazard_first and k == 0:
+            start_copy(1)
+            preview = preview_order()                          # queued behind chunks 0 and 1 on the copy engine
+        elif hazard_first and k == 1:
+            order = np.concatenate([order[:c1], rank_preview(*preview)])
+            sizes = [int(lens_rec[order[a:b]].sum()) for a, b in chunks]
+            start_copy(2)
+        elif k + 1 < len(chunks):
             start_copy(k + 1)
         main.wait_event(copied[k])
         if narrow:
@@ -725,7 +785,9 @@ def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chu
             chunk_in = wide[:sizes[k]]
         else:
             chunk_in = bufs[k % 2][:sizes[k]]
-        sub = RecordBatch(chunk_in, rec_off[c0:c1 + 1] - rec_off[c0], case_ids[c0:c1])
+        recs_k = order[c0:c1]
+        sub = RecordBatch(chunk_in, np.concatenate([[0], np.cumsum(lens_rec[recs_k])]).astype(np.int64),
+                          case_ids[recs_k])
         sc = {"y": scratch["y"][:sizes[k]], "tmp": scratch["tmp"][:sizes[k]]}
         pending.append(pre.run(sub, scratch=sc, features=features, defer=depth > 0))
         if not narrow:
@@ -735,6 +797,23 @@ def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chu
     while pending:
         finish_one(pending.pop(0))
     hazards, n_windows, n_beats, rows = tot["hazards"], tot["n_windows"], tot["n_beats"], tot["rows"]
+    sorted_dev = None
+    if hazard_first:
+        # back into case order (rows of one case are already in window order): position of every row's case in
+        # the caller's list, stable sort, one gather per array -- all on the device
+        w_all = torch.cat(waves) if waves else torch.zeros((0, pre.beat_len), dtype=torch.float32, device=pre.device)
+        i_all = torch.cat(infos) if infos else torch.zeros((0, 2), dtype=torch.float64, device=pre.device)
+        ids_sorted, inv = np.unique(case_ids, return_inverse=False), np.argsort(case_ids, kind="stable")
+        d_ids = pre._upload(ids_sorted.astype(np.int64))
+        d_pos = pre._upload(inv.astype(np.int64))
+        pos = d_pos.index_select(0, torch.searchsorted(d_ids, i_all[:, 0].to(torch.int64).contiguous()))
+        perm = torch.argsort(pos, stable=True)
+        sorted_dev = (w_all.index_select(0, perm), i_all.index_select(0, perm))
+        rows = int(sorted_dev[0].shape[0])
+        if to_host:
+            h_waves[:rows].copy_(sorted_dev[0], non_blocking=True)
+            h_info[:rows].copy_(sorted_dev[1], non_blocking=True)
+            main.synchronize()
     if to_host:
         back_stream.synchronize()
         np_waves, np_info = h_waves[:rows], h_info[:rows]
@@ -742,6 +821,8 @@ def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chu
         if not pinned_results:
             np_waves, np_info = np_waves.clone(), np_info.clone()
             np_feat = np_feat.clone() if features else None
+    elif sorted_dev is not None:
+        np_waves, np_info, np_feat = sorted_dev[0], sorted_dev[1], None
     else:
         np_feat = (torch.cat(feats) if feats else torch.zeros((0, 35), dtype=torch.float64, device=pre.device)) \
             if features else None

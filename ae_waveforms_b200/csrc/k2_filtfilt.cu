@@ -728,13 +728,17 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
 
 // ------------------------------------------------------------ exact sequential mode
 // SciPy's evaluation order (lfilter's direct form II transposed, one sample at a time, separate multiply and add):
-// bit-identical to scipy.signal.filtfilt.  The recursion cannot be re-associated without changing the bits
-// (profiles/README.md: two DF2T trajectories that start one ulp apart do not merge again), so ONE lane walks each
-// segment; what the kernel can do is keep that lane's dependent chain -- DADD, DMUL, DADD per sample, 3 x 8
-// cycles -- free of everything else.  One WARP per segment: all lanes load the next 32 samples (coalesced, one
-// block ahead), z-score them (the correctly rounded division of the first pass) and form the products b[k] x
-// into shared memory; lane 0 runs the 32 steps from there; all lanes store the 32 outputs.  ~30 cycles per sample
-// and pass instead of the ~250 of a single thread that waits for each global load in turn.
+// bit-identical to scipy.signal.filtfilt.  The recursion cannot be re-associated without changing the bits (two
+// DF2T trajectories that start one ulp apart do not merge again: profiles/README.md), so every segment is ONE
+// dependent chain -- DADD, DMUL, DADD per sample, 3 x 8 cycles, ~17 FP64 instructions in all -- and takes ~40 cycles
+// per sample and pass whatever else happens: ~150 ms for the four passes of a 1 h record.  What the kernel can
+// choose is how little of the machine that costs.  One LANE per segment: the 32 lanes of a warp walk 32 segments in
+// lockstep, every FP64 instruction serves 32 chains, and a batch of 100 records is four warps -- they run next to
+// the other kernels without taking anything noticeable from them (the earlier forms, one thread or one warp per
+// segment, needed 32 x the issue slots for the same latency: measured 185 ms per batch with three passes in flight
+// next to the window / filter kernels, against 66 ms of those kernels alone).  Memory stays coalesced: the warp
+// moves one 256-byte row per segment and round through shared memory (exact_pass below); a first lane-per-segment
+// form with per-lane loads took 5 x longer (32 sectors per load instruction).
 __device__ __forceinline__ double df2t_step_exact(const double* b, const double* a, int ord, double x, double* z) {
   const double y = __dadd_rn(z[0], __dmul_rn(b[0], x));
   for (int k = 0; k < ord - 1; ++k)
@@ -743,73 +747,94 @@ __device__ __forceinline__ double df2t_step_exact(const double* b, const double*
   return y;
 }
 
-#define K2E_WARPS 8                     // one warp per segment, eight segments per block: two chains per SM sub-partition
-                                        // (each needs ~24 of its ~44 cycles per sample on the FP64 pipe)
-#define K2E_NT (32 * K2E_WARPS)
-#define K2E_BLK 64                      // samples per round: two per lane (halves the rounds' fixed cost)
-#define K2E_HOG (150 * 1024)            // dynamic shared memory the block asks for and never touches: keeps the SM
-                                        // to itself.  The chain is a latency race -- next to the window or filter
-                                        // kernels' warps every one of its ~22 instructions per sample waits for an
-                                        // issue slot (measured: 3 passes in flight next to the main kernels took
-                                        // 185 ms per batch, against 66 ms + the 13 SMs given up here)
-// one pass over n samples: logical sample i is in[i] (REV: in[n - 1 - i]); lane 0 owns the state z
+#define K2E_T 32                        // samples per segment and round (one 256-byte row per segment)
+#define K2E_LD (K2E_T + 1)              // row stride in shared memory: lane l reads row l -> bank (l + t) mod 32
+
+// One pass of the 32 segments of a warp over their samples: logical sample i of a segment is in[i] (REV:
+// in[n - 1 - i]).  Rounds of 32 samples: the 32 rows (one per segment, 256 contiguous bytes each) of the NEXT round
+// are fetched by asynchronous copies of the whole warp (lane t fetches column t: coalesced) while every lane walks
+// its own row of the current round from shared memory; the outputs go back the same way.  s_in / s_n hold the
+// segments' base pointers and lengths.
 template <int ORD, bool REV>
-__device__ __forceinline__ void exact_stream(const double* in, double* out, long long n, const double* b,
-                                             const double* a, double* z, bool zon, double mean, const ExactDiv& sd,
-                                             double (*sp)[K2E_BLK + 2], double* sy, int lane) {
-  double v0 = 0.0, v1 = 0.0;
-  if (lane < n) v0 = in[REV ? n - 1 - lane : lane];
-  if (lane + 32 < n) v1 = in[REV ? n - 1 - (lane + 32) : lane + 32];
-  for (long long i0 = 0; i0 < n; i0 += K2E_BLK) {
-    const long long j0 = i0 + K2E_BLK + lane, j1 = j0 + 32;   // the next round is in flight while lane 0 works
-    double w0 = 0.0, w1 = 0.0;
-    if (j0 < n) w0 = in[REV ? n - 1 - j0 : j0];
-    if (j1 < n) w1 = in[REV ? n - 1 - j1 : j1];
-    const double x0 = zs(v0, zon, mean, sd), x1 = zs(v1, zon, mean, sd);
-#pragma unroll
-    for (int k = 0; k <= ORD; ++k) { sp[k][lane] = __dmul_rn(b[k], x0); sp[k][lane + 32] = __dmul_rn(b[k], x1); }
+__device__ __forceinline__ void exact_pass(const double* const* s_in, double* const* s_out, const long long* s_n,
+                                           long long n_max, double (*tin)[K2E_T][K2E_LD], double (*tout)[K2E_LD],
+                                           const double* b, const double* a, double* z, long long n, bool zon,
+                                           double mean, const ExactDiv& sd, int lane) {
+  auto fetch = [&](long long r, int buf) {
+    const long long i = r * K2E_T + lane;                 // logical index of my column in every row
+#pragma unroll 4
+    for (int sgm = 0; sgm < 32; ++sgm) {
+      const long long ns = s_n[sgm];
+      if (i < ns) {
+        const double* src = s_in[sgm] + (REV ? ns - 1 - i : i);
+#ifdef AEW_EMUL
+        tin[buf][sgm][lane] = *src;
+#else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(&tin[buf][sgm][lane])), "l"(src) : "memory");
+#endif
+      }
+    }
+#ifndef AEW_EMUL
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+  };
+  const long long rounds = (n_max + K2E_T - 1) / K2E_T;
+  if (rounds > 0) fetch(0, 0);
+  for (long long r = 0; r < rounds; ++r) {
+    const int buf = (int)(r & 1);
+    if (r + 1 < rounds) fetch(r + 1, buf ^ 1);             // (its buffer was last read in round r - 1: barrier below)
+#ifndef AEW_EMUL
+    if (r + 1 < rounds) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
     __syncwarp();
-    if (lane == 0) {
-      const int cnt = (int)(n - i0 < K2E_BLK ? n - i0 : K2E_BLK);
-      // the products of the next two samples are fetched BEFORE this sample's dependent chain (DADD, DMUL, DADD)
-      // is issued: an in-order warp would otherwise expose one shared-memory latency per sample
-      double c[ORD + 1], c1[ORD + 1];
-#pragma unroll
-      for (int k = 0; k <= ORD; ++k) { c[k] = sp[k][0]; c1[k] = sp[k][1]; }
+    const long long i0 = r * K2E_T;
+    if (i0 < n) {
+      const int cnt = (int)(n - i0 < K2E_T ? n - i0 : K2E_T);
+      const double* row = tin[buf][lane];
+      double* orow = tout[lane];
+      double c = row[0];
 #pragma unroll 4
       for (int t = 0; t < cnt; ++t) {
-        double c2[ORD + 1];
+        const double nx = row[t + 1];                      // (one pad column: in bounds; fetched before the chain)
+        const double x = zs(c, zon, mean, sd);
+        const double y = __dadd_rn(z[0], __dmul_rn(b[0], x));
 #pragma unroll
-        for (int k = 0; k <= ORD; ++k) c2[k] = sp[k][t + 2];          // (the two pad columns keep this in bounds)
-        const double y = __dadd_rn(z[0], c[0]);
-#pragma unroll
-        for (int k = 0; k < ORD - 1; ++k) z[k] = __dsub_rn(__dadd_rn(z[k + 1], c[k + 1]), __dmul_rn(y, a[k + 1]));
-        z[ORD - 1] = __dsub_rn(c[ORD], __dmul_rn(y, a[ORD]));
-        sy[t] = y;
-#pragma unroll
-        for (int k = 0; k <= ORD; ++k) { c[k] = c1[k]; c1[k] = c2[k]; }
+        for (int k = 0; k < ORD - 1; ++k)
+          z[k] = __dsub_rn(__dadd_rn(z[k + 1], __dmul_rn(x, b[k + 1])), __dmul_rn(y, a[k + 1]));
+        z[ORD - 1] = __dsub_rn(__dmul_rn(x, b[ORD]), __dmul_rn(y, a[ORD]));
+        orow[t] = y;
+        c = nx;
       }
     }
     __syncwarp();
-    if (i0 + lane < n) out[REV ? n - 1 - (i0 + lane) : i0 + lane] = sy[lane];
-    if (i0 + lane + 32 < n) out[REV ? n - 1 - (i0 + lane + 32) : i0 + lane + 32] = sy[lane + 32];
+    {
+      const long long i = i0 + lane;
+#pragma unroll 4
+      for (int sgm = 0; sgm < 32; ++sgm) {
+        const long long ns = s_n[sgm];
+        if (i < ns) s_out[sgm][REV ? ns - 1 - i : i] = tout[sgm][lane];
+      }
+    }
     __syncwarp();
-    v0 = w0; v1 = w1;
   }
 }
 
 template <int ORD>
-__global__ void __launch_bounds__(K2E_NT) k2_exact(PassArgs a) {
-  __shared__ double sp_all[K2E_WARPS][ORD + 1][K2E_BLK + 2];
-  __shared__ double sy_all[K2E_WARPS][K2E_BLK];
+__global__ void __launch_bounds__(32) k2_exact(PassArgs a) {
+  __shared__ double tin[2][K2E_T][K2E_LD];
+  __shared__ double tout[K2E_T][K2E_LD];
+  __shared__ const double* s_src[32];
+  __shared__ double* s_tmp[32];
+  __shared__ double* s_dst[32];
+  __shared__ long long s_n[32];
   const long long n_seg = a.ws.hdr[H_SEG_COUNT] < a.ws.max_seg ? a.ws.hdr[H_SEG_COUNT] : a.ws.max_seg;
-  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long seg = (long long)blockIdx.x * K2E_WARPS + wib;
-  double (*sp)[K2E_BLK + 2] = sp_all[wib];
-  double* sy = sy_all[wib];
-  if (seg >= n_seg) return;                              // (warps never meet at a block barrier)
-  const long long* sg = a.ws.segs + 4 * seg;
-  const long long g0 = sg[0], n = sg[1], rec = sg[2];
+  const int lane = threadIdx.x;
+  const long long seg = (long long)blockIdx.x * 32 + lane;
+  const bool have = seg < n_seg;
+  const long long* sg = a.ws.segs + 4 * (have ? seg : 0);
+  const long long g0 = have ? sg[0] : 0, rec = have ? sg[2] : 0;
+  long long n = have ? sg[1] : 0;
   const bool zon = a.mean != nullptr;
   const double mean = zon ? a.mean[rec] : 0.0;
   const ExactDiv sd = make_exact_div(zon ? a.sd[rec] : 1.0);
@@ -820,27 +845,32 @@ __global__ void __launch_bounds__(K2E_NT) k2_exact(PassArgs a) {
   const double* xs = a.src + g0;
   double* out = a.passthrough + g0;
   double* tmp = a.dst + g0;
-  if (n <= pad) {                                        // filters.py:50-51: too short to filter, copied through
-    for (long long i = lane; i < n; i += 32) out[i] = zs(xs[i], zon, mean, sd);
-    return;
+  if (have && n <= pad) {                                // filters.py:50-51: too short to filter, copied through
+    for (long long i = 0; i < n; ++i) out[i] = zs(xs[i], zon, mean, sd);
+    n = 0;                                               // (takes no further part, but stays with its warp)
   }
+  s_src[lane] = xs; s_tmp[lane] = tmp; s_dst[lane] = out; s_n[lane] = n;
+  const long long n_max = (long long)__reduce_max_sync(AEW_FULL, (unsigned)(n > 0x7fffffffll ? 0x7fffffffll : n));
+  __syncwarp();
   double ve[K2_MAXPAD];
-  const double x0 = zs(xs[0], zon, mean, sd), xl = zs(xs[n - 1], zon, mean, sd);
-  if (lane == 0) {                                       // odd extension on the left, zi scaled by its first sample
+  double x0 = 0.0, xl = 0.0;
+  if (n > 0) {                                           // odd extension on the left, zi scaled by its first sample
+    x0 = zs(xs[0], zon, mean, sd); xl = zs(xs[n - 1], zon, mean, sd);
     const double e0 = __dsub_rn(__dmul_rn(2.0, x0), zs(xs[pad], zon, mean, sd));
     for (int i = 0; i < ORD; ++i) z[i] = __dmul_rn(zi[i], e0);
     for (int e = 0; e < pad; ++e)
       df2t_step_exact(b, ac, ORD, __dsub_rn(__dmul_rn(2.0, x0), zs(xs[pad - e], zon, mean, sd)), z);
   }
-  exact_stream<ORD, false>(xs, tmp, n, b, ac, z, zon, mean, sd, sp, sy, lane);
-  if (lane == 0) {                                       // right extension, then the backward pass starts inside it
+  exact_pass<ORD, false>(s_src, s_tmp, s_n, n_max, tin, tout, b, ac, z, n, zon, mean, sd, lane);
+  if (n > 0) {                                           // right extension, then the backward pass starts inside it
     for (int m = 0; m < pad; ++m)
       ve[m] = df2t_step_exact(b, ac, ORD, __dsub_rn(__dmul_rn(2.0, xl), zs(xs[n - 2 - m], zon, mean, sd)), z);
     for (int i = 0; i < ORD; ++i) z[i] = __dmul_rn(zi[i], ve[pad - 1]);
     for (int e = 0; e < pad; ++e) df2t_step_exact(b, ac, ORD, ve[pad - 1 - e], z);
   }
-  __syncwarp();                                          // (orders the warp's stores to tmp before the reads below)
-  exact_stream<ORD, true>(tmp, out, n, b, ac, z, false, 0.0, sd, sp, sy, lane);
+  __threadfence_block();                                 // the warp's stores to tmp before the copies that read them
+  __syncwarp();
+  exact_pass<ORD, true>((const double* const*)s_tmp, s_dst, s_n, n_max, tin, tout, b, ac, z, n, false, 0.0, sd, lane);
 }
 
 unsigned long long* g_dbg = nullptr;   // device counters, allocated once when AEW_K2_TIMING is set
@@ -912,19 +942,15 @@ extern "C" int aew_filtfilt_f64(const double* src, const double* mean, const dou
     a.dbg = g_dbg;
   }
 #endif
-  if (mode == 1) {                                       // one warp per segment (warps beyond the count exit)
-    const long long blocks = (max_seg + K2E_WARPS - 1) / K2E_WARPS;
-#define K2E_GO(O)                                                                       \
-    if (AEW_SET_MAX_SMEM(k2_exact<O>, K2E_HOG) != 0) return (int)cudaGetLastError();     \
-    AEW_LAUNCH(k2_exact<O>, (unsigned)blocks, K2E_NT, K2E_HOG, st, a);
+  if (mode == 1) {                                       // one lane per segment (lanes beyond the count exit)
+    const long long blocks = (max_seg + 31) / 32;
     switch ((int)h_tab[K2_TAB_ORDER]) {
-      case 1: K2E_GO(1) break;
-      case 2: K2E_GO(2) break;
-      case 3: K2E_GO(3) break;
-      case 4: K2E_GO(4) break;
+      case 1: AEW_LAUNCH(k2_exact<1>, (unsigned)blocks, 32, 0, st, a); break;
+      case 2: AEW_LAUNCH(k2_exact<2>, (unsigned)blocks, 32, 0, st, a); break;
+      case 3: AEW_LAUNCH(k2_exact<3>, (unsigned)blocks, 32, 0, st, a); break;
+      case 4: AEW_LAUNCH(k2_exact<4>, (unsigned)blocks, 32, 0, st, a); break;
       default: return AEW_ERR_UNSUPPORTED;
     }
-#undef K2E_GO
     return (int)cudaGetLastError();
   }
   if (mode != 0) return AEW_ERR_ARG;
