@@ -736,100 +736,134 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
 // lockstep, every FP64 instruction serves 32 chains, and a batch of 100 records is four warps -- they run next to
 // the other kernels without taking anything noticeable from them (the earlier forms, one thread or one warp per
 // segment, needed 32 x the issue slots for the same latency: measured 185 ms per batch with three passes in flight
-// next to the window / filter kernels, against 66 ms of those kernels alone).  Memory stays coalesced: the warp
-// moves one 256-byte row per segment and round through shared memory (exact_pass below); a first lane-per-segment
-// form with per-lane loads took 5 x longer (32 sectors per load instruction).
-__device__ __forceinline__ double df2t_step_exact(const double* b, const double* a, int ord, double x, double* z) {
+// next to the window / filter kernels, against 66 ms of those kernels alone).  Memory stays coalesced: a second
+// warp moves one 256-byte row per segment and round through shared memory (exact_pass below); a first
+// lane-per-segment form with per-lane loads took 5 x longer (32 sectors per load instruction), a second one whose
+// chain warp moved the rows itself 6 x (a lone in-order warp pays every shared-memory latency in full).
+// (ORD is a template parameter and every loop over the state is unrolled: with run-time indices b, a and z would
+//  live in local memory, and the chain would wait for a memory round trip per sample)
+template <int ORD>
+__device__ __forceinline__ double df2t_step_exact(const double (&b)[5], const double (&a)[5], double x, double (&z)[4]) {
   const double y = __dadd_rn(z[0], __dmul_rn(b[0], x));
-  for (int k = 0; k < ord - 1; ++k)
+#pragma unroll
+  for (int k = 0; k < ORD - 1; ++k)
     z[k] = __dsub_rn(__dadd_rn(z[k + 1], __dmul_rn(x, b[k + 1])), __dmul_rn(y, a[k + 1]));
-  z[ord - 1] = __dsub_rn(__dmul_rn(x, b[ord]), __dmul_rn(y, a[ord]));
+  z[ORD - 1] = __dsub_rn(__dmul_rn(x, b[ORD]), __dmul_rn(y, a[ORD]));
   return y;
 }
 
 #define K2E_T 32                        // samples per segment and round (one 256-byte row per segment)
 #define K2E_LD (K2E_T + 1)              // row stride in shared memory: lane l reads row l -> bank (l + t) mod 32
+#define K2E_NT 64                       // warp 0 walks the chains, warp 1 moves the rows
 
-// One pass of the 32 segments of a warp over their samples: logical sample i of a segment is in[i] (REV:
-// in[n - 1 - i]).  Rounds of 32 samples: the 32 rows (one per segment, 256 contiguous bytes each) of the NEXT round
-// are fetched by asynchronous copies of the whole warp (lane t fetches column t: coalesced) while every lane walks
-// its own row of the current round from shared memory; the outputs go back the same way.  s_in / s_n hold the
-// segments' base pointers and lengths.
-template <int ORD, bool REV>
-__device__ __forceinline__ void exact_pass(const double* const* s_in, double* const* s_out, const long long* s_n,
-                                           long long n_max, double (*tin)[K2E_T][K2E_LD], double (*tout)[K2E_LD],
-                                           const double* b, const double* a, double* z, long long n, bool zon,
-                                           double mean, const ExactDiv& sd, int lane) {
-  auto fetch = [&](long long r, int buf) {
-    const long long i = r * K2E_T + lane;                 // logical index of my column in every row
-#pragma unroll 4
-    for (int sgm = 0; sgm < 32; ++sgm) {
-      const long long ns = s_n[sgm];
-      if (i < ns) {
-        const double* src = s_in[sgm] + (REV ? ns - 1 - i : i);
-#ifdef AEW_EMUL
-        tin[buf][sgm][lane] = *src;
-#else
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(&tin[buf][sgm][lane])), "l"(src) : "memory");
-#endif
-      }
-    }
-#ifndef AEW_EMUL
-    asm volatile("cp.async.commit_group;" ::: "memory");
-#endif
-  };
-  const long long rounds = (n_max + K2E_T - 1) / K2E_T;
-  if (rounds > 0) fetch(0, 0);
-  for (long long r = 0; r < rounds; ++r) {
-    const int buf = (int)(r & 1);
-    if (r + 1 < rounds) fetch(r + 1, buf ^ 1);             // (its buffer was last read in round r - 1: barrier below)
-#ifndef AEW_EMUL
-    if (r + 1 < rounds) asm volatile("cp.async.wait_group 1;" ::: "memory");
-    else asm volatile("cp.async.wait_group 0;" ::: "memory");
-#endif
-    __syncwarp();
-    const long long i0 = r * K2E_T;
-    if (i0 < n) {
-      const int cnt = (int)(n - i0 < K2E_T ? n - i0 : K2E_T);
-      const double* row = tin[buf][lane];
-      double* orow = tout[lane];
-      double c = row[0];
-#pragma unroll 4
-      for (int t = 0; t < cnt; ++t) {
-        const double nx = row[t + 1];                      // (one pad column: in bounds; fetched before the chain)
-        const double x = zs(c, zon, mean, sd);
-        const double y = __dadd_rn(z[0], __dmul_rn(b[0], x));
+struct alignas(16) K2ESeg { const double* in; double* out; long long n; long long pad_; };   // 32 bytes: two 16-byte loads
+
+// The mover warp's two jobs for one round.  Eight segments at a time: their table entries are loaded first (two
+// 16-byte shared-memory loads each, all independent), then the eight copies are issued -- a lone warp runs in
+// order, and with one load-then-use per row every shared-memory latency was paid in full (profiles/r2_k2_exact_simd.txt:
+// 4,600 cycles per round, short scoreboard + wait).
+template <bool REV>
+__device__ __forceinline__ void exact_fetch(const K2ESeg* tab, long long r, double (*tile)[K2E_LD], int lane) {
+  const long long i = r * K2E_T + lane;                   // logical index of my column in every row
+#pragma unroll 1
+  for (int g = 0; g < 32; g += 8) {
+    const double* p[8];
+    long long ns[8];
 #pragma unroll
-        for (int k = 0; k < ORD - 1; ++k)
-          z[k] = __dsub_rn(__dadd_rn(z[k + 1], __dmul_rn(x, b[k + 1])), __dmul_rn(y, a[k + 1]));
-        z[ORD - 1] = __dsub_rn(__dmul_rn(x, b[ORD]), __dmul_rn(y, a[ORD]));
-        orow[t] = y;
-        c = nx;
+    for (int u = 0; u < 8; ++u) { p[u] = tab[g + u].in; ns[u] = tab[g + u].n; }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (i < ns[u]) {
+        const double* src = p[u] + (REV ? ns[u] - 1 - i : i);
+#ifdef AEW_EMUL
+        tile[g + u][lane] = *src;
+#else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(&tile[g + u][lane])), "l"(src));
+#endif
       }
     }
-    __syncwarp();
-    {
-      const long long i = i0 + lane;
-#pragma unroll 4
-      for (int sgm = 0; sgm < 32; ++sgm) {
-        const long long ns = s_n[sgm];
-        if (i < ns) s_out[sgm][REV ? ns - 1 - i : i] = tout[sgm][lane];
-      }
-    }
-    __syncwarp();
+  }
+#ifndef AEW_EMUL
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <bool REV>
+__device__ __forceinline__ void exact_store(const K2ESeg* tab, long long r, const double (*tile)[K2E_LD], int lane) {
+  const long long i = r * K2E_T + lane;
+#pragma unroll 1
+  for (int g = 0; g < 32; g += 8) {
+    double* p[8];
+    long long ns[8];
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { p[u] = tab[g + u].out; ns[u] = tab[g + u].n; v[u] = tile[g + u][lane]; }
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (i < ns[u]) p[u][REV ? ns[u] - 1 - i : i] = v[u];
   }
 }
 
+// One pass of the block's 32 segments: logical sample i of a segment is in[i] (REV: in[n - 1 - i]).  Rounds of 32
+// samples; in round r warp 0 walks row `lane` of tile r & 1 (every lane its own segment's chain) while warp 1
+// fetches the rows of round r + 1 into the other tile (asynchronous copies, lane t takes column t: coalesced) and
+// stores the outputs of round r - 1.  One block barrier per round.
+template <int ORD, bool REV>
+__device__ __forceinline__ void exact_pass(const K2ESeg* tab, long long n_max, double (*tin)[K2E_T][K2E_LD],
+                                           double (*tout)[K2E_T][K2E_LD], const double (&b)[5], const double (&a)[5],
+                                           double (&z)[4], long long n, bool zon, double mean, const ExactDiv& sd,
+                                           int warp, int lane) {
+  const long long rounds = (n_max + K2E_T - 1) / K2E_T;
+  if (warp == 1 && rounds > 0) {
+    exact_fetch<REV>(tab, 0, tin[0], lane);
+#ifndef AEW_EMUL
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+  }
+  __syncthreads();
+  for (long long r = 0; r < rounds; ++r) {
+    const int buf = (int)(r & 1);
+    if (warp == 0) {
+      const long long i0 = r * K2E_T;
+      if (i0 < n) {
+        const int cnt = (int)(n - i0 < K2E_T ? n - i0 : K2E_T);
+        const double* row = tin[buf][lane];
+        double* orow = tout[buf][lane];
+        double c = row[0];
+#pragma unroll 4
+        for (int t = 0; t < cnt; ++t) {
+          const double nx = row[t + 1];                    // (one pad column: in bounds; fetched before the chain)
+          const double x = zs(c, zon, mean, sd);
+          const double y = __dadd_rn(z[0], __dmul_rn(b[0], x));
+#pragma unroll
+          for (int k = 0; k < ORD - 1; ++k)
+            z[k] = __dsub_rn(__dadd_rn(z[k + 1], __dmul_rn(x, b[k + 1])), __dmul_rn(y, a[k + 1]));
+          z[ORD - 1] = __dsub_rn(__dmul_rn(x, b[ORD]), __dmul_rn(y, a[ORD]));
+          orow[t] = y;
+          c = nx;
+        }
+      }
+    } else {
+      if (r + 1 < rounds) exact_fetch<REV>(tab, r + 1, tin[buf ^ 1], lane);
+      if (r > 0) exact_store<REV>(tab, r - 1, tout[buf ^ 1], lane);
+#ifndef AEW_EMUL
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+    }
+    __syncthreads();
+  }
+  if (warp == 1 && rounds > 0) exact_store<REV>(tab, rounds - 1, tout[(rounds - 1) & 1], lane);
+  __syncthreads();
+}
+
 template <int ORD>
-__global__ void __launch_bounds__(32) k2_exact(PassArgs a) {
+__global__ void __launch_bounds__(K2E_NT) k2_exact(PassArgs a) {
   __shared__ double tin[2][K2E_T][K2E_LD];
-  __shared__ double tout[K2E_T][K2E_LD];
-  __shared__ const double* s_src[32];
-  __shared__ double* s_tmp[32];
-  __shared__ double* s_dst[32];
-  __shared__ long long s_n[32];
+  __shared__ double tout[2][K2E_T][K2E_LD];
+  __shared__ K2ESeg s_fwd[32];                           // src -> tmp
+  __shared__ K2ESeg s_bwd[32];                           // tmp -> out
+  __shared__ long long s_nmax;
   const long long n_seg = a.ws.hdr[H_SEG_COUNT] < a.ws.max_seg ? a.ws.hdr[H_SEG_COUNT] : a.ws.max_seg;
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long seg = (long long)blockIdx.x * 32 + lane;
   const bool have = seg < n_seg;
   const long long* sg = a.ws.segs + 4 * (have ? seg : 0);
@@ -840,37 +874,49 @@ __global__ void __launch_bounds__(32) k2_exact(PassArgs a) {
   const ExactDiv sd = make_exact_div(zon ? a.sd[rec] : 1.0);
   const int pad = (int)a.tab[K2_TAB_PAD];
   double b[5], ac[5], zi[4], z[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
   for (int i = 0; i < 5; ++i) { b[i] = a.tab[K2_TAB_B + i]; ac[i] = a.tab[K2_TAB_A + i]; }
+#pragma unroll
   for (int i = 0; i < 4; ++i) zi[i] = a.tab[K2_TAB_ZI + i];
   const double* xs = a.src + g0;
   double* out = a.passthrough + g0;
   double* tmp = a.dst + g0;
-  if (have && n <= pad) {                                // filters.py:50-51: too short to filter, copied through
-    for (long long i = 0; i < n; ++i) out[i] = zs(xs[i], zon, mean, sd);
-    n = 0;                                               // (takes no further part, but stays with its warp)
+  if (warp == 0) {
+    if (have && n <= pad) {                              // filters.py:50-51: too short to filter, copied through
+      for (long long i = 0; i < n; ++i) out[i] = zs(xs[i], zon, mean, sd);
+      n = 0;                                             // (takes no further part, but stays with its warp)
+    }
+    s_fwd[lane].in = xs; s_fwd[lane].out = tmp; s_fwd[lane].n = n;
+    s_bwd[lane].in = tmp; s_bwd[lane].out = out; s_bwd[lane].n = n;
+    const long long m = (long long)__reduce_max_sync(AEW_FULL, (unsigned)(n > 0x7fffffffll ? 0x7fffffffll : n));
+    if (lane == 0) s_nmax = m;
+  } else {
+    n = 0;
   }
-  s_src[lane] = xs; s_tmp[lane] = tmp; s_dst[lane] = out; s_n[lane] = n;
-  const long long n_max = (long long)__reduce_max_sync(AEW_FULL, (unsigned)(n > 0x7fffffffll ? 0x7fffffffll : n));
-  __syncwarp();
+  __syncthreads();
+  const long long n_max = s_nmax;
   double ve[K2_MAXPAD];
   double x0 = 0.0, xl = 0.0;
-  if (n > 0) {                                           // odd extension on the left, zi scaled by its first sample
+  if (warp == 0 && n > 0) {                              // odd extension on the left, zi scaled by its first sample
     x0 = zs(xs[0], zon, mean, sd); xl = zs(xs[n - 1], zon, mean, sd);
     const double e0 = __dsub_rn(__dmul_rn(2.0, x0), zs(xs[pad], zon, mean, sd));
+#pragma unroll
     for (int i = 0; i < ORD; ++i) z[i] = __dmul_rn(zi[i], e0);
     for (int e = 0; e < pad; ++e)
-      df2t_step_exact(b, ac, ORD, __dsub_rn(__dmul_rn(2.0, x0), zs(xs[pad - e], zon, mean, sd)), z);
+      df2t_step_exact<ORD>(b, ac, __dsub_rn(__dmul_rn(2.0, x0), zs(xs[pad - e], zon, mean, sd)), z);
   }
-  exact_pass<ORD, false>(s_src, s_tmp, s_n, n_max, tin, tout, b, ac, z, n, zon, mean, sd, lane);
-  if (n > 0) {                                           // right extension, then the backward pass starts inside it
+  exact_pass<ORD, false>(s_fwd, n_max, tin, tout, b, ac, z, n, zon, mean, sd, warp, lane);
+  if (warp == 0 && n > 0) {                              // right extension, then the backward pass starts inside it
     for (int m = 0; m < pad; ++m)
-      ve[m] = df2t_step_exact(b, ac, ORD, __dsub_rn(__dmul_rn(2.0, xl), zs(xs[n - 2 - m], zon, mean, sd)), z);
-    for (int i = 0; i < ORD; ++i) z[i] = __dmul_rn(zi[i], ve[pad - 1]);
-    for (int e = 0; e < pad; ++e) df2t_step_exact(b, ac, ORD, ve[pad - 1 - e], z);
+      ve[m] = df2t_step_exact<ORD>(b, ac, __dsub_rn(__dmul_rn(2.0, xl), zs(xs[n - 2 - m], zon, mean, sd)), z);
+    const double vl = ve[pad - 1];
+#pragma unroll
+    for (int i = 0; i < ORD; ++i) z[i] = __dmul_rn(zi[i], vl);
+    for (int e = 0; e < pad; ++e) df2t_step_exact<ORD>(b, ac, ve[pad - 1 - e], z);
   }
-  __threadfence_block();                                 // the warp's stores to tmp before the copies that read them
-  __syncwarp();
-  exact_pass<ORD, true>((const double* const*)s_tmp, s_dst, s_n, n_max, tin, tout, b, ac, z, n, false, 0.0, sd, lane);
+  __threadfence_block();                                 // the block's stores to tmp before the copies that read them
+  __syncthreads();
+  exact_pass<ORD, true>(s_bwd, n_max, tin, tout, b, ac, z, n, false, 0.0, sd, warp, lane);
 }
 
 unsigned long long* g_dbg = nullptr;   // device counters, allocated once when AEW_K2_TIMING is set
@@ -945,10 +991,10 @@ extern "C" int aew_filtfilt_f64(const double* src, const double* mean, const dou
   if (mode == 1) {                                       // one lane per segment (lanes beyond the count exit)
     const long long blocks = (max_seg + 31) / 32;
     switch ((int)h_tab[K2_TAB_ORDER]) {
-      case 1: AEW_LAUNCH(k2_exact<1>, (unsigned)blocks, 32, 0, st, a); break;
-      case 2: AEW_LAUNCH(k2_exact<2>, (unsigned)blocks, 32, 0, st, a); break;
-      case 3: AEW_LAUNCH(k2_exact<3>, (unsigned)blocks, 32, 0, st, a); break;
-      case 4: AEW_LAUNCH(k2_exact<4>, (unsigned)blocks, 32, 0, st, a); break;
+      case 1: AEW_LAUNCH(k2_exact<1>, (unsigned)blocks, K2E_NT, 0, st, a); break;
+      case 2: AEW_LAUNCH(k2_exact<2>, (unsigned)blocks, K2E_NT, 0, st, a); break;
+      case 3: AEW_LAUNCH(k2_exact<3>, (unsigned)blocks, K2E_NT, 0, st, a); break;
+      case 4: AEW_LAUNCH(k2_exact<4>, (unsigned)blocks, K2E_NT, 0, st, a); break;
       default: return AEW_ERR_UNSUPPORTED;
     }
     return (int)cudaGetLastError();

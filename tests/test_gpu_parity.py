@@ -800,10 +800,15 @@ def test_full_size_properties_1000_cases(gpu):
     # affine invariance of the z-scored path: 3 x + 7 gives the same windows and (to rounding) the same beats
     flat.mul_(3.0).add_(7.0)
     aff = pre.run(B.RecordBatch(flat, off, ids), scratch=scratch)
-    assert aff["np_waves"].shape[0] >= n - 5 and aff["np_waves"].shape[0] <= n + 5     # sd/n_peaks ulp hazard only
-    if aff["np_waves"].shape[0] == n:
-        assert torch.equal(aff["np_info"], info)
-        assert float((aff["np_waves"] - waves).abs().max()) < 1e-5
+    # 3 x + 7 rounds differently inside the z-score, so np.std of a 20-peak window may land on the other side of
+    # 1.0 -- in the reference just the same; every OTHER window must keep its decision and its beat
+    same_fate = (aff["keep"] == res["keep"]) | (res["n_peaks"] == 20)
+    assert bool(same_fate.all())
+    if int(res["keep"].sum()) == n:                            # (no window dropped by the delineation stage)
+        both = (aff["keep"] & res["keep"]).bool()
+        a_rows = aff["np_waves"][both[aff["keep"].bool()]]
+        r_rows = waves[both[res["keep"].bool()]]
+        assert a_rows.shape == r_rows.shape and float((a_rows - r_rows).abs().max()) < 1e-5
 
 
 # ------------------------------------------------------------------------- configs[2]: 12-lead 10 s strips
