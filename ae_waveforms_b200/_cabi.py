@@ -54,6 +54,7 @@ SIGNATURES = {
                                       c_void_p, c_size_t, c_longlong, c_void_p]),
     "aew_filtfilt_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong,
                                  c_longlong, c_void_p, c_size_t, c_longlong, c_int, c_void_p]),
+    "aew_filt_fused_ok": (c_int, [c_void_p]),
     "aew_filt_header": (c_int, [c_void_p, c_void_p]),
     "aew_filt_timing_dump": (c_int, [c_void_p]),
     "aew_windows_max_peaks": (c_int, []),

@@ -154,6 +154,8 @@ class Preprocessor:
         # windows re-screened from that output, so every keep / remove decision is the reference's bit for bit.
         self.exact_masks = bool(exact_masks) and self.filter_mode == 0
         self.defer_chunks = 6               # run_host_pipelined: chunks finished this many chunks late (exact_masks)
+        self.fuse_passes = bool(int(__import__("os").environ.get("AEW_K2_FUSE", "1")))   # short-memory filters:
+                                            # forward + backward in one launch (k2_fused); 0 = two launches
         self.lazy_sd = True                 # run(): 'ecg_sd' is not an output; evaluate it only where it decides
         # the screen kernel parks the z-scored windows in the filter scratch for the median kernel (measured: 30.1 ms
         # per 179,000 windows against 32.5 when the median kernel re-derives them; profiles/k3_variants.py)
@@ -235,7 +237,11 @@ class Preprocessor:
     def filter_records(self, flat, beg_h, end_h, d_beg, d_end, mean=None, sd=None, cnt=None, out=None, tmp=None,
                        mode=None, max_seg=None):
         """K2: z-score (fused) + high-pass + low-pass per NaN-delimited segment.
-        Returns (filtered, device header tensor).  ``mode`` overrides the object's filter mode (0 tiled, 1 exact)."""
+        Returns (filtered, device header tensor).  ``mode`` overrides the object's filter mode (0 tiled, 1 exact with
+        one lane per segment, 3 exact with one warp per segment).  The filtered signal comes back in ``out`` OR in
+        ``tmp``: a stage whose filter has a short memory (the 30 Hz low-pass) runs forward and backward in ONE launch
+        from one buffer into the other, so the two buffers may change roles; the other one is the scratch
+        (``self._filter_tmp`` when ``mode`` is None)."""
         torch, lib = self.torch, self.lib
         n_rec, total = len(beg_h), flat.numel()
         max_seg = max_seg or self.max_segments or (4 * n_rec + 4096)
@@ -243,24 +249,43 @@ class Preprocessor:
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
         y = torch.empty_like(flat) if out is None else out
         tmp = torch.empty_like(flat) if tmp is None else tmp
-        if mode is None:
-            self._filter_tmp = tmp              # free again once the filter is done: scratch for the window kernels
         filter_mode = self.filter_mode if mode is None else mode
         st = _cabi.stream_ptr(torch)
-        _cabi.check(lib.aew_segments_find_f64(_ptr(flat), _ptr(d_beg), _ptr(d_end), n_rec, total, _ptr(cnt), _ptr(y),
-                                              _ptr(ws), ws_bytes, max_seg, st), "segments_find")
-        self.launches += 1
         stages = [d for d in (self.hp and design_filter("high", self.hp, self.fs, self.order, self.device),
                               self.lp and design_filter("low", self.lp, self.fs, self.order, self.device)) if d]
-        src, m, s = flat, mean, sd
-        for d in stages:
+        # plan: which stage takes the one-launch form, and in which buffer the result ends up (that one gets the NaN
+        # fill at NaN inputs; the kernels write segment samples only)
+        fused = [filter_mode == 0 and self.fuse_passes and d.fast_ok and bool(lib.aew_filt_fused_ok(_np_ptr(d.table_host)))
+                 for d in stages]
+        bufs = [y, tmp]
+        where, cur = 0, -1                                   # cur: -1 = the input, 0 / 1 = bufs[.]
+        for f in fused:
+            if f:
+                where = 1 - cur if cur >= 0 else 0
+            else:
+                where = cur if cur >= 0 else 0
+            cur = where
+        final = bufs[where]
+        _cabi.check(lib.aew_segments_find_f64(_ptr(flat), _ptr(d_beg), _ptr(d_end), n_rec, total, _ptr(cnt),
+                                              _ptr(final), _ptr(ws), ws_bytes, max_seg, st), "segments_find")
+        self.launches += 1
+        src, m, s, cur = flat, mean, sd, -1
+        for d, f in zip(stages, fused):
             if filter_mode == 0 and not d.fast_ok:
                 raise _cabi.AewError(f"{d}: no modal form; use filter_mode='exact'")
-            _cabi.check(lib.aew_filtfilt_f64(_ptr(src), _ptr(m), _ptr(s), _ptr(y), _ptr(tmp), _ptr(d.table),
-                                             _np_ptr(d.table_host), n_rec, total, _ptr(ws), ws_bytes, max_seg,
-                                             filter_mode, st), "filtfilt")
-            self.launches += 1 if filter_mode else 2
-            src, m, s = y, None, None
+            if f:                                            # one launch, src -> the buffer src is not in
+                dst = 1 - cur if cur >= 0 else 0
+                _cabi.check(lib.aew_filtfilt_f64(_ptr(src), _ptr(m), _ptr(s), _ptr(bufs[dst]), _ptr(bufs[1 - dst]),
+                                                 _ptr(d.table), _np_ptr(d.table_host), n_rec, total, _ptr(ws),
+                                                 ws_bytes, max_seg, 2, st), "filtfilt (one launch)")
+                self.launches += 1
+            else:                                            # forward into the other buffer, backward into dst
+                dst = cur if cur >= 0 else 0
+                _cabi.check(lib.aew_filtfilt_f64(_ptr(src), _ptr(m), _ptr(s), _ptr(bufs[dst]), _ptr(bufs[1 - dst]),
+                                                 _ptr(d.table), _np_ptr(d.table_host), n_rec, total, _ptr(ws),
+                                                 ws_bytes, max_seg, filter_mode, st), "filtfilt")
+                self.launches += 1 if filter_mode else 2
+            cur, src, m, s = dst, bufs[dst], None, None
         if not stages:                                       # both cut-offs falsy: z-score only
             if mean is not None:
                 _cabi.check(lib.aew_zscore_apply_f64(_ptr(flat), _ptr(d_beg), _ptr(d_end), n_rec, _ptr(mean),
@@ -268,6 +293,9 @@ class Preprocessor:
                 self.launches += 1
             else:
                 y.copy_(flat)
+        y, tmp = final, bufs[1 - where]
+        if mode is None:
+            self._filter_tmp = tmp              # free again once the filter is done: scratch for the window kernels
         off = (-ws.data_ptr()) % 128
         header = ws[off:off + 64].view(torch.int64)
         return y, header
@@ -400,7 +428,8 @@ class Preprocessor:
         return n if n >= 1 and abs(n * self.sd_threshold - 1.0) < 1e-9 else None
 
     @_cabi.on_device
-    def resolve_hazards(self, flat, beg_h, end_h, mean, sd, cnt, win_start, win_rec, scr, zwin_main=None):
+    def resolve_hazards(self, flat, beg_h, end_h, mean, sd, cnt, win_start, win_rec, scr, zwin_main=None,
+                        low_latency=False):
         """exact_masks: windows whose keep / remove decision depends on the last bit of np.std (n_peaks ==
         hazard_peak_count(), every other rule passed) are decided from SciPy-order filter output.  The records that
         hold such windows are gathered into a compact batch, filtered by the sequential kernel (bit-identical to
@@ -453,7 +482,8 @@ class Preprocessor:
             side.wait_event(ready)
             yc, tc = torch.empty_like(xc), torch.empty_like(xc)
             self.filter_records(xc, coff[:-1].copy(), coff[1:].copy(), d_off[:-1].contiguous(), d_off[1:].contiguous(),
-                                m_c, s_c, n_c, out=yc, tmp=tc, mode=1, max_seg=len(recs) if clean else None)
+                                m_c, s_c, n_c, out=yc, tmp=tc, mode=3 if low_latency else 1,
+                                max_seg=len(recs) if clean else None)
             scr2 = self.screen_windows(yc, start_c, zwin_scratch=tc if tc.numel() >= len(hz_h) * L else None,
                                        d_start=d_start_c)
             changed = (scr2["keep"] != scr["keep"].index_select(0, hz_idx)).sum()
@@ -472,11 +502,14 @@ class Preprocessor:
     # ------------------------------------------------------------------ whole path
     @_cabi.on_device
     def run(self, batch: RecordBatch, trim: bool = True, keep_intermediates: bool = False,
-            scratch: dict | None = None, features: bool = False, strips: bool = False, defer: bool = False):
+            scratch: dict | None = None, features: bool = False, strips: bool = False, defer: bool = False,
+            low_latency: bool = False):
         """Returns a dict of CUDA tensors: ``np_waves`` (n_keep, 320) float32,
         ``np_info`` (n_keep, 2) float64 = [case_id, idx_end], ``medians`` float64,
         plus per-window ``keep`` / ``has_nan`` / ``n_peaks`` / ``peaks`` / ``stats`` and
         counters.  ``scratch`` may hold reusable 'y' / 'tmp' tensors shaped like the input.
+        ``low_latency``: the exact-mask pass uses one warp per segment (half the wait, 32 x the issue slots: for callers
+        whose device is otherwise idle, such as the PCIe-bound feeder).
         ``defer``: return a pending handle right after the kernels have been launched; ``finish(handle)`` gives the
         result.  With exact_masks the sequential re-filtering of the 20-peak records (side stream, ~100 ms of
         latency whatever the batch size) then overlaps the NEXT batches' kernels instead of idling the device."""
@@ -509,7 +542,7 @@ class Preprocessor:
         hz = None
         if self.exact_masks:
             hz = self.resolve_hazards(flat, beg_h, end_h, mean, sd, cnt, win_start, win_rec, scr,
-                                      zwin_main=tmp if features else None)
+                                      zwin_main=tmp if features else None, low_latency=low_latency)
         pend = dict(scr=scr, hz=hz, info=info, header=header, features=features, tmp=tmp, y=y, n_win=len(win_start),
                     mean=mean, sd=sd, keep_intermediates=keep_intermediates, beg_h=beg_h, end_h=end_h,
                     win_start=win_start, flat=flat, cnt=cnt)
@@ -789,7 +822,7 @@ def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chu
         sub = RecordBatch(chunk_in, np.concatenate([[0], np.cumsum(lens_rec[recs_k])]).astype(np.int64),
                           case_ids[recs_k])
         sc = {"y": scratch["y"][:sizes[k]], "tmp": scratch["tmp"][:sizes[k]]}
-        pending.append(pre.run(sub, scratch=sc, features=features, defer=depth > 0))
+        pending.append(pre.run(sub, scratch=sc, features=features, defer=depth > 0, low_latency=True))
         if not narrow:
             freed[k].record(main)                              # (the hazard records have been copied out by now)
         while len(pending) > depth:

@@ -726,6 +726,283 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
   if (tid == K2_PRODUCER) bulk_store_wait_all();
 }
 
+// SciPy's lfilter step (direct form II transposed), separate multiply and add.  ORD is a template parameter and every
+// loop over the state is unrolled: with run-time indices b, a and z would live in local memory.
+template <int ORD>
+__device__ __forceinline__ double df2t_step_exact(const double (&b)[5], const double (&a)[5], double x, double (&z)[4]) {
+  const double y = __dadd_rn(z[0], __dmul_rn(b[0], x));
+#pragma unroll
+  for (int k = 0; k < ORD - 1; ++k)
+    z[k] = __dsub_rn(__dadd_rn(z[k + 1], __dmul_rn(x, b[k + 1])), __dmul_rn(y, a[k + 1]));
+  z[ORD - 1] = __dsub_rn(__dmul_rn(x, b[ORD]), __dmul_rn(y, a[ORD]));
+  return y;
+}
+
+// ------------------------------------------------------------ exact mode, low-latency form
+// One WARP per segment: lane 0 walks the chain, all lanes load the next 64 samples, z-score them, form the products
+// b[k] x into shared memory and store the outputs.  44 cycles per sample -- half the latency of the lane-per-segment
+// form below, whose chain warp also carries the products and the z-score -- at 32 x its issue slots.  Used where the
+// device has nothing else to do and the wait is what counts: the end-to-end feeder (PCIe-bound, the last chunk's
+// pass is a tail of the call).
+#define K2W_NT 32                       // one WARP per segment (the low-latency form)
+#define K2W_BLK 64                      // samples per round: two per lane (halves the rounds' fixed cost)
+// one pass over n samples: logical sample i is in[i] (REV: in[n - 1 - i]); lane 0 owns the state z
+template <int ORD, bool REV>
+__device__ __forceinline__ void exact_stream_warp(const double* in, double* out, long long n, const double* b,
+                                             const double* a, double* z, bool zon, double mean, const ExactDiv& sd,
+                                             double (*sp)[K2W_BLK + 2], double* sy, int lane) {
+  double v0 = 0.0, v1 = 0.0;
+  if (lane < n) v0 = in[REV ? n - 1 - lane : lane];
+  if (lane + 32 < n) v1 = in[REV ? n - 1 - (lane + 32) : lane + 32];
+  for (long long i0 = 0; i0 < n; i0 += K2W_BLK) {
+    const long long j0 = i0 + K2W_BLK + lane, j1 = j0 + 32;   // the next round is in flight while lane 0 works
+    double w0 = 0.0, w1 = 0.0;
+    if (j0 < n) w0 = in[REV ? n - 1 - j0 : j0];
+    if (j1 < n) w1 = in[REV ? n - 1 - j1 : j1];
+    const double x0 = zs(v0, zon, mean, sd), x1 = zs(v1, zon, mean, sd);
+#pragma unroll
+    for (int k = 0; k <= ORD; ++k) { sp[k][lane] = __dmul_rn(b[k], x0); sp[k][lane + 32] = __dmul_rn(b[k], x1); }
+    __syncwarp();
+    if (lane == 0) {
+      const int cnt = (int)(n - i0 < K2W_BLK ? n - i0 : K2W_BLK);
+      // the products of the next two samples are fetched BEFORE this sample's dependent chain (DADD, DMUL, DADD)
+      // is issued: an in-order warp would otherwise expose one shared-memory latency per sample
+      double c[ORD + 1], c1[ORD + 1];
+#pragma unroll
+      for (int k = 0; k <= ORD; ++k) { c[k] = sp[k][0]; c1[k] = sp[k][1]; }
+#pragma unroll 4
+      for (int t = 0; t < cnt; ++t) {
+        double c2[ORD + 1];
+#pragma unroll
+        for (int k = 0; k <= ORD; ++k) c2[k] = sp[k][t + 2];          // (the two pad columns keep this in bounds)
+        const double y = __dadd_rn(z[0], c[0]);
+#pragma unroll
+        for (int k = 0; k < ORD - 1; ++k) z[k] = __dsub_rn(__dadd_rn(z[k + 1], c[k + 1]), __dmul_rn(y, a[k + 1]));
+        z[ORD - 1] = __dsub_rn(c[ORD], __dmul_rn(y, a[ORD]));
+        sy[t] = y;
+#pragma unroll
+        for (int k = 0; k <= ORD; ++k) { c[k] = c1[k]; c1[k] = c2[k]; }
+      }
+    }
+    __syncwarp();
+    if (i0 + lane < n) out[REV ? n - 1 - (i0 + lane) : i0 + lane] = sy[lane];
+    if (i0 + lane + 32 < n) out[REV ? n - 1 - (i0 + lane + 32) : i0 + lane + 32] = sy[lane + 32];
+    __syncwarp();
+    v0 = w0; v1 = w1;
+  }
+}
+
+template <int ORD>
+__global__ void __launch_bounds__(K2W_NT) k2_exact_warp(PassArgs a) {
+  __shared__ double sp[ORD + 1][K2W_BLK + 2];
+  __shared__ double sy[K2W_BLK];
+  const long long n_seg = a.ws.hdr[H_SEG_COUNT] < a.ws.max_seg ? a.ws.hdr[H_SEG_COUNT] : a.ws.max_seg;
+  const long long seg = blockIdx.x;
+  const int lane = threadIdx.x;
+  if (seg >= n_seg) return;
+  const long long* sg = a.ws.segs + 4 * seg;
+  const long long g0 = sg[0], n = sg[1], rec = sg[2];
+  const bool zon = a.mean != nullptr;
+  const double mean = zon ? a.mean[rec] : 0.0;
+  const ExactDiv sd = make_exact_div(zon ? a.sd[rec] : 1.0);
+  const int pad = (int)a.tab[K2_TAB_PAD];
+  double b[5], ac[5], zi[4], z[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int i = 0; i < 5; ++i) { b[i] = a.tab[K2_TAB_B + i]; ac[i] = a.tab[K2_TAB_A + i]; }
+  for (int i = 0; i < 4; ++i) zi[i] = a.tab[K2_TAB_ZI + i];
+  const double* xs = a.src + g0;
+  double* out = a.passthrough + g0;
+  double* tmp = a.dst + g0;
+  if (n <= pad) {                                        // filters.py:50-51: too short to filter, copied through
+    for (long long i = lane; i < n; i += K2W_NT) out[i] = zs(xs[i], zon, mean, sd);
+    return;
+  }
+  double ve[K2_MAXPAD];
+  const double x0 = zs(xs[0], zon, mean, sd), xl = zs(xs[n - 1], zon, mean, sd);
+  if (lane == 0) {                                       // odd extension on the left, zi scaled by its first sample
+    const double e0 = __dsub_rn(__dmul_rn(2.0, x0), zs(xs[pad], zon, mean, sd));
+    for (int i = 0; i < ORD; ++i) z[i] = __dmul_rn(zi[i], e0);
+    for (int e = 0; e < pad; ++e)
+      df2t_step_exact<ORD>(b, ac, __dsub_rn(__dmul_rn(2.0, x0), zs(xs[pad - e], zon, mean, sd)), z);
+  }
+  exact_stream_warp<ORD, false>(xs, tmp, n, b, ac, z, zon, mean, sd, sp, sy, lane);
+  if (lane == 0) {                                       // right extension, then the backward pass starts inside it
+    for (int m = 0; m < pad; ++m)
+      ve[m] = df2t_step_exact<ORD>(b, ac, __dsub_rn(__dmul_rn(2.0, xl), zs(xs[n - 2 - m], zon, mean, sd)), z);
+    for (int i = 0; i < ORD; ++i) z[i] = __dmul_rn(zi[i], ve[pad - 1]);
+    for (int e = 0; e < pad; ++e) df2t_step_exact<ORD>(b, ac, ve[pad - 1 - e], z);
+  }
+  __syncwarp();                                          // (orders the warp's stores to tmp before the reads below)
+  exact_stream_warp<ORD, true>(tmp, out, n, b, ac, z, false, 0.0, sd, sp, sy, lane);
+}
+
+// ------------------------------------------------------------ forward + backward in one launch
+// A filter whose memory is short (the 30 Hz low-pass: |p| <= 0.868, a state error is below 1e-18 after 300
+// samples) needs neither published tile states nor a look-back: a block takes a 3,328-sample tile TOGETHER with a
+// halo of 416 samples on either side, runs the forward pass over the 4,160 samples from a zero state (the real
+// initial state at a segment's first sample), reverses them in shared memory, runs the backward pass the same way
+// (the real initial state at a segment's last sample, from the odd extension), and stores the middle.  One launch
+// instead of two, 8 B read + 8 B written per sample instead of 32 (the halo re-reads come from L2), no dependency
+// between tiles.  The 1 Hz high-pass (|p| = 0.995, ~8,000 samples of memory) stays with k2_pass.
+#define K2F_NT 320                      // ten warps: warp 0 and warp 9 hold the two halos of an interior tile
+#define K2F_NW (K2F_NT / 32)
+#define K2F_H (32 * K2_C)               // 416
+#define K2F_R (K2F_NT * K2_C)           // 4160 = K2_T + 2 * K2F_H
+
+// One pass over buf[0 .. K2F_R) in place: zero-state recursion per 13-sample chunk, scan of the chunk end states
+// over the warp and over the ten warps, outputs corrected with the zero-input response of the entering state.
+// S0 (shared memory, 4 doubles) is the state entering sample 0, used when `first`.  Returns the state entering the
+// caller's chunk (needed for the right extension).
+__device__ __forceinline__ void fused_pass(const PassArgs& a, const double* s_tab, double* buf, double* s_W,
+                                           const double* S0, bool first, int tid, double s_out[4]) {
+  const int lane = tid & 31, warp = tid >> 5;
+  const Modal& cf = a.cf;
+  double E[4] = {0.0, 0.0, 0.0, 0.0};
+  double* mine = buf + tid * K2_C;
+#pragma unroll
+  for (int j = 0; j < K2_C; ++j) mine[j] = modal_step(cf, mine[j], E);
+  const double Eown[4] = {E[0], E[1], E[2], E[3]};
+#pragma unroll
+  for (int kk = 0; kk < 5; ++kk) {                       // inclusive scan of the chunk end states over the warp
+    const int dd = 1 << kk;
+    double o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = __shfl_up_sync(AEW_FULL, E[i], dd);
+    if (lane >= dd) cmul_acc(a.cPK + 4 * kk, o, E);
+  }
+  if (lane == 31) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s_W[4 * warp + i] = E[i];
+  }
+  __syncthreads();
+  // every warp scans the ten warp totals for itself: state entering warp w = sum_{v < w} p^(32 C (w - 1 - v)) W_v
+  const double* PWP = s_tab + K2_TAB_PWP;                // p^(32 C m), m = 0 .. K2_NW (= 8)
+  double I[4] = {0.0, 0.0, 0.0, 0.0};
+  if (lane < K2F_NW) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) I[i] = s_W[4 * lane + i];
+  }
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    const int dd = 1 << kk;
+    double o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = __shfl_up_sync(AEW_FULL, I[i], dd);
+    if (lane >= dd && lane < K2F_NW) cmul_acc(PWP + 4 * dd, o, I);
+  }
+  double X[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) X[i] = __shfl_sync(AEW_FULL, I[i], warp > 0 ? warp - 1 : 0);
+  if (warp == 0) { X[0] = X[1] = X[2] = X[3] = 0.0; }
+  if (first) {                                           // + p^(32 C w) S0
+    const double s0[4] = {S0[0], S0[1], S0[2], S0[3]};
+    if (warp <= K2_NW) {
+      cmul_acc(PWP + 4 * warp, s0, X);
+    } else {                                             // p^(32 C 9) = p^(32 C 8) p^(32 C)
+      const double* P8 = PWP + 4 * K2_NW;
+      const double* P1 = PWP + 4;
+      const double P9[4] = {P8[0] * P1[0] - P8[1] * P1[1], P8[0] * P1[1] + P8[1] * P1[0],
+                            P8[2] * P1[2] - P8[3] * P1[3], P8[2] * P1[3] + P8[3] * P1[2]};
+      cmul_acc(P9, s0, X);
+    }
+  }
+  // state entering my chunk = p^(C lane) X + inclusive scan of the lane before me
+  double sc[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) sc[i] = __shfl_up_sync(AEW_FULL, E[i], 1);
+  if (lane == 0) { sc[0] = sc[1] = sc[2] = sc[3] = 0.0; }
+  cmul_acc(s_tab + K2_TAB_PLANE + 4 * lane, X, sc);
+  (void)Eown;
+  const double* G = a.cG;
+#pragma unroll
+  for (int j = 0; j < K2_C; ++j)
+    mine[j] = fma(G[4 * j + 3], sc[3], fma(G[4 * j + 2], sc[2], fma(G[4 * j + 1], sc[1], fma(G[4 * j], sc[0], mine[j]))));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s_out[i] = sc[i];
+}
+
+__global__ void __launch_bounds__(K2F_NT, 3) k2_fused(PassArgs a) {
+  AEW_DYN_SMEM(smem_raw);
+  double* buf0 = (double*)smem_raw;                     // [K2F_R] forward pass, in place
+  double* buf1 = buf0 + K2F_R;                          // [K2F_R] the reversed forward output, backward pass in place
+  double* s_tab = buf1 + K2F_R;                         // [K2_TAB_LEN]
+  double* s_W = s_tab + K2_TAB_LEN;                     // [K2F_NW][4]
+  double* s_in = s_W + 4 * K2F_NW;                      // [4] state entering the region's first sample (forward)
+  double* s_inb = s_in + 4;                             // [4] state entering its last sample (backward)
+  double* s_ve = s_inb + 4;                             // [16] forward outputs over the right extension
+  __shared__ long long s_tile;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < K2_TAB_LEN; i += K2F_NT) s_tab[i] = a.tab[i];
+  const int pad = (int)a.tab[K2_TAB_PAD];
+  const Modal& cf = a.cf;
+  long long* work = a.ws.hdr + H_WORK_FWD;
+  long long n_tiles = a.ws.hdr[H_TILE_TOTAL];
+  if (n_tiles > a.ws.max_tiles) n_tiles = a.ws.max_tiles;
+  for (;;) {
+    __syncthreads();                                     // (previous tile done with s_tile and the buffers)
+    if (tid == 0) s_tile = (long long)atomicAdd((unsigned long long*)work, 1ull);
+    __syncthreads();
+    const long long tile = s_tile;
+    if (tile >= n_tiles) break;
+    long long rw[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rw[i] = a.ws.tile_desc[4 * tile + i];
+    const long long g0 = rw[0], n = rw[1], rec = rw[2] >> 32, k = rw[3];
+    const bool zon = a.mean != nullptr;
+    const double mean = zon ? a.mean[rec] : 0.0;
+    const ExactDiv sd = make_exact_div(zon ? a.sd[rec] : 1.0);
+    const double inv_sd = zon ? 1.0 / a.sd[rec] : 1.0;
+    if (n <= pad) {                                      // filters.py:50-51: too short, copy through
+      for (long long i = tid; i < n; i += K2F_NT) a.dst[g0 + i] = zs(a.src[g0 + i], zon, mean, sd);
+      continue;
+    }
+    const long long t0 = k * K2_T;
+    const long long remain = n - t0;
+    const int cnt = remain < K2_T ? (int)remain : K2_T;
+    const long long r0 = t0 > K2F_H ? t0 - K2F_H : 0;
+    const long long r1e = t0 + cnt + K2F_H;
+    const long long r1 = r1e < n ? r1e : n;
+    const int len = (int)(r1 - r0);
+    const double* xs = a.src + g0 + r0;
+    for (int j = tid; j < K2F_R; j += K2F_NT) buf0[j] = j < len ? zsf(xs[j], zon, mean, inv_sd) : 0.0;
+    if (r0 == 0 && tid == 0) {                           // the odd extension on the left, from SciPy's zi-scaled state
+      double z[4];
+      const double x0 = zsf(xs[0], zon, mean, inv_sd);
+      modal_initial(s_tab, 2.0 * x0 - zsf(xs[pad], zon, mean, inv_sd), z);
+      for (int e = 0; e < pad; ++e) modal_step(cf, 2.0 * x0 - zsf(xs[pad - e], zon, mean, inv_sd), z);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s_in[i] = z[i];
+    }
+    __syncthreads();
+    double sc[4];
+    fused_pass(a, s_tab, buf0, s_W, s_in, r0 == 0, tid, sc);
+    if (r1 == n) {                                       // the segment ends in this region: right extension outputs
+      const int tl = (len - 1) / K2_C;                   // thread holding the last valid sample
+      if (tid == tl) {
+        const int c = len - tl * K2_C;                   // valid samples in its chunk, 1..C
+        double z[4] = {sc[0], sc[1], sc[2], sc[3]};
+        const double* xc = xs + (long long)tl * K2_C;
+        for (int j = 0; j < c; ++j) modal_step(cf, zsf(xc[j], zon, mean, inv_sd), z);
+        const double* xe = a.src + g0 + n - 1;           // last sample of the segment
+        const double xl = zsf(xe[0], zon, mean, inv_sd);
+        for (int m = 0; m < pad; ++m) s_ve[m] = modal_step(cf, 2.0 * xl - zsf(xe[-1 - m], zon, mean, inv_sd), z);
+        double zb[4];                                    // the backward pass starts inside the extension
+        modal_initial(s_tab, s_ve[pad - 1], zb);
+        for (int e = 0; e < pad; ++e) modal_step(cf, s_ve[pad - 1 - e], zb);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s_inb[i] = zb[i];
+      }
+    }
+    __syncthreads();
+    for (int j = tid; j < K2F_R; j += K2F_NT) buf1[j] = j < len ? buf0[len - 1 - j] : 0.0;
+    __syncthreads();
+    fused_pass(a, s_tab, buf1, s_W, s_inb, r1 == n, tid, sc);
+    __syncthreads();
+    double* out = a.dst + g0 + t0;
+    const int off = len - 1 - (int)(t0 - r0);            // out[i] = buf1[off - i]
+    for (int i = tid; i < cnt; i += K2F_NT) out[i] = buf1[off - i];
+  }
+}
+
 // ------------------------------------------------------------ exact sequential mode
 // SciPy's evaluation order (lfilter's direct form II transposed, one sample at a time, separate multiply and add):
 // bit-identical to scipy.signal.filtfilt.  The recursion cannot be re-associated without changing the bits (two
@@ -740,18 +1017,6 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
 // warp moves one 256-byte row per segment and round through shared memory (exact_pass below); a first
 // lane-per-segment form with per-lane loads took 5 x longer (32 sectors per load instruction), a second one whose
 // chain warp moved the rows itself 6 x (a lone in-order warp pays every shared-memory latency in full).
-// (ORD is a template parameter and every loop over the state is unrolled: with run-time indices b, a and z would
-//  live in local memory, and the chain would wait for a memory round trip per sample)
-template <int ORD>
-__device__ __forceinline__ double df2t_step_exact(const double (&b)[5], const double (&a)[5], double x, double (&z)[4]) {
-  const double y = __dadd_rn(z[0], __dmul_rn(b[0], x));
-#pragma unroll
-  for (int k = 0; k < ORD - 1; ++k)
-    z[k] = __dsub_rn(__dadd_rn(z[k + 1], __dmul_rn(x, b[k + 1])), __dmul_rn(y, a[k + 1]));
-  z[ORD - 1] = __dsub_rn(__dmul_rn(x, b[ORD]), __dmul_rn(y, a[ORD]));
-  return y;
-}
-
 #define K2E_T 32                        // samples per segment and round (one 256-byte row per segment)
 #define K2E_LD (K2E_T + 1)              // row stride in shared memory: lane l reads row l -> bank (l + t) mod 32
 #define K2E_NT 64                       // warp 0 walks the chains, warp 1 moves the rows
@@ -961,10 +1226,22 @@ extern "C" int aew_segments_find_f64(const double* x, const long long* d_rec_beg
   return (int)cudaGetLastError();
 }
 
+// 1 if the filter's memory is short enough for the one-launch form: |p|^416 < 1e-18 for every pole
+extern "C" int aew_filt_fused_ok(const double* h_tab) {
+  if (!h_tab) return 0;
+  const double m1 = h_tab[K2_TAB_P + 0] * h_tab[K2_TAB_P + 0] + h_tab[K2_TAB_P + 1] * h_tab[K2_TAB_P + 1];
+  const double m2 = h_tab[K2_TAB_P + 2] * h_tab[K2_TAB_P + 2] + h_tab[K2_TAB_P + 3] * h_tab[K2_TAB_P + 3];
+  const double m = m1 > m2 ? m1 : m2;                    // |p|^2
+  if (!(m > 0.0) || !(m < 1.0)) return m == 0.0 ? 1 : 0;
+  return 0.5 * K2F_H * log(m) < log(1e-18) ? 1 : 0;
+}
+
 // filtfilt of every segment found by aew_segments_find_f64 (same ws).
 //   src  input samples (flat), optionally z-scored on load with mean/sd per record
 //   out  filtered output (may alias src); tmp: scratch of the same length
-//   mode 0 = tiled scan (fast), 1 = exact sequential SciPy order (parity suite)
+//   mode 0 = tiled scan (fast), 1 = exact sequential SciPy order (one lane per segment: least machine), 3 = the same
+//   bits, one warp per segment (least latency), 2 = tiled, forward + backward in one launch (src -> out directly,
+//   tmp unused, src != out; only where aew_filt_fused_ok(h_tab))
 extern "C" int aew_filtfilt_f64(const double* src, const double* mean, const double* sd, double* out, double* tmp,
                                 const double* d_tab, const double* h_tab, long long n_rec, long long total_samples,
                                 void* ws, size_t ws_bytes, long long max_seg, int mode, void* stream) {
@@ -997,6 +1274,29 @@ extern "C" int aew_filtfilt_f64(const double* src, const double* mean, const dou
       case 4: AEW_LAUNCH(k2_exact<4>, (unsigned)blocks, K2E_NT, 0, st, a); break;
       default: return AEW_ERR_UNSUPPORTED;
     }
+    return (int)cudaGetLastError();
+  }
+  if (mode == 3) {                                       // exact, one warp per segment (low latency)
+    const long long blocks = max_seg;
+    switch ((int)h_tab[K2_TAB_ORDER]) {
+      case 1: AEW_LAUNCH(k2_exact_warp<1>, (unsigned)blocks, K2W_NT, 0, st, a); break;
+      case 2: AEW_LAUNCH(k2_exact_warp<2>, (unsigned)blocks, K2W_NT, 0, st, a); break;
+      case 3: AEW_LAUNCH(k2_exact_warp<3>, (unsigned)blocks, K2W_NT, 0, st, a); break;
+      case 4: AEW_LAUNCH(k2_exact_warp<4>, (unsigned)blocks, K2W_NT, 0, st, a); break;
+      default: return AEW_ERR_UNSUPPORTED;
+    }
+    return (int)cudaGetLastError();
+  }
+  if (mode == 2) {                                       // forward + backward in one launch (short-memory filters)
+    if (src == out) return AEW_ERR_ARG;
+    if (!aew_filt_fused_ok(h_tab)) return AEW_ERR_UNSUPPORTED;
+    const size_t fsmem = (size_t)(2 * K2F_R + K2_TAB_LEN + 4 * K2F_NW + 8 + 16) * sizeof(double);
+    if (AEW_SET_MAX_SMEM(k2_fused, fsmem) != 0) return (int)cudaGetLastError();
+    if (cudaMemsetAsync(w.hdr + H_WORK_FWD, 0, 2 * sizeof(long long), st) != 0) return (int)cudaGetLastError();
+    a.dst = out;
+    const long long cap3 = (long long)sm_count() * 3;
+    const long long grid3 = w.max_tiles < cap3 ? w.max_tiles : cap3;
+    AEW_LAUNCH(k2_fused, (unsigned)grid3, K2F_NT, fsmem, st, a);
     return (int)cudaGetLastError();
   }
   if (mode != 0) return AEW_ERR_ARG;

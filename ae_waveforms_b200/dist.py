@@ -45,11 +45,13 @@ def allgather_rows(t, group=None):
     return [b[:c] for b, c in zip(bufs, counts)]
 
 
-def gather_rows_to(arrays, dst: int = 0, group=None):
+def gather_rows_to(arrays, dst: int = 0, group=None, async_op: bool = False):
     """Variable-length gather of several row arrays to ONE rank: the row counts are all-gathered once, then every
     other rank sends its rows as they are (no padding) and ``dst`` receives them into exact-size buffers -- a
     quarter of the all-gather's bytes per link at eight ranks, and nothing lands where it is not needed.
-    Returns, on ``dst``, one tensor per array with the ranks' rows in rank order; None elsewhere."""
+    Returns, on ``dst``, one tensor per array with the ranks' rows in rank order; None elsewhere.  With ``async_op``
+    the transfers are only started: returns ``(parts, requests)``; the caller calls ``wait()`` on the requests before
+    it touches ``parts`` (or frees ``arrays``) -- the rows of one step then cross NVLink under the next step's kernels."""
     import torch
     import torch.distributed as dist
     ws, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -71,10 +73,24 @@ def gather_rows_to(arrays, dst: int = 0, group=None):
             parts.append(full)
     elif counts[rank]:
         ops = [dist.P2POp(dist.isend, a.contiguous(), glob(dst), group) for a in arrays]
-    if ops:
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
+    reqs = dist.batch_isend_irecv(ops) if ops else []
+    if async_op:
+        return parts, reqs
+    for req in reqs:
+        req.wait()
     return parts
+
+
+def sort_case_major(waves, info, feats=None):
+    """Rows of several ranks -> the case-major order of data_create_arrays.py:27-48 (sort on (case_id, idx_end))."""
+    import torch
+    if info.shape[0]:
+        key = info[:, 0].to(torch.int64) * (1 << 40) + info[:, 1].to(torch.int64)
+        order = torch.argsort(key, stable=True)
+        waves, info = waves.index_select(0, order), info.index_select(0, order)
+        if feats is not None:
+            feats = feats.index_select(0, order)
+    return (waves, info) if feats is None else (waves, info, feats)
 
 
 def gather_beat_arrays(np_waves, np_info, group=None, np_features=None, dst: int | None = None):
@@ -94,13 +110,7 @@ def gather_beat_arrays(np_waves, np_info, group=None, np_features=None, dst: int
         waves = torch.cat(allgather_rows(np_waves, group), dim=0)
         info = torch.cat(allgather_rows(np_info, group), dim=0)
         feats = None if np_features is None else torch.cat(allgather_rows(np_features, group), dim=0)
-    if info.shape[0]:
-        key = info[:, 0].to(torch.int64) * (1 << 40) + info[:, 1].to(torch.int64)
-        order = torch.argsort(key, stable=True)
-        waves, info = waves.index_select(0, order), info.index_select(0, order)
-        if feats is not None:
-            feats = feats.index_select(0, order)
-    return (waves, info) if np_features is None else (waves, info, feats)
+    return sort_case_major(waves, info, feats)
 
 
 def rows_to_host(*arrays, dst_rank: int = 0, group=None):

@@ -412,17 +412,32 @@ def run_gpu(args):
     pre_fast = batched.Preprocessor(device=dev, exact_masks=False)
     scratch = {"y": torch.empty_like(flat), "tmp": torch.empty_like(flat)}
     total = flat.numel()
-    DEPTH = 3                                                     # calls whose exact-mask pass may still be in flight
+    DEPTH = int(os.environ.get("AEW_BENCH_DEPTH", 7))            # calls whose exact-mask pass may still be in flight
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    in_flight = []                                                # the previous step's rows, still crossing NVLink
+
+    def drain():
+        while in_flight:
+            parts, reqs = in_flight.pop(0)[:2]
+            for req in reqs:
+                req.wait()
+            if parts is not None:                                 # rank 0: back into case-major order
+                awd.sort_case_major(parts[0], parts[1])
+
     def finish(p, q):
         res = p.finish(q)
         if world > 1:
-            awd.gather_beat_arrays(res["np_waves"], res["np_info"], dst=0)   # the final arrays live on one rank
+            # the final arrays live on one rank (data_create_arrays.py:56-58): every rank sends its rows to rank 0,
+            # point to point and unpadded; the transfer is only STARTED here and waited for when the next step's rows
+            # are ready to go, so that it runs under that step's kernels
+            drain()
+            in_flight.append(awd.gather_rows_to([res["np_waves"], res["np_info"]], dst=0, async_op=True)
+                             + (res["np_waves"], res["np_info"]))
         return res
 
     def run_steps(p, steps):
@@ -436,6 +451,7 @@ def run_gpu(args):
                 res = finish(p, q.pop(0))
         while q:
             res = finish(p, q.pop(0))
+        drain()
         return res
 
     # ---- stage timing (CUDA events on the launching stream) wraps the stage methods of the fast-mask object
@@ -503,15 +519,25 @@ def run_gpu(args):
     beg_h, end_h, d_beg, d_end = pre_fast._ranges(batch, trim=False)
     mean, sd, cnt = pre_fast.zscore_stats(flat, beg_h, end_h, d_beg, d_end)
     k1_ms = alone(lambda: pre_fast.zscore_stats(flat, beg_h, end_h, d_beg, d_end), args.steps)
-    k2_stage_ms = alone(lambda: pre_fast.filter_records(flat, beg_h, end_h, d_beg, d_end, mean, sd, cnt,
-                                                        out=scratch["y"], tmp=scratch["tmp"]), args.steps)
-    k2_launch_ms = k2_stage_ms / 4.0                  # segment discovery is < 1 % of this (no NaN: no scan)
+    # the high-pass alone (k2_pass forward + backward: two launches) and the low-pass alone (k2_fused: one launch)
+    pre_hp = batched.Preprocessor(device=dev, lp=None, exact_masks=False)
+    pre_lp = batched.Preprocessor(device=dev, hp=None, exact_masks=False)
+    k2_hp_ms = alone(lambda: pre_hp.filter_records(flat, beg_h, end_h, d_beg, d_end, mean, sd, cnt,
+                                                   out=scratch["y"], tmp=scratch["tmp"]), args.steps)
+    k2_lp_ms = alone(lambda: pre_lp.filter_records(flat, beg_h, end_h, d_beg, d_end, mean, sd, cnt,
+                                                   out=scratch["y"], tmp=scratch["tmp"]), args.steps)
+    k2_launch_ms = k2_hp_ms / 2.0                     # segment discovery is < 1 % of this (no NaN: no scan)
+    lp_fused = bool(pre_fast.fuse_passes)
+    y_f, _ = pre_fast.filter_records(flat, beg_h, end_h, d_beg, d_end, mean, sd, cnt, out=scratch["y"],
+                                     tmp=scratch["tmp"])
+    z_scratch = pre_fast._filter_tmp                  # (the two buffers may have changed roles)
     win_start, _, _ = pre_fast.window_table(beg_h, end_h, batch.case_ids)
     n_win = len(win_start)
-    k3w_ms = alone(lambda: pre_fast.screen_windows(scratch["y"], win_start, want_median=False, lazy_sd=True,
+    k3w_ms = alone(lambda: pre_fast.screen_windows(y_f, win_start, want_median=False, lazy_sd=True,
                                                    zwin_scratch=None), args.steps)
-    k3_both_ms = alone(lambda: pre_fast.screen_windows(scratch["y"], win_start, lazy_sd=True,
-                                                       zwin_scratch=scratch["tmp"]), args.steps)
+    k3_both_ms = alone(lambda: pre_fast.screen_windows(y_f, win_start, lazy_sd=True, zwin_scratch=z_scratch),
+                       args.steps)
+    del y_f, z_scratch
 
     # ---- secondary: the same step with the wave delineation (K7) and the 35 np_features (K6) switched on
     feat = None
@@ -672,16 +698,21 @@ def run_gpu(args):
         by_kernel = {
             "k1_leaf+k1_combine": kern("k1", k1_ms, 16.0 * total, "two NumPy-order sweeps of the record (mean, then sd): "
                                        "16 B/sample; one launch group per step", launches_per_step=1),
-            "k2_pass": kern("k2_pass", k2_launch_ms, 16.0 * total, "one direction of one filtfilt: 8 B read + 8 B "
-                            "written per sample; 4 launches per step", launches_per_step=4),
+            "k2_pass": kern("k2_pass", k2_launch_ms, 16.0 * total, "one direction of the 1 Hz high-pass filtfilt: 8 B "
+                            "read + 8 B written per sample; 2 launches per step", launches_per_step=2),
+            ("k2_fused" if lp_fused else "k2_pass (low-pass)"): kern(
+                "k2_fused", k2_lp_ms / (1.0 if lp_fused else 2.0), 16.0 * total,
+                "the 30 Hz low-pass, forward + backward in ONE launch over tiles with a 416-sample halo: 8 B read + "
+                "8 B written per sample where two launches move 32 (SURVEY.md 8d counts 32 for this filtfilt)"
+                if lp_fused else "one direction of the low-pass filtfilt", launches_per_step=1 if lp_fused else 2),
             "k3_windows": kern("k3_windows", k3w_ms, 8.0 * total, "window read once: 8 B/sample (+ peaks, stats); bound "
                                "by instruction issue, not by HBM (issue slots 63 % busy, profiles/r2_k3_windows.txt)",
                                bound="issue (hbm shown for scale)", launches_per_step=1),
             "k3_median": kern("k3_median", max(k3_both_ms - k3w_ms, 1e-6), beats_per_win * 320 * 8.0 * tot_rows / world,
                               "the beats' samples of every kept window: n_beats x 320 x 8 B per window",
                               bound="issue (hbm shown for scale)", launches_per_step=1)}
-        shares = {"k1_leaf+k1_combine": k1_ms, "k2_pass": 4 * k2_launch_ms, "k3_windows": k3w_ms,
-                  "k3_median": max(k3_both_ms - k3w_ms, 0.0)}
+        shares = {"k1_leaf+k1_combine": k1_ms, "k2_pass": k2_hp_ms, "k3_windows": k3w_ms,
+                  "k3_median": max(k3_both_ms - k3w_ms, 0.0), ("k2_fused" if lp_fused else "k2_pass (low-pass)"): k2_lp_ms}
         dominant = max(shares, key=shares.get)
         staged_gbs = tot_samples / world * args.steps / sec * 102.7 / 1e9
         tr_step = None
@@ -710,7 +741,8 @@ def run_gpu(args):
                                  "note": "the same steps without the exact-mask pass: ~0.3 % of the rows (20-peak "
                                          "windows whose np.std rounds the other way) differ from the reference's"},
             "algorithmic_gbs_staged_102.7B": staged_gbs,
-            "roofline": {"kernel": "whole step, time-weighted (K1 + 4 x K2 + K3 screen + K3 median + exact-mask pass)",
+            "roofline": {"kernel": "whole step, time-weighted (K1 + K2 high-pass x 2 + K2 low-pass + K3 screen + K3 median "
+                                   "+ exact-mask pass)",
                          "bound": "hbm", "achieved": staged_gbs, "peak": hbm, "unit": "GB/s", "frac": staged_gbs / hbm,
                          "traffic": tr_step, "peak_source": peak_src,
                          "algorithmic_bytes_per_step": 102.7 * total,

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AEW_VERSION 109
+#define AEW_VERSION 110
 
 /* return codes */
 #define AEW_OK 0
@@ -80,8 +80,15 @@ int aew_segments_find_f64(const double* d_x, const long long* d_rec_beg, const l
                           long long n_rec, long long total_samples,
                           const long long* d_nonnan_count /* may be NULL */, double* d_nan_fill /* may be NULL */,
                           void* d_ws, size_t ws_bytes, long long max_seg, void* stream);
-/* mode 0: tiled block scan (within 1e-6 relative of SciPy; measured ~1e-9);
- * mode 1: literal sequential DF2T order, bit-identical to SciPy (parity suite). */
+/* mode 0: tiled block scan, forward launch (src -> tmp) + backward launch (tmp -> out; out may alias src); within 1e-6
+ *         relative of SciPy, measured ~1e-9;
+ * mode 1: SciPy's sequential DF2T order, bit-identical to scipy.signal.filtfilt; one lane per segment (32 segments
+ *         per block in lockstep: least of the machine);
+ * mode 3: the same bits, one warp per segment (half the latency per segment, 32 x the issue slots);
+ * mode 2: tiled, forward AND backward in one launch over tiles with a 416-sample halo (src -> out, src != out, tmp
+ *         unused): only for filters whose memory is that short, aew_filt_fused_ok(h_tab) (the 30 Hz low-pass is,
+ *         the 1 Hz high-pass is not). */
+int aew_filt_fused_ok(const double* h_tab);
 int aew_filtfilt_f64(const double* d_src, const double* d_mean /* may be NULL */, const double* d_sd,
                      double* d_out, double* d_tmp, const double* d_tab, const double* h_tab /* host copy of d_tab */,
                      long long n_rec, long long total_samples, void* d_ws, size_t ws_bytes, long long max_seg, int mode,

@@ -20,8 +20,8 @@ for exact in (False, True):
         print(f"exact_masks={exact} call {rep}: {e0.elapsed_time(e1):.1f} ms, rows {res['np_waves'].shape[0]}, "
               f"20-peak windows re-decided {res['mask_hazard_windows']}, decisions changed {res['mask_flips_resolved']}", flush=True)
     if exact:
-        for depth in (1, 2, 3):
-            K = 10
+        for depth in (3, 5, 7):
+            K = 16
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize(); e0.record()
             q = []

@@ -12,9 +12,13 @@ pre = batched.Preprocessor()
 beg_h, end_h, d_beg, d_end = pre._ranges(batch, trim=False)
 mean, sd, cnt = pre.zscore_stats(flat, beg_h, end_h, d_beg, d_end)
 y = torch.empty_like(flat); tmp = torch.empty_like(flat)
-for rep in range(3):
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    pre.filter_records(flat, beg_h, end_h, d_beg, d_end, mean, sd, cnt, out=y, tmp=tmp)
-    e1.record(); torch.cuda.synchronize()
-    print(rep, f"{e0.elapsed_time(e1):.3f} ms filter stage for {n_cases} cases")
+for name, p in (("HP + LP (product)", pre), ("HP + LP, two launches each", None), ("HP alone", batched.Preprocessor(lp=None)),
+                ("LP alone", batched.Preprocessor(hp=None))):
+    if p is None:
+        p = batched.Preprocessor(); p.fuse_passes = False
+    for rep in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        p.filter_records(flat, beg_h, end_h, d_beg, d_end, mean, sd, cnt, out=y, tmp=tmp)
+        e1.record(); torch.cuda.synchronize()
+    print(f"{name:28s} {e0.elapsed_time(e1):.3f} ms filter stage for {n_cases} cases")

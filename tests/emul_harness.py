@@ -99,9 +99,20 @@ def filtfilt(records, stages, mode, zscore=False, max_seg=None):
     for btype, fc, order in stages:
         tab, trc = filter_tables(btype, fc, 500, order)
         assert trc == 0
-        rc = L.aew_filtfilt_f64(ptr(src), ptr(m), ptr(s), ptr(out), ptr(tmp), ptr(tab), ptr(tab), n, total, ptr(ws), wsb,
-                                max_seg, mode, None)
-        assert rc == 0, rc
+        if mode == 2:                                      # one launch: src -> a buffer that is not src
+            assert L.aew_filt_fused_ok(ptr(tab)) == 1
+            dst = tmp if src is out else out
+            nanmask = np.isnan(flat)
+            rc = L.aew_filtfilt_f64(ptr(src), ptr(m), ptr(s), ptr(dst), ptr(out if dst is tmp else tmp), ptr(tab),
+                                    ptr(tab), n, total, ptr(ws), wsb, max_seg, 2, None)
+            assert rc == 0, rc
+            dst[nanmask] = np.nan                          # (the caller plans the NaN fill into the final buffer)
+            if dst is tmp:
+                out, tmp = tmp, out
+        else:
+            rc = L.aew_filtfilt_f64(ptr(src), ptr(m), ptr(s), ptr(out), ptr(tmp), ptr(tab), ptr(tab), n, total, ptr(ws),
+                                    wsb, max_seg, mode, None)
+            assert rc == 0, rc
         src, m, s = out, None, None
     hdr = ws[(-ws.ctypes.data) % 128:][:64].view(np.int64).copy()
     return [out[off[i]:off[i + 1]] for i in range(n)], hdr

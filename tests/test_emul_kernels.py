@@ -47,6 +47,39 @@ def test_k2_exact_mode_is_bit_identical_to_scipy(golden):
     assert same(outs[0], g["gaps_lp"])
 
 
+def test_k2_exact_warp_form_has_the_same_bits(golden):
+    """mode 3 (one warp per segment, the low-latency form of the exact-mask pass) == mode 1 == SciPy."""
+    g = golden("filters")
+    recs = [g["gaps_z"], g["clean_z"][:9000]]
+    outs, hdr = eh.filtfilt(recs, [("high", 1, 4)], mode=3)
+    assert same(outs[0], g["gaps_hp"]) and same(outs[1], rp.butterworth(recs[1], "high", 1))
+    outs, _ = eh.filtfilt([g["gaps_hp"]], [("low", 30, 4)], mode=3)
+    assert same(outs[0], g["gaps_lp"])
+    outs, _ = eh.filtfilt([g["short_x"]], [("low", 40, 3)], mode=3)
+    assert same(outs[0], g["short_lp40_o3"])
+
+
+def test_k2_one_launch_form_within_tolerance(golden):
+    """mode 2: forward + backward of a short-memory filter in one launch over tiles with a 416-sample halo (segment
+    starts / ends inside a region, segments shorter than a tile, many tiles, NaN gaps, short islands)."""
+    g = golden("filters")
+    x = ecg_synth.synth_case(5, 30000)
+    hp = rp.butterworth(rp.zscore(x), "high", 1)
+    recs = [g["gaps_hp"], hp, hp[:3328 + 416], hp[:3328 + 417], hp[:4160], hp[:4161], hp[:2 * 3328], hp[:16], hp[:15]]
+    outs, hdr = eh.filtfilt(recs, [("low", 30, 4)], mode=2)
+    assert hdr[4] == 0
+    for out, r in zip(outs, recs):
+        ref = rp.butterworth(r, "low", 30)
+        assert same(np.isnan(out), np.isnan(ref))
+        m = ~np.isnan(ref)
+        assert np.max(np.abs(out[m] - ref[m])) <= 1e-7, (len(r), np.max(np.abs(out[m] - ref[m])))
+    outs, _ = eh.filtfilt([g["short_x"]], [("low", 40, 3)], mode=2)
+    assert np.max(np.abs(outs[0] - g["short_lp40_o3"])) <= 1e-6 * np.max(np.abs(g["short_lp40_o3"]))
+    L = eh.lib()
+    tab, _ = eh.filter_tables("high", 1, 500, 4)
+    assert L.aew_filt_fused_ok(eh.ptr(tab)) == 0           # the 1 Hz high-pass remembers ~8,000 samples: two launches
+
+
 def test_k2_tiled_scan_within_tolerance(golden):
     g = golden("filters")
     recs = [g["gaps_x"], g["clean_x"][:17000]]

@@ -616,6 +616,31 @@ def test_parity_64_cases_against_the_oracle(gpu):
             assert res["mask_hazard_windows"] >= rep["hazard_windows"] * 0.9
 
 
+def test_feature_dropins_match_golden(gpu, golden):
+    """ecg_features_relative_r -> compute_ecg_morphology_features -> compute_median_features_ecg (the stage kernels of
+    K6 behind the reference's three signatures) against arrays frozen from the reference's own functions; estimate_hr /
+    rmssd (aew_peak_stats_f64) against the reference formulas."""
+    from ae_waveforms_b200.data_load_preprocess.feature_extraction.features_ecg import (
+        compute_ecg_morphology_features, ecg_features_relative_r)
+    from ae_waveforms_b200.data_load_preprocess.median_sample import compute_median_features_ecg
+    g = golden("features")
+    fid = {n: [np.nan if v < 0 else int(v) for v in g["fiducials"][k]] for k, n in enumerate(rp.FIDUCIALS)}
+    rel = ecg_features_relative_r(g["window"], fid, list(g["r_peaks"]), 500)
+    morph = compute_ecg_morphology_features(rel, len(g["r_peaks"]))
+    assert "ECG_R_Peaks" in rel
+    med = compute_median_features_ecg(rel, morph)
+    row = [v for n in rp.FIDUCIALS for v in (med[n]["x"], med[n]["y"])] + [med[n] for n in rp.MORPHOLOGY]
+    assert np.array_equal(np.array(row), g["row35"], equal_nan=True)
+    assert np.array_equal(np.array([rel[n]["x"] for n in rp.FIDUCIALS]), g["rel_x"], equal_nan=True)
+    assert np.array_equal(np.array([morph[n] for n in rp.MORPHOLOGY]), g["morph"], equal_nan=True)
+    from ae_waveforms_b200.data_load_preprocess.remove_samples import estimate_hr, rmssd
+    assert estimate_hr([], [100, 600, 1100], 500, mod="max") == 60.0
+    pk = list(g["r_peaks"])
+    for mod in ("min", "mean", "max"):
+        assert same(estimate_hr(pk[::2], pk, 500, mod=mod), rp.estimate_hr(pk[::2], pk, 500, mod))
+    assert same(rmssd(pk, 500), rp.rmssd(pk, 500)) and np.isnan(rmssd(pk[:2], 500)) and np.isnan(estimate_hr([], [5], 500))
+
+
 def test_neurokit_shim(gpu):
     from ae_waveforms_b200 import neurokit_shim as nk
     from oracle import nk_delineate as nd
