@@ -154,8 +154,10 @@ class Preprocessor:
         # windows re-screened from that output, so every keep / remove decision is the reference's bit for bit.
         self.exact_masks = bool(exact_masks) and self.filter_mode == 0
         self.defer_chunks = 6               # run_host_pipelined: chunks finished this many chunks late (exact_masks)
-        self.fuse_passes = bool(int(__import__("os").environ.get("AEW_K2_FUSE", "1")))   # short-memory filters:
-                                            # forward + backward in one launch (k2_fused); 0 = two launches
+        # short-memory filters (the low-pass) CAN run forward + backward in one launch (k2_fused, AEW_K2_FUSE=1): half
+        # the HBM traffic, but measured SLOWER (3.14 against 2.59 ms per 200 cases): the filter kernels are bound by
+        # their FP64 instruction stream (~35 % of the measured DFMA peak), not by bytes, and the halo adds 25 % of it
+        self.fuse_passes = bool(int(__import__("os").environ.get("AEW_K2_FUSE", "0")))
         self.lazy_sd = True                 # run(): 'ecg_sd' is not an output; evaluate it only where it decides
         # the screen kernel parks the z-scored windows in the filter scratch for the median kernel (measured: 30.1 ms
         # per 179,000 windows against 32.5 when the median kernel re-derives them; profiles/k3_variants.py)

@@ -1020,6 +1020,13 @@ __global__ void __launch_bounds__(K2F_NT, 3) k2_fused(PassArgs a) {
 #define K2E_T 32                        // samples per segment and round (one 256-byte row per segment)
 #define K2E_LD (K2E_T + 1)              // row stride in shared memory: lane l reads row l -> bank (l + t) mod 32
 #define K2E_NT 64                       // warp 0 walks the chains, warp 1 moves the rows
+#define K2E_HOG (190 * 1024)            // dynamic shared memory the block asks for and never touches: no block of the
+                                        // window / filter / delineation kernels fits next to it, so the chain warp
+                                        // keeps its SM sub-partition to itself.  The chain is a latency race: with
+                                        // those kernels' warps on the same scheduler every one of its ~25
+                                        // instructions per sample queues for an issue slot (measured: the pass went
+                                        // from 315 ms alone to > 1 s next to them).  100 records are 4 blocks = 4 of
+                                        // the 148 SMs.
 
 struct alignas(16) K2ESeg { const double* in; double* out; long long n; long long pad_; };   // 32 bytes: two 16-byte loads
 
@@ -1268,10 +1275,14 @@ extern "C" int aew_filtfilt_f64(const double* src, const double* mean, const dou
   if (mode == 1) {                                       // one lane per segment (lanes beyond the count exit)
     const long long blocks = (max_seg + 31) / 32;
     switch ((int)h_tab[K2_TAB_ORDER]) {
-      case 1: AEW_LAUNCH(k2_exact<1>, (unsigned)blocks, K2E_NT, 0, st, a); break;
-      case 2: AEW_LAUNCH(k2_exact<2>, (unsigned)blocks, K2E_NT, 0, st, a); break;
-      case 3: AEW_LAUNCH(k2_exact<3>, (unsigned)blocks, K2E_NT, 0, st, a); break;
-      case 4: AEW_LAUNCH(k2_exact<4>, (unsigned)blocks, K2E_NT, 0, st, a); break;
+      case 1: if (AEW_SET_MAX_SMEM(k2_exact<1>, K2E_HOG) != 0) return (int)cudaGetLastError();
+              AEW_LAUNCH(k2_exact<1>, (unsigned)blocks, K2E_NT, K2E_HOG, st, a); break;
+      case 2: if (AEW_SET_MAX_SMEM(k2_exact<2>, K2E_HOG) != 0) return (int)cudaGetLastError();
+              AEW_LAUNCH(k2_exact<2>, (unsigned)blocks, K2E_NT, K2E_HOG, st, a); break;
+      case 3: if (AEW_SET_MAX_SMEM(k2_exact<3>, K2E_HOG) != 0) return (int)cudaGetLastError();
+              AEW_LAUNCH(k2_exact<3>, (unsigned)blocks, K2E_NT, K2E_HOG, st, a); break;
+      case 4: if (AEW_SET_MAX_SMEM(k2_exact<4>, K2E_HOG) != 0) return (int)cudaGetLastError();
+              AEW_LAUNCH(k2_exact<4>, (unsigned)blocks, K2E_NT, K2E_HOG, st, a); break;
       default: return AEW_ERR_UNSUPPORTED;
     }
     return (int)cudaGetLastError();
