@@ -189,14 +189,24 @@ class Preprocessor:
             ring = self._up_ring = torch.empty(self.UPLOAD_RING_BYTES, dtype=torch.uint8, pin_memory=True)
             self._up_ring_np = ring.numpy()
             self._up_pos = 0
-        if self._up_pos + nb > self.UPLOAD_RING_BYTES:        # wrap: everything issued so far must have been read
-            torch.cuda.synchronize(self.device)
+            self._up_events = {}
+        if self._up_pos + nb > self.UPLOAD_RING_BYTES:        # wrap: every fetch issued so far must have read its bytes
+            # (the fetch kernels only -- one event per stream that ever fetched -- not the whole device: a device-wide
+            #  wait here also waited for the exact-mask passes in flight on the side streams, ~300 ms every few calls)
+            for ev in self._up_events.values():
+                ev.synchronize()
+            self._up_events.clear()
             self._up_pos = 0
         pos = self._up_pos
         self._up_ring_np[pos:pos + nb] = arr.reshape(-1).view(np.uint8)
         _cabi.check(self.lib.aew_fetch_host(ring.data_ptr() + pos, nb, out.data_ptr(), _cabi.stream_ptr(torch)),
                     "fetch_host")
         self.launches += 1
+        st = torch.cuda.current_stream(self.device)
+        ev = self._up_events.get(st.cuda_stream)
+        if ev is None:
+            ev = self._up_events[st.cuda_stream] = torch.cuda.Event()
+        ev.record(st)
         self._up_pos = (pos + nb + 15) & ~15
         return out
 

@@ -1274,15 +1274,17 @@ extern "C" int aew_filtfilt_f64(const double* src, const double* mean, const dou
 #endif
   if (mode == 1) {                                       // one lane per segment (lanes beyond the count exit)
     const long long blocks = (max_seg + 31) / 32;
+    const char* hog_env = getenv("AEW_K2E_HOG_KB");      // measurement switch; default K2E_HOG
+    const size_t hog = hog_env ? (size_t)atoi(hog_env) * 1024 : (size_t)K2E_HOG;
     switch ((int)h_tab[K2_TAB_ORDER]) {
       case 1: if (AEW_SET_MAX_SMEM(k2_exact<1>, K2E_HOG) != 0) return (int)cudaGetLastError();
-              AEW_LAUNCH(k2_exact<1>, (unsigned)blocks, K2E_NT, K2E_HOG, st, a); break;
+              AEW_LAUNCH(k2_exact<1>, (unsigned)blocks, K2E_NT, hog, st, a); break;
       case 2: if (AEW_SET_MAX_SMEM(k2_exact<2>, K2E_HOG) != 0) return (int)cudaGetLastError();
-              AEW_LAUNCH(k2_exact<2>, (unsigned)blocks, K2E_NT, K2E_HOG, st, a); break;
+              AEW_LAUNCH(k2_exact<2>, (unsigned)blocks, K2E_NT, hog, st, a); break;
       case 3: if (AEW_SET_MAX_SMEM(k2_exact<3>, K2E_HOG) != 0) return (int)cudaGetLastError();
-              AEW_LAUNCH(k2_exact<3>, (unsigned)blocks, K2E_NT, K2E_HOG, st, a); break;
+              AEW_LAUNCH(k2_exact<3>, (unsigned)blocks, K2E_NT, hog, st, a); break;
       case 4: if (AEW_SET_MAX_SMEM(k2_exact<4>, K2E_HOG) != 0) return (int)cudaGetLastError();
-              AEW_LAUNCH(k2_exact<4>, (unsigned)blocks, K2E_NT, K2E_HOG, st, a); break;
+              AEW_LAUNCH(k2_exact<4>, (unsigned)blocks, K2E_NT, hog, st, a); break;
       default: return AEW_ERR_UNSUPPORTED;
     }
     return (int)cudaGetLastError();

@@ -31,10 +31,10 @@ names = ["load+nan+sum", "zscore", "np.std (lazy) + decision", "-", "-", "QRS in
 for rep in range(3):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    scr = pre.screen_windows(y, win_start, zwin_scratch=pre._filter_tmp)
+    scr = pre.screen_windows(y, win_start, zwin_scratch=pre._filter_tmp, lazy_sd=True)      # as Preprocessor.run calls it
     e1.record()
     e2 = torch.cuda.Event(enable_timing=True)
-    pre.screen_windows(y, win_start, want_median=False)
+    pre.screen_windows(y, win_start, want_median=False, lazy_sd=True)
     e2.record()
     torch.cuda.synchronize()
     if os.environ.get('NO_TICKS'):
