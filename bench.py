@@ -843,7 +843,10 @@ def bench_strips(dev, pre, n_records=None, leads=12):
     flat = (base[idx] * (1.0 + 0.001 * (torch.arange(n_strips, device=dev) // base.shape[0]).to(torch.float64))[:, None]
             ).reshape(-1).contiguous()
     del base, idx
-    p = batched.Preprocessor(device=dev, sample_length=10, max_segments=n_strips + 4096, exact_masks=False)
+    # (sd / n_peaks > 0.05 is the reference's rule for 20 s windows = at least 20 beats; a 10 s strip needs 0.1 for
+    #  the same heart rate)
+    p = batched.Preprocessor(device=dev, sample_length=10, max_segments=n_strips + 4096, exact_masks=False,
+                             sd_threshold=0.1)
     rec_off = np.arange(n_strips + 1, dtype=np.int64) * L
     batch = batched.RecordBatch(flat, rec_off, np.arange(n_strips) // leads)
     scratch = {"y": torch.empty_like(flat), "tmp": torch.empty_like(flat)}
