@@ -1016,23 +1016,26 @@ __global__ void __launch_bounds__(K2F_NT, 3) k2_fused(PassArgs a) {
 // next to the window / filter kernels, against 66 ms of those kernels alone).  Memory stays coalesced: a second
 // warp moves one 256-byte row per segment and round through shared memory (exact_pass below); a first
 // lane-per-segment form with per-lane loads took 5 x longer (32 sectors per load instruction), a second one whose
-// chain warp moved the rows itself 6 x (a lone in-order warp pays every shared-memory latency in full).
+// chain warp moved the rows itself 6 x (a lone in-order warp pays every shared-memory latency in full), and a
+// three-warp one whose mover also formed the products b[k] x and the z-score for the chain warp 2 x (then the mover,
+// again a lone in-order warp, is the slow one: 627 ms per pass against 310).
 #define K2E_T 32                        // samples per segment and round (one 256-byte row per segment)
 #define K2E_LD (K2E_T + 1)              // row stride in shared memory: lane l reads row l -> bank (l + t) mod 32
-#define K2E_NT 96                       // warp 0 walks the chains, warp 1 fetches the rows and prepares them, warp 2
-                                        // stores the outputs
-#define K2E_HOG (190 * 1024)            // dynamic shared memory the block asks for (it uses ~120 KB of it): no block of
-                                        // the window / filter / delineation kernels fits next to it, so the chain warp
+#define K2E_NT 64                       // warp 0 walks the chains, warp 1 moves the rows
+#define K2E_HOG (190 * 1024)            // dynamic shared memory the block asks for and never touches: no block of the
+                                        // window / filter / delineation kernels fits next to it, so the chain warp
                                         // keeps its SM sub-partition to itself.  The chain is a latency race: with
-                                        // those kernels' warps on the same scheduler every one of its instructions
-                                        // queues for an issue slot.  100 records are 4 blocks = 4 of the 148 SMs.
+                                        // those kernels' warps on the same scheduler every one of its ~25
+                                        // instructions per sample queues for an issue slot (measured: the pass went
+                                        // from 315 ms alone to > 1 s next to them).  100 records are 4 blocks = 4 of
+                                        // the 148 SMs.
 
-struct alignas(16) K2ESeg { const double* in; double* out; long long n; long long pad_; };   // two 16-byte loads
-struct alignas(16) K2EZ { double mean, b, r; long long fast; };                              // z-score of a row
+struct alignas(16) K2ESeg { const double* in; double* out; long long n; long long pad_; };   // 32 bytes: two 16-byte loads
 
-// Fetch of one round: eight segments at a time, their table entries first (all independent), then the eight
-// asynchronous copies -- a lone warp runs in order, and with one load-then-use per row every shared-memory latency
-// was paid in full (profiles/r2_k2_exact_simd.txt: 4,600 cycles per round, short scoreboard + wait).
+// The mover warp's two jobs for one round.  Eight segments at a time: their table entries are loaded first (two
+// 16-byte shared-memory loads each, all independent), then the eight copies are issued -- a lone warp runs in
+// order, and with one load-then-use per row every shared-memory latency was paid in full (profiles/r2_k2_exact_simd.txt:
+// 4,600 cycles per round, short scoreboard + wait).
 template <bool REV>
 __device__ __forceinline__ void exact_fetch(const K2ESeg* tab, long long r, double (*tile)[K2E_LD], int lane) {
   const long long i = r * K2E_T + lane;                   // logical index of my column in every row
@@ -1073,43 +1076,19 @@ __device__ __forceinline__ void exact_store(const K2ESeg* tab, long long r, cons
       if (i < ns[u]) p[u][REV ? ns[u] - 1 - i : i] = v[u];
   }
 }
-// The fetched rows -> the products b[k] x the chain consumes (x z-scored first where the pass asks for it: the
-// correctly rounded division, ten instructions, is work the chain warp should not carry).  Lane t takes column t.
-template <int ORD>
-__device__ __forceinline__ void exact_products(const double (*tile)[K2E_LD], double (*prod)[K2E_T][K2E_LD],
-                                               const K2EZ* zt, bool zon, const double (&b)[5], int lane) {
-#pragma unroll 4
-  for (int row = 0; row < K2E_T; ++row) {
-    double x = tile[row][lane];
-    if (zon) {
-      ExactDiv d;
-      d.b = zt[row].b; d.r = zt[row].r; d.fast = zt[row].fast != 0;
-      x = div_exact(__dsub_rn(x, zt[row].mean), d);
-    }
-#pragma unroll
-    for (int k = 0; k <= ORD; ++k) prod[k][row][lane] = __dmul_rn(b[k], x);
-  }
-}
 
 // One pass of the block's 32 segments: logical sample i of a segment is in[i] (REV: in[n - 1 - i]).  Rounds of 32
-// samples, three warps, one block barrier per round.  In round r: warp 0 walks row `lane` of the products of round r
-// (every lane its own segment's chain: 5 loads, 12 FP64 instructions and a store per sample); warp 1 turns the
-// rows of round r + 1 (fetched one round earlier) into products and starts the copies of round r + 2 (lane t takes
-// column t of every row: coalesced); warp 2 stores the outputs of round r - 1.
+// samples; in round r warp 0 walks row `lane` of tile r & 1 (every lane its own segment's chain) while warp 1
+// fetches the rows of round r + 1 into the other tile (asynchronous copies, lane t takes column t: coalesced) and
+// stores the outputs of round r - 1.  One block barrier per round.
 template <int ORD, bool REV>
-__device__ __forceinline__ void exact_pass(const K2ESeg* tab, const K2EZ* zt, long long n_max,
-                                           double (*tin)[K2E_T][K2E_LD], double (*prod)[ORD + 1][K2E_T][K2E_LD],
+__device__ __forceinline__ void exact_pass(const K2ESeg* tab, long long n_max, double (*tin)[K2E_T][K2E_LD],
                                            double (*tout)[K2E_T][K2E_LD], const double (&b)[5], const double (&a)[5],
-                                           double (&z)[4], long long n, bool zon, int warp, int lane) {
+                                           double (&z)[4], long long n, bool zon, double mean, const ExactDiv& sd,
+                                           int warp, int lane) {
   const long long rounds = (n_max + K2E_T - 1) / K2E_T;
   if (warp == 1 && rounds > 0) {
     exact_fetch<REV>(tab, 0, tin[0], lane);
-#ifndef AEW_EMUL
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-#endif
-    __syncwarp();
-    exact_products<ORD>(tin[0], prod[0], zt, zon, b, lane);
-    if (rounds > 1) exact_fetch<REV>(tab, 1, tin[1], lane);
 #ifndef AEW_EMUL
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 #endif
@@ -1121,51 +1100,41 @@ __device__ __forceinline__ void exact_pass(const K2ESeg* tab, const K2EZ* zt, lo
       const long long i0 = r * K2E_T;
       if (i0 < n) {
         const int cnt = (int)(n - i0 < K2E_T ? n - i0 : K2E_T);
+        const double* row = tin[buf][lane];
         double* orow = tout[buf][lane];
-        double c[ORD + 1];
-#pragma unroll
-        for (int k = 0; k <= ORD; ++k) c[k] = prod[buf][k][lane][0];
+        double c = row[0];
 #pragma unroll 4
         for (int t = 0; t < cnt; ++t) {
-          double nx[ORD + 1];                              // the next sample's products, fetched before the chain
+          const double nx = row[t + 1];                    // (one pad column: in bounds; fetched before the chain)
+          const double x = zs(c, zon, mean, sd);
+          const double y = __dadd_rn(z[0], __dmul_rn(b[0], x));
 #pragma unroll
-          for (int k = 0; k <= ORD; ++k) nx[k] = prod[buf][k][lane][t + 1];      // (one pad column: in bounds)
-          const double y = __dadd_rn(z[0], c[0]);
-#pragma unroll
-          for (int k = 0; k < ORD - 1; ++k) z[k] = __dsub_rn(__dadd_rn(z[k + 1], c[k + 1]), __dmul_rn(y, a[k + 1]));
-          z[ORD - 1] = __dsub_rn(c[ORD], __dmul_rn(y, a[ORD]));
+          for (int k = 0; k < ORD - 1; ++k)
+            z[k] = __dsub_rn(__dadd_rn(z[k + 1], __dmul_rn(x, b[k + 1])), __dmul_rn(y, a[k + 1]));
+          z[ORD - 1] = __dsub_rn(__dmul_rn(x, b[ORD]), __dmul_rn(y, a[ORD]));
           orow[t] = y;
-#pragma unroll
-          for (int k = 0; k <= ORD; ++k) c[k] = nx[k];
+          c = nx;
         }
       }
-    } else if (warp == 1) {
-      if (r + 1 < rounds) exact_products<ORD>(tin[buf ^ 1], prod[buf ^ 1], zt, zon, b, lane);
-      __syncwarp();
-      if (r + 2 < rounds) exact_fetch<REV>(tab, r + 2, tin[buf], lane);
+    } else {
+      if (r + 1 < rounds) exact_fetch<REV>(tab, r + 1, tin[buf ^ 1], lane);
+      if (r > 0) exact_store<REV>(tab, r - 1, tout[buf ^ 1], lane);
 #ifndef AEW_EMUL
       asm volatile("cp.async.wait_group 0;" ::: "memory");
 #endif
-    } else {
-      if (r > 0) exact_store<REV>(tab, r - 1, tout[buf ^ 1], lane);
     }
     __syncthreads();
   }
-  if (warp == 2 && rounds > 0) exact_store<REV>(tab, rounds - 1, tout[(rounds - 1) & 1], lane);
+  if (warp == 1 && rounds > 0) exact_store<REV>(tab, rounds - 1, tout[(rounds - 1) & 1], lane);
   __syncthreads();
 }
 
 template <int ORD>
 __global__ void __launch_bounds__(K2E_NT) k2_exact(PassArgs a) {
-  AEW_DYN_SMEM(smem_raw);
-  typedef double Tile[K2E_T][K2E_LD];
-  Tile* tin = (Tile*)smem_raw;                           // [2] fetched rows
-  Tile* tout = tin + 2;                                  // [2] outputs
-  typedef double Prod[ORD + 1][K2E_T][K2E_LD];
-  Prod* prod = (Prod*)(tout + 2);                        // [2] b[k] x of every sample
+  __shared__ double tin[2][K2E_T][K2E_LD];
+  __shared__ double tout[2][K2E_T][K2E_LD];
   __shared__ K2ESeg s_fwd[32];                           // src -> tmp
   __shared__ K2ESeg s_bwd[32];                           // tmp -> out
-  __shared__ K2EZ s_z[32];
   __shared__ long long s_nmax;
   const long long n_seg = a.ws.hdr[H_SEG_COUNT] < a.ws.max_seg ? a.ws.hdr[H_SEG_COUNT] : a.ws.max_seg;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1193,7 +1162,6 @@ __global__ void __launch_bounds__(K2E_NT) k2_exact(PassArgs a) {
     }
     s_fwd[lane].in = xs; s_fwd[lane].out = tmp; s_fwd[lane].n = n;
     s_bwd[lane].in = tmp; s_bwd[lane].out = out; s_bwd[lane].n = n;
-    s_z[lane].mean = mean; s_z[lane].b = sd.b; s_z[lane].r = sd.r; s_z[lane].fast = sd.fast ? 1 : 0;
     const long long m = (long long)__reduce_max_sync(AEW_FULL, (unsigned)(n > 0x7fffffffll ? 0x7fffffffll : n));
     if (lane == 0) s_nmax = m;
   } else {
@@ -1211,7 +1179,7 @@ __global__ void __launch_bounds__(K2E_NT) k2_exact(PassArgs a) {
     for (int e = 0; e < pad; ++e)
       df2t_step_exact<ORD>(b, ac, __dsub_rn(__dmul_rn(2.0, x0), zs(xs[pad - e], zon, mean, sd)), z);
   }
-  exact_pass<ORD, false>(s_fwd, s_z, n_max, tin, prod, tout, b, ac, z, n, zon, warp, lane);
+  exact_pass<ORD, false>(s_fwd, n_max, tin, tout, b, ac, z, n, zon, mean, sd, warp, lane);
   if (warp == 0 && n > 0) {                              // right extension, then the backward pass starts inside it
     for (int m = 0; m < pad; ++m)
       ve[m] = df2t_step_exact<ORD>(b, ac, __dsub_rn(__dmul_rn(2.0, xl), zs(xs[n - 2 - m], zon, mean, sd)), z);
@@ -1222,7 +1190,7 @@ __global__ void __launch_bounds__(K2E_NT) k2_exact(PassArgs a) {
   }
   __threadfence_block();                                 // the block's stores to tmp before the copies that read them
   __syncthreads();
-  exact_pass<ORD, true>(s_bwd, s_z, n_max, tin, prod, tout, b, ac, z, n, false, warp, lane);
+  exact_pass<ORD, true>(s_bwd, n_max, tin, tout, b, ac, z, n, false, 0.0, sd, warp, lane);
 }
 
 unsigned long long* g_dbg = nullptr;   // device counters, allocated once when AEW_K2_TIMING is set
@@ -1309,9 +1277,7 @@ extern "C" int aew_filtfilt_f64(const double* src, const double* mean, const dou
   if (mode == 1) {                                       // one lane per segment (lanes beyond the count exit)
     const long long blocks = (max_seg + 31) / 32;
     const char* hog_env = getenv("AEW_K2E_HOG_KB");      // measurement switch; default K2E_HOG
-    const size_t need = (size_t)(4 + 2 * 5) * K2E_T * K2E_LD * sizeof(double);     // tiles + products (order 4)
-    size_t hog = hog_env ? (size_t)atoi(hog_env) * 1024 : (size_t)K2E_HOG;
-    if (hog < need) hog = need;
+    const size_t hog = hog_env ? (size_t)atoi(hog_env) * 1024 : (size_t)K2E_HOG;
     switch ((int)h_tab[K2_TAB_ORDER]) {
       case 1: if (AEW_SET_MAX_SMEM(k2_exact<1>, K2E_HOG) != 0) return (int)cudaGetLastError();
               AEW_LAUNCH(k2_exact<1>, (unsigned)blocks, K2E_NT, hog, st, a); break;
