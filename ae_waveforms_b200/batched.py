@@ -751,7 +751,7 @@ def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chu
         every remaining record) crosses PCIe behind the first two chunks and goes through K1 / K2 / K3 once."""
         first = chunks[1][1]
         rest = np.arange(first, n_rec)
-        take = np.minimum(lens_rec[rest], 2 * pre.L + 1)
+        take = np.minimum(lens_rec[rest], 2 * pre.L + 1)       # two windows
         poff = np.concatenate([[0], np.cumsum(take)]).astype(np.int64)
         pbuf = torch.empty(int(poff[-1]), dtype=host_flat.dtype, device=pre.device)
         with torch.cuda.stream(copy_stream):
@@ -808,6 +808,7 @@ def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chu
         tot["n_beats"] += res["n_beats"]
         tot["mask_hazard"] += res["mask_hazard_windows"]
         tot["mask_flips"] += res["mask_flips_resolved"]
+        tot.setdefault("per_chunk", []).append(res["mask_hazard_windows"])
 
     if chunks:
         start_copy(0)
@@ -837,6 +838,8 @@ def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chu
         pending.append(pre.run(sub, scratch=sc, features=features, defer=depth > 0, low_latency=True))
         if not narrow:
             freed[k].record(main)                              # (the hazard records have been copied out by now)
+        if hazard_first and depth and pending[-1]["hz"] is None:
+            finish_one(pending.pop())                          # nothing to wait for (rows are re-ordered at the end)
         while len(pending) > depth:
             finish_one(pending.pop(0))
     while pending:
@@ -875,7 +878,8 @@ def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chu
                                                               device=pre.device)
         np_info = torch.cat(infos) if infos else torch.zeros((0, 2), dtype=torch.float64, device=pre.device)
     out = dict(np_waves=np_waves, np_info=np_info, hazard_windows=hazards, n_windows=n_windows, n_beats=n_beats,
-               mask_hazard_windows=tot["mask_hazard"], mask_flips_resolved=tot["mask_flips"])
+               mask_hazard_windows=tot["mask_hazard"], mask_flips_resolved=tot["mask_flips"],
+               mask_hazard_windows_per_chunk=tot.get("per_chunk", []))
     if features:
         out["np_features"] = np_feat
     return out
