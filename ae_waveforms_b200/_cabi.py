@@ -66,6 +66,7 @@ SIGNATURES = {
     "aew_beat_metrics_f32": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_double, c_void_p, c_void_p, c_void_p,
                                      c_void_p]),
     "aew_fetch_host": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p]),
+    "aew_copy_heads_h2d": (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_size_t, c_void_p]),
     "aew_widen_f64": (c_int, [c_void_p, c_int, c_longlong, c_double, c_double, c_int, c_int, c_void_p, c_void_p]),
     "aew_delineate_blocks": (c_int, [c_longlong]),
     "aew_delineate_workspace_bytes": (c_size_t, [c_longlong, c_int, c_double]),

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AEW_VERSION 110
+#define AEW_VERSION 111
 
 /* return codes */
 #define AEW_OK 0
@@ -175,6 +175,10 @@ int aew_widen_f64(const void* d_src, int src_type, long long n, double gain, dou
  * transfer, which would wait behind the next chunk's bulk host->device copy.  Both pointers 16-byte aligned;
  * the host buffer must stay untouched until the stream has passed this call. */
 int aew_fetch_host(const void* h_pinned, long long n_bytes, void* d_out, void* stream);
+/* The first `width` bytes of `rows` host records `src_pitch` bytes apart -> device rows `dst_pitch` apart, one
+ * strided copy (the feeder's preview of every record's first windows; page-locked source). */
+int aew_copy_heads_h2d(void* d_dst, size_t dst_pitch, const void* h_src, size_t src_pitch, size_t width, size_t rows,
+                       void* stream);
 
 /* ---- K7: wavelet delineation of the beats of a window --------------------------------
  * replaces nk.ecg_delineate(ecg_sample, r_peaks, sampling_rate=fs)[1] (neurokit2, default method
