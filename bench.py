@@ -445,8 +445,11 @@ def run_gpu(args):
         pass of its 20-peak records (side stream) runs next to the following calls' kernels.  Everything,
         including the last finish, lies inside the caller's timed region."""
         q, res = [], None
-        for _ in range(steps):
-            q.append(p.run(batch, scratch=scratch, defer=True))
+        for i in range(steps):
+            # the job's last two calls take the low-latency form of the sequential filter (one warp per record: half
+            # the wait, and the device is about to fall idle anyway): the run ends ~160 ms after its last kernels
+            # instead of ~310
+            q.append(p.run(batch, scratch=scratch, defer=True, low_latency=i >= steps - 2))
             while len(q) > DEPTH:
                 res = finish(p, q.pop(0))
         while q:
@@ -704,7 +707,7 @@ def run_gpu(args):
             "k2_pass": kern("k2_pass", k2_launch_ms, 16.0 * total, "one direction of the 1 Hz high-pass filtfilt: 8 B "
                             "read + 8 B written per sample; 2 launches per step", launches_per_step=2),
             ("k2_fused" if lp_fused else "k2_pass (low-pass)"): kern(
-                "k2_fused", k2_lp_ms / (1.0 if lp_fused else 2.0), 16.0 * total,
+                "k2_fused" if lp_fused else "k2_pass", k2_lp_ms / (1.0 if lp_fused else 2.0), 16.0 * total,
                 "the 30 Hz low-pass, forward + backward in ONE launch over tiles with a 416-sample halo: 8 B read + "
                 "8 B written per sample where two launches move 32 (SURVEY.md 8d counts 32 for this filtfilt)"
                 if lp_fused else "one direction of the low-pass filtfilt", launches_per_step=1 if lp_fused else 2),
