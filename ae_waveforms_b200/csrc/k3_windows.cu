@@ -37,14 +37,16 @@
 #include <cstdlib>
 #include "aew_pairwise.cuh"
 #include "aew_math.cuh"
+#include "aew_bulk.cuh"
 #include "../../include/aewave.h"
 
 #define K3_NT 512                         // two blocks per SM = 32 warps (64 registers per thread): the kernel is bound by
                                           // issue latency, not by a pipe (profiles/r1_k3_screen.txt: 16 warps, 45 % issue)
 #define K3_NW (K3_NT / 32)
-#define K3_ITEMS 7                        // extended positions per thread and segment (odd: conflict-free strips)
-#define K3_SEGS 4                         // the QRS indicator is evaluated in segments (prefix sums fit 24 KB)
-#define K3_CAP (K3_NT * K3_ITEMS)         // 3584 extended positions per segment at most
+#define K3_ITEMS 22                       // extended positions per thread: ONE strip of the whole window (even: the
+                                          // strip's own accesses are 16-byte pairs, conflict-free at a stride of 22)
+#define K3_WCAP (K3_NT * K3_ITEMS)        // 11,264 positions: window + the two box filters' halo
+#define K3_MAXRUN 2048                    // QRS runs per window the tables hold (a 20 s window has ~25)
 #define K3_RING 512                       // ring of smoothgrad values in the sequential evaluation (> avg_k + 1)
 #define K3_MAXL 10240                     // samples per window at most (80 KB of shared memory)
 #define K3_MAXP 72                        // peaks are > 150 samples apart -> at most 71 in 10752
@@ -55,10 +57,10 @@
 namespace {
 
 struct K3Smem {
-  double* A;            // [L]  z-scored window
-  double* B;            // [K3_CAP] prefix sums of one segment; later the run tables; ring of the sequential pass
+  double* W;            // [K3_WCAP] the window buffer: z-scored samples at W + H, then -- in place -- the prefix sums of
+                        //           |gradient|, then those of smoothgrad, then the z-scored samples again
   double* pw_vals;      // [2][128] leaf sums, double-buffered
-  double* wtot;         // [16]
+  double* wtot;         // [2][16]
   double* scal;         // [16] scalars
   double* dsq;          // [K3_MAXP] squared successive RR differences
   int* ipeaks;          // [K3_MAXP]
@@ -68,26 +70,23 @@ struct K3Smem {
   int* leaf_off;        // [128] NumPy-tree leaf ranges of a length-L vector
   int* leaf_size;       // [128]
   unsigned* Qw;         // [L/32 + 2] QRS indicator, one bit per sample
-  unsigned short* beg;  // [L/2 + 2] run tables (alias B: the prefix sums are dead by then); cand overwrites beg
-  unsigned short* end;
+  unsigned short* beg;  // [K3_MAXRUN] run tables; cand overwrites beg
+  unsigned short* end;  // [K3_MAXRUN]
+  double* ring;         // [K3_RING] smoothgrad ring of the sequential evaluation (aliases the run tables)
+  unsigned long long* mbar;   // mbarrier of the bulk copy that brings the z-scored window back
   unsigned char* pw_valid;  // [2][128]
 };
 
-// entries of B: one segment of the indicator evaluation (ceil(L / K3_SEGS) outputs + the two box filters' halo),
-// the ring of the sequential evaluation and the run tables, whichever is largest
-__host__ __device__ inline int k3_bcap(int L, int ext) {
-  const int seg = (L + K3_SEGS - 1) / K3_SEGS + ext;
-  const int rmax = L / 2 + 2;
-  const int runs = (2 * ((rmax + 7) & ~7) * 2 + 7) / 8;
-  int c = seg > runs ? seg : runs;
-  c = c > K3_RING ? c : K3_RING;
-  return (c + K3_ITEMS + 1) & ~1;
-}
+// first sample's offset inside W: the halo of the two box filters in front of it (even: 16-byte pairs stay aligned)
+__host__ __device__ inline int k3_halo(int ks, int ka) { return (ka / 2 + ks / 2 + 2) & ~1; }
+// extended positions the indicator needs: sample j sits at position j + H, the averaging box of the last sample
+// ends ka - 1 - ka/2 samples behind it
+__host__ __device__ inline int k3_ext_len(int L, int ks, int ka) { return L + k3_halo(ks, ka) + ka - ka / 2 - 1; }
 
-// Everything of fixed size comes FIRST, at compile-time offsets from the base of the dynamic shared memory (with
+// Everything is of fixed size, at compile-time offsets from the base of the dynamic shared memory (with
 // L-dependent offsets the compiler re-derived these pointers at their uses under the 64-register cap: 7.6 % of all
-// executed instructions in profiles/r2_k3_512_before_diet.txt), then the window, then B right behind it.
-__host__ __device__ inline size_t k3_smem_layout(unsigned char* base, int L, int ext, K3Smem* s) {
+// executed instructions in profiles/r2_k3_512_before_diet.txt); the window buffer comes last.
+__host__ __device__ inline size_t k3_smem_layout(unsigned char* base, K3Smem* s) {
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t at = o; o = (o + bytes + 15) & ~(size_t)15; return base ? base + at : (unsigned char*)0; };
   K3Smem t;
@@ -102,12 +101,12 @@ __host__ __device__ inline size_t k3_smem_layout(unsigned char* base, int L, int
   t.leaf_off = (int*)take(sizeof(int) * 128);
   t.leaf_size = (int*)take(sizeof(int) * 128);
   t.pw_valid = (unsigned char*)take(256);
+  t.mbar = (unsigned long long*)take(16);
   t.Qw = (unsigned*)take(sizeof(unsigned) * (K3_MAXL / 32 + 2));
-  t.A = (double*)take(sizeof(double) * L);
-  t.B = (double*)take(sizeof(double) * k3_bcap(L, ext));
-  const int rmax = L / 2 + 2;                            // (k3_bcap covers both tables)
-  t.beg = base ? (unsigned short*)t.B : (unsigned short*)0;
-  t.end = base ? (unsigned short*)t.B + ((rmax + 7) & ~7) : (unsigned short*)0;
+  t.beg = (unsigned short*)take(sizeof(unsigned short) * 2 * K3_MAXRUN);
+  t.end = base ? t.beg + K3_MAXRUN : (unsigned short*)0;
+  t.ring = (double*)t.beg;
+  t.W = (double*)take(sizeof(double) * K3_WCAP);
   if (s) *s = t;
   return o;
 }
@@ -702,7 +701,7 @@ __device__ __forceinline__ double absgrad_ext(const double* __restrict__ A, int 
 __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, unsigned long long* dbg) {
   AEW_DYN_SMEM(smem_raw);
   K3Smem sm;
-  k3_smem_layout(smem_raw, p.L, p.avg_k + p.smooth_k, &sm);
+  k3_smem_layout(smem_raw, &sm);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int L = p.L;
   const long long w = blockIdx.x;
@@ -736,8 +735,11 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, unsigned long
     }
   }
 #endif
-  double* A = sm.A;
-  double* B = sm.B;
+  const int ks = p.smooth_k, ka = p.avg_k;
+  const int ls = ks / 2, la = ka / 2;                  // uniform_filter1d: window [i - k/2, i - k/2 + k)
+  const int H = k3_halo(ks, ka);
+  double* W = sm.W;
+  double* A = W + H;                                    // sample j of the window sits at position j + H of W
   const int depth = pw_depth(L);
   if (tid < (1 << depth)) {
     long long off, size;
@@ -746,8 +748,9 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, unsigned long
     sm.leaf_size[tid] = (int)size;
   }
   for (int i = tid; i < L / 32 + 2; i += K3_NT) sm.Qw[i] = 0u;
+  if (tid == 0) mbar_init(sm.mbar, 1);
 
-  // ---- load (coalesced).  Asynchronous copies straight into shared memory: all 40 requests of a thread are in
+  // ---- load (coalesced).  Asynchronous copies straight into shared memory: all 20 requests of a thread are in
   //      flight at once and no registers are staged (8-byte form: a window start is only 8-byte aligned)
 #ifdef AEW_EMUL
   for (int i = tid; i < L; i += K3_NT) A[i] = src[i];
@@ -780,26 +783,37 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, unsigned long
   double sum_raw;
   int flag;
   K3_SWEEP(K3_PASS_PLAIN, 0.0, 1.0, sum_raw, flag)
+  fence_async_smem();                                   // (the window may leave through the bulk engine below)
   int bad = __syncthreads_or(flag);
   K3_TICK(0)   // load + NaN screen + first sum
   double sum_z = sum_raw;                               // windows that arrive z-scored: the same numbers
+  double mean = 0.0, sd0 = 1.0;
   if (!bad && p.zscore_windows) {
     // ---- per-window z-score (data_extract_vitaldb.py:93), NumPy summation order
-    const double mean = k3_div(sum_raw, (double)L);
+    mean = k3_div(sum_raw, (double)L);
     double ssq;
     K3_SWEEP(K3_PASS_DEV2, mean, 1.0, ssq, flag)
-    const double sd0 = k3_sqrt(k3_div(ssq, (double)L));
+    sd0 = k3_sqrt(k3_div(ssq, (double)L));
     K3_SWEEP(K3_PASS_ZSCORE, mean, sd0, sum_z, flag)
+    fence_async_smem();
     bad = __syncthreads_or(flag);
     if (tid == 0 && p.zparams) { p.zparams[2 * w] = mean; p.zparams[2 * w + 1] = sd0; }   // for the median kernel
   }
   K3_TICK(1)   // window z-score (+ sum of the z-scored window)
-  if (bad) {
-    if (p.zwin) {
-      double* zw = p.zwin + w * (long long)L;
+  // the z-scored window is parked for the median / delineation kernels ('ecg_sample' column): ONE bulk copy
+  // shared -> global issued by thread 0 where the addresses allow it (16-byte granules), plain stores otherwise
+  const bool tma_ok = (L & 1) == 0 && ((unsigned long long)p.zwin & 15ull) == 0;
+  if (p.zwin) {
+    double* zw = p.zwin + w * (long long)L;
+    if (tma_ok) {
+      if (tid == 0) bulk_store(zw, A, (unsigned)L * 8u);
+    } else {
 #pragma unroll 4
-      for (int i = tid; i < L; i += K3_NT) zw[i] = A[i];  // NaN windows: as z-scored by the reference or raw
+      for (int i = tid; i < L; i += K3_NT) zw[i] = A[i];
     }
+  }
+  if (bad) {                                            // NaN windows: parked as z-scored by the reference or raw
+    if (p.zwin && tma_ok && tid == 0) bulk_store_wait_all();
     if (tid == 0) {
       p.keep[w] = 0; p.has_nan[w] = 1; p.n_peaks[w] = 0;
       for (int k = 0; k < 4; ++k) p.stats[4 * w + k] = qnan;
@@ -812,124 +826,173 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, unsigned long
   //  1 up to a few ulp, so it decides sd / n_peaks > threshold only when n_peaks * threshold == 1 -- SURVEY.md
   //  C.1 -- and with p.lazy_sd the sweep is run only for those windows)
 
-  // ---- QRS indicator: smoothgrad > 1.5 * avggrad, smoothgrad / avggrad = box filters (scipy "nearest" edges)
-  // of |gradient| / smoothgrad.  Evaluated with prefix sums, one SEGMENT of the window at a time: for output
-  // samples [a, b) the sums run over the extended positions e = 0 .. Le-1 that stand for samples G0 + e,
-  // G0 = a - la - ls - 1, clamped into the window (edge value repeated), so that a box sum is P[hi] - P[lo]
-  // everywhere and nothing branches on clamping.  Thread t owns e = 13 t .. 13 t + 12 in all three passes.
-  const int ks = p.smooth_k, ka = p.avg_k;
-  const int ls = ks / 2, la = ka / 2;                  // uniform_filter1d: window [i - k/2, i - k/2 + k)
+  // ---- QRS indicator: smoothgrad > 1.5 * avggrad, smoothgrad / avggrad = box filters (scipy "nearest" edges) of
+  // |gradient| / smoothgrad.  Evaluated with prefix sums over the WHOLE window IN PLACE: position e of W stands
+  // for sample e - H clamped into the window (edge value repeated), so that a box sum is P[hi] - P[lo] everywhere.
+  // Thread t owns the strip e = 22 t .. 22 t + 21 in all three passes:
+  //   1  W <- P1 = prefix sums of g' = |z[j+1] - z[j-1]| (each thread reads its strip and one sample either side
+  //      BEFORE anyone writes; the factor 1/2 of np.gradient's central differences and the two 1/k of the box
+  //      filters are exact or common scalings of both sides of the comparison and are folded into ONE constant),
+  //   2  s'(e) = P1[e' + ks] - P1[e'] held in REGISTERS over the block scan whose barrier ends all reads of P1,
+  //      W <- P2 = prefix sums of s',
+  //   3  s' > (1.5 / ka) (P2[e - la - 1 + ka] - P2[e - la - 1]), packed into the bit array.
+  // The z-scored samples then come back from the parked copy (or are formed again from the filter output).
+  // Round 1 / early round 2 evaluated this in four segments with their own prefix buffer: 8 block scans and four
+  // times the per-thread fixed cost per window, 48 % of the kernel's instructions (profiles/r2_k3_windows.txt).
   int hazard = 0;
-  if (p.mode != 1) {
-    const double g0 = fabs(__dsub_rn(A[1], A[0])), gL = fabs(__dsub_rn(A[L - 1], A[L - 2]));
-    const double inv_s = 1.0 / (double)ks, inv_a = 1.0 / (double)ka;
-    const int Ls = (L + K3_SEGS - 1) / K3_SEGS;
+  const bool prefix_passes = p.mode != 1;
+  const bool bulk_restore = p.zwin && p.zscore_windows && tma_ok;
+  if (prefix_passes) {
     const int e0 = tid * K3_ITEMS;
-#pragma unroll 1
-    for (int a = 0; a < L; a += Ls) {
-      const int b = a + Ls < L ? a + Ls : L;
-      const int G0 = a - la - ls - 1;
-      const int Le = b - a + ka + ks - 1;               // <= K3_CAP (checked at launch)
-      const int i0 = G0 + e0;
-      double loc[K3_ITEMS], smv[K3_ITEMS];
-      double run = 0.0;
-      // the path is chosen per WARP: a warp that straddles an edge runs the general form once instead of both
-      if (__all_sync(AEW_FULL, i0 >= 1 && i0 + K3_ITEMS < L && e0 + K3_ITEMS <= Le)) {
-        const double* zp = A + i0;
-        double prv = zp[-1], cur = zp[0];
+    const int j0 = e0 - H;                              // sample the strip's first position stands for
+    const double g0 = 2.0 * fabs(__dsub_rn(A[1], A[0])), gL = 2.0 * fabs(__dsub_rn(A[L - 1], A[L - 2]));
+    const double left = e0 > 0 ? W[e0 - 1] : 0.0;
+    const double right = e0 + K3_ITEMS < K3_WCAP ? W[e0 + K3_ITEMS] : 0.0;
+    if (p.zwin && tma_ok && tid == 0) bulk_store_wait_read(0);   // the bulk engine has read the window
+    __syncthreads();                                    // every strip's neighbours are in registers
+    double2* Wp = reinterpret_cast<double2*>(W + e0);
+    double run = 0.0;
+    if (__all_sync(AEW_FULL, j0 >= 1 && j0 + K3_ITEMS - 1 <= L - 2)) {
+      double prv = left;
+      double2 cur = Wp[0];
 #pragma unroll
-        for (int k = 0; k < K3_ITEMS; ++k) {
-          const double nxt = zp[k + 1];
-          run += fabs(__dmul_rn(__dsub_rn(nxt, prv), 0.5));
-          loc[k] = run;
-          prv = cur; cur = nxt;
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < K3_ITEMS; ++k) {
-          const double g = absgrad_ext(A, i0 + k, L, g0, gL);
-          run += (e0 + k < Le) ? g : 0.0;
-          loc[k] = run;
-        }
+      for (int m = 0; m < K3_ITEMS / 2; ++m) {
+        double2 nxt;
+        if (m + 1 < K3_ITEMS / 2) nxt = Wp[m + 1];
+        else { nxt.x = right; nxt.y = 0.0; }
+        double2 o;
+        run += fabs(cur.y - prv);   o.x = run;          // position e0 + 2m: samples either side
+        run += fabs(nxt.x - cur.x); o.y = run;          // position e0 + 2m + 1
+        Wp[m] = o;
+        prv = cur.y; cur = nxt;
       }
-      double base = block_excl_scan(run, sm.wtot);      // (its barrier also ends the previous segment's reads of B)
-      if (e0 < Le) {
+    } else {                                            // strips that touch an edge of the window (warp-uniform)
+      double prv = left, cur = W[e0];
 #pragma unroll
-        for (int k = 0; k < K3_ITEMS; ++k) B[e0 + k] = base + loc[k];
+      for (int k = 0; k < K3_ITEMS; ++k) {
+        const double nxt = k + 1 < K3_ITEMS ? W[e0 + k + 1] : right;
+        const int j = j0 + k;
+        double g = fabs(nxt - prv);
+        g = j <= 0 ? g0 : g;                            // np.gradient is one-sided at the two ends (x 2 here)
+        g = j >= L - 1 ? gL : g;
+        run += g;
+        W[e0 + k] = run;
+        prv = cur; cur = nxt;
       }
-      __syncthreads();
-      const double ptot = B[Le - 1];
-      // smoothgrad at position e = box sum over positions [e' + 1, e' + ks], e' = clamp(sample) - ls - 1 - G0;
-      // positions whose box leaves the segment are not needed by any output of the segment: 0
-      run = 0.0;
-      if (__all_sync(AEW_FULL, i0 >= 0 && i0 + K3_ITEMS <= L && e0 - ls - 1 >= 0 && e0 + K3_ITEMS - ls - 1 + ks <= Le)) {
-        const double* pl = B + e0 - ls - 1;
-        const double* ph = pl + ks;
+    }
+    double base = block_excl_scan(run, sm.wtot);        // (its barrier follows every strip's local sums)
+    if (tid == K3_NT - 1) sm.scal[4] = base + run;      // sum of g' over all positions: scale of the tie tolerance
 #pragma unroll
-        for (int k = 0; k < K3_ITEMS; ++k) {
-          const double sv = (ph[k] - pl[k]) * inv_s;
-          smv[k] = sv;
-          run += sv;
-          loc[k] = run;
-        }
-      } else {
+    for (int m = 0; m < K3_ITEMS / 2; ++m) {
+      double2 v = Wp[m];
+      v.x += base; v.y += base;
+      Wp[m] = v;
+    }
+    __syncthreads();                                    // P1 complete
+    K3_TICK(3)   // |gradient| prefix sums
+    double sv[K3_ITEMS];
+    run = 0.0;
+    if (__all_sync(AEW_FULL, j0 >= 0 && j0 + K3_ITEMS - 1 <= L - 1)) {
+      const double* pl = W + e0 - ls - 1;
+      const double* ph = pl + ks;
 #pragma unroll
-        for (int k = 0; k < K3_ITEMS; ++k) {
-          int i = i0 + k;
-          i = i < 0 ? 0 : (i > L - 1 ? L - 1 : i);       // edge value repeated
-          const int lo = i - ls - 1 - G0;
-          const bool ok = e0 + k < Le && lo >= 0 && lo + ks < Le;
-          const int lc = ok ? lo : 0;
-          const double sv = ok ? (B[lc + ks] - B[lc]) * inv_s : 0.0;
-          smv[k] = sv;
-          run += sv;
-          loc[k] = run;
-        }
+      for (int k = 0; k < K3_ITEMS; ++k) { sv[k] = ph[k] - pl[k]; run += sv[k]; }
+    } else {
+#pragma unroll
+      for (int k = 0; k < K3_ITEMS; ++k) {
+        int i = j0 + k;
+        i = i < 0 ? 0 : (i > L - 1 ? L - 1 : i);        // smoothgrad's own edge value repeated
+        const double* q = W + (i - ls - 1 + H);
+        sv[k] = q[ks] - q[0];
+        run += sv[k];
       }
-      base = block_excl_scan(run, sm.wtot + K3_NW);     // (its barrier also ends all reads of B)
-      if (e0 < Le) {
+    }
+    base = block_excl_scan(run, sm.wtot + K3_NW);       // (its barrier ends all reads of P1)
+    {
+      double r = base;
 #pragma unroll
-        for (int k = 0; k < K3_ITEMS; ++k) B[e0 + k] = base + loc[k];
+      for (int m = 0; m < K3_ITEMS / 2; ++m) {
+        double2 o;
+        r += sv[2 * m];     o.x = r;
+        r += sv[2 * m + 1]; o.y = r;
+        Wp[m] = o;
       }
-      __syncthreads();
-      // outputs: samples a <= i < b, i.e. positions e = i - G0; avggrad box = P2[e - la - 1 + ka] - P2[e - la - 1]
-      const double tol_abs = 2e-12 * ptot * inv_s;
-      int klo = a - i0, khi = b - i0;
-      klo = klo < 0 ? 0 : (klo > K3_ITEMS ? K3_ITEMS : klo);
-      khi = khi < klo ? klo : (khi > K3_ITEMS ? K3_ITEMS : khi);
-      unsigned qbits = 0;
-      if (khi > klo) {
-        const int pl = e0 - la - 1;
+    }
+    __syncthreads();                                    // P2 complete
+    K3_TICK(4)   // smoothgrad prefix sums
+    // outputs: samples 0 <= j < L; avggrad box of position e = P2[e - la - 1 + ka] - P2[e - la - 1]
+    const double c15 = k3_div(1.5, (double)ka);
+    const double tol_abs = 2e-12 * sm.scal[4];
+    int klo = -j0, khi = L - j0;
+    klo = klo < 0 ? 0 : (klo > K3_ITEMS ? K3_ITEMS : klo);
+    khi = khi < klo ? klo : (khi > K3_ITEMS ? K3_ITEMS : khi);
+    unsigned qbits = 0;
+    if (__all_sync(AEW_FULL, klo == 0 && khi == K3_ITEMS)) {
+      const double* pl = W + e0 - la - 1;
 #pragma unroll
-        for (int k = 0; k < K3_ITEMS; ++k) {
-          if (k >= klo && k < khi) {
-            const double thr = 1.5 * ((B[pl + k + ka] - B[pl + k]) * inv_a);
-            qbits |= (unsigned)(smv[k] > thr) << k;
-            hazard |= (fabs(smv[k] - thr) <= 1e-9 * (smv[k] + thr) + tol_abs) ? 1 : 0;
-          }
-        }
-        // the strip's bits (13 at most) land in one or two words of the bit array
-        const int s0 = i0 + klo;                          // first sample of the strip that is an output
-        const unsigned bits = qbits >> klo;
-        if (bits) {
-          const int wq = s0 >> 5, sh = s0 & 31;
-          atomicOr((int*)sm.Qw + wq, (int)(bits << sh));
-          if (sh > 32 - K3_ITEMS && (bits >> (32 - sh))) atomicOr((int*)sm.Qw + wq + 1, (int)(bits >> (32 - sh)));
+      for (int k = 0; k < K3_ITEMS; ++k) {
+        const double thr = (pl[k + ka] - pl[k]) * c15;
+        qbits |= (unsigned)(sv[k] > thr) << k;
+        hazard |= (fabs(sv[k] - thr) <= 1e-9 * (sv[k] + thr) + tol_abs) ? 1 : 0;
+      }
+    } else if (khi > klo) {
+      const double* pl = W + e0 - la - 1;
+#pragma unroll
+      for (int k = 0; k < K3_ITEMS; ++k) {
+        if (k >= klo && k < khi) {
+          const double thr = (pl[k + ka] - pl[k]) * c15;
+          qbits |= (unsigned)(sv[k] > thr) << k;
+          hazard |= (fabs(sv[k] - thr) <= 1e-9 * (sv[k] + thr) + tol_abs) ? 1 : 0;
         }
       }
     }
-    hazard = __syncthreads_or(hazard);
+    if (khi > klo) {
+      // the strip's bits (22 at most) land in one or two words of the bit array
+      const int s0 = j0 + klo;                          // first sample of the strip that is an output
+      const unsigned bits = qbits >> klo;
+      if (bits) {
+        const int wq = s0 >> 5, sh = s0 & 31;
+        atomicOr((int*)sm.Qw + wq, (int)(bits << sh));
+        if (sh > 32 - K3_ITEMS && (bits >> (32 - sh))) atomicOr((int*)sm.Qw + wq + 1, (int)(bits >> (32 - sh)));
+      }
+    }
+    hazard = __syncthreads_or(hazard);                  // (also ends all reads of P2)
     K3_TICK(5)   // indicator + hazard vote
     if (p.mode == 2) hazard = 0;
     if (p.mode == 3) hazard = 1;                        // test hook: every window takes the fallback transition
     if (hazard && tid == 0 && p.hazard_count) atomicAdd(p.hazard_count, 1ull);
+
+    // ---- the z-scored samples come back
+    if (bulk_restore) {
+      if (tid == 0) {
+        bulk_store_wait_all();                          // the parked copy is complete ...
+        bulk_load(A, p.zwin + w * (long long)L, (unsigned)L * 8u, sm.mbar);   // ... and returns in one bulk copy
+      }
+    } else {
+#ifdef AEW_EMUL
+      for (int i = tid; i < L; i += K3_NT) A[i] = src[i];
+#else
+      const unsigned a0 = (unsigned)__cvta_generic_to_shared(A);
+#pragma unroll 8
+      for (int i = tid; i < L; i += K3_NT)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(a0 + 8u * (unsigned)i), "l"(src + i) : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+      __syncthreads();
+      if (p.zscore_windows) {                           // the same operations on the same operands: the same bits
+        (void)leaf_pass(K3_PASS_ZSCORE, A, src, mean, sd0, offa, sza, lj);
+        __syncthreads();
+      }
+    }
   }
   if (p.mode == 1 || hazard) {
     // SciPy's literal evaluation: one undivided running sum per box filter (appendix B.3), by thread 0.  The
     // second filter reads smoothgrad ka/2 ahead of and behind its position: a ring of the last K3_RING values.
     if (tid == 0) {
+      if (prefix_passes && bulk_restore && !mbar_wait(sm.mbar, 0)) atomicOr(p.status, AEW_DEV_LOOKBACK_TIMEOUT);
       const double dks = (double)ks, dka = (double)ka;
-      double* ring = B;
+      double* ring = sm.ring;
       double t = 0.0;
       for (int e = 0; e < ks; ++e) {
         int j = e - ls; j = j < 0 ? 0 : (j > L - 1 ? L - 1 : j);
@@ -990,8 +1053,16 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, unsigned long
       const int packed = block_excl_scan_int(mine, (int*)sm.wtot);
       int ob = tot_b + (packed & 0xffff), oe = tot_e + (packed >> 16);
       if (tid == K3_NT - 1) sm.iscal[4] = packed + mine;  // round totals
-      while (bbits) { const int k = __ffs(bbits) - 1; bbits &= bbits - 1; sm.beg[ob++] = (unsigned short)(32 * wi + k); }
-      while (ebits) { const int k = __ffs(ebits) - 1; ebits &= ebits - 1; sm.end[oe++] = (unsigned short)(32 * wi + k); }
+      while (bbits) {
+        const int k = __ffs(bbits) - 1; bbits &= bbits - 1;
+        if (ob < K3_MAXRUN) sm.beg[ob] = (unsigned short)(32 * wi + k);
+        ++ob;
+      }
+      while (ebits) {
+        const int k = __ffs(ebits) - 1; ebits &= ebits - 1;
+        if (oe < K3_MAXRUN) sm.end[oe] = (unsigned short)(32 * wi + k);
+        ++oe;
+      }
       __syncthreads();
       const int tot = sm.iscal[4];
       tot_b += tot & 0xffff;
@@ -999,6 +1070,11 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, unsigned long
     }
     nbeg = tot_b;
     nend = tot_e;
+    if (nbeg > K3_MAXRUN || nend > K3_MAXRUN) {          // more runs than the tables hold: reported, not guessed
+      if (tid == 0) atomicOr(p.status, AEW_DEV_RUN_OVERFLOW);
+      nbeg = nbeg > K3_MAXRUN ? K3_MAXRUN : nbeg;
+      nend = nend > K3_MAXRUN ? K3_MAXRUN : nend;
+    }
   }
   K3_TICK(7)   // run compaction
   // ends that precede the first beg are dropped (at most one, runs alternate)
@@ -1017,6 +1093,8 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, unsigned long
   }
   __syncthreads();                                      // beg[] is overwritten by the candidates below
   K3_TICK(8)   // min_len
+  // the z-scored window is back (the bulk copy was issued before the run tables were built)
+  if (prefix_passes && bulk_restore && !mbar_wait(sm.mbar, 0) && tid == 0) atomicOr(p.status, AEW_DEV_LOOKBACK_TIMEOUT);
 
   // ---- per run: most prominent strict local maximum (scipy.signal.find_peaks semantics); cand[r] replaces beg[r]
   for (int r = warp; r < num; r += K3_NT / 32) {
@@ -1084,11 +1162,6 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, unsigned long
       sm.scal[0] = hr;
       sm.scal[1] = rms;
     }
-  } else if (p.zwin) {
-    // meanwhile the other warps park the z-scored window for the delineation kernel / the 'ecg_sample' column
-    double* zw = p.zwin + w * (long long)L;
-#pragma unroll 4
-    for (int i = tid - 32; i < L; i += K3_NT - 32) zw[i] = A[i];
   }
   __syncthreads();
   const int np = sm.iscal[2];
@@ -1227,17 +1300,13 @@ extern "C" int aew_windows_beats_f64(const K3Params* hp, void* stream) {
   if (p.n_win == 0) return AEW_OK;
   if (p.L < 16 || p.L > K3_MAXL || p.n_win < 0 || p.n_win > 0x7fffffffll) return AEW_ERR_UNSUPPORTED;
   if (p.smooth_k < 1 || p.avg_k < 1) return AEW_ERR_UNSUPPORTED;
-  {
-    // one segment of the QRS evaluation (see the kernel) must fit the prefix-sum buffer, the sequential
-    // evaluation's ring must span the second box filter
-    const int seg = (p.L + K3_SEGS - 1) / K3_SEGS;
-    if ((long long)seg + p.avg_k + p.smooth_k - 1 > K3_CAP || p.avg_k + 2 > K3_RING || p.L < 2 * K3_SEGS)
-      return AEW_ERR_UNSUPPORTED;
-  }
+  // the window with the two box filters' halo must fit the window buffer, the sequential evaluation's ring must span
+  // the second box filter
+  if (k3_ext_len(p.L, p.smooth_k, p.avg_k) > K3_WCAP || p.avg_k + 2 > K3_RING) return AEW_ERR_UNSUPPORTED;
   if (pw_depth(p.L) > 7 || p.pre < 0 || p.post < 1 || p.pre + p.post > K3_MAXS || p.smooth_k < 1 || p.avg_k < 1 || p.smooth_k > p.L ||
       p.avg_k > p.L || p.refractory < 1 || (p.L / (p.refractory + 1) + 1) > K3_MAXP || p.n_win > 0x3fffffffll)
     return AEW_ERR_UNSUPPORTED;
-  const size_t smem = k3_smem_layout(nullptr, p.L, p.avg_k + p.smooth_k, nullptr);
+  const size_t smem = k3_smem_layout(nullptr, nullptr);
   if (smem > 113 * 1024) return AEW_ERR_UNSUPPORTED;    // two blocks per SM
   // (per call: the attribute is per DEVICE, and the call costs a fraction of a microsecond)
   if (AEW_SET_MAX_SMEM(k3_windows, 113 * 1024) != 0) return (int)cudaGetLastError();

@@ -134,6 +134,32 @@ def test_k3_screen_golden(golden):
     assert same(o2["keep"], o["keep"]) and same(o2["peaks"], o["peaks"])
 
 
+def test_k3_window_comes_back_after_the_in_place_prefix_sums(golden):
+    """The indicator's prefix sums overwrite the z-scored window; it returns from the parked copy (one bulk copy) or
+    is formed again from the filter output.  mode 3 runs the prefix passes and THEN the sequential evaluation on the
+    restored samples; np.std at the end of the kernel sweeps them once more.  Both restore paths, an odd window
+    length (no 16-byte granules: plain copies), pre-scaled windows: everything equals the sequential mode."""
+    g = golden("e2e")
+    nw = min(int(g["n_windows"]), 6)
+    y = g["filtered"]
+    ref = eh.screen(y, np.arange(nw) * 10000, mode=1, want_z=True)
+    for want_z in (True, False):
+        for mode in (0, 3):
+            o = eh.screen(y, np.arange(nw) * 10000, mode=mode, want_z=want_z)
+            for k in ("keep", "n_peaks", "peaks", "stats", "median", "waves"):
+                assert same(o[k], ref[k]), (want_z, mode, k)
+            if want_z:
+                assert same(o["zwin"], ref["zwin"])
+    Lw = 9999
+    ref = eh.screen(y, np.arange(3) * Lw, Lw=Lw, mode=1, want_z=True)
+    for mode in (0, 3):
+        o = eh.screen(y, np.arange(3) * Lw, Lw=Lw, mode=mode, want_z=True)
+        for k in ("keep", "n_peaks", "peaks", "stats", "median", "zwin"):
+            assert same(o[k], ref[k]), (Lw, mode, k)
+    pre = eh.screen(ref["zwin"].reshape(-1), np.arange(3) * Lw, Lw=Lw, mode=3, zscore_windows=False, want_z=True)
+    assert same(pre["keep"], ref["keep"]) and same(pre["peaks"], ref["peaks"]) and same(pre["median"], ref["median"])
+
+
 def test_k3_lazy_sd_takes_the_same_decisions():
     """lazy_sd: np.std is evaluated only where n_peaks * 0.05 == 1; every keep / remove decision, the peaks and the
     median beats are those of the full evaluation, sd is reported only for the 20-peak windows."""
