@@ -32,7 +32,8 @@ class K3Params(ctypes.Structure):
         ("pvc_threshold", c_double), ("sd_threshold", c_double), ("mode", c_int), ("zscore_windows", c_int),
         ("keep", c_void_p), ("has_nan", c_void_p), ("n_peaks", c_void_p), ("peaks", c_void_p),
         ("stats", c_void_p), ("median", c_void_p), ("waves", c_void_p), ("zwin", c_void_p),
-        ("zparams", c_void_p), ("status", c_void_p), ("hazard_count", c_void_p), ("lazy_sd", c_int)]
+        ("zparams", c_void_p), ("status", c_void_p), ("hazard_count", c_void_p), ("lazy_sd", c_int),
+        ("workspace", c_void_p), ("workspace_bytes", ctypes.c_ulonglong)]
 
 
 # name -> (restype, argtypes); every symbol include/aewave.h declares
@@ -59,6 +60,7 @@ SIGNATURES = {
     "aew_filt_timing_dump": (c_int, [c_void_p]),
     "aew_windows_max_peaks": (c_int, []),
     "aew_windows_max_len": (c_int, []),
+    "aew_windows_workspace_bytes": (c_size_t, [c_longlong]),
     "aew_windows_beats_f64": (c_int, [c_void_p, c_void_p]),
     "aew_windows_timing_dump": (c_int, [c_void_p]),
     "aew_median_beats_f64": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_int, c_int, c_int,

@@ -329,9 +329,9 @@ class Preprocessor:
     def screen_windows(self, y, win_start_h, want_median=True, want_zwin=False, zscore_windows=True,
                        pvc_threshold=None, sd_threshold=None, L=None, zwin_scratch=None, lazy_sd=False,
                        d_start=None):
-        """K3 + K4 on the windows whose flat offsets are given.  ``zwin_scratch``: optional float64 tensor of at
-        least n_win * L elements; the screen kernel parks the z-scored windows there for the median kernel (which
-        otherwise re-derives them from ``y`` and the per-window mean / sd)."""
+        """K3 (window kernel + beat kernel) + K4 on the windows whose flat offsets are given.  ``zwin_scratch``:
+        optional float64 tensor of at least n_win * L elements; the window kernel parks the z-scored windows there
+        for the beat and median kernels (a buffer of this call otherwise)."""
         torch, lib = self.torch, self.lib
         L = L or self.L
         n_win = len(win_start_h)
@@ -353,11 +353,18 @@ class Preprocessor:
             return out
         if d_start is None:
             d_start = self._upload(np.ascontiguousarray(win_start_h, dtype=np.int64))
+        # the z-scored windows are parked for the beat and median kernels: in the caller's buffer ('ecg_sample'),
+        # in the scratch the caller lends (the filter's second buffer), else in a buffer of this call
         zwin_ptr = out["zwin"].data_ptr() if want_zwin else None
-        if zwin_ptr is None and want_median and zscore_windows and zwin_scratch is not None \
-                and zwin_scratch.dtype == torch.float64 and zwin_scratch.numel() >= n_win * L \
-                and zwin_scratch.data_ptr() != y.data_ptr():
-            zwin_ptr = zwin_scratch.data_ptr()
+        if zwin_ptr is None and zscore_windows:
+            if zwin_scratch is not None and zwin_scratch.dtype == torch.float64 \
+                    and zwin_scratch.numel() >= n_win * L and zwin_scratch.data_ptr() != y.data_ptr():
+                zwin_ptr = zwin_scratch.data_ptr()
+            else:
+                out["_zwin_own"] = torch.empty((n_win, L), dtype=torch.float64, device=dev)
+                zwin_ptr = out["_zwin_own"].data_ptr()
+        ws_bytes = int(lib.aew_windows_workspace_bytes(n_win))
+        out["_ws"] = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         fs = self.fs
         p = _cabi.K3Params(
             y=y.data_ptr(), win_start=d_start.data_ptr(), n_win=n_win, L=L,
@@ -373,9 +380,10 @@ class Preprocessor:
             zwin=zwin_ptr,
             zparams=out["zparams"].data_ptr() if want_median else None,
             status=out["status"].data_ptr(), hazard_count=out["hazards"].data_ptr(),
-            lazy_sd=1 if (lazy_sd and zscore_windows) else 0)
+            lazy_sd=1 if (lazy_sd and zscore_windows) else 0,
+            workspace=out["_ws"].data_ptr(), workspace_bytes=ws_bytes)
         _cabi.check(lib.aew_windows_beats_f64(ctypes.byref(p), _cabi.stream_ptr(torch)), "windows_beats")
-        self.launches += 2 if want_median else 1
+        self.launches += 3 if want_median else 2
         out["_win_start"] = d_start
         return out
 

@@ -49,6 +49,7 @@
 #define K3_MAXRUN 2048                    // QRS runs per window the tables hold (a 20 s window has ~25)
 #define K3_RING 512                       // ring of smoothgrad values in the sequential evaluation (> avg_k + 1)
 #define K3_MAXL 10240                     // samples per window at most (80 KB of shared memory)
+#define K3_QWS (K3_MAXL / 32 + 2)         // words of a window's indicator bit array
 #define K3_MAXP 72                        // peaks are > 150 samples apart -> at most 71 in 10752
 #define K3_MAXS 512                       // beat section int(0.64 fs) at most (320 at 500 Hz; median_sample.py:20-21)
 #define K3_NONE 0xffffu
@@ -56,25 +57,25 @@
 
 namespace {
 
-struct K3Smem {
+struct K3Smem {            // shared memory of the window kernel k3_windows
   double* W;            // [K3_WCAP] the window buffer: z-scored samples at W + H, then -- in place -- the prefix sums of
-                        //           |gradient|, then those of smoothgrad, then the z-scored samples again
+                        //           |gradient|, then those of smoothgrad
   double* pw_vals;      // [2][128] leaf sums, double-buffered
   double* wtot;         // [2][16]
   double* scal;         // [16] scalars
-  double* dsq;          // [K3_MAXP] squared successive RR differences
-  int* ipeaks;          // [K3_MAXP]
-  int* idiff;           // [K3_MAXP] RR intervals
-  int* isort;           // [K3_MAXP] RR intervals, sorted
-  int* iscal;           // [16]
   int* leaf_off;        // [128] NumPy-tree leaf ranges of a length-L vector
   int* leaf_size;       // [128]
-  unsigned* Qw;         // [L/32 + 2] QRS indicator, one bit per sample
-  unsigned short* beg;  // [K3_MAXRUN] run tables; cand overwrites beg
-  unsigned short* end;  // [K3_MAXRUN]
-  double* ring;         // [K3_RING] smoothgrad ring of the sequential evaluation (aliases the run tables)
-  unsigned long long* mbar;   // mbarrier of the bulk copy that brings the z-scored window back
+  unsigned* Qw;         // [K3_QWS] QRS indicator, one bit per sample
+  double* ring;         // [K3_RING] smoothgrad ring of the sequential evaluation
+  unsigned long long* mbar;   // mbarrier of the bulk copy that brings the window in
   unsigned char* pw_valid;  // [2][128]
+};
+
+// what the window kernel hands to the beat kernel, per window (device workspace of the call)
+struct K3Ws {
+  unsigned* qbits;      // [n_win][K3_QWS] indicator bits
+  double* sumz;         // [n_win] NumPy-order sum of the z-scored window (np.std's mean)
+  double* sd;           // [n_win] np.std of the z-scored window where the window kernel formed it (lazy_sd == 0)
 };
 
 // first sample's offset inside W: the halo of the two box filters in front of it (even: 16-byte pairs stay aligned)
@@ -93,19 +94,12 @@ __host__ __device__ inline size_t k3_smem_layout(unsigned char* base, K3Smem* s)
   t.pw_vals = (double*)take(sizeof(double) * 256);
   t.wtot = (double*)take(sizeof(double) * 2 * K3_NW);
   t.scal = (double*)take(sizeof(double) * 16);
-  t.dsq = (double*)take(sizeof(double) * K3_MAXP);
-  t.ipeaks = (int*)take(sizeof(int) * K3_MAXP);
-  t.idiff = (int*)take(sizeof(int) * K3_MAXP);
-  t.isort = (int*)take(sizeof(int) * K3_MAXP);
-  t.iscal = (int*)take(sizeof(int) * 16);
   t.leaf_off = (int*)take(sizeof(int) * 128);
   t.leaf_size = (int*)take(sizeof(int) * 128);
   t.pw_valid = (unsigned char*)take(256);
   t.mbar = (unsigned long long*)take(16);
-  t.Qw = (unsigned*)take(sizeof(unsigned) * (K3_MAXL / 32 + 2));
-  t.beg = (unsigned short*)take(sizeof(unsigned short) * 2 * K3_MAXRUN);
-  t.end = base ? t.beg + K3_MAXRUN : (unsigned short*)0;
-  t.ring = (double*)t.beg;
+  t.Qw = (unsigned*)take(sizeof(unsigned) * K3_QWS);
+  t.ring = (double*)take(sizeof(double) * K3_RING);
   t.W = (double*)take(sizeof(double) * K3_WCAP);
   if (s) *s = t;
   return o;
@@ -120,7 +114,7 @@ __device__ __forceinline__ double absgrad(const double* __restrict__ z, int i, i
   return fabs(g);
 }
 
-#ifdef AEW_EMUL
+#if defined(AEW_EMUL) || !defined(AEW_K3_TICKS)     // (an instrumented build: nvcc -DAEW_K3_TICKS; the counters cost registers)
 #define K3_TICK(slot)
 #else
 #define K3_TICK(slot)                                                              \
@@ -323,7 +317,7 @@ __device__ __noinline__ double k3_sqrt(double a) { return __dsqrt_rn(a); }
 // exclusive block scan of one double per thread (fast path; not order-sensitive).  ONE barrier: consecutive scans
 // alternate between two scratch rows (the caller flips `row`), so the warp totals of one scan cannot be
 // overwritten before every warp has read them.
-__device__ __noinline__ double block_excl_scan(double v, double* wtot) {
+__device__ __forceinline__ double block_excl_scan(double v, double* wtot) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double incl = v;
 #pragma unroll
@@ -372,12 +366,13 @@ __device__ __forceinline__ double dkey_inv(unsigned long long k) {
   return __longlong_as_double(t ^ ((~t >> 63) | (long long)0x8000000000000000ull));
 }
 // minimum over the warp of per-lane keys (REDUX on the high words, then on the low words of the lanes that tie)
-__device__ __forceinline__ double warp_min_key(unsigned long long k) {
+__device__ __forceinline__ unsigned long long warp_min_key_raw(unsigned long long k) {
   const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
   const unsigned mh = __reduce_min_sync(AEW_FULL, hi);
   const unsigned ml = __reduce_min_sync(AEW_FULL, hi == mh ? lo : 0xffffffffu);
-  return dkey_inv(((unsigned long long)mh << 32) | ml);
+  return ((unsigned long long)mh << 32) | ml;
 }
+__device__ __forceinline__ double warp_min_key(unsigned long long k) { return dkey_inv(warp_min_key_raw(k)); }
 
 // ---------------------------------------------------------------------- medians
 __device__ __forceinline__ void cex(double& a, double& b) {          // a <- min, b <- max (DSETP + 4 FSEL)
@@ -626,6 +621,49 @@ __device__ __noinline__ int run_peak(const double* __restrict__ d, int n, int la
         pkbits[m] = __ballot_sync(AEW_FULL, is_pk);
       }
     }
+    // Shortcuts before any prominence is formed.  No candidate: no peak.  One candidate: it is the peak.  Several:
+    // the HIGHEST candidate g has no higher sample anywhere in the run, so its prominence is h_g - max(min of the
+    // run left of it, min right of it); every other candidate's prominence is at most (second-highest candidate)
+    // - (minimum of the run), in exact arithmetic and -- rounding being monotonic -- as computed.  If the first
+    // exceeds that bound, g is the answer (an R peak between its Q and S dips against the ripples around it: the
+    // common case); otherwise, or if the highest value is shared, the candidates are walked one by one below.
+    {
+      const int cnt = __popc(pkbits[0]) + __popc(pkbits[1]) + __popc(pkbits[2]) + __popc(pkbits[3]);
+      if (cnt == 0) return 0x7fffffff;
+      if (cnt == 1) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+          if (pkbits[m]) return 32 * m + __ffs((int)pkbits[m]) - 1;
+      }
+      unsigned long long ck = 0ull;                          // highest candidate key of this lane
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+        if (((pkbits[m] >> lane) & 1u) && kv[m] > ck) ck = kv[m];
+      const unsigned long long Mk = ~warp_min_key_raw(~ck);  // maximum over the warp
+      int g = -1, ties = 0;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const unsigned b = __ballot_sync(AEW_FULL, ((pkbits[m] >> lane) & 1u) && kv[m] == Mk);
+        ties += __popc(b);
+        if (b && g < 0) g = 32 * m + __ffs((int)b) - 1;
+      }
+      if (ties == 1) {
+        unsigned long long c2 = 0ull, kl = ~0ull, kr = ~0ull;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const int i = 32 * m + lane;
+          if (((pkbits[m] >> lane) & 1u) && i != g && kv[m] > c2) c2 = kv[m];
+          if (i < n && i <= g && kv[m] < kl) kl = kv[m];
+          if (i < n && i >= g && kv[m] < kr) kr = kv[m];
+        }
+        const double h2 = dkey_inv(~warp_min_key_raw(~c2));
+        const double lmin = dkey_inv(warp_min_key_raw(kl)), rmin = dkey_inv(warp_min_key_raw(kr));
+        const double hg = dkey_inv(Mk);
+        const double prom_g = __dsub_rn(hg, lmin > rmin ? lmin : rmin);
+        const double bound = __dsub_rn(h2, lmin < rmin ? lmin : rmin);
+        if (prom_g > bound) return g;
+      }
+    }
     // candidates in ascending order; ONE copy of the prominence code
 #pragma unroll 1
     for (int m = 0; m < 4; ++m) {
@@ -698,7 +736,37 @@ __device__ __forceinline__ double absgrad_ext(const double* __restrict__ A, int 
   return i >= L - 1 ? gL : g;
 }
 
-__global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, unsigned long long* dbg) {
+// d[k] = hi[k] - lo[k] for the K3_ITEMS consecutive entries behind two positions of the window buffer, read with
+// 16-byte loads whatever the parity of the two positions (a thread's strip starts at an even position, so the
+// parities are uniform over the block): at a stride of 22 doubles, 8-byte accesses of a warp collide two to a bank
+// pair and took twice the shared-memory wavefronts.  f(k, d) consumes the differences in order.
+template <bool LO_ODD, bool HI_ODD, class F>
+__device__ __forceinline__ void tap_diff(const double* lo, const double* hi, F&& f) {
+  const double2* ql = reinterpret_cast<const double2*>(lo - (LO_ODD ? 1 : 0));
+  const double2* qh = reinterpret_cast<const double2*>(hi - (HI_ODD ? 1 : 0));
+  double2 tl, th;
+  tl.x = tl.y = th.x = th.y = 0.0;
+  if (LO_ODD) tl = ql[0];
+  if (HI_ODD) th = qh[0];
+#pragma unroll
+  for (int m = 0; m < K3_ITEMS / 2; ++m) {
+    double l0, l1, h0, h1;
+    if (!LO_ODD) { tl = ql[m]; l0 = tl.x; l1 = tl.y; } else { l0 = tl.y; tl = ql[m + 1]; l1 = tl.x; }
+    if (!HI_ODD) { th = qh[m]; h0 = th.x; h1 = th.y; } else { h0 = th.y; th = qh[m + 1]; h1 = th.x; }
+    f(2 * m, h0 - l0);
+    f(2 * m + 1, h1 - l1);
+  }
+}
+template <class F>
+__device__ __forceinline__ void tap_diff_any(const double* W, int lo, int hi, F&& f) {
+  if ((lo & 1) == 0) {
+    if ((hi & 1) == 0) tap_diff<false, false>(W + lo, W + hi, f); else tap_diff<false, true>(W + lo, W + hi, f);
+  } else {
+    if ((hi & 1) == 0) tap_diff<true, false>(W + lo, W + hi, f); else tap_diff<true, true>(W + lo, W + hi, f);
+  }
+}
+
+__global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, K3Ws ws, unsigned long long* dbg) {
   AEW_DYN_SMEM(smem_raw);
   K3Smem sm;
   k3_smem_layout(smem_raw, &sm);
@@ -748,23 +816,27 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, unsigned long
     sm.leaf_size[tid] = (int)size;
   }
   for (int i = tid; i < L / 32 + 2; i += K3_NT) sm.Qw[i] = 0u;
-  if (tid == 0) mbar_init(sm.mbar, 1);
 
-  // ---- load (coalesced).  Asynchronous copies straight into shared memory: all 20 requests of a thread are in
-  //      flight at once and no registers are staged (8-byte form: a window start is only 8-byte aligned)
+  // ---- load.  ONE bulk copy global -> shared (TMA, completion on an mbarrier) issued by thread 0 where the window
+  //      starts on a 16-byte boundary; 8-byte asynchronous copies by all threads otherwise (20 requests per thread
+  //      in flight at once, no registers staged)
+  const bool tma_in = (L & 1) == 0 && ((unsigned long long)src & 15ull) == 0;
+  if (tma_in) {
+    if (tid == 0) { mbar_init(sm.mbar, 1); bulk_load(A, src, (unsigned)L * 8u, sm.mbar); }
+  } else {
 #ifdef AEW_EMUL
-  for (int i = tid; i < L; i += K3_NT) A[i] = src[i];
+    for (int i = tid; i < L; i += K3_NT) A[i] = src[i];
 #else
-  {
     const unsigned a0 = (unsigned)__cvta_generic_to_shared(A);
 #pragma unroll 8
     for (int i = tid; i < L; i += K3_NT)
       asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(a0 + 8u * (unsigned)i), "l"(src + i) : "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-  }
 #endif
-  __syncthreads();                                      // window, leaf table
+  }
+  __syncthreads();                                      // window (or its mbarrier), leaf table
+  if (tma_in && !mbar_wait(sm.mbar, 0) && tid == 0) atomicOr(p.status, AEW_DEV_LOOKBACK_TIMEOUT);
   // one leaf per group of four threads
   const int slot = tid >> 2, lj = tid & 3;
   const int nslots = 1 << depth;
@@ -799,6 +871,16 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, unsigned long
     bad = __syncthreads_or(flag);
     if (tid == 0 && p.zparams) { p.zparams[2 * w] = mean; p.zparams[2 * w + 1] = sd0; }   // for the median kernel
   }
+  // ecg_sd = np.std(window) (remove_samples.py:62) of the z-scored window is 1 up to a few ulp: it decides
+  // sd / n_peaks > threshold only when n_peaks * threshold == 1.  With lazy_sd the beat kernel forms
+  // it for those windows alone (from the parked copy); without, it is formed here for every window.
+  double sd_full = qnan;
+  if (!bad && !p.lazy_sd) {
+    double ssq2;
+    K3_SWEEP(K3_PASS_DEV2, k3_div(sum_z, (double)L), 1.0, ssq2, flag)
+    sd_full = k3_sqrt(k3_div(ssq2, (double)L));
+  }
+#undef K3_SWEEP
   K3_TICK(1)   // window z-score (+ sum of the z-scored window)
   // the z-scored window is parked for the median / delineation kernels ('ecg_sample' column): ONE bulk copy
   // shared -> global issued by thread 0 where the addresses allow it (16-byte granules), plain stores otherwise
@@ -821,10 +903,12 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, unsigned long
     for (int i = tid; i < K3_MAXP; i += K3_NT) p.peaks[w * K3_MAXP + i] = -1;
     return;
   }
-
-  // (ecg_sd = np.std(window), remove_samples.py:62, is formed at the END of the kernel: of a z-scored window it is
-  //  1 up to a few ulp, so it decides sd / n_peaks > threshold only when n_peaks * threshold == 1 -- SURVEY.md
-  //  C.1 -- and with p.lazy_sd the sweep is run only for those windows)
+  if (tid == 0) {                                       // what the beat kernel needs besides the bits
+    ws.sumz[w] = sum_z;
+    ws.sd[w] = sd_full;
+    p.has_nan[w] = 0;
+    sm.scal[0] = mean; sm.scal[1] = sd0;                // (for the sequential evaluation's restore, if it comes to that)
+  }
 
   // ---- QRS indicator: smoothgrad > 1.5 * avggrad, smoothgrad / avggrad = box filters (scipy "nearest" edges) of
   // |gradient| / smoothgrad.  Evaluated with prefix sums over the WHOLE window IN PLACE: position e of W stands
@@ -836,12 +920,11 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, unsigned long
   //   2  s'(e) = P1[e' + ks] - P1[e'] held in REGISTERS over the block scan whose barrier ends all reads of P1,
   //      W <- P2 = prefix sums of s',
   //   3  s' > (1.5 / ka) (P2[e - la - 1 + ka] - P2[e - la - 1]), packed into the bit array.
-  // The z-scored samples then come back from the parked copy (or are formed again from the filter output).
+  // The bits go to the beat kernel (k3_beats), which reads the z-scored samples it needs from the parked copy.
   // Round 1 / early round 2 evaluated this in four segments with their own prefix buffer: 8 block scans and four
   // times the per-thread fixed cost per window, 48 % of the kernel's instructions (profiles/r2_k3_windows.txt).
   int hazard = 0;
   const bool prefix_passes = p.mode != 1;
-  const bool bulk_restore = p.zwin && p.zscore_windows && tma_ok;
   if (prefix_passes) {
     const int e0 = tid * K3_ITEMS;
     const int j0 = e0 - H;                              // sample the strip's first position stands for
@@ -852,6 +935,8 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, unsigned long
     __syncthreads();                                    // every strip's neighbours are in registers
     double2* Wp = reinterpret_cast<double2*>(W + e0);
     double run = 0.0;
+    double loc[K3_ITEMS];                               // the strip's local prefix sums: held over the block scan, so
+                                                        // that the strip is written ONCE, with its base added
     if (__all_sync(AEW_FULL, j0 >= 1 && j0 + K3_ITEMS - 1 <= L - 2)) {
       double prv = left;
       double2 cur = Wp[0];
@@ -860,10 +945,8 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, unsigned long
         double2 nxt;
         if (m + 1 < K3_ITEMS / 2) nxt = Wp[m + 1];
         else { nxt.x = right; nxt.y = 0.0; }
-        double2 o;
-        run += fabs(cur.y - prv);   o.x = run;          // position e0 + 2m: samples either side
-        run += fabs(nxt.x - cur.x); o.y = run;          // position e0 + 2m + 1
-        Wp[m] = o;
+        run += fabs(cur.y - prv);   loc[2 * m] = run;       // position e0 + 2m: samples either side
+        run += fabs(nxt.x - cur.x); loc[2 * m + 1] = run;   // position e0 + 2m + 1
         prv = cur.y; cur = nxt;
       }
     } else {                                            // strips that touch an edge of the window (warp-uniform)
@@ -876,27 +959,24 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, unsigned long
         g = j <= 0 ? g0 : g;                            // np.gradient is one-sided at the two ends (x 2 here)
         g = j >= L - 1 ? gL : g;
         run += g;
-        W[e0 + k] = run;
+        loc[k] = run;
         prv = cur; cur = nxt;
       }
     }
-    double base = block_excl_scan(run, sm.wtot);        // (its barrier follows every strip's local sums)
+    double base = block_excl_scan(run, sm.wtot);        // (its barrier follows every strip's reads of the samples)
     if (tid == K3_NT - 1) sm.scal[4] = base + run;      // sum of g' over all positions: scale of the tie tolerance
 #pragma unroll
     for (int m = 0; m < K3_ITEMS / 2; ++m) {
-      double2 v = Wp[m];
-      v.x += base; v.y += base;
-      Wp[m] = v;
+      double2 o;
+      o.x = base + loc[2 * m]; o.y = base + loc[2 * m + 1];
+      Wp[m] = o;
     }
     __syncthreads();                                    // P1 complete
     K3_TICK(3)   // |gradient| prefix sums
     double sv[K3_ITEMS];
     run = 0.0;
     if (__all_sync(AEW_FULL, j0 >= 0 && j0 + K3_ITEMS - 1 <= L - 1)) {
-      const double* pl = W + e0 - ls - 1;
-      const double* ph = pl + ks;
-#pragma unroll
-      for (int k = 0; k < K3_ITEMS; ++k) { sv[k] = ph[k] - pl[k]; run += sv[k]; }
+      tap_diff_any(W, e0 - ls - 1, e0 - ls - 1 + ks, [&](int k, double d) { sv[k] = d; run += d; });
     } else {
 #pragma unroll
       for (int k = 0; k < K3_ITEMS; ++k) {
@@ -927,22 +1007,32 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, unsigned long
     klo = klo < 0 ? 0 : (klo > K3_ITEMS ? K3_ITEMS : klo);
     khi = khi < klo ? klo : (khi > K3_ITEMS ? K3_ITEMS : khi);
     unsigned qbits = 0;
+    // smoothgrad of the strip comes back as differences of its own prefix sums (an error of one ulp of the prefix,
+    // a hundredth of the tie tolerance): the 22 values of pass 2 need not stay in registers through this pass
+    double prevP = e0 > 0 ? W[e0 - 1] : 0.0;
+    double2 own;
+    own.x = own.y = 0.0;
     if (__all_sync(AEW_FULL, klo == 0 && khi == K3_ITEMS)) {
-      const double* pl = W + e0 - la - 1;
-#pragma unroll
-      for (int k = 0; k < K3_ITEMS; ++k) {
-        const double thr = (pl[k + ka] - pl[k]) * c15;
-        qbits |= (unsigned)(sv[k] > thr) << k;
-        hazard |= (fabs(sv[k] - thr) <= 1e-9 * (sv[k] + thr) + tol_abs) ? 1 : 0;
-      }
+      tap_diff_any(W, e0 - la - 1, e0 - la - 1 + ka, [&](int k, double d) {
+        if ((k & 1) == 0) own = Wp[k >> 1];
+        const double cur = (k & 1) ? own.y : own.x;
+        const double sk = cur - prevP;
+        prevP = cur;
+        const double thr = d * c15;
+        qbits |= (unsigned)(sk > thr) << k;
+        hazard |= (fabs(sk - thr) <= 1e-9 * (sk + thr) + tol_abs) ? 1 : 0;
+      });
     } else if (khi > klo) {
       const double* pl = W + e0 - la - 1;
 #pragma unroll
       for (int k = 0; k < K3_ITEMS; ++k) {
+        const double cur = W[e0 + k];
+        const double sk = cur - prevP;
+        prevP = cur;
         if (k >= klo && k < khi) {
           const double thr = (pl[k + ka] - pl[k]) * c15;
-          qbits |= (unsigned)(sv[k] > thr) << k;
-          hazard |= (fabs(sv[k] - thr) <= 1e-9 * (sv[k] + thr) + tol_abs) ? 1 : 0;
+          qbits |= (unsigned)(sk > thr) << k;
+          hazard |= (fabs(sk - thr) <= 1e-9 * (sk + thr) + tol_abs) ? 1 : 0;
         }
       }
     }
@@ -962,35 +1052,33 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, unsigned long
     if (p.mode == 3) hazard = 1;                        // test hook: every window takes the fallback transition
     if (hazard && tid == 0 && p.hazard_count) atomicAdd(p.hazard_count, 1ull);
 
-    // ---- the z-scored samples come back
-    if (bulk_restore) {
-      if (tid == 0) {
-        bulk_store_wait_all();                          // the parked copy is complete ...
-        bulk_load(A, p.zwin + w * (long long)L, (unsigned)L * 8u, sm.mbar);   // ... and returns in one bulk copy
-      }
-    } else {
+  }
+  if (p.mode == 1 || hazard) {
+    if (prefix_passes) {
+      // ---- the z-scored samples come back for the sequential evaluation (rare): the window is read again and the
+      //      z-score sweep repeated -- the same operations on the same operands, the same bits
 #ifdef AEW_EMUL
       for (int i = tid; i < L; i += K3_NT) A[i] = src[i];
 #else
       const unsigned a0 = (unsigned)__cvta_generic_to_shared(A);
-#pragma unroll 8
+#pragma unroll 4
       for (int i = tid; i < L; i += K3_NT)
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(a0 + 8u * (unsigned)i), "l"(src + i) : "memory");
       asm volatile("cp.async.commit_group;" ::: "memory");
       asm volatile("cp.async.wait_group 0;" ::: "memory");
 #endif
       __syncthreads();
-      if (p.zscore_windows) {                           // the same operations on the same operands: the same bits
-        (void)leaf_pass(K3_PASS_ZSCORE, A, src, mean, sd0, offa, sza, lj);
+      if (p.zscore_windows) {
+        const int slot2 = tid >> 2;
+        const bool in = slot2 < (1 << pw_depth(L));
+        (void)leaf_pass(K3_PASS_ZSCORE, A, src, sm.scal[0], sm.scal[1], in ? sm.leaf_off[slot2] : 0,
+                        in ? sm.leaf_size[slot2] : 0, tid & 3);
         __syncthreads();
       }
     }
-  }
-  if (p.mode == 1 || hazard) {
     // SciPy's literal evaluation: one undivided running sum per box filter (appendix B.3), by thread 0.  The
     // second filter reads smoothgrad ka/2 ahead of and behind its position: a ring of the last K3_RING values.
     if (tid == 0) {
-      if (prefix_passes && bulk_restore && !mbar_wait(sm.mbar, 0)) atomicOr(p.status, AEW_DEV_LOOKBACK_TIMEOUT);
       const double dks = (double)ks, dka = (double)ka;
       double* ring = sm.ring;
       double t = 0.0;
@@ -1033,93 +1121,181 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, unsigned long
   }
   K3_TICK(6)   // sequential fallback (hazard windows / mode 1)
 
-  // ---- QRS runs: beg where ~q[i] & q[i+1], end where q[i] & ~q[i+1]  (ordered compaction, one word of the
-  //      bit array per thread and round); the run tables take over the prefix-sum buffer
+  // ---- the indicator leaves for the beat kernel (k3_beats): one bit per sample, and what np.std will need there
+  {
+    unsigned* qout = ws.qbits + (size_t)blockIdx.x * K3_QWS;
+    for (int i = tid; i < (L + 31) / 32 + 1; i += K3_NT) qout[i] = sm.Qw[i];
+    if (p.zwin && tma_ok && tid == 0) bulk_store_wait_all();   // the parked copy is complete before the block ends
+  }
+  K3_TICK(7)   // bits out
+}
+
+// ---- the beat kernel: QRS runs -> R peaks -> HR / RMSSD / np.std -> keep decision, from the indicator bits of the
+// window kernel and the parked z-scored samples.  A kernel of its own with SMALL blocks (128 threads, ~17 KB of
+// shared memory, eight blocks per SM): this part of the path is a chain of short, mostly one-warp steps on a few
+// dozen numbers.  Inside the window kernel it ran while the block's 90 KB window buffer sat idle, two windows per
+// SM, and its ~2,500 cold instructions were fetched from L2 once per window (profiles/README.md, "instruction
+// fetch"); here eight windows per SM overlap each other's latencies and the code stays in the instruction cache.
+#define K3P_NT 128
+#define K3P_NW (K3P_NT / 32)
+#define K3P_WPT ((K3_QWS + K3P_NT - 1) / K3P_NT)      // indicator words per thread (3)
+
+__device__ __forceinline__ int beats_excl_scan_int(int v, int* wtot) {   // 128 threads, one barrier
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(AEW_FULL, incl, d);
+    if (lane >= d) incl += o;
+  }
+  if (lane == 31) wtot[warp] = incl;
+  __syncthreads();
+  int before = 0;
+#pragma unroll
+  for (int k = 0; k < K3P_NW; ++k) before += (k < warp) ? wtot[k] : 0;
+  return before + (incl - v);
+}
+
+struct SumDev2 {                                        // (z[i] - m)^2 of samples in global memory
+  const double* z; double m;
+  __device__ __forceinline__ double operator()(long long i, bool) { const double d = __dsub_rn(z[i], m); return __dmul_rn(d, d); }
+};
+
+__global__ void __launch_bounds__(K3P_NT, 8) k3_beats(K3Params p, K3Ws ws) {
+  __shared__ unsigned s_q[K3_QWS + 2];
+  __shared__ unsigned short s_beg[K3_MAXRUN], s_end[K3_MAXRUN];
+  __shared__ double s_run[K3P_NW][136];               // a run's samples, one row per warp
+  __shared__ double s_vals[128], s_dsq[K3_MAXP], s_scal[4];
+  __shared__ unsigned char s_valid[128];
+  __shared__ int s_ipeaks[K3_MAXP], s_idiff[K3_MAXP], s_isort[K3_MAXP], s_wtot[K3P_NW + 1], s_iscal[4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int L = p.L;
+  const long long w = blockIdx.x;
+  const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+  if (p.has_nan[w] != 0) return;                        // NaN / padding windows: the window kernel has written their rows
+  const double* z = p.zscore_windows ? p.zwin + w * (long long)L : p.y + p.win_start[w];
+  const int nwords = (L + 31) >> 5;
+  {
+    const unsigned* qin = ws.qbits + (size_t)w * K3_QWS;
+    for (int i = tid; i < nwords + 1; i += K3P_NT) s_q[i] = i < nwords ? qin[i] : 0u;
+  }
+  __syncthreads();
+
+  // ---- QRS runs: beg where ~q[i] & q[i+1], end where q[i] & ~q[i+1] (ordered compaction: each thread takes
+  //      K3P_WPT consecutive words of the bit array, one block scan of the packed counts)
   int nbeg, nend;
   {
-    const int nwords = (L + 31) >> 5;
-    int tot_b = 0, tot_e = 0;
-#pragma unroll 1
-    for (int w0 = 0; w0 < nwords; w0 += K3_NT) {
-      const int wi = w0 + tid;
+    unsigned bb[K3P_WPT], eb[K3P_WPT];
+    int mine = 0;
+#pragma unroll
+    for (int u = 0; u < K3P_WPT; ++u) {
+      const int wi = tid * K3P_WPT + u;
       unsigned qb = 0, nx = 0;
-      if (wi < nwords) { qb = sm.Qw[wi]; nx = sm.Qw[wi + 1] & 1u; }
+      if (wi < nwords) { qb = s_q[wi]; nx = s_q[wi + 1] & 1u; }
       const unsigned nextq = (qb >> 1) | (nx << 31);      // flag of sample i + 1
       int nval = L - 1 - 32 * wi;                         // transitions exist for 0 <= i < L - 1
       nval = nval < 0 ? 0 : (nval > 32 ? 32 : nval);
       const unsigned vmask = nval >= 32 ? 0xffffffffu : ((1u << nval) - 1u);
-      unsigned bbits = ~qb & nextq & vmask, ebits = qb & ~nextq & vmask;
-      const int mine = __popc(bbits) | (__popc(ebits) << 16);
-      const int packed = block_excl_scan_int(mine, (int*)sm.wtot);
-      int ob = tot_b + (packed & 0xffff), oe = tot_e + (packed >> 16);
-      if (tid == K3_NT - 1) sm.iscal[4] = packed + mine;  // round totals
-      while (bbits) {
-        const int k = __ffs(bbits) - 1; bbits &= bbits - 1;
-        if (ob < K3_MAXRUN) sm.beg[ob] = (unsigned short)(32 * wi + k);
+      bb[u] = ~qb & nextq & vmask; eb[u] = qb & ~nextq & vmask;
+      mine += __popc(bb[u]) | (__popc(eb[u]) << 16);
+    }
+    const int packed = beats_excl_scan_int(mine, s_wtot);
+    if (tid == K3P_NT - 1) s_iscal[0] = packed + mine;    // totals
+    int ob = packed & 0xffff, oe = packed >> 16;
+#pragma unroll
+    for (int u = 0; u < K3P_WPT; ++u) {
+      const int wi = tid * K3P_WPT + u;
+      unsigned b = bb[u], e = eb[u];
+      while (b) {
+        const int k = __ffs(b) - 1; b &= b - 1;
+        if (ob < K3_MAXRUN) s_beg[ob] = (unsigned short)(32 * wi + k);
         ++ob;
       }
-      while (ebits) {
-        const int k = __ffs(ebits) - 1; ebits &= ebits - 1;
-        if (oe < K3_MAXRUN) sm.end[oe] = (unsigned short)(32 * wi + k);
+      while (e) {
+        const int k = __ffs(e) - 1; e &= e - 1;
+        if (oe < K3_MAXRUN) s_end[oe] = (unsigned short)(32 * wi + k);
         ++oe;
       }
-      __syncthreads();
-      const int tot = sm.iscal[4];
-      tot_b += tot & 0xffff;
-      tot_e += tot >> 16;
     }
-    nbeg = tot_b;
-    nend = tot_e;
+    __syncthreads();
+    nbeg = s_iscal[0] & 0xffff;
+    nend = s_iscal[0] >> 16;
     if (nbeg > K3_MAXRUN || nend > K3_MAXRUN) {          // more runs than the tables hold: reported, not guessed
       if (tid == 0) atomicOr(p.status, AEW_DEV_RUN_OVERFLOW);
       nbeg = nbeg > K3_MAXRUN ? K3_MAXRUN : nbeg;
       nend = nend > K3_MAXRUN ? K3_MAXRUN : nend;
     }
   }
-  K3_TICK(7)   // run compaction
   // ends that precede the first beg are dropped (at most one, runs alternate)
-  const int skip = (nbeg > 0 && nend > 0 && sm.end[0] <= sm.beg[0]) ? 1 : 0;
+  const int skip = (nbeg > 0 && nend > 0 && s_end[0] <= s_beg[0]) ? 1 : 0;
   int num = nend - skip < nbeg ? nend - skip : nbeg;
   if (nbeg == 0) num = 0;
-  const unsigned short* endp = sm.end + skip;
+  const unsigned short* endp = s_end + skip;
 
   // ---- min_len = mean(end - beg) * 0.4 (integer sum is exact in any order); every warp computes it for itself
   double min_len = 0.0;
   {
     unsigned part = 0;                                  // <= num * L < 2^31
-    for (int i = lane; i < num; i += 32) part += (unsigned)(endp[i] - sm.beg[i]);
+    for (int i = lane; i < num; i += 32) part += (unsigned)(endp[i] - s_beg[i]);
     const unsigned tot = __reduce_add_sync(AEW_FULL, part);
     if (num > 0) min_len = __dmul_rn(k3_div((double)tot, (double)num), 0.4);
   }
   __syncthreads();                                      // beg[] is overwritten by the candidates below
-  K3_TICK(8)   // min_len
-  // the z-scored window is back (the bulk copy was issued before the run tables were built)
-  if (prefix_passes && bulk_restore && !mbar_wait(sm.mbar, 0) && tid == 0) atomicOr(p.status, AEW_DEV_LOOKBACK_TIMEOUT);
 
-  // ---- per run: most prominent strict local maximum (scipy.signal.find_peaks semantics); cand[r] replaces beg[r]
-  for (int r = warp; r < num; r += K3_NT / 32) {
-    const int b = sm.beg[r], e = endp[r];
+  // ---- per run: most prominent strict local maximum (scipy.signal.find_peaks semantics); cand[r] replaces beg[r].
+  //      A run of up to 128 samples is copied into the warp's row first (one coalesced read of the parked window)
+  for (int r = warp; r < num; r += K3P_NW) {
+    const int b = s_beg[r], e = endp[r];
     const int n = e - b;
     int best_i = 0x7fffffff;
-    if (!((double)n < min_len)) best_i = run_peak(A + b, n, lane);
+    if (!((double)n < min_len)) {
+      if (n <= 128) {
+        double* row = s_run[warp];
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+          if (32 * m + lane < n) row[32 * m + lane] = z[b + 32 * m + lane];
+        __syncwarp();
+        best_i = run_peak(row, n, lane);
+      } else {
+        best_i = run_peak(z + b, n, lane);                // long runs (noise): straight from global memory
+      }
+    }
     __syncwarp();
-    if (lane == 0) sm.beg[r] = best_i == 0x7fffffff ? (unsigned short)K3_NONE : (unsigned short)(b + best_i);
+    if (lane == 0) s_beg[r] = best_i == 0x7fffffff ? (unsigned short)K3_NONE : (unsigned short)(b + best_i);
   }
   __syncthreads();
-  K3_TICK(9)   // most prominent peak per run
-  const unsigned short* cand = sm.beg;
+  const unsigned short* cand = s_beg;
 
   // ---- everything between the candidates and the keep decision is a few hundred operations on <= 72 numbers:
-  //      warp 0 does it alone, ordered by warp barriers, while the other warps wait at ONE block barrier
+  //      warp 0 does it alone, ordered by warp barriers
   if (warp == 0) {
-    // refractory chain (sequential by definition); all lanes walk it alike so that all of them know np
-    int np = 0, last = 0;
-    for (int r = 0; r < num; ++r) {
-      const int c = cand[r];
-      if (c != (int)K3_NONE && c - last > p.refractory) {
-        if (np < K3_MAXP && lane == 0) sm.ipeaks[np] = c;
-        ++np;
-        last = c;
+    int np = 0;
+    bool chained = false;
+    if (num <= 32) {
+      // refractory chain, all candidates at once: if every candidate is more than the refractory period behind
+      // the previous one, every one is kept (the sequential rule compares with the last KEPT one, which then is
+      // the previous one)
+      const int c = lane < num ? (int)cand[lane] : (int)K3_NONE;
+      const bool have = c != (int)K3_NONE;
+      const unsigned mask = __ballot_sync(AEW_FULL, have);
+      const unsigned below = mask & ((1u << lane) - 1u);
+      const int prev = __shfl_sync(AEW_FULL, c, below ? 31 - __clz((int)below) : 0);
+      const bool ok = !have || c - (below ? prev : 0) > p.refractory;
+      if (__all_sync(AEW_FULL, ok)) {
+        np = __popc(mask);
+        if (have) s_ipeaks[__popc(below)] = c;
+        chained = true;
+      }
+    }
+    if (!chained) {                                        // sequential by definition; all lanes walk it alike
+      int last = 0;
+      for (int r = 0; r < num; ++r) {
+        const int c = cand[r];
+        if (c != (int)K3_NONE && c - last > p.refractory) {
+          if (np < K3_MAXP && lane == 0) s_ipeaks[np] = c;
+          ++np;
+          last = c;
+        }
       }
     }
     if (np > K3_MAXP) { if (lane == 0) atomicOr(p.status, AEW_DEV_RUN_OVERFLOW); np = K3_MAXP; }
@@ -1128,71 +1304,72 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, unsigned long
     // HR = 60 fs / median(RR) and RMSSD (remove_samples.py:85-121)
     const int nd = np - 1;
     for (int t = lane; t < nd; t += 32) {
-      const int d0 = sm.ipeaks[t + 1] - sm.ipeaks[t];
-      sm.idiff[t] = d0;
+      const int d0 = s_ipeaks[t + 1] - s_ipeaks[t];
+      s_idiff[t] = d0;
       if (t + 1 < nd) {
-        const double cur = k3_div((double)(sm.ipeaks[t + 2] - sm.ipeaks[t + 1]), p.rr_div);
+        const double cur = k3_div((double)(s_ipeaks[t + 2] - s_ipeaks[t + 1]), p.rr_div);
         const double prv = k3_div((double)d0, p.rr_div);
         const double dd = __dsub_rn(cur, prv);
-        sm.dsq[t] = __dmul_rn(dd, dd);
+        s_dsq[t] = __dmul_rn(dd, dd);
       }
     }
     __syncwarp();
     for (int t = lane; t < nd; t += 32) {                  // rank sort of <= 71 integers
-      const int mine = sm.idiff[t];
+      const int mine = s_idiff[t];
       int rank = 0;
       for (int j = 0; j < nd; ++j) {
-        const int o = sm.idiff[j];
+        const int o = s_idiff[j];
         rank += (o < mine) || (o == mine && j < t);
       }
-      sm.isort[rank] = mine;
+      s_isort[rank] = mine;
     }
-    SumPlain fq{sm.dsq};                                   // NumPy leaf order over np-2 <= 70 values
+    SumPlain fq{s_dsq};                                    // NumPy leaf order over np-2 <= 70 values
     const double ssq = pw_leaf_sum8(fq, 0, np >= 3 ? np - 2 : 0, lane & 7);
     __syncwarp();
     if (lane == 0) {
       double hr = qnan, rms = qnan;
       if (np >= 2) {
-        const double med = (nd & 1) ? (double)sm.isort[nd / 2]
-                                    : __dmul_rn(__dadd_rn((double)sm.isort[nd / 2 - 1], (double)sm.isort[nd / 2]), 0.5);
+        const double med = (nd & 1) ? (double)s_isort[nd / 2]
+                                    : __dmul_rn(__dadd_rn((double)s_isort[nd / 2 - 1], (double)s_isort[nd / 2]), 0.5);
         hr = k3_div(p.hr_num, med);
       }
       if (np >= 3) rms = k3_sqrt(k3_div(ssq, (double)(np - 2)));
-      sm.iscal[2] = np;
-      sm.scal[0] = hr;
-      sm.scal[1] = rms;
+      s_iscal[2] = np;
+      s_scal[0] = hr;
+      s_scal[1] = rms;
     }
   }
   __syncthreads();
-  const int np = sm.iscal[2];
-  for (int i = tid; i < K3_MAXP; i += K3_NT) p.peaks[w * K3_MAXP + i] = i < np ? sm.ipeaks[i] : -1;
-  K3_TICK(11)  // refractory chain, HR / RMSSD, peaks out
+  const int np = s_iscal[2];
+  if (tid < K3_MAXP) p.peaks[w * K3_MAXP + tid] = tid < np ? s_ipeaks[tid] : -1;
 
   // ---- ecg_sd = np.std(window) (remove_samples.py:62) and the keep decision (:70-74).  The window is z-scored
-  // (here, or by the caller), so sd = 1 up to a few ulp and sd / n_peaks > threshold is decided by n_peaks alone
-  // unless n_peaks * threshold == 1 (20 beats at 0.05: SURVEY.md C.1).  lazy_sd: the fourth NumPy-order sweep
-  // over the window runs only for those windows; the others report sd = NaN and take the decision that every
-  // sd within 1e-6 of 1 gives.  (A window the CALLER z-scored is trusted to be z-scored only with lazy_sd set.)
+  // (by the window kernel, or by the caller), so sd = 1 up to a few ulp and sd / n_peaks > threshold is decided by
+  // n_peaks alone unless n_peaks * threshold == 1 (20 beats at 0.05: SURVEY.md C.1).  lazy_sd: the NumPy-order
+  // sweep over the window runs only for those windows (here, over the parked samples); the others report sd = NaN
+  // and take the decision that every sd within 1e-6 of 1 gives.  (A window the CALLER z-scored is trusted to be
+  // z-scored only with lazy_sd set.)
   const double npt = __dmul_rn((double)np, p.sd_threshold);
   const bool need_sd = !p.lazy_sd || np == 0 || fabs(npt - 1.0) < 1e-6;
   double sd = qnan;
   if (need_sd) {
-    double ssq2;
-    K3_SWEEP(K3_PASS_DEV2, k3_div(sum_z, (double)L), 1.0, ssq2, flag)
-    sd = k3_sqrt(k3_div(ssq2, (double)L));
+    if (!p.lazy_sd) {
+      sd = ws.sd[w];
+    } else {
+      SumDev2 f{z, k3_div(ws.sumz[w], (double)L)};
+      const double ssq2 = pw_block_sum(f, L, pw_depth(L), s_vals, s_valid);
+      sd = k3_sqrt(k3_div(ssq2, (double)L));
+    }
   }
-#undef K3_SWEEP
   if (tid == 0) {
-    const double hr = sm.scal[0], rms = sm.scal[1];
+    const double hr = s_scal[0], rms = s_scal[1];
     const double sdn = need_sd ? k3_div(sd, (double)np) : qnan;
     const bool sd_rule = need_sd ? (sdn > p.sd_threshold) : (npt < 1.0);      // 1 / np > threshold
     const bool remove = (hr < p.hr_lo) || (hr > p.hr_hi) || isnan(hr) || (rms > p.pvc_threshold) || sd_rule;
     p.keep[w] = remove ? 0 : 1;
-    p.has_nan[w] = 0;
     p.n_peaks[w] = np;
     p.stats[4 * w + 0] = hr; p.stats[4 * w + 1] = rms; p.stats[4 * w + 2] = sd; p.stats[4 * w + 3] = sdn;
   }
-  K3_TICK(2)   // np.std (when needed) + keep decision
 }
 
 // ---- K3b: median beat of kept windows (median_sample.py:6-54) -> np_waves row.
@@ -1291,6 +1468,9 @@ static unsigned long long* k3_timing_buffer() {
 
 extern "C" int aew_windows_max_peaks(void) { return K3_MAXP; }
 extern "C" int aew_windows_max_len(void) { return K3_MAXL; }
+extern "C" size_t aew_windows_workspace_bytes(long long n_win) {
+  return (size_t)(n_win > 0 ? n_win : 0) * (2 * sizeof(double) + K3_QWS * sizeof(unsigned)) + 64;
+}
 
 extern "C" int aew_windows_beats_f64(const K3Params* hp, void* stream) {
   if (!hp) return AEW_ERR_ARG;
@@ -1308,10 +1488,21 @@ extern "C" int aew_windows_beats_f64(const K3Params* hp, void* stream) {
     return AEW_ERR_UNSUPPORTED;
   const size_t smem = k3_smem_layout(nullptr, nullptr);
   if (smem > 113 * 1024) return AEW_ERR_UNSUPPORTED;    // two blocks per SM
+  // the beat kernel reads the z-scored samples of the QRS runs from the parked copy: with zscore_windows it is required
+  if (p.zscore_windows && !p.zwin) return AEW_ERR_ARG;
+  if (!p.workspace || p.workspace_bytes < aew_windows_workspace_bytes(p.n_win)) return AEW_ERR_WORKSPACE;
+  K3Ws ws;
+  {
+    unsigned char* base = (unsigned char*)p.workspace;
+    base += (16 - ((size_t)base & 15)) & 15;
+    ws.sumz = (double*)base;
+    ws.sd = ws.sumz + p.n_win;
+    ws.qbits = (unsigned*)(ws.sd + p.n_win);
+  }
   // (per call: the attribute is per DEVICE, and the call costs a fraction of a microsecond)
   if (AEW_SET_MAX_SMEM(k3_windows, 113 * 1024) != 0) return (int)cudaGetLastError();
-  if ((p.median || p.waves) && p.zscore_windows && !p.zparams && !p.zwin) return AEW_ERR_ARG;
-  AEW_LAUNCH(k3_windows, (unsigned)p.n_win, K3_NT, smem, (cudaStream_t)stream, p, k3_timing_buffer());
+  AEW_LAUNCH(k3_windows, (unsigned)p.n_win, K3_NT, smem, (cudaStream_t)stream, p, ws, k3_timing_buffer());
+  AEW_LAUNCH(k3_beats, (unsigned)p.n_win, K3P_NT, 0, (cudaStream_t)stream, p, ws);
   if (p.median || p.waves) {
     const int nparts = (p.pre + p.post + K3B_NT - 1) / K3B_NT;
     AEW_LAUNCH(k3_median, (unsigned)(nparts * p.n_win), K3B_NT, 0, (cudaStream_t)stream, p, nparts);

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AEW_VERSION 111
+#define AEW_VERSION 112
 
 /* return codes */
 #define AEW_OK 0
@@ -127,19 +127,22 @@ typedef struct K3Params {
   double* median;             /* [n_win][pre + post] float64 median beat of kept windows (may be NULL); the section
                                  is int(0.64 fs) samples, 320 at 500 Hz (median_sample.py:20-25) */
   float* waves;               /* [n_win][pre + post] float32 copy = np_waves rows (may be NULL) */
-  double* zwin;               /* [n_win][L] z-scored windows = 'ecg_sample' column (may be NULL) */
-  double* zparams;            /* [n_win][2] scratch: mean, sd of each window's z-score.  With zscore_windows = 1 the
-                                 median kernel needs the z-scored samples again: it reads them from zwin if that is
-                                 given (fastest), else re-derives them from y and zparams; one of the two is required
-                                 when median / waves are requested */
+  double* zwin;               /* [n_win][L] z-scored windows = 'ecg_sample' column.  REQUIRED with zscore_windows = 1:
+                                 the beat and median kernels read the samples they need from it (may be NULL with
+                                 zscore_windows = 0, where y itself holds them) */
+  double* zparams;            /* [n_win][2] optional output: mean, sd of each window's z-score (may be NULL) */
   int* status;                /* device status word */
   unsigned long long* hazard_count; /* device counter of windows that took the exact fallback (may be NULL) */
   int lazy_sd;                /* 1: np.std of the (z-scored) window is evaluated only where it decides the mask
                                  (n_peaks * sd_threshold == 1); stats[2], stats[3] are NaN elsewhere.
                                  0: always (the 'ecg_sd' / 'ecg_sd/hr' columns of remove_samples()) */
+  void* workspace;            /* device scratch of aew_windows_workspace_bytes(n_win) bytes: what the window kernel
+                                 (z-score, QRS indicator) hands to the beat kernel (runs, R peaks, screen) */
+  unsigned long long workspace_bytes;
 } K3Params;
 int aew_windows_max_peaks(void);
 int aew_windows_max_len(void);
+size_t aew_windows_workspace_bytes(long long n_win);
 int aew_windows_beats_f64(const K3Params* h_params, void* stream);
 /* debugging aid: with AEW_K3_TIMING=1 in the environment the window kernel accumulates the cycles thread 0 of
  * every block spends per phase; this copies and clears the 16 counters (synchronises the device) */

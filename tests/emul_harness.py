@@ -131,14 +131,18 @@ def screen(flat, starts, Lw=10000, mode=0, zscore_windows=True, want_z=False, fs
              waves=np.zeros((n, sec), np.float32), zwin=np.zeros((n, Lw)), zparams=np.zeros((n, 2)),
              status=np.zeros(1, np.int32),
              hazards=np.zeros(1, np.uint64))
+    wsb = int(L.aew_windows_workspace_bytes(n))
+    ws = np.zeros(wsb + 16, np.uint8)
+    zpark = o["zwin"] if want_z else np.zeros((n, Lw))    # the z-scored windows are always parked (beat / median kernels)
     p = _cabi.K3Params(
         y=flat.ctypes.data, win_start=starts.ctypes.data, n_win=n, L=Lw, smooth_k=int(np.rint(0.1 * fs)),
         avg_k=int(np.rint(0.75 * fs)), refractory=int(np.rint(0.3 * fs)), pre=pre, post=sec - pre, hr_num=60.0 * fs,
         rr_div=fs * 1000.0, hr_lo=30.0, hr_hi=180.0, pvc_threshold=pvc, sd_threshold=sdt, mode=mode,
         zscore_windows=1 if zscore_windows else 0, keep=o["keep"].ctypes.data, has_nan=o["has_nan"].ctypes.data,
         n_peaks=o["n_peaks"].ctypes.data, peaks=o["peaks"].ctypes.data, stats=o["stats"].ctypes.data,
-        median=o["median"].ctypes.data, waves=o["waves"].ctypes.data, zwin=o["zwin"].ctypes.data if want_z else None, zparams=o["zparams"].ctypes.data,
-        status=o["status"].ctypes.data, hazard_count=o["hazards"].ctypes.data, lazy_sd=lazy_sd)
+        median=o["median"].ctypes.data, waves=o["waves"].ctypes.data, zwin=zpark.ctypes.data if zscore_windows else (o["zwin"].ctypes.data if want_z else None), zparams=o["zparams"].ctypes.data,
+        status=o["status"].ctypes.data, hazard_count=o["hazards"].ctypes.data, lazy_sd=lazy_sd,
+        workspace=ws.ctypes.data, workspace_bytes=wsb)
     rc = L.aew_windows_beats_f64(ctypes.byref(p), None)
     assert rc == 0, rc
     return o
