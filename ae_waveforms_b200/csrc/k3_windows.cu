@@ -63,8 +63,6 @@ struct K3Smem {            // shared memory of the window kernel k3_windows
   double* pw_vals;      // [2][128] leaf sums, double-buffered
   double* wtot;         // [2][16]
   double* scal;         // [16] scalars
-  int* leaf_off;        // [128] NumPy-tree leaf ranges of a length-L vector
-  int* leaf_size;       // [128]
   unsigned* Qw;         // [K3_QWS] QRS indicator, one bit per sample
   double* ring;         // [K3_RING] smoothgrad ring of the sequential evaluation
   unsigned long long* mbar;   // mbarrier of the bulk copy that brings the window in
@@ -76,6 +74,18 @@ struct K3Ws {
   unsigned* qbits;      // [n_win][K3_QWS] indicator bits
   double* sumz;         // [n_win] NumPy-order sum of the z-scored window (np.std's mean)
   double* sd;           // [n_win] np.std of the z-scored window where the window kernel formed it (lazy_sd == 0)
+};
+
+// The NumPy-tree leaves of a length-L vector, tabulated by the host per launch (they depend on L alone), and the
+// leaf each group of four threads serves.  Leaf offsets are multiples of 8 samples = 16 banks: two leaves whose
+// offsets agree modulo 16 samples collide when the same quarter-warp reads them (about half of the neighbouring
+// pairs at L = 10,000: 21 % of the kernel's shared-memory wavefronts in profiles/r2_ncu_k3.txt), so groups 2q and
+// 2q + 1 are given one leaf of either residue.
+struct K3Leaves {
+  unsigned short off[128];
+  unsigned char size[128];
+  unsigned char slot[128];    // leaf served by thread group g = tid >> 2
+  int depth, all;             // all: every one of the 2^depth = 128 slots holds samples
 };
 
 // first sample's offset inside W: the halo of the two box filters in front of it (even: 16-byte pairs stay aligned)
@@ -94,8 +104,6 @@ __host__ __device__ inline size_t k3_smem_layout(unsigned char* base, K3Smem* s)
   t.pw_vals = (double*)take(sizeof(double) * 256);
   t.wtot = (double*)take(sizeof(double) * 2 * K3_NW);
   t.scal = (double*)take(sizeof(double) * 16);
-  t.leaf_off = (int*)take(sizeof(int) * 128);
-  t.leaf_size = (int*)take(sizeof(int) * 128);
   t.pw_valid = (unsigned char*)take(256);
   t.mbar = (unsigned long long*)take(16);
   t.Qw = (unsigned*)take(sizeof(unsigned) * K3_QWS);
@@ -136,40 +144,41 @@ __device__ __forceinline__ double absgrad(const double* __restrict__ z, int i, i
 // The kernel is bound by INSTRUCTION FETCH (profiles/icache_bench.cu: straight-line code that does not fit the
 // 32 KB L1.5 instruction cache streams from L2 at about 5.5 cycles per instruction per SM, and every window runs
 // through the whole kernel once), so everything used more than once is one non-inlined function.
-enum { K3_PASS_PLAIN = 0, K3_PASS_DEV2 = 1, K3_PASS_ZSCORE = 2 };
+enum { K3_PASS_PLAIN = 0, K3_PASS_DEV2 = 1, K3_PASS_ZSCORE = 2, K3_PASS_ZDEV2 = 3 };
 struct LeafOut { double r; int flag; };
 struct SumPlain { const double* a; __device__ __forceinline__ double operator()(int i, bool) { return a[i]; } };
 
 // One sweep over the thread's share of its leaf.  PLAIN: sum of the window, flag = saw a NaN
-// (remove_samples.py:31-33).  DEV2: sum of (x - m)^2.  ZSCORE: x <- (x - m) / sd in place, sum of the new values,
-// flag = produced a non-finite value (constant window: 0/0).
-__device__ __forceinline__ double leaf_term(int mode, double v, double m, const ExactDiv& dv, int& flag) {
+// (remove_samples.py:31-33).  DEV2: sum of (x - m)^2.  ZSCORE: z = (x - m) / sd stored to D, sum of the z,
+// flag = produced a non-finite value (constant window: 0/0).  ZDEV2: sum of (z - m2)^2 with z formed on the fly
+// (np.std of the z-scored window where it is wanted for every window).
+__device__ __forceinline__ double leaf_term(int mode, double v, double m, const ExactDiv& dv, double m2, int& flag) {
   if (mode == K3_PASS_PLAIN) { flag |= isnan(v) ? 1 : 0; return v; }
   const double d = __dsub_rn(v, m);
   if (mode == K3_PASS_DEV2) return __dmul_rn(d, d);
   const double z = div_exact(d, dv);
+  if (mode == K3_PASS_ZDEV2) { const double e = __dsub_rn(z, m2); return __dmul_rn(e, e); }
   flag |= (isnan(z) || isinf(z)) ? 1 : 0;
   return z;
 }
-// The general form: every element tested (NaN / non-finite result), IEEE division through div_exact.  `S` is where
-// the untransformed samples are read from: the window in shared memory, or -- when the fast form below has already
-// overwritten part of it -- the same samples in global memory.
-__device__ __noinline__ LeafOut leaf_pass_checked(int mode, double* A, const double* S, double m, double sd, int off,
-                                                  int size, int j) {
-  const ExactDiv dv = make_exact_div(mode == K3_PASS_ZSCORE ? sd : 1.0);
+// The general form: every element tested (NaN / non-finite result), IEEE division through div_exact, 8-byte
+// accesses.  S: the samples (shared or global memory); D: where ZSCORE stores (may be S itself: every element is
+// read before it is written).
+__device__ __noinline__ LeafOut leaf_pass_checked(int mode, const double* S, double* D, double m, double sd, double m2,
+                                                  int off, int size, int j) {
+  const ExactDiv dv = make_exact_div(mode >= K3_PASS_ZSCORE ? sd : 1.0);
   const int c8 = size >> 3;
   int flag = 0;
   double r0 = 0.0, r1 = 0.0;
-  double* Aj = A + off + 2 * j;
   const double* Sj = S + off + 2 * j;
+  double* Dj = D + off + 2 * j;
 #pragma unroll 1
   for (int k = 0; k < c8; ++k) {
-    double2 t;
-    t.x = leaf_term(mode, Sj[8 * k], m, dv, flag);
-    t.y = leaf_term(mode, Sj[8 * k + 1], m, dv, flag);
-    if (mode == K3_PASS_ZSCORE) *reinterpret_cast<double2*>(Aj + 8 * k) = t;
-    r0 = k == 0 ? t.x : __dadd_rn(r0, t.x);
-    r1 = k == 0 ? t.y : __dadd_rn(r1, t.y);
+    const double tx = leaf_term(mode, Sj[8 * k], m, dv, m2, flag);
+    const double ty = leaf_term(mode, Sj[8 * k + 1], m, dv, m2, flag);
+    if (mode == K3_PASS_ZSCORE) { Dj[8 * k] = tx; Dj[8 * k + 1] = ty; }
+    r0 = k == 0 ? tx : __dadd_rn(r0, tx);
+    r1 = k == 0 ? ty : __dadd_rn(r1, ty);
   }
   double r = __dadd_rn(r0, r1);
   r = __dadd_rn(r, __shfl_xor_sync(AEW_FULL, r, 1));
@@ -185,8 +194,8 @@ __device__ __noinline__ LeafOut leaf_pass_checked(int mode, double* A, const dou
     const double v = in ? S[off + i + u] : 0.0;
     __syncwarp();
     if (in) {
-      const double t = leaf_term(mode, v, m, dv, flag);
-      if (mode == K3_PASS_ZSCORE && j == 0) A[off + i + u] = t;
+      const double t = leaf_term(mode, v, m, dv, m2, flag);
+      if (mode == K3_PASS_ZSCORE && j == 0) D[off + i + u] = t;
       r = __dadd_rn(r, t);
     }
   }
@@ -201,18 +210,20 @@ __device__ __forceinline__ unsigned odd_exponent(double q) {
   return (e - 723u) > 600u ? 1u : 0u;
 }
 
-// The sweep proper.  Lane j carries the stride-8 partial sums r_{2j} and r_{2j+1}: one 16-byte access per round
-// (the leaf offsets are multiples of 8 samples), and ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) is a local addition and
-// two xor steps.  The common case runs WITHOUT per-element tests or branches (they were more instructions than the
-// arithmetic: profiles/r2_k3_512_before_diet.txt): a NaN poisons the plain sum, and the Markstein division is
-// applied to every element while an integer test on the first quotient's exponent collects the ones it must not be
-// trusted with (zero, tiny, huge, non-finite).  Only a warp that saw such a thing repeats its leaves in the checked
-// form above -- same operations on the same operands in the same order, so the bits do not depend on the path.
-__device__ __noinline__ LeafOut leaf_pass(int mode, double* A, const double* raw, double m, double sd, int off,
+// The sweep proper over the window A in shared memory.  Lane j carries the stride-8 partial sums r_{2j} and
+// r_{2j+1}: one 16-byte access per round (the leaf offsets are multiples of 8 samples), and
+// ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) is a local addition and two xor steps.  The common case runs WITHOUT
+// per-element tests or branches (they were more instructions than the arithmetic:
+// profiles/r2_k3_512_before_diet.txt): a NaN poisons the plain sum, and the Markstein division is applied to every
+// element while an integer test on the first quotient's exponent collects the ones it must not be trusted with
+// (zero, tiny, huge, non-finite).  Only a warp that saw such a thing repeats its leaves in the checked form above --
+// same operations on the same operands in the same order, so the bits do not depend on the path.  ZSCORE leaves A
+// as it is and stores the z-scores to D (the parked copy in global memory; d16: 16-byte stores allowed).
+__device__ __noinline__ LeafOut leaf_pass(int mode, const double* A, double* D, bool d16, double m, double sd, int off,
                                           int size, int j) {
   const int c8 = size >> 3;
   double r0 = 0.0, r1 = 0.0;
-  double* Aj = A + off + 2 * j;
+  const double* Aj = A + off + 2 * j;
   unsigned odd = 0;
   if (mode == K3_PASS_PLAIN) {
     if (c8 > 0) { const double2 v = *reinterpret_cast<const double2*>(Aj); r0 = v.x; r1 = v.y; }
@@ -239,6 +250,7 @@ __device__ __noinline__ LeafOut leaf_pass(int mode, double* A, const double* raw
     const ExactDiv dv = make_exact_div(sd);
     odd = dv.fast ? 0u : 1u;
     if (dv.fast) {
+      double* Dj = D + off + 2 * j;
 #pragma unroll 2
       for (int k = 0; k < c8; ++k) {
         const double2 v = *reinterpret_cast<const double2*>(Aj + 8 * k);
@@ -249,7 +261,8 @@ __device__ __noinline__ LeafOut leaf_pass(int mode, double* A, const double* raw
         double2 t;
         t.x = __fma_rn(__fma_rn(-qx, dv.b, ax), dv.r, qx);
         t.y = __fma_rn(__fma_rn(-qy, dv.b, ay), dv.r, qy);
-        *reinterpret_cast<double2*>(Aj + 8 * k) = t;
+        if (d16) *reinterpret_cast<double2*>(Dj + 8 * k) = t;
+        else { Dj[8 * k] = t.x; Dj[8 * k + 1] = t.y; }
         r0 = k == 0 ? t.x : __dadd_rn(r0, t.x);
         r1 = k == 0 ? t.y : __dadd_rn(r1, t.y);
       }
@@ -262,7 +275,7 @@ __device__ __noinline__ LeafOut leaf_pass(int mode, double* A, const double* raw
   if ((size & 7) != 0 || size < 8) odd = 1u;             // leaves with a tail (not at L = 10,000) take the general form
   if (__any_sync(AEW_FULL, odd != 0)) {
     // (a zero sum or quotient is "odd" too: harmless, the checked form gives the same bits)
-    return leaf_pass_checked(mode, A, (mode == K3_PASS_ZSCORE && raw) ? raw : A, m, sd, off, size, j);
+    return leaf_pass_checked(mode, A, D, m, sd, 0.0, off, size, j);
   }
   LeafOut o;
   o.r = r; o.flag = 0;
@@ -335,25 +348,6 @@ __device__ __forceinline__ double block_excl_scan(double v, double* wtot) {
   }
   const double before = __shfl_sync(AEW_FULL, t, warp > 0 ? warp - 1 : 0);
   return (warp > 0 ? before : 0.0) + (incl - v);
-}
-__device__ __noinline__ int block_excl_scan_int(int v, int* wtot) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int incl = v;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int o = __shfl_up_sync(AEW_FULL, incl, d);
-    if (lane >= d) incl += o;
-  }
-  if (lane == 31) wtot[warp] = incl;
-  __syncthreads();
-  int t = lane < K3_NW ? wtot[lane] : 0;
-#pragma unroll
-  for (int d = 1; d < K3_NW; d <<= 1) {
-    const int o = __shfl_up_sync(AEW_FULL, t, d);
-    if (lane >= d) t += o;
-  }
-  const int before = __shfl_sync(AEW_FULL, t, warp > 0 ? warp - 1 : 0);
-  return (warp > 0 ? before : 0) + (incl - v);
 }
 
 // order-preserving 64-bit key of a (non-NaN) double: unsigned comparison of keys == comparison of the values
@@ -726,15 +720,6 @@ __device__ __noinline__ int run_peak(const double* __restrict__ d, int n, int la
   return best_i;
 }
 
-// |gradient| of sample i of the edge-extended window: i < 0 repeats sample 0, i >= L repeats sample L - 1
-// (np.gradient is one-sided at the two ends); branch-free
-__device__ __forceinline__ double absgrad_ext(const double* __restrict__ A, int i, int L, double g0, double gL) {
-  const int im = i - 1 < 0 ? 0 : (i - 1 > L - 1 ? L - 1 : i - 1);
-  const int ip = i + 1 < 0 ? 0 : (i + 1 > L - 1 ? L - 1 : i + 1);
-  double g = fabs(__dmul_rn(__dsub_rn(A[ip], A[im]), 0.5));
-  g = i <= 0 ? g0 : g;
-  return i >= L - 1 ? gL : g;
-}
 
 // d[k] = hi[k] - lo[k] for the K3_ITEMS consecutive entries behind two positions of the window buffer, read with
 // 16-byte loads whatever the parity of the two positions (a thread's strip starts at an even position, so the
@@ -766,17 +751,16 @@ __device__ __forceinline__ void tap_diff_any(const double* W, int lo, int hi, F&
   }
 }
 
-__global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, K3Ws ws, unsigned long long* dbg) {
+__global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, K3Ws ws, K3Leaves lv, unsigned long long* dbg) {
   AEW_DYN_SMEM(smem_raw);
   K3Smem sm;
   k3_smem_layout(smem_raw, &sm);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   const int L = p.L;
   const long long w = blockIdx.x;
   const double qnan = __longlong_as_double(0x7ff8000000000000ll);
-  long long t_last = 0;
-#ifndef AEW_EMUL
-  if (dbg) t_last = clock64();
+#if !defined(AEW_EMUL) && defined(AEW_K3_TICKS)
+  long long t_last = dbg ? clock64() : 0;
 #endif
   if (p.win_start[w] < 0) {                             // padding slot of an over-allocated window table
     if (tid == 0) {
@@ -808,13 +792,6 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, K3Ws ws, unsi
   const int H = k3_halo(ks, ka);
   double* W = sm.W;
   double* A = W + H;                                    // sample j of the window sits at position j + H of W
-  const int depth = pw_depth(L);
-  if (tid < (1 << depth)) {
-    long long off, size;
-    pw_node(L, depth, (unsigned)tid, off, size);
-    sm.leaf_off[tid] = (int)off;
-    sm.leaf_size[tid] = (int)size;
-  }
   for (int i = tid; i < L / 32 + 2; i += K3_NT) sm.Qw[i] = 0u;
 
   // ---- load.  ONE bulk copy global -> shared (TMA, completion on an mbarrier) issued by thread 0 where the window
@@ -838,14 +815,18 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, K3Ws ws, unsi
   __syncthreads();                                      // window (or its mbarrier), leaf table
   if (tma_in && !mbar_wait(sm.mbar, 0) && tid == 0) atomicOr(p.status, AEW_DEV_LOOKBACK_TIMEOUT);
   // one leaf per group of four threads
-  const int slot = tid >> 2, lj = tid & 3;
+  const int depth = lv.depth;
   const int nslots = 1 << depth;
-  const int offa = slot < nslots ? sm.leaf_off[slot] : 0, sza = slot < nslots ? sm.leaf_size[slot] : 0;
-  const bool all_leaves = nslots == K3_NT / 4 && __syncthreads_and(sza > 0);
+  const int grp = tid >> 2, lj = tid & 3;
+  const int slot = grp < nslots ? (int)lv.slot[grp] : grp;
+  const int offa = slot < nslots ? (int)lv.off[slot] : 0, sza = slot < nslots ? (int)lv.size[slot] : 0;
+  const bool all_leaves = nslots == K3_NT / 4 && lv.all != 0;
+  double* zw = p.zwin ? p.zwin + w * (long long)L : nullptr;
+  const bool z16 = (L & 1) == 0 && ((unsigned long long)p.zwin & 15ull) == 0;
   int buf = 0;
 #define K3_SWEEP(MODE, M, SD, SUM, FLAG)                                                                   \
   {                                                                                                        \
-    const LeafOut la_ = leaf_pass(MODE, A, src, M, SD, offa, sza, lj);                                     \
+    const LeafOut la_ = leaf_pass(MODE, A, zw, z16, M, SD, offa, sza, lj);                                 \
     SUM = block_combine(la_.r, sza, slot, lj, depth, sm.pw_vals + 128 * buf, sm.pw_valid + 128 * buf, all_leaves); \
     FLAG = la_.flag;                                                                                       \
     buf ^= 1;                                                                                              \
@@ -855,47 +836,44 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, K3Ws ws, unsi
   double sum_raw;
   int flag;
   K3_SWEEP(K3_PASS_PLAIN, 0.0, 1.0, sum_raw, flag)
-  fence_async_smem();                                   // (the window may leave through the bulk engine below)
   int bad = __syncthreads_or(flag);
   K3_TICK(0)   // load + NaN screen + first sum
   double sum_z = sum_raw;                               // windows that arrive z-scored: the same numbers
   double mean = 0.0, sd0 = 1.0;
+  bool parked = false;
   if (!bad && p.zscore_windows) {
-    // ---- per-window z-score (data_extract_vitaldb.py:93), NumPy summation order
+    // ---- per-window z-score (data_extract_vitaldb.py:93), NumPy summation order.  The z-scores go STRAIGHT to
+    // the parked copy in global memory ('ecg_sample': the beat, median and delineation kernels read them there);
+    // the window in shared memory stays as it came: the QRS indicator below is a comparison of two box sums of
+    // |gradient|, invariant under the positive scale 1 / sd, and is taken from the unscaled samples.
     mean = k3_div(sum_raw, (double)L);
     double ssq;
     K3_SWEEP(K3_PASS_DEV2, mean, 1.0, ssq, flag)
     sd0 = k3_sqrt(k3_div(ssq, (double)L));
     K3_SWEEP(K3_PASS_ZSCORE, mean, sd0, sum_z, flag)
-    fence_async_smem();
     bad = __syncthreads_or(flag);
-    if (tid == 0 && p.zparams) { p.zparams[2 * w] = mean; p.zparams[2 * w + 1] = sd0; }   // for the median kernel
+    parked = true;
+    if (tid == 0 && p.zparams) { p.zparams[2 * w] = mean; p.zparams[2 * w + 1] = sd0; }
   }
   // ecg_sd = np.std(window) (remove_samples.py:62) of the z-scored window is 1 up to a few ulp: it decides
   // sd / n_peaks > threshold only when n_peaks * threshold == 1.  With lazy_sd the beat kernel forms
   // it for those windows alone (from the parked copy); without, it is formed here for every window.
   double sd_full = qnan;
   if (!bad && !p.lazy_sd) {
-    double ssq2;
-    K3_SWEEP(K3_PASS_DEV2, k3_div(sum_z, (double)L), 1.0, ssq2, flag)
+    const double mz = k3_div(sum_z, (double)L);
+    const LeafOut la_ = p.zscore_windows ? leaf_pass_checked(K3_PASS_ZDEV2, A, nullptr, mean, sd0, mz, offa, sza, lj)
+                                         : leaf_pass(K3_PASS_DEV2, A, nullptr, false, mz, 1.0, offa, sza, lj);
+    const double ssq2 = block_combine(la_.r, sza, slot, lj, depth, sm.pw_vals + 128 * buf, sm.pw_valid + 128 * buf, all_leaves);
+    buf ^= 1;
     sd_full = k3_sqrt(k3_div(ssq2, (double)L));
   }
 #undef K3_SWEEP
   K3_TICK(1)   // window z-score (+ sum of the z-scored window)
-  // the z-scored window is parked for the median / delineation kernels ('ecg_sample' column): ONE bulk copy
-  // shared -> global issued by thread 0 where the addresses allow it (16-byte granules), plain stores otherwise
-  const bool tma_ok = (L & 1) == 0 && ((unsigned long long)p.zwin & 15ull) == 0;
-  if (p.zwin) {
-    double* zw = p.zwin + w * (long long)L;
-    if (tma_ok) {
-      if (tid == 0) bulk_store(zw, A, (unsigned)L * 8u);
-    } else {
+  if (zw && !parked) {                                  // windows the caller z-scored, NaN windows: parked as they came
 #pragma unroll 4
-      for (int i = tid; i < L; i += K3_NT) zw[i] = A[i];
-    }
+    for (int i = tid; i < L; i += K3_NT) zw[i] = A[i];
   }
-  if (bad) {                                            // NaN windows: parked as z-scored by the reference or raw
-    if (p.zwin && tma_ok && tid == 0) bulk_store_wait_all();
+  if (bad) {
     if (tid == 0) {
       p.keep[w] = 0; p.has_nan[w] = 1; p.n_peaks[w] = 0;
       for (int k = 0; k < 4; ++k) p.stats[4 * w + k] = qnan;
@@ -914,7 +892,7 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, K3Ws ws, unsi
   // |gradient| / smoothgrad.  Evaluated with prefix sums over the WHOLE window IN PLACE: position e of W stands
   // for sample e - H clamped into the window (edge value repeated), so that a box sum is P[hi] - P[lo] everywhere.
   // Thread t owns the strip e = 22 t .. 22 t + 21 in all three passes:
-  //   1  W <- P1 = prefix sums of g' = |z[j+1] - z[j-1]| (each thread reads its strip and one sample either side
+  //   1  W <- P1 = prefix sums of g' = |x[j+1] - x[j-1]| (each thread reads its strip and one sample either side
   //      BEFORE anyone writes; the factor 1/2 of np.gradient's central differences and the two 1/k of the box
   //      filters are exact or common scalings of both sides of the comparison and are folded into ONE constant),
   //   2  s'(e) = P1[e' + ks] - P1[e'] held in REGISTERS over the block scan whose barrier ends all reads of P1,
@@ -931,7 +909,6 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, K3Ws ws, unsi
     const double g0 = 2.0 * fabs(__dsub_rn(A[1], A[0])), gL = 2.0 * fabs(__dsub_rn(A[L - 1], A[L - 2]));
     const double left = e0 > 0 ? W[e0 - 1] : 0.0;
     const double right = e0 + K3_ITEMS < K3_WCAP ? W[e0 + K3_ITEMS] : 0.0;
-    if (p.zwin && tma_ok && tid == 0) bulk_store_wait_read(0);   // the bulk engine has read the window
     __syncthreads();                                    // every strip's neighbours are in registers
     double2* Wp = reinterpret_cast<double2*>(W + e0);
     double run = 0.0;
@@ -1069,15 +1046,15 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, K3Ws ws, unsi
 #endif
       __syncthreads();
       if (p.zscore_windows) {
-        const int slot2 = tid >> 2;
-        const bool in = slot2 < (1 << pw_depth(L));
-        (void)leaf_pass(K3_PASS_ZSCORE, A, src, sm.scal[0], sm.scal[1], in ? sm.leaf_off[slot2] : 0,
-                        in ? sm.leaf_size[slot2] : 0, tid & 3);
+        (void)leaf_pass_checked(K3_PASS_ZSCORE, A, A, sm.scal[0], sm.scal[1], 0.0, offa, sza, lj);
         __syncthreads();
       }
+    } else if (p.zscore_windows) {
+      // mode 1: the window in shared memory is still unscaled; the sequential evaluation wants SciPy's operands
+      __syncthreads();                                  // (thread 0's sm.scal)
+      (void)leaf_pass_checked(K3_PASS_ZSCORE, A, A, sm.scal[0], sm.scal[1], 0.0, offa, sza, lj);
+      __syncthreads();
     }
-    // SciPy's literal evaluation: one undivided running sum per box filter (appendix B.3), by thread 0.  The
-    // second filter reads smoothgrad ka/2 ahead of and behind its position: a ring of the last K3_RING values.
     if (tid == 0) {
       const double dks = (double)ks, dka = (double)ka;
       double* ring = sm.ring;
@@ -1125,7 +1102,6 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, K3Ws ws, unsi
   {
     unsigned* qout = ws.qbits + (size_t)blockIdx.x * K3_QWS;
     for (int i = tid; i < (L + 31) / 32 + 1; i += K3_NT) qout[i] = sm.Qw[i];
-    if (p.zwin && tma_ok && tid == 0) bulk_store_wait_all();   // the parked copy is complete before the block ends
   }
   K3_TICK(7)   // bits out
 }
@@ -1501,7 +1477,24 @@ extern "C" int aew_windows_beats_f64(const K3Params* hp, void* stream) {
   }
   // (per call: the attribute is per DEVICE, and the call costs a fraction of a microsecond)
   if (AEW_SET_MAX_SMEM(k3_windows, 113 * 1024) != 0) return (int)cudaGetLastError();
-  AEW_LAUNCH(k3_windows, (unsigned)p.n_win, K3_NT, smem, (cudaStream_t)stream, p, ws, k3_timing_buffer());
+  K3Leaves lv;
+  {
+    lv.depth = pw_depth(p.L);
+    const int ns = 1 << lv.depth;
+    lv.all = 1;
+    int cls[128], n0 = 0, n1 = 0, list0[128], list1[128];
+    for (int i = 0; i < 128; ++i) {
+      long long off = 0, size = 0;
+      if (i < ns) pw_node(p.L, lv.depth, (unsigned)i, off, size);
+      lv.off[i] = (unsigned short)off; lv.size[i] = (unsigned char)size; lv.slot[i] = (unsigned char)i;
+      if (i < ns && size == 0) lv.all = 0;
+      cls[i] = (int)((off >> 3) & 1);
+      if (i < ns) { if (cls[i]) list1[n1++] = i; else list0[n0++] = i; }
+    }
+    if (ns == 128 && n0 == n1)                          // groups 2q, 2q + 1 <- the q-th leaf of either residue
+      for (int q = 0; q < 64; ++q) { lv.slot[2 * q] = (unsigned char)list0[q]; lv.slot[2 * q + 1] = (unsigned char)list1[q]; }
+  }
+  AEW_LAUNCH(k3_windows, (unsigned)p.n_win, K3_NT, smem, (cudaStream_t)stream, p, ws, lv, k3_timing_buffer());
   AEW_LAUNCH(k3_beats, (unsigned)p.n_win, K3P_NT, 0, (cudaStream_t)stream, p, ws);
   if (p.median || p.waves) {
     const int nparts = (p.pre + p.post + K3B_NT - 1) / K3B_NT;
