@@ -449,7 +449,7 @@ class Preprocessor:
 
     @_cabi.on_device
     def resolve_hazards(self, flat, beg_h, end_h, mean, sd, cnt, win_start, win_rec, scr, zwin_main=None,
-                        low_latency=False):
+                        low_latency=False, after=None):
         """exact_masks: windows whose keep / remove decision depends on the last bit of np.std (n_peaks ==
         hazard_peak_count(), every other rule passed) are decided from SciPy-order filter output.  The records that
         hold such windows are gathered into a compact batch, filtered by the sequential kernel (bit-identical to
@@ -459,35 +459,53 @@ class Preprocessor:
         The sequential filter is a dependent chain of ~25 cycles per sample and pass: ~100 ms for a 1 h record
         whatever the batch.  It needs a handful of warps, so it runs on a SIDE stream next to the kernels of the
         following batches; this call only launches it.  Returns None (no such window) or a dict with ``event``
-        (recorded on the side stream after the rows of ``scr`` have been replaced), ``n`` and ``changed`` (device)."""
+        (recorded on the side stream after the rows of ``scr`` have been replaced), ``n`` and ``changed`` (device).
+
+        ``after``: an event recorded behind the batch's screen kernels.  With it nothing here touches the calling
+        stream: the hazard windows are selected on a small stream of their own that waits for the event (so the host
+        does not wait for whatever the caller has queued since -- the NEXT batch's kernels), and the records are
+        gathered on the side stream.  The caller keeps ``flat`` untouched until the batch is finished."""
         torch = self.torch
         nh = self.hazard_peak_count()
         if nh is None or not len(win_start):
             return None
-        st = scr["stats"]
-        hr, rms = st[:, 0], st[:, 1]
-        hz = (scr["n_peaks"] == nh) & (scr["has_nan"] == 0) & (hr >= 30.0) & (hr <= 180.0) & ~(rms > self.pvc_threshold)
-        hz_idx = torch.nonzero(hz).squeeze(1)
-        if hz_idx.numel() == 0:                                  # (sync: the list of hazard windows)
-            return None
-        hz_h = hz_idx.cpu().numpy()
-        recs = np.unique(win_rec[hz_h])
-        lens = (end_h[recs] - beg_h[recs]).astype(np.int64)
-        # records without NaN are one segment each: the sequential kernel then gets exactly the blocks it needs
-        # (every block keeps an SM to itself; see K2E_HOG in k2_filtfilt.cu)
-        clean = bool((cnt.cpu().numpy()[recs] == lens).all())
+        main = torch.cuda.current_stream(self.device)
+        if after is not None:
+            sel = getattr(self, "_resolver", None)
+            if sel is None:
+                sel = self._resolver = torch.cuda.Stream(device=self.device, priority=-1)
+        else:
+            sel = main
+        with torch.cuda.stream(sel):
+            if after is not None:
+                sel.wait_event(after)
+            st = scr["stats"]
+            hr, rms = st[:, 0], st[:, 1]
+            hz = (scr["n_peaks"] == nh) & (scr["has_nan"] == 0) & (hr >= 30.0) & (hr <= 180.0) \
+                & ~(rms > self.pvc_threshold)
+            hz_idx = torch.nonzero(hz).squeeze(1)
+            if hz_idx.numel() == 0:                              # (sync: the list of hazard windows)
+                return None
+            hz_h = hz_idx.cpu().numpy()
+            recs = np.unique(win_rec[hz_h])
+            lens = (end_h[recs] - beg_h[recs]).astype(np.int64)
+            # records without NaN are one segment each: the sequential kernel then gets exactly the blocks it needs
+            # (every block keeps an SM to itself; see K2E_HOG in k2_filtfilt.cu)
+            clean = bool((cnt.cpu().numpy()[recs] == lens).all())
         coff = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
-        # main stream: the hazard records' samples and statistics are copied out, so that the side stream touches
-        # nothing the next batch may overwrite (input buffers, filter scratch)
-        xc = torch.cat([flat[int(b):int(e)] for b, e in zip(beg_h[recs], end_h[recs])])
-        d_rec = self._upload(recs.astype(np.int64))
-        d_off = self._upload(coff)
-        m_c, s_c, n_c = mean.index_select(0, d_rec), sd.index_select(0, d_rec), cnt.index_select(0, d_rec)
         pos = np.searchsorted(recs, win_rec[hz_h])
         start_c = np.ascontiguousarray(win_start[hz_h] - beg_h[win_rec[hz_h]] + coff[pos], dtype=np.int64)
-        d_start_c = self._upload(start_c)
         L = self.L
-        main = torch.cuda.current_stream(self.device)
+
+        def gather():
+            # the hazard records' samples and statistics are copied out, so that the sequential pass touches nothing
+            # the next batch may overwrite (input buffers, filter scratch)
+            xc = torch.cat([flat[int(b):int(e)] for b, e in zip(beg_h[recs], end_h[recs])])
+            d_rec = self._upload(recs.astype(np.int64))
+            d_off = self._upload(coff)
+            return (xc, d_rec, d_off, mean.index_select(0, d_rec), sd.index_select(0, d_rec),
+                    cnt.index_select(0, d_rec), self._upload(start_c))
+
         # a POOL of side streams, round robin: one pass takes ~150 ms however few records it holds, so the passes of
         # consecutive batches / chunks must run next to each other, not queue behind each other on one stream
         pool = getattr(self, "_side_streams", None)
@@ -496,10 +514,17 @@ class Preprocessor:
             self._side_next = 0
         side = pool[self._side_next % len(pool)]
         self._side_next += 1
-        ready = torch.cuda.Event()
-        ready.record(main)
+        if after is None:
+            xc, d_rec, d_off, m_c, s_c, n_c, d_start_c = gather()   # on the calling stream, before it moves on
+            ready = torch.cuda.Event()
+            ready.record(main)
+        else:
+            ready = after
+            hz_idx.record_stream(side)
         with torch.cuda.stream(side):
             side.wait_event(ready)
+            if after is not None:
+                xc, d_rec, d_off, m_c, s_c, n_c, d_start_c = gather()
             yc, tc = torch.empty_like(xc), torch.empty_like(xc)
             self.filter_records(xc, coff[:-1].copy(), coff[1:].copy(), d_off[:-1].contiguous(), d_off[1:].contiguous(),
                                 m_c, s_c, n_c, out=yc, tmp=tc, mode=3 if low_latency else 1,
@@ -523,7 +548,7 @@ class Preprocessor:
     @_cabi.on_device
     def run(self, batch: RecordBatch, trim: bool = True, keep_intermediates: bool = False,
             scratch: dict | None = None, features: bool = False, strips: bool = False, defer: bool = False,
-            low_latency: bool = False):
+            low_latency: bool = False, lazy_hazards: bool = False):
         """Returns a dict of CUDA tensors: ``np_waves`` (n_keep, 320) float32,
         ``np_info`` (n_keep, 2) float64 = [case_id, idx_end], ``medians`` float64,
         plus per-window ``keep`` / ``has_nan`` / ``n_peaks`` / ``peaks`` / ``stats`` and
@@ -532,7 +557,11 @@ class Preprocessor:
         whose device is otherwise idle, such as the PCIe-bound feeder).
         ``defer``: return a pending handle right after the kernels have been launched; ``finish(handle)`` gives the
         result.  With exact_masks the sequential re-filtering of the 20-peak records (side stream, ~100 ms of
-        latency whatever the batch size) then overlaps the NEXT batches' kernels instead of idling the device."""
+        latency whatever the batch size) then overlaps the NEXT batches' kernels instead of idling the device.
+        ``lazy_hazards`` (with ``defer``): the 20-peak windows of THIS batch are looked for when the next batch's
+        kernels have been queued (or when a batch is finished), on streams of their own, so that the host never
+        waits on the calling stream with nothing queued behind it; ``batch.flat`` must stay untouched until
+        ``finish``."""
         torch = self.torch
         flat = batch.flat
         beg_h, end_h, d_beg, d_end = self._ranges(batch, trim)
@@ -560,21 +589,63 @@ class Preprocessor:
         scr = self.screen_windows(y, win_start, zwin_scratch=tmp if (features or self.park_windows) else None,
                                   lazy_sd=self.lazy_sd)
         hz = None
-        if self.exact_masks:
+        lazy = bool(lazy_hazards and defer and not features and self.exact_masks)
+        if self.exact_masks and not lazy:
             hz = self.resolve_hazards(flat, beg_h, end_h, mean, sd, cnt, win_start, win_rec, scr,
                                       zwin_main=tmp if features else None, low_latency=low_latency)
         pend = dict(scr=scr, hz=hz, info=info, header=header, features=features, tmp=tmp, y=y, n_win=len(win_start),
                     mean=mean, sd=sd, keep_intermediates=keep_intermediates, beg_h=beg_h, end_h=end_h,
                     win_start=win_start, flat=flat, cnt=cnt)
+        if lazy:
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(self.device))
+            pend.update(k3_done=done, hz_args=dict(win_rec=win_rec, low_latency=low_latency))
+            prev, self._lazy_prev = getattr(self, "_lazy_prev", None), pend
+            if prev is not None:                               # its screen kernels finished a batch ago
+                self._resolve_lazy(prev)
         if defer and not features:                             # (the delineation reads the shared filter scratch)
             return pend
         return self.finish(pend)
+
+    def flush_hazards(self):
+        """lazy_hazards: look for the newest batch's 20-peak windows now (end of a run: its sequential pass should
+        start before the older batches are finished one by one)."""
+        newest = getattr(self, "_lazy_prev", None)
+        if newest is not None:
+            self._resolve_lazy(newest)
+
+    def _resolve_lazy(self, pend):
+        a = pend.pop("hz_args", None)
+        if a is not None:
+            pend["hz"] = self.resolve_hazards(pend["flat"], pend["beg_h"], pend["end_h"], pend["mean"], pend["sd"],
+                                              pend["cnt"], pend["win_start"], a["win_rec"], pend["scr"],
+                                              low_latency=a["low_latency"], after=pend["k3_done"])
+        if getattr(self, "_lazy_prev", None) is pend:
+            self._lazy_prev = None
 
     @_cabi.on_device
     def finish(self, pend) -> dict:
         """Second half of ``run``: waits (on the stream, not the host) for the batch's exact-mask pass, compacts the
         kept windows and reads the counters back."""
         torch = self.torch
+        if "hz_args" in pend:
+            self._resolve_lazy(pend)
+        if "k3_done" in pend and "_fin" not in pend:
+            # a lazily resolved batch is compacted and read back on a stream of its own, which waits for THAT batch's
+            # kernels only: the host's reads below do not wait for what has been queued on the calling stream since
+            fin = getattr(self, "_finisher", None)
+            if fin is None:
+                fin = self._finisher = torch.cuda.Stream(device=self.device, priority=-1)
+            main = torch.cuda.current_stream(self.device)
+            pend["_fin"] = True
+            with torch.cuda.stream(fin):
+                fin.wait_event(pend["k3_done"])
+                res = self.finish(pend)
+            for v in res.values():
+                if isinstance(v, torch.Tensor) and v.is_cuda:
+                    v.record_stream(main)
+            main.wait_stream(fin)
+            return res
         scr, hz, info, header, features, tmp = (pend[k] for k in ("scr", "hz", "info", "header", "features", "tmp"))
         n_win, y = pend["n_win"], pend["y"]
         if hz is not None:

@@ -698,7 +698,11 @@ __device__ __forceinline__ double df2t_step_exact(const double (&b)[5], const do
 // form below, whose chain warp also carries the products and the z-score -- at 32 x its issue slots.  Used where the
 // device has nothing else to do and the wait is what counts: the end-to-end feeder (PCIe-bound, the last chunk's
 // pass is a tail of the call).
-#define K2W_NT 32                       // one WARP per segment (the low-latency form)
+#define K2W_NW 1                        // one WARP per segment (the low-latency form), one per block.  Measured
+#define K2W_NT (32 * K2W_NW)            // (profiles/README.md, "the end of a run"): 160-200 ms for the four passes of a
+                                        // 1 h record with an SM sub-partition to itself; 400 ms with four such warps
+                                        // in one block, one per sub-partition
+#define K2W_HOG (40 * 1024)
 #define K2W_BLK 64                      // samples per round: two per lane (halves the rounds' fixed cost)
 // one pass over n samples: logical sample i is in[i] (REV: in[n - 1 - i]); lane 0 owns the state z
 template <int ORD, bool REV>
@@ -748,12 +752,14 @@ __device__ __forceinline__ void exact_stream_warp(const double* in, double* out,
 
 template <int ORD>
 __global__ void __launch_bounds__(K2W_NT) k2_exact_warp(PassArgs a) {
-  __shared__ double sp[ORD + 1][K2W_BLK + 2];
-  __shared__ double sy[K2W_BLK];
+  __shared__ double sp_all[K2W_NW][ORD + 1][K2W_BLK + 2];
+  __shared__ double sy_all[K2W_NW][K2W_BLK];
   const long long n_seg = a.ws.hdr[H_SEG_COUNT] < a.ws.max_seg ? a.ws.hdr[H_SEG_COUNT] : a.ws.max_seg;
-  const long long seg = blockIdx.x;
-  const int lane = threadIdx.x;
-  if (seg >= n_seg) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long seg = (long long)blockIdx.x * K2W_NW + warp;
+  double (*sp)[K2W_BLK + 2] = sp_all[warp];
+  double* sy = sy_all[warp];
+  if (seg >= n_seg) return;                              // (warps are independent: only warp barriers below)
   const long long* sg = a.ws.segs + 4 * seg;
   const long long g0 = sg[0], n = sg[1], rec = sg[2];
   const bool zon = a.mean != nullptr;
@@ -767,7 +773,7 @@ __global__ void __launch_bounds__(K2W_NT) k2_exact_warp(PassArgs a) {
   double* out = a.passthrough + g0;
   double* tmp = a.dst + g0;
   if (n <= pad) {                                        // filters.py:50-51: too short to filter, copied through
-    for (long long i = lane; i < n; i += K2W_NT) out[i] = zs(xs[i], zon, mean, sd);
+    for (long long i = lane; i < n; i += 32) out[i] = zs(xs[i], zon, mean, sd);
     return;
   }
   double ve[K2_MAXPAD];
@@ -975,7 +981,9 @@ __global__ void __launch_bounds__(K2F_NT, 3) k2_fused(PassArgs a) {
 // again a lone in-order warp, is the slow one: 627 ms per pass against 310).
 #define K2E_T 32                        // samples per segment and round (one 256-byte row per segment)
 #define K2E_LD (K2E_T + 1)              // row stride in shared memory: lane l reads row l -> bank (l + t) mod 32
-#define K2E_NT 64                       // warp 0 walks the chains, warp 1 moves the rows
+#define K2E_NP 1                        // (chain warp, mover warp) PAIRS per block.  One: with four pairs per block
+#define K2E_NT (64 * K2E_NP)            // (one chain warp per SM sub-partition, 128 segments per SM instead of 32) a
+                                        // pass took 460 ms instead of 313 and the calls next to it 73 ms instead of 70
 #define K2E_HOG (190 * 1024)            // dynamic shared memory the block asks for and never touches: no block of the
                                         // window / filter / delineation kernels fits next to it, so the chain warp
                                         // keeps its SM sub-partition to itself.  The chain is a latency race: with
@@ -984,7 +992,17 @@ __global__ void __launch_bounds__(K2F_NT, 3) k2_fused(PassArgs a) {
                                         // from 315 ms alone to > 1 s next to them).  100 records are 4 blocks = 4 of
                                         // the 148 SMs.
 
+// barrier of one pair (named barrier 1 + pair, 64 threads): the pairs of a block never wait for each other
+#ifndef AEW_EMUL
+__device__ __forceinline__ void aew_named_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+#endif
+__device__ __forceinline__ void pair_sync(int pair) { aew_named_sync(1 + pair, 64); }
+
 struct alignas(16) K2ESeg { const double* in; double* out; long long n; long long pad_; };   // 32 bytes: two 16-byte loads
+// shared memory of one pair: two input and two output tiles, the two segment tables, the longest segment
+#define K2E_PAIR_BYTES (((4 * K2E_T * K2E_LD * 8 + 64 * 32 + 16) + 127) / 128 * 128)
 
 // The mover warp's two jobs for one round.  Eight segments at a time: their table entries are loaded first (two
 // 16-byte shared-memory loads each, all independent), then the eight copies are issued -- a lone warp runs in
@@ -1039,18 +1057,18 @@ template <int ORD, bool REV>
 __device__ __forceinline__ void exact_pass(const K2ESeg* tab, long long n_max, double (*tin)[K2E_T][K2E_LD],
                                            double (*tout)[K2E_T][K2E_LD], const double (&b)[5], const double (&a)[5],
                                            double (&z)[4], long long n, bool zon, double mean, const ExactDiv& sd,
-                                           int warp, int lane) {
+                                           int role, int pair, int lane) {
   const long long rounds = (n_max + K2E_T - 1) / K2E_T;
-  if (warp == 1 && rounds > 0) {
+  if (role == 1 && rounds > 0) {
     exact_fetch<REV>(tab, 0, tin[0], lane);
 #ifndef AEW_EMUL
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 #endif
   }
-  __syncthreads();
+  pair_sync(pair);
   for (long long r = 0; r < rounds; ++r) {
     const int buf = (int)(r & 1);
-    if (warp == 0) {
+    if (role == 0) {
       const long long i0 = r * K2E_T;
       if (i0 < n) {
         const int cnt = (int)(n - i0 < K2E_T ? n - i0 : K2E_T);
@@ -1077,22 +1095,25 @@ __device__ __forceinline__ void exact_pass(const K2ESeg* tab, long long n_max, d
       asm volatile("cp.async.wait_group 0;" ::: "memory");
 #endif
     }
-    __syncthreads();
+    pair_sync(pair);
   }
-  if (warp == 1 && rounds > 0) exact_store<REV>(tab, rounds - 1, tout[(rounds - 1) & 1], lane);
-  __syncthreads();
+  if (role == 1 && rounds > 0) exact_store<REV>(tab, rounds - 1, tout[(rounds - 1) & 1], lane);
+  pair_sync(pair);
 }
 
 template <int ORD>
 __global__ void __launch_bounds__(K2E_NT) k2_exact(PassArgs a) {
-  __shared__ double tin[2][K2E_T][K2E_LD];
-  __shared__ double tout[2][K2E_T][K2E_LD];
-  __shared__ K2ESeg s_fwd[32];                           // src -> tmp
-  __shared__ K2ESeg s_bwd[32];                           // tmp -> out
-  __shared__ long long s_nmax;
-  const long long n_seg = a.ws.hdr[H_SEG_COUNT] < a.ws.max_seg ? a.ws.hdr[H_SEG_COUNT] : a.ws.max_seg;
+  AEW_DYN_SMEM(smem_raw);                                // (the first K2E_PAIR_BYTES * K2E_NP bytes of the hog)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long seg = (long long)blockIdx.x * 32 + lane;
+  const int pair = warp % K2E_NP, role = warp / K2E_NP;  // role 0: the chains, role 1: the rows
+  unsigned char* mine = smem_raw + (size_t)pair * K2E_PAIR_BYTES;
+  double (*tin)[K2E_T][K2E_LD] = reinterpret_cast<double (*)[K2E_T][K2E_LD]>(mine);
+  double (*tout)[K2E_T][K2E_LD] = reinterpret_cast<double (*)[K2E_T][K2E_LD]>(mine + 2 * K2E_T * K2E_LD * sizeof(double));
+  K2ESeg* s_fwd = reinterpret_cast<K2ESeg*>(mine + 4 * K2E_T * K2E_LD * sizeof(double));   // src -> tmp
+  K2ESeg* s_bwd = s_fwd + 32;                            // tmp -> out
+  long long* s_nmax_p = reinterpret_cast<long long*>(s_bwd + 32);
+  const long long n_seg = a.ws.hdr[H_SEG_COUNT] < a.ws.max_seg ? a.ws.hdr[H_SEG_COUNT] : a.ws.max_seg;
+  const long long seg = ((long long)blockIdx.x * K2E_NP + pair) * 32 + lane;
   const bool have = seg < n_seg;
   const long long* sg = a.ws.segs + 4 * (have ? seg : 0);
   const long long g0 = have ? sg[0] : 0, rec = have ? sg[2] : 0;
@@ -1109,7 +1130,7 @@ __global__ void __launch_bounds__(K2E_NT) k2_exact(PassArgs a) {
   const double* xs = a.src + g0;
   double* out = a.passthrough + g0;
   double* tmp = a.dst + g0;
-  if (warp == 0) {
+  if (role == 0) {
     if (have && n <= pad) {                              // filters.py:50-51: too short to filter, copied through
       for (long long i = 0; i < n; ++i) out[i] = zs(xs[i], zon, mean, sd);
       n = 0;                                             // (takes no further part, but stays with its warp)
@@ -1117,15 +1138,15 @@ __global__ void __launch_bounds__(K2E_NT) k2_exact(PassArgs a) {
     s_fwd[lane].in = xs; s_fwd[lane].out = tmp; s_fwd[lane].n = n;
     s_bwd[lane].in = tmp; s_bwd[lane].out = out; s_bwd[lane].n = n;
     const long long m = (long long)__reduce_max_sync(AEW_FULL, (unsigned)(n > 0x7fffffffll ? 0x7fffffffll : n));
-    if (lane == 0) s_nmax = m;
+    if (lane == 0) *s_nmax_p = m;
   } else {
     n = 0;
   }
-  __syncthreads();
-  const long long n_max = s_nmax;
+  pair_sync(pair);
+  const long long n_max = *s_nmax_p;
   double ve[K2_MAXPAD];
   double x0 = 0.0, xl = 0.0;
-  if (warp == 0 && n > 0) {                              // odd extension on the left, zi scaled by its first sample
+  if (role == 0 && n > 0) {                              // odd extension on the left, zi scaled by its first sample
     x0 = zs(xs[0], zon, mean, sd); xl = zs(xs[n - 1], zon, mean, sd);
     const double e0 = __dsub_rn(__dmul_rn(2.0, x0), zs(xs[pad], zon, mean, sd));
 #pragma unroll
@@ -1133,8 +1154,8 @@ __global__ void __launch_bounds__(K2E_NT) k2_exact(PassArgs a) {
     for (int e = 0; e < pad; ++e)
       df2t_step_exact<ORD>(b, ac, __dsub_rn(__dmul_rn(2.0, x0), zs(xs[pad - e], zon, mean, sd)), z);
   }
-  exact_pass<ORD, false>(s_fwd, n_max, tin, tout, b, ac, z, n, zon, mean, sd, warp, lane);
-  if (warp == 0 && n > 0) {                              // right extension, then the backward pass starts inside it
+  exact_pass<ORD, false>(s_fwd, n_max, tin, tout, b, ac, z, n, zon, mean, sd, role, pair, lane);
+  if (role == 0 && n > 0) {                              // right extension, then the backward pass starts inside it
     for (int m = 0; m < pad; ++m)
       ve[m] = df2t_step_exact<ORD>(b, ac, __dsub_rn(__dmul_rn(2.0, xl), zs(xs[n - 2 - m], zon, mean, sd)), z);
     const double vl = ve[pad - 1];
@@ -1142,9 +1163,9 @@ __global__ void __launch_bounds__(K2E_NT) k2_exact(PassArgs a) {
     for (int i = 0; i < ORD; ++i) z[i] = __dmul_rn(zi[i], vl);
     for (int e = 0; e < pad; ++e) df2t_step_exact<ORD>(b, ac, ve[pad - 1 - e], z);
   }
-  __threadfence_block();                                 // the block's stores to tmp before the copies that read them
-  __syncthreads();
-  exact_pass<ORD, true>(s_bwd, n_max, tin, tout, b, ac, z, n, false, 0.0, sd, warp, lane);
+  __threadfence_block();                                 // the pair's stores to tmp before the copies that read them
+  pair_sync(pair);
+  exact_pass<ORD, true>(s_bwd, n_max, tin, tout, b, ac, z, n, false, 0.0, sd, role, pair, lane);
 }
 
 unsigned long long* g_dbg = nullptr;   // device counters, allocated once when AEW_K2_TIMING is set
@@ -1229,9 +1250,10 @@ extern "C" int aew_filtfilt_f64(const double* src, const double* mean, const dou
   }
 #endif
   if (mode == 1) {                                       // one lane per segment (lanes beyond the count exit)
-    const long long blocks = (max_seg + 31) / 32;
+    const long long blocks = (max_seg + 32 * K2E_NP - 1) / (32 * K2E_NP);
     const char* hog_env = getenv("AEW_K2E_HOG_KB");      // measurement switch; default K2E_HOG
-    const size_t hog = hog_env ? (size_t)atoi(hog_env) * 1024 : (size_t)K2E_HOG;
+    size_t hog = hog_env ? (size_t)atoi(hog_env) * 1024 : (size_t)K2E_HOG;
+    if (hog < (size_t)K2E_PAIR_BYTES * K2E_NP) hog = (size_t)K2E_PAIR_BYTES * K2E_NP;   // (the pairs' tiles live in it)
     switch ((int)h_tab[K2_TAB_ORDER]) {
       case 1: if (AEW_SET_MAX_SMEM(k2_exact<1>, K2E_HOG) != 0) return (int)cudaGetLastError();
               AEW_LAUNCH(k2_exact<1>, (unsigned)blocks, K2E_NT, hog, st, a); break;
@@ -1246,12 +1268,23 @@ extern "C" int aew_filtfilt_f64(const double* src, const double* mean, const dou
     return (int)cudaGetLastError();
   }
   if (mode == 3) {                                       // exact, one warp per segment (low latency)
-    const long long blocks = max_seg;
+    const long long blocks = (max_seg + K2W_NW - 1) / K2W_NW;
+    // K2W_HOG of dynamic shared memory that is never touched: enough that none of these blocks lands next to a
+    // lane-per-segment block (K2E_HOG) -- as plain 32-thread blocks all 100 of a call piled onto the few SMs those
+    // had emptied, a dozen chains per SM, 540 ms instead of 160 -- and little enough that they start wherever a
+    // block of the window / filter kernels retires (measured at the end of a run, profiles/README.md: 40 KB 200 ms,
+    // 116 KB or a whole SM 320 ms -- the 100 blocks then run in two waves)
+    const char* hog_env = getenv("AEW_K2W_HOG_KB");      // measurement switch; default K2W_HOG
+    const size_t hog = hog_env ? (size_t)atoi(hog_env) * 1024 : (size_t)K2W_HOG;
     switch ((int)h_tab[K2_TAB_ORDER]) {
-      case 1: AEW_LAUNCH(k2_exact_warp<1>, (unsigned)blocks, K2W_NT, 0, st, a); break;
-      case 2: AEW_LAUNCH(k2_exact_warp<2>, (unsigned)blocks, K2W_NT, 0, st, a); break;
-      case 3: AEW_LAUNCH(k2_exact_warp<3>, (unsigned)blocks, K2W_NT, 0, st, a); break;
-      case 4: AEW_LAUNCH(k2_exact_warp<4>, (unsigned)blocks, K2W_NT, 0, st, a); break;
+      case 1: if (AEW_SET_MAX_SMEM(k2_exact_warp<1>, K2E_HOG) != 0) return (int)cudaGetLastError();
+              AEW_LAUNCH(k2_exact_warp<1>, (unsigned)blocks, K2W_NT, hog, st, a); break;
+      case 2: if (AEW_SET_MAX_SMEM(k2_exact_warp<2>, K2E_HOG) != 0) return (int)cudaGetLastError();
+              AEW_LAUNCH(k2_exact_warp<2>, (unsigned)blocks, K2W_NT, hog, st, a); break;
+      case 3: if (AEW_SET_MAX_SMEM(k2_exact_warp<3>, K2E_HOG) != 0) return (int)cudaGetLastError();
+              AEW_LAUNCH(k2_exact_warp<3>, (unsigned)blocks, K2W_NT, hog, st, a); break;
+      case 4: if (AEW_SET_MAX_SMEM(k2_exact_warp<4>, K2E_HOG) != 0) return (int)cudaGetLastError();
+              AEW_LAUNCH(k2_exact_warp<4>, (unsigned)blocks, K2W_NT, hog, st, a); break;
       default: return AEW_ERR_UNSUPPORTED;
     }
     return (int)cudaGetLastError();

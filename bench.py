@@ -447,11 +447,12 @@ def run_gpu(args):
         q, res = [], None
         for i in range(steps):
             # the job's last two calls take the low-latency form of the sequential filter (one warp per record: half
-            # the wait, and the device is about to fall idle anyway): the run ends ~160 ms after its last kernels
-            # instead of ~310
-            q.append(p.run(batch, scratch=scratch, defer=True, low_latency=i >= steps - 2))
+            # the wait -- and the device falls idle behind them anyway): the run ends ~200 ms after its last kernels
+            # instead of ~320 (profiles/exact_masks_steady.py)
+            q.append(p.run(batch, scratch=scratch, defer=True, low_latency=i >= steps - 2, lazy_hazards=True))
             while len(q) > DEPTH:
                 res = finish(p, q.pop(0))
+        p.flush_hazards()                                         # the last call's sequential pass starts now
         while q:
             res = finish(p, q.pop(0))
         drain()

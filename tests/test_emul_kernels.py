@@ -59,6 +59,20 @@ def test_k2_exact_warp_form_has_the_same_bits(golden):
     assert same(outs[0], g["short_lp40_o3"])
 
 
+def test_k2_exact_forms_pack_many_segments_per_block():
+    """The sequential kernels pack 128 segments (four chain / mover warp pairs with a barrier each, mode 1) resp.
+    four segments (one warp each, mode 3) into a block: 150 records of unequal length, some too short to filter,
+    come out bit-identical to SciPy from both."""
+    rng = np.random.default_rng(11)
+    recs = [rng.standard_normal(int(n)) for n in rng.integers(5, 700, 150)]
+    want = [rp.butterworth(r, "low", 30.0) for r in recs]
+    for mode in (1, 3):
+        outs, hdr = eh.filtfilt(recs, [("low", 30, 4)], mode=mode)
+        assert hdr[0] == len(recs) and hdr[4] == 0
+        for k, (o, w) in enumerate(zip(outs, want)):
+            assert same(o, w), (mode, k, len(w))
+
+
 def test_k2_one_launch_form_within_tolerance(golden):
     """mode 2: forward + backward of a short-memory filter in one launch over tiles with a 416-sample halo (segment
     starts / ends inside a region, segments shorter than a tile, many tiles, NaN gaps, short islands)."""
