@@ -71,6 +71,13 @@ def test_k2_exact_forms_pack_many_segments_per_block():
         assert hdr[0] == len(recs) and hdr[4] == 0
         for k, (o, w) in enumerate(zip(outs, want)):
             assert same(o, w), (mode, k, len(w))
+    # z-scored on the way in (first stage of the exact-mask pass): the chain warp z-scores a round's samples in bulk
+    raw = [r * 3.0 + 0.7 for r in recs[:40] if len(r) > 40]
+    wantz = [rp.butterworth(rp.zscore(r), "high", 1.0) for r in raw]
+    for mode in (1, 3):
+        outs, _ = eh.filtfilt(raw, [("high", 1, 4)], mode=mode, zscore=True)
+        for k, (o, w) in enumerate(zip(outs, wantz)):
+            assert same(o, w), ("zscore", mode, k, len(w))
 
 
 def test_k2_one_launch_form_within_tolerance(golden):
