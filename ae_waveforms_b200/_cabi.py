@@ -33,7 +33,7 @@ class K3Params(ctypes.Structure):
         ("keep", c_void_p), ("has_nan", c_void_p), ("n_peaks", c_void_p), ("peaks", c_void_p),
         ("stats", c_void_p), ("median", c_void_p), ("waves", c_void_p), ("zwin", c_void_p),
         ("zparams", c_void_p), ("status", c_void_p), ("hazard_count", c_void_p), ("lazy_sd", c_int),
-        ("workspace", c_void_p), ("workspace_bytes", ctypes.c_ulonglong)]
+        ("workspace", c_void_p), ("workspace_bytes", ctypes.c_ulonglong), ("fast_stats", c_int)]
 
 
 # name -> (restype, argtypes); every symbol include/aewave.h declares
@@ -44,6 +44,8 @@ SIGNATURES = {
     "aew_zscore_workspace_bytes": (c_size_t, [c_longlong, c_longlong]),
     "aew_zscore_stats_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_longlong, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "aew_zscore_stats_fast_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_longlong, c_void_p,
+                                          c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "aew_zscore_apply_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p,
                                      c_longlong, c_longlong, c_void_p]),
     "aew_trim_nan_edges_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p]),

@@ -162,6 +162,12 @@ class Preprocessor:
         # the screen kernel parks the z-scored windows in the filter scratch for the median kernel (measured: 30.1 ms
         # per 179,000 windows against 32.5 when the median kernel re-derives them; profiles/k3_variants.py)
         self.park_windows = bool(int(__import__("os").environ.get("AEW_K3_PARK", "1")))
+        # Behind the tiled filter (~1e-9 from SciPy's output) NumPy's summation order in the per-window z-score buys
+        # nothing: the screen kernel then takes mean / sd from one pass of shifted sums, parks nothing, and the median
+        # kernel z-scores the middle values of its columns (K3Params.fast_stats).  The windows whose decision hangs
+        # on np.std's last bit go through the bit-exact chain anyway (exact_masks); so do filter_mode="exact" and the
+        # feature path (the delineation kernel reads the parked z-scored windows).
+        self.fast_stats = self.filter_mode == 0 and bool(int(__import__("os").environ.get("AEW_K3_FAST_STATS", "1")))
         self.launches = 0
         if self.L > self.lib.aew_windows_max_len():
             raise _cabi.AewError(f"window of {self.L} samples exceeds the kernel limit")
@@ -227,8 +233,9 @@ class Preprocessor:
         return beg_h, end_h, off[:-1].contiguous(), off[1:].contiguous()
 
     @_cabi.on_device
-    def zscore_stats(self, flat, beg_h, end_h, d_beg, d_end):
-        """K1: per-record mean, sd (NumPy bits) and non-NaN count."""
+    def zscore_stats(self, flat, beg_h, end_h, d_beg, d_end, fast=False):
+        """K1: per-record mean, sd (NumPy bits) and non-NaN count.  ``fast``: from one sweep over the samples
+        instead of two, within a few ulp of NumPy's but not bit-identical (``aew_zscore_stats_fast_f64``)."""
         torch, lib = self.torch, self.lib
         n_rec = len(beg_h)
         blk = np.zeros(n_rec + 1, dtype=np.int64)
@@ -239,10 +246,10 @@ class Preprocessor:
         cnt = torch.empty(n_rec, dtype=torch.int64, device=self.device)
         ws_bytes = int(lib.aew_zscore_workspace_bytes(n_rec, n_blocks))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
-        _cabi.check(lib.aew_zscore_stats_f64(_ptr(flat), _ptr(d_beg), _ptr(d_end), _ptr(d_blk), n_rec, n_blocks,
-                                             _ptr(mean), _ptr(sd), _ptr(cnt), _ptr(ws), ws_bytes,
-                                             _cabi.stream_ptr(torch)), "zscore_stats")
-        self.launches += 4
+        entry = lib.aew_zscore_stats_fast_f64 if fast else lib.aew_zscore_stats_f64
+        _cabi.check(entry(_ptr(flat), _ptr(d_beg), _ptr(d_end), _ptr(d_blk), n_rec, n_blocks, _ptr(mean), _ptr(sd),
+                          _ptr(cnt), _ptr(ws), ws_bytes, _cabi.stream_ptr(torch)), "zscore_stats")
+        self.launches += 2 if fast else 4
         return mean, sd, cnt
 
     @_cabi.on_device
@@ -328,10 +335,13 @@ class Preprocessor:
     @_cabi.on_device
     def screen_windows(self, y, win_start_h, want_median=True, want_zwin=False, zscore_windows=True,
                        pvc_threshold=None, sd_threshold=None, L=None, zwin_scratch=None, lazy_sd=False,
-                       d_start=None):
+                       d_start=None, fast_stats=False):
         """K3 (window kernel + beat kernel) + K4 on the windows whose flat offsets are given.  ``zwin_scratch``:
         optional float64 tensor of at least n_win * L elements; the window kernel parks the z-scored windows there
-        for the beat and median kernels (a buffer of this call otherwise)."""
+        for the beat and median kernels (a buffer of this call otherwise).  ``fast_stats`` (with ``lazy_sd``, windows
+        z-scored here, not with ``want_zwin`` or the sequential screen mode): the per-window z-score without NumPy's
+        summation order and without the parked copy (``K3Params.fast_stats`` in include/aewave.h) -- for the output
+        of the tiled filter, which is itself ~1e-9 from SciPy's."""
         torch, lib = self.torch, self.lib
         L = L or self.L
         n_win = len(win_start_h)
@@ -355,8 +365,9 @@ class Preprocessor:
             d_start = self._upload(np.ascontiguousarray(win_start_h, dtype=np.int64))
         # the z-scored windows are parked for the beat and median kernels: in the caller's buffer ('ecg_sample'),
         # in the scratch the caller lends (the filter's second buffer), else in a buffer of this call
+        fast_stats = bool(fast_stats and lazy_sd and zscore_windows and not want_zwin and self.screen_mode != 1)
         zwin_ptr = out["zwin"].data_ptr() if want_zwin else None
-        if zwin_ptr is None and zscore_windows:
+        if zwin_ptr is None and zscore_windows and not fast_stats:
             if zwin_scratch is not None and zwin_scratch.dtype == torch.float64 \
                     and zwin_scratch.numel() >= n_win * L and zwin_scratch.data_ptr() != y.data_ptr():
                 zwin_ptr = zwin_scratch.data_ptr()
@@ -381,7 +392,7 @@ class Preprocessor:
             zparams=out["zparams"].data_ptr() if want_median else None,
             status=out["status"].data_ptr(), hazard_count=out["hazards"].data_ptr(),
             lazy_sd=1 if (lazy_sd and zscore_windows) else 0,
-            workspace=out["_ws"].data_ptr(), workspace_bytes=ws_bytes)
+            workspace=out["_ws"].data_ptr(), workspace_bytes=ws_bytes, fast_stats=1 if fast_stats else 0)
         _cabi.check(lib.aew_windows_beats_f64(ctypes.byref(p), _cabi.stream_ptr(torch)), "windows_beats")
         self.launches += 3 if want_median else 2
         out["_win_start"] = d_start
@@ -503,8 +514,13 @@ class Preprocessor:
             xc = torch.cat([flat[int(b):int(e)] for b, e in zip(beg_h[recs], end_h[recs])])
             d_rec = self._upload(recs.astype(np.int64))
             d_off = self._upload(coff)
-            return (xc, d_rec, d_off, mean.index_select(0, d_rec), sd.index_select(0, d_rec),
-                    cnt.index_select(0, d_rec), self._upload(start_c))
+            if self.fast_stats:
+                # the batch's statistics came from the one-sweep kernel: these records get NumPy's bits here
+                m_c, s_c, n_c = self.zscore_stats(xc, coff[:-1].copy(), coff[1:].copy(), d_off[:-1].contiguous(),
+                                                  d_off[1:].contiguous())
+            else:
+                m_c, s_c, n_c = mean.index_select(0, d_rec), sd.index_select(0, d_rec), cnt.index_select(0, d_rec)
+            return (xc, d_rec, d_off, m_c, s_c, n_c, self._upload(start_c))
 
         # a POOL of side streams, round robin: one pass takes ~150 ms however few records it holds, so the passes of
         # consecutive batches / chunks must run next to each other, not queue behind each other on one stream
@@ -565,7 +581,8 @@ class Preprocessor:
         torch = self.torch
         flat = batch.flat
         beg_h, end_h, d_beg, d_end = self._ranges(batch, trim)
-        mean, sd, cnt = self.zscore_stats(flat, beg_h, end_h, d_beg, d_end)
+        # (fast_stats: one sweep; the records of the exact-mask pass get NumPy's bits in resolve_hazards)
+        mean, sd, cnt = self.zscore_stats(flat, beg_h, end_h, d_beg, d_end, fast=self.fast_stats and not features)
         y, header = self.filter_records(flat, beg_h, end_h, d_beg, d_end, mean, sd, cnt,
                                         out=(scratch or {}).get("y"), tmp=(scratch or {}).get("tmp"))
         if strips:
@@ -587,7 +604,7 @@ class Preprocessor:
         # the z-scored windows are parked (filter scratch) only for the delineation kernel; the median kernel alone
         # re-derives its samples from y and the per-window mean / sd.  np.std is evaluated where it decides the mask.
         scr = self.screen_windows(y, win_start, zwin_scratch=tmp if (features or self.park_windows) else None,
-                                  lazy_sd=self.lazy_sd)
+                                  lazy_sd=self.lazy_sd, fast_stats=self.fast_stats and not features)
         hz = None
         lazy = bool(lazy_hazards and defer and not features and self.exact_masks)
         if self.exact_masks and not lazy:
@@ -855,12 +872,12 @@ def run_host_pipelined(pre: Preprocessor, host_flat, rec_off, case_ids=None, chu
         pw = widen_to_f64(pbuf, None, gain, offset, sentinel) if narrow else pbuf
         sub = RecordBatch(pw, poff, rest)
         beg_h, end_h, d_beg, d_end = pre._ranges(sub, trim=False)
-        mean, sd, cnt = pre.zscore_stats(pw, beg_h, end_h, d_beg, d_end)
+        mean, sd, cnt = pre.zscore_stats(pw, beg_h, end_h, d_beg, d_end, fast=pre.fast_stats)
         y, _ = pre.filter_records(pw, beg_h, end_h, d_beg, d_end, mean, sd, cnt, mode=0)
         wstart, wcase, _ = pre.window_table(beg_h, end_h, rest)
         if not len(wstart):
             return rest
-        scr = pre.screen_windows(y, wstart, want_median=False, lazy_sd=True)
+        scr = pre.screen_windows(y, wstart, want_median=False, lazy_sd=True, fast_stats=pre.fast_stats)
         npk = scr["n_peaks"].cpu().numpy()
         # closest first: records whose first windows hold exactly hazard_peak_count() beats, then +-1, then +-2 (their
         # sequential pass takes ~200 ms whatever the chunk: the sooner they cross PCIe the better); the others after

@@ -225,6 +225,132 @@ __global__ void __launch_bounds__(256) k1_combine(const long long* __restrict__ 
   }
 }
 
+// ---- the statistics in ONE sweep (aew_zscore_stats_fast_f64): for callers that do not need NumPy's bits -- the
+// tiled filter behind it is ~1e-9 from SciPy's output anyway -- 8 B/sample instead of 16.  A block takes the same
+// range of its record as k1_leaf (a subtree of 32 leaves, ~3,500 samples) and reduces it to (n, mean, M2) around a
+// shift of its own (its first sample: the sums of d = x - c and d^2 cancel nothing however far the record sits from
+// zero); k1_fast_combine merges the triples of a record in a fixed order (Chan et al.): deterministic, and within a
+// few ulp of np.nanmean / np.nanstd.  A NaN poisons the plain sums; only such a block repeats its range NaN-aware.
+__global__ void __launch_bounds__(256) k1_fast_leaf(const double* __restrict__ x, const long long* __restrict__ rec_beg,
+                                                    const long long* __restrict__ rec_end,
+                                                    const long long* __restrict__ blk_start, long long n_rec,
+                                                    double* __restrict__ nodes) {
+  __shared__ double s_red[3][8];
+  __shared__ long long s_lo, s_n;
+  __shared__ double s_c;
+  __shared__ int s_redo;
+  const long long b = blockIdx.x;
+  if (threadIdx.x == 0) {
+    const long long r0 = find_record(blk_start, n_rec, b);
+    const long long base0 = rec_beg[r0], n0 = rec_end[r0] - base0;
+    const int depth = pw_depth(n0);
+    const int sub0 = depth < 5 ? depth : 5;
+    long long o, sz;
+    pw_node(n0, depth - sub0, (unsigned)(b - blk_start[r0]), o, sz);
+    s_lo = base0 + o; s_n = sz;
+    double c = sz > 0 ? x[base0 + o] : 0.0;
+    if (isnan(c) && sz > 0) c = x[base0 + o + sz - 1];
+    if (isnan(c) && sz > 0) c = x[base0 + o + sz / 2];
+    s_c = isnan(c) ? 0.0 : c;
+    s_redo = 0;
+  }
+  __syncthreads();
+  const double* xb = x + s_lo;
+  const int n = (int)s_n;
+  const double c = s_c;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double cntd = (double)n;
+#pragma unroll 1
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    double s1a = 0.0, s1b = 0.0, s2a = 0.0, s2b = 0.0, na = 0.0;
+    const bool aware = attempt == 1;
+    // a block's range is 32 leaves of at most 128 samples: 16 per thread, every load issued before the first use
+    // (a sample that is not there reads as the shift: d = 0)
+    {
+      double v[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) v[k] = (threadIdx.x + 256 * k < n) ? __ldg(xb + threadIdx.x + 256 * k) : c;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const bool there = threadIdx.x + 256 * k < n;
+        const bool ok = !aware || !isnan(v[k]);
+        const double d = ok ? v[k] - c : 0.0;
+        if (aware) na += (ok && there) ? 1.0 : 0.0;
+        if (k & 1) { s1b += d; s2b = __fma_rn(d, d, s2b); } else { s1a += d; s2a = __fma_rn(d, d, s2a); }
+      }
+    }
+    for (int i = threadIdx.x + 16 * 256; i < n; i += 256) {   // (never, with the plan of aew_zscore_plan)
+      const double v = __ldg(xb + i);
+      const bool ok = !aware || !isnan(v);
+      const double d = ok ? v - c : 0.0;
+      if (aware) na += ok ? 1.0 : 0.0;
+      s1a += d; s2a = __fma_rn(d, d, s2a);
+    }
+    double s1 = s1a + s1b, s2 = s2a + s2b;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(AEW_FULL, s1, o);
+      s2 += __shfl_xor_sync(AEW_FULL, s2, o);
+      na += __shfl_xor_sync(AEW_FULL, na, o);
+    }
+    __syncthreads();                                      // (second attempt: the first one's values have been read)
+    if (lane == 0) { s_red[0][warp] = s1; s_red[1][warp] = s2; s_red[2][warp] = na; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double S1 = 0.0, S2 = 0.0, N = 0.0;
+      for (int k = 0; k < 8; ++k) { S1 += s_red[0][k]; S2 += s_red[1][k]; N += s_red[2][k]; }
+      if (!aware && (isnan(S1) || isnan(S2))) {
+        s_redo = 1;
+      } else {
+        if (!aware) N = cntd;
+        const double md = N > 0.0 ? S1 / N : 0.0;
+        nodes[3 * b] = N;
+        nodes[3 * b + 1] = c + md;
+        nodes[3 * b + 2] = N > 0.0 ? S2 - S1 * md : 0.0;
+        s_redo = 0;
+      }
+    }
+    __syncthreads();
+    if (!s_redo) break;
+  }
+}
+
+// one block per record: n = sum n_b, mean = sum n_b mean_b / n, M2 = sum (M2_b + n_b (mean_b - mean)^2), each sum a
+// fixed tree over the record's blocks
+__device__ __forceinline__ double k1_block_sum256(double v, double* s_w) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(AEW_FULL, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int k = 0; k < 8; ++k) t += s_w[k];
+  return t;
+}
+__global__ void __launch_bounds__(256) k1_fast_combine(const long long* __restrict__ blk_start,
+                                                       const double* __restrict__ nodes, double* __restrict__ mean,
+                                                       double* __restrict__ sd, long long* __restrict__ cnt) {
+  __shared__ double s_w[8];
+  const long long r = blockIdx.x;
+  const long long b0 = blk_start[r], b1 = blk_start[r + 1];
+  double n = 0.0, nm = 0.0;
+  for (long long b = b0 + threadIdx.x; b < b1; b += 256) { n += nodes[3 * b]; nm += nodes[3 * b] * nodes[3 * b + 1]; }
+  const double N = k1_block_sum256(n, s_w);
+  const double NM = k1_block_sum256(nm, s_w);
+  const double m = NM / N;                                 // (an all-NaN record: 0 / 0 = NaN, as np.nanmean warns and gives)
+  double m2 = 0.0;
+  for (long long b = b0 + threadIdx.x; b < b1; b += 256) {
+    const double d = nodes[3 * b + 1] - m;
+    m2 += nodes[3 * b + 2] + nodes[3 * b] * d * d;
+  }
+  const double M2 = k1_block_sum256(m2, s_w);
+  if (threadIdx.x == 0) {
+    mean[r] = m;
+    sd[r] = sqrt(M2 / N);
+    if (cnt) cnt[r] = (long long)N;
+  }
+}
+
 // out[i] = (x[i] - mean[r]) / sd[r] for i inside record r; NaN between records
 __global__ void __launch_bounds__(256) k1_apply(const double* __restrict__ x, const long long* __restrict__ rec_beg,
                                                 const long long* __restrict__ rec_end, long long n_rec,
@@ -287,7 +413,7 @@ extern "C" long long aew_zscore_plan(const long long* h_rec_beg, const long long
 }
 
 extern "C" size_t aew_zscore_workspace_bytes(long long n_rec, long long n_blocks) {
-  return (size_t)(2 * n_blocks) * sizeof(double) + (size_t)n_rec * sizeof(unsigned long long) + 64;
+  return (size_t)(3 * n_blocks) * sizeof(double) + (size_t)n_rec * sizeof(unsigned long long) + 64;
 }
 
 extern "C" int aew_trim_nan_edges_f64(const double* x, const long long* d_rec_beg, const long long* d_rec_end,
@@ -319,6 +445,22 @@ extern "C" int aew_zscore_stats_f64(const double* x, const long long* d_rec_beg,
              (const double*)mean, nodes, cnt);
   AEW_LAUNCH(k1_combine<2>, (unsigned)n_rec, 256, 0, st, d_rec_beg, d_rec_end, d_blk_start, nodes, nodes2,
              (const unsigned long long*)cnt, sd);
+  return (int)cudaGetLastError();
+}
+
+// the same three outputs from one sweep over the samples, within a few ulp of NumPy's (not bit-identical)
+extern "C" int aew_zscore_stats_fast_f64(const double* x, const long long* d_rec_beg, const long long* d_rec_end,
+                                         const long long* d_blk_start, long long n_rec, long long n_blocks,
+                                         double* mean, double* sd, long long* count, void* ws, size_t ws_bytes,
+                                         void* stream) {
+  if (!x || !d_rec_beg || !d_rec_end || !d_blk_start || !mean || !sd || !ws || n_rec < 0) return AEW_ERR_ARG;
+  if (n_rec == 0) return AEW_OK;
+  if (ws_bytes < aew_zscore_workspace_bytes(n_rec, n_blocks)) return AEW_ERR_WORKSPACE;
+  if (n_blocks > 0x7fffffffll || n_rec > 0x7fffffffll) return AEW_ERR_UNSUPPORTED;
+  double* nodes = (double*)ws;
+  cudaStream_t st = (cudaStream_t)stream;
+  AEW_LAUNCH(k1_fast_leaf, (unsigned)n_blocks, 256, 0, st, x, d_rec_beg, d_rec_end, d_blk_start, n_rec, nodes);
+  AEW_LAUNCH(k1_fast_combine, (unsigned)n_rec, 256, 0, st, d_blk_start, (const double*)nodes, mean, sd, count);
   return (int)cudaGetLastError();
 }
 

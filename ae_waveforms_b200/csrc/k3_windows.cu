@@ -74,6 +74,8 @@ struct K3Ws {
   unsigned* qbits;      // [n_win][K3_QWS] indicator bits
   double* sumz;         // [n_win] NumPy-order sum of the z-scored window (np.std's mean)
   double* sd;           // [n_win] np.std of the z-scored window where the window kernel formed it (lazy_sd == 0)
+  double* mean;         // [n_win] the window's own mean and sd (its z-score): the median kernel forms the z-scores of
+  double* sd0;          //         the two middle values of a column from them; with fast_stats the beat kernel too
 };
 
 // The NumPy-tree leaves of a length-L vector, tabulated by the host per launch (they depend on L alone), and the
@@ -456,12 +458,11 @@ __device__ __forceinline__ double column_median_64(const BeatSrc& z, const int* 
     v[b] = ok ? z.z[s0 + c] : inf;
     okmask |= (unsigned)ok << b;
   }
-  if (z.zs) {
-#pragma unroll
-    for (int b = 0; b < 32; ++b) {
-      if ((okmask >> b) & 1u) v[b] = div_exact(__dsub_rn(v[b], z.mean), z.dv);   // (padding stays +inf)
-    }
-  }
+  // z.zs: the samples are unscaled and the median is wanted of their z-scores (x - mean) / sd.  The z-score is a
+  // non-decreasing map (rounding is monotonic, sd > 0), so the k-th smallest z-score is the z-score of the k-th
+  // smallest sample: the column is sorted as it is and only the one or two middle values are transformed -- the
+  // same two roundings on the same operands as np.median of the z-scored rows sees, two divisions per column
+  // instead of one per beat.
   int valid = __popc(okmask);
   sort_network<32>(v);
   if (paired) {
@@ -498,6 +499,10 @@ __device__ __forceinline__ double column_median_64(const BeatSrc& z, const int* 
     hi = ((rhi >> 5) == half) ? hi : phi;
   }
   if (valid == 0) return __longlong_as_double(0x7ff8000000000000ll);
+  if (z.zs) {
+    lo = div_exact(__dsub_rn(lo, z.mean), z.dv);
+    hi = div_exact(__dsub_rn(hi, z.mean), z.dv);
+  }
   return __dmul_rn(__dadd_rn(lo, hi), 0.5);
 }
 
@@ -751,6 +756,7 @@ __device__ __forceinline__ void tap_diff_any(const double* W, int lo, int hi, F&
   }
 }
 
+template <bool FAST>
 __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, K3Ws ws, K3Leaves lv, unsigned long long* dbg) {
   AEW_DYN_SMEM(smem_raw);
   K3Smem sm;
@@ -832,16 +838,24 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, K3Ws ws, K3Le
     buf ^= 1;                                                                                              \
   }
 
+  // fast_stats: no NumPy-order sweeps at all.  The window's mean and sd come out of the first prefix pass below
+  // (shifted sums, any order: ~1e-15 from NumPy's), nothing is z-scored here -- the indicator is scale-invariant,
+  // the beat kernel takes the R peaks from the unscaled samples, the median kernel z-scores the middle values of its
+  // columns -- and nothing is parked.  For filter output that is itself ~1e-9 from SciPy's (the tiled filter).
+  constexpr bool fast = FAST;                           // (p.fast_stats, as a template parameter)
   // ---- NaN screen (remove_samples.py:31-33) + sum of the raw window in one sweep
-  double sum_raw;
-  int flag;
-  K3_SWEEP(K3_PASS_PLAIN, 0.0, 1.0, sum_raw, flag)
-  int bad = __syncthreads_or(flag);
+  double sum_raw = 0.0;
+  int flag = 0;
+  int bad = 0;
+  if (!fast) {
+    K3_SWEEP(K3_PASS_PLAIN, 0.0, 1.0, sum_raw, flag)
+    bad = __syncthreads_or(flag);
+  }
   K3_TICK(0)   // load + NaN screen + first sum
   double sum_z = sum_raw;                               // windows that arrive z-scored: the same numbers
   double mean = 0.0, sd0 = 1.0;
   bool parked = false;
-  if (!bad && p.zscore_windows) {
+  if (!fast && !bad && p.zscore_windows) {
     // ---- per-window z-score (data_extract_vitaldb.py:93), NumPy summation order.  The z-scores go STRAIGHT to
     // the parked copy in global memory ('ecg_sample': the beat, median and delineation kernels read them there);
     // the window in shared memory stays as it came: the QRS indicator below is a comparison of two box sums of
@@ -859,7 +873,7 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, K3Ws ws, K3Le
   // sd / n_peaks > threshold only when n_peaks * threshold == 1.  With lazy_sd the beat kernel forms
   // it for those windows alone (from the parked copy); without, it is formed here for every window.
   double sd_full = qnan;
-  if (!bad && !p.lazy_sd) {
+  if (!fast && !bad && !p.lazy_sd) {
     const double mz = k3_div(sum_z, (double)L);
     const LeafOut la_ = p.zscore_windows ? leaf_pass_checked(K3_PASS_ZDEV2, A, nullptr, mean, sd0, mz, offa, sza, lj)
                                          : leaf_pass(K3_PASS_DEV2, A, nullptr, false, mz, 1.0, offa, sza, lj);
@@ -869,7 +883,7 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, K3Ws ws, K3Le
   }
 #undef K3_SWEEP
   K3_TICK(1)   // window z-score (+ sum of the z-scored window)
-  if (zw && !parked) {                                  // windows the caller z-scored, NaN windows: parked as they came
+  if (zw && !parked && !fast) {                         // windows the caller z-scored, NaN windows: parked as they came
 #pragma unroll 4
     for (int i = tid; i < L; i += K3_NT) zw[i] = A[i];
   }
@@ -881,9 +895,11 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, K3Ws ws, K3Le
     for (int i = tid; i < K3_MAXP; i += K3_NT) p.peaks[w * K3_MAXP + i] = -1;
     return;
   }
-  if (tid == 0) {                                       // what the beat kernel needs besides the bits
+  if (tid == 0 && !fast) {                              // what the beat kernel needs besides the bits
     ws.sumz[w] = sum_z;
     ws.sd[w] = sd_full;
+    ws.mean[w] = mean;
+    ws.sd0[w] = sd0;
     p.has_nan[w] = 0;
     sm.scal[0] = mean; sm.scal[1] = sd0;                // (for the sequential evaluation's restore, if it comes to that)
   }
@@ -909,7 +925,59 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, K3Ws ws, K3Le
     const double g0 = 2.0 * fabs(__dsub_rn(A[1], A[0])), gL = 2.0 * fabs(__dsub_rn(A[L - 1], A[L - 2]));
     const double left = e0 > 0 ? W[e0 - 1] : 0.0;
     const double right = e0 + K3_ITEMS < K3_WCAP ? W[e0 + K3_ITEMS] : 0.0;
+    if (fast) {
+      // sums of d = x - x[0] and d^2 over the strip's samples (shifted: no cancellation however far the window sits
+      // from zero); a NaN or an infinity anywhere in the window ends up in the totals
+      const double x0 = A[0];
+      double s1a = 0.0, s1b = 0.0, s2a = 0.0, s2b = 0.0;
+      if (__all_sync(AEW_FULL, j0 >= 0 && j0 + K3_ITEMS <= L)) {
+        const double2* Wq = reinterpret_cast<const double2*>(W + e0);
+#pragma unroll
+        for (int m = 0; m < K3_ITEMS / 2; ++m) {
+          const double2 v = Wq[m];
+          const double dx = v.x - x0, dy = v.y - x0;
+          s1a += dx; s2a += dx * dx;
+          s1b += dy; s2b += dy * dy;
+        }
+      } else {
+#pragma unroll 2
+        for (int k = 0; k < K3_ITEMS; ++k) {
+          const int j = j0 + k;
+          const double d = W[e0 + k] - x0;              // (positions outside the window hold anything)
+          const bool in = j >= 0 && j < L;
+          s1a += in ? d : 0.0;
+          s2a += in ? d * d : 0.0;
+        }
+      }
+      double s1 = s1a + s1b, s2 = s2a + s2b;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(AEW_FULL, s1, o);
+        s2 += __shfl_xor_sync(AEW_FULL, s2, o);
+      }
+      if ((tid & 31) == 0) { sm.pw_vals[tid >> 5] = s1; sm.pw_vals[K3_NW + (tid >> 5)] = s2; }
+    }
     __syncthreads();                                    // every strip's neighbours are in registers
+    if (fast && tid < 32) {
+      // warp 0 finishes the window's statistics while the others are in their strips: lanes 0..15 hold the warps'
+      // sums of d, lanes 16..31 those of d^2
+      double t = tid < 2 * K3_NW ? sm.pw_vals[tid] : 0.0;
+#pragma unroll
+      for (int o = K3_NW / 2; o > 0; o >>= 1) t += __shfl_xor_sync(AEW_FULL, t, o);
+      const double S2 = __shfl_sync(AEW_FULL, t, 16);
+      if (tid == 0) {
+        const double dL = (double)L;
+        const double md = k3_div(t, dL);
+        const double var = k3_div(S2 - t * md, dL);     // (sum d^2 - (sum d)^2 / L) / L
+        const double sdw = k3_sqrt(var);
+        const bool ok = var > 0.0 && sdw > 0.0 && sdw < 1e300;   // (a NaN fails every comparison)
+        mean = A[0] + md;
+        sm.scal[0] = mean; sm.scal[1] = sdw; sm.scal[5] = ok ? 0.0 : 1.0;
+        ws.sumz[w] = qnan; ws.sd[w] = qnan; ws.mean[w] = mean; ws.sd0[w] = sdw;
+        if (p.zparams) { p.zparams[2 * w] = mean; p.zparams[2 * w + 1] = sdw; }
+        if (ok) p.has_nan[w] = 0;
+      }
+    }
     double2* Wp = reinterpret_cast<double2*>(W + e0);
     double run = 0.0;
     double loc[K3_ITEMS];                               // the strip's local prefix sums: held over the block scan, so
@@ -949,6 +1017,14 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, K3Ws ws, K3Le
       Wp[m] = o;
     }
     __syncthreads();                                    // P1 complete
+    if (fast && sm.scal[5] != 0.0) {                    // a NaN in the window, or a constant one (no z-score): removed
+      if (tid == 0) {
+        p.keep[w] = 0; p.has_nan[w] = 1; p.n_peaks[w] = 0;
+        for (int k = 0; k < 4; ++k) p.stats[4 * w + k] = qnan;
+      }
+      for (int i = tid; i < K3_MAXP; i += K3_NT) p.peaks[w * K3_MAXP + i] = -1;
+      return;
+    }
     K3_TICK(3)   // |gradient| prefix sums
     double sv[K3_ITEMS];
     run = 0.0;
@@ -1137,6 +1213,16 @@ struct SumDev2 {                                        // (z[i] - m)^2 of sampl
   __device__ __forceinline__ double operator()(long long i, bool) { const double d = __dsub_rn(z[i], m); return __dmul_rn(d, d); }
 };
 
+struct SumZ {                                           // z = (x[i] - mean) / sd, or (z - m2)^2
+  const double* x; double mean; ExactDiv dv; double m2; int dev2;
+  __device__ __forceinline__ double operator()(long long i, bool) {
+    const double zz = div_exact(__dsub_rn(x[i], mean), dv);
+    if (!dev2) return zz;
+    const double d = __dsub_rn(zz, m2);
+    return __dmul_rn(d, d);
+  }
+};
+
 __global__ void __launch_bounds__(K3P_NT, 8) k3_beats(K3Params p, K3Ws ws) {
   __shared__ unsigned s_q[K3_QWS + 2];
   __shared__ unsigned short s_beg[K3_MAXRUN], s_end[K3_MAXRUN];
@@ -1149,7 +1235,9 @@ __global__ void __launch_bounds__(K3P_NT, 8) k3_beats(K3Params p, K3Ws ws) {
   const long long w = blockIdx.x;
   const double qnan = __longlong_as_double(0x7ff8000000000000ll);
   if (p.has_nan[w] != 0) return;                        // NaN / padding windows: the window kernel has written their rows
-  const double* z = p.zscore_windows ? p.zwin + w * (long long)L : p.y + p.win_start[w];
+  // fast_stats: the unscaled samples.  Strict local maxima and the ranking of prominences are those of the z-scored
+  // samples (a positive affine map) unless two prominences tie to the last bit.
+  const double* z = (p.zscore_windows && !p.fast_stats) ? p.zwin + w * (long long)L : p.y + p.win_start[w];
   const int nwords = (L + 31) >> 5;
   {
     const unsigned* qin = ws.qbits + (size_t)w * K3_QWS;
@@ -1331,6 +1419,12 @@ __global__ void __launch_bounds__(K3P_NT, 8) k3_beats(K3Params p, K3Ws ws) {
   if (need_sd) {
     if (!p.lazy_sd) {
       sd = ws.sd[w];
+    } else if (p.fast_stats) {                             // z-scores formed on the fly, both sums in NumPy's order
+      SumZ fz{z, ws.mean[w], make_exact_div(ws.sd0[w]), 0.0, 0};
+      fz.m2 = k3_div(pw_block_sum(fz, L, pw_depth(L), s_vals, s_valid), (double)L);
+      fz.dev2 = 1;
+      const double ssq2 = pw_block_sum(fz, L, pw_depth(L), s_vals, s_valid);
+      sd = k3_sqrt(k3_div(ssq2, (double)L));
     } else {
       SumDev2 f{z, k3_div(ws.sumz[w], (double)L)};
       const double ssq2 = pw_block_sum(f, L, pw_depth(L), s_vals, s_valid);
@@ -1357,7 +1451,7 @@ __global__ void __launch_bounds__(K3P_NT, 8) k3_beats(K3Params p, K3Ws ws) {
 // Blocks of 160 threads take half of a window's 320 columns each: three of them fit an SM (registers), and their
 // start-up round trips to global memory overlap.
 #define K3B_NT 160
-__global__ void __launch_bounds__(K3B_NT, 3) k3_median(K3Params p, int nparts) {
+__global__ void __launch_bounds__(K3B_NT, 3) k3_median(K3Params p, K3Ws ws, int nparts) {
   __shared__ int s_peaks[K3_MAXP];
   const int S = p.pre + p.post;                          // section length int(0.64 fs): nparts = ceil(S / K3B_NT)
   const long long w = blockIdx.x / nparts;
@@ -1366,15 +1460,15 @@ __global__ void __launch_bounds__(K3B_NT, 3) k3_median(K3Params p, int nparts) {
   const int keep = p.keep[w];
   const int n = p.n_peaks[w];
   const long long start = p.win_start[w];
-  const bool derive = p.zscore_windows && !p.zwin;
-  const double mean = derive ? p.zparams[2 * w] : 0.0;
-  const double sd0 = derive ? p.zparams[2 * w + 1] : 1.0;
+  const bool derive = p.zscore_windows && (!p.zwin || p.fast_stats);
+  const double mean = derive ? ws.mean[w] : 0.0;
+  const double sd0 = derive ? ws.sd0[w] : 1.0;
   if (threadIdx.x < K3_MAXP) s_peaks[threadIdx.x] = p.peaks[w * K3_MAXP + threadIdx.x];
   if (!keep) return;                                     // rows of removed windows stay undefined, as before
   __syncthreads();
   BeatSrc src;                                           // the z-scored window if the screen kernel parked it
-  src.z = p.zwin ? p.zwin + w * (long long)p.L : p.y + start;
-  src.zs = p.zscore_windows && !p.zwin;
+  src.z = derive || !p.zwin ? p.y + start : p.zwin + w * (long long)p.L;
+  src.zs = derive;
   src.mean = mean;
   src.dv = make_exact_div(sd0);
   double* med = p.median ? p.median + w * S : nullptr;
@@ -1445,7 +1539,7 @@ static unsigned long long* k3_timing_buffer() {
 extern "C" int aew_windows_max_peaks(void) { return K3_MAXP; }
 extern "C" int aew_windows_max_len(void) { return K3_MAXL; }
 extern "C" size_t aew_windows_workspace_bytes(long long n_win) {
-  return (size_t)(n_win > 0 ? n_win : 0) * (2 * sizeof(double) + K3_QWS * sizeof(unsigned)) + 64;
+  return (size_t)(n_win > 0 ? n_win : 0) * (4 * sizeof(double) + K3_QWS * sizeof(unsigned)) + 64;
 }
 
 extern "C" int aew_windows_beats_f64(const K3Params* hp, void* stream) {
@@ -1465,7 +1559,9 @@ extern "C" int aew_windows_beats_f64(const K3Params* hp, void* stream) {
   const size_t smem = k3_smem_layout(nullptr, nullptr);
   if (smem > 113 * 1024) return AEW_ERR_UNSUPPORTED;    // two blocks per SM
   // the beat kernel reads the z-scored samples of the QRS runs from the parked copy: with zscore_windows it is required
-  if (p.zscore_windows && !p.zwin) return AEW_ERR_ARG;
+  if (p.zscore_windows && !p.zwin && !p.fast_stats) return AEW_ERR_ARG;
+  // fast_stats: per-window z-score without NumPy's summation order; nothing is parked, np.std only where it decides
+  if (p.fast_stats && (!p.zscore_windows || !p.lazy_sd || p.mode == 1 || p.zwin)) return AEW_ERR_ARG;
   if (!p.workspace || p.workspace_bytes < aew_windows_workspace_bytes(p.n_win)) return AEW_ERR_WORKSPACE;
   K3Ws ws;
   {
@@ -1473,10 +1569,13 @@ extern "C" int aew_windows_beats_f64(const K3Params* hp, void* stream) {
     base += (16 - ((size_t)base & 15)) & 15;
     ws.sumz = (double*)base;
     ws.sd = ws.sumz + p.n_win;
-    ws.qbits = (unsigned*)(ws.sd + p.n_win);
+    ws.mean = ws.sd + p.n_win;
+    ws.sd0 = ws.mean + p.n_win;
+    ws.qbits = (unsigned*)(ws.sd0 + p.n_win);
   }
   // (per call: the attribute is per DEVICE, and the call costs a fraction of a microsecond)
-  if (AEW_SET_MAX_SMEM(k3_windows, 113 * 1024) != 0) return (int)cudaGetLastError();
+  if (AEW_SET_MAX_SMEM(k3_windows<false>, 113 * 1024) != 0) return (int)cudaGetLastError();
+  if (AEW_SET_MAX_SMEM(k3_windows<true>, 113 * 1024) != 0) return (int)cudaGetLastError();
   K3Leaves lv;
   {
     lv.depth = pw_depth(p.L);
@@ -1494,11 +1593,15 @@ extern "C" int aew_windows_beats_f64(const K3Params* hp, void* stream) {
     if (ns == 128 && n0 == n1)                          // groups 2q, 2q + 1 <- the q-th leaf of either residue
       for (int q = 0; q < 64; ++q) { lv.slot[2 * q] = (unsigned char)list0[q]; lv.slot[2 * q + 1] = (unsigned char)list1[q]; }
   }
-  AEW_LAUNCH(k3_windows, (unsigned)p.n_win, K3_NT, smem, (cudaStream_t)stream, p, ws, lv, k3_timing_buffer());
+  if (p.fast_stats) {
+    AEW_LAUNCH(k3_windows<true>, (unsigned)p.n_win, K3_NT, smem, (cudaStream_t)stream, p, ws, lv, k3_timing_buffer());
+  } else {
+    AEW_LAUNCH(k3_windows<false>, (unsigned)p.n_win, K3_NT, smem, (cudaStream_t)stream, p, ws, lv, k3_timing_buffer());
+  }
   AEW_LAUNCH(k3_beats, (unsigned)p.n_win, K3P_NT, 0, (cudaStream_t)stream, p, ws);
   if (p.median || p.waves) {
     const int nparts = (p.pre + p.post + K3B_NT - 1) / K3B_NT;
-    AEW_LAUNCH(k3_median, (unsigned)(nparts * p.n_win), K3B_NT, 0, (cudaStream_t)stream, p, nparts);
+    AEW_LAUNCH(k3_median, (unsigned)(nparts * p.n_win), K3B_NT, 0, (cudaStream_t)stream, p, ws, nparts);
   }
   return (int)cudaGetLastError();
 }

@@ -538,9 +538,9 @@ def run_gpu(args):
     win_start, _, _ = pre_fast.window_table(beg_h, end_h, batch.case_ids)
     n_win = len(win_start)
     k3w_ms = alone(lambda: pre_fast.screen_windows(y_f, win_start, want_median=False, lazy_sd=True,
-                                                   zwin_scratch=None), args.steps)
-    k3_both_ms = alone(lambda: pre_fast.screen_windows(y_f, win_start, lazy_sd=True, zwin_scratch=z_scratch),
-                       args.steps)
+                                                   zwin_scratch=None, fast_stats=pre_fast.fast_stats), args.steps)
+    k3_both_ms = alone(lambda: pre_fast.screen_windows(y_f, win_start, lazy_sd=True, zwin_scratch=z_scratch,
+                                                       fast_stats=pre_fast.fast_stats), args.steps)
     del y_f, z_scratch
 
     # ---- secondary: the same step with the wave delineation (K7) and the 35 np_features (K6) switched on

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AEW_VERSION 112
+#define AEW_VERSION 113
 
 /* return codes */
 #define AEW_OK 0
@@ -58,6 +58,14 @@ int aew_zscore_stats_f64(const double* d_x, const long long* d_rec_beg, const lo
                          const long long* d_blk_start, long long n_rec, long long n_blocks, double* d_mean,
                          double* d_sd, long long* d_count /* non-NaN per record, may be NULL */, void* d_ws,
                          size_t ws_bytes, void* stream);
+/* The same statistics from ONE sweep over the samples (8 B/sample instead of 16): per-block (n, mean, M2) around a
+ * local shift, merged per record in a fixed order -- deterministic and within a few ulp of np.nanmean / np.nanstd
+ * (filters.py:5-12), NOT bit-identical.  For the tiled filter, whose output is ~1e-9 from SciPy's anyway; the
+ * bit-exact chain (exact filter mode, the exact-mask pass, the zscore() drop-in) uses aew_zscore_stats_f64. */
+int aew_zscore_stats_fast_f64(const double* d_x, const long long* d_rec_beg, const long long* d_rec_end,
+                              const long long* d_blk_start, long long n_rec, long long n_blocks, double* d_mean,
+                              double* d_sd, long long* d_count /* may be NULL */, void* d_ws, size_t ws_bytes,
+                              void* stream);
 /* out[i] = (x[i] - mean[r]) / sd[r] over flat positions [lo, hi); NaN propagates, NaN between records */
 int aew_zscore_apply_f64(const double* d_x, const long long* d_rec_beg, const long long* d_rec_end, long long n_rec,
                          const double* d_mean, const double* d_sd, double* d_out, long long lo, long long hi,
@@ -127,7 +135,8 @@ typedef struct K3Params {
   double* median;             /* [n_win][pre + post] float64 median beat of kept windows (may be NULL); the section
                                  is int(0.64 fs) samples, 320 at 500 Hz (median_sample.py:20-25) */
   float* waves;               /* [n_win][pre + post] float32 copy = np_waves rows (may be NULL) */
-  double* zwin;               /* [n_win][L] z-scored windows = 'ecg_sample' column.  REQUIRED with zscore_windows = 1:
+  double* zwin;               /* [n_win][L] z-scored windows = 'ecg_sample' column.  REQUIRED with zscore_windows = 1
+                                 (unless fast_stats, where it must be NULL):
                                  the beat and median kernels read the samples they need from it (may be NULL with
                                  zscore_windows = 0, where y itself holds them) */
   double* zparams;            /* [n_win][2] optional output: mean, sd of each window's z-score (may be NULL) */
@@ -139,6 +148,12 @@ typedef struct K3Params {
   void* workspace;            /* device scratch of aew_windows_workspace_bytes(n_win) bytes: what the window kernel
                                  (z-score, QRS indicator) hands to the beat kernel (runs, R peaks, screen) */
   unsigned long long workspace_bytes;
+  int fast_stats;             /* 1 (with zscore_windows = 1, lazy_sd = 1, mode != 1, zwin = NULL): the per-window z-score
+                                 (data_extract_vitaldb.py:93) without NumPy's summation order -- mean and sd from one
+                                 pass of shifted sums (~1e-15 from np.mean / np.std), R peaks taken from the unscaled
+                                 samples, the median beat z-scored after the column medians; nothing is parked.  For
+                                 filter output that is itself ~1e-9 from SciPy's (the tiled filter); the bit-exact
+                                 chain is fast_stats = 0 */
 } K3Params;
 int aew_windows_max_peaks(void);
 int aew_windows_max_len(void);

@@ -17,7 +17,9 @@ win_start, _, _ = pre.window_table(beg_h, end_h, batch.case_ids)
 del flat
 ref = None
 for name, kw in (("parked, full sd", dict(zwin_scratch=pre._filter_tmp)), ("parked, lazy sd", dict(zwin_scratch=pre._filter_tmp, lazy_sd=True)),
-                 ("derived, full sd", dict()), ("derived, lazy sd", dict(lazy_sd=True)), ("screen only, lazy sd", dict(lazy_sd=True, want_median=False))):
+                 ("derived, full sd", dict()), ("derived, lazy sd", dict(lazy_sd=True)), ("screen only, lazy sd", dict(lazy_sd=True, want_median=False)),
+                 ("fast_stats (no NumPy-order sweeps, nothing parked)", dict(lazy_sd=True, fast_stats=True)),
+                 ("fast_stats, screen only", dict(lazy_sd=True, fast_stats=True, want_median=False))):
     ts = []
     for rep in range(4):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -25,4 +27,4 @@ for name, kw in (("parked, full sd", dict(zwin_scratch=pre._filter_tmp)), ("park
         ts.append(e0.elapsed_time(e1))
     chk = (int(scr['keep'].sum()), int(scr['peaks'].to(torch.int64).sum()),
            int(torch.nan_to_num(scr['median'][scr['keep'].bool()]).view(torch.int64).sum()) if scr['median'] is not None else None)
-    print(f"{name:22s} {min(ts[1:]):7.2f} ms per {len(win_start)} windows   checks {chk}", flush=True)
+    print(f"{name:52s} {min(ts[1:]):7.2f} ms per {len(win_start)} windows   checks {chk}", flush=True)

@@ -41,7 +41,7 @@ def flatten(records):
     return np.ascontiguousarray(flat), off
 
 
-def zscore_stats(records):
+def zscore_stats(records, fast=False):
     L = lib()
     flat, off = flatten(records)
     n = len(records)
@@ -51,8 +51,8 @@ def zscore_stats(records):
     wsb = L.aew_zscore_workspace_bytes(n, nb)
     ws = np.zeros(wsb, np.uint8)
     mean, sd, cnt = np.zeros(n), np.zeros(n), np.zeros(n, np.int64)
-    rc = L.aew_zscore_stats_f64(ptr(flat), ptr(beg), ptr(end), ptr(blk), n, nb, ptr(mean), ptr(sd), ptr(cnt), ptr(ws),
-                                wsb, None)
+    entry = L.aew_zscore_stats_fast_f64 if fast else L.aew_zscore_stats_f64
+    rc = entry(ptr(flat), ptr(beg), ptr(end), ptr(blk), n, nb, ptr(mean), ptr(sd), ptr(cnt), ptr(ws), wsb, None)
     assert rc == 0, rc
     return mean, sd, cnt
 
@@ -119,7 +119,7 @@ def filtfilt(records, stages, mode, zscore=False, max_seg=None):
 
 
 def screen(flat, starts, Lw=10000, mode=0, zscore_windows=True, want_z=False, fs=500, pvc=150.0, sdt=0.05,
-           lazy_sd=0):
+           lazy_sd=0, fast_stats=0):
     L = lib()
     flat = np.ascontiguousarray(flat, dtype=np.float64)
     starts = np.ascontiguousarray(starts, dtype=np.int64)
@@ -140,9 +140,11 @@ def screen(flat, starts, Lw=10000, mode=0, zscore_windows=True, want_z=False, fs
         rr_div=fs * 1000.0, hr_lo=30.0, hr_hi=180.0, pvc_threshold=pvc, sd_threshold=sdt, mode=mode,
         zscore_windows=1 if zscore_windows else 0, keep=o["keep"].ctypes.data, has_nan=o["has_nan"].ctypes.data,
         n_peaks=o["n_peaks"].ctypes.data, peaks=o["peaks"].ctypes.data, stats=o["stats"].ctypes.data,
-        median=o["median"].ctypes.data, waves=o["waves"].ctypes.data, zwin=zpark.ctypes.data if zscore_windows else (o["zwin"].ctypes.data if want_z else None), zparams=o["zparams"].ctypes.data,
+        median=o["median"].ctypes.data, waves=o["waves"].ctypes.data,
+        zwin=None if fast_stats else (zpark.ctypes.data if zscore_windows else (o["zwin"].ctypes.data if want_z else None)),
+        zparams=o["zparams"].ctypes.data,
         status=o["status"].ctypes.data, hazard_count=o["hazards"].ctypes.data, lazy_sd=lazy_sd,
-        workspace=ws.ctypes.data, workspace_bytes=wsb)
+        workspace=ws.ctypes.data, workspace_bytes=wsb, fast_stats=fast_stats)
     rc = L.aew_windows_beats_f64(ctypes.byref(p), None)
     assert rc == 0, rc
     return o

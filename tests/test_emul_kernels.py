@@ -29,6 +29,32 @@ def test_k1_stats_bit_exact():
         assert same(m, np.nanmean(r)) and same(s, np.nanstd(r)) and c == (~np.isnan(r)).sum()
 
 
+def test_k1_one_sweep_statistics_within_rounding():
+    """aew_zscore_stats_fast_f64: one sweep, (n, mean, M2) per block around a local shift, merged per record in a
+    fixed order: within a few ulp of np.nanmean / np.nanstd, exact counts, an all-NaN record gives NaN as NumPy does,
+    a record a long way from zero loses nothing, and two runs give the same bits."""
+    rng = np.random.default_rng(1)
+    lens = [1, 5, 8, 100, 128, 129, 1000, 4999, 10000, 30011, 200003]
+    recs = [rng.standard_normal(n) * rng.uniform(0.5, 50) + rng.uniform(-5, 5) for n in lens]
+    recs[6][3:40] = np.nan
+    recs[8][::7] = np.nan
+    recs[9][0] = np.nan; recs[9][-1] = np.nan; recs[9][15000:15100] = np.nan
+    recs[4][:] = np.nan
+    recs[10] += 1e6                                          # sd ~ 1e-5 of the mean
+    mean, sd, cnt = eh.zscore_stats(recs, fast=True)
+    mean2, sd2, _ = eh.zscore_stats(recs, fast=True)
+    assert same(mean, mean2) and same(sd, sd2)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for r, m, s, c in zip(recs, mean, sd, cnt):
+            assert c == (~np.isnan(r)).sum()
+            wm, ws = np.nanmean(r), np.nanstd(r)
+            if np.isnan(wm):
+                assert np.isnan(m) and np.isnan(s)
+            else:
+                assert abs(m - wm) <= 1e-14 * max(abs(wm), ws) and abs(s - ws) <= 1e-13 * ws, (len(r), m, wm, s, ws)
+
+
 def test_trim_edges():
     a = np.arange(50.0); a[:7] = np.nan; a[-3:] = np.nan
     b = np.full(20, np.nan)
@@ -455,3 +481,49 @@ def test_k7_other_window_lengths_and_rates():
         got = fid[0, :, :len(p)].astype(np.float64)
         got[got == eh.FID_NAN] = np.nan
         assert same(got, ref), fs
+
+
+def test_k3_fast_stats_agrees_with_the_numpy_order_chain(golden):
+    """fast_stats: window mean / sd from one pass of shifted sums, R peaks from the unscaled samples, the median beat
+    z-scored after the column medians, nothing parked.  Against the bit-exact chain on the same windows: the same
+    peaks, decisions and integer-derived statistics; mean / sd / medians to rounding (1e-12); NaN and constant
+    windows removed; np.std reported for the 20-beat windows only (lazy_sd)."""
+    g = golden("e2e")
+    nw = int(g["n_windows"])
+    y = g["filtered"]
+    ref = eh.screen(y, np.arange(nw) * 10000, lazy_sd=1)
+    for mode in (0, 3):                                     # 3: prefix passes, then the sequential evaluation
+        o = eh.screen(y, np.arange(nw) * 10000, mode=mode, lazy_sd=1, fast_stats=1)
+        for k in ("keep", "has_nan", "n_peaks", "peaks"):
+            assert same(o[k], ref[k]), (mode, k)
+        assert same(o["stats"][:, :2], ref["stats"][:, :2])
+        live = ref["has_nan"] == 0
+        assert np.allclose(o["zparams"][live], ref["zparams"][live], rtol=1e-12, atol=1e-14)
+        k = ref["keep"].astype(bool)
+        assert k.any()
+        assert np.max(np.abs(o["median"][k] - ref["median"][k])) < 1e-12
+        assert np.max(np.abs(o["waves"][k] - ref["waves"][k])) < 1e-6
+        assert o["status"][0] == 0
+    # 20-beat windows (np.std decides), a window with a NaN, a constant window, a window far from zero
+    x = ecg_synth.synth_case(7, 8 * 10000 + 5, hr_bpm=60.0)
+    y = rp.butterworth(rp.butterworth(rp.zscore(x), "high", 1.0), "low", 30.0)[:80000].copy()
+    y[10000 + 4321] = np.nan
+    y[20000:30000] = 0.25
+    y[30000:40000] += 1000.0
+    ref = eh.screen(y, np.arange(8) * 10000, lazy_sd=1)
+    o = eh.screen(y, np.arange(8) * 10000, lazy_sd=1, fast_stats=1)
+    assert list(o["has_nan"][:4]) == [0, 1, 1, 0] and same(o["has_nan"], ref["has_nan"])
+    assert same(o["n_peaks"], ref["n_peaks"]) and same(o["peaks"], ref["peaks"])
+    n20 = (ref["n_peaks"] == 20) & (ref["has_nan"] == 0)
+    assert n20.any()
+    assert np.allclose(o["stats"][n20, 2], 1.0, rtol=0, atol=1e-14) and np.isnan(o["stats"][~n20, 2]).all()
+    other = (ref["has_nan"] == 0) & ~n20
+    assert same(o["keep"][other], ref["keep"][other])
+    assert np.allclose(o["zparams"][3], ref["zparams"][3], rtol=1e-11)       # the window shifted by 1000
+    k = (ref["keep"] & o["keep"]).astype(bool)
+    assert np.max(np.abs(o["median"][k] - ref["median"][k])) < 1e-11
+    # the entry refuses what fast_stats does not serve
+    with pytest.raises(AssertionError):
+        eh.screen(y, np.arange(8) * 10000, lazy_sd=0, fast_stats=1)
+    with pytest.raises(AssertionError):
+        eh.screen(y, np.arange(8) * 10000, mode=1, lazy_sd=1, fast_stats=1)
