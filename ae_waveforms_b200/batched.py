@@ -154,6 +154,9 @@ class Preprocessor:
         # windows re-screened from that output, so every keep / remove decision is the reference's bit for bit.
         self.exact_masks = bool(exact_masks) and self.filter_mode == 0
         self.defer_chunks = 6               # run_host_pipelined: chunks finished this many chunks late (exact_masks)
+        # side streams of the exact-mask passes (round robin): at least as many as calls a caller keeps in flight,
+        # or two passes queue behind each other on one stream
+        self.side_stream_count = int(__import__("os").environ.get("AEW_SIDE_STREAMS", "16"))
         # short-memory filters (the low-pass) CAN run forward + backward in one launch (k2_fused, AEW_K2_FUSE=1): half
         # the HBM traffic, but measured SLOWER (3.14 against 2.59 ms per 200 cases): the filter kernels are bound by
         # their FP64 instruction stream (~35 % of the measured DFMA peak), not by bytes, and the halo adds 25 % of it
@@ -526,7 +529,8 @@ class Preprocessor:
         # consecutive batches / chunks must run next to each other, not queue behind each other on one stream
         pool = getattr(self, "_side_streams", None)
         if pool is None:
-            pool = self._side_streams = [torch.cuda.Stream(device=self.device, priority=-1) for _ in range(8)]
+            pool = self._side_streams = [torch.cuda.Stream(device=self.device, priority=-1)
+                                         for _ in range(self.side_stream_count)]
             self._side_next = 0
         side = pool[self._side_next % len(pool)]
         self._side_next += 1

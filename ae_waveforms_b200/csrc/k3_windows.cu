@@ -76,6 +76,7 @@ struct K3Ws {
   double* sd;           // [n_win] np.std of the z-scored window where the window kernel formed it (lazy_sd == 0)
   double* mean;         // [n_win] the window's own mean and sd (its z-score): the median kernel forms the z-scores of
   double* sd0;          //         the two middle values of a column from them; with fast_stats the beat kernel too
+  unsigned char* redo;  // [n_win] set by k3_median_keys for a window it hands back to k3_median (cleared by k3_beats)
 };
 
 // The NumPy-tree leaves of a length-L vector, tabulated by the host per launch (they depend on L alone), and the
@@ -380,10 +381,14 @@ __device__ __forceinline__ void cex(double& a, double& b) {          // a <- min
 // Batcher odd-even merge sort of N (power of two) values held in registers; the
 // recursion is unfolded by templates so that every index is a compile-time constant
 // (191 compare-exchanges for N = 32).  [LO, HI] inclusive.
+__device__ __forceinline__ void cex(unsigned& a, unsigned& b) {      // integer keys: IMNMX x 2
+  const unsigned lo = a < b ? a : b, hi = a < b ? b : a;
+  a = lo; b = hi;
+}
 template <int LO, int HI, int R>
 struct OddEvenMerge {
-  template <int N>
-  static __device__ __forceinline__ void apply(double (&v)[N]) {
+  template <class T, int N>
+  static __device__ __forceinline__ void apply(T (&v)[N]) {
     constexpr int STEP = R * 2;
     if constexpr (STEP < HI - LO) {
       OddEvenMerge<LO, HI, STEP>::apply(v);
@@ -397,8 +402,8 @@ struct OddEvenMerge {
 };
 template <int LO, int HI>
 struct OddEvenSort {
-  template <int N>
-  static __device__ __forceinline__ void apply(double (&v)[N]) {
+  template <class T, int N>
+  static __device__ __forceinline__ void apply(T (&v)[N]) {
     if constexpr (HI - LO >= 1) {
       constexpr int MID = LO + (HI - LO) / 2;
       OddEvenSort<LO, MID>::apply(v);
@@ -407,8 +412,8 @@ struct OddEvenSort {
     }
   }
 };
-template <int N>
-__device__ __forceinline__ void sort_network(double (&v)[N]) { OddEvenSort<0, N - 1>::apply(v); }
+template <class T, int N>
+__device__ __forceinline__ void sort_network(T (&v)[N]) { OddEvenSort<0, N - 1>::apply(v); }
 
 // value of beat b at column c (median_sample.py:30-41): short slices are LEFT-aligned
 // in a NaN row; +inf stands for the NaN padding
@@ -464,7 +469,7 @@ __device__ __forceinline__ double column_median_64(const BeatSrc& z, const int* 
   // same two roundings on the same operands as np.median of the z-scored rows sees, two divisions per column
   // instead of one per beat.
   int valid = __popc(okmask);
-  sort_network<32>(v);
+  sort_network(v);
   if (paired) {
     valid += __shfl_xor_sync(AEW_FULL, valid, 1);
 #pragma unroll
@@ -1213,6 +1218,7 @@ struct SumDev2 {                                        // (z[i] - m)^2 of sampl
   __device__ __forceinline__ double operator()(long long i, bool) { const double d = __dsub_rn(z[i], m); return __dmul_rn(d, d); }
 };
 
+struct SumPlainG { const double* x; __device__ __forceinline__ double operator()(long long i, bool) { return x[i]; } };
 struct SumZ {                                           // z = (x[i] - mean) / sd, or (z - m2)^2
   const double* x; double mean; ExactDiv dv; double m2; int dev2;
   __device__ __forceinline__ double operator()(long long i, bool) {
@@ -1307,7 +1313,10 @@ __global__ void __launch_bounds__(K3P_NT, 8) k3_beats(K3Params p, K3Ws ws) {
   __syncthreads();                                      // beg[] is overwritten by the candidates below
 
   // ---- per run: most prominent strict local maximum (scipy.signal.find_peaks semantics); cand[r] replaces beg[r].
-  //      A run of up to 128 samples is copied into the warp's row first (one coalesced read of the parked window)
+  //      A run of up to 128 samples is copied into the warp's row first (one coalesced read of the window).
+  //      (Staging ALL runs of the window at once with asynchronous copies was measured: 1 ms per 179,000 windows
+  //      SLOWER -- 31 KB of shared memory leave seven blocks per SM instead of eight, and the extra scan and copy
+  //      loop cost more than the overlapped round trips save.)
   for (int r = warp; r < num; r += K3P_NW) {
     const int b = s_beg[r], e = endp[r];
     const int n = e - b;
@@ -1419,9 +1428,17 @@ __global__ void __launch_bounds__(K3P_NT, 8) k3_beats(K3Params p, K3Ws ws) {
   if (need_sd) {
     if (!p.lazy_sd) {
       sd = ws.sd[w];
-    } else if (p.fast_stats) {                             // z-scores formed on the fly, both sums in NumPy's order
-      SumZ fz{z, ws.mean[w], make_exact_div(ws.sd0[w]), 0.0, 0};
-      fz.m2 = k3_div(pw_block_sum(fz, L, pw_depth(L), s_vals, s_valid), (double)L);
+    } else if (p.fast_stats) {
+      // Here the LAST BIT of np.std decides, so this window (one in fifteen) gets the whole NumPy-order chain after
+      // all: its mean and sd as np.mean / np.std form them, the z-scores from those on the fly, their sum, and the
+      // sum of their squared deviations -- the value, and the decision, of the chain without fast_stats.
+      const int dep = pw_depth(L);
+      SumPlainG fx{z};
+      const double mean_e = k3_div(pw_block_sum(fx, L, dep, s_vals, s_valid), (double)L);
+      SumDev2 fd{z, mean_e};
+      const double sd_e = k3_sqrt(k3_div(pw_block_sum(fd, L, dep, s_vals, s_valid), (double)L));
+      SumZ fz{z, mean_e, make_exact_div(sd_e), 0.0, 0};
+      fz.m2 = k3_div(pw_block_sum(fz, L, dep, s_vals, s_valid), (double)L);
       fz.dev2 = 1;
       const double ssq2 = pw_block_sum(fz, L, pw_depth(L), s_vals, s_valid);
       sd = k3_sqrt(k3_div(ssq2, (double)L));
@@ -1438,6 +1455,7 @@ __global__ void __launch_bounds__(K3P_NT, 8) k3_beats(K3Params p, K3Ws ws) {
     const bool remove = (hr < p.hr_lo) || (hr > p.hr_hi) || isnan(hr) || (rms > p.pvc_threshold) || sd_rule;
     p.keep[w] = remove ? 0 : 1;
     p.n_peaks[w] = np;
+    ws.redo[w] = 0;
     p.stats[4 * w + 0] = hr; p.stats[4 * w + 1] = rms; p.stats[4 * w + 2] = sd; p.stats[4 * w + 3] = sdn;
   }
 }
@@ -1451,7 +1469,108 @@ __global__ void __launch_bounds__(K3P_NT, 8) k3_beats(K3Params p, K3Ws ws) {
 // Blocks of 160 threads take half of a window's 320 columns each: three of them fit an SM (registers), and their
 // start-up round trips to global memory overlap.
 #define K3B_NT 160
-__global__ void __launch_bounds__(K3B_NT, 3) k3_median(K3Params p, K3Ws ws, int nparts) {
+
+// Windows of 3..32 beats whose only incomplete sections can be the first and the last beat's (all but a handful): the
+// column median from 32-BIT KEYS.  The high word of a double, made order-preserving, with its low five bits
+// replaced by the slot number, sorts like the double down to 2^-15 relative; the 32 keys of a column are sorted with
+// 191 x 2 integer min / max instead of 191 x (DSETP + 4 SEL) on register pairs, and only the four values around the
+// middle come back as doubles (re-read: they are in L1) to be ordered exactly.  The wanted ranks are FIXED: the
+// slots without a sample are padded with -inf and +inf in equal numbers (to within one), so that the middle of the
+// padded column -- sorted positions 15 and 16 -- is the middle of its samples.  Exactness: position 14..17 hold, in
+// key order, the samples of true rank 14..17 unless three or more samples around the middle agree in their key's 27
+// value bits; then (once in ~10^4 columns) the window is handed to k3_median.
+#define K3K_NEG 0x000fffe0u                             // key of -inf / +inf with the slot bits cleared; every finite
+#define K3K_POS 0xfff00000u                             // double lies strictly between them
+__device__ __forceinline__ unsigned hikey(unsigned hi) {
+  return hi ^ ((unsigned)((int)hi >> 31) | 0x80000000u);
+}
+__global__ void __launch_bounds__(K3B_NT, 6) k3_median_keys(K3Params p, K3Ws ws, int nparts) {
+  __shared__ int s_peaks[32];
+  const int S = p.pre + p.post;
+  const long long w = blockIdx.x / nparts;
+  const int c = (int)(blockIdx.x - w * nparts) * K3B_NT + (int)threadIdx.x;
+  const int keep = p.keep[w];
+  const int n = p.n_peaks[w];
+  const long long start = p.win_start[w];
+  const bool derive = p.zscore_windows && (!p.zwin || p.fast_stats);
+  const double mean = derive ? ws.mean[w] : 0.0;
+  const double sd0 = derive ? ws.sd0[w] : 1.0;
+  if (threadIdx.x < 32) s_peaks[threadIdx.x] = p.peaks[w * K3_MAXP + threadIdx.x];
+  if (!keep || n < 3 || n > 32) return;                  // (k3_median's)
+  __syncthreads();
+  const int L = p.L, pre = p.pre, post = p.post;
+  if (s_peaks[1] < pre || s_peaks[n - 2] + post > L) return;   // a second incomplete section at either end: k3_median's
+  const double* zb = (derive || !p.zwin) ? p.y + start : p.zwin + w * (long long)L;
+  const unsigned* zh = reinterpret_cast<const unsigned*>(zb) + 1;     // high words (little-endian)
+  const bool active = c < S;
+  const int cc = active ? c : 0;
+  // slot 0 <- the first beat, slot 31 <- the last one, slots 1 .. n-2 <- the beats between (whole sections),
+  // slots n-1 .. 30 <- padding
+  const int pk0 = s_peaks[0], pkl = s_peaks[n - 1];
+  const int s00 = pk0 - pre < 0 ? 0 : pk0 - pre, e00 = pk0 + post > L ? L : pk0 + post;
+  const int s0l = pkl - pre, e0l = pkl + post > L ? L : pkl + post;
+  const bool ok0 = s00 + cc < e00, okl = s0l + cc < e0l;
+  // padding alternates -inf, +inf from slot n-1 on; the first one's sign is chosen so that the column ends up with
+  // as many -inf as +inf, give or take one
+  const int P = 32 - n;
+  const bool neg_first = !(!ok0 && okl);
+  const int a_pad = (neg_first ? (P + 1) >> 1 : P >> 1) + (ok0 ? 0 : 1);    // -inf in the column
+  const int b_pad = (neg_first ? P >> 1 : (P + 1) >> 1) + (okl ? 0 : 1);    // +inf
+  unsigned k[32];
+  k[0] = ok0 ? zh[2 * (s00 + cc)] : 0u;
+  k[31] = okl ? zh[2 * (s0l + cc)] : 0u;
+#pragma unroll
+  for (int b = 1; b < 31; ++b) k[b] = b <= n - 2 ? zh[2 * (s_peaks[b] - pre + cc)] : 0u;
+  k[0] = ok0 ? (hikey(k[0]) & ~31u) : K3K_NEG;
+  k[31] = (okl ? (hikey(k[31]) & ~31u) : K3K_POS) | 31u;
+  const unsigned pad_even = neg_first ? K3K_NEG : K3K_POS, pad_odd = neg_first ? K3K_POS : K3K_NEG;
+#pragma unroll
+  for (int b = 1; b < 31; ++b) {
+    const unsigned real = hikey(k[b]) & ~31u;
+    const unsigned pad = ((b - (n - 1)) & 1) ? pad_odd : pad_even;
+    k[b] = (b <= n - 2 ? real : pad) | (unsigned)b;
+  }
+  sort_network(k);
+  // positions 14 .. 17 as doubles, in exact order
+  double v4[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const unsigned kq = k[14 + q];
+    const unsigned tk = kq & ~31u;
+    const int slot = (int)(kq & 31u);
+    const int beat = slot == 31 ? n - 1 : slot;
+    const int pk = s_peaks[beat];
+    const int s0 = pk - pre < 0 ? 0 : pk - pre;
+    double x = __longlong_as_double(tk == K3K_NEG ? (long long)0xfff0000000000000ull : 0x7ff0000000000000ll);
+    if (tk != K3K_NEG && tk != K3K_POS) x = zb[s0 + cc];
+    v4[q] = x;
+  }
+  cex(v4[0], v4[1]); cex(v4[2], v4[3]); cex(v4[0], v4[2]); cex(v4[1], v4[3]); cex(v4[1], v4[2]);
+  // three samples or more with one key around the middle: their order among the positions is not known
+  const unsigned t13 = k[13] & ~31u, t15 = k[15] & ~31u, t16 = k[16] & ~31u, t18 = k[18] & ~31u;
+  const bool unsure = (t13 == t15 && t15 != K3K_NEG && t15 != K3K_POS) || (t16 == t18 && t16 != K3K_NEG && t16 != K3K_POS);
+  if (__any_sync(AEW_FULL, active && unsure)) {
+    if ((threadIdx.x & 31) == 0) ws.redo[w] = 1;           // (both halves of the window are redone)
+  }
+  double lo = a_pad > b_pad ? v4[2] : v4[1];
+  double hi = b_pad > a_pad ? v4[1] : v4[2];
+  if (derive) {
+    const ExactDiv dv = make_exact_div(sd0);
+    lo = div_exact(__dsub_rn(lo, mean), dv);
+    hi = div_exact(__dsub_rn(hi, mean), dv);
+  }
+  const double m = __dmul_rn(__dadd_rn(lo, hi), 0.5);
+  if (active) {
+    if (p.median) p.median[w * S + c] = m;
+    if (p.waves) p.waves[w * S + c] = (float)m;
+  }
+}
+
+// the general form: any number of beats, any incomplete sections; the windows k3_median_keys does not take
+__device__ __forceinline__ bool median_keys_takes(const int* peaks, int n, int L, int pre, int post) {
+  return n >= 3 && n <= 32 && peaks[1] >= pre && peaks[n - 2] + post <= L;
+}
+__global__ void __launch_bounds__(K3B_NT, 3) k3_median(K3Params p, K3Ws ws, int nparts, int keys_done) {
   __shared__ int s_peaks[K3_MAXP];
   const int S = p.pre + p.post;                          // section length int(0.64 fs): nparts = ceil(S / K3B_NT)
   const long long w = blockIdx.x / nparts;
@@ -1466,6 +1585,7 @@ __global__ void __launch_bounds__(K3B_NT, 3) k3_median(K3Params p, K3Ws ws, int 
   if (threadIdx.x < K3_MAXP) s_peaks[threadIdx.x] = p.peaks[w * K3_MAXP + threadIdx.x];
   if (!keep) return;                                     // rows of removed windows stay undefined, as before
   __syncthreads();
+  if (keys_done && median_keys_takes(s_peaks, n, p.L, p.pre, p.post) && !ws.redo[w]) return;   // done already
   BeatSrc src;                                           // the z-scored window if the screen kernel parked it
   src.z = derive || !p.zwin ? p.y + start : p.zwin + w * (long long)p.L;
   src.zs = derive;
@@ -1539,7 +1659,7 @@ static unsigned long long* k3_timing_buffer() {
 extern "C" int aew_windows_max_peaks(void) { return K3_MAXP; }
 extern "C" int aew_windows_max_len(void) { return K3_MAXL; }
 extern "C" size_t aew_windows_workspace_bytes(long long n_win) {
-  return (size_t)(n_win > 0 ? n_win : 0) * (4 * sizeof(double) + K3_QWS * sizeof(unsigned)) + 64;
+  return (size_t)(n_win > 0 ? n_win : 0) * (4 * sizeof(double) + K3_QWS * sizeof(unsigned) + 1) + 64;
 }
 
 extern "C" int aew_windows_beats_f64(const K3Params* hp, void* stream) {
@@ -1572,6 +1692,7 @@ extern "C" int aew_windows_beats_f64(const K3Params* hp, void* stream) {
     ws.mean = ws.sd + p.n_win;
     ws.sd0 = ws.mean + p.n_win;
     ws.qbits = (unsigned*)(ws.sd0 + p.n_win);
+    ws.redo = (unsigned char*)(ws.qbits + (size_t)p.n_win * K3_QWS);
   }
   // (per call: the attribute is per DEVICE, and the call costs a fraction of a microsecond)
   if (AEW_SET_MAX_SMEM(k3_windows<false>, 113 * 1024) != 0) return (int)cudaGetLastError();
@@ -1601,7 +1722,11 @@ extern "C" int aew_windows_beats_f64(const K3Params* hp, void* stream) {
   AEW_LAUNCH(k3_beats, (unsigned)p.n_win, K3P_NT, 0, (cudaStream_t)stream, p, ws);
   if (p.median || p.waves) {
     const int nparts = (p.pre + p.post + K3B_NT - 1) / K3B_NT;
-    AEW_LAUNCH(k3_median, (unsigned)(nparts * p.n_win), K3B_NT, 0, (cudaStream_t)stream, p, ws, nparts);
+    const int use_keys = getenv("AEW_K3_MEDIAN_GENERAL") ? 0 : 1;   // (measurement switch: the general kernel alone)
+    if (use_keys) {
+      AEW_LAUNCH(k3_median_keys, (unsigned)(nparts * p.n_win), K3B_NT, 0, (cudaStream_t)stream, p, ws, nparts);
+    }
+    AEW_LAUNCH(k3_median, (unsigned)(nparts * p.n_win), K3B_NT, 0, (cudaStream_t)stream, p, ws, nparts, use_keys);
   }
   return (int)cudaGetLastError();
 }

@@ -412,7 +412,7 @@ def run_gpu(args):
     pre_fast = batched.Preprocessor(device=dev, exact_masks=False)
     scratch = {"y": torch.empty_like(flat), "tmp": torch.empty_like(flat)}
     total = flat.numel()
-    DEPTH = int(os.environ.get("AEW_BENCH_DEPTH", 7))            # calls whose exact-mask pass may still be in flight
+    DEPTH = int(os.environ.get("AEW_BENCH_DEPTH", 9))            # calls whose exact-mask pass may still be in flight
 
     def barrier():
         if world > 1:
@@ -445,7 +445,10 @@ def run_gpu(args):
         pass of its 20-peak records (side stream) runs next to the following calls' kernels.  Everything,
         including the last finish, lies inside the caller's timed region."""
         q, res = [], None
+        trace = [] if os.environ.get("AEW_BENCH_TRACE") else None
         for i in range(steps):
+            if trace is not None:
+                trace.append(torch.cuda.Event(enable_timing=True)); trace[-1].record()
             # the job's last two calls take the low-latency form of the sequential filter (one warp per record: half
             # the wait -- and the device falls idle behind them anyway): the run ends ~200 ms after its last kernels
             # instead of ~320 (profiles/exact_masks_steady.py)
@@ -456,6 +459,10 @@ def run_gpu(args):
         while q:
             res = finish(p, q.pop(0))
         drain()
+        if trace:
+            trace.append(torch.cuda.Event(enable_timing=True)); trace[-1].record(); torch.cuda.synchronize()
+            sys.stderr.write(f"[trace] exact_masks={p.exact_masks} calls started at "
+                             f"{[round(trace[0].elapsed_time(e)) for e in trace]} ms\n")
         return res
 
     # ---- stage timing (CUDA events on the launching stream) wraps the stage methods of the fast-mask object
@@ -521,8 +528,9 @@ def run_gpu(args):
         return float(np.mean(ts))
 
     beg_h, end_h, d_beg, d_end = pre_fast._ranges(batch, trim=False)
-    mean, sd, cnt = pre_fast.zscore_stats(flat, beg_h, end_h, d_beg, d_end)
-    k1_ms = alone(lambda: pre_fast.zscore_stats(flat, beg_h, end_h, d_beg, d_end), args.steps)
+    k1_fast = bool(pre_fast.fast_stats)               # the one-sweep statistics (what the timed steps run)
+    mean, sd, cnt = pre_fast.zscore_stats(flat, beg_h, end_h, d_beg, d_end, fast=k1_fast)
+    k1_ms = alone(lambda: pre_fast.zscore_stats(flat, beg_h, end_h, d_beg, d_end, fast=k1_fast), args.steps)
     # the high-pass alone (k2_pass forward + backward: two launches) and the low-pass alone (k2_fused: one launch)
     pre_hp = batched.Preprocessor(device=dev, lp=None, exact_masks=False)
     pre_lp = batched.Preprocessor(device=dev, hp=None, exact_masks=False)
@@ -702,9 +710,15 @@ def run_gpu(args):
             return e
 
         beats_per_win = tot_beats / max(tot_rows, 1.0)
+        k1_name = "k1_fast_leaf+k1_fast_combine" if k1_fast else "k1_leaf+k1_combine"
+        k3_fast = bool(pre_fast.fast_stats)
         by_kernel = {
-            "k1_leaf+k1_combine": kern("k1", k1_ms, 16.0 * total, "two NumPy-order sweeps of the record (mean, then sd): "
-                                       "16 B/sample; one launch group per step", launches_per_step=1),
+            k1_name: kern("k1_fast" if k1_fast else "k1", k1_ms, (8.0 if k1_fast else 16.0) * total,
+                          "ONE sweep of the record: per-block (n, mean, M2) around a local shift, merged per record in a "
+                          "fixed order: 8 B/sample (the NumPy-order form reads the record twice: 16 B/sample, "
+                          "6.2 ms; it serves the exact filter mode and the records of the exact-mask pass)" if k1_fast else
+                          "two NumPy-order sweeps of the record (mean, then sd): 16 B/sample; one launch group per step",
+                          launches_per_step=1),
             "k2_pass": kern("k2_pass", k2_launch_ms, 16.0 * total, "one direction of the 1 Hz high-pass filtfilt: 8 B "
                             "read + 8 B written per sample; 2 launches per step", launches_per_step=2),
             ("k2_fused" if lp_fused else "k2_pass (low-pass)"): kern(
@@ -712,18 +726,21 @@ def run_gpu(args):
                 "the 30 Hz low-pass, forward + backward in ONE launch over tiles with a 416-sample halo: 8 B read + "
                 "8 B written per sample where two launches move 32 (SURVEY.md 8d counts 32 for this filtfilt)"
                 if lp_fused else "one direction of the low-pass filtfilt", launches_per_step=1 if lp_fused else 2),
-            "k3_windows": kern("k3_windows", k3w_ms, 8.0 * total, "window read once: 8 B/sample (+ peaks, stats); bound "
-                               "by instruction issue, not by HBM (issue slots 63 % busy, profiles/r2_k3_windows.txt)",
+            "k3_windows": kern("k3_windows_fast" if k3_fast else "k3_windows", k3w_ms, 8.0 * total,
+                               "k3_windows + k3_beats: window read once: 8 B/sample (+ peaks, stats)"
+                               + ("; fast_stats: no NumPy-order sweeps, nothing parked" if k3_fast else "") +
+                               "; bound by instruction issue and shared-memory bandwidth, not by HBM",
                                bound="issue (hbm shown for scale)", launches_per_step=1),
-            "k3_median": kern("k3_median", max(k3_both_ms - k3w_ms, 1e-6), beats_per_win * 320 * 8.0 * tot_rows / world,
+            "k3_median": kern("k3_median_fast" if k3_fast else "k3_median", max(k3_both_ms - k3w_ms, 1e-6), beats_per_win * 320 * 8.0 * tot_rows / world,
                               "the beats' samples of every kept window: n_beats x 320 x 8 B per window",
                               bound="issue (hbm shown for scale)", launches_per_step=1)}
-        shares = {"k1_leaf+k1_combine": k1_ms, "k2_pass": k2_hp_ms, "k3_windows": k3w_ms,
+        shares = {k1_name: k1_ms, "k2_pass": k2_hp_ms, "k3_windows": k3w_ms,
                   "k3_median": max(k3_both_ms - k3w_ms, 0.0), ("k2_fused" if lp_fused else "k2_pass (low-pass)"): k2_lp_ms}
         dominant = max(shares, key=shares.get)
         staged_gbs = tot_samples / world * args.steps / sec * 102.7 / 1e9
         kern_ms = k1_ms + k2_hp_ms + k2_lp_ms + k3_both_ms      # the path's kernels, each timed alone with CUDA events
         kern_gbs = 102.7 * total / (kern_ms / 1e3) / 1e9
+        moved = sum(by_kernel[k]["algorithmic_bytes_per_launch"] * by_kernel[k]["launches_per_step"] for k in by_kernel)
         tr_step = None
         if all(by_kernel[k]["traffic"] for k in by_kernel):
             tr_step = sum(by_kernel[k]["traffic"] * by_kernel[k]["launches_per_step"] for k in by_kernel)
@@ -757,13 +774,19 @@ def run_gpu(args):
                          "bound": "hbm", "achieved": kern_gbs, "peak": hbm, "unit": "GB/s", "frac": kern_gbs / hbm,
                          "traffic": tr_step, "peak_source": peak_src,
                          "algorithmic_bytes_per_step": 102.7 * total, "kernel_ms_per_step": kern_ms,
+                         "bytes_these_kernels_need_per_step": moved,
+                         "frac_of_bytes_these_kernels_need": moved / (kern_ms / 1e3) / 1e9 / hbm,
                          "whole_step": {"achieved": staged_gbs, "frac": staged_gbs / hbm,
                                         "note": "the same bytes over the timed step of `value`, which also holds the "
                                                 "exact-mask pass (latency of a sequential chain, not bandwidth), the "
                                                 "host's two reads of counters per call and the compaction"},
-                         "note": "SURVEY.md 8d's staged figure: 24 + 64 + 8 + 6.4 + 0.3 B per sample; the kernels follow "
-                                 "in roofline_by_kernel -- the one with the largest share of the step is named here and is "
-                                 "NOT near the HBM roofline: it is bound by instruction issue",
+                         "note": "`achieved` / `frac`: SURVEY.md 8d's staged figure (24 + 64 + 8 + 6.4 + 0.3 B per sample: what "
+                                 "the staged pipeline moves) over these kernels' time.  The kernels themselves need fewer "
+                                 "bytes than that figure assumes -- the record statistics take one sweep instead of two, "
+                                 "the z-scored windows are never materialised -- `bytes_these_kernels_need_per_step` / "
+                                 "`frac_of_bytes_these_kernels_need` is the same ratio on THEIR bytes (the sum over "
+                                 "roofline_by_kernel).  The kernel with the largest share of the step is named here; the "
+                                 "window kernel is NOT near the HBM roofline: it is bound by instruction issue",
                          "dominant_kernel": dominant,
                          "dominant_kernel_frac": by_kernel[dominant]["frac"]},
             "roofline_by_kernel": by_kernel,

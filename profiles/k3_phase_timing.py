@@ -26,15 +26,16 @@ for mode in (0, 1):
     print('  mode', mode, 'kept', int(scr['keep'].sum()), 'hazards', int(scr['hazards'].item()), 'peaks checksum', int(scr['peaks'].to(torch.int64).sum().item()), 'median checksum', int(torch.nan_to_num(scr['median'][scr['keep'].bool()]).view(torch.int64).sum().item()))
 pre.screen_mode = 0
 out = np.zeros(16, np.uint64)
-names = ["load+nan+sum", "zscore", "np.std (lazy) + decision", "-", "-", "QRS indicator (4 segments)", "seq fallback", "run compaction",
+names = ["load (+ nan + sum)", "zscore sweeps", "t2", "|gradient| prefix (+ one-sweep statistics)", "smoothgrad prefix", "indicator + hazard vote", "seq fallback", "bits out",
          "min_len", "peak per run", "(unused)", "warp0 chain+stats, peaks out", "median", "t13 leaf table", "t14 load pass", "t15 combine"]
 for rep in range(3):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    scr = pre.screen_windows(y, win_start, zwin_scratch=pre._filter_tmp, lazy_sd=True)      # as Preprocessor.run calls it
+    fast = bool(int(os.environ.get("K3_FAST", "1")))        # as Preprocessor.run calls it behind the tiled filter
+    scr = pre.screen_windows(y, win_start, zwin_scratch=pre._filter_tmp, lazy_sd=True, fast_stats=fast)
     e1.record()
     e2 = torch.cuda.Event(enable_timing=True)
-    pre.screen_windows(y, win_start, want_median=False, lazy_sd=True)
+    pre.screen_windows(y, win_start, want_median=False, lazy_sd=True, fast_stats=fast)
     e2.record()
     torch.cuda.synchronize()
     if os.environ.get('NO_TICKS'):

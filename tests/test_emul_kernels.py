@@ -516,9 +516,9 @@ def test_k3_fast_stats_agrees_with_the_numpy_order_chain(golden):
     assert same(o["n_peaks"], ref["n_peaks"]) and same(o["peaks"], ref["peaks"])
     n20 = (ref["n_peaks"] == 20) & (ref["has_nan"] == 0)
     assert n20.any()
-    assert np.allclose(o["stats"][n20, 2], 1.0, rtol=0, atol=1e-14) and np.isnan(o["stats"][~n20, 2]).all()
-    other = (ref["has_nan"] == 0) & ~n20
-    assert same(o["keep"][other], ref["keep"][other])
+    # where np.std's last bit decides, the beat kernel runs the NumPy-order chain after all: same value, same decision
+    assert same(o["stats"], ref["stats"]) and np.isnan(o["stats"][~n20, 2]).all()
+    assert same(o["keep"], ref["keep"])
     assert np.allclose(o["zparams"][3], ref["zparams"][3], rtol=1e-11)       # the window shifted by 1000
     k = (ref["keep"] & o["keep"]).astype(bool)
     assert np.max(np.abs(o["median"][k] - ref["median"][k])) < 1e-11
@@ -527,3 +527,28 @@ def test_k3_fast_stats_agrees_with_the_numpy_order_chain(golden):
         eh.screen(y, np.arange(8) * 10000, lazy_sd=0, fast_stats=1)
     with pytest.raises(AssertionError):
         eh.screen(y, np.arange(8) * 10000, mode=1, lazy_sd=1, fast_stats=1)
+
+
+def test_k3_median_from_keys_is_exact_with_ties_and_edge_beats():
+    """k3_median_keys sorts 32-bit keys (high words + slot) and orders only the four middle values as doubles; a
+    window whose middle values agree in their keys goes back to the general kernel.  Coarsely quantised windows
+    (many exactly equal samples), the same plus 1e-10 noise (equal keys, different doubles: the hand-back), window
+    starts that cut the first / last beat short: every median equals the oracle's bit for bit."""
+    rng = np.random.default_rng(11)
+    x = ecg_synth.synth_case(21, 6 * 10000 + 700, hr_bpm=71.0)
+    y = rp.butterworth(rp.butterworth(rp.zscore(x), "high", 1.0), "low", 30.0)
+    for name, sig in (("plain", y), ("quantised", np.round(y * 64) / 64),
+                      ("quantised + noise", np.round(y * 64) / 64 + 1e-10 * rng.standard_normal(len(y)))):
+        for shift in (0, 137, 333, 611):                     # moves the beats against the window edges
+            starts = shift + np.arange(6) * 10000
+            o = eh.screen(sig, starts, lazy_sd=0)
+            wins = np.stack([rp.zscore(sig[s:s + 10000]) for s in starts])
+            want = rp.window_screen(wins)
+            checked = 0
+            for j in range(6):
+                assert same(o["peaks"][j, :o["n_peaks"][j]], want["peaks"][j]), (name, shift, j)
+                if o["keep"][j]:
+                    m = rp.compute_median_sample_ecg(wins[j], want["peaks"][j])
+                    assert same(o["median"][j], m), (name, shift, j)
+                    checked += 1
+            assert checked >= 3, (name, shift)

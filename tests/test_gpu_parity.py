@@ -814,6 +814,15 @@ def test_full_size_properties_1000_cases(gpu):
     assert torch.equal(sub["np_waves"], waves[sel]) and torch.equal(sub["np_info"], info[sel])
     assert torch.equal(torch.nan_to_num(sub["np_features"], nan=-1e300), torch.nan_to_num(feats[sel], nan=-1e300))
     del sub
+    # without the feature stage the window statistics come from the one-sweep kernels (K3Params.fast_stats, behind
+    # the tiled filter): the same windows are kept, the beats agree to rounding -- and THAT path, too, must not
+    # depend on the batching
+    plain = pre.run(B.RecordBatch(flat, off, ids), scratch=scratch)
+    assert torch.equal(plain["np_info"], info) and torch.equal(plain["keep"], res["keep"])
+    assert torch.equal(plain["peaks"], res["peaks"])
+    assert float((plain["np_waves"] - waves).abs().max()) < 1e-6
+    waves = plain["np_waves"].clone()
+    del plain
     rows = 0
     for c0 in range(0, n_cases, 100):
         part = pre.run(B.RecordBatch(flat[c0 * ns:(c0 + 100) * ns], off[c0:c0 + 101] - off[c0], ids[c0:c0 + 100]),
