@@ -156,7 +156,7 @@ class Preprocessor:
         self.defer_chunks = 6               # run_host_pipelined: chunks finished this many chunks late (exact_masks)
         # side streams of the exact-mask passes (round robin): at least as many as calls a caller keeps in flight,
         # or two passes queue behind each other on one stream
-        self.side_stream_count = int(__import__("os").environ.get("AEW_SIDE_STREAMS", "16"))
+        self.side_stream_count = int(__import__("os").environ.get("AEW_SIDE_STREAMS", "12"))
         # short-memory filters (the low-pass) CAN run forward + backward in one launch (k2_fused, AEW_K2_FUSE=1): half
         # the HBM traffic, but measured SLOWER (3.14 against 2.59 ms per 200 cases): the filter kernels are bound by
         # their FP64 instruction stream (~35 % of the measured DFMA peak), not by bytes, and the halo adds 25 % of it
@@ -511,10 +511,26 @@ class Preprocessor:
         start_c = np.ascontiguousarray(win_start[hz_h] - beg_h[win_rec[hz_h]] + coff[pos], dtype=np.int64)
         L = self.L
 
+        def side_buffer(numel, stream):
+            # The three big buffers of a pass (1.4 GB each at 100 one-hour records) come from ONE pool, whichever
+            # side stream uses them: the caching allocator keeps a pool per stream, so buffers allocated under the
+            # side streams themselves were never shared between them -- 16 streams x 4.3 GB cached for good, grown by
+            # cudaMalloc in the middle of a run (stalls of 100-250 ms per call while it grows,
+            # profiles/loop_stalls.py).  Allocated under a stream that runs nothing and marked as used by the side
+            # stream, a freed buffer goes to the next pass as soon as this one is through.
+            alloc = getattr(self, "_alloc_stream", None)
+            if alloc is None:
+                alloc = self._alloc_stream = torch.cuda.Stream(device=self.device)
+            with torch.cuda.stream(alloc):
+                buf = torch.empty(int(numel), dtype=torch.float64, device=self.device)
+            buf.record_stream(stream)
+            return buf
+
         def gather():
             # the hazard records' samples and statistics are copied out, so that the sequential pass touches nothing
             # the next batch may overwrite (input buffers, filter scratch)
-            xc = torch.cat([flat[int(b):int(e)] for b, e in zip(beg_h[recs], end_h[recs])])
+            xc = side_buffer(int(lens.sum()), torch.cuda.current_stream(self.device))
+            torch.cat([flat[int(b):int(e)] for b, e in zip(beg_h[recs], end_h[recs])], out=xc)
             d_rec = self._upload(recs.astype(np.int64))
             d_off = self._upload(coff)
             if self.fast_stats:
@@ -536,6 +552,7 @@ class Preprocessor:
         self._side_next += 1
         if after is None:
             xc, d_rec, d_off, m_c, s_c, n_c, d_start_c = gather()   # on the calling stream, before it moves on
+            xc.record_stream(side)
             ready = torch.cuda.Event()
             ready.record(main)
         else:
@@ -545,7 +562,7 @@ class Preprocessor:
             side.wait_event(ready)
             if after is not None:
                 xc, d_rec, d_off, m_c, s_c, n_c, d_start_c = gather()
-            yc, tc = torch.empty_like(xc), torch.empty_like(xc)
+            yc, tc = side_buffer(xc.numel(), side), side_buffer(xc.numel(), side)
             self.filter_records(xc, coff[:-1].copy(), coff[1:].copy(), d_off[:-1].contiguous(), d_off[1:].contiguous(),
                                 m_c, s_c, n_c, out=yc, tmp=tc, mode=3 if low_latency else 1,
                                 max_seg=len(recs) if clean else None)

@@ -1479,13 +1479,17 @@ __global__ void __launch_bounds__(K3P_NT, 8) k3_beats(K3Params p, K3Ws ws) {
 // padded column -- sorted positions 15 and 16 -- is the middle of its samples.  Exactness: position 14..17 hold, in
 // key order, the samples of true rank 14..17 unless three or more samples around the middle agree in their key's 27
 // value bits; then (once in ~10^4 columns) the window is handed to k3_median.
-#define K3K_NEG 0x000fffe0u                             // key of -inf / +inf with the slot bits cleared; every finite
+#define K3K_NEG 0x000fffc0u                             // key of -inf / +inf with (six) slot bits cleared; every finite
 #define K3K_POS 0xfff00000u                             // double lies strictly between them
 __device__ __forceinline__ unsigned hikey(unsigned hi) {
   return hi ^ ((unsigned)((int)hi >> 31) | 0x80000000u);
 }
-__global__ void __launch_bounds__(K3B_NT, 6) k3_median_keys(K3Params p, K3Ws ws, int nparts) {
-  __shared__ int s_peaks[32];
+// NS = 32 slots (3..32 beats, five slot bits) or 64 (33..64 beats, six: keys down to 2^-14 relative)
+template <int NS>
+__global__ void __launch_bounds__(K3B_NT, NS == 32 ? 6 : 4) k3_median_keys(K3Params p, K3Ws ws, int nparts) {
+  constexpr unsigned SLOT = NS - 1;                       // mask of the slot bits
+  constexpr int H = NS / 2;                               // the column's middle: sorted positions H - 1 and H
+  __shared__ int s_peaks[NS];
   const int S = p.pre + p.post;
   const long long w = blockIdx.x / nparts;
   const int c = (int)(blockIdx.x - w * nparts) * K3B_NT + (int)threadIdx.x;
@@ -1495,8 +1499,8 @@ __global__ void __launch_bounds__(K3B_NT, 6) k3_median_keys(K3Params p, K3Ws ws,
   const bool derive = p.zscore_windows && (!p.zwin || p.fast_stats);
   const double mean = derive ? ws.mean[w] : 0.0;
   const double sd0 = derive ? ws.sd0[w] : 1.0;
-  if (threadIdx.x < 32) s_peaks[threadIdx.x] = p.peaks[w * K3_MAXP + threadIdx.x];
-  if (!keep || n < 3 || n > 32) return;                  // (k3_median's)
+  if (threadIdx.x < NS) s_peaks[threadIdx.x] = p.peaks[w * K3_MAXP + threadIdx.x];
+  if (!keep || n < (NS == 32 ? 3 : 33) || n > NS) return; // (the other instance's, or k3_median's)
   __syncthreads();
   const int L = p.L, pre = p.pre, post = p.post;
   if (s_peaks[1] < pre || s_peaks[n - 2] + post > L) return;   // a second incomplete section at either end: k3_median's
@@ -1504,41 +1508,41 @@ __global__ void __launch_bounds__(K3B_NT, 6) k3_median_keys(K3Params p, K3Ws ws,
   const unsigned* zh = reinterpret_cast<const unsigned*>(zb) + 1;     // high words (little-endian)
   const bool active = c < S;
   const int cc = active ? c : 0;
-  // slot 0 <- the first beat, slot 31 <- the last one, slots 1 .. n-2 <- the beats between (whole sections),
-  // slots n-1 .. 30 <- padding
+  // slot 0 <- the first beat, slot NS-1 <- the last one, slots 1 .. n-2 <- the beats between (whole sections),
+  // slots n-1 .. NS-2 <- padding
   const int pk0 = s_peaks[0], pkl = s_peaks[n - 1];
   const int s00 = pk0 - pre < 0 ? 0 : pk0 - pre, e00 = pk0 + post > L ? L : pk0 + post;
   const int s0l = pkl - pre, e0l = pkl + post > L ? L : pkl + post;
   const bool ok0 = s00 + cc < e00, okl = s0l + cc < e0l;
   // padding alternates -inf, +inf from slot n-1 on; the first one's sign is chosen so that the column ends up with
   // as many -inf as +inf, give or take one
-  const int P = 32 - n;
+  const int P = NS - n;
   const bool neg_first = !(!ok0 && okl);
   const int a_pad = (neg_first ? (P + 1) >> 1 : P >> 1) + (ok0 ? 0 : 1);    // -inf in the column
   const int b_pad = (neg_first ? P >> 1 : (P + 1) >> 1) + (okl ? 0 : 1);    // +inf
-  unsigned k[32];
+  unsigned k[NS];
   k[0] = ok0 ? zh[2 * (s00 + cc)] : 0u;
-  k[31] = okl ? zh[2 * (s0l + cc)] : 0u;
+  k[NS - 1] = okl ? zh[2 * (s0l + cc)] : 0u;
 #pragma unroll
-  for (int b = 1; b < 31; ++b) k[b] = b <= n - 2 ? zh[2 * (s_peaks[b] - pre + cc)] : 0u;
-  k[0] = ok0 ? (hikey(k[0]) & ~31u) : K3K_NEG;
-  k[31] = (okl ? (hikey(k[31]) & ~31u) : K3K_POS) | 31u;
+  for (int b = 1; b < NS - 1; ++b) k[b] = b <= n - 2 ? zh[2 * (s_peaks[b] - pre + cc)] : 0u;
+  k[0] = ok0 ? (hikey(k[0]) & ~SLOT) : K3K_NEG;
+  k[NS - 1] = (okl ? (hikey(k[NS - 1]) & ~SLOT) : K3K_POS) | SLOT;
   const unsigned pad_even = neg_first ? K3K_NEG : K3K_POS, pad_odd = neg_first ? K3K_POS : K3K_NEG;
 #pragma unroll
-  for (int b = 1; b < 31; ++b) {
-    const unsigned real = hikey(k[b]) & ~31u;
+  for (int b = 1; b < NS - 1; ++b) {
+    const unsigned real = hikey(k[b]) & ~SLOT;
     const unsigned pad = ((b - (n - 1)) & 1) ? pad_odd : pad_even;
     k[b] = (b <= n - 2 ? real : pad) | (unsigned)b;
   }
   sort_network(k);
-  // positions 14 .. 17 as doubles, in exact order
+  // positions H-2 .. H+1 as doubles, in exact order
   double v4[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const unsigned kq = k[14 + q];
-    const unsigned tk = kq & ~31u;
-    const int slot = (int)(kq & 31u);
-    const int beat = slot == 31 ? n - 1 : slot;
+    const unsigned kq = k[H - 2 + q];
+    const unsigned tk = kq & ~SLOT;
+    const int slot = (int)(kq & SLOT);
+    const int beat = slot == NS - 1 ? n - 1 : slot;
     const int pk = s_peaks[beat];
     const int s0 = pk - pre < 0 ? 0 : pk - pre;
     double x = __longlong_as_double(tk == K3K_NEG ? (long long)0xfff0000000000000ull : 0x7ff0000000000000ll);
@@ -1547,8 +1551,8 @@ __global__ void __launch_bounds__(K3B_NT, 6) k3_median_keys(K3Params p, K3Ws ws,
   }
   cex(v4[0], v4[1]); cex(v4[2], v4[3]); cex(v4[0], v4[2]); cex(v4[1], v4[3]); cex(v4[1], v4[2]);
   // three samples or more with one key around the middle: their order among the positions is not known
-  const unsigned t13 = k[13] & ~31u, t15 = k[15] & ~31u, t16 = k[16] & ~31u, t18 = k[18] & ~31u;
-  const bool unsure = (t13 == t15 && t15 != K3K_NEG && t15 != K3K_POS) || (t16 == t18 && t16 != K3K_NEG && t16 != K3K_POS);
+  const unsigned ta = k[H - 3] & ~SLOT, tb = k[H - 1] & ~SLOT, tc = k[H] & ~SLOT, td = k[H + 2] & ~SLOT;
+  const bool unsure = (ta == tb && tb != K3K_NEG && tb != K3K_POS) || (tc == td && tc != K3K_NEG && tc != K3K_POS);
   if (__any_sync(AEW_FULL, active && unsure)) {
     if ((threadIdx.x & 31) == 0) ws.redo[w] = 1;           // (both halves of the window are redone)
   }
@@ -1568,7 +1572,7 @@ __global__ void __launch_bounds__(K3B_NT, 6) k3_median_keys(K3Params p, K3Ws ws,
 
 // the general form: any number of beats, any incomplete sections; the windows k3_median_keys does not take
 __device__ __forceinline__ bool median_keys_takes(const int* peaks, int n, int L, int pre, int post) {
-  return n >= 3 && n <= 32 && peaks[1] >= pre && peaks[n - 2] + post <= L;
+  return n >= 3 && n <= 64 && peaks[1] >= pre && peaks[n - 2] + post <= L;
 }
 __global__ void __launch_bounds__(K3B_NT, 3) k3_median(K3Params p, K3Ws ws, int nparts, int keys_done) {
   __shared__ int s_peaks[K3_MAXP];
@@ -1724,7 +1728,8 @@ extern "C" int aew_windows_beats_f64(const K3Params* hp, void* stream) {
     const int nparts = (p.pre + p.post + K3B_NT - 1) / K3B_NT;
     const int use_keys = getenv("AEW_K3_MEDIAN_GENERAL") ? 0 : 1;   // (measurement switch: the general kernel alone)
     if (use_keys) {
-      AEW_LAUNCH(k3_median_keys, (unsigned)(nparts * p.n_win), K3B_NT, 0, (cudaStream_t)stream, p, ws, nparts);
+      AEW_LAUNCH(k3_median_keys<32>, (unsigned)(nparts * p.n_win), K3B_NT, 0, (cudaStream_t)stream, p, ws, nparts);
+      AEW_LAUNCH(k3_median_keys<64>, (unsigned)(nparts * p.n_win), K3B_NT, 0, (cudaStream_t)stream, p, ws, nparts);
     }
     AEW_LAUNCH(k3_median, (unsigned)(nparts * p.n_win), K3B_NT, 0, (cudaStream_t)stream, p, ws, nparts, use_keys);
   }

@@ -11,11 +11,40 @@ from .. import _cabi
 from ..sigma_search import SigmaSearch
 
 
+def degenerate_beat_error(x_coordinates, nan_mask, x_t, n_sigma):
+    """What the reference's reconstruct_gaussian RAISES for a beat, or None (signal_reconstruction.py:23-42).
+    Its segment loop walks an index through ``nan_mask`` and ``sigma_map`` and hands the collected samples to
+    ``np.interp``; the index can run past either list (IndexError) and the collection can stay empty (np.interp's
+    ValueError).  Only that index walk is retraced here -- integers and three comparisons per segment, no arithmetic
+    of the reconstruction -- so that a caller catching the reference's exceptions sees the same ones."""
+    xc = np.asarray(x_coordinates, dtype=np.float64)
+    mask = np.asarray(nan_mask, dtype=bool)
+    at, drew = 0, False
+    for seg in range(len(xc) - 1):
+        if at >= n_sigma:
+            return IndexError("list index out of range")
+        while True:
+            if at + 1 >= len(mask):
+                return IndexError(f"index {at + 1} is out of bounds for axis 0 with size {len(mask)}")
+            if not mask[at + 1]:
+                break
+            at += 1
+        lo, hi = xc[seg], xc[seg + 1]
+        drew = drew or bool(hi - lo > 1 and hi > x_t[0] and lo < x_t[-1])
+        at += 1
+    return None if drew else ValueError("array of sample points is empty")
+
+
 def reconstruct_gaussian(x, y, x_t, baseline, sigma_map):
     """signal_reconstruction.py:17-42 -- half-Gaussian segments between consecutive
-    fiducial points, resampled to len(x_t) samples.  Degenerate inputs for which the
-    reference raises IndexError / ValueError yield an all-NaN beat."""
+    fiducial points, resampled to len(x_t) samples.  Degenerate inputs raise what the
+    reference raises (IndexError / ValueError, ``degenerate_beat_error``); the batched
+    ``SigmaSearch`` gives such a beat an all-NaN row instead."""
     x_t = np.asarray(x_t, dtype=np.float64)
+    xc, _, mask = extract_coordinates(x, y, x_t, baseline)
+    err = degenerate_beat_error(xc, mask, x_t, len(sigma_map))
+    if err is not None:
+        raise err
     s = SigmaSearch(np.asarray(x, dtype=np.float64).reshape(1, 11), np.asarray(y, dtype=np.float64).reshape(1, 11),
                     np.asarray([baseline], dtype=np.float64), None, x_t)
     return s.reconstruct(np.asarray(sigma_map, dtype=np.float64)).cpu().numpy()[0]

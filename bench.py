@@ -412,7 +412,7 @@ def run_gpu(args):
     pre_fast = batched.Preprocessor(device=dev, exact_masks=False)
     scratch = {"y": torch.empty_like(flat), "tmp": torch.empty_like(flat)}
     total = flat.numel()
-    DEPTH = int(os.environ.get("AEW_BENCH_DEPTH", 9))            # calls whose exact-mask pass may still be in flight
+    DEPTH = int(os.environ.get("AEW_BENCH_DEPTH", 7))            # calls whose exact-mask pass may still be in flight
 
     def barrier():
         if world > 1:
@@ -478,9 +478,16 @@ def run_gpu(args):
             return out
         return wrapper
 
-    for _ in range(max(1, args.warmup // 2)):
-        run_steps(pre_fast, 1)
-    run_steps(pre, args.warmup)
+    run_steps(pre_fast, 1)
+    run_steps(pre_fast, DEPTH + 2)                    # (the secondary loop's buffers, at its full depth)
+    # the deferred loop holds DEPTH + 1 calls' results and exact-mask buffers at once: the warm-up must reach that depth,
+    # or the caching allocator still grows (cudaMalloc: stalls of 100-250 ms, profiles/loop_stalls.py) inside the
+    # timed steps
+    # ... and every side stream of the exact-mask passes must have been used once: the caching allocator keeps a pool
+    # per stream, a stream's first pass calls cudaMalloc, and cudaMalloc waits for the kernels in flight -- among them
+    # the ~300 ms sequential passes of the calls before (measured: one call of 506 ms with 12 cudaMalloc in it)
+    warm_steps = max(args.warmup, DEPTH + 3, pre.side_stream_count + 2)
+    run_steps(pre, warm_steps)
     barrier()
     pre.launches = 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -619,7 +626,7 @@ def run_gpu(args):
             barrier()
             return (time.perf_counter() - t0) / steps, r
 
-        e2e_s, r_h = time_host(pre, args.steps, min(2, args.warmup))
+        e2e_s, r_h = time_host(pre, args.steps, 3)     # (every side stream of the chunk passes used at least once)
         e2e = {"seconds": e2e_s * args.steps, "h2d": total * 8,
                "d2h": r_h["np_waves"].numel() * 4 + r_h["np_info"].numel() * 8}
         s_fast, r_f = time_host(pre_fast, max(2, min(3, args.steps)), 1)
@@ -757,7 +764,11 @@ def run_gpu(args):
                        "masks": "exact: records with 20-peak windows are re-filtered in SciPy's order (side stream, "
                                 f"calls finished {DEPTH} calls late, all inside the timed region) and those windows "
                                 "re-screened, so every keep / remove decision is the reference's",
-                       "screen_mode": "parallel box filters + exact fallback"},
+                       "screen_mode": "parallel box filters + exact fallback",
+                       "warmup_steps_run": f"{warm_steps} (the deferred loop keeps {DEPTH + 1} calls in flight and "
+                                           f"rotates over {pre.side_stream_count} side streams; with fewer warm-up steps "
+                                           "the allocator still grows inside the timed steps, and a cudaMalloc waits for "
+                                           "the sequential passes in flight)"},
             "beats_per_s": tot_beats * args.steps / sec, "np_waves_rows": tot_rows,
             "hazard_windows": res["hazard_windows"], "exact_masks": mask_info,
             "gpu_launches": int(tot_launch),

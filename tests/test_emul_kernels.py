@@ -537,9 +537,12 @@ def test_k3_median_from_keys_is_exact_with_ties_and_edge_beats():
     rng = np.random.default_rng(11)
     x = ecg_synth.synth_case(21, 6 * 10000 + 700, hr_bpm=71.0)
     y = rp.butterworth(rp.butterworth(rp.zscore(x), "high", 1.0), "low", 30.0)
+    x2 = ecg_synth.synth_case(22, 6 * 10000 + 700, hr_bpm=121.0)       # ~40 beats per window: the 64-slot instance
+    y2 = rp.butterworth(rp.butterworth(rp.zscore(x2), "high", 1.0), "low", 30.0)
     for name, sig in (("plain", y), ("quantised", np.round(y * 64) / 64),
-                      ("quantised + noise", np.round(y * 64) / 64 + 1e-10 * rng.standard_normal(len(y)))):
-        for shift in (0, 137, 333, 611):                     # moves the beats against the window edges
+                      ("quantised + noise", np.round(y * 64) / 64 + 1e-10 * rng.standard_normal(len(y))),
+                      ("fast", y2), ("fast, quantised + noise", np.round(y2 * 64) / 64 + 1e-10 * rng.standard_normal(len(y2)))):
+        for shift in (0, 137, 333, 611) if not name.startswith("fast") else (0, 211):   # moves the beats against the window edges
             starts = shift + np.arange(6) * 10000
             o = eh.screen(sig, starts, lazy_sd=0)
             wins = np.stack([rp.zscore(sig[s:s + 10000]) for s in starts])
@@ -552,3 +555,5 @@ def test_k3_median_from_keys_is_exact_with_ties_and_edge_beats():
                     assert same(o["median"][j], m), (name, shift, j)
                     checked += 1
             assert checked >= 3, (name, shift)
+            if name.startswith("fast"):
+                assert (o["n_peaks"][o["keep"].astype(bool)] > 32).all()

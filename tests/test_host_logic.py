@@ -2,6 +2,7 @@
 drop-in import surface, and the two collectives on world_size-2 gloo (CPU tensors)."""
 import os
 import sys
+import warnings
 
 import numpy as np
 import pytest
@@ -194,3 +195,46 @@ def test_array_store_resume_and_final_arrays(tmp_path):
     assert np.isnan(out["np_features"][:4]).all()
     for name, shape in (("np_waves", (11, 320)), ("np_features", (11, 35)), ("np_info", (11, 2))):
         assert np.load(os.path.join(root, name + ".npy")).shape == shape
+
+
+def test_degenerate_beats_raise_what_the_reference_raises():
+    """reconstruct_gaussian (signal_reconstruction.py:17-42) raises IndexError / ValueError on degenerate beats; the
+    drop-in retraces the index walk that decides it (``degenerate_beat_error``, host integers only).  Against the
+    reference's own function on beats with missing fiducials, missing baselines, everything outside the axis, maps
+    that are too short -- same exception type, or none where the reference returns."""
+    from oracle import ref_import, ref_port as rp
+    if not ref_import.available():
+        pytest.skip("reference modules not present")
+    from ae_waveforms_b200.functions_traditional.signal_reconstruction import degenerate_beat_error
+    ref_fn = ref_import.load().signal_reconstruction.reconstruct_gaussian
+    x_t = rp.beat_time_axis()
+    rng = np.random.default_rng(5)
+    base_x = np.array([-180.0, -150, -120, -40, -25, 0, 25, 45, 150, 250, 330])
+    base_y = np.array([0.0, 0.1, 0.0, -0.1, 0.0, 1.0, -0.2, 0.0, 0.0, 0.3, 0.0])
+    full = [1, 2, 2, 3, 2, 3, 3, 2, 3, 2, 2, 1]
+    cases = [(base_x, base_y, 0.0, full)]
+    for k in range(40):
+        x, y = base_x.copy(), base_y.copy()
+        x[rng.random(11) < rng.choice([0.2, 0.6, 0.95])] = np.nan
+        y[rng.random(11) < 0.1] = np.nan
+        bl = np.nan if k % 5 == 0 else 0.05
+        smap = full[:rng.integers(1, 13)] if k % 4 == 0 else full
+        cases.append((x, y, bl, smap))
+    cases.append((np.full(11, np.nan), base_y, 0.0, full))
+    cases.append((np.full(11, np.nan), base_y, np.nan, full))
+    cases.append((base_x + 5000.0, base_y, 0.0, full))                    # everything right of the axis
+    cases.append((np.full(11, 10.0), base_y, 0.0, full))                  # eleven duplicates, bumped apart by 2 ms
+    seen = set()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for x, y, bl, smap in cases:
+            try:
+                ref_fn(x, y, x_t, bl, smap)
+                want = None
+            except (IndexError, ValueError) as exc:
+                want = type(exc)
+            xc, _, mask = rp.extract_coordinates(x, y, x_t, bl)
+            got = degenerate_beat_error(xc, mask, x_t, len(smap))
+            assert (None if got is None else type(got)) == want, (x, y, bl, smap, got, want)
+            seen.add(want)
+    assert seen == {None, IndexError, ValueError}
