@@ -76,7 +76,8 @@ struct K3Ws {
   double* sd;           // [n_win] np.std of the z-scored window where the window kernel formed it (lazy_sd == 0)
   double* mean;         // [n_win] the window's own mean and sd (its z-score): the median kernel forms the z-scores of
   double* sd0;          //         the two middle values of a column from them; with fast_stats the beat kernel too
-  unsigned char* redo;  // [n_win] set by k3_median_keys for a window it hands back to k3_median (cleared by k3_beats)
+  unsigned char* route; // [n_win] which median kernel takes the window: 0 none (removed), 1 k3_median_keys<32>,
+                        //         2 k3_median_keys<64>, 3 k3_median (also set by a keys kernel that hands a window back)
 };
 
 // The NumPy-tree leaves of a length-L vector, tabulated by the host per launch (they depend on L alone), and the
@@ -775,7 +776,7 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, K3Ws ws, K3Le
 #endif
   if (p.win_start[w] < 0) {                             // padding slot of an over-allocated window table
     if (tid == 0) {
-      p.keep[w] = 0; p.has_nan[w] = 2; p.n_peaks[w] = 0;
+      p.keep[w] = 0; p.has_nan[w] = 2; p.n_peaks[w] = 0; ws.route[w] = 0;
       for (int k = 0; k < 4; ++k) p.stats[4 * w + k] = qnan;
     }
     for (int i = tid; i < K3_MAXP; i += K3_NT) p.peaks[w * K3_MAXP + i] = -1;
@@ -894,7 +895,7 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, K3Ws ws, K3Le
   }
   if (bad) {
     if (tid == 0) {
-      p.keep[w] = 0; p.has_nan[w] = 1; p.n_peaks[w] = 0;
+      p.keep[w] = 0; p.has_nan[w] = 1; p.n_peaks[w] = 0; ws.route[w] = 0;
       for (int k = 0; k < 4; ++k) p.stats[4 * w + k] = qnan;
     }
     for (int i = tid; i < K3_MAXP; i += K3_NT) p.peaks[w * K3_MAXP + i] = -1;
@@ -1024,7 +1025,7 @@ __global__ void __launch_bounds__(K3_NT, 2) k3_windows(K3Params p, K3Ws ws, K3Le
     __syncthreads();                                    // P1 complete
     if (fast && sm.scal[5] != 0.0) {                    // a NaN in the window, or a constant one (no z-score): removed
       if (tid == 0) {
-        p.keep[w] = 0; p.has_nan[w] = 1; p.n_peaks[w] = 0;
+        p.keep[w] = 0; p.has_nan[w] = 1; p.n_peaks[w] = 0; ws.route[w] = 0;
         for (int k = 0; k < 4; ++k) p.stats[4 * w + k] = qnan;
       }
       for (int i = tid; i < K3_MAXP; i += K3_NT) p.peaks[w * K3_MAXP + i] = -1;
@@ -1455,7 +1456,14 @@ __global__ void __launch_bounds__(K3P_NT, 8) k3_beats(K3Params p, K3Ws ws) {
     const bool remove = (hr < p.hr_lo) || (hr > p.hr_hi) || isnan(hr) || (rms > p.pvc_threshold) || sd_rule;
     p.keep[w] = remove ? 0 : 1;
     p.n_peaks[w] = np;
-    ws.redo[w] = 0;
+    // the median kernel of this window: the key-sorting ones take 3..32 / 33..64 beats whose only incomplete sections
+    // can be the first and the last beat's; each median kernel reads this one byte and leaves if it is not its own
+    int route = 0;
+    if (!remove) {
+      const bool plain = np >= 3 && np <= 64 && s_ipeaks[1] >= p.pre && s_ipeaks[np - 2] + p.post <= L;
+      route = plain ? (np <= 32 ? 1 : 2) : 3;
+    }
+    ws.route[w] = (unsigned char)route;
     p.stats[4 * w + 0] = hr; p.stats[4 * w + 1] = rms; p.stats[4 * w + 2] = sd; p.stats[4 * w + 3] = sdn;
   }
 }
@@ -1492,18 +1500,16 @@ __global__ void __launch_bounds__(K3B_NT, NS == 32 ? 6 : 4) k3_median_keys(K3Par
   __shared__ int s_peaks[NS];
   const int S = p.pre + p.post;
   const long long w = blockIdx.x / nparts;
+  if (ws.route[w] != (NS == 32 ? 1 : 2)) return;          // (the other instance's, k3_median's, or nobody's)
   const int c = (int)(blockIdx.x - w * nparts) * K3B_NT + (int)threadIdx.x;
-  const int keep = p.keep[w];
   const int n = p.n_peaks[w];
   const long long start = p.win_start[w];
   const bool derive = p.zscore_windows && (!p.zwin || p.fast_stats);
   const double mean = derive ? ws.mean[w] : 0.0;
   const double sd0 = derive ? ws.sd0[w] : 1.0;
   if (threadIdx.x < NS) s_peaks[threadIdx.x] = p.peaks[w * K3_MAXP + threadIdx.x];
-  if (!keep || n < (NS == 32 ? 3 : 33) || n > NS) return; // (the other instance's, or k3_median's)
   __syncthreads();
   const int L = p.L, pre = p.pre, post = p.post;
-  if (s_peaks[1] < pre || s_peaks[n - 2] + post > L) return;   // a second incomplete section at either end: k3_median's
   const double* zb = (derive || !p.zwin) ? p.y + start : p.zwin + w * (long long)L;
   const unsigned* zh = reinterpret_cast<const unsigned*>(zb) + 1;     // high words (little-endian)
   const bool active = c < S;
@@ -1554,7 +1560,7 @@ __global__ void __launch_bounds__(K3B_NT, NS == 32 ? 6 : 4) k3_median_keys(K3Par
   const unsigned ta = k[H - 3] & ~SLOT, tb = k[H - 1] & ~SLOT, tc = k[H] & ~SLOT, td = k[H + 2] & ~SLOT;
   const bool unsure = (ta == tb && tb != K3K_NEG && tb != K3K_POS) || (tc == td && tc != K3K_NEG && tc != K3K_POS);
   if (__any_sync(AEW_FULL, active && unsure)) {
-    if ((threadIdx.x & 31) == 0) ws.redo[w] = 1;           // (both halves of the window are redone)
+    if ((threadIdx.x & 31) == 0) ws.route[w] = 3;          // (both halves of the window are redone by k3_median)
   }
   double lo = a_pad > b_pad ? v4[2] : v4[1];
   double hi = b_pad > a_pad ? v4[1] : v4[2];
@@ -1571,14 +1577,15 @@ __global__ void __launch_bounds__(K3B_NT, NS == 32 ? 6 : 4) k3_median_keys(K3Par
 }
 
 // the general form: any number of beats, any incomplete sections; the windows k3_median_keys does not take
-__device__ __forceinline__ bool median_keys_takes(const int* peaks, int n, int L, int pre, int post) {
-  return n >= 3 && n <= 64 && peaks[1] >= pre && peaks[n - 2] + post <= L;
-}
 __global__ void __launch_bounds__(K3B_NT, 3) k3_median(K3Params p, K3Ws ws, int nparts, int keys_done) {
   __shared__ int s_peaks[K3_MAXP];
   const int S = p.pre + p.post;                          // section length int(0.64 fs): nparts = ceil(S / K3B_NT)
   const long long w = blockIdx.x / nparts;
   const int c_lo = (int)(blockIdx.x - w * nparts) * K3B_NT;
+  {
+    const int route = ws.route[w];
+    if (route == 0 || (keys_done && route != 3)) return;  // removed, or done by a keys kernel
+  }
   // everything the block needs to get going, in one round trip
   const int keep = p.keep[w];
   const int n = p.n_peaks[w];
@@ -1589,7 +1596,6 @@ __global__ void __launch_bounds__(K3B_NT, 3) k3_median(K3Params p, K3Ws ws, int 
   if (threadIdx.x < K3_MAXP) s_peaks[threadIdx.x] = p.peaks[w * K3_MAXP + threadIdx.x];
   if (!keep) return;                                     // rows of removed windows stay undefined, as before
   __syncthreads();
-  if (keys_done && median_keys_takes(s_peaks, n, p.L, p.pre, p.post) && !ws.redo[w]) return;   // done already
   BeatSrc src;                                           // the z-scored window if the screen kernel parked it
   src.z = derive || !p.zwin ? p.y + start : p.zwin + w * (long long)p.L;
   src.zs = derive;
@@ -1696,7 +1702,7 @@ extern "C" int aew_windows_beats_f64(const K3Params* hp, void* stream) {
     ws.mean = ws.sd + p.n_win;
     ws.sd0 = ws.mean + p.n_win;
     ws.qbits = (unsigned*)(ws.sd0 + p.n_win);
-    ws.redo = (unsigned char*)(ws.qbits + (size_t)p.n_win * K3_QWS);
+    ws.route = (unsigned char*)(ws.qbits + (size_t)p.n_win * K3_QWS);
   }
   // (per call: the attribute is per DEVICE, and the call costs a fraction of a microsecond)
   if (AEW_SET_MAX_SMEM(k3_windows<false>, 113 * 1024) != 0) return (int)cudaGetLastError();
