@@ -314,6 +314,12 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
                                                       //   of a tile, up to the contribution of the look-back
   __shared__ unsigned long long s_bar[K2_STAGES];
   __shared__ long long s_tile[K2_STAGES];
+  // A tile's table entry and its record's z-score parameters travel with the tile: the producer thread, which has the
+  // entry in registers an iteration ahead, leaves both next to the ring slot.  Every thread used to fetch them from
+  // global memory at the top of the iteration -- two DEPENDENT round trips (entry, then mean / sd of its record) in
+  // front of the recursion, and two more loads in the B half: with the mbarrier wait 31 % of a block's time.
+  __shared__ long long s_desc[K2_STAGES][4];
+  __shared__ double s_zs[K2_STAGES][4];               // mean, sd, 1 / sd of the tile's record (forward pass with z-score)
   __shared__ double s_pt2[4];                        // (p^T)^2
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -349,6 +355,10 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
       for (int i = 0; i < 4; ++i) rw[i] = a.ws.tile_desc[4 * t + i];
       const TileDesc d = describe_tile<REV>(rw, a.bulk_ok, pad);
       if (d.bulk) bulk_load(stage0, a.src + d.gstart, K2_T * 8u, &s_bar[0]);
+      for (int i = 0; i < 4; ++i) s_desc[0][i] = rw[i];
+      const bool zon0 = (!REV) && a.mean != nullptr;
+      const double sd0 = zon0 ? a.sd[d.rec] : 1.0;
+      s_zs[0][0] = zon0 ? a.mean[d.rec] : 0.0; s_zs[0][1] = sd0; s_zs[0][2] = zon0 ? 1.0 / sd0 : 1.0;
     }
     if (id1 < n_tiles)
       for (int i = 0; i < 4; ++i) raw1[i] = a.ws.tile_desc[4 * id1 + i];
@@ -399,12 +409,12 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
     if (live) {
       long long rw[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) rw[i] = a.ws.tile_desc[4 * tile + i];
+      for (int i = 0; i < 4; ++i) rw[i] = s_desc[st][i];
       d = describe_tile<REV>(rw, a.bulk_ok, pad);
       const bool zon = (!REV) && a.mean != nullptr;
-      const double mean = zon ? a.mean[d.rec] : 0.0;
-      const ExactDiv sd = make_exact_div(zon ? a.sd[d.rec] : 1.0);
-      const double inv_sd = zon ? 1.0 / a.sd[d.rec] : 1.0;
+      const double mean = s_zs[st][0];
+      const ExactDiv sd = make_exact_div(s_zs[st][1]);
+      const double inv_sd = s_zs[st][2];
       if (d.n <= pad) {                                // filters.py:50-51: too short, copy through
         if (!REV)
           for (long long i = tid; i < d.n; i += K2_NT) a.passthrough[d.g0 + i] = zs(a.src[d.g0 + i], zon, mean, sd);
@@ -485,7 +495,10 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
     K2_TICK_T(K2_PRODUCER, 0, true)
     K2_TICK_T(K2_LOOKER, 0, true)
 
-    // producer thread (warp 1): runs while thread 0 works through its serial section below
+    // producer thread (warp 1): runs while thread 0 works through its serial section below.  (Issuing the next
+    // tile's copy at the TOP of the iteration instead was measured: the blocks wait less for tile data, 31 -> 21 % of
+    // their time, but the producer then sits ~2,000 cycles in bulk_store_wait_read -- the store of two iterations ago
+    // is still being read out of shared memory -- in front of its own A half: 28.0 against 26.3 ms per step.)
     if (tid == K2_PRODUCER) {
       if (live) {
         // start the copy of the next tile into the next ring slot; the slot's previous occupant was
@@ -498,11 +511,22 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
             bulk_store_wait_read(1);
             bulk_load(stage0 + nst * K2_T, a.src + dn.gstart, K2_T * 8u, &s_bar[nst]);
           }
+          for (int i = 0; i < 4; ++i) s_desc[nst][i] = raw1[i];
+          const bool zon1 = (!REV) && a.mean != nullptr;
+          const double sd1 = zon1 ? a.sd[dn.rec] : 1.0;     // (this thread has the time: the block is in its serial section)
+          s_zs[nst][0] = zon1 ? a.mean[dn.rec] : 0.0; s_zs[nst][1] = sd1; s_zs[nst][2] = zon1 ? 1.0 / sd1 : 1.0;
         }
         id1 = id2;                                     // advance the pipeline: results are consumed next iteration
         if (id1 < n_tiles)
           for (int i = 0; i < 4; ++i) raw1[i] = a.ws.tile_desc[4 * id1 + i];
         id2 = (long long)atomicAdd((unsigned long long*)work, 1ull);
+        // Measured and NOT kept (profiles/README.md, "K2: where a block's time goes"): an L2 prefetch of tile it + 2
+        // from here (cp.async.bulk.prefetch.L2: no change, 26.55 against 26.58 ms per step -- the wait for tile data
+        // is not DRAM latency), and claiming one iteration later so that the order of working follows the order of
+        // claiming more closely (the look-back thread's wait falls from 6,600 to 4,500 cycles per iteration, the
+        // wait for tile data grows by as much: 27.6 ms).  The waits move; the step does not -- and with the tiles'
+        // STORES switched off altogether (half the bytes) the filter stage takes 25.5 instead of 26.0 ms: the pass
+        // is bound by its own instruction stream (80 thread instructions per sample at 16 warps per SM), not by memory.
       }
       K2_TICK_T(K2_PRODUCER, 12, false)
     }
@@ -527,6 +551,7 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
           for (int i = 0; i < 4; ++i) o[i] = __shfl_up_sync(AEW_FULL, I[i], dd);
           if (lane >= dd && lane < K2_NW) cmul_acc(PWP + 4 * dd, o, I);
         }
+        K2_TICK(13)  // (thread 0) warp totals loaded + Kogge-Stone scan
         double Xw[4];                                  // exclusive scan = state entering warp `lane`
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -551,6 +576,7 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
         }
       }
     }
+    K2_TICK(14)  // (thread 0) prefixes stored, tile published
     // =================== warp 2, at the same time: resolve the pending tile ===================
     // (independent of the scan above: it combines the PREVIOUS iteration's prefixes with the look-back)
     if (warp == K2_LOOKER / 32) {
@@ -616,8 +642,9 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
     // =================== B half: correct and store the pending tile ===================
     if (have_prev) {
       const bool zon = (!REV) && a.mean != nullptr;
-      const double mean = zon ? a.mean[dp.rec] : 0.0;
-      const double inv_sd = zon ? 1.0 / a.sd[dp.rec] : 1.0;
+      const int stp = (it + K2_STAGES - 1) % K2_STAGES;   // the pending tile's ring slot
+      const double mean = s_zs[stp][0];
+      const double inv_sd = s_zs[stp][2];
       const int dir = (REV && dp.bulk) ? -1 : 1;
       const int base = (REV && dp.bulk) ? K2_T - 1 : 0;
       // state entering my chunk = p^(C*lane) S_warp + end state of the lane before me

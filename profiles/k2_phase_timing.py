@@ -19,4 +19,5 @@ for rep in range(3):
     lib.aew_filt_timing_dump(ctypes.c_void_p(out.ctypes.data))
     tot=out[:9].sum()
     names=["early look-back loads","warp scan","barrier after A","publish+lookback+chains","barrier 2","B half+store","wait tile data","phase 1 recursion","claim+describe+bulk issue"]
-    print(rep, {n: f"{100*float(v)/float(tot):.1f}%" for n,v in zip(names,out[:9])}, "cycles/iter/block", float(tot)/(n_cases*ns/3328*4), "look-back steps that had to wait:", int(out[9]), "of", int(out[10]), "| cycles/iter: look-back thread", float(out[11])/(n_cases*ns/3328*4), "producer thread", float(out[12])/(n_cases*ns/3328*4))
+    print(rep, {n: f"{100*float(v)/float(tot):.1f}%" for n,v in zip(names,out[:9])}, "cycles/iter/block", float(tot)/(n_cases*ns/3328*4), "look-back steps that had to wait:", int(out[9]), "of", int(out[10]), "| cycles/iter: look-back thread", float(out[11])/(n_cases*ns/3328*4), "producer thread", float(out[12])/(n_cases*ns/3328*4),
+          "| thread 0 inside the serial section: scan", float(out[13])/(n_cases*ns/3328*4), "store + publish", float(out[14])/(n_cases*ns/3328*4))
