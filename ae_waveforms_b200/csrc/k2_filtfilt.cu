@@ -15,20 +15,21 @@
 //                 first tile) to the segment table, fills the tile->segment map
 //                 and writes NaN to the output at NaN inputs.  Records whose
 //                 non-NaN count equals their length (known from K1) skip the scan.
-//   k2_pass<REV>  persistent blocks (2 per SM) pull 4352-sample tiles off an atomic
-//                 counter into a 3-slot ring of shared-memory buffers: while tile n is
-//                 computed, tile n+1 arrives by a 1-D bulk copy (TMA, cp.async.bulk +
-//                 mbarrier) and tile n-1 leaves by a bulk store, all issued by one
-//                 thread.  Thread t runs the recursion over its own 17-sample chunk
-//                 from a ZERO state (stride 17 doubles = conflict-free).  The recursion is carried in
+//   k2_pass<REV>  persistent blocks (K2_BPS = 4 per SM, 128 threads each) pull 1,664-sample
+//                 tiles off an atomic counter into a 4-slot ring of shared-memory buffers:
+//                 while tile n is computed, tile n+1 arrives by a 1-D bulk copy (TMA,
+//                 cp.async.bulk + mbarrier) and tile n-1 leaves by a bulk store, all issued
+//                 by one thread.  Thread t runs the recursion over its own 13-sample chunk
+//                 from a ZERO state (stride 13 doubles = conflict-free).  The recursion is carried in
 //                 MODAL form (two complex first-order sections, k2_tables.cpp) so
 //                 that the state transition is diagonal: the chunk end states are
 //                 combined by a warp-shuffle Kogge-Stone scan that costs two
 //                 complex multiplications per step, warps are chained, and the
 //                 state entering the tile comes from a bounded look-back over the
-//                 published end states of the previous tiles (|p|^4352 ~ 8e-10 for
-//                 the 1 Hz high-pass, so two predecessors suffice; the depth is
-//                 computed per filter on the host).  Outputs are then corrected in
+//                 published end states of the previous tiles (|p|^1664 ~ 2e-4 for
+//                 the 1 Hz high-pass, so six predecessors suffice, one lane of the
+//                 look-back warp each; the depth is computed per filter on the
+//                 host).  Outputs are then corrected in
 //                 place with y[j] += G[j] . s (zero-input response) and stored
 //                 coalesced.
 //                 REV=false is the forward pass (x -> tmp), REV=true the backward
@@ -39,6 +40,7 @@
 //
 // Algorithmic HBM bytes: 16 B/sample per pass, 32 B/sample per filtfilt
 // (SURVEY.md section 8d).  Roofline: HBM; FP64 work is ~17 FMA/sample/pass.
+#include <stdio.h>
 #include <stdlib.h>
 #include "aew_rt.h"
 #include "aew_math.cuh"
@@ -55,8 +57,6 @@ struct K2Ws {
   long long* segs;      // [max_seg][4] : g0, n, rec, tile_base
   double* vext;         // [max_seg][16] forward outputs over the right extension
   long long* tile_desc; // [max_tiles][4] per tile: g0, n, (record << 32) | segment, tile index in the segment
-  double* tstate_fwd;   // [max_tiles][4] published tile end states, forward pass (0xFF.. = not yet)
-  double* tstate_bwd;   // [max_tiles][4] same, backward pass
   long long max_seg, max_tiles;
 };
 
@@ -71,8 +71,6 @@ inline size_t k2_ws_layout(void* base, long long max_seg, long long max_tiles, K
   t.segs = (long long*)take((size_t)max_seg * 4 * sizeof(long long));
   t.vext = (double*)take((size_t)max_seg * 16 * sizeof(double));
   t.tile_desc = (long long*)take((size_t)max_tiles * 4 * sizeof(long long));
-  t.tstate_fwd = (double*)take((size_t)max_tiles * 4 * sizeof(double));
-  t.tstate_bwd = (double*)take((size_t)max_tiles * 4 * sizeof(double));
   t.max_seg = max_seg;
   t.max_tiles = max_tiles;
   if (w) *w = t;
@@ -240,6 +238,7 @@ struct PassArgs {
   double cG[4 * K2_C];    // zero-input response rows G[j] (K2_TAB_G)
   double cPK[20];         // p^(C 2^k), k = 0..4 (K2_TAB_PK)
   unsigned long long* dbg; // optional phase-cycle counters (AEW_K2_TIMING=1), else null
+  int run_tiles;          // tiles of a segment a block works through in a row (k2_pass)
 };
 
 // (bulk asynchronous copies and their mbarrier: aew_bulk.cuh)
@@ -266,20 +265,7 @@ __device__ __forceinline__ TileDesc describe_tile(const long long raw[4], int bu
   return d;
 }
 
-// state published by a tile: four doubles written with plain stores; "not yet published" is
-// the all-ones bit pattern (the workspace is memset to 0xFF before each pass), so the values
-// are their own flags and no fence is needed on either side
-#define K2_EMPTY 0xffffffffffffffffull
 #define K2_PRODUCER 32               // thread that claims tiles and issues the bulk copies (warp 1, lane 0)
-#define K2_LOOKER 64                 // thread that resolves the look-back of the pending tile (warp 2, lane 0)
-
-__device__ __forceinline__ bool load_state(const double* p, double q[4]) {
-  const volatile unsigned long long* v = (const volatile unsigned long long*)p;
-  const unsigned long long b0 = v[0], b1 = v[1], b2 = v[2], b3 = v[3];
-  q[0] = __longlong_as_double((long long)b0); q[1] = __longlong_as_double((long long)b1);
-  q[2] = __longlong_as_double((long long)b2); q[3] = __longlong_as_double((long long)b3);
-  return b0 != K2_EMPTY && b1 != K2_EMPTY && b2 != K2_EMPTY && b3 != K2_EMPTY;
-}
 
 #ifdef AEW_EMUL
 #define K2_TICK(slot)
@@ -300,27 +286,73 @@ __device__ __forceinline__ bool load_state(const double* p, double q[4]) {
   }
 #endif
 
+// The order in which a block works through tiles.  A RUN is K2 tiles [m R, (m + 1) R) of one segment (R =
+// PassArgs::run_tiles): a block takes a run as a whole and carries the filter state from tile to tile itself, so
+// that no tile ever waits for another block.  The state entering a run's first tile (m > 0) comes from a WARM-UP:
+// the block first works through the `lookback` tiles in front of the run without storing anything, from a zero
+// state -- |p^T|^lookback < 1e-18, the same truncation the look-back over published states used to make.  Runs are
+// cut relative to the SEGMENT, so a record's output does not depend on where its tiles sit in the batch's table.
+// Blocks claim CHUNKS of R consecutive table entries and own the runs that START inside their chunk (a run's last
+// tiles may lie in the next chunk; that chunk's owner skips them).
+struct TileSeq {
+  long long next, warm_end, run_end, chunk_end;
+};
+
+// number of tiles of the segment a table entry belongs to
+__device__ __forceinline__ long long tiles_of(long long n) { return (n + K2_T - 1) / K2_T; }
+
+// next tile of the sequence (>= n_tiles: the work is used up); *flags: K2_WARM = warm-up tile (no output),
+// K2_FRESH = first tile a block works on for a run (the state entering it is zero unless it is a segment's first)
+#define K2_WARM 1
+#define K2_FRESH 2
+__device__ __forceinline__ long long next_tile(TileSeq& q, const long long* __restrict__ tile_desc, long long* work,
+                                               long long n_tiles, long long R, long long D, int* flags) {
+  int fresh = 0;
+  if (q.next == q.run_end) {
+    fresh = K2_FRESH;
+    long long g = q.run_end;                           // the entry behind the run just finished
+    for (;;) {
+      if (g >= q.chunk_end) {                          // chunk used up: claim the next one
+        const long long r = (long long)atomicAdd((unsigned long long*)work, 1ull);
+        g = r * R;
+        if (g >= n_tiles) { q.next = q.run_end = q.chunk_end = n_tiles; *flags = 0; return n_tiles; }
+        q.chunk_end = g + R < n_tiles ? g + R : n_tiles;
+        const long long k = tile_desc[4 * g + 3], left = tiles_of(tile_desc[4 * g + 1]) - k;
+        const long long to_run = (R - k % R) % R;      // entries up to the next run boundary of this segment
+        g += to_run < left ? to_run : left;            // (or up to the next segment, whichever comes first)
+        continue;                                      // (g may have reached the end of the chunk)
+      }
+      break;
+    }
+    const long long k = tile_desc[4 * g + 3], left = tiles_of(tile_desc[4 * g + 1]) - k;
+    const long long w = k < D ? k : D;
+    q.next = g - w;
+    q.warm_end = g;
+    q.run_end = g + (R < left ? R : left);
+  }
+  *flags = fresh | (q.next < q.warm_end ? K2_WARM : 0);
+  return q.next++;
+}
+
 template <bool REV>
-__global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
+__global__ void __launch_bounds__(K2_NT, K2_BPS) k2_pass(PassArgs a) {
   long long tick_ = 0;
   (void)tick_;
   AEW_DYN_SMEM(smem_raw);
   double* stage0 = (double*)smem_raw;                 // [K2_STAGES][K2_T] tile ring
   double* s_tab = stage0 + K2_STAGES * K2_T;          // [K2_TAB_LEN]
   double* s_Wb = s_tab + K2_TAB_LEN;                  // [2][K2_NW][4] warp totals (double buffered)
-  double* s_S = s_Wb + 8 * K2_NW;                     // [K2_NW][4] state entering each warp
-  double* s_in = s_S + 4 * K2_NW;                     // [2][4] state entering a segment's first tile
-  double* s_X = s_in + 8;                             // [2][K2_NW][4] Horner prefixes: state entering each warp
-                                                      //   of a tile, up to the contribution of the look-back
+  double* s_in = s_Wb + 8 * K2_NW;                    // [2][4] state entering a segment's first tile
+  double* s_X = s_in + 8;                             // [2][K2_NW][4] state entering each warp of a tile
   __shared__ unsigned long long s_bar[K2_STAGES];
   __shared__ long long s_tile[K2_STAGES];
+  __shared__ int s_flags[K2_STAGES];                  // K2_WARM | K2_FRESH of the tile in the slot
   // A tile's table entry and its record's z-score parameters travel with the tile: the producer thread, which has the
-  // entry in registers an iteration ahead, leaves both next to the ring slot.  Every thread used to fetch them from
-  // global memory at the top of the iteration -- two DEPENDENT round trips (entry, then mean / sd of its record) in
-  // front of the recursion, and two more loads in the B half: with the mbarrier wait 31 % of a block's time.
+  // entry in registers an iteration ahead, leaves both next to the ring slot (no thread starts an iteration with two
+  // dependent global round trips -- entry, then mean / sd of its record -- in front of the recursion).
   __shared__ long long s_desc[K2_STAGES][4];
   __shared__ double s_zs[K2_STAGES][4];               // mean, sd, 1 / sd of the tile's record (forward pass with z-score)
-  __shared__ double s_pt2[4];                        // (p^T)^2
+  __shared__ double s_chain[4];                       // filter state at the end of the tile worked on last
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < K2_TAB_LEN; i += K2_NT) s_tab[i] = a.tab[i];
@@ -328,28 +360,24 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
     for (int s = 0; s < K2_STAGES; ++s) mbar_init(&s_bar[s], 1);
   __syncthreads();
   const Modal& cf = a.cf;
-  if (tid == 0) {
-    const double* PT0 = s_tab + K2_TAB_PTILE;
-    s_pt2[0] = PT0[0] * PT0[0] - PT0[1] * PT0[1]; s_pt2[1] = 2.0 * PT0[0] * PT0[1];
-    s_pt2[2] = PT0[2] * PT0[2] - PT0[3] * PT0[3]; s_pt2[3] = 2.0 * PT0[2] * PT0[3];
-  }
   const int pad = (int)s_tab[K2_TAB_PAD];
-  const int lookback = (int)s_tab[K2_TAB_LOOKBACK];
-  const double* PW = s_tab + K2_TAB_PWARP;
+  const long long lookback = (long long)s_tab[K2_TAB_LOOKBACK];
+  const long long R = a.run_tiles;
   long long* work = a.ws.hdr + (REV ? H_WORK_BWD : H_WORK_FWD);
-  double* tstate = REV ? a.ws.tstate_bwd : a.ws.tstate_fwd;
   long long n_tiles = a.ws.hdr[H_TILE_TOTAL];
   if (n_tiles > a.ws.max_tiles) n_tiles = a.ws.max_tiles;
 
-  // prologue: claim the first tile and start its copy.  Thread 0 keeps a small software pipeline so that
-  // neither the claim (atomic) nor the tile-table read is waited for in the iteration that issues it:
-  // id1/raw1 = tile it+1 (table entry already loaded), id2 = tile it+2 (claimed)
-  long long id1 = 0, id2 = 0, raw1[4] = {0, 0, 0, 0};
+  // prologue: take the first tile and start its copy.  The producer thread keeps a small software pipeline so that
+  // the tile-table read is not waited for in the iteration that issues it: id1 / raw1 = tile it + 1 (table entry
+  // already loaded)
+  TileSeq seq = {0, 0, 0, 0};
+  long long id1 = 0, raw1[4] = {0, 0, 0, 0};
+  int flags1 = 0;
   if (tid == K2_PRODUCER) {
-    const long long t = (long long)atomicAdd((unsigned long long*)work, 1ull);
-    id1 = (long long)atomicAdd((unsigned long long*)work, 1ull);
-    id2 = (long long)atomicAdd((unsigned long long*)work, 1ull);
+    int f0;
+    const long long t = next_tile(seq, a.ws.tile_desc, work, n_tiles, R, lookback, &f0);
     s_tile[0] = t;
+    s_flags[0] = f0;
     if (t < n_tiles) {
       long long rw[4];
       for (int i = 0; i < 4; ++i) rw[i] = a.ws.tile_desc[4 * t + i];
@@ -359,6 +387,9 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
       const bool zon0 = (!REV) && a.mean != nullptr;
       const double sd0 = zon0 ? a.sd[d.rec] : 1.0;
       s_zs[0][0] = zon0 ? a.mean[d.rec] : 0.0; s_zs[0][1] = sd0; s_zs[0][2] = zon0 ? 1.0 / sd0 : 1.0;
+      id1 = next_tile(seq, a.ws.tile_desc, work, n_tiles, R, lookback, &flags1);
+    } else {
+      id1 = n_tiles;
     }
     if (id1 < n_tiles)
       for (int i = 0; i < 4; ++i) raw1[i] = a.ws.tile_desc[4 * id1 + i];
@@ -370,7 +401,6 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
   TileDesc dp;
   dp.seg = -1;
   bool have_prev = false;
-  long long tile_p = 0;
   double Ep[4] = {0.0, 0.0, 0.0, 0.0};
   double* sm_p = stage0;
 
@@ -381,23 +411,7 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
     const int st = it % K2_STAGES;
     const long long tile = s_tile[st];
     const bool live = tile < n_tiles;
-    // look-back thread: issue the look-back loads of the pending tile now (raw bits, no test yet) so that their
-    // round trip overlaps this tile's recursion; they are examined after the barrier
-    unsigned long long q0[4] = {K2_EMPTY, K2_EMPTY, K2_EMPTY, K2_EMPTY}, q1[4] = {K2_EMPTY, K2_EMPTY, K2_EMPTY, K2_EMPTY},
-                       q2[4] = {K2_EMPTY, K2_EMPTY, K2_EMPTY, K2_EMPTY};
-    if (tid == K2_LOOKER && have_prev && dp.k > 0) {
-      const volatile unsigned long long* v0 = (const volatile unsigned long long*)(tstate + 4 * (tile_p - 1));
-#pragma unroll
-      for (int i = 0; i < 4; ++i) q0[i] = v0[i];
-      if (dp.k > 1 && lookback > 1) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) q1[i] = v0[i - 4];
-      }
-      if (dp.k > 2 && lookback > 2) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) q2[i] = v0[i - 8];
-      }
-    }
+    const int flags = s_flags[st];
     K2_TICK(0)
 
     // =================== A half: recursion and scan of the current tile ===================
@@ -405,7 +419,7 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
     d.seg = -1;
     double E[4] = {0.0, 0.0, 0.0, 0.0};
     double* sm = stage0 + st * K2_T;
-    bool filt = false;                                 // the tile needs a B half
+    bool filt = false;                                 // the tile is filtered (not a short segment copied through)
     if (live) {
       long long rw[4];
 #pragma unroll
@@ -461,10 +475,15 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
         // phase 1: zero-state recursion over my chunk, outputs stored in place
         double* mine = sm + base + dir * (tid * K2_C);
         if (zon) {
+          if (d.cnt == K2_T) {                           // (forward: dir = +1)
 #pragma unroll
-          for (int j = 0; j < K2_C; ++j) {
-            const bool inside = tid * K2_C + j < d.cnt;   // zero padding stays zero under the z-score
-            mine[j] = modal_step(cf, inside ? zsf(mine[j], true, mean, inv_sd) : 0.0, E);   // (forward: dir = +1)
+            for (int j = 0; j < K2_C; ++j) mine[j] = modal_step(cf, zsf(mine[j], true, mean, inv_sd), E);
+          } else {
+#pragma unroll
+            for (int j = 0; j < K2_C; ++j) {
+              const bool inside = tid * K2_C + j < d.cnt;   // zero padding stays zero under the z-score
+              mine[j] = modal_step(cf, inside ? zsf(mine[j], true, mean, inv_sd) : 0.0, E);
+            }
           }
         } else if (dir > 0) {                            // the offsets are compile-time constants in either branch
 #pragma unroll
@@ -493,9 +512,8 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
     __syncthreads();
     K2_TICK(2)   // wait at the barrier after the A half
     K2_TICK_T(K2_PRODUCER, 0, true)
-    K2_TICK_T(K2_LOOKER, 0, true)
 
-    // producer thread (warp 1): runs while thread 0 works through its serial section below.  (Issuing the next
+    // producer thread (warp 1): runs while warp 0 works through its serial section below.  (Issuing the next
     // tile's copy at the TOP of the iteration instead was measured: the blocks wait less for tile data, 31 -> 21 % of
     // their time, but the producer then sits ~2,000 cycles in bulk_store_wait_read -- the store of two iterations ago
     // is still being read out of shared memory -- in front of its own A half: 28.0 against 26.3 ms per step.)
@@ -505,6 +523,7 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
         // handed to a bulk store two iterations ago (one bulk group is committed per iteration)
         const int nst = (it + 1) % K2_STAGES;
         s_tile[nst] = id1;
+        s_flags[nst] = flags1;
         if (id1 < n_tiles) {
           const TileDesc dn = describe_tile<REV>(raw1, a.bulk_ok, pad);
           if (dn.bulk) {
@@ -515,26 +534,20 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
           const bool zon1 = (!REV) && a.mean != nullptr;
           const double sd1 = zon1 ? a.sd[dn.rec] : 1.0;     // (this thread has the time: the block is in its serial section)
           s_zs[nst][0] = zon1 ? a.mean[dn.rec] : 0.0; s_zs[nst][1] = sd1; s_zs[nst][2] = zon1 ? 1.0 / sd1 : 1.0;
+          id1 = next_tile(seq, a.ws.tile_desc, work, n_tiles, R, lookback, &flags1);   // consumed next iteration
+          if (id1 < n_tiles)
+            for (int i = 0; i < 4; ++i) raw1[i] = a.ws.tile_desc[4 * id1 + i];
         }
-        id1 = id2;                                     // advance the pipeline: results are consumed next iteration
-        if (id1 < n_tiles)
-          for (int i = 0; i < 4; ++i) raw1[i] = a.ws.tile_desc[4 * id1 + i];
-        id2 = (long long)atomicAdd((unsigned long long*)work, 1ull);
-        // Measured and NOT kept (profiles/README.md, "K2: where a block's time goes"): an L2 prefetch of tile it + 2
-        // from here (cp.async.bulk.prefetch.L2: no change, 26.55 against 26.58 ms per step -- the wait for tile data
-        // is not DRAM latency), and claiming one iteration later so that the order of working follows the order of
-        // claiming more closely (the look-back thread's wait falls from 6,600 to 4,500 cycles per iteration, the
-        // wait for tile data grows by as much: 27.6 ms).  The waits move; the step does not -- and with the tiles'
-        // STORES switched off altogether (half the bytes) the filter stage takes 25.5 instead of 26.0 ms: the pass
-        // is bound by its own instruction stream (80 thread instructions per sample at 16 warps per SM), not by memory.
       }
       K2_TICK_T(K2_PRODUCER, 12, false)
     }
 
-    // =================== warp 0: publish this tile, resolve the pending tile ===================
+    // =================== warp 0: the state entering every warp of this tile ===================
     // Lane w < NW holds the total of warp w.  An inclusive Kogge-Stone scan with p^(32 C m) gives, shifted by
-    // one lane, the state entering every warp (up to the contribution of the state entering the tile);
-    // three dependent steps instead of an eight-step Horner chain.  Lane 0 resolves the look-back.
+    // one lane, the state entering every warp up to the contribution of the state S entering the TILE, which is
+    // added with the tabulated powers: S = the zi-scaled state behind the odd extension at a segment's first tile,
+    // else the state at the end of the tile this block worked on last (s_chain: the block walks a run of the
+    // segment in order, warm-up tiles first).
     if (warp == 0) {
       const double* PWP = s_tab + K2_TAB_PWP;
       if (filt) {
@@ -544,7 +557,7 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
           for (int i = 0; i < 4; ++i) I[i] = s_Wb[(it & 1) * 4 * K2_NW + 4 * lane + i];
         }
 #pragma unroll
-        for (int kk = 0; kk < 3; ++kk) {
+        for (int kk = 0; (1 << kk) < K2_NW; ++kk) {
           const int dd = 1 << kk;
           double o[4];
 #pragma unroll
@@ -558,84 +571,27 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
           const double up = __shfl_up_sync(AEW_FULL, I[i], 1);
           Xw[i] = lane == 0 ? 0.0 : up;
         }
+        // S: a segment's first tile starts behind the odd extension; the first tile a block takes up for a run
+        // (a warm-up tile) starts from zero; every other tile goes on where the tile before it ended
+        const double* Sp = d.k == 0 ? s_in + 4 * (it & 1) : s_chain;
+        const bool zero = d.k != 0 && (flags & K2_FRESH);
+        const double S0[4] = {zero ? 0.0 : Sp[0], zero ? 0.0 : Sp[1], zero ? 0.0 : Sp[2], zero ? 0.0 : Sp[3]};
+        __syncwarp();                                    // every lane has read s_chain
         if (lane < K2_NW) {
           double Z[4] = {I[0], I[1], I[2], I[3]};
-          if (d.k == 0) {                              // first tile of a segment: the entering state is known
-            const double S0[4] = {s_in[4 * (it & 1)], s_in[4 * (it & 1) + 1], s_in[4 * (it & 1) + 2], s_in[4 * (it & 1) + 3]};
-            cmul_acc(PWP + 4 * lane, S0, Xw);
-            if (lane == K2_NW - 1) cmul_acc(PWP + 4 * K2_NW, S0, Z);
-          }
+          cmul_acc(PWP + 4 * lane, S0, Xw);
           double* X = s_X + (it & 1) * 4 * K2_NW;
 #pragma unroll
           for (int i = 0; i < 4; ++i) X[4 * lane + i] = Xw[i];
-          if (lane == K2_NW - 1) {                     // publish the tile's end state
-            volatile double* pub = tstate + 4 * tile;
+          if (lane == K2_NW - 1) {                       // the state at the end of this tile
+            cmul_acc(PWP + 4 * K2_NW, S0, Z);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) pub[i] = Z[i];
+            for (int i = 0; i < 4; ++i) s_chain[i] = Z[i];
           }
         }
       }
     }
-    K2_TICK(14)  // (thread 0) prefixes stored, tile published
-    // =================== warp 2, at the same time: resolve the pending tile ===================
-    // (independent of the scan above: it combines the PREVIOUS iteration's prefixes with the look-back)
-    if (warp == K2_LOOKER / 32) {
-      const double* PWP = s_tab + K2_TAB_PWP;
-      if (have_prev) {
-        double S[4] = {0.0, 0.0, 0.0, 0.0};
-        if (lane == 0 && dp.k > 0) {
-          // S = sum_j (p^T)^j Q[tile_p-1-j], j < min(lookback, k)
-          const double* PT = s_tab + K2_TAB_PTILE;
-          const long long depth = dp.k < lookback ? dp.k : lookback;
-          // the first three predecessors were loaded at the top of the iteration (registers q0..q2, no
-          // dynamic indexing: a pointer into them would push them to local memory and stall the loads)
-#define K2_LOOKBACK_STEP(J, QR, WJ)                                                                          \
-          if ((J) < depth) {                                                                                    \
-            double Q[4];                                                                                        \
-            bool ok = QR[0] != K2_EMPTY && QR[1] != K2_EMPTY && QR[2] != K2_EMPTY && QR[3] != K2_EMPTY;         \
-            Q[0] = __longlong_as_double((long long)QR[0]); Q[1] = __longlong_as_double((long long)QR[1]);       \
-            Q[2] = __longlong_as_double((long long)QR[2]); Q[3] = __longlong_as_double((long long)QR[3]);       \
-            unsigned spins = 0;                                                                                 \
-            if (!ok && a.dbg) atomicAdd(a.dbg + 9, 1ull);                                                       \
-            if (a.dbg) atomicAdd(a.dbg + 10, 1ull);                                                              \
-            while (!ok) {                                                                                       \
-              ok = load_state(tstate + 4 * (tile_p - 1 - (J)), Q);                                              \
-              if (!ok) {                                                                                        \
-                __nanosleep(32);                                                                                \
-                if (++spins > (1u << 22)) { atomicOr((int*)(a.ws.hdr + H_STATUS), AEW_DEV_LOOKBACK_TIMEOUT); break; } \
-              }                                                                                                 \
-            }                                                                                                   \
-            cmul_acc(WJ, Q, S);                                                                                 \
-          }
-          // three independent products with tabulated powers 1, p^T, p^2T (no chain through a running power)
-          const double one[4] = {1.0, 0.0, 1.0, 0.0};
-          K2_LOOKBACK_STEP(0, q0, one)
-          K2_LOOKBACK_STEP(1, q1, PT)
-          K2_LOOKBACK_STEP(2, q2, s_pt2)
-          double Wm[4] = {s_pt2[0], s_pt2[1], s_pt2[2], s_pt2[3]};
-          for (long long j = 3; j < depth; ++j) {      // deeper look-backs (slowly decaying filters)
-            const unsigned long long none[4] = {K2_EMPTY, K2_EMPTY, K2_EMPTY, K2_EMPTY};
-            const double w0 = Wm[0] * PT[0] - Wm[1] * PT[1], w1 = Wm[0] * PT[1] + Wm[1] * PT[0];
-            const double w2 = Wm[2] * PT[2] - Wm[3] * PT[3], w3 = Wm[2] * PT[3] + Wm[3] * PT[2];
-            Wm[0] = w0; Wm[1] = w1; Wm[2] = w2; Wm[3] = w3;
-            K2_LOOKBACK_STEP(j, none, Wm)
-          }
-#undef K2_LOOKBACK_STEP
-        }
-        // state entering warp w = prefix kept from the tile's own scan + p^(32 C w) S
-#pragma unroll
-        for (int i = 0; i < 4; ++i) S[i] = __shfl_sync(AEW_FULL, S[i], 0);
-        if (lane < K2_NW) {
-          const double* X = s_X + ((it + 1) & 1) * 4 * K2_NW;
-          double t[4] = {X[4 * lane], X[4 * lane + 1], X[4 * lane + 2], X[4 * lane + 3]};
-          if (dp.k > 0) cmul_acc(PWP + 4 * lane, S, t);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) s_S[4 * lane + i] = t[i];
-        }
-      }
-    }
-    K2_TICK(3)   // publish / look-back / chains
-    K2_TICK_T(K2_LOOKER, 11, false)
+    K2_TICK(3)   // warp 0's serial section
     __syncthreads();
     K2_TICK(4)
 
@@ -652,7 +608,8 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) s[i] = __shfl_up_sync(AEW_FULL, Ep[i], 1);
       if (lane == 0) { s[0] = s[1] = s[2] = s[3] = 0.0; }
-      const double Sw[4] = {s_S[4 * warp], s_S[4 * warp + 1], s_S[4 * warp + 2], s_S[4 * warp + 3]};
+      const double* Xp = s_X + ((it + 1) & 1) * 4 * K2_NW;   // written by warp 0 one iteration ago
+      const double Sw[4] = {Xp[4 * warp], Xp[4 * warp + 1], Xp[4 * warp + 2], Xp[4 * warp + 3]};
       cmul_acc(s_tab + K2_TAB_PLANE + 4 * lane, Sw, s);
       // forward pass, last tile of a segment: state at the segment end -> right extension outputs
       if (!REV && dp.n - dp.t0 <= K2_T) {
@@ -697,9 +654,8 @@ __global__ void __launch_bounds__(K2_NT, 2) k2_pass(PassArgs a) {
     }
     K2_TICK(5)   // B half incl. its barrier and the store hand-off
     if (!live) break;
-    have_prev = filt;
+    have_prev = filt && !(flags & K2_WARM);            // a warm-up tile leaves its end state and nothing else
     dp = d;
-    tile_p = tile;
     sm_p = sm;
 #pragma unroll
     for (int i = 0; i < 4; ++i) Ep[i] = E[i];
@@ -830,10 +786,10 @@ __global__ void __launch_bounds__(K2W_NT) k2_exact_warp(PassArgs a) {
 // (the real initial state at a segment's last sample, from the odd extension), and stores the middle.  One launch
 // instead of two, 8 B read + 8 B written per sample instead of 32 (the halo re-reads come from L2), no dependency
 // between tiles.  The 1 Hz high-pass (|p| = 0.995, ~8,000 samples of memory) stays with k2_pass.
-#define K2F_NT 320                      // ten warps: warp 0 and warp 9 hold the two halos of an interior tile
+#define K2F_NT (K2_NT + 64)             // warp 0 and the last warp hold the two halos of an interior tile
 #define K2F_NW (K2F_NT / 32)
 #define K2F_H (32 * K2_C)               // 416
-#define K2F_R (K2F_NT * K2_C)           // 4160 = K2_T + 2 * K2F_H
+#define K2F_R (K2F_NT * K2_C)           // = K2_T + 2 * K2F_H
 
 // One pass over buf[0 .. K2F_R) in place: zero-state recursion per 13-sample chunk, scan of the chunk end states
 // over the warp and over the ten warps, outputs corrected with the zero-input response of the entering state.
@@ -1265,6 +1221,7 @@ extern "C" int aew_filtfilt_f64(const double* src, const double* mean, const dou
   a.src = src; a.mean = mean; a.sd = sd; a.dst = tmp; a.passthrough = out; a.tab = d_tab; a.ws = w;
   a.bulk_ok = ((((size_t)src | (size_t)out | (size_t)tmp) & 15) == 0) ? 1 : 0;
   a.dbg = nullptr;
+  a.run_tiles = 0;
   a.cf.d = h_tab[K2_TAB_D];
   a.cf.p1r = h_tab[K2_TAB_P + 0]; a.cf.p1i = h_tab[K2_TAB_P + 1]; a.cf.p2r = h_tab[K2_TAB_P + 2]; a.cf.p2i = h_tab[K2_TAB_P + 3];
   a.cf.g0 = h_tab[K2_TAB_GC + 0]; a.cf.g1 = h_tab[K2_TAB_GC + 1]; a.cf.g2 = h_tab[K2_TAB_GC + 2]; a.cf.g3 = h_tab[K2_TAB_GC + 3];
@@ -1329,15 +1286,29 @@ extern "C" int aew_filtfilt_f64(const double* src, const double* mean, const dou
     return (int)cudaGetLastError();
   }
   if (mode != 0) return AEW_ERR_ARG;
-  const size_t smem = (size_t)(K2_STAGES * K2_T + K2_TAB_LEN + 20 * K2_NW + 8) * sizeof(double);
+  const size_t smem = (size_t)(K2_STAGES * K2_T + K2_TAB_LEN + 16 * K2_NW + 8) * sizeof(double);
   // (per call: the attribute is per DEVICE)
   if (AEW_SET_MAX_SMEM(k2_pass<false>, smem) != 0 || AEW_SET_MAX_SMEM(k2_pass<true>, smem) != 0)
     return (int)cudaGetLastError();
-  if (cudaMemsetAsync(w.hdr + H_WORK_FWD, 0, 2 * sizeof(long long), st) != 0 ||
-      cudaMemsetAsync(w.tstate_fwd, 0xFF, (size_t)w.max_tiles * 4 * sizeof(double), st) != 0 ||
-      cudaMemsetAsync(w.tstate_bwd, 0xFF, (size_t)w.max_tiles * 4 * sizeof(double), st) != 0)
-    return (int)cudaGetLastError();
-  const long long cap = (long long)sm_count() * 2;
+  if (cudaMemsetAsync(w.hdr + H_WORK_FWD, 0, 2 * sizeof(long long), st) != 0) return (int)cudaGetLastError();
+  // tiles per run: ~213,000 samples.  The warm-up in front of a run (`lookback` tiles: ~10,000 samples of the 1 Hz
+  // high-pass) is then ~5 % more tiles without stores, and the 8,500 runs of a 1,000-case batch leave the last block
+  // to finish at most ~1 / 29 behind the others.  (The value is part of the result's definition below 1e-16: a run
+  // starts from a warm-up truncated at 1e-18.  AEW_K2_RUN is a measurement switch.)
+  {
+    const char* run_env = getenv("AEW_K2_RUN");
+    a.run_tiles = run_env ? atoi(run_env) : K2_RUN;
+    if (a.run_tiles < 1) a.run_tiles = 1;
+  }
+#ifndef AEW_EMUL
+  if (getenv("AEW_K2_OCC")) {                            // measurement aid: resident blocks per SM the launch gets
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k2_pass<false>, K2_NT, smem);
+    fprintf(stderr, "k2_pass: %d threads, %zu B dynamic shared memory, %d blocks per SM (planned %d)\n", K2_NT, smem, nb,
+            K2_BPS);
+  }
+#endif
+  const long long cap = (long long)sm_count() * K2_BPS;
   const long long grid = w.max_tiles < cap ? w.max_tiles : cap;
   AEW_LAUNCH(k2_pass<false>, (unsigned)grid, K2_NT, smem, st, a);
   PassArgs r = a;

@@ -3,9 +3,13 @@
 #pragma once
 
 #define K2_C 13                      // samples per thread chunk (odd: conflict-free stride in shared memory)
-#define K2_NT 256                    // threads per block
+#ifndef K2_NT
+#define K2_NT 128                    // threads per block (-DK2_NT=256 rebuilds round 1's geometry: 3,328-sample tiles,
+#endif                               //   two blocks per SM)
 #define K2_NW (K2_NT / 32)
-#define K2_T (K2_C * K2_NT)          // samples per tile = 3328 (26 KB)
+#define K2_T (K2_C * K2_NT)          // samples per tile = 1664 (13 KB)
+#define K2_RUN (212992 / K2_T)        // tiles of a segment one block works through in a row (k2_pass): 128 resp. 64
+#define K2_BPS (512 / K2_NT)         // resident blocks per SM: 512 threads at 128 registers fill the register file
 #define K2_STAGES 4                  // ring of tile buffers per block: loading / recursion / correction / storing
 #define K2_MAXPAD 15                 // filtfilt padlen for order 4
 

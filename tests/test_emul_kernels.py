@@ -139,6 +139,29 @@ def test_k2_tiled_scan_within_tolerance(golden):
     assert hdr[4] == 0
 
 
+def test_k2_runs_of_tiles_and_their_warm_ups(monkeypatch):
+    """k2_pass hands a block RUNS of a segment's tiles and starts a run behind a warm-up over the `lookback` tiles in
+    front of it.  With short runs (AEW_K2_RUN = 1, 3: every tile resp. every third starts from a warm-up, chunks of
+    the table that hold the tail of another block's run) the output stays within the tolerance, and a record's output
+    does not depend on what else is in the batch (runs are cut relative to the segment)."""
+    x = rp.zscore(ecg_synth.synth_case(3, 24000))
+    y = rp.zscore(ecg_synth.synth_case(4, 26000)); y[11000:11010] = np.nan; y[23000] = np.nan
+    z = np.random.default_rng(5).standard_normal(12)
+    recs = [x, y, z]
+    for run, st in (("1", ("low", 30, 4)), ("3", ("high", 1, 4))):
+        monkeypatch.setenv("AEW_K2_RUN", run)
+        if True:
+            outs, hdr = eh.filtfilt(recs, [st], mode=0)
+            assert hdr[4] == 0
+            for r, o in zip(recs, outs):
+                ref = rp.butterworth(r, st[0], st[1])
+                assert same(np.isnan(o), np.isnan(ref))
+                m = ~np.isnan(ref)
+                assert np.max(np.abs(o[m] - ref[m])) <= 1e-7
+            alone, _ = eh.filtfilt([y], [st], mode=0)
+            assert same(alone[0], outs[1])
+
+
 def test_k2_other_orders(golden):
     g = golden("filters")
     xs = g["short_x"]
