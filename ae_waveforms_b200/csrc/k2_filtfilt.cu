@@ -334,6 +334,8 @@ __device__ __forceinline__ long long next_tile(TileSeq& q, const long long* __re
   return q.next++;
 }
 
+#define K2_AHEAD 2                    // tiles the producer's copies run ahead of the tile being worked on
+
 template <bool REV>
 __global__ void __launch_bounds__(K2_NT, K2_BPS) k2_pass(PassArgs a) {
   long long tick_ = 0;
@@ -341,9 +343,9 @@ __global__ void __launch_bounds__(K2_NT, K2_BPS) k2_pass(PassArgs a) {
   AEW_DYN_SMEM(smem_raw);
   double* stage0 = (double*)smem_raw;                 // [K2_STAGES][K2_T] tile ring
   double* s_tab = stage0 + K2_STAGES * K2_T;          // [K2_TAB_LEN]
-  double* s_Wb = s_tab + K2_TAB_LEN;                  // [2][K2_NW][4] warp totals (double buffered)
-  double* s_in = s_Wb + 8 * K2_NW;                    // [2][4] state entering a segment's first tile
-  double* s_X = s_in + 8;                             // [2][K2_NW][4] state entering each warp of a tile
+  double* s_W = s_tab + K2_TAB_LEN;                   // [K2_NW][4] warp totals
+  double* s_in = s_W + 4 * K2_NW;                     // [4] state entering a segment's first tile
+  double* s_chain = s_in + 4;                         // [2][4] filter state at the end of the tile worked on last
   __shared__ unsigned long long s_bar[K2_STAGES];
   __shared__ long long s_tile[K2_STAGES];
   __shared__ int s_flags[K2_STAGES];                  // K2_WARM | K2_FRESH of the tile in the slot
@@ -352,7 +354,6 @@ __global__ void __launch_bounds__(K2_NT, K2_BPS) k2_pass(PassArgs a) {
   // dependent global round trips -- entry, then mean / sd of its record -- in front of the recursion).
   __shared__ long long s_desc[K2_STAGES][4];
   __shared__ double s_zs[K2_STAGES][4];               // mean, sd, 1 / sd of the tile's record (forward pass with z-score)
-  __shared__ double s_chain[4];                       // filter state at the end of the tile worked on last
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < K2_TAB_LEN; i += K2_NT) s_tab[i] = a.tab[i];
@@ -363,46 +364,44 @@ __global__ void __launch_bounds__(K2_NT, K2_BPS) k2_pass(PassArgs a) {
   const int pad = (int)s_tab[K2_TAB_PAD];
   const long long lookback = (long long)s_tab[K2_TAB_LOOKBACK];
   const long long R = a.run_tiles;
+  const bool zon = (!REV) && a.mean != nullptr;
   long long* work = a.ws.hdr + (REV ? H_WORK_BWD : H_WORK_FWD);
   long long n_tiles = a.ws.hdr[H_TILE_TOTAL];
   if (n_tiles > a.ws.max_tiles) n_tiles = a.ws.max_tiles;
 
-  // prologue: take the first tile and start its copy.  The producer thread keeps a small software pipeline so that
-  // the tile-table read is not waited for in the iteration that issues it: id1 / raw1 = tile it + 1 (table entry
-  // already loaded)
+  // The producer thread fills ring slot (it + K2_AHEAD) % K2_STAGES while tile `it` is worked on: table entry,
+  // z-score parameters, flags, and the bulk copy of the samples.  idn / rawn / flagsn = the tile it will place next
+  // (table entry loaded one iteration before it is used).
   TileSeq seq = {0, 0, 0, 0};
-  long long id1 = 0, raw1[4] = {0, 0, 0, 0};
-  int flags1 = 0;
-  if (tid == K2_PRODUCER) {
-    int f0;
-    const long long t = next_tile(seq, a.ws.tile_desc, work, n_tiles, R, lookback, &f0);
-    s_tile[0] = t;
-    s_flags[0] = f0;
-    if (t < n_tiles) {
-      long long rw[4];
-      for (int i = 0; i < 4; ++i) rw[i] = a.ws.tile_desc[4 * t + i];
-      const TileDesc d = describe_tile<REV>(rw, a.bulk_ok, pad);
-      if (d.bulk) bulk_load(stage0, a.src + d.gstart, K2_T * 8u, &s_bar[0]);
-      for (int i = 0; i < 4; ++i) s_desc[0][i] = rw[i];
-      const bool zon0 = (!REV) && a.mean != nullptr;
-      const double sd0 = zon0 ? a.sd[d.rec] : 1.0;
-      s_zs[0][0] = zon0 ? a.mean[d.rec] : 0.0; s_zs[0][1] = sd0; s_zs[0][2] = zon0 ? 1.0 / sd0 : 1.0;
-      id1 = next_tile(seq, a.ws.tile_desc, work, n_tiles, R, lookback, &flags1);
-    } else {
-      id1 = n_tiles;
+  long long idn = 0, rawn[4] = {0, 0, 0, 0};
+  int flagsn = 0;
+  auto place = [&](int slot, bool wait_store) {        // (producer thread only)
+    s_tile[slot] = idn;
+    s_flags[slot] = flagsn;
+    if (idn < n_tiles) {
+      const TileDesc dn = describe_tile<REV>(rawn, a.bulk_ok, pad);
+      if (dn.bulk) {
+        // the slot's previous occupant was handed to a bulk store K2_STAGES - K2_AHEAD iterations ago; one bulk
+        // group is committed per iteration, so "all but the latest group read" covers it
+        if (wait_store) bulk_store_wait_read(1);
+        bulk_load(stage0 + slot * K2_T, a.src + dn.gstart, K2_T * 8u, &s_bar[slot]);
+      }
+      for (int i = 0; i < 4; ++i) s_desc[slot][i] = rawn[i];
+      const double sdn = zon ? a.sd[dn.rec] : 1.0;
+      s_zs[slot][0] = zon ? a.mean[dn.rec] : 0.0; s_zs[slot][1] = sdn; s_zs[slot][2] = zon ? 1.0 / sdn : 1.0;
+      idn = next_tile(seq, a.ws.tile_desc, work, n_tiles, R, lookback, &flagsn);
+      if (idn < n_tiles)
+        for (int i = 0; i < 4; ++i) rawn[i] = a.ws.tile_desc[4 * idn + i];
     }
-    if (id1 < n_tiles)
-      for (int i = 0; i < 4; ++i) raw1[i] = a.ws.tile_desc[4 * id1 + i];
+  };
+  if (tid == K2_PRODUCER) {
+    idn = next_tile(seq, a.ws.tile_desc, work, n_tiles, R, lookback, &flagsn);
+    if (idn < n_tiles)
+      for (int i = 0; i < 4; ++i) rawn[i] = a.ws.tile_desc[4 * idn + i];
+    for (int s = 0; s < K2_AHEAD; ++s) place(s, false);
   }
   __syncthreads();
   unsigned parity_bits = 0;                          // bit s: phase parity of ring slot s's mbarrier
-
-  // the tile whose correction ("B" half) is still pending, and my chunk's end state for it
-  TileDesc dp;
-  dp.seg = -1;
-  bool have_prev = false;
-  double Ep[4] = {0.0, 0.0, 0.0, 0.0};
-  double* sm_p = stage0;
 
 #ifndef AEW_EMUL
   tick_ = clock64();
@@ -410,255 +409,192 @@ __global__ void __launch_bounds__(K2_NT, K2_BPS) k2_pass(PassArgs a) {
   for (int it = 0;; ++it) {
     const int st = it % K2_STAGES;
     const long long tile = s_tile[st];
-    const bool live = tile < n_tiles;
+    if (tile >= n_tiles) break;                        // (slots are filled in order: nothing is in flight behind it)
     const int flags = s_flags[st];
     K2_TICK(0)
 
-    // =================== A half: recursion and scan of the current tile ===================
-    TileDesc d;
-    d.seg = -1;
-    double E[4] = {0.0, 0.0, 0.0, 0.0};
+    // =================== recursion over the tile from a zero state, scan of the chunk end states ===================
+    long long rw[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rw[i] = s_desc[st][i];
+    const TileDesc d = describe_tile<REV>(rw, a.bulk_ok, pad);
+    const double mean = s_zs[st][0];
+    const double inv_sd = s_zs[st][2];
     double* sm = stage0 + st * K2_T;
-    bool filt = false;                                 // the tile is filtered (not a short segment copied through)
-    if (live) {
-      long long rw[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) rw[i] = s_desc[st][i];
-      d = describe_tile<REV>(rw, a.bulk_ok, pad);
-      const bool zon = (!REV) && a.mean != nullptr;
-      const double mean = s_zs[st][0];
-      const ExactDiv sd = make_exact_div(s_zs[st][1]);
-      const double inv_sd = s_zs[st][2];
-      if (d.n <= pad) {                                // filters.py:50-51: too short, copy through
-        if (!REV)
-          for (long long i = tid; i < d.n; i += K2_NT) a.passthrough[d.g0 + i] = zs(a.src[d.g0 + i], zon, mean, sd);
+    const bool filt = d.n > pad;                       // else filters.py:50-51: too short, copied through
+    const int dir = (REV && d.bulk) ? -1 : 1;
+    const int base = (REV && d.bulk) ? K2_T - 1 : 0;
+    double* mine = sm + base + dir * (tid * K2_C);
+    double E[4] = {0.0, 0.0, 0.0, 0.0};
+    double y[K2_C];
+    if (!filt) {
+      if (!REV) {
+        const ExactDiv sd = make_exact_div(s_zs[st][1]);
+        for (long long i = tid; i < d.n; i += K2_NT) a.passthrough[d.g0 + i] = zs(a.src[d.g0 + i], zon, mean, sd);
+      }
+    } else {
+      if (d.bulk) {
+        if (!mbar_wait(&s_bar[st], (parity_bits >> st) & 1u) && tid == 0)   // bytes of the bulk copy have landed
+          atomicOr((int*)(a.ws.hdr + H_STATUS), AEW_DEV_LOOKBACK_TIMEOUT);
+        parity_bits ^= 1u << st;
       } else {
-        filt = true;
-        const int dir = (REV && d.bulk) ? -1 : 1;
-        const int base = (REV && d.bulk) ? K2_T - 1 : 0;
-        if (d.bulk) {
-          if (!mbar_wait(&s_bar[st], (parity_bits >> st) & 1u) && tid == 0)   // bytes of the bulk copy have landed
-            atomicOr((int*)(a.ws.hdr + H_STATUS), AEW_DEV_LOOKBACK_TIMEOUT);
-          parity_bits ^= 1u << st;
+        if (tid == K2_PRODUCER) bulk_store_wait_read(0);   // the slot may still be read by an earlier bulk store
+        __syncthreads();
+        for (int j = tid; j < K2_T; j += K2_NT) {      // cooperative copy, zero padded
+          double v = 0.0;
+          if (j < d.cnt) {
+            const long long p = d.t0 + j;
+            v = REV ? a.src[d.g0 + d.n - 1 - p] : a.src[d.g0 + p];
+          }
+          sm[j] = v;
+        }
+        __syncthreads();
+      }
+      K2_TICK(6)   // tile data ready (mbarrier wait / cooperative copy)
+      // first tile of a segment: run the odd extension (padlen samples) from SciPy's zi-scaled state
+      if (d.k == 0 && tid == 0) {
+        double z[4];
+        if (!REV) {
+          const double* xs = a.src + d.g0;
+          const double x0 = zsf(xs[0], zon, mean, inv_sd);
+          modal_initial(s_tab, 2.0 * x0 - zsf(xs[pad], zon, mean, inv_sd), z);
+          for (int e = 0; e < pad; ++e) modal_step(cf, 2.0 * x0 - zsf(xs[pad - e], zon, mean, inv_sd), z);
         } else {
-          if (tid == K2_PRODUCER) bulk_store_wait_read(0);   // the slot may still be read by an earlier bulk store
-          __syncthreads();
-          for (int j = tid; j < K2_T; j += K2_NT) {    // cooperative copy, zero padded
-            double v = 0.0;
-            if (j < d.cnt) {
-              const long long p = d.t0 + j;
-              v = REV ? a.src[d.g0 + d.n - 1 - p] : a.src[d.g0 + p];
-            }
-            sm[j] = v;
-          }
-          __syncthreads();
+          const double* ve = a.ws.vext + 16ll * d.seg;   // forward outputs over the right extension
+          modal_initial(s_tab, ve[pad - 1], z);
+          for (int e = 0; e < pad; ++e) modal_step(cf, ve[pad - 1 - e], z);
         }
-        K2_TICK(6)   // tile data ready (mbarrier wait / cooperative copy)
-        // first tile of a segment: run the odd extension (padlen samples) from SciPy's zi-scaled state
-        if (d.k == 0 && tid == 0) {
-          double z[4];
-          if (!REV) {
-            // (read from global memory: the first padlen+1 samples may span chunks that other
-            // threads are already overwriting in place)
-            const double* xs = a.src + d.g0;
-            const double x0 = zsf(xs[0], zon, mean, inv_sd);
-            modal_initial(s_tab, 2.0 * x0 - zsf(xs[pad], zon, mean, inv_sd), z);
-            for (int e = 0; e < pad; ++e) modal_step(cf, 2.0 * x0 - zsf(xs[pad - e], zon, mean, inv_sd), z);
-          } else {
-            const double* ve = a.ws.vext + 16ll * d.seg;   // forward outputs over the right extension
-            modal_initial(s_tab, ve[pad - 1], z);
-            for (int e = 0; e < pad; ++e) modal_step(cf, ve[pad - 1 - e], z);
-          }
 #pragma unroll
-          for (int i = 0; i < 4; ++i) s_in[4 * (it & 1) + i] = z[i];
-        }
-        // phase 1: zero-state recursion over my chunk, outputs stored in place
-        double* mine = sm + base + dir * (tid * K2_C);
-        if (zon) {
-          if (d.cnt == K2_T) {                           // (forward: dir = +1)
+        for (int i = 0; i < 4; ++i) s_in[i] = z[i];
+      }
+      // phase 1: zero-state recursion over my chunk; the outputs wait in registers for their correction
+      if (zon) {
+        if (d.cnt == K2_T) {                             // (forward: dir = +1)
 #pragma unroll
-            for (int j = 0; j < K2_C; ++j) mine[j] = modal_step(cf, zsf(mine[j], true, mean, inv_sd), E);
-          } else {
-#pragma unroll
-            for (int j = 0; j < K2_C; ++j) {
-              const bool inside = tid * K2_C + j < d.cnt;   // zero padding stays zero under the z-score
-              mine[j] = modal_step(cf, inside ? zsf(mine[j], true, mean, inv_sd) : 0.0, E);
-            }
-          }
-        } else if (dir > 0) {                            // the offsets are compile-time constants in either branch
-#pragma unroll
-          for (int j = 0; j < K2_C; ++j) mine[j] = modal_step(cf, mine[j], E);
+          for (int j = 0; j < K2_C; ++j) y[j] = modal_step(cf, zsf(mine[j], true, mean, inv_sd), E);
         } else {
 #pragma unroll
-          for (int j = 0; j < K2_C; ++j) mine[-j] = modal_step(cf, mine[-j], E);
+          for (int j = 0; j < K2_C; ++j) {
+            const bool inside = tid * K2_C + j < d.cnt;  // zero padding stays zero under the z-score
+            y[j] = modal_step(cf, inside ? zsf(mine[j], true, mean, inv_sd) : 0.0, E);
+          }
         }
-        K2_TICK(7)   // phase 1 recursion
-        // phase 2a: warp scan of chunk end states (Kogge-Stone with p^(C*2^k))
+      } else if (dir > 0) {                              // the offsets are compile-time constants in either branch
 #pragma unroll
-        for (int kk = 0; kk < 5; ++kk) {
-          const int dd = 1 << kk;
-          double o[4];
+        for (int j = 0; j < K2_C; ++j) y[j] = modal_step(cf, mine[j], E);
+      } else {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) o[i] = __shfl_up_sync(AEW_FULL, E[i], dd);
-          if (lane >= dd) cmul_acc(a.cPK + 4 * kk, o, E);
-        }
-        if (lane == 31) {
+        for (int j = 0; j < K2_C; ++j) y[j] = modal_step(cf, mine[-j], E);
+      }
+      K2_TICK(7)   // phase 1 recursion
+      // phase 2: warp scan of chunk end states (Kogge-Stone with p^(C*2^k))
 #pragma unroll
-          for (int i = 0; i < 4; ++i) s_Wb[(it & 1) * 4 * K2_NW + 4 * warp + i] = E[i];
-        }
+      for (int kk = 0; kk < 5; ++kk) {
+        const int dd = 1 << kk;
+        double o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = __shfl_up_sync(AEW_FULL, E[i], dd);
+        if (lane >= dd) cmul_acc(a.cPK + 4 * kk, o, E);
+      }
+      if (lane == 31) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s_W[4 * warp + i] = E[i];
       }
     }
-    K2_TICK(1)   // A half (thread 0's own work)
+    K2_TICK(1)   // recursion + warp scan (thread 0's own work)
     __syncthreads();
-    K2_TICK(2)   // wait at the barrier after the A half
+    K2_TICK(2)   // wait at the barrier
     K2_TICK_T(K2_PRODUCER, 0, true)
 
-    // producer thread (warp 1): runs while warp 0 works through its serial section below.  (Issuing the next
-    // tile's copy at the TOP of the iteration instead was measured: the blocks wait less for tile data, 31 -> 21 % of
-    // their time, but the producer then sits ~2,000 cycles in bulk_store_wait_read -- the store of two iterations ago
-    // is still being read out of shared memory -- in front of its own A half: 28.0 against 26.3 ms per step.)
+    // producer thread: the tile K2_AHEAD iterations from now
     if (tid == K2_PRODUCER) {
-      if (live) {
-        // start the copy of the next tile into the next ring slot; the slot's previous occupant was
-        // handed to a bulk store two iterations ago (one bulk group is committed per iteration)
-        const int nst = (it + 1) % K2_STAGES;
-        s_tile[nst] = id1;
-        s_flags[nst] = flags1;
-        if (id1 < n_tiles) {
-          const TileDesc dn = describe_tile<REV>(raw1, a.bulk_ok, pad);
-          if (dn.bulk) {
-            bulk_store_wait_read(1);
-            bulk_load(stage0 + nst * K2_T, a.src + dn.gstart, K2_T * 8u, &s_bar[nst]);
-          }
-          for (int i = 0; i < 4; ++i) s_desc[nst][i] = raw1[i];
-          const bool zon1 = (!REV) && a.mean != nullptr;
-          const double sd1 = zon1 ? a.sd[dn.rec] : 1.0;     // (this thread has the time: the block is in its serial section)
-          s_zs[nst][0] = zon1 ? a.mean[dn.rec] : 0.0; s_zs[nst][1] = sd1; s_zs[nst][2] = zon1 ? 1.0 / sd1 : 1.0;
-          id1 = next_tile(seq, a.ws.tile_desc, work, n_tiles, R, lookback, &flags1);   // consumed next iteration
-          if (id1 < n_tiles)
-            for (int i = 0; i < 4; ++i) raw1[i] = a.ws.tile_desc[4 * id1 + i];
-        }
-      }
+      place((it + K2_AHEAD) % K2_STAGES, true);
       K2_TICK_T(K2_PRODUCER, 12, false)
     }
 
-    // =================== warp 0: the state entering every warp of this tile ===================
-    // Lane w < NW holds the total of warp w.  An inclusive Kogge-Stone scan with p^(32 C m) gives, shifted by
-    // one lane, the state entering every warp up to the contribution of the state S entering the TILE, which is
-    // added with the tabulated powers: S = the zi-scaled state behind the odd extension at a segment's first tile,
-    // else the state at the end of the tile this block worked on last (s_chain: the block walks a run of the
-    // segment in order, warm-up tiles first).
-    if (warp == 0) {
+    // =================== state entering my chunk, correction, store ===================
+    // Every warp adds up the state entering it for itself (K2_NW - 1 products at most): S = the state entering the
+    // TILE -- the zi-scaled state behind the odd extension at a segment's first tile, zero at the first tile a block
+    // takes up for a run (a warm-up tile), else the state at the end of the tile before (s_chain: the block walks a
+    // run of the segment in order, warm-up tiles first) -- times p^(32 C w), plus the totals of the warps before.
+    if (filt) {
       const double* PWP = s_tab + K2_TAB_PWP;
-      if (filt) {
-        double I[4] = {0.0, 0.0, 0.0, 0.0};
-        if (lane < K2_NW) {
+      const double* Sp = d.k == 0 ? s_in : s_chain + 4 * (it & 1);
+      const bool zero = d.k != 0 && (flags & K2_FRESH);
+      const double S0[4] = {zero ? 0.0 : Sp[0], zero ? 0.0 : Sp[1], zero ? 0.0 : Sp[2], zero ? 0.0 : Sp[3]};
+      double X[4] = {0.0, 0.0, 0.0, 0.0};
+      cmul_acc(PWP + 4 * warp, S0, X);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) I[i] = s_Wb[(it & 1) * 4 * K2_NW + 4 * lane + i];
+      for (int v = 0; v < K2_NW - 1; ++v) {
+        if (v < warp) {
+          const double Wv[4] = {s_W[4 * v], s_W[4 * v + 1], s_W[4 * v + 2], s_W[4 * v + 3]};
+          cmul_acc(PWP + 4 * (warp - 1 - v), Wv, X);
+        }
+      }
+      if (tid == 0) {                                    // the state at the end of this tile, for the next one
+        double Z[4] = {0.0, 0.0, 0.0, 0.0};
+        cmul_acc(PWP + 4 * K2_NW, S0, Z);
+#pragma unroll
+        for (int v = 0; v < K2_NW; ++v) {
+          const double Wv[4] = {s_W[4 * v], s_W[4 * v + 1], s_W[4 * v + 2], s_W[4 * v + 3]};
+          cmul_acc(PWP + 4 * (K2_NW - 1 - v), Wv, Z);
         }
 #pragma unroll
-        for (int kk = 0; (1 << kk) < K2_NW; ++kk) {
-          const int dd = 1 << kk;
-          double o[4];
+        for (int i = 0; i < 4; ++i) s_chain[4 * ((it + 1) & 1) + i] = Z[i];
+      }
+      if (!(flags & K2_WARM)) {                          // (a warm-up tile leaves its end state and nothing else)
+        // state entering my chunk = p^(C*lane) X + end state of the lane before me
+        double s[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) o[i] = __shfl_up_sync(AEW_FULL, I[i], dd);
-          if (lane >= dd && lane < K2_NW) cmul_acc(PWP + 4 * dd, o, I);
-        }
-        K2_TICK(13)  // (thread 0) warp totals loaded + Kogge-Stone scan
-        double Xw[4];                                  // exclusive scan = state entering warp `lane`
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const double up = __shfl_up_sync(AEW_FULL, I[i], 1);
-          Xw[i] = lane == 0 ? 0.0 : up;
-        }
-        // S: a segment's first tile starts behind the odd extension; the first tile a block takes up for a run
-        // (a warm-up tile) starts from zero; every other tile goes on where the tile before it ended
-        const double* Sp = d.k == 0 ? s_in + 4 * (it & 1) : s_chain;
-        const bool zero = d.k != 0 && (flags & K2_FRESH);
-        const double S0[4] = {zero ? 0.0 : Sp[0], zero ? 0.0 : Sp[1], zero ? 0.0 : Sp[2], zero ? 0.0 : Sp[3]};
-        __syncwarp();                                    // every lane has read s_chain
-        if (lane < K2_NW) {
-          double Z[4] = {I[0], I[1], I[2], I[3]};
-          cmul_acc(PWP + 4 * lane, S0, Xw);
-          double* X = s_X + (it & 1) * 4 * K2_NW;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) X[4 * lane + i] = Xw[i];
-          if (lane == K2_NW - 1) {                       // the state at the end of this tile
-            cmul_acc(PWP + 4 * K2_NW, S0, Z);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) s_chain[i] = Z[i];
+        for (int i = 0; i < 4; ++i) s[i] = __shfl_up_sync(AEW_FULL, E[i], 1);
+        if (lane == 0) { s[0] = s[1] = s[2] = s[3] = 0.0; }
+        cmul_acc(s_tab + K2_TAB_PLANE + 4 * lane, X, s);
+        // forward pass, last tile of a segment: state at the segment end -> right extension outputs
+        if (!REV && d.n - d.t0 <= K2_T) {
+          const int tl = (d.cnt - 1) / K2_C;             // thread holding the last valid sample
+          if (tid == tl) {
+            const int c = d.cnt - tl * K2_C;             // valid samples in its chunk, 1..C
+            double z[4] = {s[0], s[1], s[2], s[3]};
+            const double* xs = a.src + d.g0 + d.t0 + (long long)tl * K2_C;
+            for (int j = 0; j < c; ++j) modal_step(cf, zsf(xs[j], zon, mean, inv_sd), z);
+            const double* xe = a.src + d.g0 + d.n - 1;   // last sample of the segment
+            const double xl = zsf(xe[0], zon, mean, inv_sd);
+            double* ve = a.ws.vext + 16ll * d.seg;
+            for (int m = 0; m < pad; ++m) ve[m] = modal_step(cf, 2.0 * xl - zsf(xe[-1 - m], zon, mean, inv_sd), z);
           }
+        }
+        // phase 3: add the zero-input response of the entering state, outputs to the tile buffer
+        const double* G = a.cG;
+        if (dir > 0) {
+#pragma unroll
+          for (int j = 0; j < K2_C; ++j)
+            mine[j] = fma(G[4 * j + 3], s[3], fma(G[4 * j + 2], s[2], fma(G[4 * j + 1], s[1], fma(G[4 * j], s[0], y[j]))));
+        } else {
+#pragma unroll
+          for (int j = 0; j < K2_C; ++j)
+            mine[-j] = fma(G[4 * j + 3], s[3], fma(G[4 * j + 2], s[2], fma(G[4 * j + 1], s[1], fma(G[4 * j], s[0], y[j]))));
         }
       }
     }
-    K2_TICK(3)   // warp 0's serial section
+    K2_TICK(3)   // entering states + correction
+    const bool out = filt && !(flags & K2_WARM);
+    if (out && d.bulk) fence_async_smem();               // my shared-memory writes -> visible to the bulk engine
     __syncthreads();
     K2_TICK(4)
-
-    // =================== B half: correct and store the pending tile ===================
-    if (have_prev) {
-      const bool zon = (!REV) && a.mean != nullptr;
-      const int stp = (it + K2_STAGES - 1) % K2_STAGES;   // the pending tile's ring slot
-      const double mean = s_zs[stp][0];
-      const double inv_sd = s_zs[stp][2];
-      const int dir = (REV && dp.bulk) ? -1 : 1;
-      const int base = (REV && dp.bulk) ? K2_T - 1 : 0;
-      // state entering my chunk = p^(C*lane) S_warp + end state of the lane before me
-      double s[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) s[i] = __shfl_up_sync(AEW_FULL, Ep[i], 1);
-      if (lane == 0) { s[0] = s[1] = s[2] = s[3] = 0.0; }
-      const double* Xp = s_X + ((it + 1) & 1) * 4 * K2_NW;   // written by warp 0 one iteration ago
-      const double Sw[4] = {Xp[4 * warp], Xp[4 * warp + 1], Xp[4 * warp + 2], Xp[4 * warp + 3]};
-      cmul_acc(s_tab + K2_TAB_PLANE + 4 * lane, Sw, s);
-      // forward pass, last tile of a segment: state at the segment end -> right extension outputs
-      if (!REV && dp.n - dp.t0 <= K2_T) {
-        const int tl = (dp.cnt - 1) / K2_C;            // thread holding the last valid sample
-        if (tid == tl) {
-          const int c = dp.cnt - tl * K2_C;            // valid samples in its chunk, 1..C
-          double z[4] = {s[0], s[1], s[2], s[3]};
-          const double* xs = a.src + dp.g0 + dp.t0 + (long long)tl * K2_C;
-          for (int j = 0; j < c; ++j) modal_step(cf, zsf(xs[j], zon, mean, inv_sd), z);
-          const double* xe = a.src + dp.g0 + dp.n - 1; // last sample of the segment
-          const double xl = zsf(xe[0], zon, mean, inv_sd);
-          double* ve = a.ws.vext + 16ll * dp.seg;
-          for (int m = 0; m < pad; ++m) ve[m] = modal_step(cf, 2.0 * xl - zsf(xe[-1 - m], zon, mean, inv_sd), z);
-        }
-      }
-      // phase 3: add the zero-input response of the entering state
-      double* mine = sm_p + base + dir * (tid * K2_C);
-      const double* G = a.cG;
-      if (dir > 0) {
-#pragma unroll
-        for (int j = 0; j < K2_C; ++j)
-          mine[j] = fma(G[4 * j + 3], s[3], fma(G[4 * j + 2], s[2], fma(G[4 * j + 1], s[1], fma(G[4 * j], s[0], mine[j]))));
+    if (out) {
+      if (d.bulk) {
+        if (tid == K2_PRODUCER) bulk_store(a.dst + d.gstart, sm, K2_T * 8u);
       } else {
-#pragma unroll
-        for (int j = 0; j < K2_C; ++j)
-          mine[-j] = fma(G[4 * j + 3], s[3], fma(G[4 * j + 2], s[2], fma(G[4 * j + 1], s[1], fma(G[4 * j], s[0], mine[-j]))));
-      }
-      if (dp.bulk) {
-        fence_async_smem();                            // my shared-memory writes -> visible to the bulk engine
-        __syncthreads();
-        if (tid == K2_PRODUCER) bulk_store(a.dst + dp.gstart, sm_p, K2_T * 8u);
-      } else {
-        __syncthreads();
-        for (int j = tid; j < dp.cnt; j += K2_NT) {
-          const long long p = dp.t0 + j;
-          a.dst[REV ? (dp.g0 + dp.n - 1 - p) : (dp.g0 + p)] = sm_p[j];
+        for (int j = tid; j < d.cnt; j += K2_NT) {
+          const long long p = d.t0 + j;
+          a.dst[REV ? (d.g0 + d.n - 1 - p) : (d.g0 + p)] = sm[j];
         }
         if (tid == K2_PRODUCER) bulk_commit_empty();
       }
     } else if (tid == K2_PRODUCER) {
-      bulk_commit_empty();                             // one bulk group per iteration keeps wait_group.read 1 exact
+      bulk_commit_empty();                               // one bulk group per iteration keeps wait_group.read 1 exact
     }
-    K2_TICK(5)   // B half incl. its barrier and the store hand-off
-    if (!live) break;
-    have_prev = filt && !(flags & K2_WARM);            // a warm-up tile leaves its end state and nothing else
-    dp = d;
-    sm_p = sm;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) Ep[i] = E[i];
+    K2_TICK(5)   // store hand-off
   }
   if (tid == K2_PRODUCER) bulk_store_wait_all();
 }
@@ -1286,7 +1222,7 @@ extern "C" int aew_filtfilt_f64(const double* src, const double* mean, const dou
     return (int)cudaGetLastError();
   }
   if (mode != 0) return AEW_ERR_ARG;
-  const size_t smem = (size_t)(K2_STAGES * K2_T + K2_TAB_LEN + 16 * K2_NW + 8) * sizeof(double);
+  const size_t smem = (size_t)(K2_STAGES * K2_T + K2_TAB_LEN + 4 * K2_NW + 12) * sizeof(double);
   // (per call: the attribute is per DEVICE)
   if (AEW_SET_MAX_SMEM(k2_pass<false>, smem) != 0 || AEW_SET_MAX_SMEM(k2_pass<true>, smem) != 0)
     return (int)cudaGetLastError();
