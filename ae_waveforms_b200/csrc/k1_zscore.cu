@@ -137,8 +137,16 @@ __device__ __forceinline__ double k1_leaf_sum8(const double* __restrict__ x, dou
   return k1_leaf_nan<PASS>(x, mean, off, size, g, cnt);
 }
 
+// the record block b belongs to.  Records of equal length -- the usual batch -- put it at b n_rec / n_blocks: two
+// independent loads confirm the guess; a binary search (log2 n_rec DEPENDENT loads in front of everything a block
+// does) only where they do not
 __device__ __forceinline__ long long find_record(const long long* __restrict__ start, long long n_rec,
-                                                 long long b) {
+                                                 long long b, long long n_blocks) {
+  if (n_blocks > 0) {                                 // (start[] has n_rec + 1 entries then)
+    long long g = b * n_rec / n_blocks;
+    if (g > n_rec - 1) g = n_rec - 1;
+    if (start[g] <= b && b < start[g + 1]) return g;
+  }
   long long lo = 0, hi = n_rec;  // start[lo] <= b < start[hi]
   while (hi - lo > 1) {
     const long long mid = (lo + hi) >> 1;
@@ -161,7 +169,7 @@ __global__ void __launch_bounds__(256) k1_leaf(const double* __restrict__ x, con
   const long long b = blockIdx.x;
   if (threadIdx.x == 0) {
     // the record, and the subtree of its NumPy tree that this block sums: walked once, not by every thread
-    const long long r0 = find_record(blk_start, n_rec, b);
+    const long long r0 = find_record(blk_start, n_rec, b, (long long)gridDim.x);
     const long long base0 = rec_beg[r0], n0 = rec_end[r0] - base0;
     const int depth = pw_depth(n0);
     const int sub0 = depth < 5 ? depth : 5;
@@ -241,48 +249,53 @@ __global__ void __launch_bounds__(256) k1_fast_leaf(const double* __restrict__ x
   __shared__ int s_redo;
   const long long b = blockIdx.x;
   if (threadIdx.x == 0) {
-    const long long r0 = find_record(blk_start, n_rec, b);
+    const long long r0 = find_record(blk_start, n_rec, b, (long long)gridDim.x);
     const long long base0 = rec_beg[r0], n0 = rec_end[r0] - base0;
     const int depth = pw_depth(n0);
     const int sub0 = depth < 5 ? depth : 5;
     long long o, sz;
     pw_node(n0, depth - sub0, (unsigned)(b - blk_start[r0]), o, sz);
     s_lo = base0 + o; s_n = sz;
-    double c = sz > 0 ? x[base0 + o] : 0.0;
-    if (isnan(c) && sz > 0) c = x[base0 + o + sz - 1];
-    if (isnan(c) && sz > 0) c = x[base0 + o + sz / 2];
-    s_c = isnan(c) ? 0.0 : c;
     s_redo = 0;
   }
   __syncthreads();
   const double* xb = x + s_lo;
   const int n = (int)s_n;
-  const double c = s_c;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double cntd = (double)n;
+  // a block's range is 32 leaves of at most 128 samples: 16 per thread, every load issued before the first use.  The
+  // shift is the block's first sample, i.e. thread 0's first value: it is handed round AFTER the loads have been
+  // issued (read by thread 0 beforehand it was one more DRAM round trip in front of them)
+  double v[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] = (threadIdx.x + 256 * k < n) ? __ldg(xb + threadIdx.x + 256 * k) : 0.0;
+  if (threadIdx.x == 0) {
+    double c0 = n > 0 ? v[0] : 0.0;
+    if (isnan(c0) && n > 0) c0 = xb[n - 1];
+    if (isnan(c0) && n > 0) c0 = xb[n / 2];
+    s_c = isnan(c0) ? 0.0 : c0;
+  }
+  __syncthreads();
+  const double c = s_c;
 #pragma unroll 1
   for (int attempt = 0; attempt < 2; ++attempt) {
     double s1a = 0.0, s1b = 0.0, s2a = 0.0, s2b = 0.0, na = 0.0;
     const bool aware = attempt == 1;
-    // a block's range is 32 leaves of at most 128 samples: 16 per thread, every load issued before the first use
-    // (a sample that is not there reads as the shift: d = 0)
+    // (a sample that is not there counts as the shift: d = 0)
     {
-      double v[16];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) v[k] = (threadIdx.x + 256 * k < n) ? __ldg(xb + threadIdx.x + 256 * k) : c;
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
         const bool there = threadIdx.x + 256 * k < n;
-        const bool ok = !aware || !isnan(v[k]);
+        const bool ok = there && (!aware || !isnan(v[k]));
         const double d = ok ? v[k] - c : 0.0;
         if (aware) na += (ok && there) ? 1.0 : 0.0;
         if (k & 1) { s1b += d; s2b = __fma_rn(d, d, s2b); } else { s1a += d; s2a = __fma_rn(d, d, s2a); }
       }
     }
     for (int i = threadIdx.x + 16 * 256; i < n; i += 256) {   // (never, with the plan of aew_zscore_plan)
-      const double v = __ldg(xb + i);
-      const bool ok = !aware || !isnan(v);
-      const double d = ok ? v - c : 0.0;
+      const double vi = __ldg(xb + i);
+      const bool ok = !aware || !isnan(vi);
+      const double d = ok ? vi - c : 0.0;
       if (aware) na += ok ? 1.0 : 0.0;
       s1a += d; s2a = __fma_rn(d, d, s2a);
     }
@@ -359,7 +372,7 @@ __global__ void __launch_bounds__(256) k1_apply(const double* __restrict__ x, co
   const long long per_thread = 4;
   long long i = lo + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * per_thread;
   if (i >= hi) return;
-  long long r = find_record(rec_beg, n_rec, i);
+  long long r = find_record(rec_beg, n_rec, i, 0);
   for (int k = 0; k < per_thread && i < hi; ++k, ++i) {
     while (r + 1 < n_rec && i >= rec_beg[r + 1]) ++r;
     out[i] = (i >= rec_beg[r] && i < rec_end[r]) ? __ddiv_rn(__dsub_rn(x[i], mean[r]), sd[r])

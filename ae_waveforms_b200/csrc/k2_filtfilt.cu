@@ -1227,10 +1227,11 @@ extern "C" int aew_filtfilt_f64(const double* src, const double* mean, const dou
   if (AEW_SET_MAX_SMEM(k2_pass<false>, smem) != 0 || AEW_SET_MAX_SMEM(k2_pass<true>, smem) != 0)
     return (int)cudaGetLastError();
   if (cudaMemsetAsync(w.hdr + H_WORK_FWD, 0, 2 * sizeof(long long), st) != 0) return (int)cudaGetLastError();
-  // tiles per run: ~213,000 samples.  The warm-up in front of a run (`lookback` tiles: ~10,000 samples of the 1 Hz
-  // high-pass) is then ~5 % more tiles without stores, and the 8,500 runs of a 1,000-case batch leave the last block
-  // to finish at most ~1 / 29 behind the others.  (The value is part of the result's definition below 1e-16: a run
-  // starts from a warm-up truncated at 1e-18.  AEW_K2_RUN is a measurement switch.)
+  // tiles per run: ~106,000 samples.  The warm-up in front of a run (`lookback` tiles: ~10,000 samples of the 1 Hz
+  // high-pass) is then ~9 % more tiles without stores; measured on 1,000 one-hour cases the filter stage takes the
+  // same time with runs of 64, 128 and 256 tiles and 4 % longer with 32, and shorter runs keep more blocks busy on
+  // small batches (a single one-hour record is 17 runs).  (The value is part of the result's definition below
+  // 1e-16: a run starts from a warm-up truncated at 1e-18.  AEW_K2_RUN is a measurement switch.)
   {
     const char* run_env = getenv("AEW_K2_RUN");
     a.run_tiles = run_env ? atoi(run_env) : K2_RUN;

@@ -8,7 +8,7 @@
 #endif                               //   two blocks per SM)
 #define K2_NW (K2_NT / 32)
 #define K2_T (K2_C * K2_NT)          // samples per tile = 1664 (13 KB)
-#define K2_RUN (212992 / K2_T)        // tiles of a segment one block works through in a row (k2_pass): 128 resp. 64
+#define K2_RUN (106496 / K2_T)        // tiles of a segment one block works through in a row (k2_pass): 64 resp. 32
 #define K2_BPS (512 / K2_NT)         // resident blocks per SM: 512 threads at 128 registers fill the register file
 #define K2_STAGES 4                  // ring of tile buffers per block: loading / recursion / correction / storing
 #define K2_MAXPAD 15                 // filtfilt padlen for order 4

@@ -727,7 +727,8 @@ def run_gpu(args):
                           "two NumPy-order sweeps of the record (mean, then sd): 16 B/sample; one launch group per step",
                           launches_per_step=1),
             "k2_pass": kern("k2_pass", k2_launch_ms, 16.0 * total, "one direction of the 1 Hz high-pass filtfilt: 8 B "
-                            "read + 8 B written per sample; 2 launches per step", launches_per_step=2),
+                            "read + 8 B written per sample (the warm-up tiles in front of every run of 64 tiles re-read "
+                            "~9 % more, not counted); 2 launches per step", launches_per_step=2),
             ("k2_fused" if lp_fused else "k2_pass (low-pass)"): kern(
                 "k2_fused" if lp_fused else "k2_pass", k2_lp_ms / (1.0 if lp_fused else 2.0), 16.0 * total,
                 "the 30 Hz low-pass, forward + backward in ONE launch over tiles with a 416-sample halo: 8 B read + "
