@@ -239,6 +239,9 @@ __global__ void __launch_bounds__(256) k1_combine(const long long* __restrict__ 
 // shift of its own (its first sample: the sums of d = x - c and d^2 cancel nothing however far the record sits from
 // zero); k1_fast_combine merges the triples of a record in a fixed order (Chan et al.): deterministic, and within a
 // few ulp of np.nanmean / np.nanstd.  A NaN poisons the plain sums; only such a block repeats its range NaN-aware.
+// (Measured and not kept, profiles/run_r2d_k1bps.sh: five or six resident blocks per SM instead of the four that 62
+// registers allow -- __launch_bounds__(256, 5 / 6) caps the kernel at 48 / 40 registers, the 16 loads in flight per
+// thread spill, 5.0 / 5.1 ms per 1,000 one-hour cases against 3.6.)
 __global__ void __launch_bounds__(256) k1_fast_leaf(const double* __restrict__ x, const long long* __restrict__ rec_beg,
                                                     const long long* __restrict__ rec_end,
                                                     const long long* __restrict__ blk_start, long long n_rec,
