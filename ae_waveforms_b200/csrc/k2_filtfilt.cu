@@ -900,7 +900,9 @@ __global__ void __launch_bounds__(K2F_NT, 3) k2_fused(PassArgs a) {
 // again a lone in-order warp, is the slow one: 627 ms per pass against 310).
 #define K2E_T 32                        // samples per segment and round (one 256-byte row per segment)
 #define K2E_LD (K2E_T + 1)              // row stride in shared memory: lane l reads row l -> bank (l + t) mod 32
+#ifndef K2E_NP
 #define K2E_NP 1                        // (chain warp, mover warp) PAIRS per block.  One: with four pairs per block
+#endif
 #define K2E_NT (64 * K2E_NP)            // (one chain warp per SM sub-partition, 128 segments per SM instead of 32) a
                                         // pass took 460 ms instead of 313 and the calls next to it 73 ms instead of 70
 #define K2E_HOG (190 * 1024)            // dynamic shared memory the block asks for and never touches: no block of the

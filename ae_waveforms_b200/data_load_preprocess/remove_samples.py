@@ -26,10 +26,13 @@ def remove_samples(samples_wave_tracks, indices_samples, track_names, sampling_f
     samples = np.asarray(samples_wave_tracks)
     col = names.index("SNUADC/ECG_II")
     n_win, L = samples.shape[0], samples.shape[1]
+    # remove_samples.py:31-33 drops a window if ANY of its wave tracks holds a NaN: the tracks next to the ECG (ART, CVP)
+    # are looked through on the device as well
     nan_other = np.zeros(n_win, dtype=bool)
-    for k in range(samples.shape[2]):
-        if k != col:
-            nan_other |= np.isnan(samples[:, :, k]).any(axis=1)
+    others = [k for k in range(samples.shape[2]) if k != col]
+    if others and n_win:
+        rest = torch.from_numpy(np.ascontiguousarray(samples[:, :, others], dtype=np.float64)).cuda()
+        nan_other = torch.isnan(rest).any(dim=2).any(dim=1).cpu().numpy().astype(bool)
     win = np.ascontiguousarray(samples[:, :, col], dtype=np.float64)
     pre = Preprocessor(fs=sampling_frequency, sample_length=L / sampling_frequency, pvc_threshold=pvc_threshold,
                        sd_threshold=sd_threshold_ecg, screen_mode=SCREEN_MODE)

@@ -440,6 +440,8 @@ def run_gpu(args):
                              + (res["np_waves"], res["np_info"]))
         return res
 
+    LL_CALLS = int(os.environ.get("AEW_BENCH_LL_CALLS", "2"))   # (measurement switch)
+
     def run_steps(p, steps):
         """`steps` passes over the batch; a call is finished DEPTH calls late so that the sequential exact-mask
         pass of its 20-peak records (side stream) runs next to the following calls' kernels.  Everything,
@@ -452,7 +454,7 @@ def run_gpu(args):
             # the job's last two calls take the low-latency form of the sequential filter (one warp per record: half
             # the wait -- and the device falls idle behind them anyway): the run ends ~200 ms after its last kernels
             # instead of ~320 (profiles/exact_masks_steady.py)
-            q.append(p.run(batch, scratch=scratch, defer=True, low_latency=i >= steps - 2, lazy_hazards=True))
+            q.append(p.run(batch, scratch=scratch, defer=True, low_latency=i >= steps - LL_CALLS, lazy_hazards=True))
             while len(q) > DEPTH:
                 res = finish(p, q.pop(0))
         p.flush_hazards()                                         # the last call's sequential pass starts now

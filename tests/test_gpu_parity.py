@@ -273,6 +273,30 @@ def test_remove_samples_dropin(gpu, golden):
         sample_from_record(rec, ["SNUADC/PLETH"])
 
 
+def test_remove_samples_dropin_three_wave_tracks(gpu, golden):
+    """remove_samples.py:31-33: a window goes if ANY wave track (ECG_II, ART, CVP) holds a NaN -- the configured path
+    is single-lead, the reference's function is not."""
+    from ae_waveforms_b200.data_load_preprocess.remove_samples import remove_samples
+    g = golden("screen")
+    wins = g["windows"]
+    rng = np.random.default_rng(3)
+    # (the reference reads the ECG from column `wave_track_names.index(name)` = 0: ECG first, as sample_from_record
+    # delivers it for the configured track order)
+    three = np.stack([wins, rng.standard_normal(wins.shape), rng.standard_normal(wins.shape)], axis=2)
+    kept = [int(k) for k in g["kept_rows"]]
+    three[kept[0], 17, 1] = np.nan                       # ART gap in a window the ECG alone would keep
+    three[kept[-1], 9999, 2] = np.nan                    # CVP gap in another
+    names = ["SNUADC/ECG_II", "SNUADC/ART", "SNUADC/CVP"]
+    idx = (np.arange(len(wins)) + 1).reshape(-1, 1) * 10000
+    df = remove_samples(three.copy(), idx, names, 500, 150)
+    ref = rp.remove_samples(three.copy(), idx, names, 500, 150)
+    assert len(df) == len(ref) == len(kept) - 2
+    assert list(df.columns) == list(ref.columns)
+    for c in df.columns:
+        for u, v in zip(df[c], ref[c]):
+            assert same(u, v), c
+
+
 # ------------------------------------------------------------------------- whole path
 def test_pipeline_e2e_golden_and_oracle(gpu, golden):
     torch, B = gpu
