@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "csrc", "libaewave.so")
 
 ERRORS = {-1: "bad argument", -2: "workspace too small", -3: "unsupported parameter", -4: "no sm_100 CUDA device"}
 DEV_STATUS = {1: "more NaN-delimited segments than max_segments", 2: "more filter tiles than the workspace holds",
-              4: "filter look-back timed out", 8: "more than max_peaks R-peaks in a window",
+              4: "filter: a tile's bulk copy did not complete", 8: "more than max_peaks R-peaks in a window",
               16: "a fiducial index lies outside its window"}
 
 

@@ -22,7 +22,7 @@
 #define K2_TAB_ZI 10                 // zi[0..3]  scipy.signal.lfilter_zi
 #define K2_TAB_ORDER 14
 #define K2_TAB_PAD 15
-#define K2_TAB_LOOKBACK 16           // predecessor tiles whose end state still matters
+#define K2_TAB_LOOKBACK 16           // tiles in front of a run whose samples still matter: the run's warm-up
 #define K2_TAB_D 17                  // direct term b[0]
 #define K2_TAB_P 20                  // p1.re p1.im p2.re p2.im
 #define K2_TAB_GC 24                 // y += GC . s          (g.re, -g.im per section)

@@ -38,7 +38,7 @@ extern "C" {
 /* bits of the device status word */
 #define AEW_DEV_SEG_OVERFLOW 1
 #define AEW_DEV_TILE_OVERFLOW 2
-#define AEW_DEV_LOOKBACK_TIMEOUT 4
+#define AEW_DEV_LOOKBACK_TIMEOUT 4 /* filter: a tile's bulk copy never completed (the name dates from the look-back over published tile states) */
 #define AEW_DEV_RUN_OVERFLOW 8
 #define AEW_DEV_FID_RANGE 16 /* a fiducial index outside [0, L) was treated as missing */
 

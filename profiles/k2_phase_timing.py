@@ -18,6 +18,10 @@ for rep in range(3):
     pre.filter_records(flat,beg_h,end_h,d_beg,d_end,mean,sd,cnt,out=y,tmp=tmp)
     lib.aew_filt_timing_dump(ctypes.c_void_p(out.ctypes.data))
     tot=out[:9].sum()
-    names=["early look-back loads","warp scan","barrier after A","publish+lookback+chains","barrier 2","B half+store","wait tile data","phase 1 recursion","claim+describe+bulk issue"]
-    print(rep, {n: f"{100*float(v)/float(tot):.1f}%" for n,v in zip(names,out[:9])}, "cycles/iter/block", float(tot)/(n_cases*ns/3328*4), "look-back steps that had to wait:", int(out[9]), "of", int(out[10]), "| cycles/iter: look-back thread", float(out[11])/(n_cases*ns/3328*4), "producer thread", float(out[12])/(n_cases*ns/3328*4),
-          "| thread 0 inside the serial section: scan", float(out[13])/(n_cases*ns/3328*4), "store + publish", float(out[14])/(n_cases*ns/3328*4))
+    # slots of thread 0 in the run-based k2_pass (k2_filtfilt.cu, K2_TICK): 0 top of the iteration, 6 tile data ready
+    # (mbarrier), 7 zero-state recursion, 1 warp scan + totals, 2 first barrier, 3 entering state + correction,
+    # 4 second barrier, 5 store hand-off; 12 = the producer thread's work per iteration
+    names=["top of the iteration","warp scan + totals","barrier 1","entering state + correction","barrier 2","store hand-off","wait tile data","recursion","-"]
+    iters=n_cases*ns/1664*4*1.055                            # tiles x launches, + the warm-up tiles in front of the runs
+    print(rep, {n: f"{100*float(v)/float(tot):.1f}%" for n,v in zip(names,out[:9])}, "cycles/iter/block", float(tot)/iters,
+          "| producer thread, cycles/iter", float(out[12])/iters)

@@ -98,11 +98,15 @@ def test_butterworth_dropin_fast_mode(gpu, golden, monkeypatch):
 
 
 def test_filter_ragged_batch_long_records(gpu):
-    """Many tiles per segment (cross-tile look-back), NaN gaps, short islands, both filters."""
+    """Many tiles per segment (several runs with their warm-ups), NaN gaps, short islands, both filters."""
     torch, B = gpu
     recs = [ecg_synth.synth_case(40, 1800000), ecg_synth.synth_case(41, 250000, nan_gaps=3),
             ecg_synth.synth_case(42, 8448 * 3), ecg_synth.synth_case(43, 8449), ecg_synth.synth_case(44, 8447),
             ecg_synth.synth_case(45, 16), ecg_synth.synth_case(46, 15), ecg_synth.synth_case(47, 33000, nan_gaps=2)]
+    # lengths around the tile (1,664 samples) and the run (64 tiles = 106,496 samples) of the tiled pass: a run's last
+    # tile one sample long, a run that is all warm-up but one tile, segments ending exactly on either boundary
+    recs += [ecg_synth.synth_case(50 + i, n) for i, n in enumerate((1663, 1664, 1665, 3 * 1664, 106495, 106496, 106497,
+                                                                    106496 + 1664, 2 * 106496 + 1, 3 * 106496))]
     batch = B.RecordBatch.from_host(recs)
     for mode in ("fast", "exact"):
         pre = B.Preprocessor(filter_mode=mode)
