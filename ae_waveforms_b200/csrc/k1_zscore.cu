@@ -239,6 +239,11 @@ __global__ void __launch_bounds__(256) k1_combine(const long long* __restrict__ 
 // shift of its own (its first sample: the sums of d = x - c and d^2 cancel nothing however far the record sits from
 // zero); k1_fast_combine merges the triples of a record in a fixed order (Chan et al.): deterministic, and within a
 // few ulp of np.nanmean / np.nanstd.  A NaN poisons the plain sums; only such a block repeats its range NaN-aware.
+// (Measured and not kept, profiles/run_r2d_k1s.sh: PERSISTENT blocks that reduce unit i out of one shared-memory
+// buffer while 8-byte cp.async copies of unit i + 1 fill another and a ninth warp looks up the range of unit i + 2 --
+// the same bits in `nodes`, but 4.35 ms per 1,000 one-hour cases against 3.63: three blocks x one 28 KB unit in
+// flight per SM is less than the 16 loads per thread x 1,024 threads this kernel keeps in its REGISTERS, and a
+// block's iteration cannot be shorter than the loaded memory latency.)
 // (Measured and not kept, profiles/run_r2d_k1bps.sh: five or six resident blocks per SM instead of the four that 62
 // registers allow -- __launch_bounds__(256, 5 / 6) caps the kernel at 48 / 40 registers, the 16 loads in flight per
 // thread spill, 5.0 / 5.1 ms per 1,000 one-hour cases against 3.6.)
