@@ -716,8 +716,8 @@ __global__ void __launch_bounds__(K2W_NT) k2_exact_warp(PassArgs a) {
 
 // ------------------------------------------------------------ forward + backward in one launch
 // A filter whose memory is short (the 30 Hz low-pass: |p| <= 0.868, a state error is below 1e-18 after 300
-// samples) needs neither published tile states nor a look-back: a block takes a 3,328-sample tile TOGETHER with a
-// halo of 416 samples on either side, runs the forward pass over the 4,160 samples from a zero state (the real
+// samples) needs no state from outside a tile's neighbourhood: a block takes a tile (K2_T samples) TOGETHER with a
+// halo of 416 samples on either side, runs the forward pass over the K2_T + 832 samples from a zero state (the real
 // initial state at a segment's first sample), reverses them in shared memory, runs the backward pass the same way
 // (the real initial state at a segment's last sample, from the odd extension), and stores the middle.  One launch
 // instead of two, 8 B read + 8 B written per sample instead of 32 (the halo re-reads come from L2), no dependency
