@@ -172,14 +172,6 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_seg_find(const double* __restr
 // s = (u1.re, u1.im, u2.re, u2.im);  u' = p u + x;  y = d x + GC . s   (k2_layout.h)
 struct Modal { double d, p1r, p1i, p2r, p2i, g0, g1, g2, g3; };
 
-__device__ __forceinline__ Modal load_modal(const double* tab) {
-  Modal c;
-  c.d = tab[K2_TAB_D];
-  c.p1r = tab[K2_TAB_P + 0]; c.p1i = tab[K2_TAB_P + 1]; c.p2r = tab[K2_TAB_P + 2]; c.p2i = tab[K2_TAB_P + 3];
-  c.g0 = tab[K2_TAB_GC + 0]; c.g1 = tab[K2_TAB_GC + 1]; c.g2 = tab[K2_TAB_GC + 2]; c.g3 = tab[K2_TAB_GC + 3];
-  return c;
-}
-
 // one sample (fast path: FMA allowed, results within 1e-6 relative of SciPy's)
 __device__ __forceinline__ double modal_step(const Modal& c, double x, double s[4]) {
   const double y = fma(c.g3, s[3], fma(c.g2, s[2], fma(c.g1, s[1], fma(c.g0, s[0], c.d * x))));
