@@ -421,8 +421,13 @@ def run_gpu(args):
 
     in_flight = []                                                # the previous step's rows, still crossing NVLink
 
-    def drain():
-        while in_flight:
+    # GATHER_SLACK (measurement switch): rows of up to GATHER_SLACK + 1 steps may still be crossing NVLink.  0 = a
+    # step's transfer is waited for when the next step's rows are ready to go.  Measured with 2 (profiles/README.md):
+    # two ranks 65.3 ms per step without the exact-mask pass against 45.9 with 0 -- not kept.
+    GATHER_SLACK = int(os.environ.get("AEW_BENCH_GATHER_SLACK", 0))
+
+    def drain(keep=0):
+        while len(in_flight) > keep:
             parts, reqs = in_flight.pop(0)[:2]
             for req in reqs:
                 req.wait()
@@ -435,7 +440,7 @@ def run_gpu(args):
             # the final arrays live on one rank (data_create_arrays.py:56-58): every rank sends its rows to rank 0,
             # point to point and unpadded; the transfer is only STARTED here and waited for when the next step's rows
             # are ready to go, so that it runs under that step's kernels
-            drain()
+            drain(GATHER_SLACK)
             in_flight.append(awd.gather_rows_to([res["np_waves"], res["np_info"]], dst=0, async_op=True)
                              + (res["np_waves"], res["np_info"]))
         return res
