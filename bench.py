@@ -401,6 +401,15 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # The rows of a step go to rank 0 by NCCL send / receive UNDER the next step's kernels.  NCCL's point-to-point
+        # kernels take a block per channel and peer and spin until the peer's data comes; with its default channel
+        # count the receive of rank 0 keeps a good part of the SMs from the path's kernels while it waits for the
+        # slowest of its peers (four ranks: 57.9 ms per step where one rank takes 45.8, the stages themselves
+        # unchanged: the reading of that number, not verified -- the round's GPU budget ended).  Two channels per peer
+        # move a step's ~0.2 GB per rank in a few ms, a tenth of the step they hide under; measured on two ranks the
+        # setting is neutral (47.8 / 90.0 ms per step without / with the exact-mask pass against 45.9 / 99.5, end to
+        # end 12.0 against 12.1 Gsamples/s).  (An explicit NCCL_MAX_P2P_NCHANNELS in the environment wins.)
+        os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "2")
         dist.init_process_group("nccl", device_id=dev)
 
     n_cases, n_samp = N_CASES, CASE_SAMPLES
