@@ -162,6 +162,25 @@ def test_k2_runs_of_tiles_and_their_warm_ups(monkeypatch):
             assert same(alone[0], outs[1])
 
 
+def test_k2_runs_across_many_short_segments(monkeypatch):
+    """Chunks of the tile table that hold several segments, runs that end at a segment's end or reach into the next
+    chunk, tiles of 1 .. 1,665 samples (AEW_K2_RUN = 2), NaN gaps: every sample comes out, within the tolerance."""
+    rng = np.random.default_rng(21)
+    lens = list(rng.integers(5, 7000, 24)) + [1664, 1663, 1665, 3328, 3329, 4992, 16, 15, 1]
+    recs = [rng.standard_normal(int(n)) for n in lens]
+    big = int(np.argmax(lens))
+    recs[big][lens[big] // 3:lens[big] // 3 + 7] = np.nan
+    recs[big][lens[big] // 2] = np.nan
+    monkeypatch.setenv("AEW_K2_RUN", "2")
+    outs, hdr = eh.filtfilt(recs, [("high", 1, 4)], mode=0)
+    assert hdr[4] == 0
+    for r, o in zip(recs, outs):
+        ref = rp.butterworth(r, "high", 1)
+        assert same(np.isnan(o), np.isnan(ref))
+        m = ~np.isnan(ref)
+        assert not m.any() or np.max(np.abs(o[m] - ref[m])) <= 1e-7
+
+
 def test_k2_other_orders(golden):
     g = golden("filters")
     xs = g["short_x"]
